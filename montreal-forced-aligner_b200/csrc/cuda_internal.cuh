@@ -1,0 +1,116 @@
+// cuda_internal.cuh -- engine / model structures for the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e__ = (x);                                                                            \
+    if (e__ != cudaSuccess) return mfa::set_error(MFA_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define MFA_TRY(x)            \
+  do {                        \
+    int r__ = (x);            \
+    if (r__ != MFA_OK) return r__; \
+  } while (0)
+
+enum DevBuf {
+  DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
+  DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
+  DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_N
+};
+enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
+
+struct mfa_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  // K2 timing: event pairs recorded around each K2 launch of the current API call
+  std::vector<cudaEvent_t> gmm_ev;
+  int gmm_ev_used = 0;
+  int64_t gmm_rows = 0;
+  void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; }
+  int gmm_timing_begin();
+  int gmm_timing_end(int64_t rows);
+  struct Buf { void *p = nullptr; size_t cap = 0; };
+  Buf dev[DB_N];
+  Buf pin[PB_N];
+  // grow-only device buffer; contents are NOT preserved on growth
+  int get(int id, size_t bytes, void **out);
+  int get_pinned(int id, size_t bytes, void **out);
+  template <typename T> int getT(int id, size_t n, T **out) { void *p; int r = get(id, n * sizeof(T), &p); *out = (T *)p; return r; }
+  // upload a small host array into a device buffer slot
+  template <typename T> int upload(int id, const T *h, size_t n, T **out) {
+    int r = getT<T>(id, n ? n : 1, out);
+    if (r) return r;
+    if (n) CUDA_TRY(cudaMemcpyAsync(*out, h, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return MFA_OK;
+  }
+};
+
+// Tiled acoustic model on the device.  Gaussians are regrouped into tiles of TILE_N rows that never split a pdf
+// (padding rows have gconst = -1e30 and zero weights), so a tile's per-pdf log-sum-exp is local to the tile.
+#define MFA_TILE_N 128
+
+struct mfa_model {
+  mfa_engine *eng = nullptr;
+  int dim = 0, num_pdfs = 0, num_gauss = 0, num_tids = 0;
+  std::vector<int32_t> h_pdf_off, h_tid2pdf;
+  std::vector<float> h_gconsts, h_miv, h_iv;
+  int32_t *d_pdf_off = nullptr, *d_tid2pdf = nullptr;
+  float *d_gconsts = nullptr, *d_miv = nullptr, *d_iv = nullptr;  // natural layout (K4)
+  // tiled layout (K2)
+  int n_tiles = 0, kdim = 0;           // kdim = 2*dim
+  std::vector<int32_t> h_tile_pdf0;    // [n_tiles+1] first pdf of each tile
+  std::vector<int32_t> h_tile_seg;     // [n_tiles][TILE_N+1] column where local pdf k starts; padded with TILE_N..
+  int32_t *d_tile_pdf0 = nullptr, *d_tile_seg = nullptr;
+  float *d_W = nullptr;                // [n_tiles][kdim][TILE_N]  (k-major: coalesced / conflict-free tile loads)
+  float *d_G = nullptr;                // [n_tiles][TILE_N] gconsts (-1e30 padding)
+  int32_t *d_gauss_row = nullptr;      // [num_gauss] tile row (tile*TILE_N + col) of natural Gaussian m
+  // tensor-core operand images (gmm_tc.cu); built lazily
+  void *d_tc_w = nullptr;
+  size_t tc_w_bytes = 0;
+  float tc_scale_shift = 0.0f;
+  std::vector<float> h_tc_colscale;    // per-dimension power-of-two feature scaling folded into the weights
+  float *d_tc_colscale = nullptr;
+  bool tc_ready = false;
+  double *d_acc = nullptr;
+  int rebuild_tiles();
+  ~mfa_model();
+};
+
+namespace mfa {
+int upload_graphs(mfa_engine *e, mfa_graphs *g);
+// kernels' host launchers (device pointers only)
+int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, const int64_t *d_sample_off, int32_t n_utts,
+                const int64_t *d_frame_off, int64_t n_frames, float *d_out);
+int launch_cmvn_stats(mfa_engine *e, const float *d_feats, int dim, const int64_t *d_frame_off, const int32_t *h_utt2spk,
+                      int32_t n_utts, int32_t n_spk, double *d_stats);
+int launch_features(mfa_engine *e, const mfa_feat_opts *o, const float *d_in, const int64_t *d_frame_off, const int64_t *h_frame_off,
+                    const int64_t *d_row_off, const int32_t *d_utt2spk, int32_t n_utts, const double *d_cmvn_stats, float *d_out,
+                    int out_ld);
+int launch_gmm_ffma(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
+int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
+int launch_transpose(mfa_engine *e, const float *d_in, int64_t rows, int64_t cols, int64_t in_ld, float *d_out, int64_t out_ld);
+struct ViterbiArgs {
+  const mfa_graphs *g; int32_t utt0, n_utts;  // utterances [utt0, utt0+n_utts) of the graph batch
+  const float *d_llT; int64_t ld;              // pdf-major log-likelihoods [num_pdfs][ld]
+  const int64_t *d_col_off;                    // [n_utts] column of each utterance's frame 0 in d_llT (multiple of 8)
+  const int64_t *d_frame_off;                  // [n_utts+1] output frame offsets (relative to d_ali / d_per_frame)
+  const int64_t *h_frame_off; const int64_t *h_col_off;
+  int32_t *d_ali; float *d_per_frame; int32_t *d_words; const int64_t *d_word_off; int32_t *d_num_words;
+  float *d_total_like; int32_t *d_status;
+  mfa_align_opts opts;
+};
+int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
+int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
+}  // namespace mfa

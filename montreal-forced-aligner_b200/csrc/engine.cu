@@ -1,0 +1,252 @@
+// engine.cu -- engine lifetime, workspaces, acoustic-model upload/tiling, graph upload.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "cuda_internal.cuh"
+
+namespace mfa {
+static thread_local std::string g_last_error;
+int set_error(int code, const std::string &msg) { g_last_error = msg; return code; }
+}  // namespace mfa
+using namespace mfa;
+
+extern "C" const char *mfa_last_error(void) { return g_last_error.c_str(); }
+extern "C" int mfa_abi_version(void) { return 1; }
+
+int mfa_engine::get(int id, size_t bytes, void **out) {
+  Buf &b = dev[id];
+  if (bytes > b.cap) {
+    if (b.p) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;
+    cudaError_t err = cudaMalloc(&b.p, cap);
+    if (err != cudaSuccess) { b.p = nullptr; return set_error(MFA_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(err)); }
+    b.cap = cap;
+  }
+  *out = b.p;
+  return MFA_OK;
+}
+
+int mfa_engine::get_pinned(int id, size_t bytes, void **out) {
+  Buf &b = pin[id];
+  if (bytes > b.cap) {
+    if (b.p) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = bytes + bytes / 8 + 256;
+    CUDA_TRY(cudaMallocHost(&b.p, cap));
+    b.cap = cap;
+  }
+  *out = b.p;
+  return MFA_OK;
+}
+
+extern "C" int mfa_engine_create(int device, mfa_engine **out) {
+  if (!out) return set_error(MFA_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess || n == 0)
+    return set_error(MFA_ERR_CUDA, std::string("no usable CUDA device (this engine has no CPU fallback): ") + cudaGetErrorString(err));
+  if (device < 0 || device >= n) return set_error(MFA_ERR_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return set_error(MFA_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this build targets sm_100a (B200) only");
+  auto *e = new mfa_engine();
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  *out = e;
+  return MFA_OK;
+}
+
+extern "C" int mfa_engine_destroy(mfa_engine *e) {
+  if (!e) return MFA_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (auto &b : e->dev) if (b.p) cudaFree(b.p);
+  for (auto &b : e->pin) if (b.p) cudaFreeHost(b.p);
+  for (auto ev : e->gmm_ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return MFA_OK;
+}
+
+extern "C" int mfa_engine_sync(mfa_engine *e) {
+  if (!e) return set_error(MFA_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  CUDA_TRY(cudaGetLastError());
+  return MFA_OK;
+}
+extern "C" void *mfa_engine_stream(mfa_engine *e) { return e ? (void *)e->stream : nullptr; }
+extern "C" int mfa_engine_sm_count(mfa_engine *e) { return e ? e->sm_count : 0; }
+extern "C" int64_t mfa_engine_launch_count(mfa_engine *e) { return e ? e->launches : 0; }
+int mfa_engine::gmm_timing_begin() {
+  if ((size_t)gmm_ev_used + 2 > gmm_ev.size()) {
+    for (int k = 0; k < 2; k++) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); gmm_ev.push_back(ev); }
+  }
+  CUDA_TRY(cudaEventRecord(gmm_ev[gmm_ev_used], stream));
+  return MFA_OK;
+}
+int mfa_engine::gmm_timing_end(int64_t rows) {
+  CUDA_TRY(cudaEventRecord(gmm_ev[gmm_ev_used + 1], stream));
+  gmm_ev_used += 2; gmm_rows += rows;
+  return MFA_OK;
+}
+extern "C" int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_launches, int64_t *n_rows) {
+  if (!e) return set_error(MFA_ERR_INVALID, "null engine");
+  float tot = 0.0f;
+  for (int k = 0; k < e->gmm_ev_used; k += 2) {
+    CUDA_TRY(cudaEventSynchronize(e->gmm_ev[k + 1]));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->gmm_ev[k], e->gmm_ev[k + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (n_launches) *n_launches = e->gmm_ev_used / 2;
+  if (n_rows) *n_rows = e->gmm_rows;
+  return MFA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+mfa_model::~mfa_model() {
+  if (eng) cudaSetDevice(eng->device);
+  for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_tile_pdf0,
+                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc})
+    if (p) cudaFree(p);
+}
+
+int mfa_model::rebuild_tiles() {
+  // greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows
+  h_tile_pdf0.clear();
+  std::vector<int> tile_of_pdf(num_pdfs);
+  int cur = 0, t = -1;
+  for (int p = 0; p < num_pdfs; p++) {
+    int ng = h_pdf_off[p + 1] - h_pdf_off[p];
+    if (ng > MFA_TILE_N) return set_error(MFA_ERR_UNSUPPORTED, "pdf " + std::to_string(p) + " has " + std::to_string(ng) + " Gaussians (> " + std::to_string(MFA_TILE_N) + ")");
+    if (t < 0 || cur + ng > MFA_TILE_N) { t++; cur = 0; h_tile_pdf0.push_back(p); }
+    tile_of_pdf[p] = t; cur += ng;
+  }
+  n_tiles = t + 1;
+  h_tile_pdf0.push_back(num_pdfs);
+  kdim = 2 * dim;
+  std::vector<float> W((size_t)n_tiles * kdim * MFA_TILE_N, 0.0f), G((size_t)n_tiles * MFA_TILE_N, -1.0e30f);
+  h_tile_seg.assign((size_t)n_tiles * (MFA_TILE_N + 1), MFA_TILE_N);
+  std::vector<int32_t> grow(num_gauss);
+  for (int tl = 0; tl < n_tiles; tl++) {
+    int col = 0;
+    int32_t *seg = &h_tile_seg[(size_t)tl * (MFA_TILE_N + 1)];
+    for (int p = h_tile_pdf0[tl]; p < h_tile_pdf0[tl + 1]; p++) {
+      seg[p - h_tile_pdf0[tl]] = col;
+      for (int m = h_pdf_off[p]; m < h_pdf_off[p + 1]; m++, col++) {
+        G[(size_t)tl * MFA_TILE_N + col] = h_gconsts[m];
+        grow[m] = tl * MFA_TILE_N + col;
+        for (int d = 0; d < dim; d++) {
+          W[((size_t)tl * kdim + d) * MFA_TILE_N + col] = h_miv[(size_t)m * dim + d];
+          W[((size_t)tl * kdim + dim + d) * MFA_TILE_N + col] = -0.5f * h_iv[(size_t)m * dim + d];
+        }
+      }
+    }
+    seg[h_tile_pdf0[tl + 1] - h_tile_pdf0[tl]] = col;  // end of the last pdf; remaining entries stay TILE_N
+  }
+  cudaStream_t s = eng->stream;
+  auto up = [&](auto **dp, const auto &v) -> int {
+    using T = typename std::remove_reference<decltype(v[0])>::type;
+    if (*dp) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree((void *)*dp)); *dp = nullptr; }
+    CUDA_TRY(cudaMalloc((void **)dp, std::max<size_t>(1, v.size()) * sizeof(T)));
+    CUDA_TRY(cudaMemcpyAsync((void *)*dp, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MFA_OK;
+  };
+  MFA_TRY(up(&d_W, W)); MFA_TRY(up(&d_G, G)); MFA_TRY(up(&d_tile_pdf0, h_tile_pdf0)); MFA_TRY(up(&d_tile_seg, h_tile_seg));
+  MFA_TRY(up(&d_gauss_row, grow)); MFA_TRY(up(&d_gconsts, h_gconsts));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  tc_ready = false;
+  return MFA_OK;
+}
+
+extern "C" int mfa_model_create(mfa_engine *e, const mfa_model_desc *d, mfa_model **out) {
+  if (!e || !d || !out) return set_error(MFA_ERR_INVALID, "null argument");
+  if (d->dim <= 0 || d->dim > 64) return set_error(MFA_ERR_UNSUPPORTED, "feature dim must be in 1..64");
+  if (d->num_pdfs <= 0 || d->pdf_off[d->num_pdfs] != d->num_gauss) return set_error(MFA_ERR_INVALID, "pdf_off inconsistent with num_gauss");
+  CUDA_TRY(cudaSetDevice(e->device));
+  auto *m = new mfa_model();
+  m->eng = e; m->dim = d->dim; m->num_pdfs = d->num_pdfs; m->num_gauss = d->num_gauss; m->num_tids = d->num_tids;
+  m->h_pdf_off.assign(d->pdf_off, d->pdf_off + d->num_pdfs + 1);
+  m->h_gconsts.assign(d->gconsts, d->gconsts + d->num_gauss);
+  m->h_miv.assign(d->means_invvars, d->means_invvars + (size_t)d->num_gauss * d->dim);
+  m->h_iv.assign(d->inv_vars, d->inv_vars + (size_t)d->num_gauss * d->dim);
+  m->h_tid2pdf.assign(d->tid2pdf, d->tid2pdf + d->num_tids + 1);
+  for (int t = 1; t <= d->num_tids; t++)
+    if (m->h_tid2pdf[t] < 0 || m->h_tid2pdf[t] >= d->num_pdfs) { delete m; return set_error(MFA_ERR_INVALID, "tid2pdf out of range"); }
+  auto alloc_up = [&](auto **dp, const auto &v) -> int {
+    using T = typename std::remove_reference<decltype(v[0])>::type;
+    CUDA_TRY(cudaMalloc((void **)dp, std::max<size_t>(1, v.size()) * sizeof(T)));
+    CUDA_TRY(cudaMemcpyAsync((void *)*dp, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    return MFA_OK;
+  };
+  int r = alloc_up(&m->d_pdf_off, m->h_pdf_off);
+  if (!r) r = alloc_up(&m->d_tid2pdf, m->h_tid2pdf);
+  if (!r) r = alloc_up(&m->d_miv, m->h_miv);
+  if (!r) r = alloc_up(&m->d_iv, m->h_iv);
+  if (!r) r = m->rebuild_tiles();
+  if (r) { delete m; return r; }
+  *out = m;
+  return MFA_OK;
+}
+
+extern "C" int mfa_model_destroy(mfa_model *m) {
+  if (m && m->eng) cudaStreamSynchronize(m->eng->stream);
+  delete m;
+  return MFA_OK;
+}
+
+extern "C" int mfa_model_boost_pdfs(mfa_model *m, float factor, const int32_t *pdfs, int32_t n) {
+  if (!m || (n > 0 && !pdfs) || !(factor > 0.0f)) return set_error(MFA_ERR_INVALID, "bad argument");
+  float lb = logf(factor);
+  for (int i = 0; i < n; i++) {
+    int p = pdfs[i];
+    if (p < 0 || p >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "pdf id out of range");
+    for (int g = m->h_pdf_off[p]; g < m->h_pdf_off[p + 1]; g++) m->h_gconsts[g] += lb;
+  }
+  CUDA_TRY(cudaSetDevice(m->eng->device));
+  return m->rebuild_tiles();
+}
+
+// ------------------------------------------------------------------------------------------------ graphs
+mfa_graphs::~mfa_graphs() {
+  if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
+}
+
+namespace mfa {
+int upload_graphs(mfa_engine *e, mfa_graphs *g) {
+  if (g->d_blob && g->device == e->device) return MFA_OK;
+  if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
+  size_t A = g->a_src.size();
+  std::vector<uint32_t> pack(A);
+  for (size_t a = 0; a < A; a++) pack[a] = (uint32_t)(g->a_src[a] & 0xFFFF) | ((uint32_t)(g->a_lp[a] < 0 ? 0xFFFF : g->a_lp[a]) << 16);
+  for (int u = 0; u < g->n_utts; u++)
+    if (g->lp_off[u + 1] - g->lp_off[u] >= 0xFFFF) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph references >= 65535 pdfs");
+  struct Item { const void *h; size_t bytes; void **d; };
+  std::vector<Item> items = {
+      {g->st_off.data(), g->st_off.size() * 8, (void **)&g->d_st_off}, {g->arc_off.data(), g->arc_off.size() * 8, (void **)&g->d_arc_off},
+      {g->lp_off.data(), g->lp_off.size() * 8, (void **)&g->d_lp_off}, {g->inb_off.data(), g->inb_off.size() * 8, (void **)&g->d_inb_off},
+      {g->start.data(), g->start.size() * 4, (void **)&g->d_start}, {g->n_eps.data(), g->n_eps.size() * 4, (void **)&g->d_n_eps},
+      {g->in_begin.data(), g->in_begin.size() * 4, (void **)&g->d_in_begin}, {g->a_tid.data(), A * 4, (void **)&g->d_a_tid},
+      {g->a_olabel.data(), A * 4, (void **)&g->d_a_olabel}, {g->lp2pdf.data(), g->lp2pdf.size() * 4, (void **)&g->d_lp2pdf},
+      {pack.data(), A * 4, (void **)&g->d_a_pack}, {g->a_w.data(), A * 4, (void **)&g->d_a_w},
+      {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}};
+  size_t total = 0;
+  for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
+  CUDA_TRY(cudaMalloc(&g->d_blob, std::max<size_t>(total, 256)));
+  g->d_bytes = total; g->device = e->device;
+  size_t off = 0;
+  for (auto &it : items) {
+    *it.d = (char *)g->d_blob + off;
+    if (it.bytes) CUDA_TRY(cudaMemcpyAsync(*it.d, it.h, it.bytes, cudaMemcpyHostToDevice, e->stream));
+    off += (it.bytes + 255) / 256 * 256;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));  // `pack` is a local
+  return MFA_OK;
+}
+}  // namespace mfa
+
+extern "C" int mfa_graphs_destroy(mfa_graphs *g) { delete g; return MFA_OK; }

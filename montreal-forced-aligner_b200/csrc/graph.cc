@@ -1,0 +1,485 @@
+// graph.cc -- host-side training-graph compiler and decoder-ready graph packing.
+//
+// Replaces kalpy TrainingGraphCompiler.compile_fst / export_graphs (reference call sites:
+// montreal_forced_aligner/alignment/multiprocessing.py:537-571, online/alignment.py:77-96), i.e. Kaldi's
+// decoder/training-graph-compiler.cc pipeline  L o G -> context -> H -> self-loops(reorder=true),
+// WITHOUT OpenFst: for a linear transcript the composition has a closed form, so the graph is
+// constructed directly.  The weighted set of (transition-id sequence, word sequence) paths equals
+// Kaldi's; state numbering and weight placement along a path are not (no determinise/minimise pass),
+// see DESIGN.md.
+//
+// Structure:
+//   phone graph   : per word boundary i the lexicon states NS_i (no silence), P_i (before optional
+//                   silence), S_i (after silence); pronunciation chains between boundaries
+//                   (tests/data/dictionaries/expected/lexicon.text.fst documents the layout).
+//   instances     : (phone arc, left phone, right phone) -- triphone context (N=3,P=1) or the arc alone (N=1).
+//   HMM expansion : node (instance, hmm state j', source state j) carries the self-loop of j
+//                   (reorder=true: [forward tid, self-loop tid x (n-1)]); nodes with j' = final are the
+//                   junctions from which the successors' state-0 transitions leave.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mfa_b200.h"
+#include "internal.h"
+
+namespace mfa {
+
+static const float kInf = std::numeric_limits<float>::infinity();
+
+struct GraphCompiler {
+  // topology
+  std::vector<int32_t> phone2entry, entry_state_off, fwd_class, self_class, trans_off, trans_dst;
+  // tuples
+  std::vector<int32_t> tuples, first_tid;
+  std::unordered_map<uint64_t, std::vector<std::pair<uint64_t, int32_t>>> tstate_map;
+  // tree
+  int ctx_width = 1, central = 0, tree_root = 0;
+  std::vector<int32_t> tree_nodes, tree_aux_off, tree_aux;
+  // lexicon
+  std::vector<int32_t> word_pron_off, pron_phone_off, pron_phones;
+  std::vector<float> pron_cost, sil_after, nonsil_after, sil_before, nonsil_before;
+  int sil_phone = 1;
+  float init_sil = 0, init_nonsil = 0, final_sil = 0, final_nonsil = 0;
+
+  int tree_lookup(const int *ctx, int pdf_class) const {
+    int n = tree_root;
+    for (;;) {
+      const int32_t *nd = &tree_nodes[4 * n];
+      if (nd[0] == 0) return nd[2];
+      int key = nd[1];
+      int v;
+      if (key == -1) v = pdf_class;
+      else if (key >= 0 && key < ctx_width) v = ctx[key];
+      else return -1;
+      const int32_t *aux = &tree_aux[tree_aux_off[n]];
+      int na = tree_aux_off[n + 1] - tree_aux_off[n];
+      if (nd[0] == 1) {
+        bool yes = std::binary_search(aux, aux + na, v);
+        n = yes ? nd[2] : nd[3];
+      } else {
+        if (v < 0 || v >= na || aux[v] < 0) return -1;
+        n = aux[v];
+      }
+      if (n < 0) return -1;
+    }
+  }
+
+  int find_tstate(int phone, int hs, int fpdf, int spdf) const {
+    uint64_t k1 = ((uint64_t)(uint32_t)phone << 32) | (uint32_t)hs;
+    auto it = tstate_map.find(k1);
+    if (it == tstate_map.end()) return -1;
+    uint64_t k2 = ((uint64_t)(uint32_t)fpdf << 32) | (uint32_t)spdf;
+    for (auto &p : it->second) if (p.first == k2) return p.second;
+    return -1;
+  }
+};
+
+struct PhoneArc { int src, dst, phone, olabel; float cost; };
+
+struct FstBuilder {
+  std::vector<int32_t> src, dst, il, ol;
+  std::vector<float> w, finals;
+  int add_state() { finals.push_back(kInf); return (int)finals.size() - 1; }
+  void add_arc(int s, int d, int i, int o, float c) { src.push_back(s); dst.push_back(d); il.push_back(i); ol.push_back(o); w.push_back(c); }
+};
+
+struct FstBatch {
+  std::vector<int64_t> state_off{0}, arc_off{0};
+  std::vector<int32_t> start, src, dst, il, ol;
+  std::vector<float> finals, w;
+  int32_t n() const { return (int32_t)start.size(); }
+};
+
+// One utterance.  Returns "" or an error string.
+static std::string compile_one(const GraphCompiler &C, const int32_t *words, int64_t nw, FstBuilder &out, int &start_state) {
+  // ---- phone graph --------------------------------------------------------------------------
+  // node ids: 0 = Start; per boundary i in 0..nw: NS_i = 1+3i, P_i = 2+3i, S_i = 3+3i; then chain nodes.
+  std::vector<PhoneArc> arcs;
+  int n_nodes = 1 + 3 * (int)(nw + 1);
+  auto NS = [](int i) { return 1 + 3 * i; };
+  auto PP = [](int i) { return 2 + 3 * i; };
+  auto SS = [](int i) { return 3 + 3 * i; };
+  for (int i = 0; i <= nw; i++) arcs.push_back({PP(i), SS(i), C.sil_phone, 0, 0.0f});
+  int nwords_tab = (int)C.word_pron_off.size() - 1;
+  for (int i = 0; i < nw; i++) {
+    int wid = words[i];
+    if (wid < 0 || wid >= nwords_tab || C.word_pron_off[wid] == C.word_pron_off[wid + 1])
+      return "word id " + std::to_string(wid) + " has no pronunciation";
+    for (int pr = C.word_pron_off[wid]; pr < C.word_pron_off[wid + 1]; pr++) {
+      int a = C.pron_phone_off[pr], b = C.pron_phone_off[pr + 1], len = b - a;
+      if (len <= 0) return "empty pronunciation";
+      // entry variants: from NS_i (non-silence before) and S_i (silence before); exit variants: to NS_{i+1} / P_{i+1}
+      // interior chain shared: nodes c_1..c_{len-1}
+      std::vector<int> chain(len + 1, -1);
+      for (int k = 1; k < len; k++) chain[k] = n_nodes++;
+      for (int k = 0; k < len; k++) {
+        int ph = C.pron_phones[a + k];
+        std::vector<std::pair<int, float>> srcs, dsts;
+        if (k == 0) { srcs.push_back({NS(i), C.pron_cost[pr] + C.nonsil_before[pr]}); srcs.push_back({SS(i), C.pron_cost[pr] + C.sil_before[pr]}); }
+        else srcs.push_back({chain[k], 0.0f});
+        if (k == len - 1) { dsts.push_back({NS(i + 1), C.nonsil_after[pr]}); dsts.push_back({PP(i + 1), C.sil_after[pr]}); }
+        else dsts.push_back({chain[k + 1], 0.0f});
+        for (auto &s : srcs) for (auto &d : dsts) arcs.push_back({s.first, d.first, ph, k == 0 ? wid : 0, s.second + d.second});
+      }
+    }
+  }
+  std::vector<float> node_final(n_nodes, kInf);
+  node_final[NS((int)nw)] = C.final_nonsil;
+  node_final[SS((int)nw)] = C.final_sil;
+  // Start: silence into S_0 with init_sil; copies of NS_0's out-arcs with init_nonsil added.
+  {
+    size_t na = arcs.size();
+    arcs.push_back({0, SS(0), C.sil_phone, 0, C.init_sil});
+    for (size_t k = 0; k < na; k++) if (arcs[k].src == NS(0)) { PhoneArc c = arcs[k]; c.src = 0; c.cost += C.init_nonsil; arcs.push_back(c); }
+    if (nw == 0) node_final[0] = C.init_nonsil + C.final_nonsil;
+  }
+  // out-adjacency
+  std::vector<std::vector<int>> out_arcs(n_nodes);
+  for (int k = 0; k < (int)arcs.size(); k++) out_arcs[arcs[k].src].push_back(k);
+
+  // ---- instances + HMM expansion ------------------------------------------------------------
+  const bool tri = C.ctx_width == 3;
+  struct Inst { int arc, l, r; std::vector<int> junctions; };  // junction graph nodes (hmm final reached)
+  std::vector<Inst> insts;
+  std::map<std::tuple<int, int, int>, int> inst_id;
+  out = FstBuilder();
+  start_state = out.add_state();
+  if (node_final[0] != kInf) out.finals[start_state] = node_final[0];
+
+  // create instance (lazily), returns id; hmm nodes created on creation
+  std::vector<int> work;
+  std::string err;
+  auto get_inst = [&](int arc, int l, int r) -> int {
+    if (!tri) { l = 0; r = 0; }
+    auto key = std::make_tuple(arc, l, r);
+    auto it = inst_id.find(key);
+    if (it != inst_id.end()) return it->second;
+    int id = (int)insts.size();
+    insts.push_back({arc, l, r, {}});
+    inst_id[key] = id;
+    work.push_back(id);
+    return id;
+  };
+  // per instance: entry arcs description = list of (tid, target graph node) for state-0 forward transitions
+  struct Entry { int tid, node; };
+  std::vector<std::vector<Entry>> entries;
+  auto expand = [&](int id) {
+    // NOTE: insts may reallocate inside; copy fields first
+    int arc = insts[id].arc, l = insts[id].l, r = insts[id].r;
+    int ph = arcs[arc].phone;
+    if (ph < 0 || ph >= (int)C.phone2entry.size() || C.phone2entry[ph] < 0) { err = "phone " + std::to_string(ph) + " has no topology"; return; }
+    int ent = C.phone2entry[ph];
+    int s0 = C.entry_state_off[ent], ns = C.entry_state_off[ent + 1] - s0;
+    int nfinal = ns - 1;
+    int ctx[3] = {l, ph, r};
+    int ctx1[1] = {ph};
+    std::vector<int> tstate(ns, -1);
+    for (int j = 0; j < ns; j++) {
+      if (C.fwd_class[s0 + j] < 0) continue;
+      int fpdf = C.tree_lookup(tri ? ctx : ctx1, C.fwd_class[s0 + j]);
+      int spdf = C.tree_lookup(tri ? ctx : ctx1, C.self_class[s0 + j]);
+      if (fpdf < 0 || spdf < 0) { err = "tree has no pdf for context (" + std::to_string(l) + "," + std::to_string(ph) + "," + std::to_string(r) + ")"; return; }
+      tstate[j] = C.find_tstate(ph, j, fpdf, spdf);
+      if (tstate[j] < 0) { err = "no transition-state for phone " + std::to_string(ph) + " state " + std::to_string(j); return; }
+    }
+    // nodes keyed by (j' dst, j src)
+    std::map<std::pair<int, int>, int> node;
+    std::vector<std::pair<int, int>> order;  // creation order (j', j)
+    auto get_node = [&](int jd, int js) {
+      auto k = std::make_pair(jd, js);
+      auto it = node.find(k);
+      if (it != node.end()) return it->second;
+      int n = out.add_state();
+      node[k] = n; order.push_back(k);
+      return n;
+    };
+    if ((int)entries.size() <= id) entries.resize(id + 1);
+    // state-0 forward transitions become entry arcs (attached to predecessors' junctions later)
+    {
+      int j = 0;
+      for (int t = C.trans_off[s0 + j], k = 0; t < C.trans_off[s0 + j + 1]; t++, k++) {
+        int jd = C.trans_dst[t];
+        if (jd == j) continue;
+        entries[id].push_back({C.first_tid[tstate[j]] + k, get_node(jd, j)});
+      }
+    }
+    // closure over internal nodes
+    for (size_t oi = 0; oi < order.size(); oi++) {
+      int jd = order[oi].first, js = order[oi].second;
+      int n = node[order[oi]];
+      if (jd != nfinal) {
+        for (int t = C.trans_off[s0 + jd], k = 0; t < C.trans_off[s0 + jd + 1]; t++, k++) {
+          int j2 = C.trans_dst[t];
+          if (j2 == jd) continue;
+          out.add_arc(n, get_node(j2, jd), C.first_tid[tstate[jd]] + k, 0, 0.0f);
+        }
+      } else {
+        insts[id].junctions.push_back(n);
+      }
+      // self-loop of the SOURCE state js sits here (reorder=true); added last like AddSelfLoops does
+      for (int t = C.trans_off[s0 + js], k = 0; t < C.trans_off[s0 + js + 1]; t++, k++)
+        if (C.trans_dst[t] == js) out.add_arc(n, n, C.first_tid[tstate[js]] + k, 0, 0.0f);
+    }
+  };
+
+  // seeds: arcs out of Start
+  struct Pending { int from_node; int inst; int olabel; float cost; };  // attach inst's entry arcs at graph node
+  std::vector<Pending> pend;
+  auto successors = [&](int pnode, int lphone, int from_graph_node, int rfilter) {
+    // all instances following phone-graph node `pnode` with left phone `lphone`; rfilter = required phone (tri) or -1
+    for (int ea : out_arcs[pnode]) {
+      if (tri && rfilter >= 0 && arcs[ea].phone != rfilter) continue;
+      int d = arcs[ea].dst;
+      if (tri) {
+        std::vector<int> rs;
+        for (int e2 : out_arcs[d]) if (std::find(rs.begin(), rs.end(), arcs[e2].phone) == rs.end()) rs.push_back(arcs[e2].phone);
+        if (node_final[d] != kInf) rs.push_back(0);
+        for (int rr : rs) pend.push_back({from_graph_node, get_inst(ea, lphone, rr), arcs[ea].olabel, arcs[ea].cost});
+      } else {
+        pend.push_back({from_graph_node, get_inst(ea, 0, 0), arcs[ea].olabel, arcs[ea].cost});
+      }
+    }
+  };
+  successors(0, 0, start_state, -1);
+  size_t wi = 0;
+  while (wi < work.size()) {
+    int id = work[wi++];
+    expand(id);
+    if (!err.empty()) return err;
+    int arc = insts[id].arc, r = insts[id].r;
+    int d = arcs[arc].dst, ph = arcs[arc].phone;
+    std::vector<int> junc = insts[id].junctions;
+    for (int jn : junc) {
+      if (tri) {
+        if (r == 0) { if (node_final[d] != kInf) out.finals[jn] = node_final[d]; }
+        else successors(d, ph, jn, r);
+      } else {
+        if (node_final[d] != kInf) out.finals[jn] = node_final[d];
+        successors(d, 0, jn, -1);
+      }
+    }
+  }
+  // attach entry arcs
+  for (auto &p : pend)
+    for (auto &en : entries[p.inst]) out.add_arc(p.from_node, en.node, en.tid, p.olabel, p.cost);
+  return "";
+}
+
+// trim states that cannot reach a final state / are unreachable (keeps the decoder's token counts honest)
+static void trim(FstBuilder &g, int &start) {
+  int S = (int)g.finals.size();
+  size_t A = g.src.size();
+  std::vector<char> fwd(S, 0), bwd(S, 0);
+  std::vector<std::vector<int>> outa(S), ina(S);
+  for (size_t a = 0; a < A; a++) { outa[g.src[a]].push_back((int)a); ina[g.dst[a]].push_back((int)a); }
+  std::vector<int> st{start}; fwd[start] = 1;
+  while (!st.empty()) { int s = st.back(); st.pop_back(); for (int a : outa[s]) if (!fwd[g.dst[a]]) { fwd[g.dst[a]] = 1; st.push_back(g.dst[a]); } }
+  for (int s = 0; s < S; s++) if (g.finals[s] != kInf) { bwd[s] = 1; st.push_back(s); }
+  while (!st.empty()) { int s = st.back(); st.pop_back(); for (int a : ina[s]) if (!bwd[g.src[a]]) { bwd[g.src[a]] = 1; st.push_back(g.src[a]); } }
+  std::vector<int> remap(S, -1); int n = 0;
+  for (int s = 0; s < S; s++) if (fwd[s] && bwd[s]) remap[s] = n++;
+  if (remap[start] < 0) { g = FstBuilder(); start = -1; return; }
+  FstBuilder o; o.finals.resize(n);
+  for (int s = 0; s < S; s++) if (remap[s] >= 0) o.finals[remap[s]] = g.finals[s];
+  for (size_t a = 0; a < A; a++) if (remap[g.src[a]] >= 0 && remap[g.dst[a]] >= 0) o.add_arc(remap[g.src[a]], remap[g.dst[a]], g.il[a], g.ol[a], g.w[a]);
+  start = remap[start];
+  g = std::move(o);
+}
+
+}  // namespace mfa
+
+using namespace mfa;
+
+struct mfa_graph_compiler { GraphCompiler c; };
+struct mfa_fst_batch { FstBatch b; };
+
+extern "C" {
+
+int mfa_graph_compiler_create(const mfa_hmm_desc *h, const mfa_lexicon_desc *l, mfa_graph_compiler **out) {
+  if (!h || !l || !out) return set_error(MFA_ERR_INVALID, "null argument");
+  if (!((h->ctx_width == 1 && h->central_pos == 0) || (h->ctx_width == 3 && h->central_pos == 1)))
+    return set_error(MFA_ERR_UNSUPPORTED, "only (N,P)=(1,0) and (3,1) context trees are supported");
+  auto *gc = new mfa_graph_compiler();
+  GraphCompiler &c = gc->c;
+  c.phone2entry.assign(h->phone2entry, h->phone2entry + h->num_phones);
+  c.entry_state_off.assign(h->entry_state_off, h->entry_state_off + h->num_entries + 1);
+  int nhs = c.entry_state_off.back();
+  c.fwd_class.assign(h->state_fwd_class, h->state_fwd_class + nhs);
+  c.self_class.assign(h->state_self_class, h->state_self_class + nhs);
+  c.trans_off.assign(h->state_trans_off, h->state_trans_off + nhs + 1);
+  c.trans_dst.assign(h->trans_dst, h->trans_dst + c.trans_off.back());
+  c.tuples.assign(h->tuples, h->tuples + 4 * (size_t)h->num_tstates);
+  c.first_tid.assign(h->tstate_first_tid, h->tstate_first_tid + h->num_tstates + 2);
+  for (int ts = 1; ts <= h->num_tstates; ts++) {
+    const int32_t *t = &c.tuples[4 * (ts - 1)];
+    uint64_t k1 = ((uint64_t)(uint32_t)t[0] << 32) | (uint32_t)t[1];
+    uint64_t k2 = ((uint64_t)(uint32_t)t[2] << 32) | (uint32_t)t[3];
+    c.tstate_map[k1].push_back({k2, ts});
+  }
+  c.ctx_width = h->ctx_width; c.central = h->central_pos; c.tree_root = h->tree_root;
+  c.tree_nodes.assign(h->tree_nodes, h->tree_nodes + 4 * (size_t)h->num_tree_nodes);
+  c.tree_aux_off.assign(h->tree_aux_off, h->tree_aux_off + h->num_tree_nodes + 1);
+  c.tree_aux.assign(h->tree_aux, h->tree_aux + c.tree_aux_off.back());
+  c.word_pron_off.assign(l->word_pron_off, l->word_pron_off + l->num_words + 1);
+  int np = c.word_pron_off.back();
+  c.pron_phone_off.assign(l->pron_phone_off, l->pron_phone_off + np + 1);
+  c.pron_phones.assign(l->pron_phones, l->pron_phones + c.pron_phone_off.back());
+  c.pron_cost.assign(l->pron_cost, l->pron_cost + np);
+  auto fill = [&](std::vector<float> &v, const float *p, float dflt) { if (p) v.assign(p, p + np); else v.assign(np, dflt); };
+  fill(c.sil_after, l->pron_sil_after_cost, l->sil_cost);
+  fill(c.nonsil_after, l->pron_nonsil_after_cost, l->nonsil_cost);
+  fill(c.sil_before, l->pron_sil_before_cost, 0.0f);
+  fill(c.nonsil_before, l->pron_nonsil_before_cost, 0.0f);
+  c.sil_phone = l->sil_phone;
+  c.init_sil = l->init_sil_cost; c.init_nonsil = l->init_nonsil_cost;
+  c.final_sil = l->final_sil_cost; c.final_nonsil = l->final_nonsil_cost;
+  *out = gc;
+  return MFA_OK;
+}
+
+int mfa_graph_compiler_destroy(mfa_graph_compiler *c) { delete c; return MFA_OK; }
+
+int mfa_graph_compile(mfa_graph_compiler *c, const int32_t *words, const int64_t *word_off, int32_t n_utts, int32_t n_threads,
+                      mfa_fst_batch **out) {
+  if (!c || !word_off || !out || n_utts < 0) return set_error(MFA_ERR_INVALID, "bad argument");
+  std::vector<FstBuilder> gs(n_utts);
+  std::vector<int> starts(n_utts, -1);
+  std::vector<std::string> errs(n_utts);
+  if (n_threads < 1) n_threads = 1;
+  n_threads = std::min<int>(n_threads, std::max(1, n_utts));
+  auto worker = [&](int tid) {
+    for (int u = tid; u < n_utts; u += n_threads) {
+      errs[u] = compile_one(c->c, words + word_off[u], word_off[u + 1] - word_off[u], gs[u], starts[u]);
+      if (errs[u].empty()) trim(gs[u], starts[u]);
+    }
+  };
+  if (n_threads == 1) worker(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < n_threads; t++) th.emplace_back(worker, t); for (auto &t : th) t.join(); }
+  for (int u = 0; u < n_utts; u++) if (!errs[u].empty()) return set_error(MFA_ERR_GRAPH, "utterance " + std::to_string(u) + ": " + errs[u]);
+  auto *fb = new mfa_fst_batch();
+  FstBatch &b = fb->b;
+  for (int u = 0; u < n_utts; u++) {
+    b.start.push_back(starts[u]);
+    b.finals.insert(b.finals.end(), gs[u].finals.begin(), gs[u].finals.end());
+    b.src.insert(b.src.end(), gs[u].src.begin(), gs[u].src.end());
+    b.dst.insert(b.dst.end(), gs[u].dst.begin(), gs[u].dst.end());
+    b.il.insert(b.il.end(), gs[u].il.begin(), gs[u].il.end());
+    b.ol.insert(b.ol.end(), gs[u].ol.begin(), gs[u].ol.end());
+    b.w.insert(b.w.end(), gs[u].w.begin(), gs[u].w.end());
+    b.state_off.push_back((int64_t)b.finals.size());
+    b.arc_off.push_back((int64_t)b.src.size());
+  }
+  *out = fb;
+  return MFA_OK;
+}
+
+int mfa_fst_batch_create(int32_t n_utts, const int64_t *state_off, const int64_t *arc_off, const int32_t *start, const float *finals,
+                         const int32_t *src, const int32_t *dst, const int32_t *ilabel, const int32_t *olabel, const float *weight,
+                         mfa_fst_batch **out) {
+  if (n_utts < 0 || !state_off || !arc_off || !out) return set_error(MFA_ERR_INVALID, "bad argument");
+  auto *fb = new mfa_fst_batch();
+  FstBatch &b = fb->b;
+  int64_t S = state_off[n_utts], A = arc_off[n_utts];
+  b.state_off.assign(state_off, state_off + n_utts + 1);
+  b.arc_off.assign(arc_off, arc_off + n_utts + 1);
+  b.start.assign(start, start + n_utts);
+  b.finals.assign(finals, finals + S);
+  b.src.assign(src, src + A); b.dst.assign(dst, dst + A); b.il.assign(ilabel, ilabel + A); b.ol.assign(olabel, olabel + A);
+  b.w.assign(weight, weight + A);
+  for (int u = 0; u < n_utts; u++) {
+    int64_t ns = state_off[u + 1] - state_off[u];
+    for (int64_t a = arc_off[u]; a < arc_off[u + 1]; a++)
+      if (src[a] < 0 || src[a] >= ns || dst[a] < 0 || dst[a] >= ns) { delete fb; return set_error(MFA_ERR_INVALID, "arc endpoint out of range"); }
+    if (start[u] >= ns) { delete fb; return set_error(MFA_ERR_INVALID, "start state out of range"); }
+  }
+  *out = fb;
+  return MFA_OK;
+}
+
+int mfa_fst_batch_destroy(mfa_fst_batch *b) { delete b; return MFA_OK; }
+
+int mfa_fst_batch_sizes(const mfa_fst_batch *b, int32_t *n_utts, int64_t *n_states, int64_t *n_arcs) {
+  if (!b) return set_error(MFA_ERR_INVALID, "null batch");
+  if (n_utts) *n_utts = b->b.n();
+  if (n_states) *n_states = b->b.state_off.back();
+  if (n_arcs) *n_arcs = b->b.arc_off.back();
+  return MFA_OK;
+}
+
+int mfa_fst_batch_export(const mfa_fst_batch *fb, int64_t *state_off, int64_t *arc_off, int32_t *start, float *finals, int32_t *src,
+                         int32_t *dst, int32_t *ilabel, int32_t *olabel, float *weight) {
+  if (!fb) return set_error(MFA_ERR_INVALID, "null batch");
+  const FstBatch &b = fb->b;
+  auto cp = [](auto *d, const auto &v) { if (d && !v.empty()) std::memcpy(d, v.data(), v.size() * sizeof(v[0])); };
+  cp(state_off, b.state_off); cp(arc_off, b.arc_off); cp(start, b.start); cp(finals, b.finals);
+  cp(src, b.src); cp(dst, b.dst); cp(ilabel, b.il); cp(olabel, b.ol); cp(weight, b.w);
+  return MFA_OK;
+}
+
+// ---- packing for the Viterbi kernel -----------------------------------------------------------
+int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_t *tid2pdf, int32_t num_tids, mfa_graphs **out) {
+  if (!fb || !tid_cost || !tid2pdf || !out) return set_error(MFA_ERR_INVALID, "null argument");
+  const FstBatch &b = fb->b;
+  auto *g = new mfa_graphs();
+  int n = b.n();
+  g->n_utts = n;
+  g->st_off.assign(n + 1, 0); g->arc_off.assign(n + 1, 0); g->lp_off.assign(n + 1, 0); g->inb_off.assign(n + 1, 0);
+  g->start.resize(n); g->n_eps.assign(n, 0); g->max_words.assign(n, 0);
+  std::vector<int32_t> lpmap;
+  for (int u = 0; u < n; u++) {
+    int64_t s0 = b.state_off[u], S = b.state_off[u + 1] - s0, a0 = b.arc_off[u], A = b.arc_off[u + 1] - a0;
+    g->start[u] = b.start[u];
+    if (S > 65534 || A > 65534) { delete g; return set_error(MFA_ERR_UNSUPPORTED, "graph of utterance " + std::to_string(u) + " exceeds 65534 states/arcs"); }
+    // order arcs by (dst, original index)
+    std::vector<int32_t> order(A);
+    for (int64_t a = 0; a < A; a++) order[a] = (int32_t)a;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.dst[a0 + x] < b.dst[a0 + y]; });
+    std::vector<int32_t> inb(S + 1, 0);
+    for (int64_t a = 0; a < A; a++) inb[b.dst[a0 + a] + 1]++;
+    for (int64_t s = 0; s < S; s++) inb[s + 1] += inb[s];
+    g->in_begin.insert(g->in_begin.end(), inb.begin(), inb.end());
+    // local pdf list
+    std::vector<int32_t> pdfs;
+    for (int64_t a = 0; a < A; a++) { int il = b.il[a0 + a]; if (il > 0) { if (il > num_tids) { delete g; return set_error(MFA_ERR_INVALID, "ilabel exceeds num_tids"); } pdfs.push_back(tid2pdf[il]); } }
+    std::sort(pdfs.begin(), pdfs.end()); pdfs.erase(std::unique(pdfs.begin(), pdfs.end()), pdfs.end());
+    int maxpdf = pdfs.empty() ? 0 : pdfs.back();
+    if ((int)lpmap.size() <= maxpdf) lpmap.resize(maxpdf + 1);
+    for (size_t k = 0; k < pdfs.size(); k++) lpmap[pdfs[k]] = (int32_t)k;
+    int words = 0;
+    for (int64_t k = 0; k < A; k++) {
+      int64_t a = a0 + order[k];
+      int il = b.il[a];
+      g->a_src.push_back(b.src[a]);
+      g->a_tid.push_back(il);
+      g->a_olabel.push_back(b.ol[a]);
+      if (b.ol[a] != 0) words++;
+      if (il > 0) { g->a_w.push_back(b.w[a] + tid_cost[il]); g->a_lp.push_back(lpmap[tid2pdf[il]]); }
+      else { g->a_w.push_back(b.w[a]); g->a_lp.push_back(-1); g->n_eps[u]++; }
+    }
+    g->max_words[u] = words;  // loose bound (a path crosses each labelled arc at most once in an acyclic word graph)
+    g->final_w.insert(g->final_w.end(), b.finals.begin() + s0, b.finals.begin() + s0 + S);
+    g->lp2pdf.insert(g->lp2pdf.end(), pdfs.begin(), pdfs.end());
+    g->st_off[u + 1] = g->st_off[u] + S;
+    g->arc_off[u + 1] = g->arc_off[u] + A;
+    g->lp_off[u + 1] = g->lp_off[u] + (int64_t)pdfs.size();
+    g->inb_off[u + 1] = g->inb_off[u] + S + 1;
+  }
+  *out = g;
+  return MFA_OK;
+}
+
+int mfa_graphs_max_words(const mfa_graphs *g, int32_t *max_words) {
+  if (!g || !max_words) return set_error(MFA_ERR_INVALID, "null argument");
+  std::memcpy(max_words, g->max_words.data(), sizeof(int32_t) * g->max_words.size());
+  return MFA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// pipeline.cu -- C-ABI entry points (host/device buffer handling) and the fused PCM -> alignment pipeline.
+//
+// mfa_align_pcm is AlignFunction._run's per-job loop (reference: montreal_forced_aligner/alignment/
+// multiprocessing.py:791-863) plus the feature stages feeding it (corpus/features.py:193-251, 287-376) for one GPU:
+// MFCC -> per-speaker CMVN -> deltas | splice+LDA (+fMLLR) -> all-pdf log-likelihoods -> beam Viterbi, in utterance
+// chunks sized so the pdf-major log-likelihood block and the back-pointers fit the HBM workspace.
+#include <algorithm>
+#include <cstring>
+
+#include "cuda_internal.cuh"
+
+using namespace mfa;
+
+namespace {
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// copy caller data to the device if it is host-resident; returns the device pointer to use
+template <typename T>
+int to_device(mfa_engine *e, int slot, const T *p, size_t n, int where, const T **out) {
+  if (where == MFA_DEVICE) { *out = p; return MFA_OK; }
+  T *d;
+  MFA_TRY(e->getT<T>(slot, n ? n : 1, &d));
+  if (n) CUDA_TRY(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+  *out = d;
+  return MFA_OK;
+}
+template <typename T>
+int out_buffer(mfa_engine *e, int slot, T *p, size_t n, int where, T **out) {
+  if (where == MFA_DEVICE) { *out = p; return MFA_OK; }
+  return e->getT<T>(slot, n ? n : 1, out);
+}
+template <typename T>
+int from_device(mfa_engine *e, const T *d, T *p, size_t n, int where) {
+  if (where == MFA_DEVICE || n == 0) return MFA_OK;
+  CUDA_TRY(cudaMemcpyAsync(p, d, n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+  return MFA_OK;
+}
+
+int check_offsets(const int64_t *off, int n, const char *what) {
+  if (!off) return set_error(MFA_ERR_INVALID, std::string(what) + " is null");
+  for (int i = 0; i < n; i++) if (off[i + 1] < off[i]) return set_error(MFA_ERR_INVALID, std::string(what) + " is not non-decreasing");
+  return MFA_OK;
+}
+
+int run_gmm(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t rows, float *d_llT, int64_t ld, int impl) {
+  MFA_TRY(e->gmm_timing_begin());
+  int r;
+  if (impl == 1) r = launch_gmm_ffma(e, m, d_feats, rows, d_llT, ld);
+  else r = launch_gmm_tc(e, m, d_feats, rows, d_llT, ld);
+  if (r) return r;
+  return e->gmm_timing_end(rows);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mfa_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *pcm, const int64_t *sample_off, int32_t n_utts, const int64_t *frame_off,
+             float *out, int where) {
+  if (!e || !o || !sample_off || !frame_off || n_utts < 0) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(check_offsets(sample_off, n_utts, "sample_off"));
+  for (int u = 0; u < n_utts; u++)
+    if (frame_off[u + 1] - frame_off[u] != mfa_mfcc_num_frames(o, sample_off[u + 1] - sample_off[u]))
+      return set_error(MFA_ERR_INVALID, "frame_off does not match mfa_mfcc_num_frames for utterance " + std::to_string(u));
+  int64_t ns = sample_off[n_utts] - sample_off[0], nf = frame_off[n_utts];
+  int64_t *d_so, *d_fo;
+  MFA_TRY(e->upload(DB_SAMPLE_OFF, sample_off, (size_t)n_utts + 1, &d_so));
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  const int16_t *d_pcm; float *d_out;
+  MFA_TRY(to_device(e, DB_PCM, pcm, (size_t)(sample_off[0] + ns), where, &d_pcm));
+  MFA_TRY(out_buffer(e, DB_MFCC, out, (size_t)nf * o->num_ceps, where, &d_out));
+  MFA_TRY(launch_mfcc(e, o, d_pcm, d_so, n_utts, d_fo, nf, d_out));
+  MFA_TRY(from_device(e, d_out, out, (size_t)nf * o->num_ceps, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+int mfa_cmvn_stats(mfa_engine *e, const float *feats, int32_t dim, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts,
+                   int32_t n_spk, double *stats, int where) {
+  if (!e || !frame_off || !utt2spk || !stats) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
+  int64_t *d_fo; const float *d_feats; double *d_stats;
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)frame_off[n_utts] * dim, where, &d_feats));
+  size_t ns = (size_t)n_spk * 2 * (dim + 1);
+  MFA_TRY(out_buffer(e, DB_CMVN_STATS, stats, ns, where, &d_stats));
+  CUDA_TRY(cudaMemsetAsync(d_stats, 0, ns * sizeof(double), e->stream));
+  MFA_TRY(launch_cmvn_stats(e, d_feats, dim, d_fo, utt2spk, n_utts, n_spk, d_stats));
+  MFA_TRY(from_device(e, d_stats, stats, ns, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+int mfa_features(mfa_engine *e, const mfa_feat_opts *o, const float *in, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts,
+                 float *out, int where) {
+  if (!e || !o || !frame_off) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
+  if ((o->fmllr || o->cmvn_stats) && !utt2spk) return set_error(MFA_ERR_INVALID, "utt2spk required with fmllr / cmvn_stats");
+  int64_t nf = frame_off[n_utts];
+  int od = mfa_feat_out_dim(o);
+  int64_t *d_fo; int32_t *d_u2s = nullptr; const float *d_in; float *d_out; double *d_stats = nullptr;
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  if (utt2spk) MFA_TRY(e->upload(DB_UTT2SPK, utt2spk, (size_t)n_utts, &d_u2s));
+  if (o->cmvn_stats) MFA_TRY(e->upload(DB_CMVN_STATS, o->cmvn_stats, (size_t)o->n_spk * 2 * (o->in_dim + 1), &d_stats));
+  MFA_TRY(to_device(e, DB_IO_FEATS, in, (size_t)nf * o->in_dim, where, &d_in));
+  MFA_TRY(out_buffer(e, DB_FEATS, out, (size_t)nf * od, where, &d_out));
+  if ((const void *)d_in == (const void *)d_out && !(o->mode == 0 && !o->fmllr)) return set_error(MFA_ERR_INVALID, "in-place only for mode 0 without fMLLR");
+  MFA_TRY(launch_features(e, o, d_in, d_fo, frame_off, d_fo, d_u2s, n_utts, d_stats, d_out, od));
+  MFA_TRY(from_device(e, d_out, out, (size_t)nf * od, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+int mfa_cmvn_apply(mfa_engine *e, float *feats, int32_t dim, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts, int32_t n_spk,
+                   const double *stats, int where) {
+  mfa_feat_opts o{};
+  o.mode = 0; o.in_dim = dim; o.n_spk = n_spk; o.cmvn_stats = stats;
+  if (where == MFA_DEVICE) return mfa_features(e, &o, feats, frame_off, utt2spk, n_utts, feats, where);
+  return mfa_features(e, &o, feats, frame_off, utt2spk, n_utts, feats, MFA_HOST);
+}
+
+int mfa_gmm_loglikes(mfa_engine *e, mfa_model *m, const float *feats, int64_t n_frames, float *out, int where, int impl) {
+  if (!e || !m || n_frames < 0) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->gmm_timing_reset();
+  const float *d_feats; float *d_out;
+  MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)n_frames * m->dim, where, &d_feats));
+  MFA_TRY(out_buffer(e, DB_IO_LL, out, (size_t)n_frames * m->num_pdfs, where, &d_out));
+  const int64_t chunk = 65536;
+  float *d_llT;
+  MFA_TRY(e->getT<float>(DB_LL, (size_t)m->num_pdfs * std::min<int64_t>(chunk, round_up(std::max<int64_t>(n_frames, 1), 128)), &d_llT));
+  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
+    int64_t n = std::min(chunk, n_frames - f0), ld = round_up(n, 128);
+    MFA_TRY(run_gmm(e, m, d_feats + f0 * m->dim, n, d_llT, ld, impl));
+    MFA_TRY(launch_transpose(e, d_llT, m->num_pdfs, n, ld, d_out + f0 * m->num_pdfs, m->num_pdfs));
+  }
+  MFA_TRY(from_device(e, d_out, out, (size_t)n_frames * m->num_pdfs, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct ChunkPlan { int u0, n; int64_t ld; std::vector<int64_t> col_off; };
+
+// split utterances into chunks bounded by the log-likelihood block (+ back-pointers) budget
+int plan_chunks(const mfa_graphs *g, const int64_t *frame_off, int n_utts, int num_pdfs, int dim, int64_t budget, std::vector<ChunkPlan> &plans) {
+  int u = 0;
+  while (u < n_utts) {
+    ChunkPlan c; c.u0 = u; c.n = 0;
+    int64_t cols = 0, bp = 0;
+    while (u < n_utts) {
+      int64_t T = frame_off[u + 1] - frame_off[u];
+      int64_t S = g->st_off[u + 1] - g->st_off[u];
+      int64_t ncols = cols + round_up(T, 8);
+      int64_t nbp = bp + (T + 1) * S * 2;
+      int64_t bytes = round_up(ncols, 128) * ((int64_t)num_pdfs * 4 + (int64_t)dim * 4) + nbp;
+      if (c.n > 0 && bytes > budget) break;
+      c.col_off.push_back(cols);
+      cols = ncols; bp = nbp; c.n++; u++;
+    }
+    c.ld = round_up(std::max<int64_t>(cols, 1), 128);
+    plans.push_back(std::move(c));
+  }
+  return MFA_OK;
+}
+
+// shared tail of mfa_align / mfa_align_pcm: per chunk, (features ->) log-likelihoods -> Viterbi
+struct AlignIO {
+  int32_t *d_ali; float *d_pf; int32_t *d_words; int64_t *d_word_off; int32_t *d_num_words; float *d_total; int32_t *d_status;
+};
+
+}  // namespace
+
+extern "C" {
+
+int mfa_align(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_opts *o, const float *loglikes, const int64_t *frame_off,
+              int32_t n_utts, int32_t *ali, float *per_frame, int32_t *words, const int64_t *word_off, int32_t *num_words,
+              float *total_like, int32_t *status, int where) {
+  if (!e || !m || !g || !o || !frame_off || !word_off) return set_error(MFA_ERR_INVALID, "bad argument");
+  if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
+  MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
+  MFA_TRY(upload_graphs(e, g));
+  const int P = m->num_pdfs;
+  int64_t nf = frame_off[n_utts], nw = word_off[n_utts];
+  const float *d_ll;
+  MFA_TRY(to_device(e, DB_IO_LL, loglikes, (size_t)nf * P, where, &d_ll));
+  AlignIO io;
+  MFA_TRY(out_buffer(e, DB_ALI, ali, (size_t)nf, where, &io.d_ali));
+  MFA_TRY(out_buffer(e, DB_PERFRAME, per_frame, (size_t)nf, where, &io.d_pf));
+  MFA_TRY(out_buffer(e, DB_WORDS, words, (size_t)nw, where, &io.d_words));
+  MFA_TRY(out_buffer(e, DB_NUM_WORDS, num_words, (size_t)n_utts, where, &io.d_num_words));
+  MFA_TRY(out_buffer(e, DB_TOTAL_LIKE, total_like, (size_t)n_utts, where, &io.d_total));
+  MFA_TRY(out_buffer(e, DB_STATUS, status, (size_t)n_utts, where, &io.d_status));
+  int64_t *d_fo;
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  MFA_TRY(e->upload(DB_WORD_OFF, word_off, (size_t)n_utts + 1, &io.d_word_off));
+  CUDA_TRY(cudaMemsetAsync(io.d_ali, 0, (size_t)nf * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(io.d_pf, 0, (size_t)nf * 4, e->stream));
+  if (nw) CUDA_TRY(cudaMemsetAsync(io.d_words, 0, (size_t)nw * 4, e->stream));
+  std::vector<ChunkPlan> plans;
+  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, 0, (int64_t)4 << 30, plans));
+  for (auto &c : plans) {
+    float *d_llT; int64_t *d_col;
+    MFA_TRY(e->getT<float>(DB_LL, (size_t)P * c.ld, &d_llT));
+    MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
+    // frame-major [T][P] rows of each utterance -> pdf-major columns at col_off (padding columns are never read
+    // beyond the 8-frame block of the last frame, whose values are unused)
+    CUDA_TRY(cudaMemsetAsync(d_llT, 0, (size_t)P * c.ld * 4, e->stream));
+    for (int k = 0; k < c.n; k++) {
+      int u = c.u0 + k;
+      int64_t T = frame_off[u + 1] - frame_off[u];
+      MFA_TRY(launch_transpose(e, d_ll + frame_off[u] * P, T, P, P, d_llT + c.col_off[k], c.ld));
+    }
+    ViterbiArgs a{};
+    a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
+    a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
+    a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
+    a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = *o;
+    MFA_TRY(launch_viterbi(e, a));
+  }
+  MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_words, words, (size_t)nw, where));
+  MFA_TRY(from_device(e, io.d_num_words, num_words, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_total, total_like, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_status, status, (size_t)n_utts, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline_opts *o, const int16_t *pcm, const int64_t *sample_off,
+                  const int32_t *utt2spk, int32_t n_utts, int32_t n_spk, const int64_t *frame_off, int32_t *ali, float *per_frame,
+                  int32_t *words, const int64_t *word_off, int32_t *num_words, float *total_like, int32_t *status, int where) {
+  if (!e || !m || !g || !o || !sample_off || !frame_off || !word_off || !utt2spk) return set_error(MFA_ERR_INVALID, "bad argument");
+  if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(check_offsets(sample_off, n_utts, "sample_off"));
+  MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
+  for (int u = 0; u < n_utts; u++)
+    if (frame_off[u + 1] - frame_off[u] != mfa_mfcc_num_frames(&o->mfcc, sample_off[u + 1] - sample_off[u]))
+      return set_error(MFA_ERR_INVALID, "frame_off does not match mfa_mfcc_num_frames for utterance " + std::to_string(u));
+  mfa_feat_opts fo = o->feat;
+  fo.in_dim = o->mfcc.num_ceps;
+  if (fo.fmllr && fo.n_spk != n_spk) return set_error(MFA_ERR_INVALID, "feat.n_spk must equal n_spk when fMLLR transforms are given");
+  const int D = mfa_feat_out_dim(&fo);
+  if (D != m->dim) return set_error(MFA_ERR_INVALID, "feature pipeline yields dim " + std::to_string(D) + " but the model expects " + std::to_string(m->dim));
+  e->gmm_timing_reset();
+  MFA_TRY(upload_graphs(e, g));
+  const int P = m->num_pdfs, C = o->mfcc.num_ceps;
+  const int64_t nf = frame_off[n_utts], nw = word_off[n_utts], ns = sample_off[n_utts];
+  // ---- inputs
+  int64_t *d_so, *d_fo; int32_t *d_u2s; const int16_t *d_pcm;
+  MFA_TRY(e->upload(DB_SAMPLE_OFF, sample_off, (size_t)n_utts + 1, &d_so));
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  MFA_TRY(e->upload(DB_UTT2SPK, utt2spk, (size_t)n_utts, &d_u2s));
+  MFA_TRY(to_device(e, DB_PCM, pcm, (size_t)ns, where, &d_pcm));
+  AlignIO io;
+  MFA_TRY(out_buffer(e, DB_ALI, ali, (size_t)nf, where, &io.d_ali));
+  MFA_TRY(out_buffer(e, DB_PERFRAME, per_frame, (size_t)nf, where, &io.d_pf));
+  MFA_TRY(out_buffer(e, DB_WORDS, words, (size_t)nw, where, &io.d_words));
+  MFA_TRY(out_buffer(e, DB_NUM_WORDS, num_words, (size_t)n_utts, where, &io.d_num_words));
+  MFA_TRY(out_buffer(e, DB_TOTAL_LIKE, total_like, (size_t)n_utts, where, &io.d_total));
+  MFA_TRY(out_buffer(e, DB_STATUS, status, (size_t)n_utts, where, &io.d_status));
+  MFA_TRY(e->upload(DB_WORD_OFF, word_off, (size_t)n_utts + 1, &io.d_word_off));
+  CUDA_TRY(cudaMemsetAsync(io.d_ali, 0, (size_t)nf * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(io.d_pf, 0, (size_t)nf * 4, e->stream));
+  if (nw) CUDA_TRY(cudaMemsetAsync(io.d_words, 0, (size_t)nw * 4, e->stream));
+  // ---- K1 + CMVN statistics over the whole batch
+  float *d_mfcc; double *d_stats = nullptr;
+  MFA_TRY(e->getT<float>(DB_MFCC, (size_t)nf * C, &d_mfcc));
+  MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
+  if (o->apply_cmvn) {
+    size_t nst = (size_t)n_spk * 2 * (C + 1);
+    if (fo.cmvn_stats) MFA_TRY(e->upload(DB_CMVN_STATS, fo.cmvn_stats, nst, &d_stats));
+    else {
+      MFA_TRY(e->getT<double>(DB_CMVN_STATS, nst, &d_stats));
+      MFA_TRY(launch_cmvn_stats(e, d_mfcc, C, d_fo, utt2spk, n_utts, n_spk, d_stats));
+    }
+  }
+  // ---- chunks
+  std::vector<ChunkPlan> plans;
+  int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
+  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, plans));
+  for (auto &c : plans) {
+    float *d_feats, *d_llT; int64_t *d_col;
+    MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
+    MFA_TRY(e->getT<float>(DB_LL, (size_t)P * c.ld, &d_llT));
+    MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
+    CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
+    MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
+    MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
+    ViterbiArgs a{};
+    a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
+    a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
+    a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
+    a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
+    MFA_TRY(launch_viterbi(e, a));
+  }
+  MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_words, words, (size_t)nw, where));
+  MFA_TRY(from_device(e, io.d_num_words, num_words, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_total, total_like, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_status, status, (size_t)n_utts, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const int32_t *ali, int64_t n_frames, int where) {
+  if (!e || !m || n_frames < 0) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const float *d_feats; const int32_t *d_ali;
+  MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)n_frames * m->dim, where, &d_feats));
+  MFA_TRY(to_device(e, DB_IO_ALI, ali, (size_t)n_frames, where, &d_ali));
+  MFA_TRY(launch_acc_stats(e, m, d_feats, d_ali, n_frames));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
+}  // extern "C"

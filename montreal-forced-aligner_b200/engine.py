@@ -1,0 +1,480 @@
+"""Python host layer over the C ABI: engine, device-resident acoustic model, graph compiler, batched hot-path calls.
+
+numpy arrays are passed as host buffers (MFA_HOST), torch CUDA tensors as device buffers (MFA_DEVICE).
+torch is only used for device memory / streams / torch.distributed plumbing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .kaldi_io import AmDiagGmm, ContextDependency, Fst, TransitionModel
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _buf(x, dtype, name="buffer"):
+    """-> (keepalive, address, where). numpy -> host; torch cuda tensor -> device."""
+    if x is None:
+        return None, None, None
+    if _is_torch(x):
+        import torch
+        want = {np.float32: torch.float32, np.int32: torch.int32, np.int16: torch.int16, np.float64: torch.float64,
+                np.int64: torch.int64}[dtype]
+        if x.dtype != want or not x.is_contiguous():
+            raise TypeError(f"{name}: expected contiguous torch tensor of {want}")
+        return x, C.c_void_p(x.data_ptr()), (L.MFA_DEVICE if x.is_cuda else L.MFA_HOST)
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a, a.ctypes.data_as(C.c_void_p), L.MFA_HOST
+
+
+def _host(x, dtype):
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def mfcc_opts(**kw) -> L.MfccOpts:
+    """kalpy/MFA option names (corpus/features.py:780-820) -> mfa_mfcc_opts."""
+    d = dict(sample_frequency=16000.0, frame_length=25.0, frame_shift=10.0, preemphasis_coefficient=0.97,
+             low_frequency=20.0, high_frequency=7800.0, cepstral_lifter=22.0, energy_floor=0.0, num_mel_bins=23,
+             num_coefficients=13, use_energy=False, raw_energy=True, snip_edges=True, remove_dc_offset=True, dither=0.0)
+    for k, v in kw.items():
+        if k in ("allow_downsample", "allow_upsample", "sample_frequency_in"):
+            continue
+        if k not in d:
+            raise TypeError(f"unknown MFCC option {k!r}")
+        d[k] = v
+    if d["dither"] not in (0, 0.0):
+        raise L.MfaError("dither != 0 is not supported by the B200 engine (parity runs force dither=0; SURVEY.md section 5)")
+    return L.MfccOpts(float(d["sample_frequency"]), float(d["frame_length"]), float(d["frame_shift"]),
+                      float(d["preemphasis_coefficient"]), float(d["low_frequency"]), float(d["high_frequency"]),
+                      float(d["cepstral_lifter"]), float(d["energy_floor"]), int(d["num_mel_bins"]),
+                      int(d["num_coefficients"]), int(bool(d["use_energy"])), int(bool(d["raw_energy"])),
+                      int(bool(d["snip_edges"])), int(bool(d["remove_dc_offset"])))
+
+
+def num_frames(opts: L.MfccOpts, n_samples: int) -> int:
+    return int(L.lib().mfa_mfcc_num_frames(C.byref(opts), C.c_int64(int(n_samples))))
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        L.check(L.lib().mfa_engine_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            L.lib().mfa_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        L.check(L.lib().mfa_engine_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(L.lib().mfa_engine_stream(self._h) or 0)
+
+    @property
+    def sm_count(self) -> int:
+        return int(L.lib().mfa_engine_sm_count(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(L.lib().mfa_engine_launch_count(self._h))
+
+    def gmm_timing(self):
+        ms, n, rows = C.c_float(), C.c_int64(), C.c_int64()
+        L.check(L.lib().mfa_engine_gmm_timing(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
+        return ms.value, n.value, rows.value
+
+    # ---- K1 / CMVN / features -----------------------------------------------------------------
+    def mfcc(self, pcm, sample_off, opts: L.MfccOpts, out=None):
+        so, sop = _host(sample_off, np.int64)
+        n = so.shape[0] - 1
+        fo = np.zeros(n + 1, dtype=np.int64)
+        for u in range(n):
+            fo[u + 1] = fo[u] + num_frames(opts, so[u + 1] - so[u])
+        keep, pp, where = _buf(pcm, np.int16, "pcm")
+        if out is None:
+            if where == L.MFA_DEVICE:
+                import torch
+                out = torch.empty((int(fo[-1]), opts.num_ceps), dtype=torch.float32, device=pcm.device)
+            else:
+                out = np.empty((int(fo[-1]), opts.num_ceps), dtype=np.float32)
+        ko, op, w2 = _buf(out, np.float32, "out")
+        assert w2 == where
+        L.check(L.lib().mfa_mfcc(self._h, C.byref(opts), pp, sop, C.c_int32(n), fo.ctypes.data_as(C.c_void_p), op, C.c_int(where)))
+        return out, fo
+
+    def cmvn_stats(self, feats, frame_off, utt2spk, n_spk: int):
+        fo, fop = _host(frame_off, np.int64)
+        us, usp = _host(utt2spk, np.int32)
+        keep, fp, where = _buf(feats, np.float32, "feats")
+        dim = feats.shape[1]
+        if where == L.MFA_DEVICE:
+            import torch
+            stats = torch.zeros((n_spk, 2, dim + 1), dtype=torch.float64, device=feats.device)
+        else:
+            stats = np.zeros((n_spk, 2, dim + 1), dtype=np.float64)
+        ks, sp, _ = _buf(stats, np.float64, "stats")
+        L.check(L.lib().mfa_cmvn_stats(self._h, fp, C.c_int32(dim), fop, usp, C.c_int32(fo.shape[0] - 1), C.c_int32(n_spk), sp, C.c_int(where)))
+        return stats
+
+    def features(self, feats, frame_off, mode: str = "deltas", lda: Optional[np.ndarray] = None, splice_ctx: int = 3,
+                 fmllr: Optional[np.ndarray] = None, cmvn_stats: Optional[np.ndarray] = None, utt2spk=None, n_spk: int = 0):
+        fo, fop = _host(frame_off, np.int64)
+        n = fo.shape[0] - 1
+        o, keep = make_feat_opts(feats.shape[1], mode, lda, splice_ctx, fmllr, cmvn_stats, n_spk)
+        od = int(L.lib().mfa_feat_out_dim(C.byref(o)))
+        k1, ip, where = _buf(feats, np.float32, "feats")
+        if where == L.MFA_DEVICE:
+            import torch
+            out = torch.empty((feats.shape[0], od), dtype=torch.float32, device=feats.device)
+        else:
+            out = np.empty((feats.shape[0], od), dtype=np.float32)
+        k2, op, _ = _buf(out, np.float32)
+        usp = None
+        if utt2spk is not None:
+            us, usp = _host(utt2spk, np.int32)
+        L.check(L.lib().mfa_features(self._h, C.byref(o), ip, fop, usp, C.c_int32(n), op, C.c_int(where)))
+        return out
+
+
+def make_feat_opts(in_dim, mode, lda, splice_ctx, fmllr, cmvn_stats, n_spk):
+    keep = []
+    o = L.FeatOpts()
+    o.mode = {"none": 0, "deltas": 1, "lda": 2, "splice_lda": 2}[mode]
+    o.in_dim = int(in_dim)
+    o.splice_ctx = int(splice_ctx)
+    o.n_spk = int(n_spk)
+    if o.mode == 2:
+        if lda is None:
+            raise ValueError("mode 'lda' needs the LDA matrix")
+        a, p = _host(lda, np.float32)
+        keep.append(a)
+        o.lda = p.value
+        o.lda_rows, o.lda_cols = a.shape
+    if fmllr is not None:
+        a, p = _host(fmllr, np.float32)
+        keep.append(a)
+        o.fmllr = p.value
+        o.n_spk = a.shape[0]
+    if cmvn_stats is not None:
+        a, p = _host(cmvn_stats, np.float64)
+        keep.append(a)
+        o.cmvn_stats = p.value
+        o.n_spk = a.shape[0]
+    o._keep = keep
+    return o, keep
+
+
+class DeviceModel:
+    """Device-resident AmDiagGmm + tid->pdf map (mfa_model)."""
+
+    def __init__(self, engine: Engine, tm: TransitionModel, am: AmDiagGmm):
+        self.engine = engine
+        self.tm, self.am = tm, am
+        self._arrs = [np.ascontiguousarray(am.offsets, dtype=np.int32), np.ascontiguousarray(am.gconsts, dtype=np.float32),
+                      np.ascontiguousarray(am.means_invvars, dtype=np.float32), np.ascontiguousarray(am.inv_vars, dtype=np.float32),
+                      np.ascontiguousarray(np.maximum(tm.tid2pdf, 0), dtype=np.int32)]
+        d = L.ModelDesc(am.dim, am.NumPdfs(), am.NumGauss(), tm.num_tids, *[a.ctypes.data_as(C.c_void_p).value for a in self._arrs])
+        self._h = C.c_void_p()
+        L.check(L.lib().mfa_model_create(engine._h, C.byref(d), C.byref(self._h)))
+        self.dim, self.num_pdfs, self.num_gauss, self.num_tids = am.dim, am.NumPdfs(), am.NumGauss(), tm.num_tids
+
+    def close(self):
+        if self._h:
+            L.lib().mfa_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def boost_pdfs(self, factor: float, pdfs: Sequence[int]):
+        p, pp = _host(np.asarray(sorted(set(int(x) for x in pdfs)), dtype=np.int32), np.int32)
+        L.check(L.lib().mfa_model_boost_pdfs(self._h, C.c_float(factor), pp, C.c_int32(p.shape[0])))
+
+    def loglikes(self, feats, impl: int = 0):
+        """[T, dim] -> [T, num_pdfs] unscaled log-likelihoods (frame-major, the kalpy gmm_compute_likes layout)."""
+        k, fp, where = _buf(feats, np.float32, "feats")
+        T = feats.shape[0]
+        if where == L.MFA_DEVICE:
+            import torch
+            out = torch.empty((T, self.num_pdfs), dtype=torch.float32, device=feats.device)
+        else:
+            out = np.empty((T, self.num_pdfs), dtype=np.float32)
+        k2, op, _ = _buf(out, np.float32)
+        L.check(L.lib().mfa_gmm_loglikes(self.engine._h, self._h, fp, C.c_int64(T), op, C.c_int(where), C.c_int(impl)))
+        return out
+
+    # ---- K4
+    def acc_size(self) -> int:
+        return int(L.lib().mfa_acc_size(self._h))
+
+    def acc_zero(self):
+        L.check(L.lib().mfa_acc_zero(self.engine._h, self._h))
+
+    def acc_stats(self, feats, ali):
+        k, fp, where = _buf(feats, np.float32, "feats")
+        k2, ap, w2 = _buf(ali, np.int32, "ali")
+        assert where == w2
+        L.check(L.lib().mfa_acc_stats(self.engine._h, self._h, fp, ap, C.c_int64(feats.shape[0]), C.c_int(where)))
+
+    def acc_device_ptr(self) -> int:
+        return int(L.lib().mfa_acc_device_ptr(self.engine._h, self._h) or 0)
+
+    def acc_tensor(self):
+        """The device accumulator block as a torch f64 tensor view (for torch.distributed.all_reduce over NCCL)."""
+        import torch
+        n = self.acc_size()
+        ptr = self.acc_device_ptr()
+        if not ptr:
+            raise L.MfaError("accumulators not allocated; call acc_zero() first")
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Holder(), device=f"cuda:{self.engine.device}")
+
+    def acc_read(self) -> dict:
+        out = np.zeros(self.acc_size(), dtype=np.float64)
+        L.check(L.lib().mfa_acc_read(self.engine._h, self._h, out.ctypes.data_as(C.c_void_p)))
+        return self.split_accs(out)
+
+    def split_accs(self, flat: np.ndarray) -> dict:
+        G, D, nt = self.num_gauss, self.dim, self.num_tids
+        o = 0
+        occ = flat[o:o + G]; o += G
+        mean = flat[o:o + G * D].reshape(G, D); o += G * D
+        var = flat[o:o + G * D].reshape(G, D); o += G * D
+        trans = flat[o:o + nt + 1]; o += nt + 1
+        return dict(occ=occ, mean=mean, var=var, trans=trans, like=float(flat[o]), frames=float(flat[o + 1]))
+
+
+def hmm_desc(tm: TransitionModel, tree: ContextDependency):
+    """Flatten topology + tuples + tree for mfa_graph_compiler_create. Returns (desc, keepalive list)."""
+    topo = tm.topo
+    nph = int(topo.phone2idx.shape[0])
+    phone2entry = np.ascontiguousarray(topo.phone2idx, dtype=np.int32)
+    eso = [0]
+    fwd, slf, toff, tdst = [], [], [0], []
+    for e in topo.entries:
+        for s in e:
+            has = len(s.transitions) > 0
+            fwd.append(s.forward_pdf_class if has else -1)
+            slf.append(s.self_loop_pdf_class if has else -1)
+            for dst, _p in s.transitions:
+                tdst.append(dst)
+            toff.append(len(tdst))
+        eso.append(len(fwd))
+    node, aux_off, aux, root = tree.flatten()
+    arrs = [phone2entry, np.asarray(eso, np.int32), np.asarray(fwd, np.int32), np.asarray(slf, np.int32), np.asarray(toff, np.int32),
+            np.asarray(tdst if tdst else [0], np.int32), np.ascontiguousarray(tm.tuples, dtype=np.int32),
+            np.ascontiguousarray(tm.state2id, dtype=np.int32), np.ascontiguousarray(node, np.int32),
+            np.ascontiguousarray(aux_off, np.int32), np.ascontiguousarray(aux if aux.size else np.zeros(1, np.int32), np.int32)]
+    p = [a.ctypes.data_as(C.c_void_p).value for a in arrs]
+    d = L.HmmDesc(nph, p[0], len(topo.entries), p[1], p[2], p[3], p[4], p[5], tm.tuples.shape[0], p[6], p[7], tree.N, tree.P,
+                  node.shape[0], root, p[8], p[9], p[10])
+    return d, arrs
+
+
+class FstBatch:
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_fsts(cls, fsts: List[Fst]) -> "FstBatch":
+        n = len(fsts)
+        so = np.zeros(n + 1, np.int64)
+        ao = np.zeros(n + 1, np.int64)
+        for i, f in enumerate(fsts):
+            so[i + 1] = so[i] + f.num_states
+            ao[i + 1] = ao[i] + f.arc_src.shape[0]
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dtype=dt)
+        start = np.asarray([f.start for f in fsts], np.int32)
+        arrs = [so, ao, start, cat([f.finals for f in fsts], np.float32), cat([f.arc_src for f in fsts], np.int32),
+                cat([f.arc_dst for f in fsts], np.int32), cat([f.arc_ilabel for f in fsts], np.int32),
+                cat([f.arc_olabel for f in fsts], np.int32), cat([f.arc_weight for f in fsts], np.float32)]
+        h = C.c_void_p()
+        L.check(L.lib().mfa_fst_batch_create(C.c_int32(n), *[a.ctypes.data_as(C.c_void_p) for a in arrs], C.byref(h)))
+        return cls(h)
+
+    def sizes(self):
+        n, s, a = C.c_int32(), C.c_int64(), C.c_int64()
+        L.check(L.lib().mfa_fst_batch_sizes(self._h, C.byref(n), C.byref(s), C.byref(a)))
+        return n.value, s.value, a.value
+
+    def export(self) -> List[Fst]:
+        n, S, A = self.sizes()
+        so, ao = np.zeros(n + 1, np.int64), np.zeros(n + 1, np.int64)
+        start, finals = np.zeros(n, np.int32), np.zeros(S, np.float32)
+        src, dst, il, ol = (np.zeros(A, np.int32) for _ in range(4))
+        w = np.zeros(A, np.float32)
+        L.check(L.lib().mfa_fst_batch_export(self._h, *[a.ctypes.data_as(C.c_void_p) for a in (so, ao, start, finals, src, dst, il, ol, w)]))
+        out = []
+        for u in range(n):
+            a, b = ao[u], ao[u + 1]
+            out.append(Fst(int(start[u]), int(so[u + 1] - so[u]), src[a:b].copy(), il[a:b].copy(), ol[a:b].copy(), dst[a:b].copy(),
+                           w[a:b].copy(), finals[so[u]:so[u + 1]].copy()))
+        return out
+
+    def close(self):
+        if self._h:
+            L.lib().mfa_fst_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GraphCompiler:
+    """Host C++ training-graph compiler (mfa_graph_compiler)."""
+
+    def __init__(self, tm: TransitionModel, tree: ContextDependency, lexicon):
+        """lexicon: mfa_b200.lexicon.Lexicon"""
+        self.tm, self.tree, self.lexicon = tm, tree, lexicon
+        hd, self._keep1 = hmm_desc(tm, tree)
+        ld, self._keep2 = lexicon.desc()
+        self._h = C.c_void_p()
+        L.check(L.lib().mfa_graph_compiler_create(C.byref(hd), C.byref(ld), C.byref(self._h)))
+
+    def compile(self, word_id_seqs: Sequence[Sequence[int]], n_threads: int = 8) -> FstBatch:
+        n = len(word_id_seqs)
+        off = np.zeros(n + 1, np.int64)
+        for i, w in enumerate(word_id_seqs):
+            off[i + 1] = off[i] + len(w)
+        words = np.ascontiguousarray(np.concatenate([np.asarray(w, np.int32) for w in word_id_seqs]) if n and off[-1] else np.zeros(0, np.int32), dtype=np.int32)
+        h = C.c_void_p()
+        L.check(L.lib().mfa_graph_compile(self._h, words.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), C.c_int32(n),
+                                          C.c_int32(n_threads), C.byref(h)))
+        return FstBatch(h)
+
+    def close(self):
+        if self._h:
+            L.lib().mfa_graph_compiler_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Graphs:
+    """Decoder-ready packed graphs (mfa_graphs): AddTransitionProbs folded in."""
+
+    def __init__(self, batch: FstBatch, tm: TransitionModel, transition_scale: float = 1.0, self_loop_scale: float = 0.1):
+        tid_cost = np.ascontiguousarray(-tm.scaled_transition_log_probs(transition_scale, self_loop_scale), dtype=np.float32)
+        tid2pdf = np.ascontiguousarray(np.maximum(tm.tid2pdf, 0), dtype=np.int32)
+        self._h = C.c_void_p()
+        L.check(L.lib().mfa_graphs_pack(batch._h, tid_cost.ctypes.data_as(C.c_void_p), tid2pdf.ctypes.data_as(C.c_void_p),
+                                        C.c_int32(tm.num_tids), C.byref(self._h)))
+        self.n_utts = batch.sizes()[0]
+
+    def max_words(self) -> np.ndarray:
+        out = np.zeros(self.n_utts, np.int32)
+        L.check(L.lib().mfa_graphs_max_words(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self):
+        if self._h:
+            L.lib().mfa_graphs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def align_opts(acoustic_scale=0.1, beam=10.0, retry_beam=40.0, beam_delta=0.5, min_active=20) -> L.AlignOpts:
+    return L.AlignOpts(float(acoustic_scale), float(beam), float(retry_beam), float(beam_delta), int(min_active))
+
+
+class AlignResult:
+    """Outputs of a batched alignment call (host numpy arrays or device torch tensors)."""
+
+    def __init__(self, ali, per_frame, words, word_off, num_words, total_like, status, frame_off):
+        self.ali, self.per_frame, self.words, self.word_off = ali, per_frame, words, word_off
+        self.num_words, self.total_like, self.status, self.frame_off = num_words, total_like, status, frame_off
+
+    def utterance(self, u: int):
+        a, b = int(self.frame_off[u]), int(self.frame_off[u + 1])
+        w0 = int(self.word_off[u])
+        nw = int(self.num_words[u])
+        return dict(status=int(self.status[u]), ali=self.ali[a:b], per_frame=self.per_frame[a:b], words=self.words[w0:w0 + nw],
+                    like=float(self.total_like[u]))
+
+
+def _alloc_outputs(n_frames, word_cap, n_utts, device=None):
+    if device is None:
+        return (np.zeros(n_frames, np.int32), np.zeros(n_frames, np.float32), np.zeros(max(word_cap, 1), np.int32),
+                np.zeros(n_utts, np.int32), np.zeros(n_utts, np.float32), np.zeros(n_utts, np.int32))
+    import torch
+    z = lambda n, dt: torch.zeros(max(int(n), 1), dtype=dt, device=device)
+    return (z(n_frames, torch.int32), z(n_frames, torch.float32), z(word_cap, torch.int32), z(n_utts, torch.int32),
+            z(n_utts, torch.float32), z(n_utts, torch.int32))
+
+
+def align_loglikes(engine: Engine, model: DeviceModel, graphs: Graphs, loglikes, frame_off, opts: L.AlignOpts) -> AlignResult:
+    """K3 only: frame-major loglikes [sum T, num_pdfs] + packed graphs -> alignments."""
+    fo, fop = _host(frame_off, np.int64)
+    n = fo.shape[0] - 1
+    wo = np.zeros(n + 1, np.int64)
+    wo[1:] = np.cumsum(graphs.max_words())
+    k, lp, where = _buf(loglikes, np.float32, "loglikes")
+    dev = loglikes.device if where == L.MFA_DEVICE else None
+    ali, pf, words, nw, tl, st = _alloc_outputs(int(fo[-1]), int(wo[-1]), n, dev)
+    ptrs = [_buf(x, dt)[1] for x, dt in ((ali, np.int32), (pf, np.float32), (words, np.int32))]
+    p2 = [_buf(x, dt)[1] for x, dt in ((nw, np.int32), (tl, np.float32), (st, np.int32))]
+    L.check(L.lib().mfa_align(engine._h, model._h, graphs._h, C.byref(opts), lp, fop, C.c_int32(n), ptrs[0], ptrs[1], ptrs[2],
+                              wo.ctypes.data_as(C.c_void_p), p2[0], p2[1], p2[2], C.c_int(where)))
+    return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
+
+
+def align_pcm(engine: Engine, model: DeviceModel, graphs: Graphs, pcm, sample_off, utt2spk, n_spk: int, mfcc: L.MfccOpts,
+              feat_mode: str = "deltas", lda=None, splice_ctx: int = 3, fmllr=None, cmvn_stats=None, apply_cmvn: bool = True,
+              align: Optional[L.AlignOpts] = None, gmm_impl: int = 0, workspace_bytes: int = 0, outputs=None) -> AlignResult:
+    """Fused hot path (mfa_align_pcm): PCM -> MFCC -> CMVN -> features -> log-likelihoods -> Viterbi."""
+    so, sop = _host(sample_off, np.int64)
+    n = so.shape[0] - 1
+    fo = np.zeros(n + 1, np.int64)
+    for u in range(n):
+        fo[u + 1] = fo[u] + num_frames(mfcc, so[u + 1] - so[u])
+    us, usp = _host(utt2spk, np.int32)
+    wo = np.zeros(n + 1, np.int64)
+    wo[1:] = np.cumsum(graphs.max_words())
+    fopts, keep = make_feat_opts(mfcc.num_ceps, feat_mode, lda, splice_ctx, fmllr, cmvn_stats, n_spk)
+    po = L.PipelineOpts(mfcc, fopts, align or align_opts(), int(apply_cmvn), int(gmm_impl), int(workspace_bytes))
+    k, pp, where = _buf(pcm, np.int16, "pcm")
+    dev = pcm.device if where == L.MFA_DEVICE else None
+    if outputs is None:
+        outputs = _alloc_outputs(int(fo[-1]), int(wo[-1]), n, dev)
+    ali, pf, words, nw, tl, st = outputs
+    ptrs = [_buf(x, dt)[1] for x, dt in ((ali, np.int32), (pf, np.float32), (words, np.int32))]
+    p2 = [_buf(x, dt)[1] for x, dt in ((nw, np.int32), (tl, np.float32), (st, np.int32))]
+    L.check(L.lib().mfa_align_pcm(engine._h, model._h, graphs._h, C.byref(po), pp, sop, usp, C.c_int32(n), C.c_int32(n_spk),
+                                  fo.ctypes.data_as(C.c_void_p), ptrs[0], ptrs[1], ptrs[2], wo.ctypes.data_as(C.c_void_p),
+                                  p2[0], p2[1], p2[2], C.c_int(where)))
+    return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
