@@ -828,7 +828,7 @@ def read_fst(f: BinaryIO) -> Fst:
 
 
 def write_fst(f: BinaryIO, fst: Fst):
-    f.write(struct.pack("<i", FST_MAGIC - (1 << 32)))
+    f.write(struct.pack("<I", FST_MAGIC))
     for s in ("vector", "standard"):
         f.write(struct.pack("<i", len(s)) + s.encode())
     f.write(struct.pack("<ii", 2, 0))

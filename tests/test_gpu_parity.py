@@ -1,0 +1,292 @@
+"""-m gpu: the CUDA hot path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): transition-id alignments identical on >= 99.9 % of frames, per-utterance
+log-likelihood and MFCC values within 1e-4 relative; integer/index outputs (words, statuses) exact."""
+import numpy as np
+import pytest
+
+from helpers import build_synth_scenario, gold, load_model, mono_sample_setup, oracle_align_all, oracle_features
+from mfa_b200 import engine as E, _lib as L
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = E.Engine(0)
+    yield e
+    e.close()
+
+
+def relmax(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(1e-30, np.abs(b).max()))
+
+
+def _cat(pcm_list):
+    off = np.zeros(len(pcm_list) + 1, np.int64)
+    off[1:] = np.cumsum([len(p) for p in pcm_list])
+    return (np.concatenate(pcm_list) if len(pcm_list) else np.zeros(0, np.int16)).astype(np.int16), off
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(snip_edges=False), dict(use_energy=True, energy_floor=1.0), dict(use_energy=True, raw_energy=False),
+                                dict(num_mel_bins=40, num_coefficients=20, low_frequency=0.0, high_frequency=-200.0, cepstral_lifter=0.0)])
+def test_mfcc_parity_ragged_batch(eng, kw):
+    g = gold()
+    a, b = g["acoustic_corpus_pcm"], g["cold_corpus_pcm"]
+    # ragged: full utterance, shorter than one window (0 frames with snip_edges), exactly one window, odd lengths, empty
+    pcm_list = [a, a[:399], a[1000:1400], b[:16001], np.zeros(0, np.int16), b[3333:77777], a[5:1234]]
+    pcm, off = _cat(pcm_list)
+    opts = E.mfcc_opts(**kw)
+    okw = dict(snip_edges=int(opts.snip_edges), use_energy=int(opts.use_energy), raw_energy=int(opts.raw_energy), energy_floor=opts.energy_floor,
+               num_mel_bins=opts.num_mel_bins, num_ceps=opts.num_ceps, low_freq=opts.low_freq, high_freq=opts.high_freq,
+               cepstral_lifter=opts.cepstral_lifter)
+    out, fo = eng.mfcc(pcm, off, opts)
+    ref = [O.mfcc(p, O.mfcc_opts(**okw)) for p in pcm_list]
+    assert [int(fo[i + 1] - fo[i]) for i in range(len(pcm_list))] == [r.shape[0] for r in ref]
+    refc = np.concatenate(ref)
+    assert relmax(out, refc) < 1e-4           # tolerance stated by north_star: MFCC within 1e-4 relative
+    # also against the independent torchaudio port for the default options
+    if not kw:
+        assert relmax(out[: 2670], g["ta_mfcc_snip"]) < 1e-4
+
+
+def test_mfcc_device_buffers_and_linearity(eng):
+    import torch
+    g = gold()
+    pcm = g["acoustic_corpus_pcm"][:160000]
+    off = np.asarray([0, 50000, 160000], np.int64)
+    host, fo = eng.mfcc(pcm, off, E.mfcc_opts())
+    dev, fo2 = eng.mfcc(torch.from_numpy(pcm.copy()).cuda(), off, E.mfcc_opts())
+    eng.sync()
+    assert np.array_equal(fo, fo2) and np.array_equal(host, dev.cpu().numpy())
+    # size-independent property: scaling the waveform by 2 shifts c0 by sqrt(23)*2*log(2)*lifter0 and leaves c1.. unchanged
+    half = (pcm // 2 * 2).astype(np.int16)
+    o1, _ = eng.mfcc((half // 2).astype(np.int16), off, E.mfcc_opts())
+    o2, _ = eng.mfcc(half, off, E.mfcc_opts())
+    assert np.allclose(o2[:, 1:], o1[:, 1:], atol=2e-3)
+    assert np.allclose(o2[:, 0] - o1[:, 0], np.sqrt(23.0) * 2 * np.log(2.0), atol=2e-3)
+
+
+def test_cmvn_and_feature_pipeline_parity(eng):
+    g = gold()
+    a, b = g["acoustic_corpus_pcm"], g["cold_corpus_pcm"]
+    pcm_list = [a[:80000], b[:64000], a[80000:200000], b[64000:], a[200000:200650]]
+    utt2spk = np.asarray([0, 1, 0, 1, 2], np.int32)
+    rng = np.random.default_rng(0)
+    lda = g["g2p_lda"]
+    fm = (np.eye(40, 41)[None] + 0.05 * rng.standard_normal((3, 40, 41))).astype(np.float32)
+    pcm, off = _cat(pcm_list)
+    raw, fo = eng.mfcc(pcm, off, E.mfcc_opts())
+    stats = eng.cmvn_stats(raw, fo, utt2spk, 3)
+    raw_o, stats_o, feats_d = oracle_features(pcm_list, utt2spk, 3, "deltas")
+    assert relmax(stats, stats_o) < 1e-5      # f64 sums of f32 values that themselves agree to ~1e-6
+    # feature kernels are checked on the ORACLE's MFCCs and stats so that only the op under test differs
+    rawc = np.concatenate(raw_o)
+    out_d = eng.features(rawc, fo, "deltas", cmvn_stats=stats_o, utt2spk=utt2spk, n_spk=3)
+    assert relmax(out_d, np.concatenate(feats_d)) < 1e-6
+    _, _, feats_l = oracle_features(pcm_list, utt2spk, 3, "lda", lda=lda, fmllr=fm)
+    out_l = eng.features(rawc, fo, "lda", lda=lda, fmllr=fm, cmvn_stats=stats_o, utt2spk=utt2spk, n_spk=3)
+    assert relmax(out_l, np.concatenate(feats_l)) < 1e-5
+    lda92 = np.concatenate([lda, rng.standard_normal((40, 1)).astype(np.float32)], 1)
+    _, _, feats_a = oracle_features(pcm_list, utt2spk, 3, "lda", lda=lda92)
+    out_a = eng.features(rawc, fo, "lda", lda=lda92, cmvn_stats=stats_o, utt2spk=utt2spk, n_spk=3)
+    assert relmax(out_a, np.concatenate(feats_a)) < 1e-5
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("which", ["mono", "g2p"])
+def test_gmm_loglikes_parity(eng, impl, which):
+    tm, am, _ = load_model(which)
+    rng = np.random.default_rng(2)
+    means = am.means()
+    # frames drawn around the model's own Gaussians (+ a few outliers), ragged count to exercise tile tails
+    pick = rng.integers(0, am.NumGauss(), 777)
+    x = (means[pick] + rng.standard_normal((777, am.dim)) * np.sqrt(am.variances()[pick])).astype(np.float32)
+    x[::97] *= 3.0
+    dm = E.DeviceModel(eng, tm, am)
+    ll = dm.loglikes(x, impl=impl)
+    ref = O.gmm_loglikes(O.GmmModel.from_am(am), x)
+    # per-value: 1e-4 relative to the magnitude of the log-likelihoods (north_star's tolerance for log-likelihoods)
+    assert np.abs(ll - ref).max() <= 1e-4 * np.abs(ref).mean(), (np.abs(ll - ref).max(), np.abs(ref).mean())
+    dm.close()
+
+
+def test_boost_silence_shifts_only_those_pdfs(eng):
+    tm, am, _ = load_model("g2p")
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((64, am.dim)).astype(np.float32)
+    dm = E.DeviceModel(eng, tm, am)
+    base = dm.loglikes(x, impl=1)
+    dm.boost_pdfs(1.5, [0, 7])
+    b = dm.loglikes(x, impl=1)
+    d = b - base
+    assert np.allclose(d[:, [0, 7]], np.log(1.5), atol=1e-4) and np.abs(np.delete(d, [0, 7], axis=1)).max() == 0.0
+    dm.close()
+
+
+def _gpu_align_from_oracle_loglikes(eng, sc, fsts_batch, beam, retry_beam):
+    tm, am = sc["tm"], sc["am"]
+    dm = E.DeviceModel(eng, tm, am)
+    graphs = E.Graphs(fsts_batch, tm, 1.0, 0.1)
+    g = O.GmmModel.from_am(am)
+    ll = np.concatenate([O.gmm_loglikes(g, f) for f in sc["feats"]])
+    res = E.align_loglikes(eng, dm, graphs, ll, sc["frame_off"], E.align_opts(0.1, beam, retry_beam))
+    dm.close()
+    return res
+
+
+@pytest.mark.parametrize("triphone,beam,retry", [(False, 10.0, 40.0), (True, 10.0, 40.0), (True, 200.0, 0.0), (False, 2.0, 8.0)])
+def test_viterbi_parity_with_oracle(eng, triphone, beam, retry):
+    sc = build_synth_scenario(seconds=60.0, seed=21, triphone=triphone, n_phones=10, n_words=50, target_pdfs=90, gauss_per_pdf=2)
+    batch = E.GraphCompiler(sc["tm"], sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts)
+    fsts = batch.export()
+    ref = oracle_align_all(sc, fsts, beam, retry)
+    res = _gpu_align_from_oracle_loglikes(eng, sc, batch, beam, retry)
+    same = total = 0
+    for u, r in enumerate(ref):
+        got = res.utterance(u)
+        assert got["status"] == r["status"], (u, got["status"], r["status"])
+        if r["status"] >= 2:
+            continue
+        same += int((got["ali"] == r["ali"]).sum()); total += len(r["ali"])
+        assert list(got["words"]) == list(r["words"])
+        assert abs(got["like"] - r["like"]) <= 1e-4 * abs(r["like"])
+        assert np.allclose(got["per_frame"], r["per_frame"], rtol=1e-4, atol=1e-3)
+    assert total > 0 and same / total >= 0.999, same / total
+
+
+def test_viterbi_edge_cases(eng):
+    sc = build_synth_scenario(seconds=12.0, seed=4, n_phones=6, n_words=20, gauss_per_pdf=2)
+    tm, am = sc["tm"], sc["am"]
+    from mfa_b200.kaldi_io import Fst
+    fsts = E.GraphCompiler(tm, sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts).export()
+    n = len(fsts)
+    empty = Fst(-1, 0, *(np.zeros(0, np.int32) for _ in range(4)), np.zeros(0, np.float32), np.zeros(0, np.float32))
+    fsts2 = [fsts[0], empty, fsts[1], fsts[2 % n]]
+    g = O.GmmModel.from_am(am)
+    lls = [O.gmm_loglikes(g, sc["feats"][0]), O.gmm_loglikes(g, sc["feats"][1]), O.gmm_loglikes(g, sc["feats"][1])[:0],
+           O.gmm_loglikes(g, sc["feats"][2 % n])[:4]]
+    fo = np.zeros(5, np.int64)
+    fo[1:] = np.cumsum([x.shape[0] for x in lls])
+    dm = E.DeviceModel(eng, tm, am)
+    graphs = E.Graphs(E.FstBatch.from_fsts(fsts2), tm)
+    res = E.align_loglikes(eng, dm, graphs, np.concatenate(lls), fo, E.align_opts())
+    assert int(res.status[0]) in (0, 1) and [int(s) for s in res.status[1:]] == [3, 4, 2]
+    dm.close()
+
+
+def test_epsilon_arcs_are_supported(eng):
+    """Graphs read from a Kaldi fsts.ark may keep input-epsilon arcs; splice one into every graph and compare with the oracle."""
+    sc = build_synth_scenario(seconds=20.0, seed=9, n_phones=6, n_words=20, gauss_per_pdf=2)
+    tm = sc["tm"]
+    from mfa_b200.kaldi_io import Fst
+    fsts = E.GraphCompiler(tm, sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts).export()
+    mod = []
+    for f in fsts:
+        # new start state with an epsilon arc (carrying a weight) into the old start, and an epsilon arc into a new final state
+        S = f.num_states
+        fin_states = np.where(np.isfinite(f.finals))[0]
+        src = np.concatenate([f.arc_src, [S], fin_states]).astype(np.int32)
+        dst = np.concatenate([f.arc_dst, [f.start], np.full(len(fin_states), S + 1)]).astype(np.int32)
+        il = np.concatenate([f.arc_ilabel, [0], np.zeros(len(fin_states))]).astype(np.int32)
+        ol = np.concatenate([f.arc_olabel, [0], np.zeros(len(fin_states))]).astype(np.int32)
+        w = np.concatenate([f.arc_weight, [0.25], f.finals[fin_states]]).astype(np.float32)
+        finals = np.full(S + 2, np.inf, np.float32)
+        finals[S + 1] = 0.0
+        mod.append(Fst(S, S + 2, src, il, ol, dst, w, finals))
+    ref = oracle_align_all(sc, mod, 10.0, 40.0)
+    res = _gpu_align_from_oracle_loglikes(eng, sc, E.FstBatch.from_fsts(mod), 10.0, 40.0)
+    base = oracle_align_all(sc, fsts, 10.0, 40.0)
+    for u, r in enumerate(ref):
+        got = res.utterance(u)
+        assert got["status"] == r["status"] and (got["ali"] == r["ali"]).mean() >= 0.999
+        assert abs(got["like"] - r["like"]) <= 1e-4 * abs(r["like"])
+        assert abs(r["like"] - (base[u]["like"] - 0.25 / 0.1)) <= 1e-4 * abs(r["like"])
+
+
+def test_fused_pipeline_config1_sample(eng, tmp_path):
+    """Config 1: the reference's sample utterance, its fixture monophone model and dictionary, PCM in -> alignment out."""
+    ms = mono_sample_setup(tmp_path)
+    tm, am, lex = ms["tm"], ms["am"], ms["lex"]
+    ids = lex.to_int(ms["text"])
+    batch = E.GraphCompiler(tm, ms["tree"], lex).compile([ids, ids[:20]])
+    fsts = batch.export()
+    pcm_list = [ms["pcm"], ms["pcm"][:140000]]
+    pcm, off = _cat(pcm_list)
+    u2s = np.asarray([0, 0], np.int32)
+    dm = E.DeviceModel(eng, tm, am)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    for impl in (1, 0):
+        res = E.align_pcm(eng, dm, graphs, pcm, off, u2s, 1, E.mfcc_opts(), "deltas", gmm_impl=impl)
+        _, _, feats = oracle_features(pcm_list, u2s, 1, "deltas")
+        g = O.GmmModel.from_am(am)
+        tc = -tm.scaled_transition_log_probs(1.0, 0.1)
+        for u in range(2):
+            r = O.align(fsts[u], tc, g, tm.tid2pdf, feats[u], feats[u].shape[0])
+            got = res.utterance(u)
+            assert got["status"] == r["status"]
+            if r["status"] < 2:
+                assert (got["ali"] == r["ali"]).mean() >= 0.999
+                assert abs(got["like"] - r["like"]) <= 1e-4 * abs(r["like"])
+                assert list(got["words"]) == list(r["words"])
+    dm.close()
+
+
+def test_fused_pipeline_triphone_lda_fmllr_chunked(eng):
+    """Config 2/3 shape in miniature: splice+LDA(+fMLLR) features, triphone tree, several speakers, forced small workspace
+    so the chunk loop runs more than once; device-resident PCM."""
+    import torch
+    sc = build_synth_scenario(seconds=90.0, seed=33, triphone=True, n_phones=10, n_words=60, target_pdfs=150, gauss_per_pdf=4, use_lda=True, n_spk=4)
+    tm, am, c = sc["tm"], sc["am"], sc["corpus"]
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    fsts = batch.export()
+    ref = oracle_align_all(sc, fsts, 10.0, 40.0)
+    dm = E.DeviceModel(eng, tm, am)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    res = E.align_pcm(eng, dm, graphs, torch.from_numpy(c.pcm).cuda(), c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"],
+                      workspace_bytes=6 << 20)
+    eng.sync()
+    ali = res.ali.cpu().numpy(); st = res.status.cpu().numpy(); tl = res.total_like.cpu().numpy()
+    same = total = 0
+    for u, r in enumerate(ref):
+        assert int(st[u]) == r["status"]
+        if r["status"] >= 2:
+            continue
+        a = ali[res.frame_off[u]:res.frame_off[u + 1]]
+        same += int((a == r["ali"]).sum()); total += len(a)
+        assert abs(float(tl[u]) - r["like"]) <= 1e-4 * abs(r["like"])
+    assert same / total >= 0.999, same / total
+    # per-speaker fMLLR path: identity transforms must reproduce the result exactly
+    fm = np.tile(np.eye(40, 41, dtype=np.float32)[None], (c.n_spk, 1, 1))
+    res2 = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"], fmllr=fm)
+    assert np.array_equal(res2.ali, ali) and np.array_equal(res2.status, st)
+    dm.close()
+
+
+def test_acc_stats_parity(eng):
+    sc = build_synth_scenario(seconds=30.0, seed=8, n_phones=8, n_words=30, gauss_per_pdf=3)
+    tm, am = sc["tm"], sc["am"]
+    fsts = E.GraphCompiler(tm, sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts).export()
+    ref = oracle_align_all(sc, fsts, 10.0, 40.0)
+    g = O.GmmModel.from_am(am)
+    accs = None
+    dm = E.DeviceModel(eng, tm, am)
+    dm.acc_zero()
+    for u, r in enumerate(ref):
+        if r["status"] >= 2:
+            continue
+        accs = O.acc_stats(g, tm.tid2pdf, sc["feats"][u], r["ali"], tm.num_tids, accs)
+        dm.acc_stats(sc["feats"][u], r["ali"])
+    got = dm.acc_read()
+    assert got["frames"] == accs["frames"] and np.array_equal(got["trans"], accs["trans"])     # integer counts: exact
+    assert abs(got["like"] - accs["like"][0]) <= 1e-5 * abs(accs["like"][0])
+    assert np.allclose(got["occ"], accs["occ"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(got["mean"], accs["mean"], rtol=1e-4, atol=1e-3) and np.allclose(got["var"], accs["var"], rtol=1e-4, atol=1e-2)
+    # linearity: accumulating the same frames twice doubles everything
+    for u, r in enumerate(ref):
+        if r["status"] < 2:
+            dm.acc_stats(sc["feats"][u], r["ali"])
+    got2 = dm.acc_read()
+    assert np.allclose(got2["occ"], 2 * got["occ"], rtol=1e-9) and got2["frames"] == 2 * got["frames"]
+    dm.close()

@@ -1,0 +1,147 @@
+"""Host training-graph compiler (csrc/graph.cc) through the C ABI: path-set equality with a brute-force enumeration of the
+lexicon semantics, context-dependent pdf selection via the tree, reorder=true self-loop placement, error behaviour."""
+import math
+
+import numpy as np
+import pytest
+
+from mfa_b200 import engine as E, kaldi_io as K, lexicon as LX, synth as SY, _lib as L
+
+
+def _setup(triphone, seed=0, position_dependent=False):
+    rng = np.random.default_rng(seed)
+    phones = ["a", "b", "c", "d"]
+    pt = LX.make_phone_table(phones, ("sil", "spn"), position_dependent)
+    prons = {"x": [LX.Pron(["a", "b"]), LX.Pron(["a", "c", "d"], 0.5)], "y": [LX.Pron(["d"])], "z": [LX.Pron(["b", "a"]), LX.Pron(["c", "a"], 0.25)]}
+    lex = LX.Lexicon(prons, pt, silence_probability=0.3, initial_silence_probability=0.6, position_dependent_phones=position_dependent)
+    topo = SY.make_topology(pt)
+    # a smaller non-Bakis silence model (skip + no self-loop on state 1) keeps the exhaustive path enumeration tractable
+    topo.entries[1] = [K.HmmState(0, 0, [(0, 0.5), (1, 0.25), (2, 0.25)]), K.HmmState(1, 1, [(2, 1.0)]), K.HmmState(2, 2, [(2, 0.6), (3, 0.4)]),
+                       K.HmmState(-1, -1, [])]
+    tree, n_pdfs = SY.make_tree(rng, topo, triphone, 40)
+    tm = SY.make_transition_model(topo, tree, n_pdfs)
+    return lex, pt, topo, tree, tm
+
+
+def _paths(fst, max_paths=200000):
+    """All simple start->final paths over non-self-loop arcs: yields (tids, olabels, cost)."""
+    out_arcs = [[] for _ in range(fst.num_states)]
+    for a in range(fst.arc_src.shape[0]):
+        if fst.arc_src[a] != fst.arc_dst[a]:
+            out_arcs[fst.arc_src[a]].append(a)
+    res = []
+    stack = [(fst.start, [], 0.0, {fst.start})]
+    while stack:
+        s, arcs, c, seen = stack.pop()
+        if np.isfinite(fst.finals[s]):
+            res.append((arcs, c + float(fst.finals[s])))
+            assert len(res) < max_paths
+        for a in out_arcs[s]:
+            d = int(fst.arc_dst[a])
+            if d in seen:
+                continue
+            stack.append((d, arcs + [a], c + float(fst.arc_weight[a]), seen | {d}))
+    return res
+
+
+def _brute(lex, words):
+    """(phone-id sequence) -> cost, straight from the lexicon definition (lexicon.text.fst layout)."""
+    sil = lex.phone_table["sil"]
+    c = lambda p: -math.log(p)
+    out = {}
+
+    def rec(i, seq, cost):
+        if i == len(words):
+            out[tuple(seq)] = cost
+            return
+        for pr in range(lex._arrs[0][words[i]], lex._arrs[0][words[i] + 1]):
+            ph = [int(x) for x in lex._arrs[2][lex._arrs[1][pr]:lex._arrs[1][pr + 1]]]
+            pc = float(lex._arrs[3][pr])
+            rec(i + 1, seq + ph, cost + pc + c(1 - lex.silence_probability))
+            rec(i + 1, seq + ph + [sil], cost + pc + c(lex.silence_probability))
+
+    rec(0, [], c(1 - lex.initial_silence_probability))
+    rec(0, [sil], c(lex.initial_silence_probability))
+    return out
+
+
+@pytest.mark.parametrize("triphone,posdep", [(False, False), (True, False), (True, True)])
+def test_path_set_equals_lexicon_language(triphone, posdep):
+    lex, pt, topo, tree, tm = _setup(triphone, position_dependent=posdep)
+    words = [lex.word_table[w] for w in ("x", "z", "y")]
+    fst = E.GraphCompiler(tm, tree, lex).compile([words]).export()[0]
+    brute = _brute(lex, words)
+    got = {}
+    for arcs, cost in _paths(fst):
+        tids = [int(fst.arc_ilabel[a]) for a in arcs]
+        assert all(t > 0 for t in tids)
+        ols = [int(fst.arc_olabel[a]) for a in arcs if fst.arc_olabel[a] != 0]
+        assert ols == words
+        # split into phone instances at transitions into the HMM's final state
+        seq, inst, cur = [], [], []
+        for t in tids:
+            cur.append(t)
+            if tm.is_final_tid[t]:
+                seq.append(int(tm.tid2phone[t])); inst.append(cur); cur = []
+        assert not cur
+        # every instance: consistent phone, consecutive HMM path starting in state 0, pdfs picked by the tree for (l, p, r)
+        for k, ts in enumerate(inst):
+            ph = seq[k]
+            l = seq[k - 1] if k > 0 else 0
+            r = seq[k + 1] if k + 1 < len(seq) else 0
+            hs = 0
+            for t in ts:
+                tstate = tm.id2state[t]
+                p_, h_, fpdf, _ = tm.tuples[tstate - 1]
+                assert p_ == ph and h_ == hs and not tm.is_self_loop[t]
+                st = topo.states_for(ph)[hs]
+                assert fpdf == tree.lookup([l, ph, r] if triphone else [ph], st.forward_pdf_class)
+                hs = st.transitions[t - tm.state2id[tstate]][0]
+        key = tuple(seq)
+        if key in got:
+            assert abs(got[key] - cost) < 1e-4
+        got[key] = cost
+    assert set(got) == set(brute)
+    for k in brute:
+        assert abs(got[k] - brute[k]) < 1e-4, (k, got[k], brute[k])
+
+
+def test_self_loops_follow_reorder_convention():
+    lex, pt, topo, tree, tm = _setup(True)
+    fst = E.GraphCompiler(tm, tree, lex).compile([[lex.word_table["x"], lex.word_table["y"]]]).export()[0]
+    loops = {}
+    for a in range(fst.arc_src.shape[0]):
+        if fst.arc_src[a] == fst.arc_dst[a]:
+            assert fst.arc_dst[a] not in loops, "one self-loop per state"
+            loops[int(fst.arc_dst[a])] = int(fst.arc_ilabel[a])
+            assert tm.is_self_loop[fst.arc_ilabel[a]] and fst.arc_weight[a] == 0 and fst.arc_olabel[a] == 0
+    # reorder=true: the self-loop on a state belongs to the transition-state of every arc ENTERING it
+    for a in range(fst.arc_src.shape[0]):
+        s, d, t = int(fst.arc_src[a]), int(fst.arc_dst[a]), int(fst.arc_ilabel[a])
+        if s == d:
+            continue
+        sl = tm.self_loop_tid[tm.id2state[t]]
+        assert loops.get(d, 0) == sl
+    assert fst.start not in loops
+
+
+def test_batch_compile_threads_and_errors():
+    lex, pt, topo, tree, tm = _setup(False)
+    gc = E.GraphCompiler(tm, tree, lex)
+    seqs = [[lex.word_table["x"]], [], [lex.word_table["y"], lex.word_table["z"], lex.word_table["x"]]] * 7
+    a = gc.compile(seqs, n_threads=1).export()
+    b = gc.compile(seqs, n_threads=4).export()
+    for f1, f2 in zip(a, b):
+        assert np.array_equal(f1.arc_ilabel, f2.arc_ilabel) and np.array_equal(f1.arc_weight, f2.arc_weight) and f1.start == f2.start
+    # empty transcript: optional silence only
+    e = a[1]
+    assert e.start >= 0 and np.isfinite(e.finals).any()
+    with pytest.raises(L.MfaError):
+        gc.compile([[len(lex.word_table) + 5]])
+    # round trip through the OpenFst binary container used by fsts.*.ark
+    import io
+    buf = io.BytesIO()
+    K.write_fst(buf, a[2])
+    back = K.read_fst(io.BytesIO(buf.getvalue()))
+    rt = E.FstBatch.from_fsts([back]).export()[0]
+    assert rt.num_states == a[2].num_states and np.array_equal(np.sort(rt.arc_ilabel), np.sort(a[2].arc_ilabel))
