@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds aligned per second (xRT) for MFA's alignment hot path on B200.
+
+A "step" is one pass of the fused hot path (PCM -> MFCC -> CMVN -> splice+LDA -> all-pdf GMM log-likelihoods ->
+beam Viterbi) over the whole per-GPU workload: BASELINE.json configs[1], a triphone LDA-shaped GMM-HMM (~4k pdfs,
+~40k Gaussians, D=40) aligning 10 h of synthetic LibriSpeech-shaped 16 kHz audio (per GPU; weak scaling).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # the CPU oracle port on the host cores (reference arm)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec aligned/sec (xRT)"
+UNIT = "audio-s/s"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0), tf_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_pass(sc, utts, cores: int):
+    """The oracle port (oracle/oracle.c: scalar restatement of the Kaldi path MFA calls through kalpy) over `utts`,
+    `cores` host threads (ctypes releases the GIL).  Returns (wall seconds, audio seconds, n_ok)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    c = sc.corpus
+    g = O.GmmModel.from_am(sc.am)
+    tid_cost = -sc.tm.scaled_transition_log_probs(1.0, 0.1)
+    fsts = sc._fsts
+    csr = {u: O.FstCsr(fsts[u]) for u in utts}
+    opts = O.mfcc_opts()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        raw = dict(zip(utts, ex.map(lambda u: O.mfcc(c.pcm[c.sample_off[u]:c.sample_off[u + 1]], opts), utts)))
+        spk = sorted({int(c.utt2spk[u]) for u in utts})
+        stats = {s: O.cmvn_stats([raw[u] for u in utts if c.utt2spk[u] == s]) for s in spk}
+
+        def one(u):
+            x = O.cmvn_apply(raw[u], stats[int(c.utt2spk[u])])
+            x = O.transform(O.splice(x, 3, 3), sc.lda) if sc.feat_mode == "lda" else O.add_deltas(x)
+            r = O.align(csr[u], tid_cost, g, sc.tm.tid2pdf, x, x.shape[0], 0.1, 10.0, 40.0)
+            return r["status"]
+        st = list(ex.map(one, utts))
+    dt = time.perf_counter() - t0
+    secs = float(sum(c.sample_off[u + 1] - c.sample_off[u] for u in utts)) / 16000.0
+    return dt, secs, sum(1 for s in st if s < 2)
+
+
+def pick_sample(sc, audio_seconds: float):
+    c = sc.corpus
+    utts, tot = [], 0.0
+    for u in range(c.n_utts):
+        utts.append(u)
+        tot += (c.sample_off[u + 1] - c.sample_off[u]) / 16000.0
+        if tot >= audio_seconds:
+            break
+    return utts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hours", type=float, default=10.0, help="audio hours per GPU (configs[1] = 10)")
+    ap.add_argument("--pdfs", type=int, default=4000)
+    ap.add_argument("--gauss-per-pdf", type=int, default=10)
+    ap.add_argument("--gmm-impl", type=int, default=0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=0.0, help="audio seconds for the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workspace-gb", type=float, default=16.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    import torch
+    import __graft_entry__ as G
+    if rank == 0:
+        G.build()
+    from mfa_b200 import engine as E, scenario as SC
+
+    dist = None
+    if world > 1 and args.impl == "b200":
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    eng = E.Engine(local_rank)
+    cores = os.cpu_count() or 1
+    seconds = args.hours * 3600.0
+    if args.impl == "reference":
+        # the reference arm only needs a bounded sample of the same workload; build a smaller corpus with the same model shape
+        seconds = min(seconds, 1800.0)
+    t0 = time.time()
+    sc = SC.build(eng, seconds, seed=1234 + rank, target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
+                  synth_device=dev, log=log if rank == 0 else None)
+    c = sc.corpus
+    audio_s = c.seconds
+    n_frames = int(sc.frame_off[-1])
+    workload = (f"configs[1]: triphone LDA-shaped GMM-HMM ({sc.am.NumPdfs()} pdfs, {sc.am.NumGauss()} Gaussians, D={sc.am.dim}), "
+                f"{audio_s / 3600:.2f} h synthetic 16 kHz audio per GPU ({c.n_utts} utts), beam 10 / retry 40")
+    config = {"workload": workload, "hours_per_gpu": round(audio_s / 3600, 3), "utterances_per_gpu": c.n_utts, "pdfs": sc.am.NumPdfs(),
+              "gaussians": sc.am.NumGauss(), "dim": sc.am.dim, "beam": 10, "retry_beam": 40, "parallelism": f"utterance-sharded x{world}",
+              "l2": "inputs larger than L2 (PCM >> 126 MB per step); no explicit flush"}
+    log(f"setup {time.time() - t0:.1f}s")
+
+    if args.impl == "reference":
+        sc._fsts = sc.batch.export()
+        sample_s = args.cpu_sample_seconds or 600.0
+        utts = pick_sample(sc, sample_s)
+        for _ in range(args.warmup):
+            cpu_reference_pass(sc, utts[: max(1, len(utts) // 8)], cores)
+        times = []
+        for _ in range(args.steps):
+            dt, secs, ok = cpu_reference_pass(sc, utts, cores)
+            times.append(dt)
+        T = float(np.sum(times))
+        val = secs * args.steps / T
+        sample = f"{len(utts)} utterances / {secs:.0f} audio-s of the same synthetic workload per step; oracle port (kalpy/Kaldi not installable offline)"
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * T / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---- device-resident arm -----------------------------------------------------------------------------------
+    mo = E.mfcc_opts()
+    wo_total = int(np.cumsum(sc.graphs.max_words())[-1])
+    d_pcm = torch.from_numpy(c.pcm).to(dev)
+    outs = E._alloc_outputs(n_frames, wo_total, c.n_utts, dev)
+    ws = int(args.workspace_gb * (1 << 30))
+
+    def step_device():
+        return E.align_pcm(eng, sc.model, sc.graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda, gmm_impl=args.gmm_impl,
+                           workspace_bytes=ws, outputs=outs)
+
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(max(0, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gmm_ms = gmm_n = gmm_rows = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res = step_device()
+        ms, n, rows = 0.0, 0, 0
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    gmm_ms, gmm_n, gmm_rows = eng.gmm_timing()   # K2 launches of the LAST step (event pairs on the engine stream)
+    launches = eng.launch_count - l0
+    clocks = sampler.stop()
+    st = res.status.cpu().numpy()
+    n_ok = int((st < 2).sum())
+    if dist is not None:
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max = float(t.item())
+        a = torch.tensor([audio_s, float(launches), float(n_ok), float(c.n_utts)], device=dev, dtype=torch.float64)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        audio_total, launches_total, ok_total, utts_total = (float(x) for x in a.tolist())
+    else:
+        dev_ms_max, audio_total, launches_total, ok_total, utts_total = dev_ms, audio_s, float(launches), float(n_ok), float(c.n_utts)
+    value = audio_total * args.steps / (dev_ms_max / 1000.0)
+
+    # ---- end-to-end arm: host (pinned) PCM in, host results out, through the same C-ABI call ---------------------
+    h_pcm = torch.from_numpy(c.pcm).pin_memory()
+    h_outs = [torch.zeros(x.shape, dtype=x.dtype).pin_memory() for x in outs]
+    h_np = tuple(x.numpy() for x in h_outs)
+
+    def step_host():
+        return E.align_pcm(eng, sc.model, sc.graphs, h_pcm.numpy(), c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda,
+                           gmm_impl=args.gmm_impl, workspace_bytes=ws, outputs=h_np)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()   # returns after the D2H copies have landed (MFA_HOST contract)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = audio_total * args.steps / e2e_s
+    h2d = int(c.pcm.nbytes)
+    d2h = int(sum(x.numel() * x.element_size() for x in h_outs))
+
+    # ---- roofline of the dominant kernel (K2) --------------------------------------------------------------------
+    pk = measured_peaks()
+    flops_per_row = 2.0 * (2 * sc.am.dim + 1) * sc.am.NumGauss()
+    roof = None
+    if gmm_n > 0 and gmm_ms > 0:
+        per_launch_flops = flops_per_row * gmm_rows / gmm_n
+        avg_ms = gmm_ms / gmm_n
+        achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
+        roof = {"kernel": "gmm_loglikes (K2)", "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                "launches_per_step": gmm_n, "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": per_launch_flops,
+                "share_of_step": gmm_ms / (dev_ms / args.steps)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches_total),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roof, "aligned_utterances": int(ok_total), "utterances": int(utts_total)}
+    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+        try:
+            sc._fsts = sc.batch.export()
+            sample_s = args.cpu_sample_seconds or 240.0
+            utts = pick_sample(sc, sample_s)
+            cpu_reference_pass(sc, utts[: max(1, len(utts) // 10)], cores)
+            dt, secs, ok = cpu_reference_pass(sc, utts, cores)
+            line["cpu_baseline"] = {"value": secs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{len(utts)} utterances / {secs:.0f} audio-s of the same workload, {dt:.1f} s wall; oracle port"}
+        except Exception as ex:  # the baseline is reported, never required
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex}"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,6 +63,21 @@ def num_frames(opts: L.MfccOpts, n_samples: int) -> int:
     return int(L.lib().mfa_mfcc_num_frames(C.byref(opts), C.c_int64(int(n_samples))))
 
 
+def frame_offsets(opts: L.MfccOpts, sample_off) -> np.ndarray:
+    """Vectorised mfa_mfcc_num_frames over a batch: sample_off[n+1] -> frame_off[n+1]."""
+    so = np.asarray(sample_off, dtype=np.int64)
+    n = so[1:] - so[:-1]
+    shift = int(np.float32(opts.sample_frequency) * np.float32(0.001) * np.float32(opts.frame_shift_ms))
+    length = int(np.float32(opts.sample_frequency) * np.float32(0.001) * np.float32(opts.frame_length_ms))
+    if opts.snip_edges:
+        t = np.where(n < length, 0, 1 + (n - length) // shift)
+    else:
+        t = (n + shift // 2) // shift
+    fo = np.zeros(so.shape[0], dtype=np.int64)
+    fo[1:] = np.cumsum(t)
+    return fo
+
+
 class Engine:
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
@@ -104,9 +119,7 @@ class Engine:
     def mfcc(self, pcm, sample_off, opts: L.MfccOpts, out=None):
         so, sop = _host(sample_off, np.int64)
         n = so.shape[0] - 1
-        fo = np.zeros(n + 1, dtype=np.int64)
-        for u in range(n):
-            fo[u + 1] = fo[u] + num_frames(opts, so[u + 1] - so[u])
+        fo = frame_offsets(opts, so)
         keep, pp, where = _buf(pcm, np.int16, "pcm")
         if out is None:
             if where == L.MFA_DEVICE:
@@ -459,9 +472,7 @@ def align_pcm(engine: Engine, model: DeviceModel, graphs: Graphs, pcm, sample_of
     """Fused hot path (mfa_align_pcm): PCM -> MFCC -> CMVN -> features -> log-likelihoods -> Viterbi."""
     so, sop = _host(sample_off, np.int64)
     n = so.shape[0] - 1
-    fo = np.zeros(n + 1, np.int64)
-    for u in range(n):
-        fo[u + 1] = fo[u] + num_frames(mfcc, so[u + 1] - so[u])
+    fo = frame_offsets(mfcc, so)
     us, usp = _host(utt2spk, np.int32)
     wo = np.zeros(n + 1, np.int64)
     wo[1:] = np.cumsum(graphs.max_words())

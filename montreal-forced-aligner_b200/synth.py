@@ -148,11 +148,11 @@ def make_corpus(seconds: float, seed: int = SEED, n_phones: int = 40, n_words: i
         for k in range(3):
             f = torch.repeat_interleave(torch.from_numpy(fr[:, k]).to(tdev, torch.float32), rep)
             a = torch.repeat_interleave(torch.from_numpy(par[:, 3 + k]).to(tdev, torch.float32), rep)
-            phase = torch.cumsum(f.double() * (2 * math.pi / sr), 0).float()
+            phase = torch.remainder(torch.cumsum(f.double() * (2 * math.pi / sr), 0), 2 * math.pi).float()
             out += a * torch.sin(phase)
             del f, a, phase
         f0 = torch.repeat_interleave(torch.from_numpy(spk_f0[seg_spk]).to(tdev, torch.float32), rep)
-        out *= 0.6 + 0.4 * torch.sin(torch.cumsum(f0.double() * (2 * math.pi / sr), 0).float())
+        out *= 0.6 + 0.4 * torch.sin(torch.remainder(torch.cumsum(f0.double() * (2 * math.pi / sr), 0), 2 * math.pi).float())
         del f0
         nz = torch.repeat_interleave(torch.from_numpy(par[:, 6]).to(tdev, torch.float32), rep)
         out += nz * torch.randn(N, device=tdev, generator=g)
@@ -308,26 +308,41 @@ def make_transition_model(topo: Topology, tree: ContextDependency, n_pdfs: int) 
 
 def frame_pdfs_from_truth(corpus: SynthCorpus, topo: Topology, tree: ContextDependency, frame_off: np.ndarray, shift: int = 160,
                           win: int = 400) -> np.ndarray:
-    """pdf id per frame from the true segmentation (each phone split evenly over its emitting HMM states; snip_edges framing)."""
+    """pdf id per frame from the true segmentation (each phone split evenly over three of its emitting HMM states;
+    snip_edges framing).  Tree look-ups are done once per distinct (left, phone, right) triple."""
     out = np.zeros(int(frame_off[-1]), dtype=np.int32)
     tri = tree.N == 3
+    nid = int(topo.phone2idx.shape[0])
+    ph_all, l_all, r_all = [], [], []
+    for segs in corpus.truth:
+        ph = segs[:, 0]
+        ph_all.append(ph)
+        l_all.append(np.concatenate([[0], ph[:-1]]))
+        r_all.append(np.concatenate([ph[1:], [0]]))
+    ph_c, l_c, r_c = np.concatenate(ph_all), np.concatenate(l_all), np.concatenate(r_all)
+    if not tri:
+        l_c = np.zeros_like(l_c)
+        r_c = np.zeros_like(r_c)
+    key = (l_c * nid + ph_c) * nid + r_c
+    uk, inv = np.unique(key, return_inverse=True)
+    table = np.zeros((len(uk), 3), dtype=np.int32)
+    for i, k in enumerate(uk):
+        r = int(k % nid); ph = int((k // nid) % nid); l = int(k // (nid * nid))
+        sts = topo.states_for(ph)[:-1]
+        if len(sts) == 5:
+            sts = [sts[0], sts[2], sts[4]]
+        table[i] = [tree.lookup([l, ph, r] if tri else [ph], s.forward_pdf_class) for s in sts]
+    pdfs_seg_all = table[inv]
+    pos = 0
     for u, segs in enumerate(corpus.truth):
+        n = len(segs)
         T = int(frame_off[u + 1] - frame_off[u])
+        pdfs_seg = pdfs_seg_all[pos:pos + n]
+        pos += n
         if T == 0:
             continue
         centers = np.arange(T) * shift + win // 2
-        idx = np.clip(np.searchsorted(segs[:, 2], centers, side="right"), 0, len(segs) - 1)
-        phones = segs[:, 0]
-        pdfs_seg = []
-        for k in range(len(segs)):
-            ph = int(phones[k])
-            l = int(phones[k - 1]) if k > 0 else 0
-            r = int(phones[k + 1]) if k + 1 < len(segs) else 0
-            sts = topo.states_for(ph)[:-1]
-            if len(sts) == 5:
-                sts = [sts[0], sts[2], sts[4]]
-            pdfs_seg.append([tree.lookup([l, ph, r] if tri else [ph], s.forward_pdf_class) for s in sts])
-        pdfs_seg = np.asarray(pdfs_seg, dtype=np.int32)  # [n_seg, 3]
+        idx = np.clip(np.searchsorted(segs[:, 2], centers, side="right"), 0, n - 1)
         frac = (centers - segs[idx, 1]) / np.maximum(1, segs[idx, 2] - segs[idx, 1])
         sub = np.clip((frac * 3).astype(np.int64), 0, 2)
         out[frame_off[u]:frame_off[u + 1]] = pdfs_seg[idx, sub]
