@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--gmm-impl", type=int, default=0)
     ap.add_argument("--cpu-sample-seconds", type=float, default=0.0, help="audio seconds for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workspace-gb", type=float, default=16.0)
+    ap.add_argument("--workspace-gb", type=float, default=100.0)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +179,7 @@ def main():
 
     if args.impl == "reference":
         sc._fsts = sc.batch.export()
-        sample_s = args.cpu_sample_seconds or 600.0
+        sample_s = args.cpu_sample_seconds or 1800.0
         utts = pick_sample(sc, sample_s)
         for _ in range(args.warmup):
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 8)], cores)
@@ -293,7 +293,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         try:
             sc._fsts = sc.batch.export()
-            sample_s = args.cpu_sample_seconds or 240.0
+            sample_s = args.cpu_sample_seconds or 7200.0
             utts = pick_sample(sc, sample_s)
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 10)], cores)
             dt, secs, ok = cpu_reference_pass(sc, utts, cores)

@@ -41,6 +41,10 @@ struct mfa_engine {
   void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; }
   int gmm_timing_begin();
   int gmm_timing_end(int64_t rows);
+  // side streams + events: the Viterbi size classes run concurrently (fork/join around the main stream)
+  static constexpr int kSide = 5;
+  cudaStream_t side[kSide] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
   struct Buf { void *p = nullptr; size_t cap = 0; };
   Buf dev[DB_N];
   Buf pin[PB_N];

@@ -55,6 +55,11 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (int k = 0; k < mfa_engine::kSide; k++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   *out = e;
   return MFA_OK;
 }
@@ -66,6 +71,8 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto &b : e->dev) if (b.p) cudaFree(b.p);
   for (auto &b : e->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : e->gmm_ev) cudaEventDestroy(ev);
+  for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   cudaStreamDestroy(e->stream);
   delete e;
   return MFA_OK;

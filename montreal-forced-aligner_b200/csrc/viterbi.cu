@@ -360,8 +360,13 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   p.total_like = a.d_total_like;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta; p.min_active = a.opts.min_active;
   int pos = 0;
-  for (int c = 0; c <= 4; c++) {
-    int cnt = 0; size_t mx = 0;
+  CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+  // largest-need classes first: they hold the longest utterances (work ~ T * arcs), the small ones fill in around them
+  for (int c = 4; c >= 0; c--) {
+    int cnt = 0;
+    pos = 0;
+    for (int k = 0; k < n; k++) { if (cls[order[k]] < c) pos++; }
+    size_t mx = 0;
     while (pos + cnt < n && cls[order[pos + cnt]] == c) {
       int u = order[pos + cnt];
       size_t nd = need[u];
@@ -371,16 +376,19 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     if (cnt == 0) continue;
     p.order = d_order + pos;
     size_t smem = (mx + 15) / 16 * 16;
+    cudaStream_t st = e->side[c];
+    CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fork, 0));
     if (c < 4) {
       CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-      viterbi_kernel<true><<<cnt, VT, smem, e->stream>>>(p);
+      viterbi_kernel<true><<<cnt, VT, smem, st>>>(p);
     } else {
       CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-      viterbi_kernel<false><<<cnt, VT, smem, e->stream>>>(p);
+      viterbi_kernel<false><<<cnt, VT, smem, st>>>(p);
     }
     e->launches++;
     CUDA_TRY(cudaGetLastError());
-    pos += cnt;
+    CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
   }
   return MFA_OK;
 }
