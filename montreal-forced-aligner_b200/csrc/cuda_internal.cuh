@@ -64,6 +64,7 @@ struct mfa_engine {
 // Tiled acoustic model on the device.  Gaussians are regrouped into tiles of TILE_N rows that never split a pdf
 // (padding rows have gconst = -1e30 and zero weights), so a tile's per-pdf log-sum-exp is local to the tile.
 #define MFA_TILE_N 128
+#define MFA_SEG_ALIGN 4
 
 struct mfa_model {
   mfa_engine *eng = nullptr;
@@ -76,6 +77,7 @@ struct mfa_model {
   int n_tiles = 0, kdim = 0;           // kdim = 2*dim
   std::vector<int32_t> h_tile_pdf0;    // [n_tiles+1] first pdf of each tile
   std::vector<int32_t> h_tile_seg;     // [n_tiles][TILE_N+1] column where local pdf k starts; padded with TILE_N..
+  std::vector<int32_t> h_gauss_col;    // [num_gauss] tile*TILE_N + column of natural Gaussian m
   int32_t *d_tile_pdf0 = nullptr, *d_tile_seg = nullptr;
   float *d_W = nullptr;                // [n_tiles][kdim][TILE_N]  (k-major: coalesced / conflict-free tile loads)
   float *d_G = nullptr;                // [n_tiles][TILE_N] gconsts (-1e30 padding)

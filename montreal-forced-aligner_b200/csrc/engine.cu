@@ -123,37 +123,43 @@ mfa_model::~mfa_model() {
 }
 
 int mfa_model::rebuild_tiles() {
-  // greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows
+  // greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows; every pdf's column range is padded to a multiple of
+  // MFA_SEG_ALIGN columns (padding = gconst -1e30 / zero weights) so the tensor-core epilogue can work on 4-column groups
   h_tile_pdf0.clear();
-  std::vector<int> tile_of_pdf(num_pdfs);
+  auto padded = [](int ng) { return (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN; };
   int cur = 0, t = -1;
   for (int p = 0; p < num_pdfs; p++) {
     int ng = h_pdf_off[p + 1] - h_pdf_off[p];
-    if (ng > MFA_TILE_N) return set_error(MFA_ERR_UNSUPPORTED, "pdf " + std::to_string(p) + " has " + std::to_string(ng) + " Gaussians (> " + std::to_string(MFA_TILE_N) + ")");
-    if (t < 0 || cur + ng > MFA_TILE_N) { t++; cur = 0; h_tile_pdf0.push_back(p); }
-    tile_of_pdf[p] = t; cur += ng;
+    if (ng <= 0) return set_error(MFA_ERR_INVALID, "pdf " + std::to_string(p) + " has no Gaussians");
+    if (padded(ng) > MFA_TILE_N) return set_error(MFA_ERR_UNSUPPORTED, "pdf " + std::to_string(p) + " has " + std::to_string(ng) + " Gaussians (> " + std::to_string(MFA_TILE_N) + ")");
+    if (t < 0 || cur + padded(ng) > MFA_TILE_N) { t++; cur = 0; h_tile_pdf0.push_back(p); }
+    cur += padded(ng);
   }
   n_tiles = t + 1;
   h_tile_pdf0.push_back(num_pdfs);
   kdim = 2 * dim;
   std::vector<float> W((size_t)n_tiles * kdim * MFA_TILE_N, 0.0f), G((size_t)n_tiles * MFA_TILE_N, -1.0e30f);
   h_tile_seg.assign((size_t)n_tiles * (MFA_TILE_N + 1), MFA_TILE_N);
+  h_gauss_col.assign(num_gauss, 0);
   std::vector<int32_t> grow(num_gauss);
   for (int tl = 0; tl < n_tiles; tl++) {
     int col = 0;
     int32_t *seg = &h_tile_seg[(size_t)tl * (MFA_TILE_N + 1)];
     for (int p = h_tile_pdf0[tl]; p < h_tile_pdf0[tl + 1]; p++) {
       seg[p - h_tile_pdf0[tl]] = col;
-      for (int m = h_pdf_off[p]; m < h_pdf_off[p + 1]; m++, col++) {
-        G[(size_t)tl * MFA_TILE_N + col] = h_gconsts[m];
-        grow[m] = tl * MFA_TILE_N + col;
+      int c = col;
+      for (int m = h_pdf_off[p]; m < h_pdf_off[p + 1]; m++, c++) {
+        G[(size_t)tl * MFA_TILE_N + c] = h_gconsts[m];
+        grow[m] = tl * MFA_TILE_N + c;
+        h_gauss_col[m] = tl * MFA_TILE_N + c;
         for (int d = 0; d < dim; d++) {
-          W[((size_t)tl * kdim + d) * MFA_TILE_N + col] = h_miv[(size_t)m * dim + d];
-          W[((size_t)tl * kdim + dim + d) * MFA_TILE_N + col] = -0.5f * h_iv[(size_t)m * dim + d];
+          W[((size_t)tl * kdim + d) * MFA_TILE_N + c] = h_miv[(size_t)m * dim + d];
+          W[((size_t)tl * kdim + dim + d) * MFA_TILE_N + c] = -0.5f * h_iv[(size_t)m * dim + d];
         }
       }
+      col += padded(h_pdf_off[p + 1] - h_pdf_off[p]);
     }
-    seg[h_tile_pdf0[tl + 1] - h_tile_pdf0[tl]] = col;  // end of the last pdf; remaining entries stay TILE_N
+    seg[h_tile_pdf0[tl + 1] - h_tile_pdf0[tl]] = col;  // end of the last pdf (padding included); remaining entries stay TILE_N
   }
   cudaStream_t s = eng->stream;
   auto up = [&](auto **dp, const auto &v) -> int {

@@ -36,11 +36,11 @@ constexpr uint32_t SBO_BYTES = 128;               // row-group-adjacent core mat
 constexpr int NTHREADS = 384;
 constexpr float kLn2 = 0.69314718055994530942f, kLog2e = 1.44269504088896340736f;
 
-struct TcMeta {  // per Gaussian tile: segment (pdf) structure of its 128 columns in four 32-column chunks
-  uint32_t start[4], end[4];
-  int32_t pdf0, pad[7];
+struct TcMeta {  // per Gaussian tile: pdf structure of its 128 columns at 4-column group granularity (32 groups)
+  uint32_t gstart, gend;  // bit g: group g starts a pdf / is the last group of a pdf (pdf column ranges are multiples of 4)
+  int32_t pdf0, pad;
 };
-static_assert(sizeof(TcMeta) == 64, "TcMeta must be 64 bytes");
+static_assert(sizeof(TcMeta) == 16, "TcMeta must be 16 bytes");
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,35 +101,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 32-column chunk of a frame's component scores (log2 domain): segmented max (forward + backward), exp2, segmented sum,
-// one log2 + store per finished pdf.  (cmx, cs) carry an unfinished pdf into the next chunk.  All predicates are warp-uniform.
-__device__ __forceinline__ void lse_chunk(const uint32_t (&vr)[32], uint32_t smask, uint32_t emask, float &cmx, float &cs, float *&out,
-                                          int64_t ld, bool row_ok) {
-  float v[32], r[32];
+// One 32-column chunk (8 groups of 4 columns) of a frame's component scores (log2 domain).  pdf boundaries fall on group
+// boundaries, so the segmented max / sum scans run over 8 group values: group max (tree) -> forward running max -> backward
+// broadcast of each pdf's max -> exp2 of the 32 values against their pdf's max -> group sums -> forward running sum; one
+// log2 + store per finished pdf.  (cmx, cs) carry an unfinished pdf into the next chunk.  All predicates are warp-uniform.
+__device__ __forceinline__ void lse_chunk(const uint32_t (&vr)[32], uint32_t gs, uint32_t ge, float &cmx, float &cs, float *&out, int64_t ld,
+                                          bool row_ok) {
+  float r[8];
   float run = cmx;
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
-    v[j] = __uint_as_float(vr[j]);
-    run = ((smask >> j) & 1u) ? v[j] : fmaxf(run, v[j]);
-    r[j] = run;
+  for (int g = 0; g < 8; g++) {
+    const float gm = fmaxf(fmaxf(__uint_as_float(vr[4 * g]), __uint_as_float(vr[4 * g + 1])),
+                           fmaxf(__uint_as_float(vr[4 * g + 2]), __uint_as_float(vr[4 * g + 3])));
+    run = ((gs >> g) & 1u) ? gm : fmaxf(run, gm);
+    r[g] = run;
   }
-  float m = r[31];
+  float m = r[7];
 #pragma unroll
-  for (int j = 31; j >= 0; j--) {
-    m = ((emask >> j) & 1u) ? r[j] : m;
-    r[j] = m;
+  for (int g = 7; g >= 0; g--) {
+    m = ((ge >> g) & 1u) ? r[g] : m;
+    r[g] = m;
   }
   float q = cs * ex2(cmx - r[0]);
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
-    float e = ex2(v[j] - r[j]);
-    q = ((smask >> j) & 1u) ? e : q + e;
-    if ((emask >> j) & 1u) {
-      if (row_ok) *out = (r[j] + lg2(q)) * kLn2;
+  for (int g = 0; g < 8; g++) {
+    const float e0 = ex2(__uint_as_float(vr[4 * g]) - r[g]), e1 = ex2(__uint_as_float(vr[4 * g + 1]) - r[g]);
+    const float e2 = ex2(__uint_as_float(vr[4 * g + 2]) - r[g]), e3 = ex2(__uint_as_float(vr[4 * g + 3]) - r[g]);
+    const float s4 = (e0 + e1) + (e2 + e3);
+    q = ((gs >> g) & 1u) ? s4 : q + s4;
+    if ((ge >> g) & 1u) {
+      if (row_ok) *out = (r[g] + lg2(q)) * kLn2;
       out += ld;
     }
   }
-  cmx = r[31];
+  cmx = r[7];
   cs = q;
 }
 
@@ -243,14 +248,21 @@ gmm_tc_kernel(TcParams p) {
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         float cmx = -INFINITY, cs = 0.0f;
         float *out = p.llT + (size_t)cur.pdf0 * p.ld + row;
-        uint32_t v[32];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          tmem_ld32(t0 + c * 32, v);
-          tmem_ld_wait();
-          if (c == 3) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); }
-          lse_chunk(v, cur.start[c], cur.end[c], cmx, cs, out, p.ld, row_ok);
-        }
+        uint32_t va[32], vb[32];
+        tmem_ld32(t0, va);
+        tmem_ld_wait();
+        tmem_ld32(t0 + 32, vb);                    // chunk c+1 is in flight while chunk c is reduced
+        lse_chunk(va, cur.gstart & 0xFF, cur.gend & 0xFF, cmx, cs, out, p.ld, row_ok);
+        tmem_ld_wait();
+        tmem_ld32(t0 + 64, va);
+        lse_chunk(vb, (cur.gstart >> 8) & 0xFF, (cur.gend >> 8) & 0xFF, cmx, cs, out, p.ld, row_ok);
+        tmem_ld_wait();
+        tmem_ld32(t0 + 96, vb);
+        lse_chunk(va, (cur.gstart >> 16) & 0xFF, (cur.gend >> 16) & 0xFF, cmx, cs, out, p.ld, row_ok);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tempty + s * 2 + f);           // accumulator drained: the MMA warp may overwrite it
+        lse_chunk(vb, (cur.gstart >> 24) & 0xFF, (cur.gend >> 24) & 0xFF, cmx, cs, out, p.ld, row_ok);
       }
     }
   }
@@ -318,29 +330,33 @@ int build_tc(mfa_model *m) {
     put(tile, 1, row, k, (float)(w - (double)hi));
     wmax = std::max(wmax, std::fabs(w));
   };
-  // walk the tiling produced by mfa_model::rebuild_tiles (whole pdfs per tile, in pdf order)
+  // walk the tiling produced by mfa_model::rebuild_tiles (whole pdfs per tile, in pdf order, column ranges padded to 4)
   for (int tl = 0; tl < nt; tl++) {
     int col = 0;
     memset(&meta[tl], 0, sizeof(TcMeta));
     meta[tl].pdf0 = m->h_tile_pdf0[tl];
     for (int pdf = m->h_tile_pdf0[tl]; pdf < m->h_tile_pdf0[tl + 1]; pdf++) {
-      meta[tl].start[col / 32] |= 1u << (col % 32);
-      for (int g = m->h_pdf_off[pdf]; g < m->h_pdf_off[pdf + 1]; g++, col++) {
+      const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
+      meta[tl].gstart |= 1u << (col / 4);
+      meta[tl].gend |= 1u << ((col + pad - 1) / 4);
+      int c = col;
+      for (int g = m->h_pdf_off[pdf]; g < m->h_pdf_off[pdf + 1]; g++, c++) {
         for (int d = 0; d < D; d++) {
           double s = m->h_tc_colscale[d];
-          split2(tl, col, d, (double)m->h_miv[(size_t)g * D + d] / s * kLog2e);
-          split2(tl, col, D + d, -0.5 * (double)m->h_iv[(size_t)g * D + d] / (s * s) * kLog2e);
+          split2(tl, c, d, (double)m->h_miv[(size_t)g * D + d] / s * kLog2e);
+          split2(tl, c, D + d, -0.5 * (double)m->h_iv[(size_t)g * D + d] / (s * s) * kLog2e);
         }
         double gc = (double)m->h_gconsts[g] * kLog2e;
         if (!(gc > -60000.0)) gc = -60000.0;
         float g1 = __half2float(__float2half_rn((float)gc));
         float g2 = __half2float(__float2half_rn((float)(gc - g1)));
         float g3 = (float)(gc - g1 - g2);
-        put(tl, 0, col, 2 * D, g1); put(tl, 0, col, 2 * D + 1, g2); put(tl, 0, col, 2 * D + 2, g3);
+        put(tl, 0, c, 2 * D, g1); put(tl, 0, c, 2 * D + 1, g2); put(tl, 0, c, 2 * D + 2, g3);
       }
-      meta[tl].end[(col - 1) / 32] |= 1u << ((col - 1) % 32);
+      for (; c < col + pad; c++) put(tl, 0, c, 2 * D, -60000.0f);  // padding columns inside the pdf's range: exp2 -> 0
+      col += pad;
     }
-    if (col < TN) meta[tl].start[col / 32] |= 1u << (col % 32);  // padding columns: one junk segment that never ends
+    if (col < TN) meta[tl].gstart |= 1u << (col / 4);  // trailing padding: one junk segment that never ends
     for (; col < TN; col++) put(tl, 0, col, 2 * D, -60000.0f);
   }
   if (wmax > 60000.0) return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel");
