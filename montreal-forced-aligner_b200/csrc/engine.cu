@@ -235,7 +235,7 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
   if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
   size_t A = g->a_src.size();
   std::vector<uint32_t> pack(A);
-  for (size_t a = 0; a < A; a++) pack[a] = (uint32_t)(g->a_src[a] & 0xFFFF) | ((uint32_t)(g->a_lp[a] < 0 ? 0xFFFF : g->a_lp[a]) << 16);
+  for (size_t a = 0; a < A; a++) pack[a] = (uint32_t)(g->a_dst[a] & 0xFFFF) | ((uint32_t)(g->a_lp[a] < 0 ? 0xFFFF : g->a_lp[a]) << 16);
   for (int u = 0; u < g->n_utts; u++)
     if (g->lp_off[u + 1] - g->lp_off[u] >= 0xFFFF) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph references >= 65535 pdfs");
   struct Item { const void *h; size_t bytes; void **d; };
@@ -246,7 +246,7 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
       {g->in_begin.data(), g->in_begin.size() * 4, (void **)&g->d_in_begin}, {g->a_tid.data(), A * 4, (void **)&g->d_a_tid},
       {g->a_olabel.data(), A * 4, (void **)&g->d_a_olabel}, {g->lp2pdf.data(), g->lp2pdf.size() * 4, (void **)&g->d_lp2pdf},
       {pack.data(), A * 4, (void **)&g->d_a_pack}, {g->a_w.data(), A * 4, (void **)&g->d_a_w},
-      {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}};
+      {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}, {g->a_src.data(), A * 4, (void **)&g->d_a_src}};
   size_t total = 0;
   for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
   CUDA_TRY(cudaMalloc(&g->d_blob, std::max<size_t>(total, 256)));

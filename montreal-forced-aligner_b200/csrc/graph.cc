@@ -438,12 +438,12 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     int64_t s0 = b.state_off[u], S = b.state_off[u + 1] - s0, a0 = b.arc_off[u], A = b.arc_off[u + 1] - a0;
     g->start[u] = b.start[u];
     if (S > 65534 || A > 65534) { delete g; return set_error(MFA_ERR_UNSUPPORTED, "graph of utterance " + std::to_string(u) + " exceeds 65534 states/arcs"); }
-    // order arcs by (dst, original index)
+    // order arcs by (src, original index)
     std::vector<int32_t> order(A);
     for (int64_t a = 0; a < A; a++) order[a] = (int32_t)a;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.dst[a0 + x] < b.dst[a0 + y]; });
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.src[a0 + x] < b.src[a0 + y]; });
     std::vector<int32_t> inb(S + 1, 0);
-    for (int64_t a = 0; a < A; a++) inb[b.dst[a0 + a] + 1]++;
+    for (int64_t a = 0; a < A; a++) inb[b.src[a0 + a] + 1]++;
     for (int64_t s = 0; s < S; s++) inb[s + 1] += inb[s];
     g->in_begin.insert(g->in_begin.end(), inb.begin(), inb.end());
     // local pdf list
@@ -458,6 +458,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
       int64_t a = a0 + order[k];
       int il = b.il[a];
       g->a_src.push_back(b.src[a]);
+      g->a_dst.push_back(b.dst[a]);
       g->a_tid.push_back(il);
       g->a_olabel.push_back(b.ol[a]);
       if (b.ol[a] != 0) words++;

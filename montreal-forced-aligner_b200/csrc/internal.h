@@ -11,14 +11,14 @@ int set_error(int code, const std::string &msg);
 }
 
 // Decoder-ready batch of graphs (host copy; device mirror uploaded on first use by an engine).
-// Arcs of utterance u are arc_off[u]..arc_off[u+1]-1, grouped by destination state:
-// the in-arcs of local state s are in_begin[inb_off[u]+s] .. in_begin[inb_off[u]+s+1]-1 (utterance-local indices).
+// Arcs of utterance u are arc_off[u]..arc_off[u+1]-1, grouped by SOURCE state (OpenFst order inside a state):
+// the out-arcs of local state s are in_begin[inb_off[u]+s] .. in_begin[inb_off[u]+s+1]-1 (utterance-local indices).
 struct mfa_graphs {
   int32_t n_utts = 0;
   std::vector<int64_t> st_off, arc_off, lp_off, inb_off;
   std::vector<int32_t> start, n_eps, max_words;
   std::vector<int32_t> in_begin;             // [sum(S_u+1)]
-  std::vector<int32_t> a_src, a_lp, a_tid, a_olabel;  // per arc; a_lp = local pdf index or -1 (epsilon input)
+  std::vector<int32_t> a_src, a_dst, a_lp, a_tid, a_olabel;  // per arc; a_lp = local pdf index or -1 (epsilon input)
   std::vector<float> a_w;                    // graph weight + AddTransitionProbs cost
   std::vector<float> final_w;                // per state, +inf = non-final
   std::vector<int32_t> lp2pdf;               // per utterance local pdf list (sorted pdf ids)
@@ -27,8 +27,8 @@ struct mfa_graphs {
   void *d_blob = nullptr;
   size_t d_bytes = 0;
   int64_t *d_st_off = nullptr, *d_arc_off = nullptr, *d_lp_off = nullptr, *d_inb_off = nullptr;
-  int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr;
-  uint32_t *d_a_pack = nullptr;  // src (low 16) | lp (high 16, 0xFFFF = epsilon)
+  int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr, *d_a_src = nullptr;
+  uint32_t *d_a_pack = nullptr;  // dst (low 16) | lp (high 16, 0xFFFF = epsilon)
   float *d_a_w = nullptr, *d_final_w = nullptr;
   ~mfa_graphs();
 };
