@@ -1,0 +1,160 @@
+"""Host-side M-step for the align -> acc-stats -> update loop (row a10 / N3 of SURVEY.md section 8).
+
+Restates Kaldi gmm/mle-diag-gmm.cc ``MleDiagGmmUpdate``, gmm/mle-am-diag-gmm.cc ``MleAmDiagGmmUpdate``,
+gmm/am-diag-gmm.cc ``SplitByCount`` / ``GetSplitTargets`` and gmm/diag-gmm.cc ``Split`` as called by the reference at
+montreal_forced_aligner/acoustic_modeling/base.py:319-338 (upstream ``acc_stats``):
+``am.mle_update(gmm_accs, mixup=current_gaussians, power=power)``.
+
+The accumulators come from the CUDA K4 kernel (f64, summed across GPUs with an NCCL all-reduce); this update is small
+(G x D float64) and runs in numpy.  ``SplitByCount`` perturbs means with Gaussian noise, so model parity across
+iterations with Kaldi is statistical (hard part 8); the RNG here is seeded.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .kaldi_io import AmDiagGmm
+
+
+class AccumAmDiagGmm:
+    """f64 accumulators for all pdfs, packed like the model: occ[G], mean_acc[G,D], var_acc[G,D]."""
+
+    def __init__(self, num_gauss: int, dim: int):
+        self.occ = np.zeros(num_gauss)
+        self.mean = np.zeros((num_gauss, dim))
+        self.var = np.zeros((num_gauss, dim))
+        self.tot_like = 0.0
+        self.tot_frames = 0.0
+
+    @classmethod
+    def init(cls, am: AmDiagGmm) -> "AccumAmDiagGmm":
+        return cls(am.NumGauss(), am.dim)
+
+    @classmethod
+    def from_dict(cls, d: Dict) -> "AccumAmDiagGmm":
+        a = cls(d["occ"].shape[0], d["mean"].shape[1])
+        a.occ, a.mean, a.var = np.array(d["occ"], dtype=np.float64), np.array(d["mean"], dtype=np.float64), np.array(d["var"], dtype=np.float64)
+        a.tot_like = float(np.asarray(d["like"]).reshape(-1)[0])
+        a.tot_frames = float(d["frames"])
+        return a
+
+    def Add(self, scale: float, other: "AccumAmDiagGmm"):
+        self.occ += scale * other.occ
+        self.mean += scale * other.mean
+        self.var += scale * other.var
+        self.tot_like += scale * other.tot_like
+        self.tot_frames += scale * other.tot_frames
+
+    def TotLogLike(self) -> float:
+        return self.tot_like
+
+    def TotCount(self) -> float:
+        return float(self.occ.sum())
+
+
+def _gmm_objf(am: AmDiagGmm, acc: AccumAmDiagGmm) -> float:
+    """MlObjective of mle-diag-gmm.cc summed over pdfs: sum_m occ*gconst + mean_acc.means_invvars - 0.5 var_acc.inv_vars."""
+    return float((acc.occ * am.gconsts.astype(np.float64)).sum() + (acc.mean * am.means_invvars).sum() - 0.5 * (acc.var * am.inv_vars).sum())
+
+
+def mle_update(am: AmDiagGmm, acc: AccumAmDiagGmm, mixup: int = 0, power: float = 0.25, min_gaussian_occupancy: float = 10.0,
+               min_gaussian_weight: float = 1.0e-5, min_variance: float = 0.001, remove_low_count_gaussians: bool = True,
+               perturb_factor: float = 0.01, min_count: float = 20.0, seed: int = 1234) -> Tuple[AmDiagGmm, float, float]:
+    """Returns (new model, objective improvement, total count).  Updates means, variances and weights."""
+    D = am.dim
+    objf_before = _gmm_objf(am, acc)
+    new_w, new_mu, new_var, new_off = [], [], [], [0]
+    old_mu, old_var = am.means(), am.variances()
+    for j in range(am.NumPdfs()):
+        a, b = int(am.offsets[j]), int(am.offsets[j + 1])
+        occ = acc.occ[a:b]
+        occ_sum = occ.sum()
+        n = b - a
+        w = am.weights[a:b].astype(np.float64).copy()
+        mu = old_mu[a:b].copy()
+        var = old_var[a:b].copy()
+        keep = np.ones(n, dtype=bool)
+        for i in range(n):
+            prob = occ[i] / occ_sum if occ_sum > 0 else 1.0 / n
+            if occ[i] > min_gaussian_occupancy and prob > min_gaussian_weight:
+                w[i] = prob
+                m = acc.mean[a + i] / occ[i]
+                v = acc.var[a + i] / occ[i] - m * m
+                mu[i] = m
+                var[i] = np.maximum(v, min_variance)
+            elif remove_low_count_gaussians:
+                keep[i] = False
+            else:
+                w[i] = prob
+        if not keep.any():
+            keep[int(np.argmax(occ))] = True  # Kaldi refuses to remove the last Gaussian of a pdf
+        w, mu, var = w[keep], mu[keep], var[keep]
+        w = w / w.sum()
+        new_w.append(w); new_mu.append(mu); new_var.append(var)
+        new_off.append(new_off[-1] + len(w))
+    w = np.concatenate(new_w); mu = np.concatenate(new_mu); var = np.concatenate(new_var)
+    off = np.asarray(new_off, dtype=np.int32)
+    # objective after the update uses the stats of the components that survived
+    state_occs = np.asarray([acc.occ[am.offsets[j]:am.offsets[j + 1]].sum() for j in range(am.NumPdfs())])
+    out = AmDiagGmm(D, off, w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))
+    objf_after = None
+    if out.NumGauss() == am.NumGauss():
+        objf_after = _gmm_objf(out, acc)
+    if mixup and mixup > out.NumGauss():
+        out = split_by_count(out, state_occs, mixup, perturb_factor, power, min_count, seed)
+    count = acc.TotCount()
+    impr = (objf_after - objf_before) if objf_after is not None else float("nan")
+    return out, impr, count
+
+
+def get_split_targets(state_occs: np.ndarray, target_components: int, power: float, min_count: float) -> np.ndarray:
+    """am-diag-gmm.cc GetSplitTargets: greedy allocation by occupancy^power / num_components."""
+    n = state_occs.shape[0]
+    comps = np.ones(n, dtype=np.int64)
+    occp = np.power(np.maximum(state_occs, 0.0), power)
+    heap = [(-occp[j] / (1 + 1.0e-10), j) for j in range(n)]
+    heapq.heapify(heap)
+    num = n
+    dead = np.zeros(n, dtype=bool)
+    while num < target_components and heap:
+        negkey, j = heapq.heappop(heap)
+        if negkey == 0.0 or dead[j]:
+            break
+        if (comps[j] + 1) * min_count >= state_occs[j]:
+            dead[j] = True
+            heapq.heappush(heap, (0.0, j))
+        else:
+            comps[j] += 1
+            num += 1
+            heapq.heappush(heap, (-occp[j] / (comps[j] + 1.0e-10), j))
+    return comps
+
+
+def split_by_count(am: AmDiagGmm, state_occs: np.ndarray, target_components: int, perturb_factor: float = 0.01, power: float = 0.25,
+                   min_count: float = 20.0, seed: int = 1234) -> AmDiagGmm:
+    """AmDiagGmm::SplitByCount -> DiagGmm::Split (heaviest component split, means perturbed by +-perturb*sqrt(var)*randn)."""
+    rng = np.random.default_rng(seed)
+    targets = get_split_targets(state_occs, target_components, power, min_count)
+    mu_all, var_all = am.means(), am.variances()
+    ws, mus, vars_, off = [], [], [], [0]
+    for j in range(am.NumPdfs()):
+        a, b = int(am.offsets[j]), int(am.offsets[j + 1])
+        w = list(am.weights[a:b].astype(np.float64))
+        mu = [m.copy() for m in mu_all[a:b]]
+        var = [v.copy() for v in var_all[a:b]]
+        while len(w) < targets[j]:
+            k = int(np.argmax(w))
+            w[k] *= 0.5
+            w.append(w[k])
+            r = rng.standard_normal(am.dim) * np.sqrt(var[k]) * perturb_factor
+            mu.append(mu[k] + r)
+            mu[k] = mu[k] - r
+            var.append(var[k].copy())
+        ws.append(np.asarray(w)); mus.append(np.asarray(mu)); vars_.append(np.asarray(var))
+        off.append(off[-1] + len(w))
+    w = np.concatenate(ws); mu = np.concatenate(mus); var = np.concatenate(vars_)
+    return AmDiagGmm(am.dim, np.asarray(off, np.int32), w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))

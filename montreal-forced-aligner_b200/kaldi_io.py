@@ -984,3 +984,11 @@ def read_wav_int16(path, channel: int = 0) -> Tuple[np.ndarray, int]:
             return np.round(x).clip(-32768, 32767).astype(np.int16), sr
         pos += 8 + sz + (sz & 1)
     raise ValueError("no data chunk")
+
+
+def write_wav_int16(path, pcm: np.ndarray, sample_rate: int = 16000):
+    """Mono 16-bit RIFF/WAVE writer (tests and synthetic corpora)."""
+    pcm = np.ascontiguousarray(pcm, dtype="<i2")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + pcm.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate, 2 * sample_rate, 2, 16))
+        f.write(b"data" + struct.pack("<I", pcm.nbytes) + pcm.tobytes())

@@ -1,0 +1,461 @@
+"""kalpy-shaped Python surface over the B200 engine (the drop-in boundary of SURVEY.md section 8b).
+
+The reference reaches its hot path only through kalpy objects; these classes keep the names, argument meaning and error
+behaviour MFA relies on (call sites cited per class, paths relative to /root/reference/montreal_forced_aligner), and run
+the arithmetic on the GPU through the C ABI.  Matrices cross the boundary as numpy arrays (kalpy ``FloatMatrix`` role);
+files are Kaldi ark/scp.  There is no CPU fallback: constructing an engine without a B200 raises ``MfaError``.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine as E, kaldi_io as K
+from ._lib import MfaError
+from .gmm_update import AccumAmDiagGmm, mle_update
+from .lexicon import Lexicon
+
+_engines: Dict[int, E.Engine] = {}
+
+
+def get_engine(device: Optional[int] = None) -> E.Engine:
+    """One engine per device per process (MFA runs one aligner per job; jobs map to GPUs via LOCAL_RANK / MFA_B200_DEVICE)."""
+    if device is None:
+        device = int(os.environ.get("MFA_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    if device not in _engines:
+        _engines[device] = E.Engine(device)
+    return _engines[device]
+
+
+read_gmm_model = K.read_gmm_model
+write_gmm_model = K.write_gmm_model
+
+
+# ------------------------------------------------------------------------------------------------ audio / MFCC
+@dataclass
+class Segment:
+    """kalpy.data.Segment (corpus/features.py:232; command_line/align_one.py:163)."""
+    file_name: str
+    begin: Optional[float] = None
+    end: Optional[float] = None
+    channel: int = 0
+
+    def load_audio(self) -> np.ndarray:
+        pcm, sr = K.read_wav_int16(self.file_name, self.channel or 0)
+        if sr != 16000:
+            raise MfaError(f"{self.file_name}: {sr} Hz audio; resampling is out of scope (SURVEY.md A.1), provide 16 kHz WAV")
+        a = 0 if self.begin is None else int(round(self.begin * sr))
+        b = pcm.shape[0] if self.end is None else int(round(self.end * sr))
+        return pcm[max(a, 0):min(b, pcm.shape[0])]
+
+
+class CompressedMatrix:
+    """Kaldi CompressedMatrix value: holds the codec bytes; ``numpy()`` decodes (corpus/features.py:209,318,356)."""
+
+    def __init__(self, mat: np.ndarray):
+        self.blob = K.compress_matrix(mat)
+        self.shape = mat.shape
+
+    def numpy(self) -> np.ndarray:
+        return K.decompress_matrix(self.blob)
+
+
+class MfccComputer:
+    """kalpy.feat.mfcc.MfccComputer (corpus/features.py:685,198,235; alignment/multiprocessing.py:1284)."""
+
+    def __init__(self, **mfcc_options):
+        self.parameters = dict(mfcc_options)
+        self.opts = E.mfcc_opts(**{k: v for k, v in mfcc_options.items() if k not in ("uses_cmvn", "use_pitch")})
+        self.frame_shift = self.opts.frame_shift_ms
+        self.engine = None
+
+    def _eng(self):
+        if self.engine is None:
+            self.engine = get_engine()
+        return self.engine
+
+    def compute_mfccs_batch(self, pcm_list: Sequence[np.ndarray]) -> List[np.ndarray]:
+        off = np.zeros(len(pcm_list) + 1, np.int64)
+        off[1:] = np.cumsum([len(p) for p in pcm_list])
+        pcm = np.concatenate(pcm_list).astype(np.int16) if len(pcm_list) else np.zeros(0, np.int16)
+        out, fo = self._eng().mfcc(pcm, off, self.opts)
+        return [out[fo[i]:fo[i + 1]] for i in range(len(pcm_list))]
+
+    def compute_mfccs(self, segment) -> np.ndarray:
+        pcm = segment.load_audio() if isinstance(segment, Segment) else np.asarray(segment, dtype=np.int16)
+        return self.compute_mfccs_batch([pcm])[0]
+
+    def compute_mfccs_for_export(self, segment, compress: bool = True):
+        m = self.compute_mfccs(segment)
+        return CompressedMatrix(m) if compress else m
+
+
+class CmvnComputer:
+    """kalpy.feat.cmvn.CmvnComputer (corpus/acoustic_corpus.py:1336-1337; command_line/align_one.py:161,168)."""
+
+    def compute_cmvn_from_features(self, feats: Sequence[np.ndarray]) -> np.ndarray:
+        feats = [np.asarray(f.numpy() if isinstance(f, CompressedMatrix) else f, dtype=np.float32) for f in feats]
+        fo = np.zeros(len(feats) + 1, np.int64)
+        fo[1:] = np.cumsum([f.shape[0] for f in feats])
+        stats = get_engine().cmvn_stats(np.concatenate(feats), fo, np.zeros(len(feats), np.int32), 1)
+        return stats[0]
+
+    def export_cmvn(self, file_name, feature_archive: "FeatureArchive", spk2utt: Dict[str, List[str]], write_scp: bool = True):
+        """Per-speaker stats over the raw features -> cmvn.ark (+ cmvn.scp), DoubleMatrix 2 x (D+1) per speaker."""
+        spks = list(spk2utt)
+        mats, u2s = [], []
+        for si, s in enumerate(spks):
+            for u in spk2utt[s]:
+                mats.append(feature_archive.raw(u))
+                u2s.append(si)
+        fo = np.zeros(len(mats) + 1, np.int64)
+        fo[1:] = np.cumsum([m.shape[0] for m in mats])
+        stats = get_engine().cmvn_stats(np.concatenate(mats), fo, np.asarray(u2s, np.int32), len(spks))
+        scp = str(file_name)[:-4] + ".scp" if write_scp else None
+        with K.ArkWriter(file_name, scp) as w:
+            for si, s in enumerate(spks):
+                w.write_matrix(str(s), stats[si].astype(np.float64))
+        return {s: stats[i] for i, s in enumerate(spks)}
+
+
+def _read_table(path, kind) -> Dict[str, object]:
+    path = str(path)
+    if path.endswith(".scp"):
+        return {k: K.read_scp_object(p, off, kind) for k, p, off in K.read_scp(path)}
+    return dict(K.read_ark(path, kind))
+
+
+def _read_map(path) -> Dict[str, str]:
+    out = {}
+    with open(path, "r", encoding="utf8") as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 2:
+                out[parts[0]] = parts[1]
+    return out
+
+
+class FeatureArchive:
+    """kalpy.feat.data.FeatureArchive (db.py:2127-2135; corpus/features.py:323-339; acoustic_modeling/monophone.py:89-99).
+
+    Lazily applies CMVN -> deltas | splice+LDA -> fMLLR (order of alignment/multiprocessing.py:1287-1304) on the GPU."""
+
+    def __init__(self, file_name, utt2spk_file_name=None, cmvn_file_name=None, lda_mat_file_name=None, transform_file_name=None,
+                 vad_file_name=None, deltas: bool = False, splices: bool = False, splice_frames: int = 3, subsample_n: int = 0,
+                 use_sliding_cmvn: bool = False):
+        if vad_file_name or subsample_n or use_sliding_cmvn:
+            raise MfaError("vad / subsampling / sliding CMVN are outside the alignment hot path (SURVEY.md section 2a)")
+        self.file_name = str(file_name)
+        self._entries = K.read_scp(self.file_name) if self.file_name.endswith(".scp") else None
+        self._ark = None if self._entries is not None else dict(K.read_ark(self.file_name, "matrix"))
+        self.keys = [e[0] for e in self._entries] if self._entries is not None else list(self._ark)
+        self._index = {e[0]: e for e in self._entries} if self._entries is not None else None
+        self.utt2spk = _read_map(utt2spk_file_name) if utt2spk_file_name else {}
+        self.cmvn_read_specifier = str(cmvn_file_name) if cmvn_file_name else None
+        self._cmvn = {k: np.asarray(v, np.float64) for k, v in _read_table(cmvn_file_name, "matrix").items()} if cmvn_file_name else None
+        self.lda_mat_file_name = str(lda_mat_file_name) if lda_mat_file_name else None
+        self._lda = K.read_matrix_file(lda_mat_file_name).astype(np.float32) if lda_mat_file_name else None
+        self.transform_read_specifier = str(transform_file_name) if transform_file_name else None
+        self._trans = {k: np.asarray(v, np.float32) for k, v in _read_table(transform_file_name, "matrix").items()} if transform_file_name else None
+        self.use_deltas, self.use_splices, self.splice_frames = bool(deltas), bool(splices) or self._lda is not None, splice_frames
+
+    def raw(self, key: str) -> np.ndarray:
+        if self._ark is not None:
+            return np.asarray(self._ark[key], np.float32)
+        _, p, off = self._index[key]
+        return np.asarray(K.read_scp_object(p, off, "matrix"), np.float32)
+
+    def batch(self, keys: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+        """Final features of `keys`, concatenated, + frame offsets: one fused kernel launch for the whole batch."""
+        mats = [self.raw(k) for k in keys]
+        fo = np.zeros(len(mats) + 1, np.int64)
+        fo[1:] = np.cumsum([m.shape[0] for m in mats])
+        if not mats:
+            return np.zeros((0, 0), np.float32), fo
+        spk_names = sorted({self.utt2spk.get(k, k) for k in keys})
+        sidx = {s: i for i, s in enumerate(spk_names)}
+        u2s = np.asarray([sidx[self.utt2spk.get(k, k)] for k in keys], np.int32)
+        cmvn = fm = None
+        dim = mats[0].shape[1]
+        if self._cmvn is not None:
+            cmvn = np.stack([self._cmvn[s] if s in self._cmvn else np.concatenate([np.zeros((2, dim)), np.ones((2, 1))], 1) for s in spk_names])
+        mode = "lda" if self._lda is not None else ("deltas" if self.use_deltas else "none")
+        if self._trans is not None:
+            od = self._lda.shape[0] if self._lda is not None else (3 * dim if self.use_deltas else dim)
+            fm = np.stack([self._trans.get(s, np.eye(od, od + 1, dtype=np.float32)) for s in spk_names])
+        out = get_engine().features(np.concatenate(mats), fo, mode, lda=self._lda, splice_ctx=self.splice_frames, fmllr=fm, cmvn_stats=cmvn,
+                                    utt2spk=u2s, n_spk=len(spk_names))
+        return out, fo
+
+    def __getitem__(self, key: str) -> np.ndarray:
+        return self.batch([key])[0]
+
+    def __iter__(self) -> Iterator[Tuple[str, np.ndarray]]:
+        B = 256
+        for i in range(0, len(self.keys), B):
+            ks = self.keys[i:i + B]
+            out, fo = self.batch(ks)
+            for j, k in enumerate(ks):
+                yield k, out[fo[j]:fo[j + 1]]
+
+    def close(self):
+        self._ark = None
+
+
+# ------------------------------------------------------------------------------------------------ graphs
+class TrainingGraphCompiler:
+    """kalpy.decoder.training_graphs.TrainingGraphCompiler (alignment/multiprocessing.py:537-571,1189,1282;
+    online/alignment.py:77-96).  ``lexicon_compiler`` is a mfa_b200.lexicon.Lexicon."""
+
+    def __init__(self, model_path, tree_path, lexicon_compiler: Lexicon, use_g2p: bool = False, batch_size: int = 500):
+        if use_g2p:
+            raise MfaError("G2P-backed lexicons are outside the hot path (SURVEY.md section 2a)")
+        self.transition_model, self.acoustic_model = K.read_gmm_model(model_path)
+        self.tree = K.read_tree(tree_path)
+        self.lexicon_compiler = lexicon_compiler
+        self.batch_size = batch_size
+        self._gc = E.GraphCompiler(self.transition_model, self.tree, lexicon_compiler)
+
+    def compile_fst(self, text: str) -> K.Fst:
+        return self._gc.compile([self.lexicon_compiler.to_int(text)]).export()[0]
+
+    def compile_batch(self, texts: Sequence[str], n_threads: int = 8) -> E.FstBatch:
+        return self._gc.compile([self.lexicon_compiler.to_int(t) for t in texts], n_threads=n_threads)
+
+    def export_graphs(self, file_name, records: Iterable[Tuple[str, str]], interjection_words=None, callback: Optional[Callable] = None):
+        if interjection_words:
+            raise MfaError("interjection-word graphs (transcript verification) are outside the hot path")
+        records = list(records)
+        with K.ArkWriter(file_name) as w:
+            for i in range(0, len(records), self.batch_size):
+                chunk = records[i:i + self.batch_size]
+                fsts = self.compile_batch([t for _, t in chunk]).export()
+                for (key, _), fst in zip(chunk, fsts):
+                    w.write_fst(key, fst)
+                    if callback:
+                        callback(1)
+
+
+class FstArchive:
+    """kalpy.decoder.data.FstArchive (alignment/multiprocessing.py:831; acoustic_modeling/monophone.py:93-104)."""
+
+    def __init__(self, file_name):
+        self.file_name = str(file_name)
+        self._fsts = dict(K.read_ark(self.file_name, "fst"))
+
+    def __getitem__(self, key) -> K.Fst:
+        return self._fsts[key]
+
+    def __contains__(self, key):
+        return key in self._fsts
+
+    def __iter__(self):
+        return iter(self._fsts.items())
+
+    def keys(self):
+        return list(self._fsts)
+
+    def close(self):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------ alignment
+@dataclass
+class CtmInterval:
+    begin: float
+    end: float
+    label: object
+    confidence: float = 0.0
+
+
+class Alignment:
+    """kalpy.gmm.data.Alignment (alignment/multiprocessing.py:1316-1320,1542-1546; online/alignment.py:113-121)."""
+
+    def __init__(self, utterance_id, alignment, words, likelihood=None, per_frame_likelihoods=None):
+        self.utterance_id = utterance_id
+        self.alignment = [int(x) for x in alignment]
+        self.words = [int(x) for x in words]
+        self.likelihood = likelihood
+        self.per_frame_likelihoods = None if per_frame_likelihoods is None else np.asarray(per_frame_likelihoods, np.float32)
+
+    def generate_ctm(self, transition_model: K.TransitionModel, phone_table: Dict[int, str], frame_shift: float = 0.01) -> List[CtmInterval]:
+        """Phone intervals from transition-ids: a phone ends at a transition into its HMM's final state followed (reorder=true)
+        by that state's trailing self-loops (Kaldi SplitToPhones)."""
+        out: List[CtmInterval] = []
+        tids = self.alignment
+        n = len(tids)
+        start = 0
+        t = 0
+        while t < n:
+            tid = tids[t]
+            if transition_model.is_final_tid[tid]:
+                e = t + 1
+                sl = transition_model.self_loop_tid[transition_model.id2state[tid]]
+                while e < n and sl != 0 and tids[e] == sl:
+                    e += 1
+                ph = int(transition_model.tid2phone[tid])
+                conf = float(np.mean(self.per_frame_likelihoods[start:e])) if self.per_frame_likelihoods is not None else 0.0
+                out.append(CtmInterval(round(start * frame_shift, 4), round(e * frame_shift, 4), phone_table.get(ph, ph) if phone_table else ph, conf))
+                start = e
+                t = e
+            else:
+                t += 1
+        return out
+
+
+class GmmAligner:
+    """kalpy.gmm.align.GmmAligner (alignment/multiprocessing.py:814-853,1204-1315; online/alignment.py:97-117)."""
+
+    def __init__(self, acoustic_model_path, transition_scale: float = 1.0, acoustic_scale: float = 0.1, self_loop_scale: float = 0.1,
+                 beam: float = 10, retry_beam: float = 40, disambiguation_symbols=None, careful: bool = False, gmm_impl: int = 0):
+        self.acoustic_model_path = str(acoustic_model_path)
+        self.transition_model, self.acoustic_model = K.read_gmm_model(acoustic_model_path)
+        self.transition_scale, self.acoustic_scale, self.self_loop_scale = transition_scale, acoustic_scale, self_loop_scale
+        self.beam, self.retry_beam = beam, retry_beam
+        self.gmm_impl = gmm_impl
+        self.engine = get_engine()
+        self._dm = E.DeviceModel(self.engine, self.transition_model, self.acoustic_model)
+        self.num_done = self.num_error = self.num_retry = 0
+        self.total_likelihood = 0.0
+        self.total_frames = 0
+
+    def boost_silence(self, factor: float, silence_phones: Sequence[int]):
+        """gmm-boost-silence: weights of every pdf reachable from a silence phone are scaled by `factor` (no renormalisation)."""
+        tm = self.transition_model
+        sil = set(int(p) for p in silence_phones)
+        pdfs = set()
+        for ph, _hs, fpdf, spdf in tm.tuples:
+            if int(ph) in sil:
+                pdfs.add(int(fpdf)); pdfs.add(int(spdf))
+        self._dm.boost_pdfs(factor, sorted(pdfs))
+        for j in sorted(pdfs):
+            a, b = self.acoustic_model.offsets[j], self.acoustic_model.offsets[j + 1]
+            self.acoustic_model.weights[a:b] *= factor
+        self.acoustic_model.gconsts = self.acoustic_model.compute_gconsts()
+
+    def _opts(self):
+        return E.align_opts(self.acoustic_scale, self.beam, self.retry_beam)
+
+    def align_batch(self, keys: Sequence[str], fsts: Sequence[K.Fst], feats: np.ndarray, frame_off: np.ndarray) -> List[Optional[Alignment]]:
+        """K2 + K3 for a batch of utterances whose final features are concatenated in `feats`."""
+        batch = E.FstBatch.from_fsts(list(fsts))
+        graphs = E.Graphs(batch, self.transition_model, self.transition_scale, self.self_loop_scale)
+        ll = self._dm.loglikes(np.ascontiguousarray(feats, np.float32), impl=self.gmm_impl)
+        res = E.align_loglikes(self.engine, self._dm, graphs, ll, frame_off, self._opts())
+        out: List[Optional[Alignment]] = []
+        for u, k in enumerate(keys):
+            r = res.utterance(u)
+            if r["status"] >= 2:
+                self.num_error += 1
+                out.append(None)
+                continue
+            if r["status"] == 1:
+                self.num_retry += 1
+            self.num_done += 1
+            self.total_likelihood += r["like"]
+            self.total_frames += len(r["ali"])
+            out.append(Alignment(k, r["ali"], r["words"], r["like"], r["per_frame"]))
+        graphs.close(); batch.close()
+        return out
+
+    def align_utterance(self, training_graph: K.Fst, features: np.ndarray, utterance_id: Optional[str] = None) -> Optional[Alignment]:
+        features = np.ascontiguousarray(features, np.float32)
+        fo = np.asarray([0, features.shape[0]], np.int64)
+        return self.align_batch([utterance_id], [training_graph], features, fo)[0]
+
+    def export_alignments(self, file_name, training_graph_archive: FstArchive, feature_archive: FeatureArchive, word_file_name=None,
+                          likelihood_file_name=None, callback: Optional[Callable] = None, batch_size: int = 512):
+        """ali.ark (+ words.ark, likelihoods.ark); failed utterances are skipped; callback gets (utt_id, log-likelihood)."""
+        wa = K.ArkWriter(file_name)
+        ww = K.ArkWriter(word_file_name) if word_file_name else None
+        wl = K.ArkWriter(likelihood_file_name) if likelihood_file_name else None
+        keys = [k for k in feature_archive.keys if k in training_graph_archive]
+        try:
+            for i in range(0, len(keys), batch_size):
+                ks = keys[i:i + batch_size]
+                feats, fo = feature_archive.batch(ks)
+                alis = self.align_batch(ks, [training_graph_archive[k] for k in ks], feats, fo)
+                for k, a in zip(ks, alis):
+                    if a is None:
+                        continue
+                    wa.write_int_vector(k, np.asarray(a.alignment, np.int32))
+                    if ww:
+                        ww.write_int_vector(k, np.asarray(a.words, np.int32))
+                    if wl:
+                        wl.write_vector(k, a.per_frame_likelihoods)
+                    if callback:
+                        callback((k, a.likelihood))
+        finally:
+            wa.close()
+            if ww:
+                ww.close()
+            if wl:
+                wl.close()
+
+
+class AlignmentArchive:
+    """kalpy.gmm.data.AlignmentArchive (alignment/multiprocessing.py:657,1540,1729-1731,1809)."""
+
+    def __init__(self, file_name, words_file_name=None, likelihood_file_name=None):
+        self._ali = dict(K.read_ark(str(file_name), "int_vector"))
+        self._words = dict(K.read_ark(str(words_file_name), "int_vector")) if words_file_name else {}
+        self._likes = dict(K.read_ark(str(likelihood_file_name), "vector")) if likelihood_file_name else {}
+
+    def __getitem__(self, key) -> Alignment:
+        pf = self._likes.get(key)
+        return Alignment(key, self._ali[key], self._words.get(key, []), None if pf is None else float(np.sum(pf)), pf)
+
+    def __contains__(self, key):
+        return key in self._ali
+
+    def __iter__(self):
+        for k in self._ali:
+            yield self[k]
+
+    def keys(self):
+        return list(self._ali)
+
+    def close(self):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------ statistics
+class GmmStatsAccumulator:
+    """kalpy.gmm.train.GmmStatsAccumulator (alignment/multiprocessing.py:652-666; acoustic_modeling/monophone.py:84,114-120)."""
+
+    def __init__(self, acoustic_model_path):
+        self.transition_model, self.acoustic_model = K.read_gmm_model(acoustic_model_path)
+        self.engine = get_engine()
+        self._dm = E.DeviceModel(self.engine, self.transition_model, self.acoustic_model)
+        self._dm.acc_zero()
+        self.transition_accs = self.transition_model.InitStats()
+        self.gmm_accs = AccumAmDiagGmm.init(self.acoustic_model)
+
+    def accumulate_stats(self, feature_archive: FeatureArchive, alignment_archive: AlignmentArchive, callback: Optional[Callable] = None,
+                         batch_size: int = 512):
+        keys = [k for k in feature_archive.keys if k in alignment_archive]
+        for i in range(0, len(keys), batch_size):
+            ks = keys[i:i + batch_size]
+            feats, fo = feature_archive.batch(ks)
+            ali = np.zeros(int(fo[-1]), np.int32)
+            for j, k in enumerate(ks):
+                a = np.asarray(alignment_archive[k].alignment, np.int32)
+                n = min(len(a), int(fo[j + 1] - fo[j]))
+                ali[fo[j]:fo[j] + n] = a[:n]
+            self._dm.acc_stats(np.ascontiguousarray(feats, np.float32), ali)
+            if callback:
+                callback(len(ks))
+        self.sync()
+
+    def device_tensor(self):
+        """f64 device view of the accumulator block, for torch.distributed.all_reduce (NCCL)."""
+        return self._dm.acc_tensor()
+
+    def sync(self):
+        d = self._dm.acc_read()
+        self.gmm_accs = AccumAmDiagGmm.from_dict(d)
+        self.transition_accs = np.array(d["trans"], dtype=np.float64)

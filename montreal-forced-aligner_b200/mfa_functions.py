@@ -1,0 +1,433 @@
+"""MFA's per-job functions on the hot path, re-hosted on the B200 engine.
+
+Mirrors (same names, argument meaning, files written, callback protocol, error behaviour) of the reference's
+  MfccFunction                 montreal_forced_aligner/corpus/features.py:162-251      (row a1)
+  FinalFeatureFunction         montreal_forced_aligner/corpus/features.py:254-376      (row a4)
+  CompileTrainGraphsFunction   montreal_forced_aligner/alignment/multiprocessing.py:386-574 (row a6)
+  AlignFunction                montreal_forced_aligner/alignment/multiprocessing.py:668-863 (row a7)
+  AccStatsFunction             montreal_forced_aligner/alignment/multiprocessing.py:576-666 (row a9)
+and of the drivers calc_cmvn (corpus/acoustic_corpus.py:1315-1367, row a3), AlignMixin.align_utterances
+(alignment/mixins.py:282-380, row a8) and AcousticModelTrainingMixin.acc_stats (acoustic_modeling/base.py:277-338 upstream,
+row a10).  The reference pulls utterances from its database; here a ``Job`` carries them explicitly (the DB is out of scope).
+File names follow Job.construct_path (db.py:2212-2236).
+"""
+from __future__ import annotations
+
+import os
+import traceback
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import kaldi_io as K
+from . import kalpy_compat as KC
+from .gmm_update import AccumAmDiagGmm, mle_update
+from .lexicon import Lexicon
+
+MetaDict = dict
+
+
+class MultiprocessingError(Exception):
+    """abc.py:939-952: a job function's exception, tagged with the job."""
+
+    def __init__(self, job_name, error_text):
+        super().__init__(f"Job {job_name} encountered an error:\n{error_text}")
+        self.job_name, self.error_text = job_name, error_text
+
+
+class NoAlignmentsError(Exception):
+    """exceptions.py:493-512: raised when no utterance could be aligned."""
+
+    def __init__(self, num_utterances, beam, retry_beam):
+        super().__init__(f"There were no successful alignments for {num_utterances} utterances with beam {beam} / retry beam {retry_beam}; "
+                         f"try beam {beam * 10} / retry beam {retry_beam * 10}")
+
+
+@dataclass
+class Utterance:
+    id: int
+    speaker_id: int
+    path: str
+    normalized_text: str = ""
+    begin: Optional[float] = None
+    end: Optional[float] = None
+    channel: int = 0
+    duration: float = 1.0
+    dictionary_id: int = 1
+    ignored: bool = False
+    alignment_log_likelihood: Optional[float] = None
+    num_frames: Optional[int] = None
+
+    @property
+    def kaldi_id(self) -> str:  # db_polars.py:2186-2192
+        return f"{self.speaker_id}-{self.id}"
+
+
+@dataclass
+class Job:
+    """One unit of parallelism = one set of speakers (corpus/base.py:994-1015); maps to one GPU rank in the B200 build."""
+    id: int
+    utterances: List[Utterance]
+    split_directory: Path
+    dictionary_ids: List[int] = field(default_factory=lambda: [1])
+
+    def construct_path(self, directory, identifier: str, extension: str, dictionary_id: Optional[int] = None) -> Path:
+        if dictionary_id is None:
+            return Path(directory) / f"{identifier}.{self.id}.{extension}"
+        return Path(directory) / f"{identifier}.{dictionary_id}.{self.id}.{extension}"
+
+    def utts(self, dictionary_id: Optional[int] = None) -> List[Utterance]:
+        us = [u for u in self.utterances if not u.ignored and (dictionary_id is None or u.dictionary_id == dictionary_id)]
+        return sorted(us, key=lambda u: u.kaldi_id)
+
+    def write_maps(self, dictionary_id: int):
+        """utt2spk / spk2utt / per-dictionary feats scp (corpus/multiprocessing.py:403-566)."""
+        us = self.utts(dictionary_id)
+        with open(self.construct_path(self.split_directory, "utt2spk", "scp", dictionary_id), "w") as f:
+            for u in us:
+                f.write(f"{u.kaldi_id} {u.speaker_id}\n")
+        feats = {k: (p, o) for k, p, o in K.read_scp(self.construct_path(self.split_directory, "feats", "scp"))}
+        with open(self.construct_path(self.split_directory, "feats", "scp", dictionary_id), "w") as f:
+            for u in us:
+                if u.kaldi_id in feats:
+                    p, o = feats[u.kaldi_id]
+                    f.write(f"{u.kaldi_id} {p}:{o}\n")
+
+    def construct_feature_archive(self, working_directory, dictionary_id: Optional[int] = None, **kwargs) -> KC.FeatureArchive:
+        """db.py:2101-2136: lda.mat in the working directory -> splice+LDA, else deltas; trans.*.scp -> fMLLR."""
+        working_directory = Path(working_directory)
+        fmllr = self.construct_path(working_directory, "trans", "scp", dictionary_id)
+        if not fmllr.exists():
+            fmllr = self.construct_path(self.split_directory, "trans", "scp", dictionary_id)
+        lda = working_directory / "lda.mat"
+        feat = self.construct_path(self.split_directory, "feats", "scp", dictionary_id)
+        if not feat.exists():
+            feat = self.construct_path(self.split_directory, "feats", "scp")
+        u2s = self.construct_path(self.split_directory, "utt2spk", "scp", dictionary_id)
+        return KC.FeatureArchive(feat, utt2spk_file_name=u2s if u2s.exists() else None,
+                                 lda_mat_file_name=lda if lda.exists() else None,
+                                 transform_file_name=fmllr if fmllr.exists() else None,
+                                 deltas=kwargs.get("uses_deltas", not lda.exists()), splices=lda.exists(),
+                                 splice_frames=kwargs.get("splice_context", 3))
+
+
+def assign_jobs(utterances: Sequence[Utterance], num_jobs: int, split_directory) -> List[Job]:
+    """Speakers sorted by utterance count, each to the currently lightest job (corpus/base.py:994-1015).  A speaker never
+    spans jobs, so per-speaker CMVN / fMLLR stay job-local -- and GPU-local when jobs map to ranks."""
+    by_spk: Dict[int, List[Utterance]] = {}
+    for u in utterances:
+        by_spk.setdefault(u.speaker_id, []).append(u)
+    jobs = [Job(i + 1, [], Path(split_directory)) for i in range(num_jobs)]
+    load = [0] * num_jobs
+    for spk, us in sorted(by_spk.items(), key=lambda kv: (-len(kv[1]), kv[0])):
+        j = int(np.argmin(load))
+        jobs[j].utterances.extend(us)
+        load[j] += len(us)
+    return jobs
+
+
+# ------------------------------------------------------------------------------------------------ function base
+@dataclass
+class MfaArguments:
+    job_name: int
+    job: Job            # stands in for the reference's `session` (data.py:268-284)
+    log_path: Optional[Path]
+
+
+class KaldiFunction:
+    """abc.py:915-969: run() wraps _run(); results/progress only through self.callback (ints = progress, tuples = payloads)."""
+
+    def __init__(self, args: MfaArguments):
+        self.args = args
+        self.job_name = args.job_name
+        self.job = args.job
+        self.log_path = args.log_path
+        self.callback: Callable = lambda x: None
+
+    def run(self, callback: Optional[Callable] = None):
+        if callback is not None:
+            self.callback = callback
+        try:
+            self._run()
+        except Exception:
+            raise MultiprocessingError(self.job_name, traceback.format_exc())
+
+    def _run(self):
+        raise NotImplementedError
+
+
+def run_kaldi_function(function, arguments: Sequence[MfaArguments], progress: Optional[Callable] = None):
+    """utils.py:1505-1642 minus the process/thread pool: on a GPU rank the jobs of that rank run back to back."""
+    for a in arguments:
+        results = []
+        function(a).run(results.append)
+        for r in results:
+            if isinstance(r, int):
+                if progress:
+                    progress(r)
+            else:
+                yield r
+
+
+# ------------------------------------------------------------------------------------------------ a1: MFCC
+@dataclass
+class MfccArguments(MfaArguments):
+    data_directory: Path
+    mfcc_computer: KC.MfccComputer
+    pitch_computer: Optional[object] = None
+
+
+class MfccFunction(KaldiFunction):
+    def __init__(self, args: MfccArguments):
+        super().__init__(args)
+        self.data_directory, self.mfcc_computer = Path(args.data_directory), args.mfcc_computer
+        if args.pitch_computer is not None:
+            raise KC.MfaError("pitch features are outside the hot path (SURVEY.md section 2a)")
+
+    def _run(self):
+        ark = self.job.construct_path(self.data_directory, "feats", "ark")
+        scp = self.job.construct_path(self.data_directory, "feats", "scp")
+        if ark.exists():   # features.py:202-203: resume
+            return
+        us = [u for u in self.job.utts() if u.duration >= 0.1]   # features.py:206,223
+        B = 256
+        with K.ArkWriter(ark, scp) as w:
+            for i in range(0, len(us), B):
+                chunk = us[i:i + B]
+                pcm = [KC.Segment(u.path, u.begin, u.end, u.channel).load_audio() for u in chunk]
+                mats = self.mfcc_computer.compute_mfccs_batch(pcm)
+                for u, m in zip(chunk, mats):
+                    if m.shape[0] == 0:
+                        u.ignored = True   # acoustic_corpus.py:880-912: feature failure -> utterance ignored
+                        continue
+                    w.write_matrix(u.kaldi_id, m, compress=True)
+                    self.callback(1)
+
+
+# ------------------------------------------------------------------------------------------------ a3: CMVN
+def calc_cmvn(jobs: Sequence[Job], split_directory) -> Path:
+    """acoustic_corpus.py:1315-1367: per-speaker statistics over all raw features -> cmvn.ark/scp, then per-job cmvn.J.scp."""
+    split_directory = Path(split_directory)
+    all_scp = split_directory / "feats.scp"
+    spk2utt: Dict[str, List[str]] = {}
+    with open(all_scp, "w") as f:
+        for j in jobs:
+            for k, p, o in K.read_scp(j.construct_path(split_directory, "feats", "scp")):
+                f.write(f"{k} {p}:{o}\n")
+            for u in j.utts():
+                spk2utt.setdefault(str(u.speaker_id), []).append(u.kaldi_id)
+    fa = KC.FeatureArchive(all_scp)
+    have = set(fa.keys)
+    spk2utt = {s: [k for k in ks if k in have] for s, ks in spk2utt.items()}
+    spk2utt = {s: ks for s, ks in spk2utt.items() if ks}
+    KC.CmvnComputer().export_cmvn(split_directory / "cmvn.ark", fa, spk2utt, write_scp=True)
+    entries = {k: (p, o) for k, p, o in K.read_scp(split_directory / "cmvn.scp")}
+    for j in jobs:
+        with open(j.construct_path(split_directory, "cmvn", "scp"), "w") as f:
+            for s in sorted({str(u.speaker_id) for u in j.utts()}):
+                if s in entries:
+                    f.write(f"{s} {entries[s][0]}:{entries[s][1]}\n")
+    return split_directory / "cmvn.scp"
+
+
+# ------------------------------------------------------------------------------------------------ a4: final features
+@dataclass
+class FinalFeatureArguments(MfaArguments):
+    data_directory: Path
+    uses_cmvn: bool = True
+    sliding_cmvn: bool = False
+    voiced_only: bool = False
+    subsample_feats: int = 0
+
+
+class FinalFeatureFunction(KaldiFunction):
+    def __init__(self, args: FinalFeatureArguments):
+        super().__init__(args)
+        self.data_directory, self.uses_cmvn = Path(args.data_directory), args.uses_cmvn
+        if args.sliding_cmvn or args.voiced_only or args.subsample_feats:
+            raise KC.MfaError("sliding CMVN / VAD / subsampling are outside the hot path")
+
+    def _run(self):
+        d = self.data_directory
+        feats_scp = self.job.construct_path(d, "feats", "scp")
+        u2s = d / f"utt2spk.{self.job.id}.scp"
+        with open(u2s, "w") as f:
+            for u in self.job.utts():
+                f.write(f"{u.kaldi_id} {u.speaker_id}\n")
+        cmvn = self.job.construct_path(d, "cmvn", "scp")
+        fa = KC.FeatureArchive(feats_scp, utt2spk_file_name=u2s, cmvn_file_name=cmvn if self.uses_cmvn else None)
+        out_ark = self.job.construct_path(d, "final_features", "ark")
+        out_scp = self.job.construct_path(d, "final_features", "scp")
+        with K.ArkWriter(out_ark, out_scp) as w:
+            for k, m in fa:
+                w.write_matrix(k, m, compress=True)   # features.py:356-365: CMVN'd features are re-compressed
+                self.callback(1)
+        fa.close()
+        os.replace(out_scp, feats_scp)   # features.py:368-376: the scp now points at the final features
+        for did in self.job.dictionary_ids:
+            self.job.write_maps(did)
+
+
+# ------------------------------------------------------------------------------------------------ a6: graphs
+@dataclass
+class CompileTrainGraphsArguments(MfaArguments):
+    working_directory: Path
+    lexicon_compilers: Dict[int, Lexicon]
+    tree_path: Path
+    model_path: Path
+    use_g2p: bool = False
+
+
+class CompileTrainGraphsFunction(KaldiFunction):
+    def __init__(self, args: CompileTrainGraphsArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        for did, lexicon in self.a.lexicon_compilers.items():
+            compiler = KC.TrainingGraphCompiler(self.a.model_path, self.a.tree_path, lexicon, use_g2p=self.a.use_g2p, batch_size=500)
+            fst_ark = self.job.construct_path(self.a.working_directory, "fsts", "ark", did)
+            records = [(u.kaldi_id, u.normalized_text) for u in self.job.utts(did)]
+            compiler.export_graphs(fst_ark, records, callback=self.callback)
+            del compiler
+
+
+# ------------------------------------------------------------------------------------------------ a7: align
+@dataclass
+class AlignArguments(MfaArguments):
+    working_directory: Path
+    model_path: Path
+    align_options: MetaDict
+    confidence: bool = False
+    final: bool = False
+    silence_phone_ids: Sequence[int] = ()
+
+
+class AlignFunction(KaldiFunction):
+    def __init__(self, args: AlignArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        opts = dict(self.a.align_options)
+        boost = opts.pop("boost_silence", 1.0)
+        aligner = KC.GmmAligner(self.a.model_path, **opts)
+        if boost != 1.0 and self.a.silence_phone_ids:
+            aligner.boost_silence(boost, self.a.silence_phone_ids)
+        first_pass = str(self.a.model_path).endswith(".alimdl")   # multiprocessing.py:841-863
+        wd = Path(self.a.working_directory)
+        for did in self.job.dictionary_ids:
+            fst_path = self.job.construct_path(wd, "fsts", "ark", did)
+            graphs = KC.FstArchive(fst_path)
+            feats = self.job.construct_feature_archive(wd, did)
+            sfx = "_first_pass" if first_pass else ""
+            ali = self.job.construct_path(wd, "ali" + sfx, "ark", did)
+            words = self.job.construct_path(wd, "words" + sfx, "ark", did)
+            likes = self.job.construct_path(wd, "likelihoods" + sfx, "ark", did)
+            aligner.export_alignments(ali, graphs, feats, word_file_name=words, likelihood_file_name=likes, callback=self.callback)
+            if first_pass:
+                for src, name in ((ali, "ali"), (words, "words"), (likes, "likelihoods")):
+                    link = self.job.construct_path(wd, name, "ark", did)
+                    if link.exists() or link.is_symlink():
+                        link.unlink()
+                    os.symlink(src.name, link)
+            feats.close()
+
+
+def align_utterances(jobs: Sequence[Job], working_directory, model_path, align_options: MetaDict, silence_phone_ids=(), training: bool = False):
+    """AlignMixin.align_utterances (alignment/mixins.py:282-380): drains (utt, loglike), stores per-utterance likelihood / frames,
+    returns the workflow score (mean log-likelihood per utterance); raises NoAlignmentsError when nothing aligned."""
+    args = [AlignArguments(j.id, j, None, Path(working_directory), Path(model_path), align_options, False, False, silence_phone_ids) for j in jobs]
+    by_id = {u.kaldi_id: u for j in jobs for u in j.utterances}
+    likes = []
+    for utt_id, like in run_kaldi_function(AlignFunction, args):
+        u = by_id[utt_id]
+        u.alignment_log_likelihood = like
+        likes.append(like)
+    if not likes:
+        raise NoAlignmentsError(len(by_id), align_options.get("beam", 10), align_options.get("retry_beam", 40))
+    return float(np.mean(likes)), len(by_id) - len(likes)
+
+
+# ------------------------------------------------------------------------------------------------ a9 / a10: statistics + update
+@dataclass
+class AccStatsArguments(MfaArguments):
+    working_directory: Path
+    model_path: Path
+
+
+class AccStatsFunction(KaldiFunction):
+    def __init__(self, args: AccStatsArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        wd = Path(self.a.working_directory)
+        for did in self.job.dictionary_ids:
+            acc = KC.GmmStatsAccumulator(self.a.model_path)
+            feats = self.job.construct_feature_archive(wd, did)
+            alis = KC.AlignmentArchive(self.job.construct_path(wd, "ali", "ark", did))
+            acc.accumulate_stats(feats, alis, callback=self.callback)
+            self.callback((acc.transition_accs, acc.gmm_accs))
+
+
+def acc_stats(jobs: Sequence[Job], working_directory, iteration: int, mixup: int = 0, power: float = 0.25, min_gaussian_occupancy: float = 10.0,
+              all_reduce: Optional[Callable[[np.ndarray], np.ndarray]] = None):
+    """AcousticModelTrainingMixin.acc_stats (acoustic_modeling/base.py:277-338 upstream): sum the jobs' accumulators
+    (`all_reduce`, when given, additionally sums across ranks: NCCL over the packed f64 block), MLE update, write (it+1).mdl.
+    Returns (avg log-likelihood per frame, objective improvement, frames)."""
+    wd = Path(working_directory)
+    model_path = wd / f"{iteration}.mdl"
+    tm, am = K.read_gmm_model(model_path)
+    trans = tm.InitStats()
+    gacc = AccumAmDiagGmm.init(am)
+    args = [AccStatsArguments(j.id, j, None, wd, model_path) for j in jobs]
+    for t, g in run_kaldi_function(AccStatsFunction, args):
+        trans += t            # transition_accs.AddVec(1.0, t)
+        gacc.Add(1.0, g)      # gmm_accs.Add(1.0, g)
+    if all_reduce is not None:
+        flat = np.concatenate([gacc.occ, gacc.mean.ravel(), gacc.var.ravel(), trans, [gacc.tot_like, gacc.tot_frames]])
+        flat = all_reduce(flat)
+        G, D = am.NumGauss(), am.dim
+        gacc.occ = flat[:G]; gacc.mean = flat[G:G + G * D].reshape(G, D); gacc.var = flat[G + G * D:G + 2 * G * D].reshape(G, D)
+        trans = flat[G + 2 * G * D:G + 2 * G * D + tm.num_tids + 1]
+        gacc.tot_like, gacc.tot_frames = float(flat[-2]), float(flat[-1])
+    tm.mle_update(trans)
+    new_am, impr, count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=min_gaussian_occupancy)
+    K.write_gmm_model(wd / f"{iteration + 1}.mdl", tm, new_am)
+    avg = gacc.tot_like / max(gacc.tot_frames, 1.0)
+    return avg, impr, gacc.tot_frames
+
+
+# ------------------------------------------------------------------------------------------------ online path (section 3.2)
+class AlignerError(Exception):
+    """online/alignment.py:108-112: raised when the single utterance cannot be aligned."""
+
+
+def align_utterance_online(model_path, tree_path, lexicon: Lexicon, pcm: np.ndarray, text: str, mfcc_options: Optional[dict] = None,
+                           cmvn: Optional[np.ndarray] = None, lda_mat: Optional[np.ndarray] = None, fmllr_trans: Optional[np.ndarray] = None,
+                           beam: float = 10, retry_beam: float = 40, transition_scale: float = 1.0, acoustic_scale: float = 0.1,
+                           self_loop_scale: float = 0.1, boost_silence: float = 1.0, silence_phone_ids: Sequence[int] = (),
+                           phone_table: Optional[Dict[int, str]] = None):
+    """online/alignment.py:29-123 (align_utterance_online) without files: MFCC -> CMVN -> deltas | splice+LDA -> fMLLR ->
+    compile_fst(text) -> GmmAligner.align_utterance -> phone CTM.  Returns (Alignment, [CtmInterval])."""
+    mc = KC.MfccComputer(**(mfcc_options or {}))
+    raw = mc.compute_mfccs(np.asarray(pcm, np.int16))
+    if cmvn is None:
+        cmvn = KC.CmvnComputer().compute_cmvn_from_features([raw])
+    fo = np.asarray([0, raw.shape[0]], np.int64)
+    fm = None if fmllr_trans is None else np.asarray(fmllr_trans, np.float32)[None]
+    feats = KC.get_engine().features(raw, fo, "lda" if lda_mat is not None else "deltas", lda=lda_mat, fmllr=fm, cmvn_stats=np.asarray(cmvn)[None],
+                                     utt2spk=np.zeros(1, np.int32), n_spk=1)
+    compiler = KC.TrainingGraphCompiler(model_path, tree_path, lexicon)
+    fst = compiler.compile_fst(text)
+    aligner = KC.GmmAligner(model_path, transition_scale=transition_scale, acoustic_scale=acoustic_scale, self_loop_scale=self_loop_scale, beam=beam,
+                            retry_beam=retry_beam)
+    if boost_silence != 1.0 and silence_phone_ids:
+        aligner.boost_silence(boost_silence, silence_phone_ids)
+    ali = aligner.align_utterance(fst, feats)
+    if ali is None:
+        raise AlignerError(f"Could not align the file with the current beam size ({beam}, please try increasing the beam size via `--beam X`")
+    return ali, ali.generate_ctm(aligner.transition_model, phone_table or {}, mc.frame_shift / 1000.0)

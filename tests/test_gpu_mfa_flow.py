@@ -1,0 +1,120 @@
+"""-m gpu: MFA's corpus path and online path end to end through the kalpy-shaped API and the job functions, on files, against the
+oracle chain (including the 8-bit CompressedMatrix round trips of the corpus path)."""
+import numpy as np
+import pytest
+
+from helpers import build_synth_scenario, mono_sample_setup
+from mfa_b200 import kaldi_io as K, kalpy_compat as KC, mfa_functions as MF
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _codec(m):
+    return K.decompress_matrix(K.compress_matrix(m))
+
+
+def test_corpus_path_files_and_training_iteration(tmp_path):
+    sc = build_synth_scenario(seconds=50.0, seed=17, triphone=False, n_phones=8, n_words=40, gauss_per_pdf=2, n_spk=3)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    split = tmp_path / "split2"; work = tmp_path / "work"
+    split.mkdir(); work.mkdir()
+    K.write_gmm_model(work / "1.mdl", tm, am)
+    K.write_tree(work / "tree", sc["tree"])
+    id2w = c.lexicon.id2word
+    utts = []
+    for u in range(c.n_utts):
+        wav = tmp_path / f"u{u}.wav"
+        K.write_wav_int16(wav, c.pcm[c.sample_off[u]:c.sample_off[u + 1]])
+        utts.append(MF.Utterance(u, int(c.utt2spk[u]), str(wav), " ".join(id2w[w] for w in c.transcripts[u]),
+                                 duration=(c.sample_off[u + 1] - c.sample_off[u]) / 16000.0))
+    jobs = MF.assign_jobs(utts, 2, split)
+    # a1: MFCC (compressed ark), a3: CMVN, a4: final features (CMVN applied, re-compressed)
+    mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
+    n_done = []
+    list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs], progress=n_done.append))
+    assert sum(n_done) == c.n_utts
+    MF.calc_cmvn(jobs, split)
+    list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs]))
+    # oracle chain with the same codec round trips
+    raw = {u.kaldi_id: _codec(O.mfcc(c.pcm[c.sample_off[u.id]:c.sample_off[u.id + 1]])) for u in utts}
+    stats = {s: O.cmvn_stats([raw[u.kaldi_id] for u in utts if u.speaker_id == s]) for s in range(c.n_spk)}
+    final = {u.kaldi_id: _codec(O.cmvn_apply(raw[u.kaldi_id], stats[u.speaker_id])) for u in utts}
+    cm = dict(K.read_ark(split / "cmvn.ark", "matrix"))
+    for s in range(c.n_spk):
+        assert np.allclose(cm[str(s)], stats[s], rtol=1e-4, atol=1e-2)
+    got_final = {}
+    for j in jobs:
+        for k, p, o in K.read_scp(j.construct_path(split, "feats", "scp")):
+            got_final[k] = K.read_scp_object(p, o, "matrix")
+    assert set(got_final) == set(final)
+    # 8-bit codec: a 1e-6 difference upstream may move a value by at most one quantisation step in rare cells
+    frac_equal = np.mean([np.mean(np.abs(got_final[k] - final[k]) < 1e-5) for k in final])
+    assert frac_equal > 0.995, frac_equal
+    # a6: graphs, a7/a8: alignment
+    lex = {1: c.lexicon}
+    list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
+                               [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "1.mdl") for j in jobs]))
+    opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
+    score, n_fail = MF.align_utterances(jobs, work, work / "1.mdl", opts)
+    assert n_fail == 0 and np.isfinite(score)
+    g = O.GmmModel.from_am(am)
+    tc = -tm.scaled_transition_log_probs(1.0, 0.1)
+    same = total = 0
+    accs = None
+    for j in jobs:
+        fsts = KC.FstArchive(j.construct_path(work, "fsts", "ark", 1))
+        alis = KC.AlignmentArchive(j.construct_path(work, "ali", "ark", 1), j.construct_path(work, "words", "ark", 1),
+                                   j.construct_path(work, "likelihoods", "ark", 1))
+        for u in j.utts(1):
+            f = O.add_deltas(got_final[u.kaldi_id])   # same (GPU-written) final features: isolates K2/K3 from codec flips
+            r = O.align(fsts[u.kaldi_id], tc, g, tm.tid2pdf, f, f.shape[0])
+            a = alis[u.kaldi_id]
+            assert r["status"] < 2 and a.words == list(r["words"])
+            same += int((np.asarray(a.alignment) == r["ali"]).sum()); total += len(r["ali"])
+            assert abs(u.alignment_log_likelihood - r["like"]) <= 1e-4 * abs(r["like"])
+            accs = O.acc_stats(g, tm.tid2pdf, f, np.asarray(a.alignment, np.int32), tm.num_tids, accs)
+    assert same / total >= 0.999
+    # a9/a10: statistics -> update -> 2.mdl
+    avg, impr, frames = MF.acc_stats(jobs, work, 1, mixup=am.NumGauss() + 10)
+    assert frames == accs["frames"] and abs(avg - accs["like"][0] / accs["frames"]) < 1e-4 * abs(avg)
+    tm2, am2 = K.read_gmm_model(work / "2.mdl")
+    assert am2.NumPdfs() == am.NumPdfs() and am2.NumGauss() >= am.NumGauss() - 5
+    # one EM step on the same alignments must not lower the likelihood of the data under the new model
+    from mfa_b200.gmm_update import AccumAmDiagGmm, mle_update
+    ref_new, _, _ = mle_update(am, AccumAmDiagGmm.from_dict(accs), mixup=0)
+    like_old = like_new = 0.0
+    gn = O.GmmModel.from_am(ref_new)
+    for j in jobs:
+        alis = KC.AlignmentArchive(j.construct_path(work, "ali", "ark", 1))
+        for u in j.utts(1):
+            f = O.add_deltas(got_final[u.kaldi_id])
+            a = np.asarray(alis[u.kaldi_id].alignment, np.int32)
+            like_old += O.acc_stats(g, tm.tid2pdf, f, a, tm.num_tids)["like"][0]
+            like_new += O.acc_stats(gn, tm.tid2pdf, f, a, tm.num_tids)["like"][0]
+    assert like_new >= like_old - 1e-6 * abs(like_old)
+
+
+def test_online_path_config1(tmp_path):
+    ms = mono_sample_setup(tmp_path)
+    tm, am, lex = ms["tm"], ms["am"], ms["lex"]
+    K.write_gmm_model(tmp_path / "final.mdl", tm, am)
+    K.write_tree(tmp_path / "tree", ms["tree"])
+    id2ph = {v: k for k, v in ms["pt"].items()}
+    ali, ctm = MF.align_utterance_online(tmp_path / "final.mdl", tmp_path / "tree", lex, ms["pcm"], ms["text"], phone_table=id2ph)
+    m = O.mfcc(ms["pcm"])
+    f = O.add_deltas(O.cmvn_apply(m, O.cmvn_stats([m])))
+    fst = KC.TrainingGraphCompiler(tmp_path / "final.mdl", tmp_path / "tree", lex).compile_fst(ms["text"])
+    r = O.align(fst, -tm.scaled_transition_log_probs(1.0, 0.1), O.GmmModel.from_am(am), tm.tid2pdf, f, f.shape[0])
+    assert (np.asarray(ali.alignment) == r["ali"]).mean() >= 0.999 and abs(ali.likelihood - r["like"]) <= 1e-4 * abs(r["like"])
+    # phone intervals tile the utterance on the 10 ms grid; boundaries within one frame of the oracle's
+    assert ctm[0].begin == 0.0 and abs(ctm[-1].end - len(r["ali"]) * 0.01) < 1e-6
+    assert all(abs(a.end - b.begin) < 1e-9 for a, b in zip(ctm, ctm[1:]))
+    from mfa_b200.kalpy_compat import Alignment
+    ref_ctm = Alignment("u", r["ali"], r["words"], r["like"], r["per_frame"]).generate_ctm(tm, id2ph, 0.01)
+    assert len(ctm) == len(ref_ctm)
+    assert max(abs(a.begin - b.begin) for a, b in zip(ctm, ref_ctm)) <= 0.0100001
+    assert [x.label for x in ctm] == [x.label for x in ref_ctm] and ctm[1].label.split("_")[0] in ("dh", "sil")
+    # too tight a beam without retry -> AlignerError (online/alignment.py:108-112)
+    with pytest.raises(MF.AlignerError):
+        MF.align_utterance_online(tmp_path / "final.mdl", tmp_path / "tree", lex, ms["pcm"], ms["text"], beam=0.001, retry_beam=0.0)

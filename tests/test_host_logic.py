@@ -1,0 +1,132 @@
+"""Host-side logic of the hot path's callers (no GPU): job partition, file naming, M-step, CTM extraction, and the N>1
+reduction of accumulator statistics over torch.distributed (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from helpers import load_model
+from mfa_b200 import gmm_update as GU, kaldi_io as K, mfa_functions as MF
+
+
+def test_job_assignment_and_paths(tmp_path):
+    rng = np.random.default_rng(0)
+    utts = []
+    for spk in range(9):
+        for k in range(int(rng.integers(1, 30))):
+            utts.append(MF.Utterance(len(utts), spk, f"/x/{spk}_{k}.wav"))
+    jobs = MF.assign_jobs(utts, 3, tmp_path)
+    assert sum(len(j.utterances) for j in jobs) == len(utts)
+    owner = {}
+    for j in jobs:
+        for u in j.utterances:
+            assert owner.setdefault(u.speaker_id, j.id) == j.id      # a speaker never spans jobs
+    loads = [len(j.utterances) for j in jobs]
+    assert max(loads) - min(loads) <= max(np.bincount([u.speaker_id for u in utts]))   # LPT bound
+    j = jobs[0]
+    assert j.construct_path(tmp_path, "ali", "ark", 1).name == f"ali.1.{j.id}.ark"        # db.py:2212-2236
+    assert j.construct_path(tmp_path, "feats", "scp").name == f"feats.{j.id}.scp"
+    assert utts[5].kaldi_id == f"{utts[5].speaker_id}-{utts[5].id}"
+
+
+def test_mle_update_matches_closed_form():
+    tm, am, _ = load_model("g2p")
+    rng = np.random.default_rng(1)
+    G, D = am.NumGauss(), am.dim
+    acc = GU.AccumAmDiagGmm(G, D)
+    acc.occ = rng.uniform(0, 60, G)
+    mu = rng.standard_normal((G, D))
+    var = rng.uniform(0.5, 2.0, (G, D))
+    acc.mean = acc.occ[:, None] * mu
+    acc.var = acc.occ[:, None] * (var + mu ** 2)
+    new, impr, count = GU.mle_update(am, acc, mixup=0, min_gaussian_occupancy=10.0)
+    assert abs(count - acc.occ.sum()) < 1e-6 and new.NumPdfs() == am.NumPdfs()
+    k = 0
+    for j in range(am.NumPdfs()):
+        a, b = am.offsets[j], am.offsets[j + 1]
+        keep = np.where(acc.occ[a:b] > 10.0)[0]
+        if len(keep) == 0:
+            keep = np.array([np.argmax(acc.occ[a:b])])
+        na, nb = new.offsets[j], new.offsets[j + 1]
+        assert nb - na == len(keep)
+        if (acc.occ[a:b][keep] > 10.0).all():
+            assert np.allclose(new.means()[na:nb], mu[a:b][keep], atol=1e-4)
+            assert np.allclose(new.variances()[na:nb], var[a:b][keep], rtol=1e-4)
+            w = acc.occ[a:b][keep] / acc.occ[a:b][keep].sum()
+            # weights are occ/occ_sum over ALL components, renormalised over the survivors
+            assert np.allclose(new.weights[na:nb], w, atol=1e-5)
+        assert abs(new.weights[na:nb].sum() - 1.0) < 1e-5
+    # gconsts of the written model are the closed form
+    assert np.allclose(new.gconsts, new.compute_gconsts())
+    # mix-up: total grows to the target, per-pdf targets follow occupancy^power
+    state_occs = np.asarray([acc.occ[am.offsets[j]:am.offsets[j + 1]].sum() for j in range(am.NumPdfs())])
+    t = GU.get_split_targets(state_occs, 600, 0.25, 20.0)
+    assert t.sum() <= 600 and t.min() >= 1
+    target = new.NumGauss() + 40
+    up, _, _ = GU.mle_update(am, acc, mixup=target)
+    tg = GU.get_split_targets(state_occs, target, 0.25, 20.0)
+    # SplitByCount only ever splits: every pdf ends with max(its current size, its target)
+    for j in range(up.NumPdfs()):
+        assert up.offsets[j + 1] - up.offsets[j] == max(new.offsets[j + 1] - new.offsets[j], tg[j])
+    assert up.NumGauss() > new.NumGauss()
+    for j in range(up.NumPdfs()):
+        assert abs(up.weights[up.offsets[j]:up.offsets[j + 1]].sum() - 1.0) < 1e-5
+
+
+def test_transition_update_and_ctm():
+    tm, am, _ = load_model("mono")
+    stats = tm.InitStats()
+    rng = np.random.default_rng(2)
+    stats[1:] = rng.integers(0, 50, tm.num_tids)
+    old = tm.log_probs.copy()
+    impr, cnt = tm.mle_update(stats)
+    assert cnt > 0 and np.isfinite(tm.log_probs[1:]).all()
+    for ts in range(1, tm.tuples.shape[0] + 1):
+        a, b = tm.state2id[ts], tm.state2id[ts + 1]
+        assert abs(np.exp(tm.log_probs[a:b].astype(np.float64)).sum() - 1.0) < 1e-4
+    # CTM: phone = [forward tids..., final-transition tid, trailing self-loops]
+    from mfa_b200.kalpy_compat import Alignment
+    tm2, _, _ = load_model("mono")
+    ph = 20
+    states = tm2.topo.states_for(ph)
+    seq = []
+    for hs in range(3):
+        ts = [i + 1 for i, r in enumerate(tm2.tuples) if r[0] == ph and r[1] == hs][0]
+        fwd = [tm2.state2id[ts] + k for k, (d, _) in enumerate(states[hs].transitions) if d != hs][0]
+        seq += [fwd] + [tm2.self_loop_tid[ts]] * (hs + 1)
+    ctm = Alignment("u", seq + seq, [], 0.0, np.zeros(2 * len(seq))).generate_ctm(tm2, {ph: "x"}, 0.01)
+    assert [(c.begin, c.end, c.label) for c in ctm] == [(0.0, 0.09, "x"), (0.09, 0.18, "x")]
+
+
+def test_accumulator_allreduce_two_ranks_gloo(tmp_path):
+    """N>1 path on CPU: two processes hold different accumulator blocks; after all_reduce(SUM) over gloo both hold the total,
+    and the M-step run on either rank gives the identical model."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))})
+        sys.path.insert(0, {repr(os.path.dirname(os.path.abspath(__file__)))})
+        import numpy as np, torch, torch.distributed as dist
+        from helpers import load_model
+        from mfa_b200 import gmm_update as GU
+        dist.init_process_group("gloo")
+        r = dist.get_rank()
+        tm, am, _ = load_model("g2p")
+        G, D = am.NumGauss(), am.dim
+        rng = np.random.default_rng(10 + r)
+        flat = rng.uniform(0, 5, G + 2 * G * D + tm.num_tids + 1 + 2)
+        np.save({repr(str(tmp_path))} + f"/in{{r}}.npy", flat)
+        t = torch.from_numpy(flat.copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        np.save({repr(str(tmp_path))} + f"/out{{r}}.npy", t.numpy())
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    i0, i1 = np.load(tmp_path / "in0.npy"), np.load(tmp_path / "in1.npy")
+    o0, o1 = np.load(tmp_path / "out0.npy"), np.load(tmp_path / "out1.npy")
+    assert np.array_equal(o0, o1) and np.allclose(o0, i0 + i1, rtol=1e-15)
