@@ -14,6 +14,14 @@ def _codec(m):
     return K.decompress_matrix(K.compress_matrix(m))
 
 
+def _codec_close(a, b):
+    """Two decodes of (nearly) the same matrix: a 1e-6 upstream difference perturbs the codec's header (all cells move by
+    ~1e-6 of the range) and flips a rare cell by one 8-bit step (<= range/64)."""
+    rng = b.max(0) - b.min(0) + 1e-6
+    d = np.abs(a - b) / rng
+    return float(np.mean(d < 1e-3)), float(d.max())
+
+
 def test_corpus_path_files_and_training_iteration(tmp_path):
     sc = build_synth_scenario(seconds=50.0, seed=17, triphone=False, n_phones=8, n_words=40, gauss_per_pdf=2, n_spk=3)
     c, tm, am = sc["corpus"], sc["tm"], sc["am"]
@@ -36,21 +44,27 @@ def test_corpus_path_files_and_training_iteration(tmp_path):
     assert sum(n_done) == c.n_utts
     MF.calc_cmvn(jobs, split)
     list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs]))
-    # oracle chain with the same codec round trips
-    raw = {u.kaldi_id: _codec(O.mfcc(c.pcm[c.sample_off[u.id]:c.sample_off[u.id + 1]])) for u in utts}
-    stats = {s: O.cmvn_stats([raw[u.kaldi_id] for u in utts if u.speaker_id == s]) for s in range(c.n_spk)}
-    final = {u.kaldi_id: _codec(O.cmvn_apply(raw[u.kaldi_id], stats[u.speaker_id])) for u in utts}
+    # oracle chain with the same codec round trips.  The 8-bit codec turns a 1e-6 upstream difference into (rarely) one
+    # quantisation step, so each stage is checked on the files the previous GPU stage actually wrote.
+    raw_gpu = {}
+    for j in jobs:
+        raw_gpu.update(dict(K.read_ark(j.construct_path(split, "feats", "ark"), "matrix")))
+    raw_ref = {u.kaldi_id: _codec(O.mfcc(c.pcm[c.sample_off[u.id]:c.sample_off[u.id + 1]])) for u in utts}
+    assert set(raw_gpu) == set(raw_ref)
+    cc = [_codec_close(raw_gpu[k], raw_ref[k]) for k in raw_ref]
+    assert np.mean([x[0] for x in cc]) > 0.995 and max(x[1] for x in cc) <= 1.0 / 60
+    stats = {s: O.cmvn_stats([raw_gpu[u.kaldi_id] for u in utts if u.speaker_id == s]) for s in range(c.n_spk)}
     cm = dict(K.read_ark(split / "cmvn.ark", "matrix"))
     for s in range(c.n_spk):
-        assert np.allclose(cm[str(s)], stats[s], rtol=1e-4, atol=1e-2)
+        assert np.allclose(cm[str(s)], stats[s], rtol=1e-9, atol=1e-6)
+    final = {u.kaldi_id: _codec(O.cmvn_apply(raw_gpu[u.kaldi_id], stats[u.speaker_id])) for u in utts}
     got_final = {}
     for j in jobs:
         for k, p, o in K.read_scp(j.construct_path(split, "feats", "scp")):
             got_final[k] = K.read_scp_object(p, o, "matrix")
     assert set(got_final) == set(final)
-    # 8-bit codec: a 1e-6 difference upstream may move a value by at most one quantisation step in rare cells
-    frac_equal = np.mean([np.mean(np.abs(got_final[k] - final[k]) < 1e-5) for k in final])
-    assert frac_equal > 0.995, frac_equal
+    cc = [_codec_close(got_final[k], final[k]) for k in final]
+    assert np.mean([x[0] for x in cc]) > 0.995 and max(x[1] for x in cc) <= 1.0 / 60
     # a6: graphs, a7/a8: alignment
     lex = {1: c.lexicon}
     list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
