@@ -280,8 +280,14 @@ def main():
         per_launch_flops = flops_per_row * gmm_rows / gmm_n
         avg_ms = gmm_ms / gmm_n
         achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
-        roof = {"kernel": "gmm_loglikes (K2)", "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_gmm_tc_traffic.json")
+        if os.path.exists(tp) and args.gmm_impl == 0:
+            # DRAM bytes per frame row from the committed ncu --set full capture x rows of this launch
+            traffic = json.load(open(tp))["dram_bytes_per_row"] * gmm_rows / gmm_n
+        roof = {"kernel": "gmm_loglikes (K2: xsplit + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["source"] + " bf16 sustained",
+                "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1),
                 "launches_per_step": gmm_n, "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": per_launch_flops,
                 "share_of_step": gmm_ms / (dev_ms / args.steps)}
 
