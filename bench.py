@@ -274,20 +274,23 @@ def main():
 
     # ---- roofline of the dominant kernel (K2) --------------------------------------------------------------------
     pk = measured_peaks()
-    flops_per_row = 2.0 * (2 * sc.am.dim + 1) * sc.am.NumGauss()
     roof = None
     if gmm_n > 0 and gmm_ms > 0:
-        per_launch_flops = flops_per_row * gmm_rows / gmm_n
+        # useful FLOPs = 2*(2D+1) per (frame, Gaussian) actually scored: the fused pipeline scores, per utterance, only the pdfs
+        # its graph references (what Kaldi's decodable evaluates lazily), not frames x all Gaussians
+        per_launch_flops = eng.gmm_flops() / gmm_n
         avg_ms = gmm_ms / gmm_n
         achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r1_gmm_tc_traffic.json")
-        if os.path.exists(tp) and args.gmm_impl == 0:
-            # DRAM bytes per frame row from the committed ncu --set full capture x rows of this launch
-            traffic = json.load(open(tp))["dram_bytes_per_row"] * gmm_rows / gmm_n
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            key = {0: "dram_bytes_per_flop_ragged", 2: "dram_bytes_per_flop_dense"}.get(args.gmm_impl)
+            if key in tj:   # DRAM bytes per useful FLOP from the committed ncu --set full capture x FLOPs of this launch
+                traffic = tj[key] * per_launch_flops
         roof = {"kernel": "gmm_loglikes (K2: xsplit + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["source"] + " bf16 sustained",
-                "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1),
+                "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1), "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs",
                 "launches_per_step": gmm_n, "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": per_launch_flops,
                 "share_of_step": gmm_ms / (dev_ms / args.steps)}
 

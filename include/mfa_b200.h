@@ -65,6 +65,9 @@ MFA_API int64_t mfa_engine_launch_count(mfa_engine *e);
 /* CUDA-event timing (on the engine stream) of the K2 launches issued by the most recent API call that ran K2:
  * total milliseconds, number of K2 kernel launches and frame rows they covered (padding included). */
 MFA_API int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_launches, int64_t *n_rows);
+/* useful FLOPs of those launches: 2*(2*dim+1) per (frame, Gaussian) actually scored.  The fused pipeline scores, per utterance,
+ * only the pdfs its graph references (what Kaldi's decodable evaluates lazily), so this is less than frames x all Gaussians. */
+MFA_API int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops);
 
 /* ---- K1: MFCC.  Replaces kalpy MfccComputer.compute_mfccs_for_export
  *      (corpus/features.py:235, online/alignment.py:83).  Options = FeatureConfigMixin.mfcc_options
@@ -212,7 +215,8 @@ typedef struct {
   mfa_feat_opts feat;        /* cmvn_stats may be NULL: then per-speaker stats are computed on device */
   mfa_align_opts align;
   int32_t apply_cmvn;        /* 1: per-speaker CMVN (stats computed on device unless feat.cmvn_stats given) */
-  int32_t gmm_impl;          /* see mfa_gmm_loglikes */
+  int32_t gmm_impl;          /* 0 = auto: tcgen05, per utterance only the pdfs of its graph; 1 = fp32 CUDA-core kernel, all pdfs;
+                                2 = tcgen05, all pdfs (dense) */
   int64_t workspace_bytes;   /* 0 = default (8 GiB) */
 } mfa_pipeline_opts;
 MFA_API int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline_opts *o, const int16_t *pcm,

@@ -24,7 +24,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -38,7 +38,8 @@ struct mfa_engine {
   std::vector<cudaEvent_t> gmm_ev;
   int gmm_ev_used = 0;
   int64_t gmm_rows = 0;
-  void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; }
+  double gmm_flops = 0.0;              // useful FLOPs (2*(2D+1) per frame x Gaussian actually scored) of the K2 launches timed
+  void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; gmm_flops = 0.0; }
   int gmm_timing_begin();
   int gmm_timing_end(int64_t rows);
   // side streams + events: the Viterbi size classes run concurrently (fork/join around the main stream)
@@ -89,6 +90,8 @@ struct mfa_model {
   std::vector<float> h_tc_colscale;    // per-dimension power-of-two feature scaling folded into the weights
   float *d_tc_colscale = nullptr;
   bool tc_ready = false;
+  void *d_tc_rows = nullptr;           // fp16 hi/lo weight rows [2][G][96] (row-major; source of the per-utterance tile gather)
+  uint64_t tc_version = 0;             // bumps whenever the tiling / weights change (invalidates cached ragged plans)
   double *d_acc = nullptr;
   int rebuild_tiles();
   ~mfa_model();
@@ -106,11 +109,15 @@ int launch_features(mfa_engine *e, const mfa_feat_opts *o, const float *d_in, co
                     int out_ld);
 int launch_gmm_ffma(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
 int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
+bool gmm_tc_supported(mfa_model *m);
+int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
+                         const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld);
 int launch_transpose(mfa_engine *e, const float *d_in, int64_t rows, int64_t cols, int64_t in_ld, float *d_out, int64_t out_ld);
 struct ViterbiArgs {
   const mfa_graphs *g; int32_t utt0, n_utts;  // utterances [utt0, utt0+n_utts) of the graph batch
   const float *d_llT; int64_t ld;              // pdf-major log-likelihoods [num_pdfs][ld]
   const int64_t *d_col_off;                    // [n_utts] column of each utterance's frame 0 in d_llT (multiple of 8)
+  const int64_t *d_ll_off, *d_ld_u;            // ragged mode (both non-null): per-utterance block offset / leading dim; rows = local pdfs
   const int64_t *d_frame_off;                  // [n_utts+1] output frame offsets (relative to d_ali / d_per_frame)
   const int64_t *h_frame_off; const int64_t *h_col_off;
   int32_t *d_ali; float *d_per_frame; int32_t *d_words; const int64_t *d_word_off; int32_t *d_num_words;

@@ -114,11 +114,17 @@ extern "C" int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_
   return MFA_OK;
 }
 
+extern "C" int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops) {
+  if (!e || !useful_flops) return set_error(MFA_ERR_INVALID, "null argument");
+  *useful_flops = e->gmm_flops;
+  return MFA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ model
 mfa_model::~mfa_model() {
   if (eng) cudaSetDevice(eng->device);
   for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_tile_pdf0,
-                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc})
+                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows})
     if (p) cudaFree(p);
 }
 
@@ -227,6 +233,7 @@ extern "C" int mfa_model_boost_pdfs(mfa_model *m, float factor, const int32_t *p
 // ------------------------------------------------------------------------------------------------ graphs
 mfa_graphs::~mfa_graphs() {
   if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
+  if (d_rag) { cudaSetDevice(device); cudaFree(d_rag); }
 }
 
 namespace mfa {

@@ -109,6 +109,7 @@ int launch_gmm_ffma(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n
   gmm_ffma_kernel<<<grid, 256, smem, e->stream>>>(d_feats, n_rows, m->dim, m->kdim, m->d_W, m->d_G, m->d_tile_pdf0, m->d_tile_seg, m->n_tiles,
                                                    d_llT, ld);
   e->launches++;
+  e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
   CUDA_TRY(cudaGetLastError());
   return MFA_OK;
 }

@@ -19,6 +19,7 @@
 // columns (all 512 columns): the MMA warp runs one Gaussian tile ahead of the two epilogue warpgroups.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -33,7 +34,7 @@ constexpr uint32_t IMG_BYTES = TM * TK * 2;       // one fp16 image (hi or lo) o
 constexpr uint32_t TILE_BYTES = 2 * IMG_BYTES;    // hi + lo
 constexpr uint32_t LBO_BYTES = (TM / 8) * 128;    // K-adjacent core matrices
 constexpr uint32_t SBO_BYTES = 128;               // row-group-adjacent core matrices
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 640;   // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
 constexpr float kLn2 = 0.69314718055994530942f, kLog2e = 1.44269504088896340736f;
 
 struct TcMeta {  // per Gaussian tile: pdf structure of its 128 columns at 4-column group granularity (32 groups)
@@ -138,13 +139,23 @@ __device__ __forceinline__ void lse_chunk(const uint32_t (&vr)[32], uint32_t gs,
   cs = q;
 }
 
+// One work item = one pair of frame tiles (256 frames) against a run of Gaussian tiles.
+struct TcItem {
+  uint32_t a_tile;       // first of the two A images of the pair
+  uint32_t b_tile0, n_b; // Gaussian tiles [b_tile0, b_tile0 + n_b): images in b_img, segment masks in meta
+  uint32_t rows_valid;   // frames of the pair that exist (<= 256)
+  uint64_t out_off;      // float offset of the pair's first frame in `out`
+  uint32_t ld, pad;      // leading dimension (frames) of this item's output block
+};
+static_assert(sizeof(TcItem) == 32, "TcItem must be 32 bytes");
+
 struct TcParams {
   const uint8_t *a_img;   // [n_frame_tiles (even)][TILE_BYTES]
-  const uint8_t *b_img;   // [n_gauss_tiles][TILE_BYTES]
-  const TcMeta *meta;     // [n_gauss_tiles]
-  int n_pairs, n_tiles, n_splits, tiles_per_split;
-  float *llT;
-  int64_t ld;
+  const uint8_t *b_img;   // [n_b_tiles][TILE_BYTES]
+  const TcMeta *meta;     // [n_b_tiles]; pdf0 = first output row of the tile (global pdf id, or utterance-local pdf index)
+  const TcItem *items;    // [n_items]
+  int n_items;
+  float *out;             // pdf-major blocks: out[item.out_off + (meta.pdf0 + k) * item.ld + frame]
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -171,20 +182,18 @@ gmm_tc_kernel(TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = p.n_pairs * p.n_splits;
+  const int n_items = p.n_items;
 
   if (warp == 0) {
     // ===== producer: bulk copies of the A pair (once per item) and of each B tile =====
     if (lane == 0) {
       uint32_t cnt = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        const int pair = item / p.n_splits, sp = item % p.n_splits;
-        const int n0 = sp * p.tiles_per_split, n1 = min(p.n_tiles, n0 + p.tiles_per_split);
+        const TcItem I = p.items[item];
         mbar_wait(empty_a, (it & 1) ^ 1);
         mbar_expect_tx(full_a, 2 * TILE_BYTES);
-        bulk_g2s(sA, p.a_img + (size_t)(2 * pair) * TILE_BYTES, TILE_BYTES, full_a);
-        bulk_g2s(sA + TILE_BYTES, p.a_img + (size_t)(2 * pair + 1) * TILE_BYTES, TILE_BYTES, full_a);
-        for (int n = n0; n < n1; n++, cnt++) {
+        bulk_g2s(sA, p.a_img + (size_t)I.a_tile * TILE_BYTES, 2 * TILE_BYTES, full_a);
+        for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
           const uint32_t s = cnt & 1;
           mbar_wait(empty_b + s, ((cnt >> 1) & 1) ^ 1);
           mbar_expect_tx(full_b + s, TILE_BYTES);
@@ -200,11 +209,10 @@ gmm_tc_kernel(TcParams p) {
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t cnt = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
-        const int sp = item % p.n_splits;
-        const int n0 = sp * p.tiles_per_split, n1 = min(p.n_tiles, n0 + p.tiles_per_split);
+        const uint32_t n_b = p.items[item].n_b, rows_valid = p.items[item].rows_valid;
         mbar_wait(full_a, it & 1);
         tc_fence_after();
-        for (int n = n0; n < n1; n++, cnt++) {
+        for (uint32_t n = 0; n < n_b; n++, cnt++) {
           const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
           mbar_wait(full_b + s, ph);
           tc_fence_after();
@@ -212,14 +220,16 @@ gmm_tc_kernel(TcParams p) {
           for (int f = 0; f < 2; f++) {
             mbar_wait(tempty + s * 2 + f, ph ^ 1);
             tc_fence_after();
-            const uint32_t d = tmem_base + s * 256 + f * 128;
-            const uint32_t a0 = a_base + f * TILE_BYTES, b0 = b_base + s * TILE_BYTES;
+            if (f == 0 || rows_valid > TM) {   // a pair whose second tile holds no frames skips its 18 MMAs
+              const uint32_t d = tmem_base + s * 256 + f * 128;
+              const uint32_t a0 = a_base + f * TILE_BYTES, b0 = b_base + s * TILE_BYTES;
 #pragma unroll
-            for (int prod = 0; prod < 3; prod++) {
-              const uint32_t ao = a0 + (prod == 2 ? IMG_BYTES : 0), bo = b0 + (prod == 1 ? IMG_BYTES : 0);
+              for (int prod = 0; prod < 3; prod++) {
+                const uint32_t ao = a0 + (prod == 2 ? IMG_BYTES : 0), bo = b0 + (prod == 1 ? IMG_BYTES : 0);
 #pragma unroll
-              for (int k = 0; k < TK / 16; k++)
-                umma_f16(d, make_desc(ao + k * 2 * LBO_BYTES), make_desc(bo + k * 2 * LBO_BYTES), idesc, (prod | k) != 0);
+                for (int k = 0; k < TK / 16; k++)
+                  umma_f16(d, make_desc(ao + k * 2 * LBO_BYTES), make_desc(bo + k * 2 * LBO_BYTES), idesc, (prod | k) != 0);
+              }
             }
             umma_commit(tfull + s * 2 + f);
           }
@@ -229,40 +239,36 @@ gmm_tc_kernel(TcParams p) {
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warpgroup f handles frame tile f; thread = one frame (TMEM lane) =====
-    const int f = (warp - 4) >> 2, wq = warp & 3;
+    // ===== epilogue: 16 warps = 2 accumulator stages x 2 frame tiles x 4 lane quarters; thread = one frame (TMEM lane).
+    // The warps of stage s take every other Gaussian tile, so four epilogue warps share each SM sub-partition and the
+    // TMEM-load / MUFU latency of one is covered by the others. =====
+    const int e = warp - 4, wq = e & 3, f = (e >> 2) & 1, s = e >> 3;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0;   // tiles seen by the CTA so far (all roles count alike); this warp serves those with (cnt & 1) == s
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int pair = item / p.n_splits, sp = item % p.n_splits;
-      const int n0 = sp * p.tiles_per_split, n1 = min(p.n_tiles, n0 + p.tiles_per_split);
-      const int64_t row = (int64_t)(2 * pair + f) * TM + wq * 32 + lane;
-      const bool row_ok = row < p.ld;
-      TcMeta mt = p.meta[n0];
-      for (int n = n0; n < n1; n++, cnt++) {
-        const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
-        const TcMeta cur = mt;
-        if (n + 1 < n1) mt = p.meta[n + 1];
+      const TcItem I = p.items[item];
+      const uint32_t row = f * TM + wq * 32 + lane;
+      const bool row_ok = row < I.rows_valid;
+      const bool tile_live = (uint32_t)(f * TM) < I.rows_valid;
+      float *out_base = p.out + I.out_off + row;
+      for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
+        if ((cnt & 1u) != (uint32_t)s) continue;
+        const uint32_t ph = (cnt >> 1) & 1;
+        const TcMeta cur = p.meta[n];
         mbar_wait(tfull + s * 2 + f, ph);
         tc_fence_after();
+        if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); continue; }
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         float cmx = -INFINITY, cs = 0.0f;
-        float *out = p.llT + (size_t)cur.pdf0 * p.ld + row;
-        uint32_t va[32], vb[32];
-        tmem_ld32(t0, va);
-        tmem_ld_wait();
-        tmem_ld32(t0 + 32, vb);                    // chunk c+1 is in flight while chunk c is reduced
-        lse_chunk(va, cur.gstart & 0xFF, cur.gend & 0xFF, cmx, cs, out, p.ld, row_ok);
-        tmem_ld_wait();
-        tmem_ld32(t0 + 64, va);
-        lse_chunk(vb, (cur.gstart >> 8) & 0xFF, (cur.gend >> 8) & 0xFF, cmx, cs, out, p.ld, row_ok);
-        tmem_ld_wait();
-        tmem_ld32(t0 + 96, vb);
-        lse_chunk(va, (cur.gstart >> 16) & 0xFF, (cur.gend >> 16) & 0xFF, cmx, cs, out, p.ld, row_ok);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tempty + s * 2 + f);           // accumulator drained: the MMA warp may overwrite it
-        lse_chunk(vb, (cur.gstart >> 24) & 0xFF, (cur.gend >> 24) & 0xFF, cmx, cs, out, p.ld, row_ok);
+        float *out = out_base + (size_t)cur.pdf0 * I.ld;
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          tmem_ld32(t0 + 32 * c, v);
+          tmem_ld_wait();
+          if (c == 3) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); }   // accumulator drained: the MMA warp may overwrite it
+          lse_chunk(v, (cur.gstart >> (8 * c)) & 0xFF, (cur.gend >> (8 * c)) & 0xFF, cmx, cs, out, I.ld, row_ok);
+        }
       }
     }
   }
@@ -271,23 +277,28 @@ gmm_tc_kernel(TcParams p) {
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-// features fp32 [n_rows][dim] -> A images (fp16 hi / lo, canonical layout), one 48 KB image per 128-row tile
-__global__ void xsplit_kernel(const float *__restrict__ feats, int64_t n_rows, int dim, const float *__restrict__ colscale, uint8_t *__restrict__ a_img,
-                              int64_t n_tiles) {
+// features fp32 -> A images (fp16 hi / lo, canonical layout), one 48 KB image per 128-frame tile.  Tile t covers feature rows
+// tile_row0[t] .. tile_row0[t] + tile_rows[t] - 1 (rows beyond that are zero), so tiles may follow utterance boundaries.
+__global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const float *__restrict__ colscale, uint8_t *__restrict__ a_img,
+                              int64_t n_tiles, const int64_t *__restrict__ tile_row0, const int32_t *__restrict__ tile_rows, int64_t dense_rows) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, kc, row)
   if (idx >= n_tiles * KC * TM) return;
   const int r = (int)(idx % TM), kc = (int)((idx / TM) % KC);
-  const int64_t tile = idx / (TM * KC), row = tile * TM + r;
+  const int64_t tile = idx / (TM * KC);
+  int64_t row; bool live;
+  if (tile_row0) { live = r < tile_rows[tile]; row = tile_row0[tile] + r; }
+  else { row = tile * TM + r; live = row < dense_rows; }
   __half hi[8], lo[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) {
     const int k = kc * 8 + e;
     float a = 0.0f;
-    if (row < n_rows) {
-      if (k < dim) a = feats[row * dim + k] * colscale[k];
-      else if (k < 2 * dim) { float x = feats[row * dim + (k - dim)] * colscale[k - dim]; x = fminf(fmaxf(x, -240.0f), 240.0f); a = x * x; }
-      else if (k < 2 * dim + 3) a = 1.0f;
-      if (k < dim) a = fminf(fmaxf(a, -240.0f), 240.0f);
+    if (live) {
+      if (k < 2 * dim) {
+        float x = feats[row * dim + (k < dim ? k : k - dim)] * colscale[k < dim ? k : k - dim];
+        x = fminf(fmaxf(x, -240.0f), 240.0f);
+        a = k < dim ? x : x * x;
+      } else if (k < 2 * dim + 3) a = 1.0f;
     }
     hi[e] = __float2half_rn(a);
     lo[e] = __float2half_rn(a - __half2float(hi[e]));
@@ -297,40 +308,71 @@ __global__ void xsplit_kernel(const float *__restrict__ feats, int64_t n_rows, i
   *(uint4 *)(a_img + off + IMG_BYTES) = *(const uint4 *)lo;
 }
 
-// host: fp16 hi/lo images of the weights + per-tile segment masks
+// B images for utterance-specific Gaussian tiles: row r of tile t is Gaussian row_src[t*128 + r] of the model (row-major fp16
+// hi/lo weight rows), or padding (zero weights, gconst column = -60000 -> exp2 -> 0) when row_src < 0.
+__global__ void gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int32_t *__restrict__ row_src, uint8_t *__restrict__ b_img,
+                                int64_t n_tiles, int gcol) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, which, kc, row)
+  if (idx >= n_tiles * 2 * KC * TN) return;
+  const int r = (int)(idx % TN), kc = (int)((idx / TN) % KC), which = (int)((idx / (TN * KC)) % 2);
+  const int64_t tile = idx / (2 * TN * KC);
+  const int g = row_src[tile * TN + r];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (g >= 0) v = *(const uint4 *)(w_rows + ((size_t)which * num_gauss + g) * TK + kc * 8);
+  else if (which == 0 && kc == gcol / 8) {
+    __half pad[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) pad[e] = __float2half_rn(e == gcol % 8 ? -60000.0f : 0.0f);
+    v = *(const uint4 *)pad;
+  }
+  const size_t off = (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES + ((size_t)(kc * (TN / 8) + r / 8) * 64 + (size_t)(r % 8) * 8) * 2;
+  *(uint4 *)(b_img + off) = v;
+}
+
+// host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
 int build_tc(mfa_model *m) {
   const int D = m->dim;
   if (2 * D + 3 > TK) return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96");
-  // per-dimension power-of-two scale: x*s has roughly unit spread under the model
-  std::vector<double> m1(D, 0.0), m2(D, 0.0);
+  std::vector<double> m2(D, 0.0);
   for (int g = 0; g < m->num_gauss; g++)
     for (int d = 0; d < D; d++) {
       double iv = m->h_iv[(size_t)g * D + d], mu = m->h_miv[(size_t)g * D + d] / iv;
-      m1[d] += mu; m2[d] += mu * mu + 1.0 / iv;
+      m2[d] += mu * mu + 1.0 / iv;
     }
   m->h_tc_colscale.assign(D, 1.0f);
   for (int d = 0; d < D; d++) {
-    double mean = m1[d] / m->num_gauss, var = m2[d] / m->num_gauss - mean * mean;
     double rms = std::sqrt(std::max(m2[d] / m->num_gauss, 1e-30));  // second moment about 0: features are not re-centred
-    (void)var;
     m->h_tc_colscale[d] = (float)std::exp2(-std::round(std::log2(rms)));
   }
   const int nt = m->n_tiles;
-  std::vector<uint8_t> img((size_t)nt * TILE_BYTES, 0);
-  std::vector<TcMeta> meta(nt);
+  const int G = m->num_gauss;
+  std::vector<__half> rows((size_t)2 * G * TK, __float2half_rn(0.0f));
   double wmax = 0.0;
-  auto put = [&](int tile, int which, int row, int k, float val) {
-    size_t off = (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES + ((size_t)((k / 8) * (TN / 8) + row / 8) * 64 + (size_t)(row % 8) * 8 + (k % 8)) * 2;
-    __half h = __float2half_rn(val);
-    memcpy(&img[off], &h, 2);
-  };
-  auto split2 = [&](int tile, int row, int k, double w) {
-    float hi = __half2float(__float2half_rn((float)w));
-    put(tile, 0, row, k, hi);
-    put(tile, 1, row, k, (float)(w - (double)hi));
+  auto split2 = [&](int g, int k, double w) {
+    __half h = __float2half_rn((float)w);
+    rows[((size_t)0 * G + g) * TK + k] = h;
+    rows[((size_t)1 * G + g) * TK + k] = __float2half_rn((float)(w - (double)__half2float(h)));
     wmax = std::max(wmax, std::fabs(w));
   };
-  // walk the tiling produced by mfa_model::rebuild_tiles (whole pdfs per tile, in pdf order, column ranges padded to 4)
+  for (int g = 0; g < G; g++) {
+    for (int d = 0; d < D; d++) {
+      double s = m->h_tc_colscale[d];
+      split2(g, d, (double)m->h_miv[(size_t)g * D + d] / s * kLog2e);
+      split2(g, D + d, -0.5 * (double)m->h_iv[(size_t)g * D + d] / (s * s) * kLog2e);
+    }
+    double gc = (double)m->h_gconsts[g] * kLog2e;
+    if (!(gc > -60000.0)) gc = -60000.0;
+    float g1 = __half2float(__float2half_rn((float)gc));
+    float g2 = __half2float(__float2half_rn((float)(gc - g1)));
+    float g3 = (float)(gc - g1 - g2);
+    rows[(size_t)g * TK + 2 * D] = __float2half_rn(g1);
+    rows[(size_t)g * TK + 2 * D + 1] = __float2half_rn(g2);
+    rows[(size_t)g * TK + 2 * D + 2] = __float2half_rn(g3);
+  }
+  if (wmax > 60000.0) return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel");
+  // dense tiling (all pdfs): per-tile masks + source rows; the images themselves are gathered on the device
+  std::vector<TcMeta> meta(nt);
+  std::vector<int32_t> row_src((size_t)nt * TN, -1);
   for (int tl = 0; tl < nt; tl++) {
     int col = 0;
     memset(&meta[tl], 0, sizeof(TcMeta));
@@ -339,39 +381,42 @@ int build_tc(mfa_model *m) {
       const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
       meta[tl].gstart |= 1u << (col / 4);
       meta[tl].gend |= 1u << ((col + pad - 1) / 4);
-      int c = col;
-      for (int g = m->h_pdf_off[pdf]; g < m->h_pdf_off[pdf + 1]; g++, c++) {
-        for (int d = 0; d < D; d++) {
-          double s = m->h_tc_colscale[d];
-          split2(tl, c, d, (double)m->h_miv[(size_t)g * D + d] / s * kLog2e);
-          split2(tl, c, D + d, -0.5 * (double)m->h_iv[(size_t)g * D + d] / (s * s) * kLog2e);
-        }
-        double gc = (double)m->h_gconsts[g] * kLog2e;
-        if (!(gc > -60000.0)) gc = -60000.0;
-        float g1 = __half2float(__float2half_rn((float)gc));
-        float g2 = __half2float(__float2half_rn((float)(gc - g1)));
-        float g3 = (float)(gc - g1 - g2);
-        put(tl, 0, c, 2 * D, g1); put(tl, 0, c, 2 * D + 1, g2); put(tl, 0, c, 2 * D + 2, g3);
-      }
-      for (; c < col + pad; c++) put(tl, 0, c, 2 * D, -60000.0f);  // padding columns inside the pdf's range: exp2 -> 0
+      for (int k = 0; k < ng; k++) row_src[(size_t)tl * TN + col + k] = m->h_pdf_off[pdf] + k;
       col += pad;
     }
     if (col < TN) meta[tl].gstart |= 1u << (col / 4);  // trailing padding: one junk segment that never ends
-    for (; col < TN; col++) put(tl, 0, col, 2 * D, -60000.0f);
   }
-  if (wmax > 60000.0) return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel");
   cudaStream_t s = m->eng->stream;
   if (m->d_tc_w) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree(m->d_tc_w)); m->d_tc_w = nullptr; }
   if (m->d_tc_colscale) { CUDA_TRY(cudaFree(m->d_tc_colscale)); m->d_tc_colscale = nullptr; }
-  size_t meta_bytes = (size_t)nt * sizeof(TcMeta);
-  m->tc_w_bytes = img.size();
-  CUDA_TRY(cudaMalloc(&m->d_tc_w, img.size() + meta_bytes));
-  CUDA_TRY(cudaMemcpyAsync(m->d_tc_w, img.data(), img.size(), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img.size(), meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
+  if (m->d_tc_rows) { CUDA_TRY(cudaFree(m->d_tc_rows)); m->d_tc_rows = nullptr; }
+  const size_t img_bytes = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
+  m->tc_w_bytes = img_bytes;
+  CUDA_TRY(cudaMalloc(&m->d_tc_w, img_bytes + meta_bytes));
+  CUDA_TRY(cudaMalloc(&m->d_tc_rows, rows.size() * sizeof(__half)));
+  CUDA_TRY(cudaMemcpyAsync(m->d_tc_rows, rows.data(), rows.size() * sizeof(__half), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_bytes, meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
+  int32_t *d_src;
+  MFA_TRY(m->eng->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
+  const int64_t total = (int64_t)nt * 2 * KC * TN;
+  gather_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, 2 * D);
+  m->eng->launches++;
   CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, D * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_colscale, m->h_tc_colscale.data(), D * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  static uint64_t version_counter = 0;
+  m->tc_version = ++version_counter;
   m->tc_ready = true;
+  return MFA_OK;
+}
+
+int launch_tc(mfa_engine *e, const TcParams &p) {
+  const size_t smem = 4 * (size_t)TILE_BYTES + 256;
+  CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(p.n_items, e->sm_count);
+  gmm_tc_kernel<<<grid, NTHREADS, smem, e->stream>>>(p);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
   return MFA_OK;
 }
 
@@ -379,6 +424,12 @@ int build_tc(mfa_model *m) {
 
 namespace mfa {
 
+bool gmm_tc_supported(mfa_model *m) {
+  if (!m->tc_ready) { if (build_tc(m) != MFA_OK) return false; }
+  return true;
+}
+
+// dense: every pdf for every row of `d_feats`; output pdf-major llT[pdf][ld]
 int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld) {
   if (n_rows == 0) return MFA_OK;
   if (ld < n_rows) return set_error(MFA_ERR_INVALID, "ld < n_rows");
@@ -391,23 +442,109 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   uint8_t *d_a;
   MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_pairs * 2 * TILE_BYTES, &d_a));
   const int64_t total = n_pairs * 2 * KC * TM;
-  xsplit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(d_feats, n_rows, m->dim, m->d_tc_colscale, d_a, n_pairs * 2);
+  xsplit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_pairs * 2, nullptr, nullptr, n_rows);
   e->launches++;
-  TcParams p;
-  p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
-  p.n_pairs = (int)n_pairs; p.n_tiles = m->n_tiles; p.llT = d_llT; p.ld = ld;
   int splits = 1;
   if (n_pairs < 2 * (int64_t)e->sm_count) splits = (int)std::min<int64_t>(m->n_tiles, (2 * (int64_t)e->sm_count + n_pairs - 1) / n_pairs);
-  p.tiles_per_split = (m->n_tiles + splits - 1) / splits;
-  p.n_splits = (m->n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  const size_t smem = 4 * (size_t)TILE_BYTES + 256;
-  CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t items = n_pairs * p.n_splits;
-  const int grid = (int)std::min<int64_t>(items, e->sm_count);
-  gmm_tc_kernel<<<grid, NTHREADS, smem, e->stream>>>(p);
+  const int tps = (m->n_tiles + splits - 1) / splits;
+  splits = (m->n_tiles + tps - 1) / tps;
+  std::vector<TcItem> items;
+  items.reserve((size_t)n_pairs * splits);
+  for (int64_t pr = 0; pr < n_pairs; pr++)
+    for (int sp = 0; sp < splits; sp++) {
+      TcItem I{};
+      I.a_tile = (uint32_t)(2 * pr); I.b_tile0 = (uint32_t)(sp * tps); I.n_b = (uint32_t)std::min(tps, m->n_tiles - sp * tps);
+      I.rows_valid = (uint32_t)std::min<int64_t>(2 * TM, ld - pr * 2 * TM); I.out_off = (uint64_t)(pr * 2 * TM); I.ld = (uint32_t)ld;
+      items.push_back(I);
+    }
+  if (ld > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "leading dimension exceeds 2^32 frames");
+  TcItem *d_items;
+  MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
+  TcParams p;
+  p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
+  p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
+  e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
+  return launch_tc(e, p);
+}
+
+// ragged: for each utterance only the pdfs its graph references (g->lp2pdf), output block per utterance [P_u][ld_u]
+// at out + ll_off[u].  This is what Kaldi's decodable computes lazily; here it is ~13x less work than the dense matrix.
+int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
+                         const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld) {
+  if (n_utts == 0) return MFA_OK;
+  if (!m->tc_ready) MFA_TRY(build_tc(m));
+  // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles
+  if (g->rag_version != m->tc_version) {
+    g->rag_tile_off.assign(g->n_utts + 1, 0);
+    std::vector<TcMeta> meta;
+    std::vector<int32_t> src;
+    for (int u = 0; u < g->n_utts; u++) {
+      int col = TN;  // force a new tile
+      for (int64_t k = g->lp_off[u]; k < g->lp_off[u + 1]; k++) {
+        const int pdf = g->lp2pdf[k];
+        if (pdf < 0 || pdf >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
+        const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
+        if (col + pad > TN) {
+          if (!meta.empty() && col < TN && (int64_t)meta.size() > g->rag_tile_off[u]) meta.back().gstart |= 1u << (col / 4);
+          TcMeta mt; memset(&mt, 0, sizeof(mt)); mt.pdf0 = (int32_t)(k - g->lp_off[u]);
+          meta.push_back(mt); src.resize(src.size() + TN, -1); col = 0;
+        }
+        meta.back().gstart |= 1u << (col / 4);
+        meta.back().gend |= 1u << ((col + pad - 1) / 4);
+        for (int j = 0; j < ng; j++) src[(meta.size() - 1) * TN + col + j] = m->h_pdf_off[pdf] + j;
+        col += pad;
+      }
+      if (!meta.empty() && col < TN && (int64_t)meta.size() > g->rag_tile_off[u]) meta.back().gstart |= 1u << (col / 4);
+      g->rag_tile_off[u + 1] = (int64_t)meta.size();
+    }
+    if (g->d_rag) { CUDA_TRY(cudaStreamSynchronize(e->stream)); CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
+    const size_t mb = meta.size() * sizeof(TcMeta), sb = src.size() * sizeof(int32_t);
+    CUDA_TRY(cudaMalloc(&g->d_rag, std::max<size_t>(mb + sb, 16)));
+    CUDA_TRY(cudaMemcpyAsync(g->d_rag, meta.data(), mb, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync((uint8_t *)g->d_rag + mb, src.data(), sb, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    g->rag_meta_bytes = mb;
+    g->rag_version = m->tc_version;
+  }
+  const int64_t bt0 = g->rag_tile_off[utt0], n_bt = g->rag_tile_off[utt0 + n_utts] - bt0;
+  // ---- frame tiles follow utterance boundaries (pairs of 128 frames)
+  std::vector<int64_t> tile_row0; std::vector<int32_t> tile_rows; std::vector<TcItem> items;
+  for (int u = 0; u < n_utts; u++) {
+    const int64_t T = h_frame_off[u + 1] - h_frame_off[u];
+    const int64_t nb = g->rag_tile_off[utt0 + u + 1] - g->rag_tile_off[utt0 + u];
+    if (h_ld[u] > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "utterance longer than 2^32 frames");
+    for (int64_t r0 = 0; r0 < T; r0 += 2 * TM) {
+      TcItem I{};
+      I.a_tile = (uint32_t)tile_row0.size();
+      for (int h = 0; h < 2; h++) { tile_row0.push_back(h_row_off[u] + r0 + h * TM); tile_rows.push_back((int32_t)std::max<int64_t>(0, std::min<int64_t>(TM, T - r0 - h * TM))); }
+      I.b_tile0 = (uint32_t)(g->rag_tile_off[utt0 + u] - bt0); I.n_b = (uint32_t)nb;
+      I.rows_valid = (uint32_t)std::min<int64_t>(2 * TM, T - r0); I.out_off = (uint64_t)(h_ll_off[u] + r0); I.ld = (uint32_t)h_ld[u];
+      if (nb > 0) items.push_back(I);
+    }
+    int64_t ng = 0;
+    for (int64_t k = g->lp_off[utt0 + u]; k < g->lp_off[utt0 + u + 1]; k++) ng += m->h_pdf_off[g->lp2pdf[k] + 1] - m->h_pdf_off[g->lp2pdf[k]];
+    e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)ng * (double)T;
+  }
+  if (items.empty()) return MFA_OK;
+  // longest items first (static round-robin over CTAs then balances well)
+  std::stable_sort(items.begin(), items.end(), [](const TcItem &a, const TcItem &b) { return a.n_b > b.n_b; });
+  const int64_t n_at = (int64_t)tile_row0.size();
+  uint8_t *d_a, *d_b; int64_t *d_row0; int32_t *d_rows; TcItem *d_items;
+  MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_at * TILE_BYTES, &d_a));
+  MFA_TRY(e->getT<uint8_t>(DB_BIMG, (size_t)n_bt * TILE_BYTES, &d_b));
+  MFA_TRY(e->upload(DB_TILE_ROW0, tile_row0.data(), tile_row0.size(), &d_row0));
+  MFA_TRY(e->upload(DB_TILE_ROWS, tile_rows.data(), tile_rows.size(), &d_rows));
+  MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
+  const int64_t tot_a = n_at * KC * TM;
+  xsplit_kernel<<<(unsigned)((tot_a + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_at, d_row0, d_rows, 0);
   e->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return MFA_OK;
+  const int32_t *d_src = (const int32_t *)((const uint8_t *)g->d_rag + g->rag_meta_bytes) + bt0 * TN;
+  const int64_t tot_b = n_bt * 2 * KC * TN;
+  gather_b_kernel<<<(unsigned)((tot_b + 255) / 256), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, d_src, d_b, n_bt, 2 * m->dim);
+  e->launches++;
+  TcParams p;
+  p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
+  return launch_tc(e, p);
 }
 
 }  // namespace mfa

@@ -30,5 +30,10 @@ struct mfa_graphs {
   int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr, *d_a_src = nullptr;
   uint32_t *d_a_pack = nullptr;  // dst (low 16) | lp (high 16, 0xFFFF = epsilon)
   float *d_a_w = nullptr, *d_final_w = nullptr;
+  // per-utterance Gaussian tiling for the ragged K2 path (cached against the model's tiling version)
+  uint64_t rag_version = 0;
+  std::vector<int64_t> rag_tile_off;
+  void *d_rag = nullptr;
+  size_t rag_meta_bytes = 0;
   ~mfa_graphs();
 };

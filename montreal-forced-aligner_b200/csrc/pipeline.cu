@@ -147,25 +147,30 @@ int mfa_gmm_loglikes(mfa_engine *e, mfa_model *m, const float *feats, int64_t n_
 
 namespace {
 
-struct ChunkPlan { int u0, n; int64_t ld; std::vector<int64_t> col_off; };
+struct ChunkPlan { int u0, n; int64_t ld; std::vector<int64_t> col_off, ll_off, ld_u; int64_t ll_floats = 0; };
 
 // split utterances into chunks bounded by the log-likelihood block (+ back-pointers) budget
-int plan_chunks(const mfa_graphs *g, const int64_t *frame_off, int n_utts, int num_pdfs, int dim, int64_t budget, std::vector<ChunkPlan> &plans) {
+int plan_chunks(const mfa_graphs *g, const int64_t *frame_off, int n_utts, int num_pdfs, int dim, int64_t budget, std::vector<ChunkPlan> &plans,
+                bool ragged = false) {
   int u = 0;
   while (u < n_utts) {
     ChunkPlan c; c.u0 = u; c.n = 0;
-    int64_t cols = 0, bp = 0;
+    int64_t cols = 0, bp = 0, llf = 0;
     while (u < n_utts) {
       int64_t T = frame_off[u + 1] - frame_off[u];
-      int64_t S = g->st_off[u + 1] - g->st_off[u];
+      int64_t S = g->st_off[u + 1] - g->st_off[u], P = g->lp_off[u + 1] - g->lp_off[u];
       int64_t ncols = cols + round_up(T, 8);
       int64_t nbp = bp + (T + 1) * S * 2;
-      int64_t bytes = round_up(ncols, 128) * ((int64_t)num_pdfs * 4 + (int64_t)dim * 4) + nbp;
+      int64_t nllf = llf + P * round_up(T, 8);
+      // ragged: per-utterance [P_u][ld_u] blocks + A images (384 B per frame) + B images (~P_u*11 Gaussian rows * 384 B)
+      int64_t bytes = ragged ? nllf * 4 + round_up(ncols, 128) * ((int64_t)dim * 4 + 800) + nbp + (P * 12 + 128) * 400
+                             : round_up(ncols, 128) * ((int64_t)num_pdfs * 4 + (int64_t)dim * 4 + 400) + nbp;
       if (c.n > 0 && bytes > budget) break;
-      c.col_off.push_back(cols);
-      cols = ncols; bp = nbp; c.n++; u++;
+      c.col_off.push_back(cols); c.ll_off.push_back(llf); c.ld_u.push_back(round_up(T, 8));
+      cols = ncols; bp = nbp; llf = nllf; c.n++; u++;
     }
     c.ld = round_up(std::max<int64_t>(cols, 1), 128);
+    c.ll_floats = llf;
     plans.push_back(std::move(c));
   }
   return MFA_OK;
@@ -289,16 +294,26 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   // ---- chunks
   std::vector<ChunkPlan> plans;
   int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
-  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, plans));
+  const bool ragged = o->gmm_impl == 0 && gmm_tc_supported(m);
+  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, plans, ragged));
   for (auto &c : plans) {
-    float *d_feats, *d_llT; int64_t *d_col;
+    float *d_feats, *d_llT; int64_t *d_col, *d_ll_off = nullptr, *d_ld_u = nullptr;
     MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
-    MFA_TRY(e->getT<float>(DB_LL, (size_t)P * c.ld, &d_llT));
+    MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
     MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
     CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
     MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
-    MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
+    if (ragged) {
+      MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
+      MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &d_ld_u));
+      MFA_TRY(e->gmm_timing_begin());
+      MFA_TRY(launch_gmm_tc_ragged(e, m, g, c.u0, c.n, d_feats, c.col_off.data(), frame_off + c.u0, d_llT, c.ll_off.data(), c.ld_u.data()));
+      MFA_TRY(e->gmm_timing_end(frame_off[c.u0 + c.n] - frame_off[c.u0]));
+    } else {
+      MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
+    }
     ViterbiArgs a{};
+    a.d_ll_off = d_ll_off; a.d_ld_u = d_ld_u;
     a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
     a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
     a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;

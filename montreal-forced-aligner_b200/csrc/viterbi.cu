@@ -46,7 +46,7 @@ struct VitParams {
   const int32_t *order;
   const float *llT;
   int64_t ld;
-  const int64_t *col_off, *frame_off, *bp_off, *word_off;
+  const int64_t *col_off, *frame_off, *bp_off, *word_off, *ll_off, *ld_u;   // ll_off/ld_u non-null: per-utterance [local pdf][ld_u] blocks
   uint16_t *bp;
   int32_t *ali, *num_words, *words, *status;
   float *per_frame, *total_like;
@@ -102,7 +102,9 @@ viterbi_kernel(VitParams p) {
   const float *fin = p.final_w + p.st_off[ug];
   const int32_t *lp2pdf = p.lp2pdf + p.lp_off[ug];
   uint16_t *bp = p.bp + p.bp_off[ul];           // rows 0..T-1 (+ row T: initial epsilon closure)
-  const float *ll = p.llT + p.col_off[ul];
+  const bool rag = p.ll_off != nullptr;
+  const float *ll = p.llT + (rag ? p.ll_off[ul] : p.col_off[ul]);
+  const int64_t ldu = rag ? p.ld_u[ul] : p.ld;
   const float inf = INFINITY;
 
   int result = MFA_ALIGN_NO_FINAL;
@@ -267,7 +269,7 @@ viterbi_kernel(VitParams p) {
       if ((t & 7) == 0) {
         __syncthreads();
         for (int lp = tid; lp < P; lp += VT) {
-          const float4 *src = (const float4 *)(ll + (size_t)lp2pdf[lp] * p.ld + t);
+          const float4 *src = (const float4 *)(ll + (size_t)(rag ? lp : lp2pdf[lp]) * ldu + t);
           float4 v0 = src[0], v1 = src[1];
           ac[0 * P + lp] = -p.acwt * v0.x; ac[1 * P + lp] = -p.acwt * v0.y; ac[2 * P + lp] = -p.acwt * v0.z; ac[3 * P + lp] = -p.acwt * v0.w;
           ac[4 * P + lp] = -p.acwt * v1.x; ac[5 * P + lp] = -p.acwt * v1.y; ac[6 * P + lp] = -p.acwt * v1.z; ac[7 * P + lp] = -p.acwt * v1.w;
@@ -422,7 +424,7 @@ viterbi_kernel(VitParams p) {
     if ((pk >> 16) == kEps) { if (++guard > S) { p.status[ul] = MFA_ALIGN_NO_FINAL; p.num_words[ul] = 0; return; } continue; }
     guard = 0;
     ali[t] = a_tid[a];
-    pf[t] = ll[(size_t)lp2pdf[pk >> 16] * p.ld + t];
+    pf[t] = ll[(size_t)(rag ? (int)(pk >> 16) : lp2pdf[pk >> 16]) * ldu + t];
     t--;
   }
   if (has_eps) {
@@ -462,8 +464,10 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     need[u] = (size_t)S * 12 + (size_t)P * 32 + (size_t)((S + 1) & ~1) * 4 + 16;
     work[u] = (double)T;
     if (need[u] > limit) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph too large for the Viterbi kernel's shared memory");
-    if (a.h_col_off[u] % 8 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 8");
-    if (a.h_col_off[u] + ((T + 7) / 8) * 8 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 8-frame blocks");
+    if (!a.d_ll_off) {
+      if (a.h_col_off[u] % 8 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 8");
+      if (a.h_col_off[u] + ((T + 7) / 8) * 8 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 8-frame blocks");
+    }
   }
   uint16_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
   MFA_TRY(e->getT<uint16_t>(DB_BP, (size_t)bp_off[n] + 8, &d_bp));
@@ -483,6 +487,7 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.bp_off = d_bp_off; p.word_off = a.d_word_off;
   p.bp = d_bp; p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.per_frame = a.d_per_frame;
   p.total_like = a.d_total_like;
+  p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta; p.min_active = a.opts.min_active;
   CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));

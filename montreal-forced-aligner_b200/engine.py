@@ -115,6 +115,11 @@ class Engine:
         L.check(L.lib().mfa_engine_gmm_timing(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
         return ms.value, n.value, rows.value
 
+    def gmm_flops(self) -> float:
+        f = C.c_double()
+        L.check(L.lib().mfa_engine_gmm_flops(self._h, C.byref(f)))
+        return f.value
+
     # ---- K1 / CMVN / features -----------------------------------------------------------------
     def mfcc(self, pcm, sample_off, opts: L.MfccOpts, out=None):
         so, sop = _host(sample_off, np.int64)

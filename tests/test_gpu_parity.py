@@ -219,7 +219,7 @@ def test_fused_pipeline_config1_sample(eng, tmp_path):
     u2s = np.asarray([0, 0], np.int32)
     dm = E.DeviceModel(eng, tm, am)
     graphs = E.Graphs(batch, tm, 1.0, 0.1)
-    for impl in (1, 0):
+    for impl in (1, 0, 2):   # fp32 CUDA-core (all pdfs), tcgen05 on per-utterance pdf subsets, tcgen05 on all pdfs
         res = E.align_pcm(eng, dm, graphs, pcm, off, u2s, 1, E.mfcc_opts(), "deltas", gmm_impl=impl)
         _, _, feats = oracle_features(pcm_list, u2s, 1, "deltas")
         g = O.GmmModel.from_am(am)
