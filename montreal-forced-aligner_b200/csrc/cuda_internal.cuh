@@ -43,7 +43,7 @@ struct mfa_engine {
   int gmm_timing_begin();
   int gmm_timing_end(int64_t rows);
   // side streams + events: the Viterbi size classes run concurrently (fork/join around the main stream)
-  static constexpr int kSide = 5;
+  static constexpr int kSide = 12;
   cudaStream_t side[kSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
   struct Buf { void *p = nullptr; size_t cap = 0; };

@@ -9,7 +9,7 @@
 //   emitting arcs, keep new tokens under best_new + adaptive_beam -> epsilon closure under the same cutoff;
 //   success iff a live token sits in a final state after the last frame, else rerun with retry_beam.
 //
-// Formulation: sparse token passing.  One CTA per utterance keeps in shared memory a compact list of live states with their
+// Formulation: sparse token passing.  One warp (= one CTA of 32 threads) per utterance keeps in shared memory a compact list of live states with their
 // costs, and per frame (a) pushes every live token under the cutoff over its out-arcs with one 64-bit atomicMin per arc on a
 // packed (ordered cost, arc index) word per destination state -- the first toucher appends the state to the next list --,
 // (b) block-reduces the best new cost, (c) prunes against best + adaptive_beam, renormalises, writes the surviving
@@ -26,6 +26,7 @@
 // Kaldi for one frame; they are pruned by the next GetCutoff unless fewer than min_active tokens are in the beam);
 // (2) ties between equal-cost arcs into a state resolve to the lowest arc index.
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 
 #include "cuda_internal.cuh"
@@ -33,7 +34,7 @@
 using namespace mfa;
 
 namespace {
-constexpr int VT = 128;  // threads per CTA
+constexpr int VT = 32;   // one warp per utterance: every barrier is a __syncwarp, every reduction a shuffle
 constexpr unsigned kNoArc = 0xFFFFu;
 constexpr unsigned kEps = 0xFFFFu;
 
@@ -70,17 +71,15 @@ __device__ __forceinline__ uint32_t f2key(float f) { uint32_t u = __float_as_uin
 __device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 constexpr unsigned long long kEmpty = ~0ull;
 
-__global__ void __launch_bounds__(VT, 6)
+__global__ void __launch_bounds__(VT, 16)
 viterbi_kernel(VitParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ float red_f[2][VT / 32];
-  __shared__ int red_i[2][2 * (VT / 32)];
   __shared__ int sh_cnt, sh_nnext, sh_best_state, sh_bin, sh_rank, sh_head;
   __shared__ float sh_sel;
-  __shared__ int sh_hist[VT];
+  __shared__ int sh_hist[128];
   __shared__ float sh_cand[64];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = 0, lane = tid;
   const int ul = p.order[blockIdx.x];
   const int ug = p.utt0 + ul;
   const int S = (int)(p.st_off[ug + 1] - p.st_off[ug]);
@@ -93,8 +92,8 @@ viterbi_kernel(VitParams p) {
 
   unsigned long long *nxt = (unsigned long long *)smraw;   // [S] packed (ordered cost << 32 | arc), kEmpty = untouched
   float *cost = (float *)(nxt + S);                         // [S] normalised cost of live states (stale elsewhere)
-  float *ac = cost + S;                                     // [8][P]
-  uint16_t *list_a = (uint16_t *)(ac + 8 * P);              // live states (current frame)
+  float *ac = cost + S;                                     // [4][P]
+  uint16_t *list_a = (uint16_t *)(ac + 4 * P);              // live states (current frame)
   uint16_t *list_b = list_a + ((S + 1) & ~1);               // states touched while expanding
   const int32_t *outb = p.in_begin + p.inb_off[ug];         // out-arc offsets [S+1]
   const uint32_t *pack = p.a_pack + p.arc_off[ug];          // dst | lp << 16
@@ -109,29 +108,28 @@ viterbi_kernel(VitParams p) {
 
   int result = MFA_ALIGN_NO_FINAL;
   double offset = 0.0;
-  int par = 0;
   int n_cur = 0;
 
   for (int attempt = 0; attempt < 2; attempt++) {
     const float beam = attempt == 0 ? p.beam : p.retry_beam;
     if (attempt == 1 && !(p.retry_beam > 0.0f)) break;
-    __syncthreads();
+    __syncwarp();
     offset = 0.0;
     for (int s = tid; s < S; s += VT) nxt[s] = kEmpty;
     if (has_eps) for (int s = tid; s < S; s += VT) bp[(size_t)T * S + s] = (uint16_t)kNoArc;
     if (tid == 0) { list_a[0] = (uint16_t)start; cost[start] = 0.0f; }
     n_cur = 1;
-    __syncthreads();
+    __syncwarp();
     float cutoff = inf, adaptive = inf;
     int n_tot = 1, n_beam = 1;
     if (has_eps) {
       // ProcessNonemitting(+inf) from the start state: label-correcting relaxation over epsilon arcs.
       // Live states are marked in nxt with their current (cost, arc) so improvements are detected by atomicMin.
       if (tid == 0) { nxt[start] = ((unsigned long long)f2key(0.0f) << 32) | kNoArc; sh_cnt = 1; sh_head = 0; }
-      __syncthreads();
+      __syncwarp();
       for (;;) {
         const int head = sh_head, n = sh_cnt;
-        __syncthreads();
+        __syncwarp();
         if (head >= n) break;
         for (int i = head + tid; i < n; i += VT) {
           const int s = list_a[i];
@@ -144,15 +142,15 @@ viterbi_kernel(VitParams p) {
             if (old == kEmpty) list_a[atomicAdd(&sh_cnt, 1)] = (uint16_t)d;
           }
         }
-        __syncthreads();
+        __syncwarp();
         if (tid == 0) sh_head = n;
-        __syncthreads();
+        __syncwarp();
       }
       // a state's cost may have improved after it was expanded: iterate the whole list to a fixed point
       for (;;) {
-        __syncthreads();
+        __syncwarp();
         if (tid == 0) sh_head = 0;
-        __syncthreads();
+        __syncwarp();
         const int n = sh_cnt;
         for (int i = tid; i < n; i += VT) {
           const int s = list_a[i];
@@ -166,7 +164,7 @@ viterbi_kernel(VitParams p) {
             if (cand < old) { sh_head = 1; if (old == kEmpty) list_a[atomicAdd(&sh_cnt, 1)] = (uint16_t)d; }
           }
         }
-        __syncthreads();
+        __syncwarp();
         if (!sh_head) break;
       }
       n_cur = sh_cnt;
@@ -179,12 +177,8 @@ viterbi_kernel(VitParams p) {
         nxt[s] = kEmpty;
         ct++; if (v <= beam) cb++;
       }
-      ct = warp_sum(ct); cb = warp_sum(cb);
-      if (lane == 0) { red_i[par][warp] = ct; red_i[par][VT / 32 + warp] = cb; }
-      __syncthreads();
-      n_tot = 0; n_beam = 0;
-      for (int w = 0; w < VT / 32; w++) { n_tot += red_i[par][w]; n_beam += red_i[par][VT / 32 + w]; }
-      par ^= 1;
+      n_tot = warp_sum(ct); n_beam = warp_sum(cb);
+      __syncwarp();
     }
     bool dead = false;
     for (int64_t t = 0; t < T; t++) {
@@ -193,22 +187,32 @@ viterbi_kernel(VitParams p) {
       else if (n_beam > p.min_active) { cutoff = beam; adaptive = beam; }
       else {
         // min_active-th order statistic (0-based) of the live costs (Kaldi: nth_element on the token costs).
-        // Block-parallel: 128-bin histogram over [0, max] -> the bin holding that rank -> exact rank inside the bin.
+        if (n_cur <= 64) {
+          // the common case: each lane holds two costs, ranks them against all others by shuffle broadcast
+          const float x0 = lane < n_cur ? cost[list_a[lane]] : inf, x1 = lane + 32 < n_cur ? cost[list_a[lane + 32]] : inf;
+          int r0 = 0, r1 = 0;
+          for (int j = 0; j < n_cur; j++) {
+            const float y = __shfl_sync(0xffffffffu, j < 32 ? x0 : x1, j & 31);
+            r0 += (y < x0) || (y == x0 && j < lane);
+            r1 += (y < x1) || (y == x1 && j < lane + 32);
+          }
+          const unsigned m0 = __ballot_sync(0xffffffffu, r0 == p.min_active && lane < n_cur);
+          const unsigned m1 = __ballot_sync(0xffffffffu, r1 == p.min_active && lane + 32 < n_cur);
+          cutoff = m0 ? __shfl_sync(0xffffffffu, x0, __ffs(m0) - 1) : __shfl_sync(0xffffffffu, x1, __ffs(m1) - 1);
+          adaptive = cutoff + p.beam_delta;
+        } else {
+        // many live tokens: 128-bin histogram over [0, max] -> the bin holding that rank -> exact rank inside the bin.
         float lmx = 0.0f;
         for (int i = tid; i < n_cur; i += VT) lmx = fmaxf(lmx, cost[list_a[i]]);
 #pragma unroll
         for (int o = 16; o; o >>= 1) lmx = fmaxf(lmx, __shfl_xor_sync(0xffffffffu, lmx, o));
-        if (lane == 0) red_f[par][warp] = lmx;
-        sh_hist[tid] = 0;
+        for (int i = tid; i < 128; i += VT) sh_hist[i] = 0;
         if (tid == 0) sh_cnt = 0;
-        __syncthreads();
-        float vmax = red_f[par][0];
-#pragma unroll
-        for (int w = 1; w < VT / 32; w++) vmax = fmaxf(vmax, red_f[par][w]);
-        par ^= 1;
+        __syncwarp();
+        const float vmax = lmx;
         const float scale = 128.0f / (vmax * 1.000001f + 1e-30f);
         for (int i = tid; i < n_cur; i += VT) atomicAdd(&sh_hist[min(127, (int)(cost[list_a[i]] * scale))], 1);
-        __syncthreads();
+        __syncwarp();
         if (warp == 0) {
           int c0 = sh_hist[4 * lane], c1 = sh_hist[4 * lane + 1], c2 = sh_hist[4 * lane + 2], c3 = sh_hist[4 * lane + 3];
           int tot = c0 + c1 + c2 + c3, incl = tot;
@@ -222,13 +226,13 @@ viterbi_kernel(VitParams p) {
             sh_bin = b; sh_rank = k - e;
           }
         }
-        __syncthreads();
+        __syncwarp();
         const int bin = sh_bin;
         for (int i = tid; i < n_cur; i += VT) {
           const float v = cost[list_a[i]];
           if (min(127, (int)(v * scale)) == bin) { int idx = atomicAdd(&sh_cnt, 1); if (idx < 64) sh_cand[idx] = v; }
         }
-        __syncthreads();
+        __syncwarp();
         const int nc = sh_cnt;
         if (nc <= 64) {
           if (warp == 0) {
@@ -244,7 +248,7 @@ viterbi_kernel(VitParams p) {
               }
             }
           }
-          __syncthreads();
+          __syncwarp();
         } else {
           // many tokens share one bin (clustered costs): exact bitwise radix select over the live costs (warp 0)
           if (warp == 0) {
@@ -260,24 +264,23 @@ viterbi_kernel(VitParams p) {
             }
             if (lane == 0) sh_sel = __uint_as_float(prefix);
           }
-          __syncthreads();
+          __syncwarp();
         }
         cutoff = sh_sel; adaptive = cutoff + p.beam_delta;
-        __syncthreads();
+        __syncwarp();
+        }
       }
-      // ---- acoustic costs for frames t..t+7
-      if ((t & 7) == 0) {
-        __syncthreads();
+      // ---- acoustic costs for frames t..t+3 (one 16-byte streaming load per pdf: the matrix is read exactly once)
+      if ((t & 3) == 0) {
+        __syncwarp();
         for (int lp = tid; lp < P; lp += VT) {
-          const float4 *src = (const float4 *)(ll + (size_t)(rag ? lp : lp2pdf[lp]) * ldu + t);
-          float4 v0 = src[0], v1 = src[1];
+          const float4 v0 = __ldcs((const float4 *)(ll + (size_t)(rag ? lp : lp2pdf[lp]) * ldu + t));
           ac[0 * P + lp] = -p.acwt * v0.x; ac[1 * P + lp] = -p.acwt * v0.y; ac[2 * P + lp] = -p.acwt * v0.z; ac[3 * P + lp] = -p.acwt * v0.w;
-          ac[4 * P + lp] = -p.acwt * v1.x; ac[5 * P + lp] = -p.acwt * v1.y; ac[6 * P + lp] = -p.acwt * v1.z; ac[7 * P + lp] = -p.acwt * v1.w;
         }
       }
       if (tid == 0) sh_cnt = 0;
-      __syncthreads();
-      const float *acf = ac + (int)(t & 7) * P;
+      __syncwarp();
+      const float *acf = ac + (int)(t & 3) * P;
       uint16_t *bprow = bp + (size_t)t * S;
       // ---- ProcessEmitting: push every live token under the cutoff over its emitting out-arcs
       for (int i = tid; i < n_cur; i += VT) {
@@ -294,17 +297,13 @@ viterbi_kernel(VitParams p) {
           if (old == kEmpty) list_b[atomicAdd(&sh_cnt, 1)] = (uint16_t)d;
         }
       }
-      __syncthreads();
+      __syncwarp();
       const int n_new = sh_cnt;
       float lmin = inf;
       for (int i = tid; i < n_new; i += VT) lmin = fminf(lmin, key2f((uint32_t)(nxt[list_b[i]] >> 32)));
-      lmin = warp_min(lmin);
-      if (lane == 0) red_f[par][warp] = lmin;
+      const float best_new = warp_min(lmin);
       if (tid == 0) sh_nnext = 0;
-      __syncthreads();
-      float best_new = red_f[par][0];
-#pragma unroll
-      for (int w = 1; w < VT / 32; w++) best_new = fminf(best_new, red_f[par][w]);
+      __syncwarp();
       if (!(best_new < inf)) { dead = true; break; }
       const float next_cutoff = best_new + adaptive;  // inf stays inf
       int ct = 0, cb = 0;
@@ -334,9 +333,9 @@ viterbi_kernel(VitParams p) {
           } else nxt[d] = kEmpty;
         }
         for (;;) {
-          __syncthreads();
+          __syncwarp();
           if (tid == 0) sh_head = 0;
-          __syncthreads();
+          __syncwarp();
           const int n = sh_nnext;
           for (int i = tid; i < n; i += VT) {
             const int s = list_a[i];
@@ -353,7 +352,7 @@ viterbi_kernel(VitParams p) {
               if (cand < old) { sh_head = 1; if (old == kEmpty) list_a[atomicAdd(&sh_nnext, 1)] = (uint16_t)d; }
             }
           }
-          __syncthreads();
+          __syncwarp();
           if (!sh_head) break;
         }
         const int n = sh_nnext;
@@ -366,41 +365,32 @@ viterbi_kernel(VitParams p) {
           ct++; if (v <= beam) cb++;
         }
       }
-      ct = warp_sum(ct); cb = warp_sum(cb);
-      if (lane == 0) { red_i[par][warp] = ct; red_i[par][VT / 32 + warp] = cb; }
-      __syncthreads();
-      n_tot = 0; n_beam = 0;
-#pragma unroll
-      for (int w = 0; w < VT / 32; w++) { n_tot += red_i[par][w]; n_beam += red_i[par][VT / 32 + w]; }
+      n_tot = warp_sum(ct); n_beam = warp_sum(cb);
+      __syncwarp();
       n_cur = sh_nnext;
-      par ^= 1;
       offset += (double)best_new;
     }
     if (dead) {
       // leave nxt clean for the retry
-      __syncthreads();
+      __syncwarp();
       continue;
     }
     // ---- ReachedFinal / best final token
     float lbest = inf;
     for (int i = tid; i < n_cur; i += VT) { const int s = list_a[i]; lbest = fminf(lbest, cost[s] + fin[s]); }
-    lbest = warp_min(lbest);
-    if (lane == 0) red_f[par][warp] = lbest;
+    const float fbest = warp_min(lbest);
     if (tid == 0) sh_best_state = 0x7fffffff;
-    __syncthreads();
-    float fbest = red_f[par][0];
-    for (int w = 1; w < VT / 32; w++) fbest = fminf(fbest, red_f[par][w]);
-    par ^= 1;
+    __syncwarp();
     if (fbest < inf) {
       for (int i = tid; i < n_cur; i += VT) { const int s = list_a[i]; if (cost[s] + fin[s] == fbest) atomicMin(&sh_best_state, s); }
-      __syncthreads();
+      __syncwarp();
       result = attempt == 0 ? MFA_ALIGN_OK : MFA_ALIGN_RETRIED;
       if (tid == 0) p.total_like[ul] = (float)(-(offset + (double)fbest) / (double)p.acwt);
       break;
     }
-    __syncthreads();
+    __syncwarp();
   }
-  __syncthreads();  // all back-pointer writes of this CTA are visible to thread 0 below (same CTA, global memory)
+  __syncwarp();  // all back-pointer writes of this CTA are visible to thread 0 below (same CTA, global memory)
   if (tid != 0) return;
   p.status[ul] = result;
   if (result == MFA_ALIGN_NO_FINAL) { p.num_words[ul] = 0; p.total_like[ul] = 0.0f; return; }
@@ -461,21 +451,24 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     int64_t S = g->st_off[ug + 1] - g->st_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
     int64_t T = a.h_frame_off[u + 1] - a.h_frame_off[u];
     bp_off[u + 1] = bp_off[u] + (T + (g->n_eps[ug] > 0 ? 1 : 0)) * S;
-    need[u] = (size_t)S * 12 + (size_t)P * 32 + (size_t)((S + 1) & ~1) * 4 + 16;
+    need[u] = (size_t)S * 12 + (size_t)P * 16 + (size_t)((S + 1) & ~1) * 4 + 16;
     work[u] = (double)T;
     if (need[u] > limit) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph too large for the Viterbi kernel's shared memory");
     if (!a.d_ll_off) {
-      if (a.h_col_off[u] % 8 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 8");
-      if (a.h_col_off[u] + ((T + 7) / 8) * 8 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 8-frame blocks");
+      if (a.h_col_off[u] % 4 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 4");
+      if (a.h_col_off[u] + ((T + 3) / 4) * 4 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 4-frame blocks");
     }
   }
   uint16_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
   MFA_TRY(e->getT<uint16_t>(DB_BP, (size_t)bp_off[n] + 8, &d_bp));
   MFA_TRY(e->upload(DB_BP_OFF, bp_off.data(), bp_off.size(), &d_bp_off));
   // classes by shared-memory need (occupancy); inside a class, longest utterance first
-  const size_t bounds[4] = {24 * 1024, 48 * 1024, 100 * 1024, limit};
+  constexpr int NC = mfa_engine::kSide;
+  size_t bounds[NC];
+  for (int c = 0; c < NC; c++) bounds[c] = std::min<size_t>(limit, (size_t)(7168.0 * std::pow(2.0, 0.5 * c)));   // 7, 9.9, 14, ... KB
+  bounds[NC - 1] = limit;
   std::vector<int> cls(n);
-  for (int u = 0; u < n; u++) { int c = 0; while (c < 3 && need[u] > bounds[c]) c++; cls[u] = c; }
+  for (int u = 0; u < n; u++) { int c = 0; while (c < NC - 1 && need[u] > bounds[c]) c++; cls[u] = c; }
   std::vector<int32_t> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cls[x] != cls[y] ? cls[x] < cls[y] : work[x] > work[y]; });
@@ -492,7 +485,7 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
   // largest-need classes first: they hold the biggest graphs; the small ones fill in around them on the side streams
-  for (int c = 3; c >= 0; c--) {
+  for (int c = NC - 1; c >= 0; c--) {
     int pos = 0, cnt = 0;
     for (int k = 0; k < n; k++) { if (cls[order[k]] < c) pos++; }
     size_t mx = 0;
