@@ -24,7 +24,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -46,6 +46,11 @@ struct mfa_engine {
   static constexpr int kSide = 12;
   cudaStream_t side[kSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
+  std::vector<cudaEvent_t> ev_piece;   // H2D pieces of the PCM upload (end-to-end path)
+  // cached MFCC tables (device blob in DB_MFCC_TAB) for the last option set
+  bool mfcc_tab_valid = false;
+  mfa_mfcc_opts mfcc_tab_opts{};
+  alignas(8) unsigned char mfcc_tab_desc[96] = {};
   struct Buf { void *p = nullptr; size_t cap = 0; };
   Buf dev[DB_N];
   Buf pin[PB_N];
@@ -101,7 +106,7 @@ namespace mfa {
 int upload_graphs(mfa_engine *e, mfa_graphs *g);
 // kernels' host launchers (device pointers only)
 int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, const int64_t *d_sample_off, int32_t n_utts,
-                const int64_t *d_frame_off, int64_t n_frames, float *d_out);
+                const int64_t *d_frame_off, int64_t n_frames, float *d_out, int64_t frame_base = 0);
 int launch_cmvn_stats(mfa_engine *e, const float *d_feats, int dim, const int64_t *d_frame_off, const int32_t *h_utt2spk,
                       int32_t n_utts, int32_t n_spk, double *d_stats);
 int launch_features(mfa_engine *e, const mfa_feat_opts *o, const float *d_in, const int64_t *d_frame_off, const int64_t *h_frame_off,

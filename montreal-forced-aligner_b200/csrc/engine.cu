@@ -71,6 +71,7 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto &b : e->dev) if (b.p) cudaFree(b.p);
   for (auto &b : e->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : e->gmm_ev) cudaEventDestroy(ev);
+  for (auto ev : e->ev_piece) cudaEventDestroy(ev);
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   cudaStreamDestroy(e->stream);

@@ -88,7 +88,7 @@ constexpr int kWarps = 4;
 
 __global__ void __launch_bounds__(kWarps * 32)
 mfcc_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restrict__ pcm, const int64_t *__restrict__ sample_off,
-            const int64_t *__restrict__ frame_off, int n_utts, int64_t n_frames, int64_t frames_per_warp, float *__restrict__ out,
+            const int64_t *__restrict__ frame_off, int n_utts, int64_t frame_base, int64_t n_frames, int64_t frames_per_warp, float *__restrict__ out,
             float preemph, int snip_edges, int remove_dc, int use_energy, int raw_energy, float log_energy_floor) {
   extern __shared__ float smem[];
   float *stab = smem;                                   // t.total floats
@@ -103,8 +103,8 @@ mfcc_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restri
   float2 *bufA = (float2 *)wbuf, *bufB = (float2 *)(wbuf + 2 * t.NB);
 
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
-  int64_t f0 = gw * frames_per_warp, f1 = f0 + frames_per_warp;
-  if (f1 > n_frames) f1 = n_frames;
+  int64_t f0 = frame_base + gw * frames_per_warp, f1 = f0 + frames_per_warp;
+  if (f1 > frame_base + n_frames) f1 = frame_base + n_frames;
   if (f0 >= f1) return;
   // utterance of frame f0: largest u with frame_off[u] <= f0
   int lo = 0, hi = n_utts - 1;
@@ -243,15 +243,25 @@ __global__ void cmvn_reduce_kernel(const double *__restrict__ part, int dim, con
 
 namespace mfa {
 
+// d_sample_off / d_frame_off are the (global) offset arrays of the utterances [0, n_utts) handed in; the launch covers the frames
+// [frame_base, frame_base + n_frames) of that numbering (pieces of a batch can be launched as their PCM arrives).
 int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, const int64_t *d_sample_off, int32_t n_utts,
-                const int64_t *d_frame_off, int64_t n_frames, float *d_out) {
+                const int64_t *d_frame_off, int64_t n_frames, float *d_out, int64_t frame_base) {
   if (n_frames == 0 || n_utts == 0) return MFA_OK;
-  MfccTables t; std::vector<float> blob;
-  MFA_TRY(build_tables(o, t, blob));
+  static_assert(sizeof(MfccTables) <= sizeof(e->mfcc_tab_desc), "table descriptor cache too small");
+  MfccTables t;
   float *d_tab;
-  MFA_TRY(e->getT<float>(DB_SCRATCH, blob.size(), &d_tab));
-  CUDA_TRY(cudaMemcpyAsync(d_tab, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));  // blob is a local
+  if (e->mfcc_tab_valid && memcmp(&e->mfcc_tab_opts, o, sizeof(*o)) == 0) {
+    memcpy(&t, e->mfcc_tab_desc, sizeof(t));
+    d_tab = (float *)e->dev[DB_MFCC_TAB].p;
+  } else {
+    std::vector<float> blob;
+    MFA_TRY(build_tables(o, t, blob));
+    MFA_TRY(e->getT<float>(DB_MFCC_TAB, blob.size(), &d_tab));
+    CUDA_TRY(cudaMemcpyAsync(d_tab, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));  // blob is a local
+    memcpy(e->mfcc_tab_desc, &t, sizeof(t)); e->mfcc_tab_opts = *o; e->mfcc_tab_valid = true;
+  }
   size_t smem = ((t.total + 3) / 4 * 4 + kWarps * (4 * t.NB + 4)) * sizeof(float);
   if (smem > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "MFCC tables exceed shared memory");
   CUDA_TRY(cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -261,7 +271,7 @@ int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, con
   int64_t warps = (n_frames + fpw - 1) / fpw;
   int blocks = (int)((warps + kWarps - 1) / kWarps);
   float lef = (o->energy_floor > 0.0f) ? logf(o->energy_floor) : -INFINITY;
-  mfcc_kernel<<<blocks, kWarps * 32, smem, e->stream>>>(t, d_tab, d_pcm, d_sample_off, d_frame_off, n_utts, n_frames, fpw, d_out,
+  mfcc_kernel<<<blocks, kWarps * 32, smem, e->stream>>>(t, d_tab, d_pcm, d_sample_off, d_frame_off, n_utts, frame_base, n_frames, fpw, d_out,
                                                          o->preemph_coeff, o->snip_edges, o->remove_dc_offset, o->use_energy, o->raw_energy, lef);
   e->launches++;
   CUDA_TRY(cudaGetLastError());

@@ -267,7 +267,9 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   MFA_TRY(e->upload(DB_SAMPLE_OFF, sample_off, (size_t)n_utts + 1, &d_so));
   MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
   MFA_TRY(e->upload(DB_UTT2SPK, utt2spk, (size_t)n_utts, &d_u2s));
-  MFA_TRY(to_device(e, DB_PCM, pcm, (size_t)ns, where, &d_pcm));
+  // host PCM is uploaded in pieces on a copy stream; each piece's MFCC launch waits only for its own bytes (below)
+  if (where == MFA_DEVICE) d_pcm = pcm;
+  else { int16_t *d; MFA_TRY(e->getT<int16_t>(DB_PCM, (size_t)std::max<int64_t>(ns, 1), &d)); d_pcm = d; }
   AlignIO io;
   MFA_TRY(out_buffer(e, DB_ALI, ali, (size_t)nf, where, &io.d_ali));
   MFA_TRY(out_buffer(e, DB_PERFRAME, per_frame, (size_t)nf, where, &io.d_pf));
@@ -282,7 +284,27 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   // ---- K1 + CMVN statistics over the whole batch
   float *d_mfcc; double *d_stats = nullptr;
   MFA_TRY(e->getT<float>(DB_MFCC, (size_t)nf * C, &d_mfcc));
-  MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
+  if (where == MFA_DEVICE) {
+    MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
+  } else {
+    const int64_t piece = std::max<int64_t>((int64_t)16 << 20, ns / 12 + 1);   // samples per H2D piece (>= 32 MB)
+    cudaStream_t cs = e->side[0];
+    CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+    CUDA_TRY(cudaStreamWaitEvent(cs, e->ev_fork, 0));   // earlier work on the main stream may still read DB_PCM
+    int u0 = 0, k = 0;
+    while (u0 < n_utts) {
+      int u1 = u0;
+      while (u1 < n_utts && sample_off[u1 + 1] - sample_off[u0] <= piece) u1++;
+      if (u1 == u0) u1 = u0 + 1;
+      const int64_t s0 = sample_off[u0], s1 = sample_off[u1];
+      if ((int)e->ev_piece.size() <= k) { cudaEvent_t ev; CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_piece.push_back(ev); }
+      if (s1 > s0) CUDA_TRY(cudaMemcpyAsync((int16_t *)d_pcm + s0, pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaEventRecord(e->ev_piece[k], cs));
+      CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_piece[k], 0));
+      MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, frame_off[u1] - frame_off[u0], d_mfcc, frame_off[u0]));
+      u0 = u1; k++;
+    }
+  }
   if (o->apply_cmvn) {
     size_t nst = (size_t)n_spk * 2 * (C + 1);
     if (fo.cmvn_stats) MFA_TRY(e->upload(DB_CMVN_STATS, fo.cmvn_stats, nst, &d_stats));
