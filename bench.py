@@ -43,24 +43,41 @@ def measured_peaks():
 
 
 class ClockSampler:
-    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every ~5 ms; falls back to nvidia-smi polling)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.mask, self.max_mhz = [], 0, None
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self._h is not None:
+                    self.sm.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+                    try:
+                        self.mask |= int(self._nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    except Exception:
+                        self.mask |= int(self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self._stop.wait(0.005)
+                else:
+                    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.sm.append(float(out[0])); self.max_mhz = float(out[1]); self.mask |= int(out[2].strip(), 16)
+                    self._stop.wait(0.05)
             except Exception:
-                pass
-            self._stop.wait(0.2)
+                self._stop.wait(0.05)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -70,17 +87,8 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx = max(mx, float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted(n for n, b in self.REASONS.items() if self.mask & b)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -233,6 +241,8 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     gmm_ms, gmm_n, gmm_rows = eng.gmm_timing()   # K2 launches of the LAST step (event pairs on the engine stream)
+    gmm_flops_last = eng.gmm_flops()
+    stage_ms = eng.stage_timing()
     launches = eng.launch_count - l0
     clocks = sampler.stop()
     st = res.status.cpu().numpy()
@@ -272,13 +282,15 @@ def main():
     h2d = int(c.pcm.nbytes)
     d2h = int(sum(x.numel() * x.element_size() for x in h_outs))
 
-    # ---- roofline of the dominant kernel (K2) --------------------------------------------------------------------
+    # ---- rooflines: per-stage CUDA-event times of the last device-resident step; the dominant kernel goes into "roofline"
     pk = measured_peaks()
-    roof = None
+    stages = stage_ms
+    step_ms = dev_ms / args.steps
+    k2 = None
     if gmm_n > 0 and gmm_ms > 0:
         # useful FLOPs = 2*(2D+1) per (frame, Gaussian) actually scored: the fused pipeline scores, per utterance, only the pdfs
         # its graph references (what Kaldi's decodable evaluates lazily), not frames x all Gaussians
-        per_launch_flops = eng.gmm_flops() / gmm_n
+        per_launch_flops = gmm_flops_last / gmm_n
         avg_ms = gmm_ms / gmm_n
         achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
         traffic = None
@@ -288,17 +300,40 @@ def main():
             key = {0: "dram_bytes_per_flop_ragged", 2: "dram_bytes_per_flop_dense"}.get(args.gmm_impl)
             if key in tj:   # DRAM bytes per useful FLOP from the committed ncu --set full capture x FLOPs of this launch
                 traffic = tj[key] * per_launch_flops
-        roof = {"kernel": "gmm_loglikes (K2: xsplit + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sustained"], "traffic": traffic, "peak_source": pk["source"] + " bf16 sustained",
-                "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1), "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs",
-                "launches_per_step": gmm_n, "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": per_launch_flops,
-                "share_of_step": gmm_ms / (dev_ms / args.steps)}
+        k2 = {"kernel": "K2 gmm log-likelihoods (xsplit + gather_b + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved,
+              "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+              "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1),
+              "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs", "launches_per_step": gmm_n, "avg_launch_ms": avg_ms,
+              "algorithmic_flops_per_launch": per_launch_flops, "share_of_step": gmm_ms / step_ms}
+    # K3: bytes per utterance = T*(4*P_u + 2*S_u) + 4*T + graph (12 B per arc + 8 B per state)
+    so, ao, po = sc.graphs.offsets()
+    T_u = (sc.frame_off[1:] - sc.frame_off[:-1]).astype(np.float64)
+    S_u, A_u, P_u = np.diff(so).astype(np.float64), np.diff(ao).astype(np.float64), np.diff(po).astype(np.float64)
+    k3_bytes = float((T_u * (4 * P_u + 2 * S_u) + 4 * T_u + 12 * A_u + 8 * S_u).sum())
+    k3 = None
+    if stages["viterbi"] > 0:
+        ach = k3_bytes / (stages["viterbi"] * 1e-3) / 1e9
+        k3 = {"kernel": "K3 viterbi_kernel (all shared-memory classes, fork to join)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
+              "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " HBM copy",
+              "algorithmic_bytes_per_launch": k3_bytes, "avg_launch_ms": stages["viterbi"], "share_of_step": stages["viterbi"] / step_ms,
+              "note": "latency-bound sequential recursion (one warp per utterance); see profiles/r1_viterbi_full.md for stall reasons"}
+    # K1: bytes = 2 per sample + 4*13 per frame
+    k1_bytes = float(2 * c.pcm.shape[0] + 52 * n_frames)
+    k1 = None
+    if stages["mfcc_cmvn"] > 0:
+        ach = k1_bytes / (stages["mfcc_cmvn"] * 1e-3) / 1e9
+        k1 = {"kernel": "K1 mfcc_kernel + CMVN statistics", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+              "frac": ach / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": stages["mfcc_cmvn"],
+              "share_of_step": stages["mfcc_cmvn"] / step_ms, "note": "fp32-ALU / issue bound (2.7k warp instructions per frame), not HBM bound"}
+    cands = [x for x in (k2, k3, k1) if x]
+    roof = max(cands, key=lambda x: x["share_of_step"]) if cands else None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches_total),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": roof, "aligned_utterances": int(ok_total), "utterances": int(utts_total)}
+            "roofline": roof, "roofline_k2": k2, "roofline_k3": k3, "roofline_k1": k1, "stages_ms": stages,
+            "aligned_utterances": int(ok_total), "utterances": int(utts_total)}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         try:
             sc._fsts = sc.batch.export()

@@ -68,6 +68,10 @@ MFA_API int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_lau
 /* useful FLOPs of those launches: 2*(2*dim+1) per (frame, Gaussian) actually scored.  The fused pipeline scores, per utterance,
  * only the pdfs its graph references (what Kaldi's decodable evaluates lazily), so this is less than frames x all Gaussians. */
 MFA_API int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops);
+/* CUDA-event time (ms, engine stream) the last mfa_align_pcm call spent per stage:
+ * ms4[0] = K1 MFCC + CMVN statistics (host-buffer calls: including the piecewise PCM upload it overlaps with),
+ * ms4[1] = feature finalisation, ms4[2] = K2 log-likelihoods, ms4[3] = K3 Viterbi (all size classes, fork to join). */
+MFA_API int mfa_engine_stage_timing(mfa_engine *e, float *ms4);
 
 /* ---- K1: MFCC.  Replaces kalpy MfccComputer.compute_mfccs_for_export
  *      (corpus/features.py:235, online/alignment.py:83).  Options = FeatureConfigMixin.mfcc_options
@@ -192,6 +196,8 @@ MFA_API int mfa_graphs_pack(const mfa_fst_batch *b, const float *tid_cost, const
                             mfa_graphs **out);
 MFA_API int mfa_graphs_destroy(mfa_graphs *g);
 MFA_API int mfa_graphs_max_words(const mfa_graphs *g, int32_t *max_words /* [n_utts] upper bound on olabels per path */);
+/* per-utterance prefix offsets ([n_utts+1] each; any pointer may be NULL): states, arcs, distinct pdfs referenced */
+MFA_API int mfa_graphs_offsets(const mfa_graphs *g, int64_t *state_off, int64_t *arc_off, int64_t *pdf_off);
 
 /* ---- K3: batched beam Viterbi.  Replaces GmmAligner.align_utterance / export_alignments ->
  *      AlignUtteranceWrapper + FasterDecoder (alignment/multiprocessing.py:846-853;

@@ -47,6 +47,13 @@ struct mfa_engine {
   cudaStream_t side[kSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
   std::vector<cudaEvent_t> ev_piece;   // H2D pieces of the PCM upload (end-to-end path)
+  // per-stage CUDA-event timing of the last fused call: intervals (begin event, end event, stage) on the main stream
+  enum Stage { ST_MFCC = 0, ST_FEAT = 1, ST_GMM = 2, ST_VITERBI = 3, ST_N = 4 };
+  std::vector<cudaEvent_t> st_ev;
+  std::vector<int> st_stage;           // stage of interval k (events 2k, 2k+1)
+  int stage_begin(int stage);
+  int stage_end();
+  void stage_reset() { st_stage.clear(); }
   // cached MFCC tables (device blob in DB_MFCC_TAB) for the last option set
   bool mfcc_tab_valid = false;
   mfa_mfcc_opts mfcc_tab_opts{};

@@ -72,6 +72,7 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto &b : e->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : e->gmm_ev) cudaEventDestroy(ev);
   for (auto ev : e->ev_piece) cudaEventDestroy(ev);
+  for (auto ev : e->st_ev) cudaEventDestroy(ev);
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   cudaStreamDestroy(e->stream);
@@ -112,6 +113,29 @@ extern "C" int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_
   if (total_ms) *total_ms = tot;
   if (n_launches) *n_launches = e->gmm_ev_used / 2;
   if (n_rows) *n_rows = e->gmm_rows;
+  return MFA_OK;
+}
+
+int mfa_engine::stage_begin(int stage) {
+  const size_t k = st_stage.size();
+  while (st_ev.size() < 2 * (k + 1)) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); st_ev.push_back(ev); }
+  st_stage.push_back(stage);
+  CUDA_TRY(cudaEventRecord(st_ev[2 * k], stream));
+  return MFA_OK;
+}
+int mfa_engine::stage_end() {
+  CUDA_TRY(cudaEventRecord(st_ev[2 * (st_stage.size() - 1) + 1], stream));
+  return MFA_OK;
+}
+extern "C" int mfa_engine_stage_timing(mfa_engine *e, float *ms4) {
+  if (!e || !ms4) return set_error(MFA_ERR_INVALID, "null argument");
+  for (int i = 0; i < mfa_engine::ST_N; i++) ms4[i] = 0.0f;
+  for (size_t k = 0; k < e->st_stage.size(); k++) {
+    CUDA_TRY(cudaEventSynchronize(e->st_ev[2 * k + 1]));
+    float ms = 0.0f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->st_ev[2 * k], e->st_ev[2 * k + 1]));
+    ms4[e->st_stage[k]] += ms;
+  }
   return MFA_OK;
 }
 

@@ -477,6 +477,15 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
   return MFA_OK;
 }
 
+int mfa_graphs_offsets(const mfa_graphs *g, int64_t *state_off, int64_t *arc_off, int64_t *pdf_off) {
+  if (!g) return set_error(MFA_ERR_INVALID, "null argument");
+  const size_t n = (size_t)g->n_utts + 1;
+  if (state_off) std::memcpy(state_off, g->st_off.data(), n * sizeof(int64_t));
+  if (arc_off) std::memcpy(arc_off, g->arc_off.data(), n * sizeof(int64_t));
+  if (pdf_off) std::memcpy(pdf_off, g->lp_off.data(), n * sizeof(int64_t));
+  return MFA_OK;
+}
+
 int mfa_graphs_max_words(const mfa_graphs *g, int32_t *max_words) {
   if (!g || !max_words) return set_error(MFA_ERR_INVALID, "null argument");
   std::memcpy(max_words, g->max_words.data(), sizeof(int32_t) * g->max_words.size());

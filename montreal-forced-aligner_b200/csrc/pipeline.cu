@@ -259,6 +259,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   const int D = mfa_feat_out_dim(&fo);
   if (D != m->dim) return set_error(MFA_ERR_INVALID, "feature pipeline yields dim " + std::to_string(D) + " but the model expects " + std::to_string(m->dim));
   e->gmm_timing_reset();
+  e->stage_reset();
   MFA_TRY(upload_graphs(e, g));
   const int P = m->num_pdfs, C = o->mfcc.num_ceps;
   const int64_t nf = frame_off[n_utts], nw = word_off[n_utts], ns = sample_off[n_utts];
@@ -284,6 +285,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   // ---- K1 + CMVN statistics over the whole batch
   float *d_mfcc; double *d_stats = nullptr;
   MFA_TRY(e->getT<float>(DB_MFCC, (size_t)nf * C, &d_mfcc));
+  MFA_TRY(e->stage_begin(mfa_engine::ST_MFCC));
   if (where == MFA_DEVICE) {
     MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
   } else {
@@ -313,6 +315,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
       MFA_TRY(launch_cmvn_stats(e, d_mfcc, C, d_fo, utt2spk, n_utts, n_spk, d_stats));
     }
   }
+  MFA_TRY(e->stage_end());
   // ---- chunks
   std::vector<ChunkPlan> plans;
   int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
@@ -323,8 +326,11 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
     MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
     MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
     MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
+    MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
     CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
     MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
+    MFA_TRY(e->stage_end());
+    MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
     if (ragged) {
       MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
       MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &d_ld_u));
@@ -334,13 +340,16 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
     } else {
       MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
     }
+    MFA_TRY(e->stage_end());
     ViterbiArgs a{};
     a.d_ll_off = d_ll_off; a.d_ld_u = d_ld_u;
     a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
     a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
     a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
     a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
+    MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
     MFA_TRY(launch_viterbi(e, a));
+    MFA_TRY(e->stage_end());
   }
   MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));

@@ -115,6 +115,11 @@ class Engine:
         L.check(L.lib().mfa_engine_gmm_timing(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
         return ms.value, n.value, rows.value
 
+    def stage_timing(self) -> dict:
+        ms = (C.c_float * 4)()
+        L.check(L.lib().mfa_engine_stage_timing(self._h, ms))
+        return {"mfcc_cmvn": ms[0], "features": ms[1], "gmm": ms[2], "viterbi": ms[3]}
+
     def gmm_flops(self) -> float:
         f = C.c_double()
         L.check(L.lib().mfa_engine_gmm_flops(self._h, C.byref(f)))
@@ -408,6 +413,12 @@ class Graphs:
         L.check(L.lib().mfa_graphs_pack(batch._h, tid_cost.ctypes.data_as(C.c_void_p), tid2pdf.ctypes.data_as(C.c_void_p),
                                         C.c_int32(tm.num_tids), C.byref(self._h)))
         self.n_utts = batch.sizes()[0]
+
+    def offsets(self):
+        """(state_off, arc_off, pdf_off): per-utterance prefix offsets of states / arcs / distinct pdfs."""
+        so, ao, po = (np.zeros(self.n_utts + 1, np.int64) for _ in range(3))
+        L.check(L.lib().mfa_graphs_offsets(self._h, *[a.ctypes.data_as(C.c_void_p) for a in (so, ao, po)]))
+        return so, ao, po
 
     def max_words(self) -> np.ndarray:
         out = np.zeros(self.n_utts, np.int32)
