@@ -231,6 +231,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = eng.launch_count
+    fb0 = eng.band_fallbacks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gmm_ms = gmm_n = gmm_rows = 0
     ev0.record(stream)
@@ -244,6 +245,7 @@ def main():
     gmm_flops_last = eng.gmm_flops()
     stage_ms = eng.stage_timing()
     launches = eng.launch_count - l0
+    fallbacks = eng.band_fallbacks - fb0
     clocks = sampler.stop()
     st = res.status.cpu().numpy()
     n_ok = int((st < 2).sum())
@@ -333,7 +335,8 @@ def main():
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches_total),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "roofline_k2": k2, "roofline_k3": k3, "roofline_k1": k1, "stages_ms": stages,
-            "aligned_utterances": int(ok_total), "utterances": int(utts_total)}
+            "aligned_utterances": int(ok_total), "utterances": int(utts_total),
+            "k3_band_fallbacks_per_step": fallbacks / max(1, args.steps)}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         try:
             sc._fsts = sc.batch.export()

@@ -62,6 +62,8 @@ MFA_API void *mfa_engine_stream(mfa_engine *e); /* cudaStream_t, for torch inter
 MFA_API int mfa_engine_sm_count(mfa_engine *e);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 MFA_API int64_t mfa_engine_launch_count(mfa_engine *e);
+/* Cumulative number of utterances the band Viterbi kernel handed to the sparse kernel (live window wider than the band). */
+MFA_API int64_t mfa_engine_band_fallbacks(mfa_engine *e);
 /* CUDA-event timing (on the engine stream) of the K2 launches issued by the most recent API call that ran K2:
  * total milliseconds, number of K2 kernel launches and frame rows they covered (padding included). */
 MFA_API int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_launches, int64_t *n_rows);
@@ -198,6 +200,13 @@ MFA_API int mfa_graphs_destroy(mfa_graphs *g);
 MFA_API int mfa_graphs_max_words(const mfa_graphs *g, int32_t *max_words /* [n_utts] upper bound on olabels per path */);
 /* per-utterance prefix offsets ([n_utts+1] each; any pointer may be NULL): states, arcs, distinct pdfs referenced */
 MFA_API int mfa_graphs_offsets(const mfa_graphs *g, int64_t *state_off, int64_t *arc_off, int64_t *pdf_off);
+/* Band view of the packed graphs (the layout the primary Viterbi kernel runs on; see csrc/viterbi_band.cu): per utterance
+ * band_ok[n] (0: sparse kernel only), start[n] and maxback[n] in band numbering; per state (offsets = state_off) the packed
+ * word first-in-arc | in-degree << 16 | forward reach << 24 and the original state id; per arc (offsets = arc_off), grouped by
+ * DESTINATION band state: source band state | local pdf << 16, and the index of the same arc in by-source order.  Any pointer
+ * may be NULL.  Host-only (tests / inspection). */
+MFA_API int mfa_graphs_band_view(const mfa_graphs *g, int32_t *band_ok, int32_t *start, int32_t *maxback, uint32_t *state_word,
+                                 uint16_t *orig_state, uint32_t *arc_word, uint16_t *arc_index);
 
 /* ---- K3: batched beam Viterbi.  Replaces GmmAligner.align_utterance / export_alignments ->
  *      AlignUtteranceWrapper + FasterDecoder (alignment/multiprocessing.py:846-853;

@@ -24,7 +24,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -34,6 +34,7 @@ struct mfa_engine {
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  int64_t band_fallbacks = 0;          // utterances the band Viterbi kernel handed to the sparse kernel (cumulative)
   // K2 timing: event pairs recorded around each K2 launch of the current API call
   std::vector<cudaEvent_t> gmm_ev;
   int gmm_ev_used = 0;
@@ -137,5 +138,7 @@ struct ViterbiArgs {
   mfa_align_opts opts;
 };
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P);   // shared memory the band kernel needs for one utterance
+int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
 }  // namespace mfa

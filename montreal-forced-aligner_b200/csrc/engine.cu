@@ -89,6 +89,7 @@ extern "C" int mfa_engine_sync(mfa_engine *e) {
 extern "C" void *mfa_engine_stream(mfa_engine *e) { return e ? (void *)e->stream : nullptr; }
 extern "C" int mfa_engine_sm_count(mfa_engine *e) { return e ? e->sm_count : 0; }
 extern "C" int64_t mfa_engine_launch_count(mfa_engine *e) { return e ? e->launches : 0; }
+extern "C" int64_t mfa_engine_band_fallbacks(mfa_engine *e) { return e ? e->band_fallbacks : 0; }
 int mfa_engine::gmm_timing_begin() {
   if ((size_t)gmm_ev_used + 2 > gmm_ev.size()) {
     for (int k = 0; k < 2; k++) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); gmm_ev.push_back(ev); }
@@ -278,7 +279,11 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
       {g->in_begin.data(), g->in_begin.size() * 4, (void **)&g->d_in_begin}, {g->a_tid.data(), A * 4, (void **)&g->d_a_tid},
       {g->a_olabel.data(), A * 4, (void **)&g->d_a_olabel}, {g->lp2pdf.data(), g->lp2pdf.size() * 4, (void **)&g->d_lp2pdf},
       {pack.data(), A * 4, (void **)&g->d_a_pack}, {g->a_w.data(), A * 4, (void **)&g->d_a_w},
-      {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}, {g->a_src.data(), A * 4, (void **)&g->d_a_src}};
+      {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}, {g->a_src.data(), A * 4, (void **)&g->d_a_src},
+      {g->b_start.data(), g->b_start.size() * 4, (void **)&g->d_b_start}, {g->b_maxback.data(), g->b_maxback.size() * 4, (void **)&g->d_b_maxback},
+      {g->b_stw.data(), g->b_stw.size() * 4, (void **)&g->d_b_stw}, {g->b_apk.data(), g->b_apk.size() * 4, (void **)&g->d_b_apk},
+      {g->b_aw.data(), g->b_aw.size() * 4, (void **)&g->d_b_aw}, {g->b_fin.data(), g->b_fin.size() * 4, (void **)&g->d_b_fin},
+      {g->b_arcid.data(), g->b_arcid.size() * 2, (void **)&g->d_b_arcid}, {g->b_orig.data(), g->b_orig.size() * 2, (void **)&g->d_b_orig}};
   size_t total = 0;
   for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
   CUDA_TRY(cudaMalloc(&g->d_blob, std::max<size_t>(total, 256)));

@@ -22,6 +22,14 @@ struct mfa_graphs {
   std::vector<float> a_w;                    // graph weight + AddTransitionProbs cost
   std::vector<float> final_w;                // per state, +inf = non-final
   std::vector<int32_t> lp2pdf;               // per utterance local pdf list (sorted pdf ids)
+  // Band view (viterbi_band.cu): states renumbered in a topological order of the strongly-connected-component DAG (self-loops and
+  // the small cycles of Kaldi's silence topology stay inside a component), arcs grouped by DESTINATION state in that order.
+  // b_stw[st_off[u]+s]  = first in-arc (low 16) | in-degree << 16 | largest forward jump of s's out-arcs << 24
+  // b_apk[arc_off[u]+j] = source band state (low 16) | local pdf << 16;  b_arcid = index of the same arc in the by-source arrays
+  std::vector<int32_t> band_ok, b_start, b_maxback;   // per utterance; band_ok = 0: graph only runs on the sparse kernel
+  std::vector<uint32_t> b_stw, b_apk;
+  std::vector<float> b_aw, b_fin;
+  std::vector<uint16_t> b_arcid, b_orig;              // b_orig: band state -> original state id
   // device mirror
   int device = -1;
   void *d_blob = nullptr;
@@ -29,6 +37,10 @@ struct mfa_graphs {
   int64_t *d_st_off = nullptr, *d_arc_off = nullptr, *d_lp_off = nullptr, *d_inb_off = nullptr;
   int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr, *d_a_src = nullptr;
   uint32_t *d_a_pack = nullptr;  // dst (low 16) | lp (high 16, 0xFFFF = epsilon)
+  int32_t *d_b_start = nullptr, *d_b_maxback = nullptr;
+  uint32_t *d_b_stw = nullptr, *d_b_apk = nullptr;
+  float *d_b_aw = nullptr, *d_b_fin = nullptr;
+  uint16_t *d_b_arcid = nullptr, *d_b_orig = nullptr;
   float *d_a_w = nullptr, *d_final_w = nullptr;
   // per-utterance Gaussian tiling for the ragged K2 path (cached against the model's tiling version)
   uint64_t rag_version = 0;

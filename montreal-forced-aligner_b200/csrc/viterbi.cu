@@ -543,41 +543,39 @@ viterbi_kernel(VitParams p) {
 
 namespace mfa {
 
-int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
+// Sparse kernel over the utterances in `subset` (chunk-local ids).
+static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset) {
   const mfa_graphs *g = a.g;
-  const int n = a.n_utts;
-  if (n == 0) return MFA_OK;
+  const int n = a.n_utts, ns = (int)subset.size();
+  if (ns == 0) return MFA_OK;
   if (a.ld % 8 != 0) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension must be a multiple of 8");
   // shared-memory need and back-pointer offsets per utterance
   std::vector<int64_t> bp_off(n + 1, 0);
-  std::vector<size_t> need(n);
-  std::vector<double> work(n);
+  std::vector<size_t> need(n, 0);
+  std::vector<double> work(n, 0.0);
   const size_t limit = e->smem_optin - 2048;
-  for (int u = 0; u < n; u++) {
+  int64_t bp_total = 0;
+  for (int u : subset) {
     int ug = a.utt0 + u;
     int64_t S = g->st_off[ug + 1] - g->st_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
     int64_t T = a.h_frame_off[u + 1] - a.h_frame_off[u];
-    bp_off[u + 1] = bp_off[u] + (T + (g->n_eps[ug] > 0 ? 1 : 0)) * S;
+    bp_off[u] = bp_total;
+    bp_total += (T + (g->n_eps[ug] > 0 ? 1 : 0)) * S;
     need[u] = (size_t)S * 12 + (size_t)P * 16 + (size_t)((S + 1) & ~1) * 4 + 16;
     work[u] = (double)T;
     if (need[u] > limit) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph too large for the Viterbi kernel's shared memory");
-    if (!a.d_ll_off) {
-      if (a.h_col_off[u] % 4 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 4");
-      if (a.h_col_off[u] + ((T + 3) / 4) * 4 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 4-frame blocks");
-    }
   }
   uint16_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
-  MFA_TRY(e->getT<uint16_t>(DB_BP, (size_t)bp_off[n] + 8, &d_bp));
+  MFA_TRY(e->getT<uint16_t>(DB_BP, (size_t)bp_total + 8, &d_bp));
   MFA_TRY(e->upload(DB_BP_OFF, bp_off.data(), bp_off.size(), &d_bp_off));
   // classes by shared-memory need (occupancy); inside a class, longest utterance first
   constexpr int NC = mfa_engine::kSide;
   size_t bounds[NC];
   for (int c = 0; c < NC; c++) bounds[c] = std::min<size_t>(limit, (size_t)(7168.0 * std::pow(2.0, 0.5 * c)));   // 7, 9.9, 14, ... KB
   bounds[NC - 1] = limit;
-  std::vector<int> cls(n);
-  for (int u = 0; u < n; u++) { int c = 0; while (c < NC - 1 && need[u] > bounds[c]) c++; cls[u] = c; }
-  std::vector<int32_t> order(n);
-  std::iota(order.begin(), order.end(), 0);
+  std::vector<int> cls(n, 0);
+  for (int u : subset) { int c = 0; while (c < NC - 1 && need[u] > bounds[c]) c++; cls[u] = c; }
+  std::vector<int32_t> order(subset);
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cls[x] != cls[y] ? cls[x] < cls[y] : work[x] > work[y]; });
   MFA_TRY(e->upload(DB_UTT_ORDER, order.data(), order.size(), &d_order));
   VitParams p;
@@ -600,9 +598,9 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   // largest-need classes first: they hold the biggest graphs; the small ones fill in around them on the side streams
   for (int c = NC - 1; c >= 0; c--) {
     int pos = 0, cnt = 0;
-    for (int k = 0; k < n; k++) { if (cls[order[k]] < c) pos++; }
+    for (int k = 0; k < ns; k++) { if (cls[order[k]] < c) pos++; }
     size_t mx = 0;
-    while (pos + cnt < n && cls[order[pos + cnt]] == c) { mx = std::max(mx, need[order[pos + cnt]]); cnt++; }
+    while (pos + cnt < ns && cls[order[pos + cnt]] == c) { mx = std::max(mx, need[order[pos + cnt]]); cnt++; }
     if (cnt == 0) continue;
     p.order = d_order + pos;
     size_t smem = (mx + 15) / 16 * 16;
@@ -613,6 +611,59 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
+  }
+  return MFA_OK;
+}
+
+// K3 dispatch: graphs with a band view run on the band kernel (viterbi_band.cu); graphs without one (input-epsilon arcs, very
+// high in-degree) run on the sparse kernel, and so does any utterance whose live window outgrew the band at run time -- the
+// band kernel lists those, the host reads the (almost always zero) count back and re-launches them.
+// MFA_VIT_BAND=0 forces the sparse kernel; MFA_VIT_MAXGROUPS=k (1..8) narrows the band (tests use it to exercise the fallback).
+int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
+  const mfa_graphs *g = a.g;
+  const int n = a.n_utts;
+  if (n == 0) return MFA_OK;
+  if (a.ld % 8 != 0) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension must be a multiple of 8");
+  if (!a.d_ll_off) {
+    for (int u = 0; u < n; u++) {
+      const int64_t T = a.h_frame_off[u + 1] - a.h_frame_off[u];
+      if (a.h_col_off[u] % 4 != 0) return set_error(MFA_ERR_INVALID, "col_off must be a multiple of 4");
+      if (a.h_col_off[u] + ((T + 3) / 4) * 4 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 4-frame blocks");
+    }
+  }
+  const char *env_band = getenv("MFA_VIT_BAND"), *env_mg = getenv("MFA_VIT_MAXGROUPS");
+  const bool use_band = !(env_band && atoi(env_band) == 0);
+  const int max_groups = env_mg ? atoi(env_mg) : 8;
+  std::vector<int32_t> band, sparse;
+  for (int u = 0; u < n; u++) {
+    const int ug = a.utt0 + u;
+    bool ok = use_band && g->band_ok[ug];
+    if (ok) {
+      const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
+      ok = viterbi_band_smem(S, A, P) <= e->smem_optin - 4096;
+    }
+    (ok ? band : sparse).push_back(u);
+  }
+  int32_t *d_fb = nullptr;
+  if (!band.empty()) {
+    MFA_TRY(e->getT<int32_t>(DB_FALLBACK, (size_t)n + 1, &d_fb));
+    MFA_TRY(launch_viterbi_band(e, a, band, max_groups, d_fb));
+  }
+  MFA_TRY(launch_viterbi_sparse(e, a, sparse));
+  if (!band.empty()) {
+    int32_t *h_fb;
+    { void *pp; MFA_TRY(e->get_pinned(PB_E, ((size_t)n + 1) * sizeof(int32_t), &pp)); h_fb = (int32_t *)pp; }
+    CUDA_TRY(cudaMemcpyAsync(h_fb, d_fb, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const int nfb = h_fb[0];
+    e->band_fallbacks += nfb;
+    if (nfb > 0) {
+      CUDA_TRY(cudaMemcpyAsync(h_fb + 1, d_fb + 1, (size_t)nfb * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      std::vector<int32_t> again(h_fb + 1, h_fb + 1 + nfb);
+      std::sort(again.begin(), again.end());
+      MFA_TRY(launch_viterbi_sparse(e, a, again));
+    }
   }
   return MFA_OK;
 }

@@ -1,0 +1,456 @@
+// viterbi_band.cu -- K3 (primary path): beam Viterbi as a dense band recursion, one warp per utterance, the utterance's
+// whole graph in shared memory.
+//
+// Replaces GmmAligner.align_utterance / export_alignments -> Kaldi AlignUtteranceWrapper + FasterDecoder (reference call
+// sites: montreal_forced_aligner/alignment/multiprocessing.py:846-853, online/alignment.py:97-107); semantics per
+// SURVEY.md A.7, identical to viterbi.cu (the sparse token-passing kernel, which stays as the path for graphs with
+// input-epsilon arcs and as the fallback when a token set outgrows the band).
+//
+// Formulation.  mfa_graphs_pack renumbers each graph's states in a topological order of its strongly-connected-component
+// DAG (graph.cc: build_band) and groups arcs by destination.  Every arc then goes forward by at most 255 positions or
+// back by at most `maxback` (inside a silence model), so
+//   * the lowest live state index never decreases by more than maxback, and
+//   * the tokens alive under the beam sit in a narrow index window (median 29 states, maximum 170 on LibriSpeech-shaped
+//     graphs) that slides through the graph as the utterance is consumed.
+// Per frame the warp evaluates, for every state d of the 32-aligned window [lo - maxback, max(s + fwd(s))], the PULL
+//   new(d) = min over in-arcs (s -> d) with cost(s) < cutoff of  (cost(s) + w) + (-acoustic_scale * loglike(pdf))
+// lane = d mod 32, results in registers; one REDUX gives the frame's best cost; survivors (< best + adaptive beam) are
+// renormalised and written to the other cost ring.  No atomics, no token lists, no hash: the only per-frame
+// synchronisation is two __syncwarp.  Token costs live in two 512-entry shared-memory rings indexed by (state & 511).
+// Back-pointers are ONE BYTE per window slot (index of the winning in-arc of that state, 0xFF = dead): a 256-byte row per
+// frame plus the row's first group, instead of 2 bytes x all states of the graph; they are walked back in 32-frame batches
+// staged through shared memory.  Acoustic costs of 4 frames x all pdfs of the utterance are prefetched two blocks ahead
+// with cp.async (three stages), so the HBM latency of the log-likelihood matrix never sits on the recursion.
+//
+// GetCutoff (beam / min_active widening with beam_delta), the retry with retry_beam and tie-breaking (lowest by-source arc
+// index; lowest original state id among equal final costs) are the same as the sparse kernel's, so both produce the same
+// alignments.  A frame whose window would exceed GMAX groups hands the utterance to the sparse kernel (fallback list).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <numeric>
+
+#include "cuda_internal.cuh"
+
+using namespace mfa;
+
+namespace {
+constexpr int GMAX = 8;              // groups of 32 band states a frame may span
+constexpr int RS = GMAX * 32;        // back-pointer row stride in bytes
+constexpr int WRING = 512;           // cost ring entries; >= RS + largest maxback (96) + 32
+constexpr unsigned MASK = WRING - 1;
+constexpr int NST = 3;               // acoustic-cost stages of 4 frames
+constexpr int BT_ROWS = 32;          // frames per back-trace batch
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NW = 4;                // warps per utterance: warp w pulls window groups w, w + NW
+constexpr int NT = NW * 32;
+constexpr int GPW = GMAX / NW;       // groups per warp
+
+struct BandParams {
+  const int64_t *st_off, *arc_off, *lp_off;
+  const int32_t *b_start, *b_maxback, *a_tid, *a_olabel, *lp2pdf;
+  const uint32_t *b_stw, *b_apk;
+  const float *b_aw, *b_fin;
+  const uint16_t *b_arcid, *b_orig;
+  int utt0;
+  const int32_t *order;
+  const float *llT;
+  int64_t ld;
+  const int64_t *col_off, *frame_off, *word_off, *ll_off, *ld_u, *bp_off;
+  uint8_t *bp;
+  int32_t *ali, *num_words, *words, *status, *fallback;   // fallback[0] = count, fallback[1..] = chunk-local utterance ids
+  float *per_frame, *total_like;
+  float acwt, beam, retry_beam, beam_delta;
+  int min_active, max_groups;
+};
+
+__device__ __forceinline__ uint32_t f2key(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// min_active-th (0-based) smallest live cost (Kaldi: nth_element over the token costs).  The decoder sits at this branch on
+// most frames when the beam alone keeps fewer than min_active tokens, so it must be cheap: the survivors' costs are kept as a
+// compact list (written in phase 2 of the previous frame) and sorted with a shuffle bitonic network -- 15 exchange steps for
+// up to 32 values, 21 two-register steps for up to 64; larger sets use a bitwise radix select over the list.
+__device__ __forceinline__ float bitonic_step(float x, int lane, int e, int size, int stride) {
+  const float y = __shfl_xor_sync(FULL, x, stride);
+  const bool up = (e & size) == 0, lower = (lane & stride) == 0;
+  return (lower == up) ? fminf(x, y) : fmaxf(x, y);
+}
+
+__device__ __noinline__ float select_rank(const float *live, int n, int want, int lane) {
+  if (n <= 32) {
+    float x = lane < n ? live[lane] : INFINITY;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) x = bitonic_step(x, lane, lane, size, stride);
+    return __shfl_sync(FULL, x, want);
+  }
+  if (n <= 64) {
+    float x0 = live[lane], x1 = lane + 32 < n ? live[lane + 32] : INFINITY;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        x0 = bitonic_step(x0, lane, lane, size, stride);
+        x1 = bitonic_step(x1, lane, lane + 32, size, stride);
+      }
+    { const float a = fminf(x0, x1), b = fmaxf(x0, x1); x0 = a; x1 = b; }     // size 64, stride 32: same lane
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) { x0 = bitonic_step(x0, lane, lane, 64, stride); x1 = bitonic_step(x1, lane, lane, 64, stride); }
+    return want < 32 ? __shfl_sync(FULL, x0, want) : __shfl_sync(FULL, x1, want - 32);
+  }
+  // costs are >= +0, so the raw bit patterns order like the values
+  unsigned prefix = 0, mask = 0;
+  for (int bit = 31; bit >= 0; bit--) {
+    const unsigned b = 1u << bit;
+    int c0 = 0;
+    for (int i = lane; i < ((n + 31) & ~31); i += 32) {
+      const unsigned x = i < n ? __float_as_uint(live[i]) : 0xFFFFFFFFu;
+      c0 += __popc(__ballot_sync(FULL, (x & mask) == prefix && !(x & b)));
+    }
+    if (want >= c0) { prefix |= b; want -= c0; }
+    mask |= b;
+  }
+  return __uint_as_float(prefix);
+}
+
+__global__ void __launch_bounds__(NT, 4)
+viterbi_band_kernel(BandParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ uint32_t s_min[NW];          // per-warp best new cost (ordered key) of the current frame
+  __shared__ int s_stat[NW][4];           // per-warp {lowest live state, highest live state, highest reachable state, n_tot | n_beam << 16}
+  __shared__ float s_live[2][RS];         // compact list of the survivors' costs of frame t in s_live[t & 1] (for GetCutoff's rank)
+  __shared__ int s_cnt[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ul = p.order[blockIdx.x];
+  const int ug = p.utt0 + ul;
+  const int S = (int)(p.st_off[ug + 1] - p.st_off[ug]);
+  const int A = (int)(p.arc_off[ug + 1] - p.arc_off[ug]);
+  const int P = (int)(p.lp_off[ug + 1] - p.lp_off[ug]);
+  const int64_t T = p.frame_off[ul + 1] - p.frame_off[ul];
+  if (T == 0) { if (tid == 0) { p.status[ul] = MFA_ALIGN_ZERO_FRAMES; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; } return; }
+  const int start = p.b_start[ug], maxback = p.b_maxback[ug];
+
+  uint32_t *stw = (uint32_t *)smraw;                            // [S]  first in-arc | in-degree << 16 | forward reach << 24
+  uint2 *arcs = (uint2 *)(stw + ((S + 1) & ~1));                // [A]  {source state | local pdf << 16, weight bits}
+  float *ring = (float *)smraw + ((((S + 1) & ~1) + 2 * A + 3) & ~3);   // [2][WRING], 16-byte aligned
+  float *ac = ring + 2 * WRING;                                 // [NST][P][4] raw log-likelihoods; later the back-trace staging area
+  {
+    const uint32_t *gs = p.b_stw + p.st_off[ug], *ga = p.b_apk + p.arc_off[ug];
+    const float *gw = p.b_aw + p.arc_off[ug];
+    for (int i = tid; i < S; i += NT) stw[i] = gs[i];
+    for (int i = tid; i < A; i += NT) arcs[i] = make_uint2(ga[i], __float_as_uint(gw[i]));
+  }
+  const bool rag = p.ll_off != nullptr;
+  const float *ll = p.llT + (rag ? p.ll_off[ul] : p.col_off[ul]);
+  const int64_t ldu = rag ? p.ld_u[ul] : p.ld;
+  const int32_t *lp2pdf = p.lp2pdf + p.lp_off[ug];
+  uint8_t *bp = p.bp + p.bp_off[ul];                        // [T][RS] choice bytes
+  uint16_t *bpg = (uint16_t *)(bp + (size_t)T * RS);        // [T] first group of each row
+  const float inf = INFINITY, nacwt = -p.acwt;
+  const int NB = (int)((T + 3) >> 2);
+  const int max_groups = min(p.max_groups, GMAX);
+
+  auto issue_block = [&](int b) {
+    if (b < NB) {
+      float *dst = ac + (size_t)(b % NST) * 4 * P;
+      for (int lp = tid; lp < P; lp += NT) cp_async16(dst + 4 * lp, ll + (size_t)(rag ? lp : lp2pdf[lp]) * ldu + 4 * (size_t)b);
+    }
+    cp_async_commit();
+  };
+
+  int result = MFA_ALIGN_NO_FINAL;
+  bool overflow = false;
+  double offset = 0.0;
+  int lo = 0, hi = 0;
+  float *cur = ring, *nxt = ring + WRING;
+
+  for (int attempt = 0; attempt < 2 && !overflow; attempt++) {
+    const float beam = attempt == 0 ? p.beam : p.retry_beam;
+    if (attempt == 1 && !(p.retry_beam > 0.0f)) break;
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int i = tid; i < 2 * WRING; i += NT) ring[i] = inf;
+    cur = ring; nxt = ring + WRING;
+    __syncthreads();
+    if (tid == 0) { cur[start & MASK] = 0.0f; s_cnt[0] = 0; s_cnt[1] = 0; s_live[1][0] = 0.0f; }
+    lo = hi = start;
+    int hib = start + (int)(stw[start] >> 24);
+    int n_tot = 1, n_beam = 1;
+    float cutoff = inf, adaptive = inf;
+    offset = 0.0;
+    issue_block(0); issue_block(1); issue_block(2);
+    cp_async_wait<2>();
+    __syncthreads();
+    bool dead = false;
+    for (int64_t t = 0; t < T; t++) {
+      // ---- GetCutoff on the live tokens (normalised: best == 0); every warp computes the same values
+      if (n_tot <= p.min_active) { cutoff = inf; adaptive = inf; }
+      else if (n_beam > p.min_active) { cutoff = beam; adaptive = beam; }
+      else { cutoff = select_rank(s_live[(t & 1) ^ 1], n_tot, p.min_active, lane); adaptive = cutoff + p.beam_delta; }
+      const float *acf = ac + (size_t)((int)(t >> 2) % NST) * 4 * P + (int)(t & 3);
+      const int glo = max(lo - maxback, 0) >> 5;
+      const int ng = (min(hib, S - 1) >> 5) - glo + 1;
+      if (ng > max_groups) { overflow = true; break; }
+      // ---- pull: warp w owns groups w, w + NW of the window
+      float nv[GPW];
+      uint32_t na[GPW];
+      uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+      for (int k = 0; k < GPW; k++) {
+        const int i = warp + k * NW;
+        nv[k] = inf; na[k] = 0xFFu;
+        if (i < ng) {
+          const int d = (glo + i) * 32 + lane;
+          if (d < S) {
+            const uint32_t st = stw[d];
+            int a = st & 0xFFFF;
+            const int cnt = (st >> 16) & 0xFF;
+            float v = inf;
+            uint32_t arg = 0xFFu;
+            for (int j = 0; j < cnt; j++, a++) {
+              const uint2 ar = arcs[a];
+              const float c = cur[ar.x & MASK];
+              if (c < cutoff) {
+                const float x = __fadd_rn(__fadd_rn(c, __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
+                if (x < v) { v = x; arg = (uint32_t)j; }
+              }
+            }
+            nv[k] = v; na[k] = arg | (st >> 24 << 8);
+            kmin = min(kmin, f2key(v));
+          }
+        }
+      }
+      kmin = __reduce_min_sync(FULL, kmin);
+      if (lane == 0) s_min[warp] = kmin;
+      __syncthreads();                                 // A: every warp has finished reading `cur`; s_min complete
+      {
+        uint32_t m = s_min[0];
+#pragma unroll
+        for (int w = 1; w < NW; w++) m = min(m, s_min[w]);
+        kmin = m;
+      }
+      const float best_new = key2f(kmin);
+      if (!(best_new < inf)) { dead = true; break; }
+      const float next_cutoff = best_new + adaptive;   // inf stays inf
+      uint8_t *bprow = bp + (size_t)t * RS;
+      int mylo = 0x7fffffff, myhi = -1, myhib = -1, nt = 0, nb = 0;
+#pragma unroll
+      for (int k = 0; k < GPW; k++) {
+        const int i = warp + k * NW;
+        if (i < ng) {
+          const int d = (glo + i) * 32 + lane;
+          float v = nv[k];
+          const bool keep = v < next_cutoff;
+          v = keep ? v - best_new : inf;
+          nxt[d & MASK] = v;
+          cur[d & MASK] = inf;
+          __stcs(bprow + i * 32 + lane, (uint8_t)(keep ? (na[k] & 0xFFu) : 0xFFu));
+          const unsigned km = __ballot_sync(FULL, keep);
+          if (km) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_cnt[t & 1], __popc(km));
+            base = __shfl_sync(FULL, base, 0);
+            if (keep) s_live[t & 1][base + __popc(km & ((1u << lane) - 1u))] = v;
+          }
+          nt += __popc(km);
+          nb += __popc(__ballot_sync(FULL, keep && v <= beam));
+          if (keep) { mylo = min(mylo, d); myhi = max(myhi, d); myhib = max(myhib, d + (int)(na[k] >> 8)); }
+        }
+      }
+      if (tid == 0) s_cnt[(t & 1) ^ 1] = 0;            // the other list was read before A; it is appended to in the next frame
+      mylo = __reduce_min_sync(FULL, mylo); myhi = __reduce_max_sync(FULL, myhi); myhib = __reduce_max_sync(FULL, myhib);
+      if (lane == 0) { s_stat[warp][0] = mylo; s_stat[warp][1] = myhi; s_stat[warp][2] = myhib; s_stat[warp][3] = nt | (nb << 16); }
+      if (tid == 0) bpg[t] = (uint16_t)glo;
+      if ((t & 3) == 3) { issue_block((int)((t + 1) >> 2) + 2); cp_async_wait<2>(); }   // nobody reads `ac` between A and B
+      __syncthreads();                                 // B: rings, statistics and the next frame's acoustic block are visible
+      lo = s_stat[0][0]; hi = s_stat[0][1]; hib = s_stat[0][2];
+      { const int x = s_stat[0][3]; n_tot = x & 0xFFFF; n_beam = x >> 16; }
+#pragma unroll
+      for (int w = 1; w < NW; w++) {
+        lo = min(lo, s_stat[w][0]); hi = max(hi, s_stat[w][1]); hib = max(hib, s_stat[w][2]);
+        const int x = s_stat[w][3]; n_tot += x & 0xFFFF; n_beam += x >> 16;
+      }
+      offset += (double)best_new;
+      float *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (overflow || dead) continue;
+    // ---- ReachedFinal / best final token (ties: lowest original state id, like the sparse kernel); every warp redundantly
+    const float *fin = p.b_fin + p.st_off[ug];
+    const uint16_t *orig = p.b_orig + p.st_off[ug];
+    float fv[GMAX];
+    uint32_t kf = 0xFFFFFFFFu;
+    const int g0 = lo >> 5;
+#pragma unroll
+    for (int i = 0; i < GMAX; i++) {
+      const int d = (g0 + i) * 32 + lane;
+      fv[i] = inf;
+      if (d <= hi && d < S) { const float c = cur[d & MASK]; if (c < inf) fv[i] = c + fin[d]; }
+      kf = min(kf, f2key(fv[i]));
+    }
+    kf = __reduce_min_sync(FULL, kf);
+    const float fbest = key2f(kf);
+    if (fbest < inf) {
+      uint32_t sel = 0xFFFFFFFFu;
+#pragma unroll
+      for (int i = 0; i < GMAX; i++) {
+        const int d = (g0 + i) * 32 + lane;
+        if (fv[i] == fbest) sel = min(sel, ((uint32_t)orig[d] << 16) | (uint32_t)d);
+      }
+      sel = __reduce_min_sync(FULL, sel);
+      hi = (int)(sel & 0xFFFF);    // reuse: the best final band state
+      result = attempt == 0 ? MFA_ALIGN_OK : MFA_ALIGN_RETRIED;
+      if (tid == 0) p.total_like[ul] = (float)(-(offset + (double)fbest) / (double)p.acwt);
+      break;
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                 // all back-pointer rows written; nobody touches `ac` any more
+  if (warp != 0) return;
+  if (overflow) {
+    if (lane == 0) { const int k = atomicAdd(p.fallback, 1); p.fallback[1 + k] = ul; }
+    return;
+  }
+  if (result == MFA_ALIGN_NO_FINAL) {
+    if (lane == 0) { p.status[ul] = result; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; }
+    return;
+  }
+  // ---- back-trace (warp 0): 32 frames at a time.  The rows are staged in shared memory by the warp, lane 0 follows the chain
+  // (three dependent shared-memory reads per frame), then the lanes emit one frame each.
+  uint8_t *stage = (uint8_t *)ac;                                  // [BT_ROWS][RS]
+  uint16_t *g0s = (uint16_t *)(stage + BT_ROWS * RS);              // [BT_ROWS]
+  uint16_t *jarr = g0s + BT_ROWS;                                  // [BT_ROWS]
+  const int32_t *a_tid = p.a_tid + p.arc_off[ug], *a_ol = p.a_olabel + p.arc_off[ug];
+  const uint16_t *arcid = p.b_arcid + p.arc_off[ug];
+  int32_t *ali = p.ali + p.frame_off[ul];
+  float *pf = p.per_frame + p.frame_off[ul];
+  int32_t *words = p.words + p.word_off[ul];
+  const int wcap = (int)(p.word_off[ul + 1] - p.word_off[ul]);
+  int nw = 0, s = hi, bad = 0;
+  for (int64_t tb = T; tb > 0; tb -= BT_ROWS) {
+    const int64_t r0 = tb > BT_ROWS ? tb - BT_ROWS : 0;
+    const int n = (int)(tb - r0);
+    const uint4 *src = (const uint4 *)(bp + (size_t)r0 * RS);
+    for (int i = lane; i < n * (RS / 16); i += 32) ((uint4 *)stage)[i] = __ldcs(src + i);
+    if (lane < n) g0s[lane] = bpg[r0 + lane];
+    __syncwarp();
+    if (lane == 0) {
+      for (int k = n - 1; k >= 0; k--) {
+        const int slot = s - 32 * (int)g0s[k];
+        const unsigned ch = (slot >= 0 && slot < RS) ? stage[k * RS + slot] : 0xFFu;
+        if (ch == 0xFFu) { bad = 1; break; }    // cannot happen
+        const int j = (int)(stw[s] & 0xFFFF) + (int)ch;
+        jarr[k] = (uint16_t)j;
+        s = (int)(arcs[j].x & 0xFFFF);
+      }
+    }
+    bad = __shfl_sync(FULL, bad, 0);
+    if (bad) break;
+    s = __shfl_sync(FULL, s, 0);
+    __syncwarp();
+    int ol = 0;
+    if (lane < n) {
+      const int j = jarr[lane];
+      const int arc = arcid[j];
+      const int64_t t = r0 + lane;
+      const int lp = (int)(arcs[j].x >> 16);
+      ali[t] = a_tid[arc];
+      pf[t] = ll[(size_t)(rag ? lp : lp2pdf[lp]) * ldu + t];
+      ol = a_ol[arc];
+    }
+    // words are collected in walk order (descending frame); reversed at the end
+    const unsigned m = __ballot_sync(FULL, ol != 0);
+    if (ol != 0) {
+      const int idx = nw + __popc(m & ~((2u << lane) - 1u));
+      if (idx < wcap) words[idx] = ol;
+    }
+    nw += __popc(m);
+    __syncwarp();
+  }
+  if (bad) { if (lane == 0) { p.status[ul] = MFA_ALIGN_NO_FINAL; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; } return; }
+  __syncwarp();
+  const int nwc = nw < wcap ? nw : wcap;
+  for (int i = lane; i < nwc / 2; i += 32) { const int32_t x = words[i]; words[i] = words[nwc - 1 - i]; words[nwc - 1 - i] = x; }
+  if (lane == 0) { p.status[ul] = result; p.num_words[ul] = nw; }
+}
+
+}  // namespace
+
+namespace mfa {
+
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P) {
+  return (size_t)(((((S + 1) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, BT_ROWS * RS + 4 * BT_ROWS) + 16);
+}
+
+// Launches the band kernel for the utterances in `subset` (chunk-local ids, all band_ok).  d_fallback: [1 + n_utts] ints, count
+// first; cleared here.
+int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback) {
+  const mfa_graphs *g = a.g;
+  const int n = a.n_utts, ns = (int)subset.size();
+  CUDA_TRY(cudaMemsetAsync(d_fallback, 0, sizeof(int32_t), e->stream));
+  if (ns == 0) return MFA_OK;
+  const size_t limit = e->smem_optin - 4096;   // the kernel also has ~2 KB of static shared memory
+  std::vector<int64_t> bp_off(n + 1, 0);
+  std::vector<size_t> need(n, 0);
+  std::vector<int64_t> work(n, 0);
+  int64_t bp_total = 0;
+  for (int ul : subset) {
+    const int ug = a.utt0 + ul;
+    const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
+    const int64_t T = a.h_frame_off[ul + 1] - a.h_frame_off[ul];
+    bp_off[ul] = bp_total;
+    bp_total += (T * RS + T * 2 + 15) / 16 * 16;
+    need[ul] = viterbi_band_smem(S, A, P);
+    work[ul] = T;
+    if (need[ul] > limit) return set_error(MFA_ERR_UNSUPPORTED, "internal: band utterance exceeds shared memory");
+  }
+  uint8_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
+  MFA_TRY(e->getT<uint8_t>(DB_BBP, (size_t)bp_total + 16, &d_bp));
+  MFA_TRY(e->upload(DB_BBP_OFF, bp_off.data(), bp_off.size(), &d_bp_off));
+  constexpr int NC = mfa_engine::kSide;
+  size_t bounds[NC];
+  for (int c = 0; c < NC; c++) bounds[c] = std::min<size_t>(limit, (size_t)(14336.0 * std::pow(2.0, 0.34 * c)));   // 14 KB ... 190 KB
+  bounds[NC - 1] = limit;
+  std::vector<int> cls(n, 0);
+  for (int ul : subset) { int c = 0; while (c < NC - 1 && need[ul] > bounds[c]) c++; cls[ul] = c; }
+  std::vector<int32_t> order(subset);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cls[x] != cls[y] ? cls[x] < cls[y] : work[x] > work[y]; });
+  MFA_TRY(e->upload(DB_BORDER, order.data(), order.size(), &d_order));
+  BandParams p;
+  p.st_off = g->d_st_off; p.arc_off = g->d_arc_off; p.lp_off = g->d_lp_off;
+  p.b_start = g->d_b_start; p.b_maxback = g->d_b_maxback; p.a_tid = g->d_a_tid; p.a_olabel = g->d_a_olabel; p.lp2pdf = g->d_lp2pdf;
+  p.b_stw = g->d_b_stw; p.b_apk = g->d_b_apk; p.b_aw = g->d_b_aw; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
+  p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
+  p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u; p.bp_off = d_bp_off; p.bp = d_bp;
+  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fallback;
+  p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
+  p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
+  p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GMAX));
+  CUDA_TRY(cudaFuncSetAttribute(viterbi_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+  CUDA_TRY(cudaFuncSetAttribute(viterbi_band_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
+  for (int c = NC - 1; c >= 0; c--) {
+    int pos = 0, cnt = 0;
+    for (int k = 0; k < ns; k++) if (cls[order[k]] < c) pos++;
+    size_t mx = 0;
+    while (pos + cnt < ns && cls[order[pos + cnt]] == c) { mx = std::max(mx, need[order[pos + cnt]]); cnt++; }
+    if (cnt == 0) continue;
+    p.order = d_order + pos;
+    cudaStream_t st = e->side[c];
+    CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fork, 0));
+    viterbi_band_kernel<<<cnt, NT, (mx + 15) / 16 * 16, st>>>(p);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
+  }
+  return MFA_OK;
+}
+
+}  // namespace mfa

@@ -110,6 +110,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(L.lib().mfa_engine_launch_count(self._h))
 
+    @property
+    def band_fallbacks(self) -> int:
+        """Utterances the band Viterbi kernel handed to the sparse kernel so far (live window wider than the band)."""
+        return int(L.lib().mfa_engine_band_fallbacks(self._h))
+
     def gmm_timing(self):
         ms, n, rows = C.c_float(), C.c_int64(), C.c_int64()
         L.check(L.lib().mfa_engine_gmm_timing(self._h, C.byref(ms), C.byref(n), C.byref(rows)))
@@ -419,6 +424,17 @@ class Graphs:
         so, ao, po = (np.zeros(self.n_utts + 1, np.int64) for _ in range(3))
         L.check(L.lib().mfa_graphs_offsets(self._h, *[a.ctypes.data_as(C.c_void_p) for a in (so, ao, po)]))
         return so, ao, po
+
+    def band_view(self):
+        """The band layout the primary Viterbi kernel runs on (mfa_graphs_band_view): dict of per-utterance / per-state / per-arc arrays."""
+        so, ao, _ = self.offsets()
+        S, A = int(so[-1]), int(ao[-1])
+        ok, start, maxback = (np.zeros(self.n_utts, np.int32) for _ in range(3))
+        stw, orig = np.zeros(S, np.uint32), np.zeros(S, np.uint16)
+        apk, arcid = np.zeros(A, np.uint32), np.zeros(A, np.uint16)
+        L.check(L.lib().mfa_graphs_band_view(self._h, *[a.ctypes.data_as(C.c_void_p) for a in (ok, start, maxback, stw, orig, apk, arcid)]))
+        return dict(state_off=so, arc_off=ao, band_ok=ok, start=start, maxback=maxback, state_word=stw, orig_state=orig, arc_word=apk,
+                    arc_index=arcid)
 
     def max_words(self) -> np.ndarray:
         out = np.zeros(self.n_utts, np.int32)

@@ -158,6 +158,36 @@ def test_viterbi_parity_with_oracle(eng, triphone, beam, retry):
     assert total > 0 and same / total >= 0.999, same / total
 
 
+def _align_env(eng, sc, batch, beam, retry, monkeypatch, **env):
+    for k in ("MFA_VIT_BAND", "MFA_VIT_MAXGROUPS"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return _gpu_align_from_oracle_loglikes(eng, sc, batch, beam, retry)
+
+
+@pytest.mark.parametrize("triphone,beam,retry", [(True, 10.0, 40.0), (False, 3.0, 60.0), (True, 200.0, 0.0)])
+def test_band_kernel_equals_sparse_kernel(eng, monkeypatch, triphone, beam, retry):
+    """K3's two kernels implement one recursion: the band kernel (primary), the sparse kernel (epsilon graphs, fallback) and the
+    band kernel with a 1- or 2-group band (most utterances overflow and are re-run by the sparse kernel) must agree exactly."""
+    sc = build_synth_scenario(seconds=80.0, seed=5, triphone=triphone, n_phones=12, n_words=60, target_pdfs=100, gauss_per_pdf=2)
+    batch = E.GraphCompiler(sc["tm"], sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts)
+    f0 = eng.band_fallbacks
+    band = _align_env(eng, sc, batch, beam, retry, monkeypatch)
+    f1 = eng.band_fallbacks
+    sparse = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_BAND=0)
+    assert eng.band_fallbacks == f1
+    narrow = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_MAXGROUPS=1 if beam < 100 else 2)
+    assert eng.band_fallbacks > f1                      # the fallback path really ran
+    if beam <= 10.0:
+        assert f1 == f0                                   # ... and the default band is wide enough for ordinary beams
+    assert np.isin(sparse.status, (0, 1)).sum() > 0
+    for other in (band, narrow):
+        assert np.array_equal(other.status, sparse.status) and np.array_equal(other.num_words, sparse.num_words)
+        assert np.array_equal(other.ali, sparse.ali) and np.array_equal(other.words, sparse.words)
+        assert np.array_equal(other.total_like, sparse.total_like) and np.array_equal(other.per_frame, sparse.per_frame)
+
+
 def test_viterbi_edge_cases(eng):
     sc = build_synth_scenario(seconds=12.0, seed=4, n_phones=6, n_words=20, gauss_per_pdf=2)
     tm, am = sc["tm"], sc["am"]

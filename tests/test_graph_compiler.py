@@ -145,3 +145,69 @@ def test_batch_compile_threads_and_errors():
     back = K.read_fst(io.BytesIO(buf.getvalue()))
     rt = E.FstBatch.from_fsts([back]).export()[0]
     assert rt.num_states == a[2].num_states and np.array_equal(np.sort(rt.arc_ilabel), np.sort(a[2].arc_ilabel))
+
+
+def _check_band(fst, tm, bv, u):
+    """The band view is a renumbering of the same graph: a permutation, arcs grouped by destination, reach fields valid."""
+    s0, s1, a0, a1 = int(bv["state_off"][u]), int(bv["state_off"][u + 1]), int(bv["arc_off"][u]), int(bv["arc_off"][u + 1])
+    S, A = s1 - s0, a1 - a0
+    assert S == fst.num_states and A == fst.arc_src.shape[0]
+    orig = bv["orig_state"][s0:s1].astype(np.int64)
+    assert sorted(orig.tolist()) == list(range(S))              # permutation
+    pos = np.empty(S, np.int64)
+    pos[orig] = np.arange(S)
+    assert int(bv["start"][u]) == pos[fst.start]
+    stw, apk, aidx = bv["state_word"][s0:s1], bv["arc_word"][a0:a1], bv["arc_index"][a0:a1].astype(np.int64)
+    begin, cnt, reach = (stw & 0xFFFF).astype(np.int64), ((stw >> 16) & 0xFF).astype(np.int64), (stw >> 24).astype(np.int64)
+    assert begin[0] == 0 and np.array_equal(begin[1:], np.cumsum(cnt)[:-1]) and cnt.sum() == A
+    # by-source order of the packed graph = stable sort of the fst's arcs by source state
+    by_src = np.argsort(fst.arc_src, kind="stable")
+    assert sorted(aidx.tolist()) == list(range(A))              # every arc exactly once
+    tid2pdf = np.maximum(tm.tid2pdf, 0)
+    maxback, fwd = 0, np.zeros(S, np.int64)
+    for d in range(S):
+        lst = aidx[begin[d]:begin[d] + cnt[d]]
+        assert np.all(np.diff(lst) > 0)                         # ties resolve to the lowest by-source arc index
+        for j, k in zip(range(begin[d], begin[d] + cnt[d]), lst):
+            a = by_src[k]
+            assert pos[fst.arc_dst[a]] == d and (apk[j] & 0xFFFF) == pos[fst.arc_src[a]]
+            ps = int(pos[fst.arc_src[a]])
+            fwd[ps] = max(fwd[ps], d - ps)
+            maxback = max(maxback, ps - d)
+    assert np.array_equal(fwd, reach) and maxback == int(bv["maxback"][u])
+    # local pdf ids in the arc words index the utterance's sorted pdf list
+    pdfs = np.unique(tid2pdf[fst.arc_ilabel[fst.arc_ilabel > 0]])
+    for j in range(A):
+        a = by_src[aidx[j]]
+        assert pdfs[apk[j] >> 16] == tid2pdf[fst.arc_ilabel[a]]
+    return maxback, int(reach.max())
+
+
+@pytest.mark.parametrize("triphone", [False, True])
+def test_band_view_is_a_forward_renumbering(triphone):
+    lex, pt, topo, tree, tm = _setup(triphone)
+    # the default 5-state silence model: its ergodic middle states are the only cycles (besides self-loops) in a training graph
+    rng = np.random.default_rng(3)
+    topo = SY.make_topology(pt)
+    tree, n_pdfs = SY.make_tree(rng, topo, triphone, 40)
+    tm = SY.make_transition_model(topo, tree, n_pdfs)
+    w = lex.word_table
+    seqs = [[w["x"], w["y"], w["z"], w["x"]], [], [w["z"]] * 6, [w["y"]]]
+    batch = E.GraphCompiler(tm, tree, lex).compile(seqs)
+    fsts = batch.export()
+    bv = E.Graphs(batch, tm).band_view()
+    assert bv["band_ok"].tolist() == [1] * len(seqs)
+    for u, f in enumerate(fsts):
+        maxback, reach = _check_band(f, tm, bv, u)
+        assert maxback <= 16 and reach <= 255
+
+
+def test_band_view_refuses_epsilon_graphs():
+    lex, pt, topo, tree, tm = _setup(False)
+    f = E.GraphCompiler(tm, tree, lex).compile([[lex.word_table["x"]]]).export()[0]
+    # splice an input-epsilon arc in front of the start state (as a Kaldi fsts.ark graph may have)
+    g = K.Fst(f.num_states, f.num_states + 1, np.append(f.arc_src, f.num_states).astype(np.int32), np.append(f.arc_ilabel, 0).astype(np.int32),
+              np.append(f.arc_olabel, 0).astype(np.int32), np.append(f.arc_dst, f.start).astype(np.int32),
+              np.append(f.arc_weight, 0.25).astype(np.float32), np.append(f.finals, np.inf).astype(np.float32))
+    bv = E.Graphs(E.FstBatch.from_fsts([g, f]), tm).band_view()
+    assert bv["band_ok"].tolist() == [0, 1]
