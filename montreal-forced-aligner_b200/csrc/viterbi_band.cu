@@ -45,6 +45,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int NW = 4;                // warps per utterance: warp w pulls window groups w, w + NW
 constexpr int NT = NW * 32;
 constexpr int GPW = GMAX / NW;       // groups per warp
+constexpr int SEG = GPW * 32;        // survivors one warp can produce per frame
 
 struct BandParams {
   const int64_t *st_off, *arc_off, *lp_off;
@@ -73,37 +74,42 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // min_active-th (0-based) smallest live cost (Kaldi: nth_element over the token costs).  The decoder sits at this branch on
-// most frames when the beam alone keeps fewer than min_active tokens, so it must be cheap: the survivors' costs are kept as a
-// compact list (written in phase 2 of the previous frame) and sorted with a shuffle bitonic network -- 15 exchange steps for
-// up to 32 values, 21 two-register steps for up to 64; larger sets use a bitwise radix select over the list.
-__device__ __forceinline__ float bitonic_step(float x, int lane, int e, int size, int stride) {
-  const float y = __shfl_xor_sync(FULL, x, stride);
-  const bool up = (e & size) == 0, lower = (lane & stride) == 0;
-  return (lower == up) ? fminf(x, y) : fmaxf(x, y);
+// most frames when the beam alone keeps fewer than min_active tokens, so it must be short AND shallow: the survivors' costs
+// are compact per-warp segments (written while pruning the previous frame); every lane ranks its own value against all
+// others with independent broadcast reads (no dependent exchange network), and the lane whose rank is `want` holds the
+// answer.  More than 64 survivors: bitwise radix select.
+struct LiveList { const float *seg; int n[NW]; };     // seg[w * SEG + j], j < n[w]
+__device__ __forceinline__ float live_at(const LiveList &L, int i) {
+  int w = 0;
+#pragma unroll
+  for (int k = 0; k < NW - 1; k++) { if (i >= L.n[k] && w == k) { i -= L.n[k]; w = k + 1; } }
+  return L.seg[w * SEG + i];
 }
-
-__device__ __noinline__ float select_rank(const float *live, int n, int want, int lane) {
-  if (n <= 32) {
-    float x = lane < n ? live[lane] : INFINITY;
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) x = bitonic_step(x, lane, lane, size, stride);
-    return __shfl_sync(FULL, x, want);
-  }
+__device__ __forceinline__ float select_rank(const LiveList &L, int n, int want, int lane) {
   if (n <= 64) {
-    float x0 = live[lane], x1 = lane + 32 < n ? live[lane + 32] : INFINITY;
+    const float x0 = lane < n ? live_at(L, lane) : INFINITY, x1 = (n > 32 && lane + 32 < n) ? live_at(L, lane + 32) : INFINITY;
+    int r0 = 0, r1 = 0, jj = 0;
+    if (n <= 32) {
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        x0 = bitonic_step(x0, lane, lane, size, stride);
-        x1 = bitonic_step(x1, lane, lane + 32, size, stride);
+      for (int w = 0; w < NW; w++) {
+        const float *sg = L.seg + w * SEG;
+#pragma unroll 4
+        for (int j = 0; j < L.n[w]; j++, jj++) { const float y = sg[j]; r0 += (y < x0) || (y == x0 && jj < lane); }
       }
-    { const float a = fminf(x0, x1), b = fmaxf(x0, x1); x0 = a; x1 = b; }     // size 64, stride 32: same lane
+    } else {
 #pragma unroll
-    for (int stride = 16; stride > 0; stride >>= 1) { x0 = bitonic_step(x0, lane, lane, 64, stride); x1 = bitonic_step(x1, lane, lane, 64, stride); }
-    return want < 32 ? __shfl_sync(FULL, x0, want) : __shfl_sync(FULL, x1, want - 32);
+      for (int w = 0; w < NW; w++) {
+        const float *sg = L.seg + w * SEG;
+#pragma unroll 2
+        for (int j = 0; j < L.n[w]; j++, jj++) {
+          const float y = sg[j];
+          r0 += (y < x0) || (y == x0 && jj < lane);
+          r1 += (y < x1) || (y == x1 && jj < lane + 32);
+        }
+      }
+    }
+    const unsigned m0 = __ballot_sync(FULL, r0 == want && lane < n), m1 = __ballot_sync(FULL, r1 == want && lane + 32 < n);
+    return m0 ? __shfl_sync(FULL, x0, __ffs(m0) - 1) : __shfl_sync(FULL, x1, __ffs(m1) - 1);
   }
   // costs are >= +0, so the raw bit patterns order like the values
   unsigned prefix = 0, mask = 0;
@@ -111,7 +117,7 @@ __device__ __noinline__ float select_rank(const float *live, int n, int want, in
     const unsigned b = 1u << bit;
     int c0 = 0;
     for (int i = lane; i < ((n + 31) & ~31); i += 32) {
-      const unsigned x = i < n ? __float_as_uint(live[i]) : 0xFFFFFFFFu;
+      const unsigned x = i < n ? __float_as_uint(live_at(L, i)) : 0xFFFFFFFFu;
       c0 += __popc(__ballot_sync(FULL, (x & mask) == prefix && !(x & b)));
     }
     if (want >= c0) { prefix |= b; want -= c0; }
@@ -120,13 +126,44 @@ __device__ __noinline__ float select_rank(const float *live, int n, int want, in
   return __uint_as_float(prefix);
 }
 
+// pull for one band state in two halves, so that the shared-memory reads are in flight while the cutoff is being ranked:
+// gather the first four in-arcs' (source cost, candidate cost) -- in-degrees are 2..5 in training graphs -- then reduce them
+// under the cutoff; a loop takes any further arcs.
+struct Pull { uint32_t st; float c[4], x[4]; };
+__device__ __forceinline__ void pull_gather(Pull &q, const uint32_t st, const uint2 *__restrict__ arcs, const float *__restrict__ cur,
+                                            const float *__restrict__ acf, const float nacwt) {
+  q.st = st;
+  const int a = st & 0xFFFF, cnt = (st >> 16) & 0xFF;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    q.c[j] = INFINITY; q.x[j] = INFINITY;
+    if (j < cnt) {
+      const uint2 ar = arcs[a + j];
+      q.c[j] = cur[ar.x & MASK];
+      q.x[j] = __fadd_rn(__fadd_rn(q.c[j], __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
+    }
+  }
+}
+__device__ __forceinline__ void pull_reduce(const Pull &q, const uint2 *__restrict__ arcs, const float *__restrict__ cur, const float *__restrict__ acf,
+                                            const float cutoff, const float nacwt, float &v, uint32_t &arg) {
+  v = INFINITY; arg = 0xFFu;
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (q.c[j] < cutoff && q.x[j] < v) { v = q.x[j]; arg = (uint32_t)j; }
+  const int a = q.st & 0xFFFF, cnt = (q.st >> 16) & 0xFF;
+  for (int j = 4; j < cnt; j++) {
+    const uint2 ar = arcs[a + j];
+    const float c = cur[ar.x & MASK];
+    const float x = __fadd_rn(__fadd_rn(c, __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
+    if (c < cutoff && x < v) { v = x; arg = (uint32_t)j; }
+  }
+}
+
 __global__ void __launch_bounds__(NT, 4)
 viterbi_band_kernel(BandParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  __shared__ uint32_t s_min[NW];          // per-warp best new cost (ordered key) of the current frame
-  __shared__ int s_stat[NW][4];           // per-warp {lowest live state, highest live state, highest reachable state, n_tot | n_beam << 16}
-  __shared__ float s_live[2][RS];         // compact list of the survivors' costs of frame t in s_live[t & 1] (for GetCutoff's rank)
-  __shared__ int s_cnt[2];
+  __shared__ uint32_t s_min[NW];                   // per-warp best new cost (ordered key) of the current frame
+  __shared__ __align__(16) int s_stat[NW][4];      // per-warp {lowest live state, highest live state, highest reachable state, n_tot | n_beam << 16}
+  __shared__ float s_live[NW * SEG];               // per-warp compact lists of the survivors' costs (for GetCutoff's rank)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ul = p.order[blockIdx.x];
   const int ug = p.utt0 + ul;
@@ -137,14 +174,15 @@ viterbi_band_kernel(BandParams p) {
   if (T == 0) { if (tid == 0) { p.status[ul] = MFA_ALIGN_ZERO_FRAMES; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; } return; }
   const int start = p.b_start[ug], maxback = p.b_maxback[ug];
 
-  uint32_t *stw = (uint32_t *)smraw;                            // [S]  first in-arc | in-degree << 16 | forward reach << 24
-  uint2 *arcs = (uint2 *)(stw + ((S + 1) & ~1));                // [A]  {source state | local pdf << 16, weight bits}
-  float *ring = (float *)smraw + ((((S + 1) & ~1) + 2 * A + 3) & ~3);   // [2][WRING], 16-byte aligned
+  uint32_t *stw = (uint32_t *)smraw;                            // [S+]  first in-arc | in-degree << 16 | forward reach << 24
+  const int Spad = (S + 32) & ~1;                               // states beyond S read as 0 (no in-arcs) up to the next group
+  uint2 *arcs = (uint2 *)(stw + Spad);                          // [A]  {source state | local pdf << 16, weight bits}
+  float *ring = (float *)smraw + ((Spad + 2 * A + 3) & ~3);     // [2][WRING], 16-byte aligned
   float *ac = ring + 2 * WRING;                                 // [NST][P][4] raw log-likelihoods; later the back-trace staging area
   {
     const uint32_t *gs = p.b_stw + p.st_off[ug], *ga = p.b_apk + p.arc_off[ug];
     const float *gw = p.b_aw + p.arc_off[ug];
-    for (int i = tid; i < S; i += NT) stw[i] = gs[i];
+    for (int i = tid; i < Spad; i += NT) stw[i] = i < S ? gs[i] : 0u;
     for (int i = tid; i < A; i += NT) arcs[i] = make_uint2(ga[i], __float_as_uint(gw[i]));
   }
   const bool rag = p.ll_off != nullptr;
@@ -156,10 +194,11 @@ viterbi_band_kernel(BandParams p) {
   const float inf = INFINITY, nacwt = -p.acwt;
   const int NB = (int)((T + 3) >> 2);
   const int max_groups = min(p.max_groups, GMAX);
+  const int gend = (S - 1) >> 5;                            // last group holding a state
 
-  auto issue_block = [&](int b) {
+  auto issue_block = [&](int b, int stage) {
     if (b < NB) {
-      float *dst = ac + (size_t)(b % NST) * 4 * P;
+      float *dst = ac + (size_t)stage * 4 * P;
       for (int lp = tid; lp < P; lp += NT) cp_async16(dst + 4 * lp, ll + (size_t)(rag ? lp : lp2pdf[lp]) * ldu + 4 * (size_t)b);
     }
     cp_async_commit();
@@ -179,57 +218,53 @@ viterbi_band_kernel(BandParams p) {
     for (int i = tid; i < 2 * WRING; i += NT) ring[i] = inf;
     cur = ring; nxt = ring + WRING;
     __syncthreads();
-    if (tid == 0) { cur[start & MASK] = 0.0f; s_cnt[0] = 0; s_cnt[1] = 0; s_live[1][0] = 0.0f; }
+    if (tid == 0) { cur[start & MASK] = 0.0f; s_live[0] = 0.0f; }
     lo = hi = start;
     int hib = start + (int)(stw[start] >> 24);
     int n_tot = 1, n_beam = 1;
+    LiveList L;
+    L.seg = s_live; L.n[0] = 1;
+#pragma unroll
+    for (int w = 1; w < NW; w++) L.n[w] = 0;
     float cutoff = inf, adaptive = inf;
     offset = 0.0;
-    issue_block(0); issue_block(1); issue_block(2);
+    issue_block(0, 0); issue_block(1, 1); issue_block(2, 2);
     cp_async_wait<2>();
     __syncthreads();
+    int stage = 0;                                            // stage holding the current 4-frame block
     bool dead = false;
     for (int64_t t = 0; t < T; t++) {
+      const float *acf = ac + (size_t)stage * 4 * P + (int)(t & 3);
+      const int glo = max(lo - maxback, 0) >> 5;
+      const int ng = min(hib >> 5, gend) - glo + 1;
+      if (ng > max_groups) { overflow = true; break; }
+      // ---- pull, first half: warp w owns groups w and w + NW of the window; the gather does not need the cutoff
+      Pull q;
+      pull_gather(q, warp < ng ? stw[(glo + warp) * 32 + lane] : 0u, arcs, cur, acf, nacwt);
       // ---- GetCutoff on the live tokens (normalised: best == 0); every warp computes the same values
       if (n_tot <= p.min_active) { cutoff = inf; adaptive = inf; }
       else if (n_beam > p.min_active) { cutoff = beam; adaptive = beam; }
-      else { cutoff = select_rank(s_live[(t & 1) ^ 1], n_tot, p.min_active, lane); adaptive = cutoff + p.beam_delta; }
-      const float *acf = ac + (size_t)((int)(t >> 2) % NST) * 4 * P + (int)(t & 3);
-      const int glo = max(lo - maxback, 0) >> 5;
-      const int ng = (min(hib, S - 1) >> 5) - glo + 1;
-      if (ng > max_groups) { overflow = true; break; }
-      // ---- pull: warp w owns groups w, w + NW of the window
+      else { cutoff = select_rank(L, n_tot, p.min_active, lane); adaptive = cutoff + p.beam_delta; }
+      // ---- pull, second half
       float nv[GPW];
       uint32_t na[GPW];
-      uint32_t kmin = 0xFFFFFFFFu;
+      pull_reduce(q, arcs, cur, acf, cutoff, nacwt, nv[0], na[0]);
+      na[0] |= q.st >> 24 << 8;
+      uint32_t kmin = f2key(nv[0]);
 #pragma unroll
-      for (int k = 0; k < GPW; k++) {
-        const int i = warp + k * NW;
+      for (int k = 1; k < GPW; k++) {
         nv[k] = inf; na[k] = 0xFFu;
-        if (i < ng) {
-          const int d = (glo + i) * 32 + lane;
-          if (d < S) {
-            const uint32_t st = stw[d];
-            int a = st & 0xFFFF;
-            const int cnt = (st >> 16) & 0xFF;
-            float v = inf;
-            uint32_t arg = 0xFFu;
-            for (int j = 0; j < cnt; j++, a++) {
-              const uint2 ar = arcs[a];
-              const float c = cur[ar.x & MASK];
-              if (c < cutoff) {
-                const float x = __fadd_rn(__fadd_rn(c, __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
-                if (x < v) { v = x; arg = (uint32_t)j; }
-              }
-            }
-            nv[k] = v; na[k] = arg | (st >> 24 << 8);
-            kmin = min(kmin, f2key(v));
-          }
+        if (warp + k * NW < ng) {
+          Pull q2;
+          pull_gather(q2, stw[(glo + warp + k * NW) * 32 + lane], arcs, cur, acf, nacwt);
+          pull_reduce(q2, arcs, cur, acf, cutoff, nacwt, nv[k], na[k]);
+          na[k] |= q2.st >> 24 << 8;
+          kmin = min(kmin, f2key(nv[k]));
         }
       }
       kmin = __reduce_min_sync(FULL, kmin);
       if (lane == 0) s_min[warp] = kmin;
-      __syncthreads();                                 // A: every warp has finished reading `cur`; s_min complete
+      __syncthreads();                                 // A: every warp has finished reading `cur` and the survivor lists; s_min complete
       {
         uint32_t m = s_min[0];
 #pragma unroll
@@ -239,8 +274,9 @@ viterbi_band_kernel(BandParams p) {
       const float best_new = key2f(kmin);
       if (!(best_new < inf)) { dead = true; break; }
       const float next_cutoff = best_new + adaptive;   // inf stays inf
+      // ---- prune, renormalise, back-pointers, this warp's survivor list and window bounds
       uint8_t *bprow = bp + (size_t)t * RS;
-      int mylo = 0x7fffffff, myhi = -1, myhib = -1, nt = 0, nb = 0;
+      int nt = 0, nb = 0, myhib = -1, flo = 0x7fffffff, fhi = -1;
 #pragma unroll
       for (int k = 0; k < GPW; k++) {
         const int i = warp + k * NW;
@@ -253,29 +289,30 @@ viterbi_band_kernel(BandParams p) {
           cur[d & MASK] = inf;
           __stcs(bprow + i * 32 + lane, (uint8_t)(keep ? (na[k] & 0xFFu) : 0xFFu));
           const unsigned km = __ballot_sync(FULL, keep);
-          if (km) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_cnt[t & 1], __popc(km));
-            base = __shfl_sync(FULL, base, 0);
-            if (keep) s_live[t & 1][base + __popc(km & ((1u << lane) - 1u))] = v;
-          }
+          if (keep) { s_live[warp * SEG + nt + __popc(km & ((1u << lane) - 1u))] = v; myhib = max(myhib, d + (int)(na[k] >> 8)); }
           nt += __popc(km);
           nb += __popc(__ballot_sync(FULL, keep && v <= beam));
-          if (keep) { mylo = min(mylo, d); myhi = max(myhi, d); myhib = max(myhib, d + (int)(na[k] >> 8)); }
+          if (km) { flo = min(flo, (glo + i) * 32 + __ffs(km) - 1); fhi = (glo + i) * 32 + 31 - __clz(km); }
         }
       }
-      if (tid == 0) s_cnt[(t & 1) ^ 1] = 0;            // the other list was read before A; it is appended to in the next frame
-      mylo = __reduce_min_sync(FULL, mylo); myhi = __reduce_max_sync(FULL, myhi); myhib = __reduce_max_sync(FULL, myhib);
-      if (lane == 0) { s_stat[warp][0] = mylo; s_stat[warp][1] = myhi; s_stat[warp][2] = myhib; s_stat[warp][3] = nt | (nb << 16); }
+      myhib = __reduce_max_sync(FULL, myhib);
+      if (lane == 0) *(int4 *)s_stat[warp] = make_int4(flo, fhi, myhib, nt | (nb << 16));
       if (tid == 0) bpg[t] = (uint16_t)glo;
-      if ((t & 3) == 3) { issue_block((int)((t + 1) >> 2) + 2); cp_async_wait<2>(); }   // nobody reads `ac` between A and B
-      __syncthreads();                                 // B: rings, statistics and the next frame's acoustic block are visible
-      lo = s_stat[0][0]; hi = s_stat[0][1]; hib = s_stat[0][2];
-      { const int x = s_stat[0][3]; n_tot = x & 0xFFFF; n_beam = x >> 16; }
+      if ((t & 3) == 3) {                              // the block just finished frees its stage for block b + 3; nobody reads `ac` between A and B
+        issue_block((int)(t >> 2) + 3, stage);
+        stage = stage == NST - 1 ? 0 : stage + 1;
+        cp_async_wait<2>();
+      }
+      __syncthreads();                                 // B: rings, lists, statistics and the next frame's acoustic block are visible
+      {
+        const int4 s0 = *(const int4 *)s_stat[0];
+        lo = s0.x; hi = s0.y; hib = s0.z; n_tot = s0.w & 0xFFFF; n_beam = s0.w >> 16; L.n[0] = s0.w & 0xFFFF;
 #pragma unroll
-      for (int w = 1; w < NW; w++) {
-        lo = min(lo, s_stat[w][0]); hi = max(hi, s_stat[w][1]); hib = max(hib, s_stat[w][2]);
-        const int x = s_stat[w][3]; n_tot += x & 0xFFFF; n_beam += x >> 16;
+        for (int w = 1; w < NW; w++) {
+          const int4 sw = *(const int4 *)s_stat[w];
+          lo = min(lo, sw.x); hi = max(hi, sw.y); hib = max(hib, sw.z);
+          n_tot += sw.w & 0xFFFF; n_beam += sw.w >> 16; L.n[w] = sw.w & 0xFFFF;
+        }
       }
       offset += (double)best_new;
       float *tmp = cur; cur = nxt; nxt = tmp;
@@ -321,10 +358,10 @@ viterbi_band_kernel(BandParams p) {
     if (lane == 0) { p.status[ul] = result; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; }
     return;
   }
-  // ---- back-trace (warp 0): 32 frames at a time.  The rows are staged in shared memory by the warp, lane 0 follows the chain
+  // ---- back-trace: 32 frames at a time.  The rows are staged in shared memory by the warp, lane 0 follows the chain
   // (three dependent shared-memory reads per frame), then the lanes emit one frame each.
-  uint8_t *stage = (uint8_t *)ac;                                  // [BT_ROWS][RS]
-  uint16_t *g0s = (uint16_t *)(stage + BT_ROWS * RS);              // [BT_ROWS]
+  uint8_t *stg = (uint8_t *)ac;                                    // [BT_ROWS][RS]
+  uint16_t *g0s = (uint16_t *)(stg + BT_ROWS * RS);                // [BT_ROWS]
   uint16_t *jarr = g0s + BT_ROWS;                                  // [BT_ROWS]
   const int32_t *a_tid = p.a_tid + p.arc_off[ug], *a_ol = p.a_olabel + p.arc_off[ug];
   const uint16_t *arcid = p.b_arcid + p.arc_off[ug];
@@ -337,13 +374,13 @@ viterbi_band_kernel(BandParams p) {
     const int64_t r0 = tb > BT_ROWS ? tb - BT_ROWS : 0;
     const int n = (int)(tb - r0);
     const uint4 *src = (const uint4 *)(bp + (size_t)r0 * RS);
-    for (int i = lane; i < n * (RS / 16); i += 32) ((uint4 *)stage)[i] = __ldcs(src + i);
+    for (int i = lane; i < n * (RS / 16); i += 32) ((uint4 *)stg)[i] = __ldcs(src + i);
     if (lane < n) g0s[lane] = bpg[r0 + lane];
     __syncwarp();
     if (lane == 0) {
       for (int k = n - 1; k >= 0; k--) {
         const int slot = s - 32 * (int)g0s[k];
-        const unsigned ch = (slot >= 0 && slot < RS) ? stage[k * RS + slot] : 0xFFu;
+        const unsigned ch = (slot >= 0 && slot < RS) ? stg[k * RS + slot] : 0xFFu;
         if (ch == 0xFFu) { bad = 1; break; }    // cannot happen
         const int j = (int)(stw[s] & 0xFFFF) + (int)ch;
         jarr[k] = (uint16_t)j;
@@ -385,7 +422,7 @@ viterbi_band_kernel(BandParams p) {
 namespace mfa {
 
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P) {
-  return (size_t)(((((S + 1) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, BT_ROWS * RS + 4 * BT_ROWS) + 16);
+  return (size_t)(((((S + 32) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, BT_ROWS * RS + 4 * BT_ROWS) + 16);
 }
 
 // Launches the band kernel for the utterances in `subset` (chunk-local ids, all band_ok).  d_fallback: [1 + n_utts] ints, count
