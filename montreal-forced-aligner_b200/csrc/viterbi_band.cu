@@ -39,8 +39,8 @@ constexpr int GMAX = 8;              // groups of 32 band states a frame may spa
 constexpr int RS = GMAX * 32;        // back-pointer row stride in bytes
 constexpr int WRING = 512;           // cost ring entries; >= RS + largest maxback (96) + 32
 constexpr unsigned MASK = WRING - 1;
-constexpr int NST = 3;               // acoustic-cost stages of 4 frames
-constexpr int BT_ROWS = 32;          // frames per back-trace batch
+constexpr int NST = 2;               // acoustic-cost stages of 4 frames (a block is prefetched 4 frames ahead: several microseconds)
+constexpr int BT_ROWS = 16;          // frames per back-trace batch
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NW = 4;                // warps per utterance: warp w pulls window groups w, w + NW
 constexpr int NT = NW * 32;
@@ -86,6 +86,16 @@ __device__ __forceinline__ float live_at(const LiveList &L, int i) {
   return L.seg[w * SEG + i];
 }
 __device__ __forceinline__ float select_rank(const LiveList &L, int n, int want, int lane) {
+  if (n <= 32 && n - want <= 12) {
+    // the usual case: a few more survivors than min_active.  The (n - want)-th largest value is the answer: peel maxima off with
+    // one REDUX each (costs are >= +0, so their bit patterns order like the values; a peeled or empty lane holds 0)
+    uint32_t xb = lane < n ? __float_as_uint(live_at(L, lane)) : 0u, m = 0u;
+    for (int r = n - want; r > 0; r--) {
+      m = __reduce_max_sync(FULL, xb);
+      if (r > 1) { const unsigned who = __ballot_sync(FULL, xb == m); if (lane == __ffs(who) - 1) xb = 0u; }
+    }
+    return __uint_as_float(m);
+  }
   if (n <= 64) {
     const float x0 = lane < n ? live_at(L, lane) : INFINITY, x1 = (n > 32 && lane + 32 < n) ? live_at(L, lane + 32) : INFINITY;
     int r0 = 0, r1 = 0, jj = 0;
@@ -228,8 +238,8 @@ viterbi_band_kernel(BandParams p) {
     for (int w = 1; w < NW; w++) L.n[w] = 0;
     float cutoff = inf, adaptive = inf;
     offset = 0.0;
-    issue_block(0, 0); issue_block(1, 1); issue_block(2, 2);
-    cp_async_wait<2>();
+    issue_block(0, 0); issue_block(1, 1);
+    cp_async_wait<1>();
     __syncthreads();
     int stage = 0;                                            // stage holding the current 4-frame block
     bool dead = false;
@@ -298,10 +308,10 @@ viterbi_band_kernel(BandParams p) {
       myhib = __reduce_max_sync(FULL, myhib);
       if (lane == 0) *(int4 *)s_stat[warp] = make_int4(flo, fhi, myhib, nt | (nb << 16));
       if (tid == 0) bpg[t] = (uint16_t)glo;
-      if ((t & 3) == 3) {                              // the block just finished frees its stage for block b + 3; nobody reads `ac` between A and B
-        issue_block((int)(t >> 2) + 3, stage);
+      if ((t & 3) == 3) {                              // the block just finished frees its stage for block b + 2; nobody reads `ac` between A and B
+        issue_block((int)(t >> 2) + NST, stage);
         stage = stage == NST - 1 ? 0 : stage + 1;
-        cp_async_wait<2>();
+        cp_async_wait<NST - 1>();                      // everything but the block just issued has landed: the next block is complete
       }
       __syncthreads();                                 // B: rings, lists, statistics and the next frame's acoustic block are visible
       {
