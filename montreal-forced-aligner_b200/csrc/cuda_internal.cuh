@@ -138,7 +138,8 @@ struct ViterbiArgs {
   mfa_align_opts opts;
 };
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
-size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P);   // shared memory the band kernel needs for one utterance
+bool viterbi_band_graph_in_smem();                            // MFA_VIT_GRAPH_SMEM=1: copy each graph to shared memory (default: read it through L1)
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem);   // shared memory the band kernel needs for one utterance
 int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
 }  // namespace mfa

@@ -267,6 +267,8 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
   if (g->d_blob && g->device == e->device) return MFA_OK;
   if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
   size_t A = g->a_src.size();
+  std::vector<uint32_t> barc(2 * A);
+  for (size_t a = 0; a < A; a++) { barc[2 * a] = g->b_apk[a]; std::memcpy(&barc[2 * a + 1], &g->b_aw[a], 4); }
   std::vector<uint32_t> pack(A);
   for (size_t a = 0; a < A; a++) pack[a] = (uint32_t)(g->a_dst[a] & 0xFFFF) | ((uint32_t)(g->a_lp[a] < 0 ? 0xFFFF : g->a_lp[a]) << 16);
   for (int u = 0; u < g->n_utts; u++)
@@ -281,8 +283,8 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
       {pack.data(), A * 4, (void **)&g->d_a_pack}, {g->a_w.data(), A * 4, (void **)&g->d_a_w},
       {g->final_w.data(), g->final_w.size() * 4, (void **)&g->d_final_w}, {g->a_src.data(), A * 4, (void **)&g->d_a_src},
       {g->b_start.data(), g->b_start.size() * 4, (void **)&g->d_b_start}, {g->b_maxback.data(), g->b_maxback.size() * 4, (void **)&g->d_b_maxback},
-      {g->b_stw.data(), g->b_stw.size() * 4, (void **)&g->d_b_stw}, {g->b_apk.data(), g->b_apk.size() * 4, (void **)&g->d_b_apk},
-      {g->b_aw.data(), g->b_aw.size() * 4, (void **)&g->d_b_aw}, {g->b_fin.data(), g->b_fin.size() * 4, (void **)&g->d_b_fin},
+      {g->b_stw.data(), g->b_stw.size() * 4, (void **)&g->d_b_stw}, {barc.data(), barc.size() * 4, (void **)&g->d_b_arc},
+      {g->b_fin.data(), g->b_fin.size() * 4, (void **)&g->d_b_fin},
       {g->b_arcid.data(), g->b_arcid.size() * 2, (void **)&g->d_b_arcid}, {g->b_orig.data(), g->b_orig.size() * 2, (void **)&g->d_b_orig}};
   size_t total = 0;
   for (auto &it : items) total += (it.bytes + 255) / 256 * 256;

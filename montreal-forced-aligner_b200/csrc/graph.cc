@@ -366,8 +366,9 @@ static bool build_band(int S, int A, int start, const int32_t *inb, const int32_
     fwd[ps] = std::max(fwd[ps], pd - ps);
     maxback = std::max(maxback, ps - pd);
   }
-  for (int s = 0; s < S; s++) { if (cnt[s + 1] > 255 || fwd[s] > 255) return false; cnt[s + 1] += cnt[s]; }
-  if (maxback > 96) return false;
+  // in-degree, forward reach and the back-pointer's source-delta code (dst - src + 16) are packed into bytes
+  for (int s = 0; s < S; s++) { if (cnt[s + 1] > 254 || fwd[s] > 239) return false; cnt[s + 1] += cnt[s]; }
+  if (maxback > 16) return false;
   o.start = pos[start]; o.maxback = maxback;
   o.stw.assign(S, 0); o.fin.assign(S, 0.0f); o.orig.assign(S, 0);
   o.apk.assign(A, 0); o.aw.assign(A, 0.0f); o.arcid.assign(A, 0);

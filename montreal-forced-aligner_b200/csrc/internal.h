@@ -38,8 +38,9 @@ struct mfa_graphs {
   int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr, *d_a_src = nullptr;
   uint32_t *d_a_pack = nullptr;  // dst (low 16) | lp (high 16, 0xFFFF = epsilon)
   int32_t *d_b_start = nullptr, *d_b_maxback = nullptr;
-  uint32_t *d_b_stw = nullptr, *d_b_apk = nullptr;
-  float *d_b_aw = nullptr, *d_b_fin = nullptr;
+  uint32_t *d_b_stw = nullptr;
+  void *d_b_arc = nullptr;       // uint2 per arc: {b_apk, bits of b_aw}
+  float *d_b_fin = nullptr;
   uint16_t *d_b_arcid = nullptr, *d_b_orig = nullptr;
   float *d_a_w = nullptr, *d_final_w = nullptr;
   // per-utterance Gaussian tiling for the ragged K2 path (cached against the model's tiling version)

@@ -640,7 +640,7 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     bool ok = use_band && g->band_ok[ug];
     if (ok) {
       const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
-      ok = viterbi_band_smem(S, A, P) <= e->smem_optin - 4096;
+      ok = viterbi_band_smem(S, A, P, viterbi_band_graph_in_smem()) <= e->smem_optin - 4096;
     }
     (ok ? band : sparse).push_back(u);
   }

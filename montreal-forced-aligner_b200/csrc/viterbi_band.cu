@@ -36,29 +36,31 @@ using namespace mfa;
 
 namespace {
 constexpr int GMAX = 8;              // groups of 32 band states a frame may span
-constexpr int RS = GMAX * 32;        // back-pointer row stride in bytes
+constexpr int RS = GMAX * 32;        // window slots per frame
+constexpr int ROWB = RS * 2;         // back-pointer row stride in bytes (2 bytes per slot)
+constexpr int BIAS = 16;             // back-pointer source-delta code = (dst - src) + BIAS, in 0..255
 constexpr int WRING = 512;           // cost ring entries; >= RS + largest maxback (96) + 32
 constexpr unsigned MASK = WRING - 1;
 constexpr int NST = 2;               // acoustic-cost stages of 4 frames (a block is prefetched 4 frames ahead: several microseconds)
-constexpr int BT_ROWS = 16;          // frames per back-trace batch
+constexpr int BT_ROWS = 8;           // frames per back-trace batch (two staging buffers)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int NW = 4;                // warps per utterance: warp w pulls window groups w, w + NW
-constexpr int NT = NW * 32;
-constexpr int GPW = GMAX / NW;       // groups per warp
-constexpr int SEG = GPW * 32;        // survivors one warp can produce per frame
+// Warps per utterance (template parameter NW = 4 or 2): warp w pulls window groups w, w + NW, ...  Four warps shorten the
+// per-frame dependency chain (used where shared memory limits an SM to a few utterances); two warps issue ~35 % fewer
+// instructions per frame (used where many utterances share an SM and the issue slots are the limit).
 
 struct BandParams {
   const int64_t *st_off, *arc_off, *lp_off;
   const int32_t *b_start, *b_maxback, *a_tid, *a_olabel, *lp2pdf;
-  const uint32_t *b_stw, *b_apk;
-  const float *b_aw, *b_fin;
+  const uint32_t *b_stw;
+  const uint2 *b_arc;
+  const float *b_fin;
   const uint16_t *b_arcid, *b_orig;
   int utt0;
   const int32_t *order;
   const float *llT;
   int64_t ld;
   const int64_t *col_off, *frame_off, *word_off, *ll_off, *ld_u, *bp_off;
-  uint8_t *bp;
+  uint8_t *bp;   // per utterance: [T][RS] uint16 {in-arc choice, source-delta code}, then [T] uint16 first group of each row
   int32_t *ali, *num_words, *words, *status, *fallback;   // fallback[0] = count, fallback[1..] = chunk-local utterance ids
   float *per_frame, *total_like;
   float acwt, beam, retry_beam, beam_delta;
@@ -78,14 +80,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // are compact per-warp segments (written while pruning the previous frame); every lane ranks its own value against all
 // others with independent broadcast reads (no dependent exchange network), and the lane whose rank is `want` holds the
 // answer.  More than 64 survivors: bitwise radix select.
-struct LiveList { const float *seg; int n[NW]; };     // seg[w * SEG + j], j < n[w]
-__device__ __forceinline__ float live_at(const LiveList &L, int i) {
+template <int NW> struct LiveList { const float *seg; int n[NW]; };     // seg[w * SEG + j], j < n[w]; SEG = RS / NW
+template <int NW> __device__ __forceinline__ float live_at(const LiveList<NW> &L, int i) {
+  constexpr int SEG = RS / NW;
   int w = 0;
 #pragma unroll
   for (int k = 0; k < NW - 1; k++) { if (i >= L.n[k] && w == k) { i -= L.n[k]; w = k + 1; } }
   return L.seg[w * SEG + i];
 }
-__device__ __forceinline__ float select_rank(const LiveList &L, int n, int want, int lane) {
+template <int NW> __device__ __forceinline__ float select_rank(const LiveList<NW> &L, int n, int want, int lane) {
+  constexpr int SEG = RS / NW;
   if (n <= 32 && n - want <= 12) {
     // the usual case: a few more survivors than min_active.  The (n - want)-th largest value is the answer: peel maxima off with
     // one REDUX each (costs are >= +0, so their bit patterns order like the values; a peeled or empty lane holds 0)
@@ -139,37 +143,45 @@ __device__ __forceinline__ float select_rank(const LiveList &L, int n, int want,
 // pull for one band state in two halves, so that the shared-memory reads are in flight while the cutoff is being ranked:
 // gather the first four in-arcs' (source cost, candidate cost) -- in-degrees are 2..5 in training graphs -- then reduce them
 // under the cutoff; a loop takes any further arcs.
-struct Pull { uint32_t st; float c[4], x[4]; };
-__device__ __forceinline__ void pull_gather(Pull &q, const uint32_t st, const uint2 *__restrict__ arcs, const float *__restrict__ cur,
+struct Pull { uint32_t st; uint32_t s[4]; float c[4], x[4]; };
+template <class LdArc>
+__device__ __forceinline__ void pull_gather(Pull &q, const uint32_t st, LdArc ld_arc, const float *__restrict__ cur,
                                             const float *__restrict__ acf, const float nacwt) {
   q.st = st;
   const int a = st & 0xFFFF, cnt = (st >> 16) & 0xFF;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    q.c[j] = INFINITY; q.x[j] = INFINITY;
+    q.c[j] = INFINITY; q.x[j] = INFINITY; q.s[j] = 0;
     if (j < cnt) {
-      const uint2 ar = arcs[a + j];
+      const uint2 ar = ld_arc(a + j);
+      q.s[j] = ar.x;
       q.c[j] = cur[ar.x & MASK];
       q.x[j] = __fadd_rn(__fadd_rn(q.c[j], __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
     }
   }
 }
-__device__ __forceinline__ void pull_reduce(const Pull &q, const uint2 *__restrict__ arcs, const float *__restrict__ cur, const float *__restrict__ acf,
+template <class LdArc>
+__device__ __forceinline__ void pull_reduce(const Pull &q, LdArc ld_arc, const float *__restrict__ cur, const float *__restrict__ acf,
                                             const float cutoff, const float nacwt, float &v, uint32_t &arg) {
   v = INFINITY; arg = 0xFFu;
 #pragma unroll
-  for (int j = 0; j < 4; j++) if (q.c[j] < cutoff && q.x[j] < v) { v = q.x[j]; arg = (uint32_t)j; }
+  for (int j = 0; j < 4; j++) if (q.c[j] < cutoff && q.x[j] < v) { v = q.x[j]; arg = (uint32_t)j | ((q.s[j] & 0xFFFFu) << 8); }   // choice | source state << 8
   const int a = q.st & 0xFFFF, cnt = (q.st >> 16) & 0xFF;
   for (int j = 4; j < cnt; j++) {
-    const uint2 ar = arcs[a + j];
+    const uint2 ar = ld_arc(a + j);
     const float c = cur[ar.x & MASK];
     const float x = __fadd_rn(__fadd_rn(c, __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
-    if (c < cutoff && x < v) { v = x; arg = (uint32_t)j; }
+    if (c < cutoff && x < v) { v = x; arg = (uint32_t)j | ((ar.x & 0xFFFFu) << 8); }
   }
 }
 
-__global__ void __launch_bounds__(NT, 4)
+template <int NW, bool GS>
+#ifndef MFA_BAND_MINB2
+#define MFA_BAND_MINB2 8
+#endif
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : MFA_BAND_MINB2)
 viterbi_band_kernel(BandParams p) {
+  constexpr int NT = NW * 32, GPW = GMAX / NW, SEG = GPW * 32;
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ uint32_t s_min[NW];                   // per-warp best new cost (ordered key) of the current frame
   __shared__ __align__(16) int s_stat[NW][4];      // per-warp {lowest live state, highest live state, highest reachable state, n_tot | n_beam << 16}
@@ -184,23 +196,34 @@ viterbi_band_kernel(BandParams p) {
   if (T == 0) { if (tid == 0) { p.status[ul] = MFA_ALIGN_ZERO_FRAMES; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; } return; }
   const int start = p.b_start[ug], maxback = p.b_maxback[ug];
 
-  uint32_t *stw = (uint32_t *)smraw;                            // [S+]  first in-arc | in-degree << 16 | forward reach << 24
+  // GS: the utterance's graph is copied to shared memory; !GS: it stays in global memory and the (small, slowly sliding) window
+  // of it that a frame touches is read through L1 -- the CTA then needs only the cost rings and the acoustic stages.
   const int Spad = (S + 32) & ~1;                               // states beyond S read as 0 (no in-arcs) up to the next group
-  uint2 *arcs = (uint2 *)(stw + Spad);                          // [A]  {source state | local pdf << 16, weight bits}
-  float *ring = (float *)smraw + ((Spad + 2 * A + 3) & ~3);     // [2][WRING], 16-byte aligned
-  float *ac = ring + 2 * WRING;                                 // [NST][P][4] raw log-likelihoods; later the back-trace staging area
-  {
-    const uint32_t *gs = p.b_stw + p.st_off[ug], *ga = p.b_apk + p.arc_off[ug];
-    const float *gw = p.b_aw + p.arc_off[ug];
-    for (int i = tid; i < Spad; i += NT) stw[i] = i < S ? gs[i] : 0u;
-    for (int i = tid; i < A; i += NT) arcs[i] = make_uint2(ga[i], __float_as_uint(gw[i]));
+  const uint32_t *stw;                                          // [S+]  first in-arc | in-degree << 16 | forward reach << 24
+  const uint2 *arcs;                                            // [A]  {source state | local pdf << 16, weight bits}
+  float *ring;                                                  // [2][WRING], 16-byte aligned
+  if (GS) {
+    uint32_t *sw = (uint32_t *)smraw;
+    uint2 *sa = (uint2 *)(sw + Spad);
+    ring = (float *)smraw + ((Spad + 2 * A + 3) & ~3);
+    const uint32_t *gs = p.b_stw + p.st_off[ug];
+    const uint2 *ga = p.b_arc + p.arc_off[ug];
+    for (int i = tid; i < Spad; i += NT) sw[i] = i < S ? gs[i] : 0u;
+    for (int i = tid; i < A; i += NT) sa[i] = ga[i];
+    stw = sw; arcs = sa;
+  } else {
+    stw = p.b_stw + p.st_off[ug]; arcs = p.b_arc + p.arc_off[ug];
+    ring = (float *)smraw;
   }
+  float *ac = ring + 2 * WRING;                                 // [NST][P][4] raw log-likelihoods; later the back-trace staging area
+  auto ld_st = [&](int d) -> uint32_t { return GS ? stw[d] : (d < S ? __ldg(stw + d) : 0u); };
+  auto ld_arc = [&](int a) -> uint2 { return GS ? arcs[a] : __ldg(arcs + a); };
   const bool rag = p.ll_off != nullptr;
   const float *ll = p.llT + (rag ? p.ll_off[ul] : p.col_off[ul]);
   const int64_t ldu = rag ? p.ld_u[ul] : p.ld;
   const int32_t *lp2pdf = p.lp2pdf + p.lp_off[ug];
   uint8_t *bp = p.bp + p.bp_off[ul];                        // [T][RS] choice bytes
-  uint16_t *bpg = (uint16_t *)(bp + (size_t)T * RS);        // [T] first group of each row
+  uint16_t *bpg = (uint16_t *)(bp + (size_t)T * ROWB);      // [T] first group of each row
   const float inf = INFINITY, nacwt = -p.acwt;
   const int NB = (int)((T + 3) >> 2);
   const int max_groups = min(p.max_groups, GMAX);
@@ -230,9 +253,9 @@ viterbi_band_kernel(BandParams p) {
     __syncthreads();
     if (tid == 0) { cur[start & MASK] = 0.0f; s_live[0] = 0.0f; }
     lo = hi = start;
-    int hib = start + (int)(stw[start] >> 24);
+    int hib = start + (int)(ld_st(start) >> 24);
     int n_tot = 1, n_beam = 1;
-    LiveList L;
+    LiveList<NW> L;
     L.seg = s_live; L.n[0] = 1;
 #pragma unroll
     for (int w = 1; w < NW; w++) L.n[w] = 0;
@@ -243,32 +266,33 @@ viterbi_band_kernel(BandParams p) {
     __syncthreads();
     int stage = 0;                                            // stage holding the current 4-frame block
     bool dead = false;
-    for (int64_t t = 0; t < T; t++) {
+    for (int t = 0; t < (int)T; t++) {
       const float *acf = ac + (size_t)stage * 4 * P + (int)(t & 3);
       const int glo = max(lo - maxback, 0) >> 5;
       const int ng = min(hib >> 5, gend) - glo + 1;
       if (ng > max_groups) { overflow = true; break; }
       // ---- pull, first half: warp w owns groups w and w + NW of the window; the gather does not need the cutoff
       Pull q;
-      pull_gather(q, warp < ng ? stw[(glo + warp) * 32 + lane] : 0u, arcs, cur, acf, nacwt);
+      pull_gather(q, warp < ng ? ld_st((glo + warp) * 32 + lane) : 0u, ld_arc, cur, acf, nacwt);
       // ---- GetCutoff on the live tokens (normalised: best == 0); every warp computes the same values
+      // (a warp without a group this frame needs neither value)
       if (n_tot <= p.min_active) { cutoff = inf; adaptive = inf; }
       else if (n_beam > p.min_active) { cutoff = beam; adaptive = beam; }
-      else { cutoff = select_rank(L, n_tot, p.min_active, lane); adaptive = cutoff + p.beam_delta; }
+      else if (warp < ng) { cutoff = select_rank(L, n_tot, p.min_active, lane); adaptive = cutoff + p.beam_delta; }
       // ---- pull, second half
       float nv[GPW];
       uint32_t na[GPW];
-      pull_reduce(q, arcs, cur, acf, cutoff, nacwt, nv[0], na[0]);
-      na[0] |= q.st >> 24 << 8;
+      pull_reduce(q, ld_arc, cur, acf, cutoff, nacwt, nv[0], na[0]);
+      na[0] |= q.st & 0xFF000000u;                     // forward reach in the top byte
       uint32_t kmin = f2key(nv[0]);
 #pragma unroll
       for (int k = 1; k < GPW; k++) {
         nv[k] = inf; na[k] = 0xFFu;
         if (warp + k * NW < ng) {
           Pull q2;
-          pull_gather(q2, stw[(glo + warp + k * NW) * 32 + lane], arcs, cur, acf, nacwt);
-          pull_reduce(q2, arcs, cur, acf, cutoff, nacwt, nv[k], na[k]);
-          na[k] |= q2.st >> 24 << 8;
+          pull_gather(q2, ld_st((glo + warp + k * NW) * 32 + lane), ld_arc, cur, acf, nacwt);
+          pull_reduce(q2, ld_arc, cur, acf, cutoff, nacwt, nv[k], na[k]);
+          na[k] |= q2.st & 0xFF000000u;
           kmin = min(kmin, f2key(nv[k]));
         }
       }
@@ -285,7 +309,7 @@ viterbi_band_kernel(BandParams p) {
       if (!(best_new < inf)) { dead = true; break; }
       const float next_cutoff = best_new + adaptive;   // inf stays inf
       // ---- prune, renormalise, back-pointers, this warp's survivor list and window bounds
-      uint8_t *bprow = bp + (size_t)t * RS;
+      uint16_t *bprow = (uint16_t *)(bp + (size_t)t * ROWB);
       int nt = 0, nb = 0, myhib = -1, flo = 0x7fffffff, fhi = -1;
 #pragma unroll
       for (int k = 0; k < GPW; k++) {
@@ -297,9 +321,9 @@ viterbi_band_kernel(BandParams p) {
           v = keep ? v - best_new : inf;
           nxt[d & MASK] = v;
           cur[d & MASK] = inf;
-          __stcs(bprow + i * 32 + lane, (uint8_t)(keep ? (na[k] & 0xFFu) : 0xFFu));
+          __stcs(bprow + i * 32 + lane, (uint16_t)(keep ? ((na[k] & 0xFFu) | ((uint32_t)(d - (int)((na[k] >> 8) & 0xFFFF) + BIAS) << 8)) : 0xFFu));
           const unsigned km = __ballot_sync(FULL, keep);
-          if (keep) { s_live[warp * SEG + nt + __popc(km & ((1u << lane) - 1u))] = v; myhib = max(myhib, d + (int)(na[k] >> 8)); }
+          if (keep) { s_live[warp * SEG + nt + __popc(km & ((1u << lane) - 1u))] = v; myhib = max(myhib, d + (int)(na[k] >> 24)); }
           nt += __popc(km);
           nb += __popc(__ballot_sync(FULL, keep && v <= beam));
           if (km) { flo = min(flo, (glo + i) * 32 + __ffs(km) - 1); fhi = (glo + i) * 32 + 31 - __clz(km); }
@@ -309,7 +333,7 @@ viterbi_band_kernel(BandParams p) {
       if (lane == 0) *(int4 *)s_stat[warp] = make_int4(flo, fhi, myhib, nt | (nb << 16));
       if (tid == 0) bpg[t] = (uint16_t)glo;
       if ((t & 3) == 3) {                              // the block just finished frees its stage for block b + 2; nobody reads `ac` between A and B
-        issue_block((int)(t >> 2) + NST, stage);
+        issue_block((t >> 2) + NST, stage);
         stage = stage == NST - 1 ? 0 : stage + 1;
         cp_async_wait<NST - 1>();                      // everything but the block just issued has landed: the next block is complete
       }
@@ -368,62 +392,80 @@ viterbi_band_kernel(BandParams p) {
     if (lane == 0) { p.status[ul] = result; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; }
     return;
   }
-  // ---- back-trace: 32 frames at a time.  The rows are staged in shared memory by the warp, lane 0 follows the chain
-  // (three dependent shared-memory reads per frame), then the lanes emit one frame each.
-  uint8_t *stg = (uint8_t *)ac;                                    // [BT_ROWS][RS]
-  uint16_t *g0s = (uint16_t *)(stg + BT_ROWS * RS);                // [BT_ROWS]
-  uint16_t *jarr = g0s + BT_ROWS;                                  // [BT_ROWS]
+  // ---- back-trace (warp 0).  Pass 1, BT_ROWS frames at a time: a batch's rows (and their first groups) are copied to shared
+  // memory with cp.async one batch ahead of use and lane 0 follows the chain using only the staged rows (state -= source
+  // delta), parking (state, in-arc choice) of every frame in the `ali` output array.  Pass 2: the lanes resolve 4 x 32 frames
+  // at a time -- graph, transition-id, word label and log-likelihood look-ups of different frames are independent, so their
+  // latencies overlap -- and emit the outputs in frame order.
+  uint8_t *stg = (uint8_t *)ac;                                    // [2][BT_ROWS][ROWB]
+  uint16_t *g0s = (uint16_t *)(stg + 2 * BT_ROWS * ROWB);          // [2][BT_ROWS] (16-byte aligned)
   const int32_t *a_tid = p.a_tid + p.arc_off[ug], *a_ol = p.a_olabel + p.arc_off[ug];
   const uint16_t *arcid = p.b_arcid + p.arc_off[ug];
   int32_t *ali = p.ali + p.frame_off[ul];
   float *pf = p.per_frame + p.frame_off[ul];
   int32_t *words = p.words + p.word_off[ul];
   const int wcap = (int)(p.word_off[ul + 1] - p.word_off[ul]);
-  int nw = 0, s = hi, bad = 0;
-  for (int64_t tb = T; tb > 0; tb -= BT_ROWS) {
-    const int64_t r0 = tb > BT_ROWS ? tb - BT_ROWS : 0;
-    const int n = (int)(tb - r0);
-    const uint4 *src = (const uint4 *)(bp + (size_t)r0 * RS);
-    for (int i = lane; i < n * (RS / 16); i += 32) ((uint4 *)stg)[i] = __ldcs(src + i);
-    if (lane < n) g0s[lane] = bpg[r0 + lane];
+  auto stage_batch = [&](int b, int buf) {                         // frames [b * BT_ROWS, ...): whole rows, BT_ROWS * ROWB contiguous bytes
+    if (b >= 0) {
+      const uint8_t *src = bp + (size_t)b * BT_ROWS * ROWB;
+      uint8_t *dst = stg + buf * BT_ROWS * ROWB;
+      for (int i = lane; i < BT_ROWS * ROWB / 16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+      if (lane == 0) cp_async16(g0s + buf * BT_ROWS, bpg + (size_t)b * BT_ROWS);
+    }
+    cp_async_commit();
+  };
+  int s = hi, bad = 0;
+  const int nbat = (int)((T + BT_ROWS - 1) / BT_ROWS);
+  stage_batch(nbat - 1, (nbat - 1) & 1);
+  for (int b = nbat - 1; b >= 0; b--) {
+    const int buf = b & 1, r0 = b * BT_ROWS, n = min(BT_ROWS, (int)T - r0);
+    stage_batch(b - 1, buf ^ 1);
+    cp_async_wait<1>();
     __syncwarp();
     if (lane == 0) {
+      const uint16_t *rows = (const uint16_t *)(stg + buf * BT_ROWS * ROWB);
       for (int k = n - 1; k >= 0; k--) {
-        const int slot = s - 32 * (int)g0s[k];
-        const unsigned ch = (slot >= 0 && slot < RS) ? stg[k * RS + slot] : 0xFFu;
-        if (ch == 0xFFu) { bad = 1; break; }    // cannot happen
-        const int j = (int)(stw[s] & 0xFFFF) + (int)ch;
-        jarr[k] = (uint16_t)j;
-        s = (int)(arcs[j].x & 0xFFFF);
+        const int slot = s - 32 * (int)g0s[buf * BT_ROWS + k];
+        const unsigned w = (slot >= 0 && slot < RS) ? rows[k * RS + slot] : 0xFFu;
+        if ((w & 0xFFu) == 0xFFu) { bad = 1; break; }    // cannot happen
+        ali[r0 + k] = s | (int)((w & 0xFFu) << 16);
+        s -= (int)(w >> 8) - BIAS;
       }
     }
     bad = __shfl_sync(FULL, bad, 0);
     if (bad) break;
-    s = __shfl_sync(FULL, s, 0);
-    __syncwarp();
-    int ol = 0;
-    if (lane < n) {
-      const int j = jarr[lane];
-      const int arc = arcid[j];
-      const int64_t t = r0 + lane;
-      const int lp = (int)(arcs[j].x >> 16);
-      ali[t] = a_tid[arc];
-      pf[t] = ll[(size_t)(rag ? lp : lp2pdf[lp]) * ldu + t];
-      ol = a_ol[arc];
-    }
-    // words are collected in walk order (descending frame); reversed at the end
-    const unsigned m = __ballot_sync(FULL, ol != 0);
-    if (ol != 0) {
-      const int idx = nw + __popc(m & ~((2u << lane) - 1u));
-      if (idx < wcap) words[idx] = ol;
-    }
-    nw += __popc(m);
     __syncwarp();
   }
+  cp_async_wait<0>();
   if (bad) { if (lane == 0) { p.status[ul] = MFA_ALIGN_NO_FINAL; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; } return; }
-  __syncwarp();
-  const int nwc = nw < wcap ? nw : wcap;
-  for (int i = lane; i < nwc / 2; i += 32) { const int32_t x = words[i]; words[i] = words[nwc - 1 - i]; words[nwc - 1 - i] = x; }
+  __syncwarp();                    // lane 0's parked codes are visible to the warp (same CTA, global memory)
+  int nw = 0;
+  for (int t0 = 0; t0 < (int)T; t0 += 128) {
+    int code[4], tid_[4], ol[4];
+    float lk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int t = t0 + 32 * u + lane; code[u] = t < (int)T ? __ldcg(ali + t) : -1; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      tid_[u] = 0; ol[u] = 0; lk[u] = 0.0f;
+      if (code[u] >= 0) {
+        const int t = t0 + 32 * u + lane;
+        const int j = (int)(ld_st(code[u] & 0xFFFF) & 0xFFFF) + (code[u] >> 16);
+        const int arc = arcid[j];
+        const int lp = (int)(ld_arc(j).x >> 16);
+        tid_[u] = a_tid[arc]; ol[u] = a_ol[arc];
+        lk[u] = ll[(size_t)(rag ? lp : lp2pdf[lp]) * ldu + t];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = t0 + 32 * u + lane;
+      if (code[u] >= 0) { ali[t] = tid_[u]; pf[t] = lk[u]; }
+      const unsigned m = __ballot_sync(FULL, ol[u] != 0);
+      if (ol[u] != 0) { const int idx = nw + __popc(m & ((1u << lane) - 1u)); if (idx < wcap) words[idx] = ol[u]; }
+      nw += __popc(m);
+    }
+  }
   if (lane == 0) { p.status[ul] = result; p.num_words[ul] = nw; }
 }
 
@@ -431,8 +473,11 @@ viterbi_band_kernel(BandParams p) {
 
 namespace mfa {
 
-size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P) {
-  return (size_t)(((((S + 32) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, BT_ROWS * RS + 4 * BT_ROWS) + 16);
+bool viterbi_band_graph_in_smem() { const char *v = getenv("MFA_VIT_GRAPH_SMEM"); return v ? atoi(v) != 0 : false; }
+
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem) {
+  const int64_t graph = graph_in_smem ? ((((S + 32) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 : 0;
+  return (size_t)(graph + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, 2 * BT_ROWS * ROWB + 4 * BT_ROWS) + 16);
 }
 
 // Launches the band kernel for the utterances in `subset` (chunk-local ids, all band_ok).  d_fallback: [1 + n_utts] ints, count
@@ -443,6 +488,7 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   CUDA_TRY(cudaMemsetAsync(d_fallback, 0, sizeof(int32_t), e->stream));
   if (ns == 0) return MFA_OK;
   const size_t limit = e->smem_optin - 4096;   // the kernel also has ~2 KB of static shared memory
+  const bool graph_smem = viterbi_band_graph_in_smem();
   std::vector<int64_t> bp_off(n + 1, 0);
   std::vector<size_t> need(n, 0);
   std::vector<int64_t> work(n, 0);
@@ -452,13 +498,13 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
     const int64_t T = a.h_frame_off[ul + 1] - a.h_frame_off[ul];
     bp_off[ul] = bp_total;
-    bp_total += (T * RS + T * 2 + 15) / 16 * 16;
-    need[ul] = viterbi_band_smem(S, A, P);
+    bp_total += (T * ROWB + T * 2 + 15) / 16 * 16;
+    need[ul] = viterbi_band_smem(S, A, P, graph_smem);
     work[ul] = T;
     if (need[ul] > limit) return set_error(MFA_ERR_UNSUPPORTED, "internal: band utterance exceeds shared memory");
   }
   uint8_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
-  MFA_TRY(e->getT<uint8_t>(DB_BBP, (size_t)bp_total + 16, &d_bp));
+  MFA_TRY(e->getT<uint8_t>(DB_BBP, (size_t)bp_total + BT_ROWS * ROWB + 64, &d_bp));   // the back-trace stages whole batches of rows
   MFA_TRY(e->upload(DB_BBP_OFF, bp_off.data(), bp_off.size(), &d_bp_off));
   constexpr int NC = mfa_engine::kSide;
   size_t bounds[NC];
@@ -472,15 +518,26 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   BandParams p;
   p.st_off = g->d_st_off; p.arc_off = g->d_arc_off; p.lp_off = g->d_lp_off;
   p.b_start = g->d_b_start; p.b_maxback = g->d_b_maxback; p.a_tid = g->d_a_tid; p.a_olabel = g->d_a_olabel; p.lp2pdf = g->d_lp2pdf;
-  p.b_stw = g->d_b_stw; p.b_apk = g->d_b_apk; p.b_aw = g->d_b_aw; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
+  p.b_stw = g->d_b_stw; p.b_arc = (const uint2 *)g->d_b_arc; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
   p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
   p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u; p.bp_off = d_bp_off; p.bp = d_bp;
   p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fallback;
   p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
   p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GMAX));
-  CUDA_TRY(cudaFuncSetAttribute(viterbi_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-  CUDA_TRY(cudaFuncSetAttribute(viterbi_band_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  // shared-memory share of the unified L1 (percent).  Graph through L1, 10 h workload: 25 -> 16.8 ms, 50 -> 9.4, 65 -> 7.6, 75 -> 7.6,
+  // 88 -> 8.8, 100 -> 10.5: enough shared memory for ~9 resident utterances per SM, the rest as L1 for their graph windows
+  const int carve = getenv("MFA_VIT_CARVEOUT_BAND") ? atoi(getenv("MFA_VIT_CARVEOUT_BAND")) : (graph_smem ? 100 : 70);
+  for (auto fn : {(const void *)viterbi_band_kernel<4, true>, (const void *)viterbi_band_kernel<2, true>, (const void *)viterbi_band_kernel<4, false>,
+                  (const void *)viterbi_band_kernel<2, false>}) {
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
+  // two-warp CTAs where many utterances share an SM: always when the graph is read through L1 (a CTA then needs ~15 KB), and
+  // for the classes under 44 KB when it is copied to shared memory (MFA_VIT_NW2_KB overrides the threshold).  Measured on the
+  // 10 h config-2 workload, graph through L1: 2 warps 7.6 ms, 4 warps 10.0 ms; graph in shared memory: 11.7 ms.
+  const char *env_nw = getenv("MFA_VIT_NW2_KB");
+  const size_t nw2_below = (size_t)(env_nw ? atoi(env_nw) : (graph_smem ? 44 : 256)) * 1024;
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
   for (int c = NC - 1; c >= 0; c--) {
     int pos = 0, cnt = 0;
@@ -491,7 +548,9 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     p.order = d_order + pos;
     cudaStream_t st = e->side[c];
     CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fork, 0));
-    viterbi_band_kernel<<<cnt, NT, (mx + 15) / 16 * 16, st>>>(p);
+    const size_t sm = (mx + 15) / 16 * 16;
+    if (graph_smem) { if (mx <= nw2_below) viterbi_band_kernel<2, true><<<cnt, 64, sm, st>>>(p); else viterbi_band_kernel<4, true><<<cnt, 128, sm, st>>>(p); }
+    else { if (mx <= nw2_below) viterbi_band_kernel<2, false><<<cnt, 64, sm, st>>>(p); else viterbi_band_kernel<4, false><<<cnt, 128, sm, st>>>(p); }
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(e->ev_join[c], st));

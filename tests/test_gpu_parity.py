@@ -159,7 +159,7 @@ def test_viterbi_parity_with_oracle(eng, triphone, beam, retry):
 
 
 def _align_env(eng, sc, batch, beam, retry, monkeypatch, **env):
-    for k in ("MFA_VIT_BAND", "MFA_VIT_MAXGROUPS"):
+    for k in ("MFA_VIT_BAND", "MFA_VIT_MAXGROUPS", "MFA_VIT_GRAPH_SMEM", "MFA_VIT_NW2_KB"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, str(v))
@@ -182,7 +182,9 @@ def test_band_kernel_equals_sparse_kernel(eng, monkeypatch, triphone, beam, retr
     if beam <= 10.0:
         assert f1 == f0                                   # ... and the default band is wide enough for ordinary beams
     assert np.isin(sparse.status, (0, 1)).sum() > 0
-    for other in (band, narrow):
+    smem4 = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_GRAPH_SMEM=1, MFA_VIT_NW2_KB=0)   # graph in shared memory, 4 warps
+    l1w4 = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_NW2_KB=0)                           # graph through L1, 4 warps
+    for other in (band, narrow, smem4, l1w4):
         assert np.array_equal(other.status, sparse.status) and np.array_equal(other.num_words, sparse.num_words)
         assert np.array_equal(other.ali, sparse.ali) and np.array_equal(other.words, sparse.words)
         assert np.array_equal(other.total_like, sparse.total_like) and np.array_equal(other.per_frame, sparse.per_frame)
