@@ -58,7 +58,7 @@ struct mfa_engine {
   // cached MFCC tables (device blob in DB_MFCC_TAB) for the last option set
   bool mfcc_tab_valid = false;
   mfa_mfcc_opts mfcc_tab_opts{};
-  alignas(8) unsigned char mfcc_tab_desc[96] = {};
+  alignas(8) unsigned char mfcc_tab_desc[128] = {};
   struct Buf { void *p = nullptr; size_t cap = 0; };
   Buf dev[DB_N];
   Buf pin[PB_N];

@@ -6,11 +6,18 @@
 // Algorithm per SURVEY.md A.2 (Kaldi feat/feature-window.cc, mel-computations.cc, feature-mfcc.cc).
 //
 // Mapping: one warp per frame; each warp walks a contiguous range of frames so the utterance lookup is
-// amortised and neighbouring frames re-read their 60 % overlapping samples from L1/L2.  The 512-point real
-// FFT is a 256-point complex Stockham radix-2 FFT in the warp's private shared-memory ping-pong buffers.
+// amortised and neighbouring frames re-read their 60 % overlapping samples from L1/L2.
+//   * mfcc512_kernel (the path MFA's defaults take: 25 ms at 16 kHz -> 512-point real FFT, <= 32 mel bins, <= 16 cepstra):
+//     the 256-point complex FFT runs in REGISTERS, 8 points per lane: radix-8 over the in-lane index, twiddle, padded
+//     shared-memory transpose, radix-8, twiddle, transpose, radix-4 (256 = 8 x 8 x 4); the real-FFT untangling works on
+//     (k, 256-k) pairs and goes straight to the power spectrum; mel taps are split into <= 32 balanced chunks, one per lane;
+//     the DCT is split over two half-warps.  ~600 warp instructions per frame instead of ~2 700.
+//   * mfcc_kernel (any other geometry): 256-point complex Stockham radix-2 FFT in the warp's shared-memory ping-pong buffers.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "cuda_internal.cuh"
 
@@ -21,6 +28,9 @@ namespace {
 struct MfccTables {  // offsets (in floats) into one device blob
   int N, NP, NB, shift, nbins, nceps, log2nb;
   int off_window, off_tw, off_ptw, off_melw, off_melfirst, off_mellen, off_meloff, off_dct, off_lift, total;
+  // fast path (mfcc512_kernel): per-lane mel chunks {first power bin, weight offset (floats, from the blob start), taps, mel bin},
+  // per-bin {first chunk, number of chunks}; fast = 0 when the geometry does not fit
+  int fast, off_chunk, off_binchunk, chunk_max;
 };
 
 static int round_up_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
@@ -65,7 +75,29 @@ static int build_tables(const mfa_mfcc_opts *o, MfccTables &t, std::vector<float
     for (int i = first[b]; i <= last; i++) melw.push_back(w[i]);
   }
   t.total = t.off_melw + (int)melw.size();
+  // fast-path tables: split every bin's taps into chunks of at most C taps, C minimal such that <= 32 chunks result
+  t.fast = 0; t.chunk_max = 0;
+  t.off_chunk = (t.total + 3) / 4 * 4; t.off_binchunk = t.off_chunk + 4 * 32; t.total = t.off_binchunk + 2 * 32;
+  std::vector<int> chunk(4 * 32, 0), binchunk(2 * 32, 0);
+  if (t.NP == 512 && t.nbins <= 32 && t.nceps <= 16 && t.N >= 64 && t.N <= 512) {
+    int C = 1;
+    for (;; C++) { int n = 0; for (int b = 0; b < t.nbins; b++) n += (len[b] + C - 1) / C; if (n <= 32) break; }
+    int lane = 0;
+    for (int b = 0; b < t.nbins; b++) {
+      int nc = (len[b] + C - 1) / C, per = (len[b] + nc - 1) / nc;   // even split inside the bin
+      binchunk[2 * b] = lane; binchunk[2 * b + 1] = nc;
+      for (int c = 0, done = 0; c < nc; c++, lane++) {
+        int cnt = std::min(per, len[b] - done);
+        chunk[4 * lane] = first[b] + done; chunk[4 * lane + 1] = t.off_melw + woff[b] + done; chunk[4 * lane + 2] = cnt; chunk[4 * lane + 3] = b;
+        t.chunk_max = std::max(t.chunk_max, cnt);
+        done += cnt;
+      }
+    }
+    t.fast = 1;
+  }
   blob.assign(t.total, 0.0f);
+  memcpy(&blob[t.off_chunk], chunk.data(), chunk.size() * 4);
+  memcpy(&blob[t.off_binchunk], binchunk.data(), binchunk.size() * 4);
   for (int i = 0; i < t.N; i++) blob[t.off_window + i] = (float)pow(0.5 - 0.5 * cos(2.0 * M_PI / (t.N - 1) * (double)i), 0.85);
   for (int k = 0; k < t.NB; k++) {
     blob[t.off_tw + 2 * k] = (float)cos(2.0 * M_PI * k / t.NB); blob[t.off_tw + 2 * k + 1] = (float)(-sin(2.0 * M_PI * k / t.NB));
@@ -204,6 +236,258 @@ mfcc_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fast path (512-point frames)
+// in-place 8-point forward DFT (W = exp(-2 pi i / 8)), natural order in and out
+__device__ __forceinline__ void dft4(float c0r, float c0i, float c1r, float c1i, float c2r, float c2i, float c3r, float c3i,
+                                     float &y0r, float &y0i, float &y1r, float &y1i, float &y2r, float &y2i, float &y3r, float &y3i) {
+  const float e0r = c0r + c2r, e0i = c0i + c2i, e1r = c0r - c2r, e1i = c0i - c2i;
+  const float o0r = c1r + c3r, o0i = c1i + c3i, o1r = c1i - c3i, o1i = c3r - c1r;   // (c1 - c3) * (-i)
+  y0r = e0r + o0r; y0i = e0i + o0i; y2r = e0r - o0r; y2i = e0i - o0i;
+  y1r = e1r + o1r; y1i = e1i + o1i; y3r = e1r - o1r; y3i = e1i - o1i;
+}
+__device__ __forceinline__ void dft8(float (&xr)[8], float (&xi)[8]) {
+  const float h = 0.70710678118654752f;
+  float ar[4], ai[4], br[4], bi[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { ar[i] = xr[i] + xr[i + 4]; ai[i] = xi[i] + xi[i + 4]; br[i] = xr[i] - xr[i + 4]; bi[i] = xi[i] - xi[i + 4]; }
+  float t;
+  t = br[1]; br[1] = (t + bi[1]) * h; bi[1] = (bi[1] - t) * h;          // * (1 - i) / sqrt 2
+  t = br[2]; br[2] = bi[2]; bi[2] = -t;                                  // * -i
+  t = br[3]; br[3] = (bi[3] - t) * h; bi[3] = -(bi[3] + t) * h;         // * (-1 - i) / sqrt 2
+  dft4(ar[0], ai[0], ar[1], ai[1], ar[2], ai[2], ar[3], ai[3], xr[0], xi[0], xr[2], xi[2], xr[4], xi[4], xr[6], xi[6]);
+  dft4(br[0], bi[0], br[1], bi[1], br[2], bi[2], br[3], bi[3], xr[1], xi[1], xr[3], xi[3], xr[5], xi[5], xr[7], xi[7]);
+}
+
+constexpr int kFW = 4;                 // warps per CTA
+constexpr int kT1 = 34;                // row stride (float2) of the first transpose [k1][m2]: 2 wavefronts per 64-bit access
+constexpr int kT2 = 9;                 // row stride (float2) of the second transpose [lane][s]
+constexpr int kTB = 32 * kT2;          // float2 entries of the transpose / spectrum buffer: max(8 * kT1, 32 * kT2, 256 + 16)
+static_assert(kTB >= 8 * kT1 && kTB >= 256 + 16, "transpose buffer too small");
+constexpr int kWarpFloats = 2 * kTB + 260 + 32 + 32;   // transpose / spectrum buffer, power spectrum, chunk sums, log-mel
+
+__global__ void __launch_bounds__(kFW * 32, 6)
+mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restrict__ pcm, const int64_t *__restrict__ sample_off,
+               const int64_t *__restrict__ frame_off, int n_utts, int64_t frame_base, int64_t n_frames, int64_t frames_per_warp, float *__restrict__ out,
+               float preemph, int snip_edges, int remove_dc, int use_energy, int raw_energy, float log_energy_floor) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA-wide tables, laid out so that lane-indexed reads are conflict-free
+  float2 *s_win = (float2 *)smem;                        // [8][32]  window[64 m1 + 2 lane + {0,1}]
+  float2 *s_tw1 = s_win + 8 * 32;                        // [8][32]  W_256^(lane k1)
+  float2 *s_tw2 = s_tw1 + 8 * 32;                        // [8][32]  W_32^((lane & 3) s)
+  float *s_tab = (float *)(s_tw2 + 8 * 32);              // the table blob (mel weights, dct, lifter, chunk tables)
+  float *wbase = s_tab + ((t.total + 3) & ~3) + warp * kWarpFloats;
+  float2 *tb = (float2 *)wbase;                          // kTB float2: both transposes and the spectrum Z (idx(k) = k + 4 (k >> 6))
+  float *pw = wbase + 2 * kTB;                       // [257] power spectrum
+  float *part = pw + 260;                                // [32] per-chunk mel sums
+  float *melv = part + 32;                               // [32] log mel energies
+  const float2 *g_tw = (const float2 *)(tab + t.off_tw), *g_ptw = (const float2 *)(tab + t.off_ptw);
+  for (int i = threadIdx.x; i < t.total; i += blockDim.x) s_tab[i] = tab[i];
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    const int a = i >> 5, l = i & 31, n = 64 * a + 2 * l;
+    s_win[i] = make_float2(n < t.N ? tab[t.off_window + n] : 0.0f, n + 1 < t.N ? tab[t.off_window + n + 1] : 0.0f);
+    s_tw1[i] = g_tw[l * a];
+    s_tw2[i] = g_tw[8 * (l & 3) * a];
+  }
+  __syncthreads();
+  const int4 *chunks = (const int4 *)(s_tab + t.off_chunk);
+  const int2 *binchunk = (const int2 *)(s_tab + t.off_binchunk);
+  const float *dct = s_tab + t.off_dct, *lift = s_tab + t.off_lift;
+  // W_512^k for this lane's pairs k = lane + 32 i
+  float2 ptw[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) ptw[i] = g_ptw[lane + 32 * i];
+  const int4 my_chunk = chunks[lane];
+  const int2 my_bin = lane < t.nbins ? binchunk[lane] : make_int2(0, 0);
+  const int N = t.N, nbins = t.nbins, nceps = t.nceps;
+  const int dc_c = lane & 15, dc_h = lane >> 4, dc_half = (nbins + 1) >> 1;   // DCT: coefficient dc_c, bins [dc_h * dc_half, ...)
+
+  const int64_t gw = (int64_t)blockIdx.x * kFW + warp;
+  int64_t f0 = frame_base + gw * frames_per_warp, f1 = f0 + frames_per_warp;
+  if (f1 > frame_base + n_frames) f1 = frame_base + n_frames;
+  if (f0 >= f1) return;
+  int lo = 0, hi = n_utts - 1;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (frame_off[mid] <= f0) lo = mid; else hi = mid - 1; }
+  int u = lo;
+  int64_t u_f0 = frame_off[u], u_f1 = frame_off[u + 1], u_s0 = sample_off[u], u_n = sample_off[u + 1] - u_s0;
+  for (int64_t f = f0; f < f1; f++) {
+    while (f >= u_f1) { u++; u_f0 = u_f1; u_f1 = frame_off[u + 1]; u_s0 = sample_off[u]; u_n = sample_off[u + 1] - u_s0; }
+    const int64_t fi = f - u_f0;
+    const int64_t start = snip_edges ? fi * t.shift : fi * t.shift + t.shift / 2 - N / 2;
+    // ---- samples: lane holds x[64 a + 2 lane + {0,1}], a = 0..7 (128 contiguous bytes per load across the warp)
+    float x[16];
+    const int16_t *base = pcm + u_s0 + start;
+    if (start >= 0 && start + N <= u_n) {
+      if ((((size_t)base) & 3) == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+          const int n = 64 * a + 2 * lane;
+          x[2 * a] = 0.0f; x[2 * a + 1] = 0.0f;
+          if (n + 1 < N) { const uint32_t v = __ldg((const uint32_t *)(base + n)); x[2 * a] = (float)(int16_t)(v & 0xFFFF); x[2 * a + 1] = (float)(int16_t)(v >> 16); }
+          else if (n < N) x[2 * a] = (float)__ldg(base + n);
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+          const int n = 64 * a + 2 * lane;
+          x[2 * a] = n < N ? (float)__ldg(base + n) : 0.0f;
+          x[2 * a + 1] = n + 1 < N ? (float)__ldg(base + n + 1) : 0.0f;
+        }
+      }
+    } else {   // frame overlaps an utterance edge (snip_edges = false): reflected indices
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int n = 64 * a + 2 * lane + e;
+          float v = 0.0f;
+          if (n < N) {
+            int64_t k = start + n;
+            while (k < 0 || k >= u_n) k = (k < 0) ? -k - 1 : 2 * u_n - 1 - k;
+            v = (float)pcm[u_s0 + k];
+          }
+          x[2 * a + e] = v;
+        }
+    }
+    if (remove_dc) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; i++) sum += x[i];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / (float)N;
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int n = 64 * a + 2 * lane;
+        if (n < N) x[2 * a] -= mean;
+        if (n + 1 < N) x[2 * a + 1] -= mean;
+      }
+    }
+    float energy = 0.0f;
+    if (use_energy && raw_energy) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) energy += x[i] * x[i];
+    }
+    // ---- pre-emphasis + window -> z[32 a + lane] = y[64 a + 2 lane] + i y[64 a + 2 lane + 1]
+    float zr[8], zi[8];
+    {
+      float rot[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) rot[a] = __shfl_sync(0xffffffffu, x[2 * a + 1], (lane + 31) & 31);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const float xm1 = lane == 0 ? (a > 0 ? rot[a > 0 ? a - 1 : 0] : x[0]) : rot[a];
+        const float2 w = s_win[a * 32 + lane];
+        zr[a] = (x[2 * a] - preemph * xm1) * w.x;
+        zi[a] = (x[2 * a + 1] - preemph * x[2 * a]) * w.y;
+      }
+    }
+    if (use_energy && !raw_energy) {
+#pragma unroll
+      for (int a = 0; a < 8; a++) energy += zr[a] * zr[a] + zi[a] * zi[a];
+    }
+    // ---- 256-point complex FFT, k = k1 + 8 (s + 8 t)
+    dft8(zr, zi);                                            // over a -> k1
+#pragma unroll
+    for (int k1 = 1; k1 < 8; k1++) {
+      const float2 w = s_tw1[k1 * 32 + lane];
+      const float r = zr[k1] * w.x - zi[k1] * w.y, i = zr[k1] * w.y + zi[k1] * w.x;
+      zr[k1] = r; zi[k1] = i;
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 8; k1++) tb[k1 * kT1 + lane] = make_float2(zr[k1], zi[k1]);
+    __syncwarp();
+    {
+      const int k1 = lane >> 2, j = lane & 3;                // lane (k1, j) takes m2 = 4 r + j
+#pragma unroll
+      for (int r = 0; r < 8; r++) { const float2 v = tb[k1 * kT1 + 4 * r + j]; zr[r] = v.x; zi[r] = v.y; }
+    }
+    __syncwarp();
+    dft8(zr, zi);                                            // over r -> s
+#pragma unroll
+    for (int sx = 1; sx < 8; sx++) {
+      const float2 w = s_tw2[sx * 32 + lane];
+      const float r = zr[sx] * w.x - zi[sx] * w.y, i = zr[sx] * w.y + zi[sx] * w.x;
+      zr[sx] = r; zi[sx] = i;
+    }
+#pragma unroll
+    for (int sx = 0; sx < 8; sx++) tb[lane * kT2 + sx] = make_float2(zr[sx], zi[sx]);
+    __syncwarp();
+    {
+      const int k1 = lane & 7, g = lane >> 3;                // lane (k1, g) finishes s = g and s = g + 4: 4-point DFT over j -> t
+      float2 c[2][4];
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) c[e][j] = tb[(k1 * 4 + j) * kT2 + g + 4 * e];
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float yr[4], yi[4];
+        dft4(c[e][0].x, c[e][0].y, c[e][1].x, c[e][1].y, c[e][2].x, c[e][2].y, c[e][3].x, c[e][3].y, yr[0], yi[0], yr[1], yi[1], yr[2], yi[2], yr[3], yi[3]);
+#pragma unroll
+        for (int tt = 0; tt < 4; tt++) tb[k1 + 8 * (g + 4 * e) + 68 * tt] = make_float2(yr[tt], yi[tt]);   // idx(k), k = k1 + 8 s + 64 t
+      }
+    }
+    __syncwarp();
+    // ---- real-FFT untangling on pairs (k, 256 - k) -> power spectrum
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = lane + 32 * i;
+      if (k == 0) {
+        const float2 z = tb[0];
+        pw[0] = (z.x + z.y) * (z.x + z.y); pw[256] = (z.x - z.y) * (z.x - z.y);
+        const float2 zm = tb[128 + 4 * 2];
+        pw[128] = zm.x * zm.x + zm.y * zm.y;
+      } else {
+        const int k2 = 256 - k;
+        const float2 a = tb[k + 4 * (k >> 6)], b = tb[k2 + 4 * (k2 >> 6)];
+        const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);      // E = (Z[k] + conj Z[256-k]) / 2
+        const float dr = 0.5f * (a.x - b.x), di = 0.5f * (a.y + b.y);      // D = (Z[k] - conj Z[256-k]) / 2;  O = D / i = (di, -dr)
+        const float gr = di * ptw[i].x + dr * ptw[i].y, gi = di * ptw[i].y - dr * ptw[i].x;   // G = W_512^k O
+        const float p1r = er + gr, p1i = ei + gi, p2r = er - gr, p2i = ei - gi;
+        pw[k] = p1r * p1r + p1i * p1i;
+        pw[k2] = p2r * p2r + p2i * p2i;
+      }
+    }
+    __syncwarp();
+    // ---- mel: one balanced chunk of taps per lane, chunks of a bin summed in order, log
+    {
+      float e = 0.0f;
+      const float *w = s_tab + my_chunk.y, *pp = pw + my_chunk.x;
+      for (int i = 0; i < my_chunk.z; i++) e += w[i] * pp[i];
+      part[lane] = e;
+    }
+    if (use_energy) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) energy += __shfl_xor_sync(0xffffffffu, energy, o);
+    }
+    __syncwarp();
+    if (lane < nbins) {
+      float e = part[my_bin.x];
+      for (int c = 1; c < my_bin.y; c++) e += part[my_bin.x + c];
+      melv[lane] = logf(fmaxf(e, FLT_EPSILON));
+    }
+    __syncwarp();
+    // ---- DCT-II + lifter: lanes (c, half) take half of the bins each
+    {
+      float acc = 0.0f;
+      if (dc_c < nceps) {
+        const float *d = dct + dc_c * nbins;
+        const int b0 = dc_h * dc_half, b1 = min(nbins, b0 + dc_half);
+        for (int b = b0; b < b1; b++) acc += d[b] * melv[b];
+      }
+      acc += __shfl_down_sync(0xffffffffu, acc, 16);
+      if (lane < nceps) {
+        acc *= lift[lane];
+        if (use_energy && lane == 0) { const float le = logf(fmaxf(energy, FLT_EPSILON)); acc = fmaxf(le, log_energy_floor); }
+        out[f * nceps + lane] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- CMVN statistics: per-utterance partial sums (f64), then per-speaker sums in utterance order (deterministic)
 __global__ void cmvn_partial_kernel(const float *__restrict__ feats, int dim, const int64_t *__restrict__ frame_off, double *__restrict__ part) {
   const int u = blockIdx.x;
@@ -261,6 +545,22 @@ int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, con
     CUDA_TRY(cudaMemcpyAsync(d_tab, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));  // blob is a local
     memcpy(e->mfcc_tab_desc, &t, sizeof(t)); e->mfcc_tab_opts = *o; e->mfcc_tab_valid = true;
+  }
+  const bool fast = t.fast && !(getenv("MFA_MFCC_GENERIC") && atoi(getenv("MFA_MFCC_GENERIC")));
+  if (fast) {
+    const size_t smem = (size_t)(3 * 8 * 32 * 2 + ((t.total + 3) & ~3) + kFW * kWarpFloats) * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(mfcc512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t max_warps = (int64_t)e->sm_count * 6 * kFW * 4;   // ~4 waves of 6 resident CTAs per SM: the tables are rebuilt per CTA
+    int64_t fpw = (n_frames + max_warps - 1) / max_warps;
+    if (fpw < 8) fpw = 8;
+    int64_t warps = (n_frames + fpw - 1) / fpw;
+    int blocks = (int)((warps + kFW - 1) / kFW);
+    float lef = (o->energy_floor > 0.0f) ? logf(o->energy_floor) : -INFINITY;
+    mfcc512_kernel<<<blocks, kFW * 32, smem, e->stream>>>(t, d_tab, d_pcm, d_sample_off, d_frame_off, n_utts, frame_base, n_frames, fpw, d_out,
+                                                             o->preemph_coeff, o->snip_edges, o->remove_dc_offset, o->use_energy, o->raw_energy, lef);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MFA_OK;
   }
   size_t smem = ((t.total + 3) / 4 * 4 + kWarps * (4 * t.NB + 4)) * sizeof(float);
   if (smem > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "MFCC tables exceed shared memory");
