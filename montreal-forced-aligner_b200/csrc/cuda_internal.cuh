@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -66,13 +67,49 @@ struct mfa_engine {
   int get(int id, size_t bytes, void **out);
   int get_pinned(int id, size_t bytes, void **out);
   template <typename T> int getT(int id, size_t n, T **out) { void *p; int r = get(id, n * sizeof(T), &p); *out = (T *)p; return r; }
-  // upload a small host array into a device buffer slot
+  // Pinned staging for the small host->device uploads of an API call (offsets, plans, work lists): the bytes are copied into an
+  // engine-owned pinned arena first, so the cudaMemcpyAsync neither blocks the host nor drains the stream (a copy from pageable
+  // memory does both) and the caller's vector may die immediately.  Two arenas serve alternate calls; an arena is reused once
+  // the call that filled it has drained (event).  Entry points open a scope with CallScope.
+  static constexpr size_t kStageBytes = (size_t)32 << 20;
+  void *stage_mem[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  bool stage_busy[2] = {false, false};
+  size_t stage_used = kStageBytes;     // full until the first begin_call
+  int stage_cur = 0;
+  int begin_call();
+  int end_call();
+  // moves staged bytes with a small SM kernel that reads the pinned arena directly: a cudaMemcpyAsync would queue on the copy
+  // engine BEHIND bulk transfers already enqueued there (the PCM pieces of the end-to-end path: ~20 ms), stalling the stream
+  int stage_copy(void *dst, const void *src_pinned, size_t bytes);
+  void *stage_alloc(size_t bytes) {
+    const size_t off = (stage_used + 255) & ~(size_t)255;
+    if (!stage_mem[stage_cur] || off + bytes > kStageBytes) return nullptr;
+    stage_used = off + bytes;
+    return (char *)stage_mem[stage_cur] + off;
+  }
+  // upload a host array into a device buffer slot (stream-ordered; `h` may be freed on return)
   template <typename T> int upload(int id, const T *h, size_t n, T **out) {
     int r = getT<T>(id, n ? n : 1, out);
     if (r) return r;
-    if (n) CUDA_TRY(cudaMemcpyAsync(*out, h, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    if (n) {
+      if (void *st = stage_alloc(n * sizeof(T))) {
+        memcpy(st, h, n * sizeof(T));
+        int r2 = stage_copy(*out, st, n * sizeof(T));
+        if (r2) return r2;
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(*out, h, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+      }
+    }
     return MFA_OK;
   }
+};
+
+struct CallScope {   // one per C-ABI entry point that uploads: recycles the staging arena
+  mfa_engine *e;
+  explicit CallScope(mfa_engine *e_) : e(e_) { e->begin_call(); }
+  ~CallScope() { e->end_call(); }
 };
 
 // Tiled acoustic model on the device.  Gaussians are regrouped into tiles of TILE_N rows that never split a pdf

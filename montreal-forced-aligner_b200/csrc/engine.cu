@@ -1,6 +1,9 @@
 // engine.cu -- engine lifetime, workspaces, acoustic-model upload/tiling, graph upload.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "cuda_internal.cuh"
@@ -60,6 +63,10 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) {
+    CUDA_TRY(cudaMallocHost(&e->stage_mem[k], mfa_engine::kStageBytes));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->stage_ev[k], cudaEventDisableTiming));
+  }
   *out = e;
   return MFA_OK;
 }
@@ -75,6 +82,7 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto ev : e->st_ev) cudaEventDestroy(ev);
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int k = 0; k < 2; k++) { if (e->stage_mem[k]) cudaFreeHost(e->stage_mem[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }
   cudaStreamDestroy(e->stream);
   delete e;
   return MFA_OK;
@@ -90,6 +98,30 @@ extern "C" void *mfa_engine_stream(mfa_engine *e) { return e ? (void *)e->stream
 extern "C" int mfa_engine_sm_count(mfa_engine *e) { return e ? e->sm_count : 0; }
 extern "C" int64_t mfa_engine_launch_count(mfa_engine *e) { return e ? e->launches : 0; }
 extern "C" int64_t mfa_engine_band_fallbacks(mfa_engine *e) { return e ? e->band_fallbacks : 0; }
+namespace {
+__global__ void stage_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+int mfa_engine::stage_copy(void *dst, const void *src_pinned, size_t bytes) {
+  // arena chunks are 256-byte aligned and device buffers carry >= 256 bytes of slack, so whole 16-byte words may be moved
+  const size_t n16 = (bytes + 15) / 16;
+  const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 4 * (size_t)sm_count);
+  stage_copy_kernel<<<blocks, 256, 0, stream>>>((const uint4 *)src_pinned, (uint4 *)dst, n16);
+  CUDA_TRY(cudaGetLastError());
+  return MFA_OK;
+}
+int mfa_engine::begin_call() {
+  stage_cur ^= 1;
+  if (stage_busy[stage_cur]) { CUDA_TRY(cudaEventSynchronize(stage_ev[stage_cur])); stage_busy[stage_cur] = false; }
+  stage_used = 0;
+  return MFA_OK;
+}
+int mfa_engine::end_call() {
+  if (stage_used > 0) { CUDA_TRY(cudaEventRecord(stage_ev[stage_cur], stream)); stage_busy[stage_cur] = true; }
+  stage_used = kStageBytes;   // uploads outside a scope take the synchronous path
+  return MFA_OK;
+}
 int mfa_engine::gmm_timing_begin() {
   if ((size_t)gmm_ev_used + 2 > gmm_ev.size()) {
     for (int k = 0; k < 2; k++) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); gmm_ev.push_back(ev); }
@@ -118,6 +150,12 @@ extern "C" int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_
 }
 
 int mfa_engine::stage_begin(int stage) {
+  if (getenv("MFA_TRACE")) {
+    static thread_local std::chrono::steady_clock::time_point t0;
+    auto now = std::chrono::steady_clock::now();
+    if (st_stage.empty()) t0 = now;
+    fprintf(stderr, "[trace] host %.3f ms: enqueue stage %d\n", std::chrono::duration<double, std::milli>(now - t0).count(), stage);
+  }
   const size_t k = st_stage.size();
   while (st_ev.size() < 2 * (k + 1)) { cudaEvent_t ev; CUDA_TRY(cudaEventCreate(&ev)); st_ev.push_back(ev); }
   st_stage.push_back(stage);

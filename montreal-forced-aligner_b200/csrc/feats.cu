@@ -252,7 +252,6 @@ int launch_features(mfa_engine *e, const mfa_feat_opts *o, const float *d_in, co
   float *d_lda = nullptr, *d_fmllr = nullptr;
   if (p.mode == 2) MFA_TRY(e->upload(DB_LDA, o->lda, (size_t)p.lda_rows * p.lda_cols, &d_lda));
   if (p.has_fmllr) MFA_TRY(e->upload(DB_FMLLR, o->fmllr, (size_t)o->n_spk * p.mid_dim * (p.mid_dim + 1), &d_fmllr));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));  // tile_off is a local
   if (tiled) {
     const int sd = (2 * p.ctx + 1) * p.in_dim, KP = 4 * n_kq;
     const size_t smem = ((size_t)(sd + 1) * KP + (((size_t)(tf + 2 * p.ctx) * p.in_dim + 3) & ~(size_t)3) + (p.has_fmllr ? (size_t)tf * KP + (size_t)p.mid_dim * (p.mid_dim + 1) : 0)) * sizeof(float);

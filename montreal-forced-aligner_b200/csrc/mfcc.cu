@@ -513,6 +513,7 @@ __global__ void cmvn_reduce_kernel(const double *__restrict__ part, int dim, con
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_spk * (dim + 1)) return;
   int s = idx / (dim + 1), d = idx % (dim + 1);
+  if (spk_utt_off[s] == spk_utt_off[s + 1]) return;   // speaker has no utterance in this call: its (zeroed or earlier) statistics stay
   double a = 0.0, b = 0.0;
   for (int k = spk_utt_off[s]; k < spk_utt_off[s + 1]; k++) {
     int u = spk_utts[k];
@@ -589,7 +590,6 @@ int launch_cmvn_stats(mfa_engine *e, const float *d_feats, int dim, const int64_
   int32_t *d_off, *d_utts; double *d_part;
   MFA_TRY(e->upload(DB_SPK_UTT_OFF, off.data(), off.size(), &d_off));
   MFA_TRY(e->upload(DB_SPK_UTTS, utts.data(), utts.size(), &d_utts));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
   MFA_TRY(e->getT<double>(DB_CMVN_PART, (size_t)n_utts * 2 * dim, &d_part));
   int threads = 256, lanes = threads / dim;
   cmvn_partial_kernel<<<n_utts, threads, (size_t)lanes * dim * 2 * sizeof(double), e->stream>>>(d_feats, dim, d_frame_off, d_part);

@@ -5,6 +5,7 @@
 // MFCC -> per-speaker CMVN -> deltas | splice+LDA (+fMLLR) -> all-pdf log-likelihoods -> beam Viterbi, in utterance
 // chunks sized so the pdf-major log-likelihood block and the back-pointers fit the HBM workspace.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "cuda_internal.cuh"
@@ -60,6 +61,7 @@ int mfa_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *pcm, const in
              float *out, int where) {
   if (!e || !o || !sample_off || !frame_off || n_utts < 0) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   MFA_TRY(check_offsets(sample_off, n_utts, "sample_off"));
   for (int u = 0; u < n_utts; u++)
     if (frame_off[u + 1] - frame_off[u] != mfa_mfcc_num_frames(o, sample_off[u + 1] - sample_off[u]))
@@ -81,6 +83,7 @@ int mfa_cmvn_stats(mfa_engine *e, const float *feats, int32_t dim, const int64_t
                    int32_t n_spk, double *stats, int where) {
   if (!e || !frame_off || !utt2spk || !stats) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
   int64_t *d_fo; const float *d_feats; double *d_stats;
   MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
@@ -98,6 +101,7 @@ int mfa_features(mfa_engine *e, const mfa_feat_opts *o, const float *in, const i
                  float *out, int where) {
   if (!e || !o || !frame_off) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
   if ((o->fmllr || o->cmvn_stats) && !utt2spk) return set_error(MFA_ERR_INVALID, "utt2spk required with fmllr / cmvn_stats");
   int64_t nf = frame_off[n_utts];
@@ -126,6 +130,7 @@ int mfa_cmvn_apply(mfa_engine *e, float *feats, int32_t dim, const int64_t *fram
 int mfa_gmm_loglikes(mfa_engine *e, mfa_model *m, const float *feats, int64_t n_frames, float *out, int where, int impl) {
   if (!e || !m || n_frames < 0) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   e->gmm_timing_reset();
   const float *d_feats; float *d_out;
   MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)n_frames * m->dim, where, &d_feats));
@@ -151,8 +156,8 @@ struct ChunkPlan { int u0, n; int64_t ld; std::vector<int64_t> col_off, ll_off, 
 
 // split utterances into chunks bounded by the log-likelihood block (+ back-pointers) budget
 int plan_chunks(const mfa_graphs *g, const int64_t *frame_off, int n_utts, int num_pdfs, int dim, int64_t budget, std::vector<ChunkPlan> &plans,
-                bool ragged = false) {
-  int u = 0;
+                bool ragged = false, int u_begin = 0) {
+  int u = u_begin;
   while (u < n_utts) {
     ChunkPlan c; c.u0 = u; c.n = 0;
     int64_t cols = 0, bp = 0, llf = 0;
@@ -191,6 +196,7 @@ int mfa_align(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_opts *
   if (!e || !m || !g || !o || !frame_off || !word_off) return set_error(MFA_ERR_INVALID, "bad argument");
   if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
   MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
   MFA_TRY(upload_graphs(e, g));
@@ -248,6 +254,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   if (!e || !m || !g || !o || !sample_off || !frame_off || !word_off || !utt2spk) return set_error(MFA_ERR_INVALID, "bad argument");
   if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   MFA_TRY(check_offsets(sample_off, n_utts, "sample_off"));
   MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
   for (int u = 0; u < n_utts; u++)
@@ -282,74 +289,165 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   CUDA_TRY(cudaMemsetAsync(io.d_ali, 0, (size_t)nf * 4, e->stream));
   CUDA_TRY(cudaMemsetAsync(io.d_pf, 0, (size_t)nf * 4, e->stream));
   if (nw) CUDA_TRY(cudaMemsetAsync(io.d_words, 0, (size_t)nw * 4, e->stream));
-  // ---- K1 + CMVN statistics over the whole batch
+  // ---- segments.  Device-resident PCM: one segment.  Host PCM: the batch is cut after a speaker boundary near the middle so
+  // that the second half is still crossing PCIe while the first half is scored and aligned; CMVN statistics are per speaker,
+  // so a cut is only legal where every speaker's utterances are contiguous (MFA orders jobs by speaker-utterance key) and the
+  // speaker changes.  All uploads are queued on the copy stream before any compute, each MFCC launch waits for its own bytes.
   float *d_mfcc; double *d_stats = nullptr;
   MFA_TRY(e->getT<float>(DB_MFCC, (size_t)nf * C, &d_mfcc));
-  MFA_TRY(e->stage_begin(mfa_engine::ST_MFCC));
-  if (where == MFA_DEVICE) {
-    MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
-  } else {
-    const int64_t piece = std::max<int64_t>((int64_t)16 << 20, ns / 12 + 1);   // samples per H2D piece (>= 32 MB)
+  const size_t nst = (size_t)n_spk * 2 * (C + 1);
+  if (o->apply_cmvn) {
+    if (fo.cmvn_stats) MFA_TRY(e->upload(DB_CMVN_STATS, fo.cmvn_stats, nst, &d_stats));
+    else { MFA_TRY(e->getT<double>(DB_CMVN_STATS, nst, &d_stats)); CUDA_TRY(cudaMemsetAsync(d_stats, 0, nst * sizeof(double), e->stream)); }
+  }
+  std::vector<int> seg_begin{0};
+  // Two ways to use the cuts (MFA_PIPELINE_SPLIT): 2 (default for host PCM when the batch fits one chunk) = STREAM: MFCC, CMVN,
+  // features and log-likelihoods run per segment as its bytes arrive, the Viterbi stage runs once over the whole batch at the
+  // end -- it is bounded by its longest utterance's sequential recursion, not by throughput, so it must not be cut;
+  // 1 = every stage per segment (measured on the 10 h config-2 workload: end to end 45 -> 55 ms, two Viterbi tails); 0 = no cuts.
+  const char *env_split = getenv("MFA_PIPELINE_SPLIT");
+  const int split_mode = env_split ? atoi(env_split) : 2;
+  const int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
+  const bool ragged = o->gmm_impl == 0 && gmm_tc_supported(m);
+  std::vector<ChunkPlan> whole;
+  bool stream = false;
+  if (where == MFA_HOST && split_mode == 2 && (getenv("MFA_PIPELINE_SPLIT") || (n_utts >= 64 && ns >= ((int64_t)64 << 20)))) {
+    MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, whole, ragged));
+    stream = whole.size() == 1 && ragged;   // (dense scoring keeps the chunk loop: its tiles want 128-column alignment)
+  }
+  if (where == MFA_HOST && n_utts >= 2 && (stream || split_mode == 1)) {
+    bool contiguous = true;
+    if (o->apply_cmvn && !fo.cmvn_stats) {
+      std::vector<char> seen((size_t)std::max(n_spk, 1), 0);
+      for (int u = 0; u < n_utts && contiguous; u++) {
+        const int sp = utt2spk[u];
+        if (sp < 0 || sp >= n_spk) return set_error(MFA_ERR_INVALID, "utt2spk out of range");
+        if (u > 0 && sp != utt2spk[u - 1] && seen[sp]) contiguous = false;
+        seen[sp] = 1;
+      }
+    }
+    if (contiguous) {
+      const int n_cut = stream ? 4 : 2;                      // segments
+      for (int k = 1, u = 0; k < n_cut; k++) {
+        while (u < n_utts && sample_off[u] < ns * k / n_cut) u++;
+        if (o->apply_cmvn && !fo.cmvn_stats) while (u < n_utts && u > 0 && utt2spk[u] == utt2spk[u - 1]) u++;
+        if (u > seg_begin.back() && u < n_utts) seg_begin.push_back(u);
+      }
+    } else stream = false;
+  }
+  if (seg_begin.size() == 1) stream = false;
+  seg_begin.push_back(n_utts);
+  // ---- uploads (host PCM): pieces of >= 32 MB that never straddle a segment
+  struct Piece { int u0, u1, ev; };
+  std::vector<Piece> pieces;
+  if (where == MFA_HOST) {
+    const int64_t piece = std::max<int64_t>((int64_t)16 << 20, ns / 12 + 1);   // samples per H2D piece
     cudaStream_t cs = e->side[0];
     CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
     CUDA_TRY(cudaStreamWaitEvent(cs, e->ev_fork, 0));   // earlier work on the main stream may still read DB_PCM
-    int u0 = 0, k = 0;
-    while (u0 < n_utts) {
-      int u1 = u0;
-      while (u1 < n_utts && sample_off[u1 + 1] - sample_off[u0] <= piece) u1++;
-      if (u1 == u0) u1 = u0 + 1;
-      const int64_t s0 = sample_off[u0], s1 = sample_off[u1];
-      if ((int)e->ev_piece.size() <= k) { cudaEvent_t ev; CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_piece.push_back(ev); }
-      if (s1 > s0) CUDA_TRY(cudaMemcpyAsync((int16_t *)d_pcm + s0, pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
-      CUDA_TRY(cudaEventRecord(e->ev_piece[k], cs));
-      CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_piece[k], 0));
-      MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, frame_off[u1] - frame_off[u0], d_mfcc, frame_off[u0]));
-      u0 = u1; k++;
+    for (size_t sg = 0; sg + 1 < seg_begin.size(); sg++) {
+      int u0 = seg_begin[sg];
+      while (u0 < seg_begin[sg + 1]) {
+        int u1 = u0;
+        while (u1 < seg_begin[sg + 1] && sample_off[u1 + 1] - sample_off[u0] <= piece) u1++;
+        if (u1 == u0) u1 = u0 + 1;
+        const int64_t s0 = sample_off[u0], s1 = sample_off[u1];
+        const int k = (int)pieces.size();
+        if ((int)e->ev_piece.size() <= k) { cudaEvent_t ev; CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e->ev_piece.push_back(ev); }
+        if (s1 > s0) CUDA_TRY(cudaMemcpyAsync((int16_t *)d_pcm + s0, pcm + s0, (size_t)(s1 - s0) * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaEventRecord(e->ev_piece[k], cs));
+        pieces.push_back({u0, u1, k});
+        u0 = u1;
+      }
     }
   }
-  if (o->apply_cmvn) {
-    size_t nst = (size_t)n_spk * 2 * (C + 1);
-    if (fo.cmvn_stats) MFA_TRY(e->upload(DB_CMVN_STATS, fo.cmvn_stats, nst, &d_stats));
-    else {
-      MFA_TRY(e->getT<double>(DB_CMVN_STATS, nst, &d_stats));
-      MFA_TRY(launch_cmvn_stats(e, d_mfcc, C, d_fo, utt2spk, n_utts, n_spk, d_stats));
-    }
-  }
-  MFA_TRY(e->stage_end());
-  // ---- chunks
-  std::vector<ChunkPlan> plans;
-  int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
-  const bool ragged = o->gmm_impl == 0 && gmm_tc_supported(m);
-  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, plans, ragged));
-  for (auto &c : plans) {
-    float *d_feats, *d_llT; int64_t *d_col, *d_ll_off = nullptr, *d_ld_u = nullptr;
-    MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
-    MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
-    MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
-    MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
-    CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
-    MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
-    MFA_TRY(e->stage_end());
-    MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
+  size_t next_piece = 0;
+  // STREAM mode: one chunk plan for the whole batch; its buffers are filled segment by segment
+  float *w_feats = nullptr, *w_llT = nullptr; int64_t *w_col = nullptr, *w_ll_off = nullptr, *w_ld_u = nullptr;
+  if (stream) {
+    ChunkPlan &c = whole[0];
+    MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &w_feats));
+    MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &w_llT));
+    MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &w_col));
     if (ragged) {
-      MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
-      MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &d_ld_u));
-      MFA_TRY(e->gmm_timing_begin());
-      MFA_TRY(launch_gmm_tc_ragged(e, m, g, c.u0, c.n, d_feats, c.col_off.data(), frame_off + c.u0, d_llT, c.ll_off.data(), c.ld_u.data()));
-      MFA_TRY(e->gmm_timing_end(frame_off[c.u0 + c.n] - frame_off[c.u0]));
-    } else {
-      MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
+      MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &w_ll_off));
+      MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &w_ld_u));
     }
+    CUDA_TRY(cudaMemsetAsync(w_feats, 0, (size_t)c.ld * D * 4, e->stream));
+  }
+  for (size_t sg = 0; sg + 1 < seg_begin.size(); sg++) {
+    const int sb = seg_begin[sg], se = seg_begin[sg + 1];
+    // ---- K1 + CMVN statistics of the segment
+    MFA_TRY(e->stage_begin(mfa_engine::ST_MFCC));
+    if (where == MFA_DEVICE) {
+      MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, nf, d_mfcc));
+    } else {
+      for (; next_piece < pieces.size() && pieces[next_piece].u1 <= se; next_piece++) {
+        const Piece &pc = pieces[next_piece];
+        CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_piece[pc.ev], 0));
+        MFA_TRY(launch_mfcc(e, &o->mfcc, d_pcm, d_so, n_utts, d_fo, frame_off[pc.u1] - frame_off[pc.u0], d_mfcc, frame_off[pc.u0]));
+      }
+    }
+    if (o->apply_cmvn && !fo.cmvn_stats) MFA_TRY(launch_cmvn_stats(e, d_mfcc, C, d_fo + sb, utt2spk + sb, se - sb, n_spk, d_stats));
     MFA_TRY(e->stage_end());
-    ViterbiArgs a{};
-    a.d_ll_off = d_ll_off; a.d_ld_u = d_ld_u;
-    a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
-    a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
-    a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
-    a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
-    MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
-    MFA_TRY(launch_viterbi(e, a));
-    MFA_TRY(e->stage_end());
+    if (stream) {
+      // features and log-likelihoods of the segment's utterances, written into the whole-batch buffers
+      ChunkPlan &c = whole[0];
+      const int sn = se - sb;
+      MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
+      MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + sb, frame_off + sb, w_col + sb, d_u2s + sb, sn, d_stats, w_feats, D));
+      MFA_TRY(e->stage_end());
+      MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
+      MFA_TRY(e->gmm_timing_begin());
+      MFA_TRY(launch_gmm_tc_ragged(e, m, g, sb, sn, w_feats, c.col_off.data() + sb, frame_off + sb, w_llT, c.ll_off.data() + sb, c.ld_u.data() + sb));
+      MFA_TRY(e->gmm_timing_end(frame_off[se] - frame_off[sb]));
+      MFA_TRY(e->stage_end());
+      if (se == n_utts) {
+        ViterbiArgs a{};
+        a.d_ll_off = w_ll_off; a.d_ld_u = w_ld_u;
+        a.g = g; a.utt0 = 0; a.n_utts = n_utts; a.d_llT = w_llT; a.ld = c.ld; a.d_col_off = w_col; a.d_frame_off = d_fo;
+        a.h_frame_off = frame_off; a.h_col_off = c.col_off.data();
+        a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off;
+        a.d_num_words = io.d_num_words; a.d_total_like = io.d_total; a.d_status = io.d_status; a.opts = o->align;
+        MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
+        MFA_TRY(launch_viterbi(e, a));
+        MFA_TRY(e->stage_end());
+      }
+      continue;
+    }
+    // ---- chunks of the segment
+    std::vector<ChunkPlan> plans;
+    MFA_TRY(plan_chunks(g, frame_off, se, P, D, budget, plans, ragged, sb));
+    for (auto &c : plans) {
+      float *d_feats, *d_llT; int64_t *d_col, *d_ll_off = nullptr, *d_ld_u = nullptr;
+      MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
+      MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
+      MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
+      MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
+      CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
+      MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
+      MFA_TRY(e->stage_end());
+      MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
+      if (ragged) {
+        MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
+        MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &d_ld_u));
+        MFA_TRY(e->gmm_timing_begin());
+        MFA_TRY(launch_gmm_tc_ragged(e, m, g, c.u0, c.n, d_feats, c.col_off.data(), frame_off + c.u0, d_llT, c.ll_off.data(), c.ld_u.data()));
+        MFA_TRY(e->gmm_timing_end(frame_off[c.u0 + c.n] - frame_off[c.u0]));
+      } else {
+        MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, o->gmm_impl));
+      }
+      MFA_TRY(e->stage_end());
+      ViterbiArgs a{};
+      a.d_ll_off = d_ll_off; a.d_ld_u = d_ld_u;
+      a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
+      a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
+      a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
+      a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
+      MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
+      MFA_TRY(launch_viterbi(e, a));
+      MFA_TRY(e->stage_end());
+    }
   }
   MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
@@ -364,6 +462,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
 int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const int32_t *ali, int64_t n_frames, int where) {
   if (!e || !m || n_frames < 0) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
   const float *d_feats; const int32_t *d_ali;
   MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)n_frames * m->dim, where, &d_feats));
   MFA_TRY(to_device(e, DB_IO_ALI, ali, (size_t)n_frames, where, &d_ali));

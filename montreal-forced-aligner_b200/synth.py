@@ -125,7 +125,8 @@ def make_corpus(seconds: float, seed: int = SEED, n_phones: int = 40, n_words: i
     if n_spk is None:
         n_spk = max(1, int(round(total / 3600.0 * 2.5)))
     n_spk = max(1, min(n_spk, n_utts))
-    utt2spk = (rng.permutation(n_utts) % n_spk).astype(np.int32)
+    # MFA orders a job's utterances by their "{speaker}-{utterance}" key (corpus/multiprocessing.py:482-497): speakers are contiguous
+    utt2spk = np.sort(rng.permutation(n_utts) % n_spk).astype(np.int32)
     spk_scale = rng.uniform(0.88, 1.12, n_spk)
     spk_f0 = rng.uniform(90, 220, n_spk)
     sample_off = np.zeros(n_utts + 1, dtype=np.int64)

@@ -267,7 +267,7 @@ def test_fused_pipeline_config1_sample(eng, tmp_path):
     dm.close()
 
 
-def test_fused_pipeline_triphone_lda_fmllr_chunked(eng):
+def test_fused_pipeline_triphone_lda_fmllr_chunked(eng, monkeypatch):
     """Config 2/3 shape in miniature: splice+LDA(+fMLLR) features, triphone tree, several speakers, forced small workspace
     so the chunk loop runs more than once; device-resident PCM."""
     import torch
@@ -291,6 +291,19 @@ def test_fused_pipeline_triphone_lda_fmllr_chunked(eng):
         same += int((a == r["ali"]).sum()); total += len(a)
         assert abs(float(tl[u]) - r["like"]) <= 1e-4 * abs(r["like"])
     assert same / total >= 0.999, same / total
+    # host-buffer path cut into segments at speaker boundaries (uploads overlap work on earlier segments): same outputs as the
+    # single-segment run; the corpus generator keeps each speaker's utterances contiguous, like MFA's job ordering
+    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "1")
+    res_split = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
+    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "0")
+    res_whole = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
+    # streamed: K1 / CMVN / features / K2 per segment as its PCM arrives, one Viterbi launch at the end (the default for big batches)
+    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "2")
+    res_stream = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
+    monkeypatch.delenv("MFA_PIPELINE_SPLIT")
+    assert len(set(c.utt2spk.tolist())) > 1
+    for r_ in (res_split, res_whole, res_stream):
+        assert np.array_equal(r_.ali, ali) and np.array_equal(r_.status, st) and np.array_equal(r_.total_like, tl)
     # per-speaker fMLLR path: identity transforms must reproduce the result exactly
     fm = np.tile(np.eye(40, 41, dtype=np.float32)[None], (c.n_spk, 1, 1))
     res2 = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"], fmllr=fm)
