@@ -345,26 +345,29 @@ def main():
               "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1),
               "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs", "launches_per_step": gmm_n, "avg_launch_ms": avg_ms,
               "algorithmic_flops_per_launch": per_launch_flops, "share_of_step": gmm_ms / step_ms}
-    # K3: bytes per utterance = T*(4*P_u + 2*S_u) + 4*T + graph (12 B per arc + 8 B per state)
+    # K3 (band kernel): algorithmic bytes per utterance = T * (4 P_u log-likelihoods read once + 512 back-pointer row
+    # written + 512 read by the back-trace + 8 outputs) + its graph (4 B per state + 8 B per arc, read through L1)
     so, ao, po = sc.graphs.offsets()
     T_u = (sc.frame_off[1:] - sc.frame_off[:-1]).astype(np.float64)
     S_u, A_u, P_u = np.diff(so).astype(np.float64), np.diff(ao).astype(np.float64), np.diff(po).astype(np.float64)
-    k3_bytes = float((T_u * (4 * P_u + 2 * S_u) + 4 * T_u + 12 * A_u + 8 * S_u).sum())
+    k3_bytes = float((T_u * (4 * P_u + 512 + 512 + 8) + 8 * A_u + 4 * S_u).sum())
     k3 = None
     if stages["viterbi"] > 0:
         ach = k3_bytes / (stages["viterbi"] * 1e-3) / 1e9
-        k3 = {"kernel": "K3 viterbi_kernel (all shared-memory classes, fork to join)", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
-              "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " HBM copy",
+        k3 = {"kernel": "K3 viterbi_band_kernel (all shared-memory classes on side streams, fork to join)", "bound": "hbm", "achieved": ach,
+              "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"] + " HBM copy",
               "algorithmic_bytes_per_launch": k3_bytes, "avg_launch_ms": stages["viterbi"], "share_of_step": stages["viterbi"] / step_ms,
-              "note": "latency-bound sequential recursion (one warp per utterance); see profiles/r1_viterbi_full.md for stall reasons"}
+              "note": "latency-bound: a sequential per-frame recursion per utterance (2 warps each); bounded by resident utterances x "
+                      "per-frame dependency chain, not by bytes -- see profiles/r1_viterbi_band_full.md for stall reasons"}
     # K1: bytes = 2 per sample + 4*13 per frame
     k1_bytes = float(2 * c.pcm.shape[0] + 52 * n_frames)
     k1 = None
     if stages["mfcc_cmvn"] > 0:
         ach = k1_bytes / (stages["mfcc_cmvn"] * 1e-3) / 1e9
-        k1 = {"kernel": "K1 mfcc_kernel + CMVN statistics", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+        k1 = {"kernel": "K1 mfcc512_kernel + CMVN statistics", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
               "frac": ach / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": stages["mfcc_cmvn"],
-              "share_of_step": stages["mfcc_cmvn"] / step_ms, "note": "fp32-ALU / issue bound (2.7k warp instructions per frame), not HBM bound"}
+              "share_of_step": stages["mfcc_cmvn"] / step_ms,
+              "note": "fp32-ALU / issue bound (register FFT, ~600 warp instructions per frame), not HBM bound -- see profiles/r1_mfcc512_full.md"}
     cands = [x for x in (k2, k3, k1) if x]
     roof = max(cands, key=lambda x: x["share_of_step"]) if cands else None
 
