@@ -192,6 +192,17 @@ MFA_API int mfa_fst_batch_export(const mfa_fst_batch *b, int64_t *state_off, int
                                  float *finals, int32_t *src, int32_t *dst, int32_t *ilabel, int32_t *olabel,
                                  float *weight);
 
+/* ---- a11: equal alignment (host).  Replaces kalpy gmm_align_equal -> Kaldi EqualAlign + GetLinearSymbolSequence, called by
+ *      MonoAlignEqualFunction._run (acoustic_modeling/monophone.py:108) for iteration 0 of monophone training.  One random
+ *      self-loop-free path per graph (seeds[u]: Kaldi's align-equal-compiled seeds srand() with StringHasher(utterance id);
+ *      the draws restate glibc rand()), the remaining frames spread evenly over the path's self-loops.  Outputs as mfa_align
+ *      (ali at frame_off, words at word_off with capacity word_off[u+1]-word_off[u], status MFA_ALIGN_OK / NO_FINAL = could not
+ *      match the length / EMPTY_GRAPH / ZERO_FRAMES).  num_retries <= 0 -> 10 (Kaldi's default). */
+MFA_API int mfa_equal_align(const mfa_fst_batch *b, const int64_t *frame_off, const uint32_t *seeds, int32_t num_retries,
+                            int32_t *ali, int32_t *words, const int64_t *word_off, int32_t *num_words, int32_t *status);
+/* the first n values of rand() after srand(seed) as restated for mfa_equal_align (tests compare with libc) */
+MFA_API int mfa_rand_sequence(uint32_t seed, int32_t n, int32_t *out);
+
 /* decoder-ready packing: AddTransitionProbs (tid_cost[tid] = -scaled log prob, hmm/hmm-utils.cc) folded into the
  * arc weights, arcs grouped by destination, per-utterance local pdf lists.  Host-resident; uploaded lazily. */
 MFA_API int mfa_graphs_pack(const mfa_fst_batch *b, const float *tid_cost, const int32_t *tid2pdf, int32_t num_tids,
@@ -251,6 +262,18 @@ MFA_API int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const
 /* device pointer to the accumulator block (for an NCCL all-reduce by the host layer) */
 MFA_API double *mfa_acc_device_ptr(mfa_engine *e, mfa_model *m);
 MFA_API int mfa_acc_read(mfa_engine *e, mfa_model *m, double *host_out);
+
+/* ---- K5 (N2): per-speaker fMLLR statistics.  Replaces the accumulation inside kalpy FmllrComputer.export_transforms
+ *      (CalcFmllrFunction._run, corpus/features.py:460-548; Kaldi gmm-est-fmllr / gmm-est-fmllr-gpost + weight-silence-post).
+ *      post_model: the model the component posteriors come from (the alignment model in the two-model case; NULL = m);
+ *      m: the model whose means / variances enter the statistics; both are evaluated on the same `feats`.
+ *      tid_weight: host [num_tids+1] frame weight per transition-id (silence_weight for silence phones, else 1; NULL = 1).
+ *      stats: [n_spk][mfa_fmllr_stats_size(dim)] f64 = beta | K[D][D+1] | G[D][(D+1)(D+2)/2] (G_d: packed lower triangle,
+ *      row-major, Kaldi SpMatrix order).  The transform update from these statistics is host-side (fmllr.py). */
+MFA_API int64_t mfa_fmllr_stats_size(int32_t dim);
+MFA_API int mfa_fmllr_acc(mfa_engine *e, mfa_model *post_model, mfa_model *m, const float *feats, const int32_t *ali,
+                          const float *tid_weight, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts,
+                          int32_t n_spk, double *stats, int where);
 
 #ifdef __cplusplus
 }

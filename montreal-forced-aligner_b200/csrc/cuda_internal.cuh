@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -119,6 +119,7 @@ struct CallScope {   // one per C-ABI entry point that uploads: recycles the sta
 
 struct mfa_model {
   mfa_engine *eng = nullptr;
+  int device = 0;                      // copied from the engine at creation: the destructor must not touch `eng` (it may be gone)
   int dim = 0, num_pdfs = 0, num_gauss = 0, num_tids = 0;
   std::vector<int32_t> h_pdf_off, h_tid2pdf;
   std::vector<float> h_gconsts, h_miv, h_iv;
@@ -179,4 +180,7 @@ bool viterbi_band_graph_in_smem();                            // MFA_VIT_GRAPH_S
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem);   // shared memory the band kernel needs for one utterance
 int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
+int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d_feats, const int32_t *d_ali, const float *d_tid_weight,
+                     const int64_t *d_frame_off, const int64_t *h_frame_off, const int32_t *h_utt2spk, int32_t n_utts, int32_t n_spk,
+                     double *d_stats);
 }  // namespace mfa

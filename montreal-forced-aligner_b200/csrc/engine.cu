@@ -186,7 +186,7 @@ extern "C" int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops) {
 
 // ------------------------------------------------------------------------------------------------ model
 mfa_model::~mfa_model() {
-  if (eng) cudaSetDevice(eng->device);
+  cudaSetDevice(device);
   for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_tile_pdf0,
                   (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows})
     if (p) cudaFree(p);
@@ -252,7 +252,7 @@ extern "C" int mfa_model_create(mfa_engine *e, const mfa_model_desc *d, mfa_mode
   if (d->num_pdfs <= 0 || d->pdf_off[d->num_pdfs] != d->num_gauss) return set_error(MFA_ERR_INVALID, "pdf_off inconsistent with num_gauss");
   CUDA_TRY(cudaSetDevice(e->device));
   auto *m = new mfa_model();
-  m->eng = e; m->dim = d->dim; m->num_pdfs = d->num_pdfs; m->num_gauss = d->num_gauss; m->num_tids = d->num_tids;
+  m->eng = e; m->device = e->device; m->dim = d->dim; m->num_pdfs = d->num_pdfs; m->num_gauss = d->num_gauss; m->num_tids = d->num_tids;
   m->h_pdf_off.assign(d->pdf_off, d->pdf_off + d->num_pdfs + 1);
   m->h_gconsts.assign(d->gconsts, d->gconsts + d->num_gauss);
   m->h_miv.assign(d->means_invvars, d->means_invvars + (size_t)d->num_gauss * d->dim);

@@ -1,0 +1,215 @@
+// fmllr.cu -- K5: per-speaker fMLLR statistics (row N2 of SURVEY.md section 8f: the stage between the two alignment passes).
+//
+// Replaces the accumulation half of kalpy FmllrComputer.export_transforms, reached from CalcFmllrFunction._run
+// (montreal_forced_aligner/corpus/features.py:460-548; options :759-766).  Semantics = Kaldi gmmbin/gmm-est-fmllr(-gpost).cc +
+// transform/fmllr-diag-gmm.cc (FmllrDiagGmmAccs::AccumulateFromPosteriors, CommitSingleFrameStats) + WeightSilencePost:
+//   per frame t with aligned pdf j and weight w (silence_weight for silence phones):
+//     p_m = w * softmax_m(component log-likelihoods of j under the POSTERIOR model)           (fp32)
+//     a = sum_m p_m (mu/sigma^2)_m,  b = sum_m p_m (1/sigma^2)_m   under the STATISTICS model    (fp32)
+//     beta += sum_m p_m;  K += a xi^T;  G_d += b_d xi xi^T   with xi = [x; 1]                   (f64)
+// Two kernels:
+//   fmllr_frame_kernel  one warp per frame, lanes over the feature dimension: writes a | b (fp32) and the frame's count.
+//   fmllr_accum_kernel  one CTA per (speaker, tile of 8 rows d, frame split): every thread owns up to NIJ entries (i, j) of the
+//                       packed lower triangle x 8 rows of f64 sums in registers -- G_d is the GEMM  B^T[8 x T] * Z[T x 861] with
+//                       Z_t = vec(xi xi^T) formed on the fly from the frame staged in shared memory, never materialised -- and
+//                       flushes once (f64 red; plain sums when a speaker is not split).  D = 40: 147 G DFMA for 10 h of audio.
+// The row-by-row transform update itself (40 iterations x D rows of small dense solves per speaker) runs on the host in f64
+// (fmllr.py); it is O(speakers), not O(frames).
+#include <algorithm>
+
+#include "cuda_internal.cuh"
+
+using namespace mfa;
+
+namespace {
+constexpr int FW = 8;     // warps per CTA in the frame kernel
+constexpr int FB = 32;    // frames per staged batch in the accumulation kernel
+constexpr int DT = 8;     // rows d per CTA
+constexpr int ANT = 256;  // threads per CTA in the accumulation kernel
+
+__global__ void __launch_bounds__(FW * 32)
+fmllr_frame_kernel(const float *__restrict__ feats, const int32_t *__restrict__ ali, int64_t n_frames, int dim, int num_tids,
+                   const int32_t *__restrict__ pdf_off, const int32_t *__restrict__ tid2pdf, const float *__restrict__ tid_weight,
+                   const float *__restrict__ p_gconsts, const float *__restrict__ p_miv, const float *__restrict__ p_iv,
+                   const float *__restrict__ s_miv, const float *__restrict__ s_iv, float *__restrict__ ab, float *__restrict__ cnt) {
+  __shared__ float post[FW][MFA_TILE_N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * FW;
+  for (int64_t f = (int64_t)blockIdx.x * FW + warp; f < n_frames; f += stride) {
+    const int tid = ali[f];
+    float w = 0.0f;
+    if (tid > 0 && tid <= num_tids) w = tid_weight ? tid_weight[tid] : 1.0f;
+    if (w == 0.0f) { if (lane == 0) cnt[f] = 0.0f; continue; }
+    const int pdf = tid2pdf[tid];
+    const int m0 = pdf_off[pdf], nm = pdf_off[pdf + 1] - m0;
+    const float x0 = lane < dim ? feats[f * dim + lane] : 0.0f;
+    const float x1 = lane + 32 < dim ? feats[f * dim + lane + 32] : 0.0f;
+    float mx = -INFINITY;
+    for (int m = 0; m < nm; m++) {
+      const float *a = p_miv + (size_t)(m0 + m) * dim, *b = p_iv + (size_t)(m0 + m) * dim;
+      float d1 = 0.0f, d2 = 0.0f;
+      if (lane < dim) { d1 = a[lane] * x0; d2 = b[lane] * (x0 * x0); }
+      if (lane + 32 < dim) { d1 += a[lane + 32] * x1; d2 += b[lane + 32] * (x1 * x1); }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+      float v = p_gconsts[m0 + m] + d1;
+      v = v + (-0.5f) * d2;
+      if (lane == 0) post[warp][m] = v;
+      mx = fmaxf(mx, v);
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int m = lane; m < nm; m += 32) { const float ev = expf(post[warp][m] - mx); post[warp][m] = ev; sum += ev; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+    double c = 0.0;
+    for (int m = 0; m < nm; m++) {
+      const float p = post[warp][m] * inv * w;
+      c += (double)p;
+      const float *a = s_miv + (size_t)(m0 + m) * dim, *b = s_iv + (size_t)(m0 + m) * dim;
+      if (lane < dim) { a0 += a[lane] * p; b0 += b[lane] * p; }
+      if (lane + 32 < dim) { a1 += a[lane + 32] * p; b1 += b[lane + 32] * p; }
+    }
+    float *o = ab + (size_t)f * 2 * dim;
+    if (lane < dim) { o[lane] = a0; o[dim + lane] = b0; }
+    if (lane + 32 < dim) { o[lane + 32] = a1; o[dim + lane + 32] = b1; }
+    if (lane == 0) cnt[f] = (float)c;
+    __syncwarp();
+  }
+}
+
+// stats per speaker (doubles): beta | K[D][D+1] | G[D][NP], NP = (D+1)(D+2)/2 (row-major lower triangle)
+template <int NIJ>
+__global__ void __launch_bounds__(ANT)
+fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab, const float *__restrict__ cnt, int dim,
+                   const int64_t *__restrict__ frame_off, const int32_t *__restrict__ spk_utt_off, const int32_t *__restrict__ spk_utts,
+                   int n_dtile, int n_split, double *__restrict__ stats, int64_t stats_stride) {
+  __shared__ __align__(16) double s_xp[FB][66];
+  __shared__ __align__(16) double s_b[FB][DT], s_a[FB][DT];
+  __shared__ float s_c[FB];
+  const int t = threadIdx.x;
+  const int D1 = dim + 1, NP = D1 * (D1 + 1) / 2;
+  int bid = blockIdx.x;
+  const int split = bid % n_split; bid /= n_split;
+  const int dtile = bid % n_dtile;
+  const int spk = bid / n_dtile;
+  const int d0 = dtile * DT;
+  int pi[NIJ], pj[NIJ];
+#pragma unroll
+  for (int k = 0; k < NIJ; k++) {
+    const int ij = t + k * ANT;
+    int i = (int)((sqrtf(8.0f * (float)ij + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= ij) i++;
+    while (i * (i + 1) / 2 > ij) i--;
+    pi[k] = ij < NP ? i : 0;
+    pj[k] = ij < NP ? ij - i * (i + 1) / 2 : 0;
+  }
+  double g[NIJ][DT];
+#pragma unroll
+  for (int k = 0; k < NIJ; k++)
+#pragma unroll
+    for (int d = 0; d < DT; d++) g[k][d] = 0.0;
+  double kacc[2] = {0.0, 0.0};
+  const int kd0 = t / D1, kj0 = t - kd0 * D1, kd1 = (t + ANT) / D1, kj1 = (t + ANT) - kd1 * D1;
+  const bool k0ok = t < DT * D1, k1ok = t + ANT < DT * D1;
+  double beta = 0.0;
+  int batch = 0;
+  for (int ui = spk_utt_off[spk]; ui < spk_utt_off[spk + 1]; ui++) {
+    const int u = spk_utts[ui];
+    const int64_t f0 = frame_off[u], f1 = frame_off[u + 1];
+    for (int64_t fb = f0; fb < f1; fb += FB, batch++) {
+      if (batch % n_split != split) continue;
+      const int n = (int)min((int64_t)FB, f1 - fb);
+      __syncthreads();
+      for (int i = t; i < n * D1; i += ANT) {
+        const int f = i / D1, j = i - f * D1;
+        s_xp[f][j] = j < dim ? (double)feats[(fb + f) * dim + j] : 1.0;
+      }
+      for (int i = t; i < n * DT; i += ANT) {
+        const int f = i / DT, d = i - f * DT;
+        const bool ok = d0 + d < dim && cnt[fb + f] != 0.0f;
+        s_a[f][d] = ok ? (double)ab[(size_t)(fb + f) * 2 * dim + d0 + d] : 0.0;
+        s_b[f][d] = ok ? (double)ab[(size_t)(fb + f) * 2 * dim + dim + d0 + d] : 0.0;
+      }
+      if (t < n) s_c[t] = cnt[fb + t];
+      __syncthreads();
+      for (int f = 0; f < n; f++) {
+        if (s_c[f] == 0.0f) continue;   // dropped frame (weight 0): Kaldi never sees it
+        double b[DT];
+#pragma unroll
+        for (int d = 0; d < DT; d += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_b[f][d]); b[d] = v.x; b[d + 1] = v.y; }
+#pragma unroll
+        for (int k = 0; k < NIJ; k++) {
+          const double z = s_xp[f][pi[k]] * s_xp[f][pj[k]];
+#pragma unroll
+          for (int d = 0; d < DT; d++) g[k][d] += b[d] * z;
+        }
+        if (k0ok) kacc[0] += s_a[f][kd0] * s_xp[f][kj0];
+        if (k1ok) kacc[1] += s_a[f][kd1] * s_xp[f][kj1];
+        if (t == 0) beta += (double)s_c[f];
+      }
+    }
+  }
+  double *st = stats + (size_t)spk * stats_stride;
+  double *K = st + 1, *G = K + (size_t)dim * D1;
+#pragma unroll
+  for (int k = 0; k < NIJ; k++) {
+    const int ij = t + k * ANT;
+    if (ij >= NP) continue;
+#pragma unroll
+    for (int d = 0; d < DT; d++)
+      if (d0 + d < dim && g[k][d] != 0.0) atomicAdd(&G[(size_t)(d0 + d) * NP + ij], g[k][d]);
+  }
+  if (k0ok && d0 + kd0 < dim && kacc[0] != 0.0) atomicAdd(&K[(size_t)(d0 + kd0) * D1 + kj0], kacc[0]);
+  if (k1ok && d0 + kd1 < dim && kacc[1] != 0.0) atomicAdd(&K[(size_t)(d0 + kd1) * D1 + kj1], kacc[1]);
+  if (t == 0 && dtile == 0 && beta != 0.0) atomicAdd(&st[0], beta);
+}
+}  // namespace
+
+extern "C" int64_t mfa_fmllr_stats_size(int32_t dim) {
+  const int64_t D1 = dim + 1;
+  return 1 + (int64_t)dim * D1 + (int64_t)dim * (D1 * (D1 + 1) / 2);
+}
+
+namespace mfa {
+int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d_feats, const int32_t *d_ali, const float *d_tid_weight,
+                     const int64_t *d_frame_off, const int64_t *h_frame_off, const int32_t *h_utt2spk, int32_t n_utts, int32_t n_spk,
+                     double *d_stats) {
+  const int dim = ms->dim;
+  if (mp->dim != dim || mp->num_gauss != ms->num_gauss || mp->num_pdfs != ms->num_pdfs || mp->h_pdf_off != ms->h_pdf_off)
+    return set_error(MFA_ERR_INVALID, "fMLLR: the posterior model and the statistics model must share one Gaussian layout");
+  if (dim > 64) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: dim > 64");
+  for (int p = 0; p < ms->num_pdfs; p++)
+    if (ms->h_pdf_off[p + 1] - ms->h_pdf_off[p] > MFA_TILE_N) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: pdf with more than 128 components");
+  const int64_t n_frames = h_frame_off[n_utts];
+  if (n_frames == 0 || n_spk == 0) return MFA_OK;
+  std::vector<int32_t> off(n_spk + 1, 0), utts(n_utts);
+  for (int u = 0; u < n_utts; u++) { const int s = h_utt2spk[u]; if (s < 0 || s >= n_spk) return set_error(MFA_ERR_INVALID, "utt2spk out of range"); off[s + 1]++; }
+  for (int s = 0; s < n_spk; s++) off[s + 1] += off[s];
+  { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int u = 0; u < n_utts; u++) utts[cur[h_utt2spk[u]]++] = u; }
+  int32_t *d_off, *d_utts; float *d_ab;
+  MFA_TRY(e->upload(DB_SPK_UTT_OFF, off.data(), off.size(), &d_off));
+  MFA_TRY(e->upload(DB_SPK_UTTS, utts.data(), utts.size(), &d_utts));
+  MFA_TRY(e->getT<float>(DB_FM_AUX, (size_t)n_frames * (2 * dim + 1), &d_ab));
+  float *d_cnt = d_ab + (size_t)n_frames * 2 * dim;
+  int64_t blocks = (n_frames + FW - 1) / FW;
+  blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * 16);
+  fmllr_frame_kernel<<<(unsigned)blocks, FW * 32, 0, e->stream>>>(d_feats, d_ali, n_frames, dim, ms->num_tids, ms->d_pdf_off, ms->d_tid2pdf,
+                                                                   d_tid_weight, mp->d_gconsts, mp->d_miv, mp->d_iv, ms->d_miv, ms->d_iv, d_ab, d_cnt);
+  const int n_dtile = (dim + DT - 1) / DT;
+  int n_split = (int)std::max<int64_t>(1, std::min<int64_t>(64, ((int64_t)e->sm_count * 4 + (int64_t)n_spk * n_dtile - 1) / ((int64_t)n_spk * n_dtile)));
+  const int64_t grid = (int64_t)n_spk * n_dtile * n_split;
+  const int NP = (dim + 1) * (dim + 2) / 2;
+  const int64_t stride = mfa_fmllr_stats_size(dim);
+  if (NP <= 4 * ANT)
+    fmllr_accum_kernel<4><<<(unsigned)grid, ANT, 0, e->stream>>>(d_feats, d_ab, d_cnt, dim, d_frame_off, d_off, d_utts, n_dtile, n_split, d_stats, stride);
+  else
+    fmllr_accum_kernel<9><<<(unsigned)grid, ANT, 0, e->stream>>>(d_feats, d_ab, d_cnt, dim, d_frame_off, d_off, d_utts, n_dtile, n_split, d_stats, stride);
+  e->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return MFA_OK;
+}
+}  // namespace mfa

@@ -394,6 +394,127 @@ using namespace mfa;
 struct mfa_graph_compiler { GraphCompiler c; };
 struct mfa_fst_batch { FstBatch b; };
 
+// ---- a11: equal alignment ----------------------------------------------------------------------------------------------
+// MonoAlignEqualFunction (acoustic_modeling/monophone.py:63-139) -> kalpy gmm_align_equal -> Kaldi EqualAlign
+// (fstext/fstext-utils-inl.h) + GetLinearSymbolSequence: a random start-to-final path without self-loops (uniform choice among
+// the out-arcs and, on a final state, "stop"; self-loop draws are re-drawn), retried while it has more input labels than
+// frames; the missing frames are spread over the path's self-loops, the first `extra % loops` of them getting one more.
+// Kaldi draws with srand(seed) / rand(); glibc's TYPE_3 additive-feedback generator is restated here so the batch can run
+// re-entrantly (tests/test_host_logic.py checks it against libc).
+namespace {
+struct GlibcRand {
+  int32_t r[34];
+  uint32_t ring[31];
+  int pos = 0;
+  explicit GlibcRand(uint32_t seed) {
+    if (seed == 0) seed = 1;
+    r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+      int64_t v = (16807LL * r[i - 1]) % 2147483647LL;
+      if (v < 0) v += 2147483647LL;
+      r[i] = (int32_t)v;
+    }
+    uint32_t st[344];
+    for (int i = 0; i < 31; i++) st[i] = (uint32_t)r[i];
+    for (int i = 31; i < 34; i++) st[i] = st[i - 31];
+    for (int i = 34; i < 344; i++) st[i] = st[i - 31] + st[i - 3];
+    for (int i = 0; i < 31; i++) ring[i] = st[313 + i];   // the last 31 values; ring[k] = st[313 + k]
+    pos = 0;
+  }
+  int next() {   // value i = value[i-31] + value[i-3]
+    const uint32_t v = ring[pos] + ring[(pos + 28) % 31];
+    ring[pos] = v;
+    pos = (pos + 1) % 31;
+    return (int)(v >> 1);
+  }
+  int rand_int(int lo, int hi) { return lo == hi ? lo : lo + next() % (hi - lo + 1); }   // kaldi::RandInt
+};
+}  // namespace
+
+extern "C" int mfa_rand_sequence(uint32_t seed, int32_t n, int32_t *out) {
+  if (n < 0 || (n && !out)) return set_error(MFA_ERR_INVALID, "bad argument");
+  GlibcRand g(seed);
+  for (int i = 0; i < n; i++) out[i] = g.next();
+  return MFA_OK;
+}
+
+extern "C" int mfa_equal_align(const mfa_fst_batch *fb, const int64_t *frame_off, const uint32_t *seeds, int32_t num_retries, int32_t *ali,
+                               int32_t *words, const int64_t *word_off, int32_t *num_words, int32_t *status) {
+  if (!fb || !frame_off || !seeds || !ali || !status) return set_error(MFA_ERR_INVALID, "null argument");
+  const FstBatch &b = fb->b;
+  if (num_retries <= 0) num_retries = 10;
+  for (int u = 0; u < b.n(); u++) {
+    const int64_t T = frame_off[u + 1] - frame_off[u];
+    const int ns = (int)(b.state_off[u + 1] - b.state_off[u]);
+    const int64_t a0 = b.arc_off[u], a1 = b.arc_off[u + 1];
+    if (num_words) num_words[u] = 0;
+    if (T <= 0) { status[u] = MFA_ALIGN_ZERO_FRAMES; continue; }
+    if (b.start[u] < 0 || ns == 0) { status[u] = MFA_ALIGN_EMPTY_GRAPH; continue; }
+    // out-arcs per state, in the batch's (= OpenFst's) order
+    std::vector<int> first(ns + 1, 0);
+    for (int64_t a = a0; a < a1; a++) first[b.src[a] + 1]++;
+    for (int s = 0; s < ns; s++) first[s + 1] += first[s];
+    std::vector<int64_t> arcs(a1 - a0);
+    { std::vector<int> cur(first.begin(), first.end() - 1); for (int64_t a = a0; a < a1; a++) arcs[cur[b.src[a]]++] = a; }
+    const float *fin = &b.finals[b.state_off[u]];
+    GlibcRand rng(seeds[u]);
+    std::vector<int> path;
+    std::vector<int64_t> taken;
+    int64_t n_il = 0;
+    int retry = 0;
+    bool stuck = false;
+    do {
+      n_il = 0; taken.clear(); path.clear(); path.push_back(b.start[u]);
+      int64_t guard = 0;
+      for (;;) {
+        const int s = path.back();
+        const int na = first[s + 1] - first[s];
+        const int tot = na + (fin[s] < kInf ? 1 : 0);
+        if (tot == 0 || ++guard > (int64_t)50000000) { stuck = true; break; }   // dead end: Kaldi asserts co-accessibility
+        const int off = rng.rand_int(0, tot - 1);
+        if (off >= na) break;   // chose the final weight
+        const int64_t a = arcs[first[s] + off];
+        if (b.dst[a] == s) continue;   // self-loops are not taken here
+        taken.push_back(a); path.push_back(b.dst[a]);
+        if (b.il[a] != 0) n_il++;
+      }
+    } while (!stuck && ++retry < num_retries && n_il > T);
+    if (stuck || n_il > T) { status[u] = MFA_ALIGN_NO_FINAL; continue; }
+    std::vector<int64_t> loop(path.size(), -1);
+    int64_t n_loops = 0;
+    for (size_t i = 0; i < path.size(); i++) {
+      const int s = path[i];
+      for (int k = first[s]; k < first[s + 1]; k++)
+        if (b.dst[arcs[k]] == s && b.il[arcs[k]] != 0) { loop[i] = arcs[k]; n_loops++; break; }
+    }
+    if (n_loops == 0 && n_il < T) { status[u] = MFA_ALIGN_NO_FINAL; continue; }
+    const int64_t extra = T - n_il;
+    const int64_t min_loops = extra != 0 ? extra / n_loops : 0;
+    const int64_t one_more = extra - min_loops * n_loops;
+    int64_t counter = 0, t = 0, nw = 0;
+    const int64_t wcap = word_off ? word_off[u + 1] - word_off[u] : 0;
+    int32_t *out = ali + frame_off[u];
+    bool overflow = false;
+    auto emit = [&](int64_t a) {
+      if (b.il[a] != 0) { if (t < T) out[t] = b.il[a]; t++; }
+      if (b.ol[a] != 0) { if (words && nw < wcap) words[word_off[u] + nw] = b.ol[a]; else if (words) overflow = true; nw++; }
+    };
+    for (size_t i = 0; i < path.size(); i++) {
+      if (loop[i] >= 0) {
+        const int64_t k = min_loops + (counter < one_more ? 1 : 0);
+        counter++;
+        for (int64_t j = 0; j < k; j++) emit(loop[i]);
+      }
+      if (i + 1 < path.size()) emit(taken[i]);
+    }
+    if (t != T) return set_error(MFA_ERR_GRAPH, "equal alignment length mismatch");
+    if (overflow) return set_error(MFA_ERR_INVALID, "word buffer too small for the equal-alignment path");
+    if (num_words) num_words[u] = (int32_t)nw;
+    status[u] = MFA_ALIGN_OK;
+  }
+  return MFA_OK;
+}
+
 extern "C" {
 
 int mfa_graph_compiler_create(const mfa_hmm_desc *h, const mfa_lexicon_desc *l, mfa_graph_compiler **out) {

@@ -471,4 +471,26 @@ int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const int32_t
   return MFA_OK;
 }
 
+int mfa_fmllr_acc(mfa_engine *e, mfa_model *post_model, mfa_model *m, const float *feats, const int32_t *ali, const float *tid_weight,
+                  const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts, int32_t n_spk, double *stats, int where) {
+  if (!e || !m || !frame_off || !utt2spk || !stats || n_utts < 0 || n_spk < 0) return set_error(MFA_ERR_INVALID, "bad argument");
+  if (!post_model) post_model = m;
+  CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
+  MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
+  const int64_t nf = frame_off[n_utts];
+  int64_t *d_fo; const float *d_feats; const int32_t *d_ali; float *d_tw = nullptr; double *d_stats;
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  if (tid_weight) MFA_TRY(e->upload(DB_SCRATCH, tid_weight, (size_t)m->num_tids + 1, &d_tw));
+  MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)nf * m->dim, where, &d_feats));
+  MFA_TRY(to_device(e, DB_IO_ALI, ali, (size_t)nf, where, &d_ali));
+  const size_t ns = (size_t)n_spk * (size_t)mfa_fmllr_stats_size(m->dim);
+  MFA_TRY(out_buffer(e, DB_FM_STATS, stats, ns, where, &d_stats));
+  CUDA_TRY(cudaMemsetAsync(d_stats, 0, ns * sizeof(double), e->stream));
+  MFA_TRY(launch_fmllr_acc(e, post_model, m, d_feats, d_ali, d_tw, d_fo, frame_off, utt2spk, n_utts, n_spk, d_stats));
+  MFA_TRY(from_device(e, d_stats, stats, ns, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
 }  // extern "C"

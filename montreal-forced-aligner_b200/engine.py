@@ -264,6 +264,32 @@ class DeviceModel:
         assert where == w2
         L.check(L.lib().mfa_acc_stats(self.engine._h, self._h, fp, ap, C.c_int64(feats.shape[0]), C.c_int(where)))
 
+    # ---- K5
+    def fmllr_stats_size(self) -> int:
+        return int(L.lib().mfa_fmllr_stats_size(C.c_int32(self.dim)))
+
+    def fmllr_acc(self, feats, ali, frame_off, utt2spk, n_spk: int, tid_weight=None, post_model: Optional["DeviceModel"] = None):
+        """Per-speaker fMLLR statistics (mfa_fmllr_acc): [n_spk, 1 + D(D+1) + D(D+1)(D+2)/2] f64 (numpy in -> numpy out, torch in -> torch out)."""
+        k, fp, where = _buf(feats, np.float32, "feats")
+        k2, ap, w2 = _buf(ali, np.int32, "ali")
+        assert where == w2
+        fo, fop = _host(frame_off, np.int64)
+        us, usp = _host(utt2spk, np.int32)
+        twp = None
+        if tid_weight is not None:
+            tw, twp = _host(tid_weight, np.float32)
+            assert tw.shape[0] == self.num_tids + 1
+        n = self.fmllr_stats_size()
+        if where == L.MFA_DEVICE:
+            import torch
+            stats = torch.zeros((n_spk, n), dtype=torch.float64, device=feats.device)
+        else:
+            stats = np.zeros((n_spk, n), dtype=np.float64)
+        k3, sp, _ = _buf(stats, np.float64, "stats")
+        L.check(L.lib().mfa_fmllr_acc(self.engine._h, post_model._h if post_model is not None else None, self._h, fp, ap, twp, fop, usp,
+                                      C.c_int32(fo.shape[0] - 1), C.c_int32(n_spk), sp, C.c_int(where)))
+        return stats
+
     def acc_device_ptr(self) -> int:
         return int(L.lib().mfa_acc_device_ptr(self.engine._h, self._h) or 0)
 
@@ -361,6 +387,21 @@ class FstBatch:
             out.append(Fst(int(start[u]), int(so[u + 1] - so[u]), src[a:b].copy(), il[a:b].copy(), ol[a:b].copy(), dst[a:b].copy(),
                            w[a:b].copy(), finals[so[u]:so[u + 1]].copy()))
         return out
+
+    def equal_align(self, frame_off, seeds, num_retries: int = 10, olabel_counts: Optional[np.ndarray] = None):
+        """a11: Kaldi EqualAlign per graph (mfa_equal_align, host).  -> (ali[sum T], words, word_off, num_words, status)."""
+        n = self.sizes()[0]
+        fo, fop = _host(frame_off, np.int64)
+        sd, sdp = _host(np.asarray(seeds, np.uint64) & 0xFFFFFFFF, np.uint32)
+        if olabel_counts is None:   # a self-loop-free path of an acyclic training graph crosses each word arc at most once
+            olabel_counts = np.asarray([int(np.count_nonzero(f.arc_olabel)) for f in self.export()], np.int64)
+        wo = np.zeros(n + 1, np.int64)
+        wo[1:] = np.cumsum(olabel_counts)
+        ali = np.zeros(max(int(fo[-1]), 1), np.int32)
+        words = np.zeros(max(int(wo[-1]), 1), np.int32)
+        nw, st = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        L.check(L.lib().mfa_equal_align(self._h, fop, sdp, C.c_int32(num_retries), *[a.ctypes.data_as(C.c_void_p) for a in (ali, words, wo, nw, st)]))
+        return ali[:int(fo[-1])], words, wo, nw[:n], st[:n]
 
     def close(self):
         if self._h:

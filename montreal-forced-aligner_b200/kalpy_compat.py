@@ -423,6 +423,40 @@ class AlignmentArchive:
         pass
 
 
+def string_hash(key: str) -> int:
+    """Kaldi StringHasher (util/stl-utils.h): the srand() seed align-equal-compiled derives from the utterance id."""
+    h = 0
+    for ch in key.encode("utf8"):
+        h = (h * 7853 + ch) & 0xFFFFFFFFFFFFFFFF
+    return h & 0xFFFFFFFF
+
+
+def gmm_align_equal_batch(keys: Sequence[str], fsts: Sequence[K.Fst], num_frames: Sequence[int], seeds: Optional[Sequence[int]] = None,
+                          num_retries: int = 10) -> List[Optional[Tuple[List[int], List[int]]]]:
+    """Equal alignment of a batch of training graphs (mfa_equal_align).  None where Kaldi's EqualAlign fails."""
+    batch = E.FstBatch.from_fsts(list(fsts))
+    fo = np.zeros(len(fsts) + 1, np.int64)
+    fo[1:] = np.cumsum(np.asarray(num_frames, np.int64))
+    if seeds is None:
+        seeds = [string_hash(k if k is not None else "") for k in keys]
+    counts = np.asarray([int(np.count_nonzero(f.arc_olabel)) for f in fsts], np.int64)
+    ali, words, wo, nw, st = batch.equal_align(fo, seeds, num_retries, counts)
+    batch.close()
+    out = []
+    for u in range(len(fsts)):
+        if st[u] != 0:
+            out.append(None)
+        else:
+            out.append(([int(x) for x in ali[fo[u]:fo[u + 1]]], [int(x) for x in words[wo[u]:wo[u] + nw[u]]]))
+    return out
+
+
+def gmm_align_equal(decode_fst: K.Fst, feats: np.ndarray, utterance_id: Optional[str] = None):
+    """kalpy.gmm.align.gmm_align_equal (acoustic_modeling/monophone.py:108): -> (alignment, words) or (None, None)."""
+    r = gmm_align_equal_batch([utterance_id], [decode_fst], [feats.shape[0]])[0]
+    return (None, None) if r is None else r
+
+
 # ------------------------------------------------------------------------------------------------ statistics
 class GmmStatsAccumulator:
     """kalpy.gmm.train.GmmStatsAccumulator (alignment/multiprocessing.py:652-666; acoustic_modeling/monophone.py:84,114-120)."""
@@ -451,6 +485,10 @@ class GmmStatsAccumulator:
                 callback(len(ks))
         self.sync()
 
+    def accumulate_batch(self, feats: np.ndarray, ali: np.ndarray):
+        """AccumAmDiagGmm.acc_stats + TransitionModel.acc_stats for concatenated utterances (acoustic_modeling/monophone.py:114-120)."""
+        self._dm.acc_stats(np.ascontiguousarray(feats, np.float32), np.ascontiguousarray(ali, np.int32))
+
     def device_tensor(self):
         """f64 device view of the accumulator block, for torch.distributed.all_reduce (NCCL)."""
         return self._dm.acc_tensor()
@@ -459,3 +497,22 @@ class GmmStatsAccumulator:
         d = self._dm.acc_read()
         self.gmm_accs = AccumAmDiagGmm.from_dict(d)
         self.transition_accs = np.array(d["trans"], dtype=np.float64)
+
+
+from .fmllr import FmllrComputer, compose_transforms  # noqa: E402  (kalpy exposes FmllrComputer next to the aligner classes)
+
+
+class MatrixArchive:
+    """kalpy.util MatrixArchive (corpus/features.py:494,531): speaker -> float matrix (trans.ark / trans.scp)."""
+
+    def __init__(self, file_name):
+        self._m = {k: np.asarray(v, np.float32) for k, v in _read_table(file_name, "matrix").items()}
+
+    def __getitem__(self, key):
+        return self._m[str(key)]
+
+    def __contains__(self, key):
+        return str(key) in self._m
+
+    def __iter__(self):
+        return iter(self._m.items())

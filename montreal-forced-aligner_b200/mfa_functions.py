@@ -6,6 +6,8 @@ Mirrors (same names, argument meaning, files written, callback protocol, error b
   CompileTrainGraphsFunction   montreal_forced_aligner/alignment/multiprocessing.py:386-574 (row a6)
   AlignFunction                montreal_forced_aligner/alignment/multiprocessing.py:668-863 (row a7)
   AccStatsFunction             montreal_forced_aligner/alignment/multiprocessing.py:576-666 (row a9)
+  MonoAlignEqualFunction       montreal_forced_aligner/acoustic_modeling/monophone.py:40-139 (row a11)
+  CalcFmllrFunction            montreal_forced_aligner/corpus/features.py:423-548          (row N2)
 and of the drivers calc_cmvn (corpus/acoustic_corpus.py:1315-1367, row a3), AlignMixin.align_utterances
 (alignment/mixins.py:282-380, row a8) and AcousticModelTrainingMixin.acc_stats (acoustic_modeling/base.py:277-338 upstream,
 row a10).  The reference pulls utterances from its database; here a ``Job`` carries them explicitly (the DB is out of scope).
@@ -399,6 +401,131 @@ def acc_stats(jobs: Sequence[Job], working_directory, iteration: int, mixup: int
     K.write_gmm_model(wd / f"{iteration + 1}.mdl", tm, new_am)
     avg = gacc.tot_like / max(gacc.tot_frames, 1.0)
     return avg, impr, gacc.tot_frames
+
+
+# ------------------------------------------------------------------------------------------------ a11: equal alignment (mono iteration 0)
+@dataclass
+class MonoAlignEqualArguments(MfaArguments):
+    working_directory: Path
+    model_path: Path
+
+
+class MonoAlignEqualFunction(KaldiFunction):
+    """acoustic_modeling/monophone.py:40-139: equal alignment of every utterance through its training graph (Kaldi
+    align-equal-compiled), ali.D.J.ark written, statistics of the flat-start model accumulated on those alignments.  Progress
+    callbacks are utterance ids; the payload is (transition_accs, gmm_accs)."""
+
+    def __init__(self, args: MonoAlignEqualArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        wd = Path(self.a.working_directory)
+        for did in self.job.dictionary_ids:
+            acc = KC.GmmStatsAccumulator(self.a.model_path)
+            feat_path = self.job.construct_path(self.job.split_directory, "feats", "scp", did)
+            if not feat_path.exists():
+                feat_path = self.job.construct_path(self.job.split_directory, "feats", "scp")
+            feats = KC.FeatureArchive(feat_path, deltas=True)   # monophone.py:96-99: deltas only, CMVN already applied (a4)
+            graphs = KC.FstArchive(self.job.construct_path(wd, "fsts", "ark", did))
+            keys = [k for k in graphs.keys() if k in set(feats.keys)]
+            with K.ArkWriter(self.job.construct_path(wd, "ali", "ark", did)) as w:
+                B = 512
+                for i in range(0, len(keys), B):
+                    ks = keys[i:i + B]
+                    x, fo = feats.batch(ks)
+                    fsts = [graphs[k] for k in ks]
+                    res = KC.gmm_align_equal_batch(ks, fsts, np.diff(fo))
+                    ali = np.zeros(int(fo[-1]), np.int32)
+                    for j, (k, r) in enumerate(zip(ks, res)):
+                        if r is None or len(r[0]) == 0:   # monophone.py:100-113: zero-length / empty graph / failed -> error, skipped
+                            continue
+                        ali[fo[j]:fo[j + 1]] = r[0]
+                        w.write_int_vector(k, np.asarray(r[0], np.int32))
+                        self.callback(k)
+                    acc.accumulate_batch(x, ali)   # frames of skipped utterances carry tid 0 and are ignored by K4
+            acc.sync()
+            self.callback((acc.transition_accs, acc.gmm_accs))
+
+
+def mono_align_equal(jobs: Sequence[Job], working_directory, all_reduce: Optional[Callable[[np.ndarray], np.ndarray]] = None,
+                     mixup: int = 0, power: float = 0.25):
+    """MonophoneTrainer.mono_align_equal (acoustic_modeling/monophone.py:237-296): equal alignments + statistics with 0.mdl, then the
+    first MLE update (min_gaussian_occupancy 3, mix-up to `mixup` = current_gaussians) -> 1.mdl.
+    Returns (avg log-likelihood per frame, frames)."""
+    wd = Path(working_directory)
+    model_path = wd / "0.mdl"
+    tm, am = K.read_gmm_model(model_path)
+    trans = tm.InitStats()
+    gacc = AccumAmDiagGmm.init(am)
+    args = [MonoAlignEqualArguments(j.id, j, None, wd, model_path) for j in jobs]
+    for r in run_kaldi_function(MonoAlignEqualFunction, args):
+        if isinstance(r, tuple):
+            trans += r[0]
+            gacc.Add(1.0, r[1])
+    if all_reduce is not None:
+        flat = all_reduce(np.concatenate([gacc.occ, gacc.mean.ravel(), gacc.var.ravel(), trans, [gacc.tot_like, gacc.tot_frames]]))
+        G, D = am.NumGauss(), am.dim
+        gacc.occ = flat[:G]; gacc.mean = flat[G:G + G * D].reshape(G, D); gacc.var = flat[G + G * D:G + 2 * G * D].reshape(G, D)
+        trans = flat[G + 2 * G * D:G + 2 * G * D + tm.num_tids + 1]
+        gacc.tot_like, gacc.tot_frames = float(flat[-2]), float(flat[-1])
+    tm.mle_update(trans)
+    new_am, _impr, _count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=3.0)   # monophone.py:279-284
+    K.write_gmm_model(wd / "1.mdl", tm, new_am)
+    return gacc.tot_like / max(gacc.tot_frames, 1.0), gacc.tot_frames
+
+
+# ------------------------------------------------------------------------------------------------ N2: fMLLR between the passes
+@dataclass
+class CalcFmllrArguments(MfaArguments):
+    working_directory: Path
+    ali_model_path: Path
+    model_path: Path
+    fmllr_options: MetaDict
+    silence_phone_ids: Sequence[int] = ()
+
+
+class CalcFmllrFunction(KaldiFunction):
+    """corpus/features.py:423-548: per dictionary, speaker transforms from the job's alignments (two-model when ali_model_path is
+    the .alimdl), composed with previous transforms when trans.D.J.scp exists, written to trans.D.J.ark/.scp in the split directory
+    (where Job.construct_feature_archive picks them up for the second pass).  callback: (speaker, objf improvement, count)."""
+
+    def __init__(self, args: CalcFmllrArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        wd = Path(self.a.working_directory)
+        for did in self.job.dictionary_ids:
+            ali_path = self.job.construct_path(wd, "ali", "ark", did)
+            if not ali_path.exists():
+                continue
+            trans_scp = self.job.construct_path(self.job.split_directory, "trans", "scp", did)
+            previous = KC.MatrixArchive(trans_scp) if trans_scp.exists() else None
+            spk2utt: Dict[str, List[str]] = {}
+            for u in self.job.utts(did):
+                spk2utt.setdefault(str(u.speaker_id), []).append(u.kaldi_id)
+            feats = self.job.construct_feature_archive(wd, did)
+            computer = KC.FmllrComputer(self.a.ali_model_path, self.a.model_path, list(self.a.silence_phone_ids), spk2utt=spk2utt,
+                                        **self.a.fmllr_options)
+            alis = KC.AlignmentArchive(ali_path)
+            tmp = self.job.construct_path(wd, "trans", "ark", did)
+            out = computer.export_transforms(tmp, feats, alis, previous_transform_archive=previous, callback=self.callback)
+            feats.close()
+            final_ark = self.job.construct_path(self.job.split_directory, "trans", "ark", did)
+            with K.ArkWriter(final_ark, trans_scp) as w:   # features.py:536-546: rewritten with an scp next to it
+                for s, m in out.items():
+                    w.write_matrix(str(s), np.asarray(m, np.float32))
+            tmp.unlink()
+
+
+def calc_fmllr(jobs: Sequence[Job], working_directory, ali_model_path, model_path, fmllr_options: Optional[MetaDict] = None,
+               silence_phone_ids: Sequence[int] = ()):
+    """AcousticCorpusMixin.calc_fmllr (corpus/acoustic_corpus.py:1370-1419).  Returns {speaker: (improvement, count)}."""
+    opts = dict(fmllr_update_type="full", silence_weight=0.0, acoustic_scale=0.1)
+    opts.update(fmllr_options or {})
+    args = [CalcFmllrArguments(j.id, j, None, Path(working_directory), Path(ali_model_path), Path(model_path), opts, silence_phone_ids) for j in jobs]
+    return {s: (impr, count) for s, impr, count in run_kaldi_function(CalcFmllrFunction, args)}
 
 
 # ------------------------------------------------------------------------------------------------ online path (section 3.2)

@@ -4,7 +4,8 @@
  * Scalar CPU restatement of the algorithms MFA's alignment hot path executes inside the
  * un-vendored third-party dependency kalpy 0.6.7 / Kaldi (not present under /root/reference):
  *   MFCC+CMVN -> deltas | splice+LDA -> fMLLR -> diagonal-GMM log-likelihoods -> FasterDecoder
- *   Viterbi with AlignUtteranceWrapper's retry -> GMM accumulator statistics.
+ *   Viterbi with AlignUtteranceWrapper's retry -> GMM accumulator statistics; plus EqualAlign (monophone
+ *   iteration 0) and fMLLR estimation (statistics + row-by-row update) between the two alignment passes.
  *
  * PARITY UNPINNED: the reference's tests hold no numeric golden vectors for this path and kalpy
  * cannot be installed offline, so this restatement follows the published Kaldi algorithms
@@ -615,6 +616,227 @@ ORC_API void orc_acc_stats(const orc_gmm *g, const int32_t *tid2pdf, const float
   }
   *tot_like += like;
   free(x2);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Equal alignment.  Call site: acoustic_modeling/monophone.py:108 (MonoAlignEqualFunction ->
+ * kalpy gmm_align_equal).  Restates Kaldi fstext/fstext-utils-inl.h EqualAlign (random self-loop-free
+ * path drawn with srand(seed)/rand() through kaldi::RandInt, retried while it has more input labels
+ * than frames; extra frames spread over the path's self-loops, the first (extra % loops) of them get
+ * one more) followed by GetLinearSymbolSequence.  Uses libc rand() directly (single-threaded).
+ * Returns 0 ok, 2 failed, 3 empty graph, 4 zero frames.
+ * ---------------------------------------------------------------------------------------- */
+static int kaldi_rand_int(int lo, int hi) { return lo == hi ? lo : lo + rand() % (hi - lo + 1); }
+
+ORC_API int orc_equal_align(const orc_fst *fst, int64_t T, unsigned seed, int num_retries, int32_t *ali, int32_t *words,
+                            int32_t *num_words, int32_t max_words) {
+  *num_words = 0;
+  if (T <= 0) return 4;
+  if (fst->start < 0 || fst->num_states == 0) return 3;
+  srand(seed);
+  int cap = 1024, np = 0; int64_t n_il = 0;
+  int32_t *path = malloc(sizeof(int32_t) * cap), *taken = malloc(sizeof(int32_t) * cap);
+  int retry = 0;
+  do {
+    n_il = 0; np = 0; path[np++] = fst->start;
+    for (;;) {
+      int s = path[np - 1];
+      int na = fst->arc_off[s + 1] - fst->arc_off[s];
+      int tot = na + (fst->final[s] < INFINITY ? 1 : 0);
+      if (tot == 0) { free(path); free(taken); return 2; }
+      int off = kaldi_rand_int(0, tot - 1);
+      if (off >= na) break;
+      int a = fst->arc_off[s] + off;
+      if (fst->nextstate[a] == s) continue;
+      if (np == cap) { cap *= 2; path = realloc(path, sizeof(int32_t) * cap); taken = realloc(taken, sizeof(int32_t) * cap); }
+      taken[np - 1] = a; path[np++] = fst->nextstate[a];
+      if (fst->ilabel[a] != 0) n_il++;
+    }
+  } while (++retry < num_retries && n_il > T);
+  int status = 0;
+  if (n_il > T) status = 2;
+  int32_t *loop = malloc(sizeof(int32_t) * np);
+  int64_t n_loops = 0;
+  for (int i = 0; i < np && !status; i++) {
+    loop[i] = -1;
+    for (int a = fst->arc_off[path[i]]; a < fst->arc_off[path[i] + 1]; a++)
+      if (fst->nextstate[a] == path[i] && fst->ilabel[a] != 0) { loop[i] = a; n_loops++; break; }
+  }
+  if (!status && n_loops == 0 && n_il < T) status = 2;
+  if (!status) {
+    int64_t extra = T - n_il, min_loops = extra ? extra / n_loops : 0, one_more = extra - min_loops * n_loops, counter = 0, t = 0;
+    for (int i = 0; i < np; i++) {
+      if (loop[i] >= 0) {
+        int64_t k = min_loops + (counter < one_more ? 1 : 0);
+        counter++;
+        for (int64_t j = 0; j < k; j++) {
+          ali[t++] = fst->ilabel[loop[i]];
+          if (fst->olabel[loop[i]] != 0) { if (*num_words < max_words) words[*num_words] = fst->olabel[loop[i]]; (*num_words)++; }
+        }
+      }
+      if (i + 1 < np) {
+        int a = taken[i];
+        if (fst->ilabel[a] != 0) ali[t++] = fst->ilabel[a];
+        if (fst->olabel[a] != 0) { if (*num_words < max_words) words[*num_words] = fst->olabel[a]; (*num_words)++; }
+      }
+    }
+    if (t != T) status = 2;
+  }
+  free(path); free(taken); free(loop);
+  return status;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * fMLLR estimation.  Call site: corpus/features.py:460-548 (CalcFmllrFunction -> kalpy FmllrComputer.export_transforms),
+ * options corpus/features.py:759-766.  Restates Kaldi gmmbin/gmm-est-fmllr(-gpost).cc, transform/fmllr-diag-gmm.cc
+ * (FmllrDiagGmmAccs::AccumulateFromPosteriors / CommitSingleFrameStats, ComputeFmllrMatrixDiagGmmFull, FmllrInnerUpdate,
+ * FmllrAuxFuncDiagGmm) and hmm/posterior.cc WeightSilencePost.
+ *   g_post: model the component posteriors come from (the alignment model when two models are used), g: model whose
+ *   means / variances enter the statistics; both evaluated on the SAME features.  tid_weight[tid]: frame weight
+ *   (silence_weight for silence phones, else 1; weight 0 drops the frame).
+ *   stats (doubles): beta | K[D][D+1] | G[D][(D+1)(D+2)/2]  (G_d packed lower triangle, row-major: Kaldi SpMatrix).
+ * ---------------------------------------------------------------------------------------- */
+ORC_API void orc_fmllr_acc(const orc_gmm *g_post, const orc_gmm *g, const int32_t *tid2pdf, const float *tid_weight,
+                           const float *feats, const int32_t *ali, int64_t T, double *stats) {
+  const int D = g->dim, D1 = D + 1, NP = D1 * (D1 + 1) / 2;
+  double *beta = stats, *K = stats + 1, *G = K + (size_t)D * D1;
+  float comp[4096];
+  float *a = malloc(sizeof(float) * D), *b = malloc(sizeof(float) * D), *x2 = malloc(sizeof(float) * D);
+  double *xp = malloc(sizeof(double) * D1);
+  for (int64_t t = 0; t < T; t++) {
+    const int tid = ali[t];
+    const float w = tid_weight ? tid_weight[tid] : 1.0f;
+    if (w == 0.0f) continue;
+    const int pdf = tid2pdf[tid];
+    const float *x = feats + t * D;
+    for (int d = 0; d < D; d++) x2[d] = x[d] * x[d];
+    const int m0 = g_post->off[pdf], m1 = g_post->off[pdf + 1];
+    float mx = -INFINITY;
+    for (int m = m0; m < m1; m++) {
+      const float *miv = g_post->means_invvars + (size_t)m * D, *iv = g_post->inv_vars + (size_t)m * D;
+      float d1 = 0.0f, d2 = 0.0f;
+      for (int d = 0; d < D; d++) d1 += miv[d] * x[d];
+      for (int d = 0; d < D; d++) d2 += iv[d] * x2[d];
+      float v = g_post->gconsts[m] + d1; v = v + (-0.5f) * d2;
+      comp[m - m0] = v; if (v > mx) mx = v;
+    }
+    float sum = 0.0f;
+    for (int m = 0; m < m1 - m0; m++) { comp[m] = expf(comp[m] - mx); sum += comp[m]; }
+    const float inv = 1.0f / sum;
+    double count = 0.0;
+    for (int d = 0; d < D; d++) { a[d] = 0.0f; b[d] = 0.0f; }
+    for (int m = 0; m < m1 - m0; m++) {
+      const float p = comp[m] * inv * w;
+      count += p;
+      const float *miv = g->means_invvars + (size_t)(m0 + m) * D, *iv = g->inv_vars + (size_t)(m0 + m) * D;
+      for (int d = 0; d < D; d++) { a[d] += miv[d] * p; b[d] += iv[d] * p; }
+    }
+    for (int d = 0; d < D; d++) xp[d] = x[d];
+    xp[D] = 1.0;
+    *beta += count;
+    for (int d = 0; d < D; d++) for (int j = 0; j < D1; j++) K[(size_t)d * D1 + j] += (double)a[d] * xp[j];
+    for (int d = 0; d < D; d++) {
+      if (b[d] == 0.0f) continue;
+      double *Gd = G + (size_t)d * NP;
+      const double bd = b[d];
+      int k = 0;
+      for (int i = 0; i < D1; i++) for (int j = 0; j <= i; j++, k++) Gd[k] += bd * (xp[i] * xp[j]);
+    }
+  }
+  free(a); free(b); free(x2); free(xp);
+}
+
+/* in-place inverse of an n x n matrix (Gauss-Jordan, partial pivoting); returns log|det| through *logdet (may be NULL); 0 ok */
+static int mat_invert(double *A, int n, double *logdet) {
+  int *piv = malloc(sizeof(int) * n);
+  double ld = 0.0; int ok = 0;
+  for (int c = 0; c < n; c++) {
+    int p = c; double best = fabs(A[c * n + c]);
+    for (int r = c + 1; r < n; r++) if (fabs(A[r * n + c]) > best) { best = fabs(A[r * n + c]); p = r; }
+    if (best == 0.0) { ok = -1; break; }
+    piv[c] = p;
+    if (p != c) for (int j = 0; j < n; j++) { double tmp = A[c * n + j]; A[c * n + j] = A[p * n + j]; A[p * n + j] = tmp; }
+    const double d = A[c * n + c];
+    ld += log(fabs(d));
+    A[c * n + c] = 1.0;
+    for (int j = 0; j < n; j++) A[c * n + j] /= d;
+    for (int r = 0; r < n; r++) {
+      if (r == c) continue;
+      const double f = A[r * n + c];
+      if (f == 0.0) continue;
+      A[r * n + c] = 0.0;
+      for (int j = 0; j < n; j++) A[r * n + j] -= f * A[c * n + j];
+    }
+  }
+  if (!ok) for (int c = n - 1; c >= 0; c--) if (piv[c] != c) for (int r = 0; r < n; r++) { double tmp = A[r * n + c]; A[r * n + c] = A[r * n + piv[c]]; A[r * n + piv[c]] = tmp; }
+  free(piv);
+  if (logdet) *logdet = ld;
+  return ok;
+}
+
+static double fmllr_auxf(const double *W, const double *stats, int D) {
+  const int D1 = D + 1, NP = D1 * (D1 + 1) / 2;
+  const double beta = stats[0], *K = stats + 1, *G = K + (size_t)D * D1;
+  double *A = malloc(sizeof(double) * D * D), ld = 0.0;
+  for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) A[i * D + j] = W[i * D1 + j];
+  mat_invert(A, D, &ld);
+  free(A);
+  double obj = beta * ld;
+  for (int i = 0; i < D * D1; i++) obj += W[i] * K[i];
+  for (int d = 0; d < D; d++) {
+    const double *Gd = G + (size_t)d * NP, *w = W + d * D1;
+    double q = 0.0;
+    for (int i = 0; i < D1; i++) {
+      double r = 0.0;
+      for (int j = 0; j < D1; j++) r += (j <= i ? Gd[i * (i + 1) / 2 + j] : Gd[j * (j + 1) / 2 + i]) * w[j];
+      q += r * w[i];
+    }
+    obj -= 0.5 * q;
+  }
+  return obj;
+}
+
+/* W: [D][D+1] float, in = starting transform (unit for gmm-est-fmllr), out = estimate.  Returns the objective improvement
+ * (0 and W untouched when beta <= min_count or the objective did not increase). */
+ORC_API double orc_fmllr_update(const double *stats, int D, int num_iters, double min_count, float *W) {
+  const int D1 = D + 1, NP = D1 * (D1 + 1) / 2;
+  const double beta = stats[0], *K = stats + 1, *G = K + (size_t)D * D1;
+  if (!(beta > min_count)) return 0.0;
+  double *invG = malloc(sizeof(double) * D * D1 * D1);
+  for (int d = 0; d < D; d++) {
+    double *M = invG + (size_t)d * D1 * D1;
+    const double *Gd = G + (size_t)d * NP;
+    for (int i = 0; i < D1; i++) for (int j = 0; j < D1; j++) M[i * D1 + j] = j <= i ? Gd[i * (i + 1) / 2 + j] : Gd[j * (j + 1) / 2 + i];
+    mat_invert(M, D1, NULL);
+  }
+  double *Wo = malloc(sizeof(double) * D * D1), *Wn = malloc(sizeof(double) * D * D1), *cof = malloc(sizeof(double) * D * D);
+  double *c = malloc(sizeof(double) * D1), *cg = malloc(sizeof(double) * D1);
+  for (int i = 0; i < D * D1; i++) Wo[i] = Wn[i] = W[i];
+  const double old_objf = (float)fmllr_auxf(Wo, stats, D);
+  for (int it = 0; it < num_iters; it++) {
+    for (int row = 0; row < D; row++) {
+      const double *iG = invG + (size_t)row * D1 * D1, *k = K + (size_t)row * D1;
+      for (int i = 0; i < D; i++) for (int j = 0; j < D; j++) cof[i * D + j] = Wn[j * D1 + i];   /* A^T */
+      mat_invert(cof, D, NULL);
+      for (int j = 0; j < D; j++) c[j] = cof[row * D + j];
+      c[D] = 0.0;
+      for (int i = 0; i < D1; i++) { double r = 0.0; for (int j = 0; j < D1; j++) r += iG[i * D1 + j] * c[j]; cg[i] = r; }
+      double e1 = 0.0, e2 = 0.0;
+      for (int i = 0; i < D1; i++) { e1 += cg[i] * c[i]; e2 += cg[i] * k[i]; }
+      const double discr = sqrt(e2 * e2 + 4 * e1 * beta);
+      const double a1 = (-e2 + discr) / (2 * e1), a2 = (-e2 - discr) / (2 * e1);
+      const double f1 = beta * log(fabs(a1 * e1 + e2)) - 0.5 * a1 * a1 * e1, f2 = beta * log(fabs(a2 * e1 + e2)) - 0.5 * a2 * a2 * e1;
+      const double alpha = f1 > f2 ? a1 : a2;
+      for (int i = 0; i < D1; i++) c[i] = alpha * c[i] + k[i];
+      for (int i = 0; i < D1; i++) { double r = 0.0; for (int j = 0; j < D1; j++) r += iG[i * D1 + j] * c[j]; Wn[row * D1 + i] = r; }
+    }
+  }
+  const double new_objf = (float)fmllr_auxf(Wn, stats, D), impr = new_objf - old_objf;
+  double ret = 0.0;
+  const int approx_equal = fabs(new_objf - old_objf) <= 0.001 * (fabs(new_objf) + fabs(old_objf));
+  if (!(impr < 0.0 && !approx_equal)) { for (int i = 0; i < D * D1; i++) W[i] = (float)Wn[i]; ret = impr; }
+  free(invG); free(Wo); free(Wn); free(cof); free(c); free(cg);
+  return ret;
 }
 
 /* sizes of the structs, so the ctypes mirror can assert it matches */

@@ -197,3 +197,41 @@ def acc_stats(g: GmmModel, tid2pdf: np.ndarray, feats: np.ndarray, ali: np.ndarr
                         _p(accs["mean"]), _p(accs["var"]), _p(accs["trans"]), _p(accs["like"]))
     accs["frames"] += int(ali.shape[0])
     return accs
+
+
+def equal_align(fst, T: int, seed: int, num_retries: int = 10, max_words: int = 4096):
+    """Kaldi EqualAlign + GetLinearSymbolSequence (libc srand/rand). Returns dict(status, ali, words)."""
+    csr = fst if isinstance(fst, FstCsr) else FstCsr(fst)
+    ali = np.zeros(max(T, 1), dtype=np.int32)
+    words = np.zeros(max_words, dtype=np.int32)
+    nw = C.c_int32(0)
+    st = lib().orc_equal_align(C.byref(csr.s), C.c_int64(T), C.c_uint(seed & 0xFFFFFFFF), C.c_int(num_retries), _p(ali), _p(words),
+                               C.byref(nw), C.c_int32(max_words))
+    return dict(status=st, ali=ali[:T], words=words[: nw.value])
+
+
+def fmllr_stats_size(D: int) -> int:
+    return 1 + D * (D + 1) + D * ((D + 1) * (D + 2) // 2)
+
+
+def fmllr_acc(g_post: GmmModel, g: GmmModel, tid2pdf: np.ndarray, tid_weight, feats: np.ndarray, ali: np.ndarray, stats=None):
+    """FmllrDiagGmmAccs accumulation for one speaker's frames: stats = beta | K[D][D+1] | G[D][packed lower triangle]."""
+    D = g.dim
+    if stats is None:
+        stats = np.zeros(fmllr_stats_size(D), dtype=np.float64)
+    feats = np.ascontiguousarray(feats, dtype=np.float32)
+    ali = np.ascontiguousarray(ali, dtype=np.int32)
+    tid2pdf = np.ascontiguousarray(tid2pdf, dtype=np.int32)
+    tw = None if tid_weight is None else np.ascontiguousarray(tid_weight, dtype=np.float32)
+    lib().orc_fmllr_acc(C.byref(g_post.s), C.byref(g.s), _p(tid2pdf), None if tw is None else _p(tw), _p(feats), _p(ali),
+                        C.c_int64(ali.shape[0]), _p(stats))
+    return stats
+
+
+def fmllr_update(stats: np.ndarray, D: int, num_iters: int = 40, min_count: float = 500.0, W0=None):
+    """ComputeFmllrMatrixDiagGmmFull from the unit transform (gmm-est-fmllr). Returns (W [D][D+1] f32, objf improvement)."""
+    lib().orc_fmllr_update.restype = C.c_double
+    W = np.ascontiguousarray(np.hstack([np.eye(D), np.zeros((D, 1))]) if W0 is None else W0, dtype=np.float32).copy()
+    stats = np.ascontiguousarray(stats, dtype=np.float64)
+    impr = lib().orc_fmllr_update(_p(stats), C.c_int(D), C.c_int(num_iters), C.c_double(min_count), _p(W))
+    return W, float(impr)

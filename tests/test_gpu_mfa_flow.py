@@ -132,3 +132,126 @@ def test_online_path_config1(tmp_path):
     # too tight a beam without retry -> AlignerError (online/alignment.py:108-112)
     with pytest.raises(MF.AlignerError):
         MF.align_utterance_online(tmp_path / "final.mdl", tmp_path / "tree", lex, ms["pcm"], ms["text"], beam=0.001, retry_beam=0.0)
+
+
+def _write_corpus(tmp_path, sc):
+    c = sc["corpus"]
+    split = tmp_path / "split"; work = tmp_path / "work"
+    split.mkdir(); work.mkdir()
+    id2w = c.lexicon.id2word
+    utts = []
+    for u in range(c.n_utts):
+        wav = tmp_path / f"u{u}.wav"
+        K.write_wav_int16(wav, c.pcm[c.sample_off[u]:c.sample_off[u + 1]])
+        utts.append(MF.Utterance(u, int(c.utt2spk[u]), str(wav), " ".join(id2w[w] for w in c.transcripts[u]),
+                                 duration=(c.sample_off[u + 1] - c.sample_off[u]) / 16000.0))
+    jobs = MF.assign_jobs(utts, 2, split)
+    mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
+    list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs]))
+    MF.calc_cmvn(jobs, split)
+    list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs]))
+    return utts, jobs, split, work
+
+
+def test_mono_align_equal_iteration_zero(tmp_path):
+    """Row a11: equal alignments through the training graphs (== the oracle's EqualAlign), ali archives written, statistics of the
+    flat-start model == the oracle's on those alignments, first update -> 1.mdl; one more align/acc-stats pass raises the likelihood."""
+    sc = build_synth_scenario(seconds=40.0, seed=23, triphone=False, n_phones=8, n_words=40, gauss_per_pdf=1, n_spk=2)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    utts, jobs, split, work = _write_corpus(tmp_path, sc)
+    # flat start (gmm-init-mono): every pdf = one Gaussian with the global mean / variance
+    feats_all = {}
+    for j in jobs:
+        fa = KC.FeatureArchive(j.construct_path(split, "feats", "scp", 1), deltas=True)
+        for k, m in fa:
+            feats_all[k] = m
+    X = np.concatenate(list(feats_all.values()))
+    mu, var = X.mean(0), X.var(0)
+    P = am.NumPdfs()
+    flat = K.AmDiagGmm(am.dim, np.arange(P + 1, dtype=np.int32), np.ones(P, np.float32), np.tile(mu / var, (P, 1)).astype(np.float32),
+                       np.tile(1.0 / var, (P, 1)).astype(np.float32))
+    K.write_gmm_model(work / "0.mdl", tm, flat)
+    K.write_tree(work / "tree", sc["tree"])
+    list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
+                               [MF.CompileTrainGraphsArguments(j.id, j, None, work, {1: c.lexicon}, work / "tree", work / "0.mdl") for j in jobs]))
+    avg0, frames = MF.mono_align_equal(jobs, work)
+    assert frames == X.shape[0] and np.isfinite(avg0)
+    g = O.GmmModel.from_am(flat)
+    accs = None
+    for j in jobs:
+        fsts = KC.FstArchive(j.construct_path(work, "fsts", "ark", 1))
+        alis = KC.AlignmentArchive(j.construct_path(work, "ali", "ark", 1))
+        for u in j.utts(1):
+            f = feats_all[u.kaldi_id]
+            r = O.equal_align(fsts[u.kaldi_id], f.shape[0], KC.string_hash(u.kaldi_id))
+            assert r["status"] == 0 and alis[u.kaldi_id].alignment == r["ali"].tolist()
+            accs = O.acc_stats(g, tm.tid2pdf, f, r["ali"], tm.num_tids, accs)
+    assert abs(avg0 - accs["like"][0] / accs["frames"]) <= 1e-5 * abs(avg0)
+    tm1, am1 = K.read_gmm_model(work / "1.mdl")
+    assert am1.NumPdfs() == P and am1.NumGauss() >= P
+    # iteration 1: Viterbi alignments with 1.mdl fit better than the equal alignments did under 0.mdl
+    opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=6, retry_beam=40, boost_silence=1.0)
+    MF.align_utterances(jobs, work, work / "1.mdl", opts)
+    avg1, _, frames1 = MF.acc_stats(jobs, work, 1)
+    assert frames1 == frames and avg1 > avg0
+
+
+def test_two_pass_sat_alignment_with_estimated_fmllr(tmp_path):
+    """Rows a12 + N2: pass 1 with the speaker-independent model, per-speaker fMLLR from those alignments (CalcFmllrFunction ->
+    trans.D.J.ark/.scp), pass 2 picks the transforms up through construct_feature_archive.  The corpus is given a per-speaker
+    affine distortion in feature space so the transforms have something to undo."""
+    sc = build_synth_scenario(seconds=90.0, seed=29, triphone=True, n_phones=8, n_words=40, gauss_per_pdf=2, n_spk=3, use_lda=True)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    utts, jobs, split, work = _write_corpus(tmp_path, sc)
+    K.write_matrix_file(work / "lda.mat", sc["lda"])
+    K.write_gmm_model(work / "final.mdl", tm, am)
+    K.write_tree(work / "tree", sc["tree"])
+    list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
+                               [MF.CompileTrainGraphsArguments(j.id, j, None, work, {1: c.lexicon}, work / "tree", work / "final.mdl") for j in jobs]))
+    opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
+    score1, fail1 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
+    sil = [c.lexicon.phone_table["sil"]]
+    res = MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil)
+    assert set(res) == {str(s) for s in range(c.n_spk)}
+    # oracle: statistics from the GPU-written final features + pass-1 alignments, per speaker, then the row update
+    g = O.GmmModel.from_am(am)
+    tw = np.where(tm.tid2phone == sil[0], np.float32(0), np.float32(1)).astype(np.float32)
+    tw[0] = 0
+    D = am.dim
+    stats = np.zeros((c.n_spk, O.fmllr_stats_size(D)))
+    base = {}
+    for j in jobs:
+        scp = {k: (p, o) for k, p, o in K.read_scp(j.construct_path(split, "feats", "scp"))}
+        alis = KC.AlignmentArchive(j.construct_path(work, "ali", "ark", 1))
+        for u in j.utts(1):
+            m = K.read_scp_object(*scp[u.kaldi_id], "matrix")
+            f = O.transform(O.splice(np.asarray(m, np.float32), 3, 3), sc["lda"])
+            base[u.kaldi_id] = f
+            if u.kaldi_id in alis:
+                O.fmllr_acc(g, g, tm.tid2pdf, tw, f, np.asarray(alis[u.kaldi_id].alignment, np.int32), stats[u.speaker_id])
+    for j in jobs:
+        tr = KC.MatrixArchive(j.construct_path(split, "trans", "scp", 1))
+        for s in sorted({u.speaker_id for u in j.utts(1)}):
+            Wo, io = O.fmllr_update(stats[s], D)
+            assert np.abs(tr[str(s)] - Wo).max() < 2e-3
+            assert abs(res[str(s)][1] - stats[s, 0]) <= 1e-4 * stats[s, 0]
+            if stats[s, 0] > 500:
+                assert res[str(s)][0] > 0
+    # pass 2: features now carry the transforms; per-utterance likelihoods are those of the oracle on transformed features
+    score2, fail2 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
+    assert fail2 <= fail1 and np.isfinite(score2)   # (the decoder's score omits the log|det A| Jacobian, so it need not rise)
+    tc = -tm.scaled_transition_log_probs(1.0, 0.1)
+    same = total = 0
+    for j in jobs:
+        tr = KC.MatrixArchive(j.construct_path(split, "trans", "scp", 1))
+        fsts = KC.FstArchive(j.construct_path(work, "fsts", "ark", 1))
+        alis = KC.AlignmentArchive(j.construct_path(work, "ali", "ark", 1))
+        for u in j.utts(1)[:6]:
+            f = O.transform(base[u.kaldi_id], tr[str(u.speaker_id)])
+            r = O.align(fsts[u.kaldi_id], tc, g, tm.tid2pdf, f, f.shape[0])
+            same += int((np.asarray(alis[u.kaldi_id].alignment) == r["ali"]).sum()); total += len(r["ali"])
+            assert abs(u.alignment_log_likelihood - r["like"]) <= 1e-4 * abs(r["like"])
+    assert same / total >= 0.999
+    # a second estimation composes on top of the first (features.py:486-495): the composed transform stays close to the first
+    res2 = MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil)
+    assert all(v[0] >= 0.0 for v in res2.values())

@@ -337,3 +337,110 @@ def test_acc_stats_parity(eng):
     got2 = dm.acc_read()
     assert np.allclose(got2["occ"], 2 * got["occ"], rtol=1e-9) and got2["frames"] == 2 * got["frames"]
     dm.close()
+
+
+def test_acc_stats_segmented_equals_atomic_kernel_and_handles_ragged_input(eng, monkeypatch):
+    """K4's two kernels (counting sort by pdf + register accumulation per item | one red per frame) on one concatenated batch:
+    integer fields identical, f64 sums equal to rounding; frames with tid 0 / out-of-range are skipped; a pdf with many
+    components and a pdf with thousands of frames (several items, one CTA reusing its staged Gaussians) are both present."""
+    rng = np.random.default_rng(3)
+    D, P = 39, 50
+    comps = rng.integers(1, 6, size=P); comps[7] = 70; comps[0] = 1
+    off = np.zeros(P + 1, np.int32); off[1:] = np.cumsum(comps)
+    G = int(off[-1])
+    means, var = rng.normal(size=(G, D)), np.exp(rng.normal(scale=0.3, size=(G, D)))
+    w = np.concatenate([rng.dirichlet(np.ones(c)) for c in comps])
+    from mfa_b200 import kaldi_io as K
+    am = K.AmDiagGmm(D, off, w.astype(np.float32), (means / var).astype(np.float32), (1.0 / var).astype(np.float32))
+    tm, _, _ = load_model("mono")
+    # a fake tid -> pdf map over the fixture's transition model: only tid2pdf matters to K4
+    tid2pdf = np.concatenate([[0], rng.integers(0, P, size=tm.num_tids)]).astype(np.int32)
+    tid2pdf[1:40] = 3                                   # many tids share a heavy pdf
+    tm.tid2pdf = tid2pdf
+    T = 20000
+    ali = rng.integers(1, tm.num_tids + 1, size=T).astype(np.int32)
+    heavy = rng.random(T) < 0.3
+    ali[heavy] = rng.integers(1, 40, size=int(heavy.sum()))
+    ali[::97] = 0
+    ali[5::1013] = tm.num_tids + 5
+    feats = rng.normal(size=(T, D)).astype(np.float32)
+    dm = E.DeviceModel(eng, tm, am)
+    res = {}
+    for impl in ("atomic", "segmented"):
+        monkeypatch.setenv("MFA_ACC_IMPL", impl)
+        dm.acc_zero()
+        dm.acc_stats(feats, ali)
+        dm.acc_stats(feats[:0], ali[:0])               # empty call is a no-op
+        res[impl] = dm.acc_read()
+    a, s = res["atomic"], res["segmented"]
+    valid = (ali > 0) & (ali <= tm.num_tids)
+    assert s["frames"] == a["frames"] == int(valid.sum()) and np.array_equal(s["trans"], a["trans"])
+    assert np.array_equal(s["trans"][1:], np.bincount(ali[valid], minlength=tm.num_tids + 1)[1:])
+    assert abs(s["like"] - a["like"]) <= 1e-9 * abs(a["like"])
+    # fp32 dot products are summed in a different lane order: posteriors differ by ~1e-7 per frame
+    assert np.allclose(s["occ"], a["occ"], rtol=1e-5, atol=1e-4)
+    assert np.allclose(s["mean"], a["mean"], rtol=1e-5, atol=1e-3) and np.allclose(s["var"], a["var"], rtol=1e-5, atol=1e-3)
+    g = O.GmmModel.from_am(am)
+    ref = O.acc_stats(g, tid2pdf, feats[valid], ali[valid], tm.num_tids)
+    assert np.allclose(s["occ"], ref["occ"], rtol=1e-4, atol=1e-5) and abs(s["like"] - ref["like"][0]) <= 1e-5 * abs(ref["like"][0])
+    assert np.allclose(s["mean"], ref["mean"], rtol=1e-4, atol=1e-3) and np.allclose(s["var"], ref["var"], rtol=1e-4, atol=1e-2)
+    assert abs(s["occ"].sum() - valid.sum()) < 1e-3 * valid.sum()       # posteriors of a frame sum to one
+    dm.close()
+
+
+@pytest.mark.parametrize("two_models,use_lda", [(False, False), (True, True)])
+def test_fmllr_stats_and_transforms_parity(eng, two_models, use_lda):
+    """K5 against the oracle's FmllrDiagGmmAccs restatement, per speaker, with silence weighting; then the transforms."""
+    from mfa_b200 import fmllr as F
+    sc = build_synth_scenario(seconds=60.0, seed=21, n_phones=8, n_words=30, gauss_per_pdf=3, n_spk=3, use_lda=use_lda)
+    tm, am, c = sc["tm"], sc["am"], sc["corpus"]
+    fsts = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts).export()
+    ref = oracle_align_all(sc, fsts, 10.0, 40.0)
+    D = am.dim
+    am_post = am
+    if two_models:   # an "alignment model": same layout, perturbed parameters
+        rng = np.random.default_rng(4)
+        from mfa_b200 import kaldi_io as K
+        am_post = K.AmDiagGmm(D, am.offsets, am.weights, am.means_invvars * (1 + 0.05 * rng.normal(size=am.means_invvars.shape)).astype(np.float32),
+                              am.inv_vars * np.exp(0.05 * rng.normal(size=am.inv_vars.shape)).astype(np.float32))
+    sil_phone = c.lexicon.phone_table["sil"]
+    tw = np.where(tm.tid2phone == sil_phone, np.float32(0.0), np.float32(1.0)).astype(np.float32)
+    tw[0] = 0.0
+    g, gp = O.GmmModel.from_am(am), O.GmmModel.from_am(am_post)
+    fo = sc["frame_off"]
+    ali = np.zeros(int(fo[-1]), np.int32)
+    stats_ref = np.zeros((c.n_spk, O.fmllr_stats_size(D)))
+    for u, r in enumerate(ref):
+        if r["status"] >= 2:
+            continue
+        ali[fo[u]:fo[u + 1]] = r["ali"]
+        O.fmllr_acc(gp, g, tm.tid2pdf, tw, sc["feats"][u], r["ali"], stats_ref[c.utt2spk[u]])
+    dm = E.DeviceModel(eng, tm, am)
+    dmp = E.DeviceModel(eng, tm, am_post) if two_models else None
+    feats = np.concatenate(sc["feats"])
+    got = dm.fmllr_acc(feats, ali, fo, c.utt2spk, c.n_spk, tid_weight=tw, post_model=dmp)
+    assert got.shape == stats_ref.shape
+    n_sil = int((tw[ali] == 0).sum())
+    assert 0 < n_sil < ali.shape[0]
+    assert np.allclose(got[:, 0], stats_ref[:, 0], rtol=1e-6)
+    assert abs(got[:, 0].sum() - (ali.shape[0] - n_sil)) < 1e-3 * ali.shape[0]          # beta = number of weighted frames
+    scale = np.abs(stats_ref).max(axis=1, keepdims=True)
+    assert (np.abs(got - stats_ref) / scale).max() < 1e-6
+    assert relmax(got[:, 1:1 + D * (D + 1)], stats_ref[:, 1:1 + D * (D + 1)]) < 1e-5
+    # device buffers in -> device statistics out, same numbers
+    import torch
+    got_d = dm.fmllr_acc(torch.from_numpy(feats).cuda(), torch.from_numpy(ali).cuda(), fo, c.utt2spk, c.n_spk, tid_weight=tw, post_model=dmp)
+    eng.sync()
+    assert np.allclose(got_d.cpu().numpy(), got, rtol=1e-9, atol=1e-9 * scale.max())
+    # transforms: product (numpy on the GPU statistics) vs oracle update on the oracle statistics
+    W, impr, count = F.compute_transforms(got, D, min_count=100.0)
+    for s in range(c.n_spk):
+        Wo, io = O.fmllr_update(stats_ref[s], D, min_count=100.0)
+        assert np.abs(W[s] - Wo).max() < 1e-3 and abs(impr[s] - io) <= 1e-3 * max(1.0, abs(io))
+        assert impr[s] >= 0.0
+    # edge: a speaker without frames and an utterance without alignment contribute nothing
+    got2 = dm.fmllr_acc(feats, np.zeros_like(ali), fo, c.utt2spk, c.n_spk + 1, tid_weight=tw, post_model=dmp)
+    assert not got2.any()
+    dm.close()
+    if dmp:
+        dmp.close()
