@@ -131,6 +131,72 @@ def pick_sample(sc, audio_seconds: float):
     return utts
 
 
+def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
+    """K4 (GMM accumulator statistics) and K5 (per-speaker fMLLR statistics + transform update) on the 10 h workload."""
+    import torch
+    from mfa_b200 import engine as E, fmllr as F
+    c = sc.corpus
+    raw, fo = eng.mfcc(d_pcm, c.sample_off, mo)
+    stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
+    eng.sync()
+    feats = eng.features(raw, fo, sc.feat_mode, lda=sc.lda, cmvn_stats=stats.cpu().numpy(), utt2spk=c.utt2spk, n_spk=c.n_spk)
+    del raw
+    ali = res.ali[: int(fo[-1])].contiguous()
+    T, D, G = int(fo[-1]), sc.am.dim, sc.am.NumGauss()
+    out = {}
+
+    def timed(fn, reps):
+        fn(); eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        eng.sync(); torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def k4():
+        sc.model.acc_zero()
+        sc.model.acc_stats(feats, ali)
+    k4_ms = timed(k4, max(1, args.steps))
+    k4_bytes = float(T * (4 * D + 4) + 8 * G * (1 + 2 * D))
+    out["k4_acc_stats"] = {"kernel": "K4 acc_hist + acc_scan + acc_scatter + acc_items_kernel (one acc-stats pass over the step's alignments)",
+                           "ms": k4_ms, "bound": "hbm", "algorithmic_bytes": k4_bytes, "achieved": k4_bytes / (k4_ms * 1e-3) / 1e9, "unit": "GB/s",
+                           "peak": pk["hbm_gbs"], "frac": k4_bytes / (k4_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "xRT": c.seconds / (k4_ms * 1e-3)}
+    os.environ["MFA_ACC_IMPL"] = "atomic"
+    try:
+        out["k4_acc_stats"]["first_version_atomic_ms"] = timed(k4, 1)
+    finally:
+        os.environ.pop("MFA_ACC_IMPL", None)
+    acc = sc.model.acc_read()
+    out["k4_acc_stats"]["frames"] = acc["frames"]
+    out["k4_acc_stats"]["avg_loglike_per_frame"] = acc["like"] / max(1.0, acc["frames"])
+    sil = c.lexicon.phone_table.get("sil")
+    tw = np.where(sc.tm.tid2phone == sil, np.float32(0), np.float32(1)).astype(np.float32)
+    tw[0] = 0
+    holder = {}
+
+    def k5():
+        holder["s"] = sc.model.fmllr_acc(feats, ali, fo, c.utt2spk, c.n_spk, tid_weight=tw)
+    k5_ms = timed(k5, max(1, args.steps))
+    D1 = D + 1
+    weighted = float(holder["s"][:, 0].sum().item())
+    dfma = weighted * D * (D1 * (D1 + 1) // 2)
+    out["k5_fmllr_stats"] = {"kernel": "K5 fmllr_frame_kernel + fmllr_accum_kernel (per-speaker beta, K, G_d in f64)", "ms": k5_ms, "bound": "f64 FMA",
+                             "speakers": int(c.n_spk), "weighted_frames": weighted, "algorithmic_dfma": dfma,
+                             "achieved_tflops_f64": 2.0 * dfma / (k5_ms * 1e-3) / 1e12, "xRT": c.seconds / (k5_ms * 1e-3)}
+    upd = {}
+
+    def k5u():
+        upd["r"] = F.compute_transforms_device(eng, holder["s"], D)
+    upd_ms = timed(k5u, max(1, args.steps))
+    W, impr, cnt = upd["r"]
+    out["k5_fmllr_update"] = {"kernel": "fmllr_update_kernel (one CTA per speaker, 40 sweeps of row updates in f64)", "ms": upd_ms,
+                              "speakers_updated": int((np.asarray(cnt) > 500).sum()),
+                              "mean_objf_impr_per_frame": float(np.sum(impr) / max(1.0, float(np.sum(cnt))))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +210,7 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=0.0, help="audio seconds for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=100.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the K4 / K5 timings reported under 'extras'")
     ap.add_argument("--e2e-jobs", type=int, default=2, help="concurrent jobs (engines) per GPU in the end-to-end arm")
     args = ap.parse_args()
 
@@ -379,6 +446,14 @@ def main():
             "roofline": roof, "roofline_k2": k2, "roofline_k3": k3, "roofline_k1": k1, "stages_ms": stages,
             "aligned_utterances": int(ok_total), "utterances": int(utts_total),
             "k3_band_fallbacks_per_step": fallbacks / max(1, args.steps)}
+    # ---- training-loop / SAT stages next to the alignment path (config 4 and config 3's fMLLR pass), timed on their own with CUDA
+    # events on the engine stream, OUTSIDE the timed alignment step: K4 accumulator statistics and K5 per-speaker fMLLR statistics
+    # over the step's device-resident features and alignments.
+    if not args.no_extras:
+        try:
+            line["extras"] = train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args)
+        except Exception as ex:
+            line["extras"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         try:
             sc._fsts = sc.batch.export()

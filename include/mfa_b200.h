@@ -274,6 +274,12 @@ MFA_API int64_t mfa_fmllr_stats_size(int32_t dim);
 MFA_API int mfa_fmllr_acc(mfa_engine *e, mfa_model *post_model, mfa_model *m, const float *feats, const int32_t *ali,
                           const float *tid_weight, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts,
                           int32_t n_spk, double *stats, int where);
+/* fMLLR transform update from those statistics, one CTA per speaker: Kaldi ComputeFmllrMatrixDiagGmmFull started from the unit
+ * transform (gmm-est-fmllr): num_iters (<= 0 -> 40) sweeps of the row update, accepted only if the auxiliary function did not
+ * decrease; speakers with beta <= min_count (Kaldi: 500) keep the unit transform.  stats / transforms [n_spk][dim][dim+1] f32 follow
+ * `where`; objf_impr[n_spk] and count[n_spk] (either may be NULL) are host pointers. */
+MFA_API int mfa_fmllr_update(mfa_engine *e, const double *stats, int32_t dim, int32_t n_spk, int32_t num_iters, double min_count,
+                             float *transforms, double *objf_impr, double *count, int where);
 
 #ifdef __cplusplus
 }

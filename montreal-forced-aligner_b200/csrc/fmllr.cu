@@ -167,6 +167,201 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
   if (k1ok && d0 + kd1 < dim && kacc[1] != 0.0) atomicAdd(&K[(size_t)(d0 + kd1) * D1 + kj1], kacc[1]);
   if (t == 0 && dtile == 0 && beta != 0.0) atomicAdd(&st[0], beta);
 }
+
+// ---------------------------------------------------------------------------------------------- transform update
+// One CTA per speaker: Kaldi ComputeFmllrMatrixDiagGmmFull (transform/fmllr-diag-gmm.cc) in f64 -- invert the D second-order
+// matrices G_d (warp-level Gauss-Jordan in shared memory, SPD so unpivoted), then num_iters sweeps of FmllrInnerUpdate over the
+// rows: cofactor row = column d of A^-1 (A^-1 is re-inverted with partial pivoting once per sweep and carried across the row
+// updates of a sweep with the Sherman-Morrison identity), the quadratic for the step size, w_d = (alpha c + k_d) G_d^-1.  The
+// auxiliary function before / after decides whether the estimate is kept (FmllrAuxFuncDiagGmm, compared in float like Kaldi).
+constexpr int UNT = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[i] = sum_j M[i][j] v[j] for an n x n row-major matrix in global memory; v, out in shared memory.  Rows are dealt to warps.
+__device__ __forceinline__ void matvec_rows(const double *M, const double *v, double *out, int n, int warp, int lane) {
+  constexpr int NW = UNT / 32, MAXR = 9;   // n <= 65 -> at most 9 rows per warp
+  double acc[MAXR];
+#pragma unroll
+  for (int k = 0; k < MAXR; k++) {
+    const int i = warp + k * NW;
+    double a = 0.0;
+    if (i < n) {
+      const double *row = M + (size_t)i * n;
+      for (int j = lane; j < n; j += 32) a += row[j] * v[j];   // plain loads: this CTA wrote M earlier in the kernel
+    }
+    acc[k] = a;
+  }
+#pragma unroll
+  for (int k = 0; k < MAXR; k++) {
+    const int i = warp + k * NW;
+    if (i < n) { const double r = warp_sum(acc[k]); if (lane == 0) out[i] = r; }   // i is warp-uniform
+  }
+}
+
+// in-place inverse of the n x n matrix A (shared memory) by Gauss-Jordan with partial pivoting, all threads of the CTA;
+// returns log|det A| (valid in every thread).  s_col: n doubles, s_piv: n ints, s_ld: 1 double of scratch.
+__device__ double cta_invert(double *A, int n, double *s_col, int *s_piv, double *s_ld) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  if (t == 0) *s_ld = 0.0;
+  for (int c = 0; c < n; c++) {
+    if (warp == 0) {
+      double best = -1.0; int bi = c;
+      for (int r = c + lane; r < n; r += 32) { const double v = fabs(A[r * n + c]); if (v > best) { best = v; bi = r; } }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) s_piv[c] = bi;
+    }
+    __syncthreads();
+    const int p = s_piv[c];
+    if (p != c && t < n) { const double a = A[c * n + t]; A[c * n + t] = A[p * n + t]; A[p * n + t] = a; }
+    __syncthreads();
+    const double pv = A[c * n + c], ipv = 1.0 / pv;
+    __syncthreads();
+    if (t == 0) *s_ld += log(fabs(pv));
+    if (t < n) { s_col[t] = A[t * n + c]; A[c * n + t] = (t == c) ? ipv : A[c * n + t] * ipv; }
+    __syncthreads();
+    for (int idx = t; idx < n * n; idx += UNT) {
+      const int r = idx / n, j = idx - r * n;
+      if (r != c) A[idx] = (j == c) ? -s_col[r] * ipv : A[idx] - s_col[r] * A[c * n + j];
+    }
+    __syncthreads();
+  }
+  for (int c = n - 1; c >= 0; c--) {
+    const int p = s_piv[c];
+    if (p != c && t < n) { const double a = A[t * n + c]; A[t * n + c] = A[t * n + p]; A[t * n + p] = a; }
+    __syncthreads();
+  }
+  return *s_ld;
+}
+
+__device__ double cta_sum(double v, double *s_red) {
+  const int t = threadIdx.x;
+  v = warp_sum(v);
+  __syncthreads();
+  if ((t & 31) == 0) s_red[t >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < UNT / 32; w++) r += s_red[w];
+  return r;
+}
+
+// beta log|det A| + tr(W K^T) - 1/2 sum_d w_d G_d w_d^T  (logdet supplied by the caller)
+__device__ double cta_auxf(const double *W, const double *K, const double *Gp, double beta, double logdet, int D, double *s_red) {
+  const int D1 = D + 1, NP = D1 * (D1 + 1) / 2, t = threadIdx.x;
+  double part = 0.0;
+  for (int idx = t; idx < D * D1; idx += UNT) part += W[idx] * K[idx];
+  for (int idx = t; idx < D * NP; idx += UNT) {
+    const int d = idx / NP, ij = idx - d * NP;
+    int i = (int)((sqrtf(8.0f * (float)ij + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= ij) i++;
+    while (i * (i + 1) / 2 > ij) i--;
+    const int j = ij - i * (i + 1) / 2;
+    const double q = Gp[idx] * W[d * D1 + i] * W[d * D1 + j];
+    part -= (i == j ? 0.5 : 1.0) * q;
+  }
+  return beta * logdet + cta_sum(part, s_red);
+}
+
+__global__ void __launch_bounds__(UNT)
+fmllr_update_kernel(const double *__restrict__ stats, int64_t stats_stride, int dim, int num_iters, double min_count, int n_par,
+                    double *invG_all, float *__restrict__ W_out, double *__restrict__ impr_out, double *__restrict__ count_out) {
+  extern __shared__ double sm[];
+  const int D = dim, D1 = D + 1, NP = D1 * (D1 + 1) / 2;
+  const int spk = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const double *st = stats + (size_t)spk * stats_stride;
+  const double beta = st[0], *K = st + 1, *Gp = K + (size_t)D * D1;
+  float *Wo = W_out + (size_t)spk * D * D1;
+  if (t == 0) { count_out[spk] = beta; impr_out[spk] = 0.0; }
+  for (int idx = t; idx < D * D1; idx += UNT) Wo[idx] = (idx / D1 == idx % D1) ? 1.0f : 0.0f;
+  if (!(beta > min_count)) return;   // gmm-est-fmllr: below min-count the unit transform is written
+  double *invG = invG_all + (size_t)spk * D * D1 * D1;
+  // ---- phase A: G_d^-1, one matrix per warp at a time
+  if (warp < n_par) {
+    double *M = sm + (size_t)warp * D1 * D1;
+    for (int d = warp; d < D; d += n_par) {
+      const double *g = Gp + (size_t)d * NP;
+      for (int idx = lane; idx < D1 * D1; idx += 32) {
+        const int i = idx / D1, j = idx - i * D1;
+        M[idx] = j <= i ? g[i * (i + 1) / 2 + j] : g[j * (j + 1) / 2 + i];
+      }
+      __syncwarp();
+      for (int c = 0; c < D1; c++) {
+        const double ip = 1.0 / M[c * D1 + c];
+        __syncwarp();
+        for (int j = lane; j < D1; j += 32) M[c * D1 + j] = (j == c) ? ip : M[c * D1 + j] * ip;
+        __syncwarp();
+        for (int r = 0; r < D1; r++) {
+          if (r == c) continue;
+          const double f = M[r * D1 + c];
+          __syncwarp();
+          for (int j = lane; j < D1; j += 32) M[r * D1 + j] = (j == c) ? -f * ip : M[r * D1 + j] - f * M[c * D1 + j];
+        }
+        __syncwarp();
+      }
+      double *o = invG + (size_t)d * D1 * D1;
+      for (int idx = lane; idx < D1 * D1; idx += 32) o[idx] = M[idx];
+      __syncwarp();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // ---- phase B: row updates.  Shared memory is re-carved.
+  double *W = sm, *Ainv = W + D * D1, *cvec = Ainv + D * D, *cg = cvec + D1, *vvec = cg + D1, *wnew = vvec + D1, *delta = wnew + D1,
+         *u = delta + D1, *vv = u + D1, *s_col = vv + D1, *s_red = s_col + D1, *s_ld = s_red + 8;
+  int *s_piv = reinterpret_cast<int *>(s_ld + 1);
+  for (int idx = t; idx < D * D1; idx += UNT) W[idx] = (idx / D1 == idx % D1) ? 1.0 : 0.0;
+  __syncthreads();
+  // objective at the unit transform: log|det| = 0
+  const double old_objf = (double)(float)cta_auxf(W, K, Gp, beta, 0.0, D, s_red);
+  for (int it = 0; it < num_iters; it++) {
+    for (int idx = t; idx < D * D; idx += UNT) { const int r = idx / D, j = idx - r * D; Ainv[idx] = W[r * D1 + j]; }
+    __syncthreads();
+    cta_invert(Ainv, D, s_col, s_piv, s_ld);
+    for (int d = 0; d < D; d++) {
+      const double *iG = invG + (size_t)d * D1 * D1, *k = K + (size_t)d * D1;
+      if (t < D1) cvec[t] = t < D ? Ainv[t * D + d] : 0.0;
+      __syncthreads();
+      matvec_rows(iG, cvec, cg, D1, warp, lane);
+      __syncthreads();
+      double p1 = 0.0, p2 = 0.0;
+      for (int j = lane; j < D1; j += 32) { p1 += cg[j] * cvec[j]; p2 += cg[j] * k[j]; }
+      const double e1 = warp_sum(p1), e2 = warp_sum(p2);
+      const double disc = sqrt(e2 * e2 + 4.0 * e1 * beta);
+      const double a1 = (-e2 + disc) / (2.0 * e1), a2 = (-e2 - disc) / (2.0 * e1);
+      const double f1 = beta * log(fabs(a1 * e1 + e2)) - 0.5 * a1 * a1 * e1, f2 = beta * log(fabs(a2 * e1 + e2)) - 0.5 * a2 * a2 * e1;
+      const double alpha = f1 > f2 ? a1 : a2;
+      if (t < D1) vvec[t] = alpha * cvec[t] + k[t];
+      __syncthreads();
+      matvec_rows(iG, vvec, wnew, D1, warp, lane);
+      __syncthreads();
+      if (t < D) { delta[t] = wnew[t] - W[d * D1 + t]; u[t] = Ainv[t * D + d]; }
+      __syncthreads();
+      if (t < D1) W[d * D1 + t] = wnew[t];
+      if (t < D) { double a = 0.0; for (int i = 0; i < D; i++) a += delta[i] * Ainv[i * D + t]; vv[t] = a; }
+      __syncthreads();
+      const double inv_den = 1.0 / (1.0 + vv[d]);
+      for (int idx = t; idx < D * D; idx += UNT) { const int i = idx / D, j = idx - i * D; Ainv[idx] -= u[i] * vv[j] * inv_den; }
+      __syncthreads();
+    }
+  }
+  for (int idx = t; idx < D * D; idx += UNT) { const int r = idx / D, j = idx - r * D; Ainv[idx] = W[r * D1 + j]; }
+  __syncthreads();
+  const double logdet = cta_invert(Ainv, D, s_col, s_piv, s_ld);
+  const double new_objf = (double)(float)cta_auxf(W, K, Gp, beta, logdet, D, s_red);
+  const double impr = new_objf - old_objf;
+  const bool approx_equal = fabs(new_objf - old_objf) <= 0.001 * (fabs(new_objf) + fabs(old_objf));
+  if (impr < 0.0 && !approx_equal) return;   // "objective function did not increase": keep the unit transform
+  for (int idx = t; idx < D * D1; idx += UNT) Wo[idx] = (float)W[idx];
+  if (t == 0) impr_out[spk] = impr;
+}
 }  // namespace
 
 extern "C" int64_t mfa_fmllr_stats_size(int32_t dim) {
@@ -209,6 +404,25 @@ int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d
   else
     fmllr_accum_kernel<9><<<(unsigned)grid, ANT, 0, e->stream>>>(d_feats, d_ab, d_cnt, dim, d_frame_off, d_off, d_utts, n_dtile, n_split, d_stats, stride);
   e->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return MFA_OK;
+}
+
+int launch_fmllr_update(mfa_engine *e, const double *d_stats, int dim, int32_t n_spk, int num_iters, double min_count, float *d_W,
+                        double *d_impr, double *d_count) {
+  if (n_spk == 0) return MFA_OK;
+  if (dim > 64 || dim < 1) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: dim must be in 1..64");
+  const size_t D1 = dim + 1;
+  double *d_invG;
+  MFA_TRY(e->getT<double>(DB_FM_INVG, (size_t)n_spk * dim * D1 * D1, &d_invG));
+  const size_t phase_b = sizeof(double) * ((size_t)dim * D1 + (size_t)dim * dim + 9 * D1 + 16) + sizeof(int) * D1;
+  int n_par = 8;
+  while (n_par > 1 && sizeof(double) * n_par * D1 * D1 > e->smem_optin - 2048) n_par--;
+  const size_t smem = std::max(phase_b, sizeof(double) * n_par * D1 * D1);
+  CUDA_TRY(cudaFuncSetAttribute(fmllr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fmllr_update_kernel<<<(unsigned)n_spk, UNT, smem, e->stream>>>(d_stats, mfa_fmllr_stats_size(dim), dim, num_iters, min_count, n_par, d_invG,
+                                                                  d_W, d_impr, d_count);
+  e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MFA_OK;
 }

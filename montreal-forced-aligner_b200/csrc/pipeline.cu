@@ -493,4 +493,23 @@ int mfa_fmllr_acc(mfa_engine *e, mfa_model *post_model, mfa_model *m, const floa
   return MFA_OK;
 }
 
+int mfa_fmllr_update(mfa_engine *e, const double *stats, int32_t dim, int32_t n_spk, int32_t num_iters, double min_count, float *transforms,
+                     double *objf_impr, double *count, int where) {
+  if (!e || !stats || !transforms || n_spk < 0 || dim < 1) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (num_iters <= 0) num_iters = 40;
+  const size_t ns = (size_t)n_spk * (size_t)mfa_fmllr_stats_size(dim), nw = (size_t)n_spk * dim * (dim + 1);
+  const double *d_stats; float *d_W; double *d_out;
+  MFA_TRY(to_device(e, DB_FM_STATS, stats, ns, where, &d_stats));
+  MFA_TRY(out_buffer(e, DB_FM_W, transforms, nw, where, &d_W));
+  MFA_TRY(e->getT<double>(DB_FM_OUT, (size_t)2 * std::max(n_spk, 1), &d_out));
+  MFA_TRY(launch_fmllr_update(e, d_stats, dim, n_spk, num_iters, min_count, d_W, d_out, d_out + n_spk));
+  MFA_TRY(from_device(e, d_W, transforms, nw, where));
+  // the two small per-speaker vectors always land in host memory
+  if (objf_impr) CUDA_TRY(cudaMemcpyAsync(objf_impr, d_out, sizeof(double) * n_spk, cudaMemcpyDeviceToHost, e->stream));
+  if (count) CUDA_TRY(cudaMemcpyAsync(count, d_out + n_spk, sizeof(double) * n_spk, cudaMemcpyDeviceToHost, e->stream));
+  if (where == MFA_HOST || objf_impr || count) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
 }  // extern "C"

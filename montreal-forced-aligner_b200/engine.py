@@ -130,6 +130,22 @@ class Engine:
         L.check(L.lib().mfa_engine_gmm_flops(self._h, C.byref(f)))
         return f.value
 
+    def fmllr_update(self, stats, dim: int, num_iters: int = 40, min_count: float = 500.0):
+        """mfa_fmllr_update: per-speaker statistics [S, size] (numpy or torch cuda f64) -> (W [S, D, D+1] f32 of the same kind,
+        objective improvement [S] numpy, count [S] numpy)."""
+        k, sp, where = _buf(stats, np.float64, "stats")
+        S = int(stats.shape[0])
+        if where == L.MFA_DEVICE:
+            import torch
+            W = torch.empty((S, dim, dim + 1), dtype=torch.float32, device=stats.device)
+        else:
+            W = np.empty((S, dim, dim + 1), dtype=np.float32)
+        k2, wp, _ = _buf(W, np.float32, "transforms")
+        impr, cnt = np.zeros(max(S, 1), np.float64), np.zeros(max(S, 1), np.float64)
+        L.check(L.lib().mfa_fmllr_update(self._h, sp, C.c_int32(dim), C.c_int32(S), C.c_int32(num_iters), C.c_double(min_count), wp,
+                                         impr.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), C.c_int(where)))
+        return W, impr[:S], cnt[:S]
+
     # ---- K1 / CMVN / features -----------------------------------------------------------------
     def mfcc(self, pcm, sample_off, opts: L.MfccOpts, out=None):
         so, sop = _host(sample_off, np.int64)

@@ -2,8 +2,9 @@
 
 Mirrors kalpy's ``FmllrComputer`` as MFA uses it in CalcFmllrFunction._run (montreal_forced_aligner/corpus/features.py:460-548;
 options ``fmllr_update_type / silence_weight / acoustic_scale`` from :759-766).  The O(frames) part -- posterior-weighted
-per-speaker statistics beta, K, G_d -- runs on the GPU (``mfa_fmllr_acc``, csrc/fmllr.cu).  The O(speakers) part restated here
-in float64 numpy, batched over speakers, is Kaldi transform/fmllr-diag-gmm.cc ``ComputeFmllrMatrixDiagGmmFull``: 40 sweeps of
+per-speaker statistics beta, K, G_d -- runs on the GPU (``mfa_fmllr_acc``, csrc/fmllr.cu), and so does the O(speakers) transform
+update (``mfa_fmllr_update``, one CTA per speaker).  The same update is restated here in float64 numpy, batched over speakers,
+as the host cross-check of that kernel; it is Kaldi transform/fmllr-diag-gmm.cc ``ComputeFmllrMatrixDiagGmmFull``: 40 sweeps of
 the row update  w_d = (alpha c_d + k_d) G_d^-1  where c_d is the cofactor row of A and alpha the better root of the quadratic
 (``FmllrInnerUpdate``), accepted only if the auxiliary function did not decrease; speakers with beta <= min_count (500) keep the
 unit transform (gmm-est-fmllr writes it).  The inverse of A is carried across row updates with the Sherman-Morrison identity and
@@ -86,6 +87,11 @@ def compute_transforms(stats: np.ndarray, D: int, num_iters: int = 40, min_count
     return W_out.astype(np.float32), impr_out, beta
 
 
+def compute_transforms_device(engine: "E.Engine", stats, D: int, num_iters: int = 40, min_count: float = 500.0):
+    """The same update on the GPU (mfa_fmllr_update, one CTA per speaker); `stats` numpy or torch cuda f64."""
+    return engine.fmllr_update(stats, D, num_iters, min_count)
+
+
 def compose_transforms(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """Kaldi ComposeTransforms(a, b, b_is_affine=true): apply b first, then a.  [D, D+1] x [D, D+1] -> [D, D+1]."""
     D = a.shape[0]
@@ -125,8 +131,12 @@ class FmllrComputer:
     def compute_stats(self, feats, ali, frame_off, utt2spk, n_spk: int):
         return self._dm.fmllr_acc(feats, ali, frame_off, utt2spk, n_spk, tid_weight=self.tid_weight, post_model=self._dm_post)
 
-    def compute_transforms(self, stats):
-        return compute_transforms(np.asarray(stats), self.acoustic_model.dim, self.num_iters, self.min_count)
+    def compute_transforms(self, stats, impl: str = "device"):
+        """impl 'device': mfa_fmllr_update (CUDA, default); 'host': the float64 numpy restatement above (cross-check)."""
+        if impl == "host":
+            return compute_transforms(np.asarray(stats), self.acoustic_model.dim, self.num_iters, self.min_count)
+        W, impr, count = compute_transforms_device(self.engine, stats, self.acoustic_model.dim, self.num_iters, self.min_count)
+        return np.asarray(W), impr, count
 
     def export_transforms(self, file_name, feature_archive, alignment_archive, previous_transform_archive=None, callback: Optional[Callable] = None,
                           max_frames: int = 4_000_000):

@@ -434,10 +434,18 @@ def test_fmllr_stats_and_transforms_parity(eng, two_models, use_lda):
     assert np.allclose(got_d.cpu().numpy(), got, rtol=1e-9, atol=1e-9 * scale.max())
     # transforms: product (numpy on the GPU statistics) vs oracle update on the oracle statistics
     W, impr, count = F.compute_transforms(got, D, min_count=100.0)
+    Wd, impr_d, count_d = eng.fmllr_update(got, D, 40, 100.0)                      # the CUDA update kernel (host buffers)
+    Wt, impr_t, _ = eng.fmllr_update(got_d, D, 40, 100.0)                           # ... and on the device-resident statistics
+    eng.sync()
+    assert np.allclose(count_d, got[:, 0]) and np.abs(Wt.cpu().numpy() - Wd).max() == 0.0 and np.array_equal(impr_t, impr_d)
     for s in range(c.n_spk):
         Wo, io = O.fmllr_update(stats_ref[s], D, min_count=100.0)
         assert np.abs(W[s] - Wo).max() < 1e-3 and abs(impr[s] - io) <= 1e-3 * max(1.0, abs(io))
-        assert impr[s] >= 0.0
+        assert np.abs(Wd[s] - Wo).max() < 1e-3 and abs(impr_d[s] - io) <= 1e-3 * max(1.0, abs(io))
+        assert impr[s] >= 0.0 and impr_d[s] >= 0.0
+    # below min_count the unit transform is kept
+    Wu, impr_u, _ = eng.fmllr_update(got, D, 40, 1e9)
+    assert (Wu == np.eye(D, D + 1, dtype=np.float32)).all() and not impr_u.any()
     # edge: a speaker without frames and an utterance without alignment contribute nothing
     got2 = dm.fmllr_acc(feats, np.zeros_like(ali), fo, c.utt2spk, c.n_spk + 1, tid_weight=tw, post_model=dmp)
     assert not got2.any()
