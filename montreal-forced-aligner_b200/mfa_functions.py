@@ -8,6 +8,7 @@ Mirrors (same names, argument meaning, files written, callback protocol, error b
   AccStatsFunction             montreal_forced_aligner/alignment/multiprocessing.py:576-666 (row a9)
   MonoAlignEqualFunction       montreal_forced_aligner/acoustic_modeling/monophone.py:40-139 (row a11)
   CalcFmllrFunction            montreal_forced_aligner/corpus/features.py:423-548          (row N2)
+  AlignmentExtractionFunction  montreal_forced_aligner/alignment/multiprocessing.py:1549-1862 (row N4; + export_textgrids)
 and of the drivers calc_cmvn (corpus/acoustic_corpus.py:1315-1367, row a3), AlignMixin.align_utterances
 (alignment/mixins.py:282-380, row a8) and AcousticModelTrainingMixin.acc_stats (acoustic_modeling/base.py:277-338 upstream,
 row a10).  The reference pulls utterances from its database; here a ``Job`` carries them explicitly (the DB is out of scope).
@@ -526,6 +527,75 @@ def calc_fmllr(jobs: Sequence[Job], working_directory, ali_model_path, model_pat
     opts.update(fmllr_options or {})
     args = [CalcFmllrArguments(j.id, j, None, Path(working_directory), Path(ali_model_path), Path(model_path), opts, silence_phone_ids) for j in jobs]
     return {s: (impr, count) for s, impr, count in run_kaldi_function(CalcFmllrFunction, args)}
+
+
+# ------------------------------------------------------------------------------------------------ N4: ali -> CTM -> TextGrid
+@dataclass
+class AlignmentExtractionArguments(MfaArguments):
+    working_directory: Path
+    model_path: Path
+    lexicon_compilers: Dict[int, Lexicon]
+    frame_shift: float = 0.01
+    cleanup_textgrids: bool = True
+
+
+class AlignmentExtractionFunction(KaldiFunction):
+    """alignment/multiprocessing.py:1549-1862 (non-transcription branch): per dictionary, read ali/words/likelihoods archives, turn
+    every alignment into word + phone intervals; callback payload (utterance id, dictionary id, HierarchicalCtm)."""
+
+    def __init__(self, args: AlignmentExtractionArguments):
+        super().__init__(args)
+        self.a = args
+
+    def _run(self):
+        from . import export as X
+        tm, _ = K.read_gmm_model(self.a.model_path)
+        wd = Path(self.a.working_directory)
+        for did in self.job.dictionary_ids:
+            ali_path = self.job.construct_path(wd, "ali", "ark", did)
+            if not ali_path.exists():
+                continue
+            lex = self.a.lexicon_compilers[did]
+            by_key = {u.kaldi_id: u for u in self.job.utts(did)}
+            archive = KC.AlignmentArchive(ali_path, self.job.construct_path(wd, "words", "ark", did), self.job.construct_path(wd, "likelihoods", "ark", did))
+            for alignment in archive:
+                u = by_key.get(alignment.utterance_id)
+                if u is None:
+                    continue
+                ctm = X.alignment_to_ctm(alignment, tm, lex, self.a.frame_shift, u.begin, u.end, u.normalized_text or None)
+                self.callback((u.id, did, ctm))
+
+
+def export_textgrids(jobs: Sequence[Job], working_directory, model_path, lexicon_compilers: Dict[int, Lexicon], output_directory,
+                     frame_shift: float = 0.01, output_format: str = "long_textgrid", cleanup_textgrids: bool = True) -> Dict[int, Path]:
+    """CorpusAligner.collect_alignments + export_files (alignment/base.py:1549-1720, 2536-2748) without the database: one output file per
+    sound file (utterances of the same `path` share it; several speakers -> "speaker - words" tiers).  Returns {utterance id: path}."""
+    from . import export as X
+    out_dir = Path(output_directory)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    args = [AlignmentExtractionArguments(j.id, j, None, Path(working_directory), Path(model_path), lexicon_compilers, frame_shift, cleanup_textgrids)
+            for j in jobs]
+    by_id = {u.id: u for j in jobs for u in j.utterances}
+    files: Dict[str, Dict[str, Dict[str, list]]] = {}
+    durations: Dict[str, float] = {}
+    written: Dict[int, Path] = {}
+    for uid, did, ctm in run_kaldi_function(AlignmentExtractionFunction, args):
+        u = by_id[uid]
+        data = X.ctm_to_speaker_data(ctm, str(u.speaker_id), lexicon_compilers[did], cleanup_textgrids)
+        spk = files.setdefault(u.path, {}).setdefault(str(u.speaker_id), {"words": [], "phones": []})
+        for kind in ("words", "phones"):
+            spk[kind].extend(data[str(u.speaker_id)][kind])
+        end = u.end if u.end is not None else (u.begin or 0.0) + u.duration
+        durations[u.path] = max(durations.get(u.path, 0.0), float(end))
+        written[uid] = None
+    ext = {"long_textgrid": ".TextGrid", "short_textgrid": ".TextGrid", "json": ".json", "csv": ".csv"}[output_format]
+    for path, speaker_data in files.items():
+        out = out_dir / (Path(path).stem + ext)
+        X.export_textgrid(speaker_data, out, durations[path], frame_shift, output_format)
+        for uid, u in by_id.items():
+            if u.path == path and uid in written:
+                written[uid] = out
+    return written
 
 
 # ------------------------------------------------------------------------------------------------ online path (section 3.2)

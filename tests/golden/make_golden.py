@@ -71,6 +71,10 @@ def main():
     out["ta_mfcc_nosnip"] = TK.mfcc(w, use_energy=False, snip_edges=False, **kw).numpy()
     kw["energy_floor"] = 1.0
     out["ta_mfcc_energy"] = TK.mfcc(w, use_energy=True, snip_edges=True, **kw).numpy()
+    # reference TextGrids of the sample corpus (short format, words + phones tiers; made upstream with a different English
+    # model: a loose sanity bound for the exported boundaries, and a parser fixture) and one long-format file
+    for key, name in (("acoustic_corpus_textgrid", "acoustic_corpus"), ("long_textgrid_fixture", "michaelandsickmichael")):
+        out[key] = np.frombuffer(open(f"{REF}/textgrid/{name}.TextGrid", "rb").read(), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, "reference_fixtures.npz"), **out)
     print("wrote", os.path.join(OUT, "reference_fixtures.npz"), os.path.getsize(os.path.join(OUT, "reference_fixtures.npz")))
 
