@@ -140,6 +140,7 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
     eng.sync()
     feats = eng.features(raw, fo, sc.feat_mode, lda=sc.lda, cmvn_stats=stats.cpu().numpy(), utt2spk=c.utt2spk, n_spk=c.n_spk)
+    eng.sync()   # the feature kernel reads `raw` on the engine stream: it must finish before torch may recycle that memory
     del raw
     ali = res.ali[: int(fo[-1])].contiguous()
     T, D, G = int(fo[-1]), sc.am.dim, sc.am.NumGauss()
@@ -197,6 +198,66 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     return out
 
 
+def train_loop(eng, sc, step_device, dev, stream, dist, args):
+    """Config 4's loop on this rank's shard: align (fused step) -> K4 statistics -> all-reduce over NCCL (N > 1) -> D2H -> host M-step
+    (gmm_update.mle_update, vectorised numpy f64) -> new model on the device.  Transition costs stay folded in the packed graphs
+    (MFA recompiles graphs only at realignment iterations).  Wall-clock per stage, max over ranks is NOT taken: rank 0's view."""
+    import torch
+    from mfa_b200 import engine as E, gmm_update as GU
+    c = sc.corpus
+    mo = E.mfcc_opts()
+    fo = sc.frame_off
+    T = int(fo[-1])
+    model, am = sc.model, sc.am
+    raw, _ = eng.mfcc(_D_PCM[0], c.sample_off, mo)
+    stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
+    eng.sync()
+    feats = eng.features(raw, fo, sc.feat_mode, lda=sc.lda, cmvn_stats=stats.cpu().numpy(), utt2spk=c.utt2spk, n_spk=c.n_spk)
+    eng.sync()   # the feature kernel reads `raw` on the engine stream: it must finish before torch may recycle that memory
+    del raw
+    wo_total = int(np.cumsum(sc.graphs.max_words())[-1])
+    outs = E._alloc_outputs(T, wo_total, c.n_utts, dev)
+    iters = []
+    for it in range(args.train_iters):
+        t = {}
+        t0 = time.perf_counter()
+        res = E.align_pcm(eng, model, sc.graphs, _D_PCM[0], c.sample_off, c.utt2spk, c.n_spk, mo,
+                          sc.feat_mode, lda=sc.lda, workspace_bytes=int(args.workspace_gb * (1 << 30)), outputs=outs)
+        eng.sync(); t["align_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        model.acc_zero()
+        model.acc_stats(feats, res.ali[:T].contiguous())
+        eng.sync(); t["acc_stats_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        if dist is not None:
+            eng.sync()
+            dist.all_reduce(model.acc_tensor())
+            torch.cuda.synchronize(dev)
+        t["allreduce_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        acc = model.acc_read()
+        t["d2h_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        new_am, impr, count = GU.mle_update(am, GU.AccumAmDiagGmm.from_dict(acc), mixup=0)
+        t["mstep_host_ms"] = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        new_model = E.DeviceModel(eng, sc.tm, new_am)
+        eng.sync(); t["model_upload_ms"] = 1e3 * (time.perf_counter() - t0)
+        t["avg_loglike_per_frame"] = acc["like"] / max(1.0, acc["frames"])
+        t["frames_all_ranks"] = acc["frames"]
+        t["gaussians"] = new_am.NumGauss()
+        if model is not sc.model:
+            model.close()
+        model, am = new_model, new_am
+        iters.append(t)
+    if model is not sc.model:
+        model.close()
+    return {"iterations": iters, "note": "wall-clock per stage on rank 0 (host timers around synchronised stages); avg_loglike_per_frame must not decrease"}
+
+
+_D_PCM = [None]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,10 +271,15 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=0.0, help="audio seconds for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=100.0)
+    ap.add_argument("--train-iters", type=int, default=2, help="iterations of the align -> acc-stats -> all-reduce -> update loop timed under extras.train_loop")
+    ap.add_argument("--extras-dist", action="store_true", help="run the extras (incl. the NCCL all-reduce of the training loop) on multi-rank runs too")
     ap.add_argument("--no-extras", action="store_true", help="skip the K4 / K5 timings reported under 'extras'")
     ap.add_argument("--e2e-jobs", type=int, default=2, help="concurrent jobs (engines) per GPU in the end-to-end arm")
     args = ap.parse_args()
 
+    # the ONE JSON line goes to the real stdout; anything a library prints on fd 1 meanwhile (NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,13 +337,14 @@ def main():
                 "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
         return 0
 
     # ---- device-resident arm -----------------------------------------------------------------------------------
     mo = E.mfcc_opts()
     wo_total = int(np.cumsum(sc.graphs.max_words())[-1])
     d_pcm = torch.from_numpy(c.pcm).to(dev)
+    _D_PCM[0] = d_pcm
     outs = E._alloc_outputs(n_frames, wo_total, c.n_utts, dev)
     ws = int(args.workspace_gb * (1 << 30))
 
@@ -449,9 +516,11 @@ def main():
     # ---- training-loop / SAT stages next to the alignment path (config 4 and config 3's fMLLR pass), timed on their own with CUDA
     # events on the engine stream, OUTSIDE the timed alignment step: K4 accumulator statistics and K5 per-speaker fMLLR statistics
     # over the step's device-resident features and alignments.
-    if not args.no_extras:
+    # (multi-rank runs skip them unless --extras-dist: a rank failing inside would leave the others waiting in the all-reduce)
+    if not args.no_extras and (world == 1 or args.extras_dist):
         try:
             line["extras"] = train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args)
+            line["extras"]["train_loop"] = train_loop(eng, sc, step_device, dev, stream, dist, args)
         except Exception as ex:
             line["extras"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
@@ -469,7 +538,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     return 0
 
 

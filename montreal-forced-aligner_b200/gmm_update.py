@@ -64,43 +64,38 @@ def _gmm_objf(am: AmDiagGmm, acc: AccumAmDiagGmm) -> float:
 def mle_update(am: AmDiagGmm, acc: AccumAmDiagGmm, mixup: int = 0, power: float = 0.25, min_gaussian_occupancy: float = 10.0,
                min_gaussian_weight: float = 1.0e-5, min_variance: float = 0.001, remove_low_count_gaussians: bool = True,
                perturb_factor: float = 0.01, min_count: float = 20.0, seed: int = 1234) -> Tuple[AmDiagGmm, float, float]:
-    """Returns (new model, objective improvement, total count).  Updates means, variances and weights."""
-    D = am.dim
+    """Returns (new model, objective improvement, total count).  Updates means, variances and weights.
+    Vectorised over all Gaussians (segment sums per pdf with np.add.reduceat); only mix-up walks pdfs one by one."""
+    D, P = am.dim, am.NumPdfs()
     objf_before = _gmm_objf(am, acc)
-    new_w, new_mu, new_var, new_off = [], [], [], [0]
-    old_mu, old_var = am.means(), am.variances()
-    for j in range(am.NumPdfs()):
-        a, b = int(am.offsets[j]), int(am.offsets[j + 1])
-        occ = acc.occ[a:b]
-        occ_sum = occ.sum()
-        n = b - a
-        w = am.weights[a:b].astype(np.float64).copy()
-        mu = old_mu[a:b].copy()
-        var = old_var[a:b].copy()
-        keep = np.ones(n, dtype=bool)
-        for i in range(n):
-            prob = occ[i] / occ_sum if occ_sum > 0 else 1.0 / n
-            if occ[i] > min_gaussian_occupancy and prob > min_gaussian_weight:
-                w[i] = prob
-                m = acc.mean[a + i] / occ[i]
-                v = acc.var[a + i] / occ[i] - m * m
-                mu[i] = m
-                var[i] = np.maximum(v, min_variance)
-            elif remove_low_count_gaussians:
-                keep[i] = False
-            else:
-                w[i] = prob
-        if not keep.any():
-            keep[int(np.argmax(occ))] = True  # Kaldi refuses to remove the last Gaussian of a pdf
-        w, mu, var = w[keep], mu[keep], var[keep]
-        w = w / w.sum()
-        new_w.append(w); new_mu.append(mu); new_var.append(var)
-        new_off.append(new_off[-1] + len(w))
-    w = np.concatenate(new_w); mu = np.concatenate(new_mu); var = np.concatenate(new_var)
-    off = np.asarray(new_off, dtype=np.int32)
-    # objective after the update uses the stats of the components that survived
-    state_occs = np.asarray([acc.occ[am.offsets[j]:am.offsets[j + 1]].sum() for j in range(am.NumPdfs())])
-    out = AmDiagGmm(D, off, w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))
+    off = np.asarray(am.offsets, dtype=np.int64)
+    n_per = np.diff(off)
+    pdf_of = np.repeat(np.arange(P), n_per)
+    occ = acc.occ
+    state_occs = np.add.reduceat(occ, off[:-1]) if P else np.zeros(0)
+    state_occs[n_per == 0] = 0.0
+    prob = np.where(state_occs[pdf_of] > 0, occ / np.where(state_occs[pdf_of] > 0, state_occs[pdf_of], 1.0), 1.0 / n_per[pdf_of])
+    upd = (occ > min_gaussian_occupancy) & (prob > min_gaussian_weight)
+    w = am.weights.astype(np.float64).copy()
+    mu, var = am.means().copy(), am.variances().copy()
+    safe = np.where(upd, occ, 1.0)[:, None]
+    m_new = acc.mean / safe
+    v_new = np.maximum(acc.var / safe - m_new * m_new, min_variance)
+    mu[upd], var[upd], w[upd] = m_new[upd], v_new[upd], prob[upd]
+    if remove_low_count_gaussians:
+        keep = upd.copy()
+        none = np.add.reduceat(keep.astype(np.int64), off[:-1]) == 0
+        for j in np.nonzero(none)[0]:   # Kaldi refuses to remove the last Gaussian of a pdf: the heaviest one stays (un-updated)
+            keep[off[j] + int(np.argmax(occ[off[j]:off[j + 1]]))] = True
+    else:
+        keep = np.ones_like(upd)
+        w[~upd] = prob[~upd]
+    w, mu, var = w[keep], mu[keep], var[keep]
+    new_n = np.add.reduceat(keep.astype(np.int64), off[:-1])
+    new_off = np.zeros(P + 1, dtype=np.int64)
+    new_off[1:] = np.cumsum(new_n)
+    w = w / np.repeat(np.add.reduceat(w, new_off[:-1]), new_n)
+    out = AmDiagGmm(D, new_off.astype(np.int32), w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))
     objf_after = None
     if out.NumGauss() == am.NumGauss():
         objf_after = _gmm_objf(out, acc)
@@ -143,6 +138,10 @@ def split_by_count(am: AmDiagGmm, state_occs: np.ndarray, target_components: int
     ws, mus, vars_, off = [], [], [], [0]
     for j in range(am.NumPdfs()):
         a, b = int(am.offsets[j]), int(am.offsets[j + 1])
+        if targets[j] <= b - a:   # nothing to split: copy the pdf as it is (no random draws are consumed, as in DiagGmm::Split)
+            ws.append(am.weights[a:b].astype(np.float64)); mus.append(mu_all[a:b]); vars_.append(var_all[a:b])
+            off.append(off[-1] + (b - a))
+            continue
         w = list(am.weights[a:b].astype(np.float64))
         mu = [m.copy() for m in mu_all[a:b]]
         var = [v.copy() for v in var_all[a:b]]

@@ -452,3 +452,50 @@ def test_fmllr_stats_and_transforms_parity(eng, two_models, use_lda):
     dm.close()
     if dmp:
         dmp.close()
+
+
+def test_acc_stats_large_many_pdfs_against_numpy(eng, monkeypatch):
+    """K4 at a size where every CTA walks several items and pdfs (4 000 pdfs x 10 components, 600 k frames): both kernels against a
+    float64 numpy evaluation of the same posteriors (total log-likelihood, occupancies, first-order sums)."""
+    from mfa_b200 import kaldi_io as K
+    rng = np.random.default_rng(12)
+    D, P, M, T = 40, 4000, 10, 600_000
+    off = (np.arange(P + 1) * M).astype(np.int32)
+    G = P * M
+    means, var = rng.normal(size=(G, D)), np.exp(rng.normal(scale=0.2, size=(G, D)))
+    w = rng.dirichlet(np.ones(M), size=P).ravel()
+    am = K.AmDiagGmm(D, off, w.astype(np.float32), (means / var).astype(np.float32), (1.0 / var).astype(np.float32))
+    tm, _, _ = load_model("mono")
+    nt = tm.num_tids
+    tid2pdf = np.concatenate([[0], rng.integers(0, P, size=nt)]).astype(np.int32)
+    tm.tid2pdf = tid2pdf
+    # skewed usage: a handful of pdfs take a quarter of the frames (silence-like), the rest spread thin
+    ali = rng.integers(1, nt + 1, size=T).astype(np.int32)
+    hot = rng.random(T) < 0.25
+    ali[hot] = rng.integers(1, 6, size=int(hot.sum()))
+    pdf = tid2pdf[ali]
+    comp = rng.integers(0, M, size=T)
+    feats = (means[pdf * M + comp] + rng.normal(size=(T, D)) * np.sqrt(var[pdf * M + comp])).astype(np.float32)
+    # float64 reference, frames grouped by pdf
+    x = feats.astype(np.float64)
+    miv, iv, gc = am.means_invvars.astype(np.float64), am.inv_vars.astype(np.float64), am.gconsts.astype(np.float64)
+    ll = gc[(pdf * M)[:, None] + np.arange(M)[None]]
+    idx = (pdf * M)[:, None] + np.arange(M)[None]
+    ll = ll + np.einsum("tmd,td->tm", miv[idx], x) - 0.5 * np.einsum("tmd,td->tm", iv[idx], x * x)
+    mx = ll.max(1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(ll - mx).sum(1))
+    post = np.exp(ll - lse[:, None])
+    occ_ref = np.bincount(idx.ravel(), weights=post.ravel(), minlength=G)
+    mean0_ref = np.bincount(idx.ravel(), weights=(post * x[:, :1]).ravel(), minlength=G)
+    dm = E.DeviceModel(eng, tm, am)
+    for impl in ("segmented", "atomic"):
+        monkeypatch.setenv("MFA_ACC_IMPL", impl)
+        dm.acc_zero()
+        dm.acc_stats(feats, ali)
+        got = dm.acc_read()
+        assert got["frames"] == T
+        assert abs(got["like"] - lse.sum()) <= 2e-6 * abs(lse.sum()), impl
+        assert np.allclose(got["occ"], occ_ref, rtol=1e-3, atol=2e-3), impl
+        assert np.allclose(got["mean"][:, 0], mean0_ref, rtol=1e-3, atol=5e-3), impl
+        assert np.array_equal(got["trans"][1:], np.bincount(ali, minlength=nt + 1)[1:])
+    dm.close()
