@@ -308,7 +308,16 @@ def main():
         seconds = min(seconds, 1800.0)
     t0 = time.time()
     sc = SC.build(eng, seconds, seed=1234 + rank, target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
-                  synth_device=dev, log=log if rank == 0 else None)
+                  synth_device=dev, log=log if rank == 0 else None, model_seed=1234 if world > 1 else None)
+    if dist is not None:
+        # one replicated acoustic model (rank 0's estimate), each rank its own shard of utterances: what MFA's jobs see
+        box = [(sc.am.dim, sc.am.offsets, sc.am.weights, sc.am.means_invvars, sc.am.inv_vars) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            from mfa_b200.kaldi_io import AmDiagGmm
+            sc.am = AmDiagGmm(*box[0])
+            sc.model.close()
+            sc.model = E.DeviceModel(eng, sc.tm, sc.am)
     c = sc.corpus
     audio_s = c.seconds
     n_frames = int(sc.frame_off[-1])

@@ -31,12 +31,16 @@ class Scenario:
 
 
 def build(engine: E.Engine, seconds: float, seed: int = SY.SEED, triphone: bool = True, target_pdfs: int = 4000, gauss_per_pdf: int = 10,
-          use_lda: bool = True, n_phones: int = 40, n_words: int = 2000, n_threads: int = 8, synth_device=None, log=None) -> Scenario:
+          use_lda: bool = True, n_phones: int = 40, n_words: int = 2000, n_threads: int = 8, synth_device=None, log=None,
+          model_seed: Optional[int] = None) -> Scenario:
+    """model_seed (multi-rank runs): lexicon, phone spectra, tree, transition model and LDA are drawn from it and are therefore the
+    same on every rank; `seed` then only selects the rank's own utterances / speakers.  The Gaussians are still estimated from this
+    rank's features: a replicated model additionally needs rank 0's AmDiagGmm broadcast (bench.py does that)."""
     t = {}
     t0 = time.time()
-    corpus = SY.make_corpus(seconds, seed=seed, n_phones=n_phones, n_words=n_words, device=synth_device)
+    corpus = SY.make_corpus(seconds, seed=seed, n_phones=n_phones, n_words=n_words, device=synth_device, lexicon_seed=model_seed)
     t["corpus"] = time.time() - t0
-    rng = np.random.default_rng(seed + 1)
+    rng = np.random.default_rng((seed if model_seed is None else model_seed) + 1)
     topo = SY.make_topology(corpus.phone_table)
     tree, n_pdfs = SY.make_tree(rng, topo, triphone, target_pdfs)
     tm = SY.make_transition_model(topo, tree, n_pdfs)

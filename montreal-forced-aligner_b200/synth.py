@@ -75,14 +75,17 @@ def _phone_spectra(rng: np.random.Generator, n_ids: int) -> np.ndarray:
 
 def make_corpus(seconds: float, seed: int = SEED, n_phones: int = 40, n_words: int = 2000, n_spk: Optional[int] = None,
                 position_dependent: bool = False, mean_utt_s: float = 12.3, min_utt_s: float = 1.0, max_utt_s: float = 30.0,
-                device=None) -> SynthCorpus:
-    """Generate ~``seconds`` of audio.  ``device`` (a torch device) moves the waveform synthesis onto the GPU."""
+                device=None, lexicon_seed: Optional[int] = None) -> SynthCorpus:
+    """Generate ~``seconds`` of audio.  ``device`` (a torch device) moves the waveform synthesis onto the GPU.
+    ``lexicon_seed`` (multi-rank runs): lexicon and phone spectra come from their own generator, so every rank shares one "language"
+    while ``seed`` gives it its own utterances and speakers."""
     rng = np.random.default_rng(seed)
-    lex, pt = make_lexicon(rng, n_phones, n_words, position_dependent)
+    rng_lex = rng if lexicon_seed is None else np.random.default_rng(lexicon_seed)
+    lex, pt = make_lexicon(rng_lex, n_phones, n_words, position_dependent)
     word_ids = [lex.word_table[w] for w in lex.prons if w.startswith("w")]
     sil = pt["sil"]
     n_ids = max(pt.values()) + 1
-    spectra = _phone_spectra(rng, n_ids)
+    spectra = _phone_spectra(rng_lex, n_ids)
     spectra[sil] = [300, 1200, 3000, 0.01, 0.01, 0.01, 0.03]
     if "spn" in pt:
         spectra[pt["spn"]] = [500, 1500, 2500, 0.1, 0.1, 0.1, 0.5]
