@@ -81,9 +81,15 @@ fmllr_frame_kernel(const float *__restrict__ feats, const int32_t *__restrict__ 
   }
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // stats per speaker (doubles): beta | K[D][D+1] | G[D][NP], NP = (D+1)(D+2)/2 (row-major lower triangle)
 template <int NIJ>
-__global__ void __launch_bounds__(ANT)
+__global__ void __launch_bounds__(ANT, NIJ <= 4 ? 2 : 1)
 fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab, const float *__restrict__ cnt, int dim,
                    const int64_t *__restrict__ frame_off, const int32_t *__restrict__ spk_utt_off, const int32_t *__restrict__ spk_utts,
                    int n_dtile, int n_split, double *__restrict__ stats, int64_t stats_stride) {
@@ -116,41 +122,65 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
   const int kd0 = t / D1, kj0 = t - kd0 * D1, kd1 = (t + ANT) / D1, kj1 = (t + ANT) - kd1 * D1;
   const bool k0ok = t < DT * D1, k1ok = t + ANT < DT * D1;
   double beta = 0.0;
+  // Batches of FB frames of this speaker, every n_split-th one for this CTA.  The next batch's global loads are issued into
+  // registers before the current batch is consumed (the f64 accumulation hides their latency), staged to shared memory as doubles.
+  const int xc = t & 63, xr = t >> 6;          // x: column xc of rows xr, xr+4, ..., xr+28
+  const int af = t >> 3, ad = t & 7;           // a / b: frame af, row d0 + ad
+  int ui = spk_utt_off[spk];
+  const int ui_end = spk_utt_off[spk + 1];
+  int64_t fb = 0, f1 = 0;
   int batch = 0;
-  for (int ui = spk_utt_off[spk]; ui < spk_utt_off[spk + 1]; ui++) {
-    const int u = spk_utts[ui];
-    const int64_t f0 = frame_off[u], f1 = frame_off[u + 1];
-    for (int64_t fb = f0; fb < f1; fb += FB, batch++) {
-      if (batch % n_split != split) continue;
-      const int n = (int)min((int64_t)FB, f1 - fb);
-      __syncthreads();
-      for (int i = t; i < n * D1; i += ANT) {
-        const int f = i / D1, j = i - f * D1;
-        s_xp[f][j] = j < dim ? (double)feats[(fb + f) * dim + j] : 1.0;
+  bool have_u = false;
+  auto next_batch = [&](int64_t &o_fb, int &o_n) -> bool {   // uniform across the CTA
+    for (;;) {
+      if (!have_u) {
+        if (ui >= ui_end) return false;
+        const int u = spk_utts[ui];
+        fb = frame_off[u]; f1 = frame_off[u + 1]; have_u = true;
       }
-      for (int i = t; i < n * DT; i += ANT) {
-        const int f = i / DT, d = i - f * DT;
-        const bool ok = d0 + d < dim && cnt[fb + f] != 0.0f;
-        s_a[f][d] = ok ? (double)ab[(size_t)(fb + f) * 2 * dim + d0 + d] : 0.0;
-        s_b[f][d] = ok ? (double)ab[(size_t)(fb + f) * 2 * dim + dim + d0 + d] : 0.0;
+      if (fb >= f1) { have_u = false; ui++; continue; }
+      const bool mine = (batch % n_split) == split;
+      o_fb = fb; o_n = (int)min((int64_t)FB, f1 - fb);
+      fb += FB; batch++;
+      if (mine) return true;
+    }
+  };
+  float px[8], pa = 0.0f, pb = 0.0f, pc = 0.0f;
+  auto prefetch = [&](int64_t b0, int n) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int r = xr + 4 * k; px[k] = (r < n && xc < dim) ? __ldg(feats + (b0 + r) * dim + xc) : 0.0f; }
+    const bool ok = af < n && d0 + ad < dim;
+    pa = ok ? __ldg(ab + (size_t)(b0 + af) * 2 * dim + d0 + ad) : 0.0f;
+    pb = ok ? __ldg(ab + (size_t)(b0 + af) * 2 * dim + dim + d0 + ad) : 0.0f;
+    pc = t < n ? __ldg(cnt + b0 + t) : 0.0f;
+  };
+  int64_t cur_fb = 0; int cur_n = 0;
+  bool more = next_batch(cur_fb, cur_n);
+  if (more) prefetch(cur_fb, cur_n);
+  while (more) {
+    const int n = cur_n;
+    __syncthreads();   // the previous batch has been consumed
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int r = xr + 4 * k; if (xc < dim) s_xp[r][xc] = (double)px[k]; else if (xc == dim) s_xp[r][xc] = 1.0; }
+    s_a[af][ad] = (double)pa; s_b[af][ad] = (double)pb;
+    if (t < FB) s_c[t] = t < n ? pc : 0.0f;
+    __syncthreads();
+    more = next_batch(cur_fb, cur_n);
+    if (more) prefetch(cur_fb, cur_n);
+    if (dtile == 0 && t < 32) { const double c = warp_sum_d((double)s_c[t]); if (t == 0) beta += c; }
+    for (int f = 0; f < n; f++) {
+      if (s_c[f] == 0.0f) continue;   // dropped frame (weight 0): Kaldi never sees it
+      double b[DT];
+#pragma unroll
+      for (int d = 0; d < DT; d += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_b[f][d]); b[d] = v.x; b[d + 1] = v.y; }
+#pragma unroll
+      for (int k = 0; k < NIJ; k++) {
+        const double z = s_xp[f][pi[k]] * s_xp[f][pj[k]];
+#pragma unroll
+        for (int d = 0; d < DT; d++) g[k][d] += b[d] * z;
       }
-      if (t < n) s_c[t] = cnt[fb + t];
-      __syncthreads();
-      for (int f = 0; f < n; f++) {
-        if (s_c[f] == 0.0f) continue;   // dropped frame (weight 0): Kaldi never sees it
-        double b[DT];
-#pragma unroll
-        for (int d = 0; d < DT; d += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_b[f][d]); b[d] = v.x; b[d + 1] = v.y; }
-#pragma unroll
-        for (int k = 0; k < NIJ; k++) {
-          const double z = s_xp[f][pi[k]] * s_xp[f][pj[k]];
-#pragma unroll
-          for (int d = 0; d < DT; d++) g[k][d] += b[d] * z;
-        }
-        if (k0ok) kacc[0] += s_a[f][kd0] * s_xp[f][kj0];
-        if (k1ok) kacc[1] += s_a[f][kd1] * s_xp[f][kj1];
-        if (t == 0) beta += (double)s_c[f];
-      }
+      if (k0ok) kacc[0] += s_a[f][kd0] * s_xp[f][kj0];
+      if (k1ok) kacc[1] += s_a[f][kd1] * s_xp[f][kj1];
     }
   }
   double *st = stats + (size_t)spk * stats_stride;
