@@ -160,3 +160,32 @@ def test_acc_stats_against_float64():
     assert np.allclose(accs["mean"], mean, rtol=1e-4, atol=1e-4) and np.allclose(accs["var"], var, rtol=1e-4, atol=1e-3)
     assert abs(accs["like"][0] - like) < 1e-5 * abs(like)
     assert accs["trans"].sum() == x.shape[0] and abs(accs["occ"].sum() - x.shape[0]) < 1e-3
+
+
+def test_gmm_loglikes_and_posteriors_against_sklearn():
+    """An independent implementation of the same model: scikit-learn's diagonal GaussianMixture, loaded with the reference's own
+    fixture model (tests/data/am/acoustic_g2p_output_model.zip -> golden arrays).  score_samples == per-pdf log-likelihood,
+    predict_proba == the component posteriors behind the K4 / fMLLR statistics."""
+    from sklearn.mixture import GaussianMixture
+    tm, am, _ = load_model("g2p")
+    rng = np.random.default_rng(5)
+    D = am.dim
+    X = (am.means()[rng.integers(0, am.NumGauss(), size=64)] + 0.5 * rng.standard_normal((64, D))).astype(np.float32)
+    ll = O.gmm_loglikes(O.GmmModel.from_am(am), X)
+    g = O.GmmModel.from_am(am)
+    checked = 0
+    for j in list(range(0, am.NumPdfs(), max(1, am.NumPdfs() // 25)))[:25]:
+        a, b = int(am.offsets[j]), int(am.offsets[j + 1])
+        gm = GaussianMixture(n_components=b - a, covariance_type="diag")
+        gm.weights_ = am.weights[a:b].astype(np.float64) / am.weights[a:b].sum()
+        gm.means_ = am.means()[a:b].astype(np.float64)
+        gm.covariances_ = am.variances()[a:b].astype(np.float64)
+        gm.precisions_cholesky_ = 1.0 / np.sqrt(gm.covariances_)
+        ref = gm.score_samples(X.astype(np.float64))
+        assert np.abs(ll[:, j] - ref).max() <= 1e-4 * np.abs(ref).max(), j
+        # posteriors through the accumulator: one frame at a time, occ == predict_proba
+        tid = int(np.nonzero(tm.tid2pdf == j)[0][0])
+        acc = O.acc_stats(g, tm.tid2pdf, X[:8], np.full(8, tid, np.int32), tm.num_tids)
+        assert np.allclose(acc["occ"][a:b], gm.predict_proba(X[:8].astype(np.float64)).sum(0), rtol=1e-3, atol=1e-4)
+        checked += 1
+    assert checked >= 10
