@@ -21,6 +21,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "cuda_internal.cuh"
@@ -156,6 +158,8 @@ struct TcParams {
   const TcItem *items;    // [n_items]
   int n_items;
   float *out;             // pdf-major blocks: out[item.out_off + (meta.pdf0 + k) * item.ld + frame]
+  int no_epilogue;        // MFA_TC_NOEPI=1 (experiment): epilogue warps release the accumulators without reading them
+  long long *dbg;         // optional [grid][4]: cycles the MMA issuer waited on full_a, full_b, tempty, and its whole loop (MFA_TC_DEBUG=1)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -208,17 +212,26 @@ gmm_tc_kernel(TcParams p) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t cnt = 0, it = 0;
+      long long w_a = 0, w_b = 0, w_t = 0;
+      const bool dbg = p.dbg != nullptr;
+      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         const uint32_t n_b = p.items[item].n_b, rows_valid = p.items[item].rows_valid;
+        long long c0 = dbg ? clock64() : 0;
         mbar_wait(full_a, it & 1);
+        if (dbg) w_a += clock64() - c0;
         tc_fence_after();
         for (uint32_t n = 0; n < n_b; n++, cnt++) {
           const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
+          c0 = dbg ? clock64() : 0;
           mbar_wait(full_b + s, ph);
+          if (dbg) w_b += clock64() - c0;
           tc_fence_after();
 #pragma unroll
           for (int f = 0; f < 2; f++) {
+            c0 = dbg ? clock64() : 0;
             mbar_wait(tempty + s * 2 + f, ph ^ 1);
+            if (dbg) w_t += clock64() - c0;
             tc_fence_after();
             if (f == 0 || rows_valid > TM) {   // a pair whose second tile holds no frames skips its 18 MMAs
               const uint32_t d = tmem_base + s * 256 + f * 128;
@@ -237,6 +250,7 @@ gmm_tc_kernel(TcParams p) {
         }
         umma_commit(empty_a);
       }
+      if (dbg) { long long *o = p.dbg + 4 * blockIdx.x; o[0] += w_a; o[1] += w_b; o[2] += w_t; o[3] += clock64() - t_begin; }
     }
   } else if (warp >= 4) {
     // ===== epilogue: 16 warps = 2 accumulator stages x 2 frame tiles x 4 lane quarters; thread = one frame (TMEM lane).
@@ -257,7 +271,7 @@ gmm_tc_kernel(TcParams p) {
         const TcMeta cur = p.meta[n];
         mbar_wait(tfull + s * 2 + f, ph);
         tc_fence_after();
-        if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); continue; }
+        if (!tile_live || p.no_epilogue) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); continue; }
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         float cmx = -INFINITY, cs = 0.0f;
         float *out = out_base + (size_t)cur.pdf0 * I.ld;
@@ -327,6 +341,28 @@ __global__ void gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_g
   }
   const size_t off = (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES + ((size_t)(kc * (TN / 8) + r / 8) * 64 + (size_t)(r % 8) * 8) * 2;
   *(uint4 *)(b_img + off) = v;
+}
+
+
+// MFA_TC_DEBUG=1: a device buffer [1024][4] of cycle counters filled by the MMA issuer threads; printed (and cleared) by tc_debug_dump
+static long long *g_tc_dbg = nullptr;
+static long long *tc_debug_buffer(mfa_engine *e) {
+  static int on = -1;
+  if (on < 0) { const char *v = getenv("MFA_TC_DEBUG"); on = v && atoi(v) ? 1 : 0; }
+  if (!on) return nullptr;
+  if (!g_tc_dbg) { if (cudaMalloc((void **)&g_tc_dbg, 1024 * 4 * sizeof(long long)) != cudaSuccess) return nullptr; cudaMemset(g_tc_dbg, 0, 1024 * 4 * sizeof(long long)); }
+  (void)e;
+  return g_tc_dbg;
+}
+static void tc_debug_dump(mfa_engine *e, int grid) {
+  if (!g_tc_dbg) return;
+  cudaStreamSynchronize(e->stream);
+  std::vector<long long> h(1024 * 4);
+  cudaMemcpy(h.data(), g_tc_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_tc_dbg, 0, h.size() * sizeof(long long));
+  double a = 0, b = 0, t = 0, tot = 0;
+  for (int i = 0; i < grid && i < 1024; i++) { a += h[4 * i]; b += h[4 * i + 1]; t += h[4 * i + 2]; tot += h[4 * i + 3]; }
+  if (tot > 0) fprintf(stderr, "[tc-debug] MMA issuer: wait full_a %.1f%%  full_b %.1f%%  tempty %.1f%%  of %.0f cycles per CTA\n", 100 * a / tot, 100 * b / tot, 100 * t / tot, tot / grid);
 }
 
 // host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
@@ -415,6 +451,7 @@ int launch_tc(mfa_engine *e, const TcParams &p) {
   CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.n_items, e->sm_count);
   gmm_tc_kernel<<<grid, NTHREADS, smem, e->stream>>>(p);
+  if (p.dbg) tc_debug_dump(e, grid);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MFA_OK;
@@ -461,6 +498,8 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   TcItem *d_items;
   MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
   TcParams p;
+  p.dbg = tc_debug_buffer(e);
+  { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
@@ -543,6 +582,8 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   gather_b_kernel<<<(unsigned)((tot_b + 255) / 256), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, d_src, d_b, n_bt, 2 * m->dim);
   e->launches++;
   TcParams p;
+  p.dbg = tc_debug_buffer(e);
+  { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
   return launch_tc(e, p);
 }
