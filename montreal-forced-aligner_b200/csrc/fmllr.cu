@@ -212,24 +212,23 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// out[i] = sum_j M[i][j] v[j] for an n x n row-major matrix in global memory; v, out in shared memory.  Rows are dealt to warps.
-__device__ __forceinline__ void matvec_rows(const double *M, const double *v, double *out, int n, int warp, int lane) {
-  constexpr int NW = UNT / 32, MAXR = 9;   // n <= 65 -> at most 9 rows per warp
-  double acc[MAXR];
+// out[i] = sum_j M[i][j] v[j] for an n x n row-major matrix in global memory; v, out in shared memory.  Eight lanes share a row (32 rows
+// per pass over the CTA's 256 threads), partial sums meet in three shuffles.
+__device__ __forceinline__ void matvec_rows(const double *M, const double *v, double *out, int n, int t) {
+  const int sub = t & 7;
 #pragma unroll
-  for (int k = 0; k < MAXR; k++) {
-    const int i = warp + k * NW;
+  for (int pass = 0; pass < 3; pass++) {   // n <= 65 < 96
+    const int i = (t >> 3) + 32 * pass;
+    if (32 * pass >= n) break;             // uniform
     double a = 0.0;
     if (i < n) {
-      const double *row = M + (size_t)i * n;
-      for (int j = lane; j < n; j += 32) a += row[j] * v[j];   // plain loads: this CTA wrote M earlier in the kernel
+      const double *row = M + (size_t)i * n;   // plain loads: this CTA wrote M earlier in the kernel
+      for (int j = sub; j < n; j += 8) a += row[j] * v[j];
     }
-    acc[k] = a;
-  }
-#pragma unroll
-  for (int k = 0; k < MAXR; k++) {
-    const int i = warp + k * NW;
-    if (i < n) { const double r = warp_sum(acc[k]); if (lane == 0) out[i] = r; }   // i is warp-uniform
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    if (i < n && sub == 0) out[i] = a;
   }
 }
 
@@ -349,6 +348,10 @@ fmllr_update_kernel(const double *__restrict__ stats, int64_t stats_stride, int 
   int *s_piv = reinterpret_cast<int *>(s_ld + 1);
   for (int idx = t; idx < D * D1; idx += UNT) W[idx] = (idx / D1 == idx % D1) ? 1.0 : 0.0;
   __syncthreads();
+  constexpr int MAXE = (64 * 64 + UNT - 1) / UNT;   // D x D elements per thread, D <= 64
+  unsigned char ei[MAXE], ej[MAXE];
+#pragma unroll
+  for (int k = 0; k < MAXE; k++) { const int idx = t + k * UNT; ei[k] = (unsigned char)(idx < D * D ? idx / D : 0); ej[k] = (unsigned char)(idx < D * D ? idx % D : 0); }
   // objective at the unit transform: log|det| = 0
   const double old_objf = (double)(float)cta_auxf(W, K, Gp, beta, 0.0, D, s_red);
   for (int it = 0; it < num_iters; it++) {
@@ -359,7 +362,7 @@ fmllr_update_kernel(const double *__restrict__ stats, int64_t stats_stride, int 
       const double *iG = invG + (size_t)d * D1 * D1, *k = K + (size_t)d * D1;
       if (t < D1) cvec[t] = t < D ? Ainv[t * D + d] : 0.0;
       __syncthreads();
-      matvec_rows(iG, cvec, cg, D1, warp, lane);
+      matvec_rows(iG, cvec, cg, D1, t);
       __syncthreads();
       double p1 = 0.0, p2 = 0.0;
       for (int j = lane; j < D1; j += 32) { p1 += cg[j] * cvec[j]; p2 += cg[j] * k[j]; }
@@ -370,7 +373,7 @@ fmllr_update_kernel(const double *__restrict__ stats, int64_t stats_stride, int 
       const double alpha = f1 > f2 ? a1 : a2;
       if (t < D1) vvec[t] = alpha * cvec[t] + k[t];
       __syncthreads();
-      matvec_rows(iG, vvec, wnew, D1, warp, lane);
+      matvec_rows(iG, vvec, wnew, D1, t);
       __syncthreads();
       if (t < D) { delta[t] = wnew[t] - W[d * D1 + t]; u[t] = Ainv[t * D + d]; }
       __syncthreads();
@@ -378,7 +381,8 @@ fmllr_update_kernel(const double *__restrict__ stats, int64_t stats_stride, int 
       if (t < D) { double a = 0.0; for (int i = 0; i < D; i++) a += delta[i] * Ainv[i * D + t]; vv[t] = a; }
       __syncthreads();
       const double inv_den = 1.0 / (1.0 + vv[d]);
-      for (int idx = t; idx < D * D; idx += UNT) { const int i = idx / D, j = idx - i * D; Ainv[idx] -= u[i] * vv[j] * inv_den; }
+#pragma unroll
+      for (int k = 0; k < MAXE; k++) { const int idx = t + k * UNT; if (idx < D * D) Ainv[idx] -= u[ei[k]] * vv[ej[k]] * inv_den; }
       __syncthreads();
     }
   }

@@ -437,7 +437,8 @@ def test_fmllr_stats_and_transforms_parity(eng, two_models, use_lda):
     Wd, impr_d, count_d = eng.fmllr_update(got, D, 40, 100.0)                      # the CUDA update kernel (host buffers)
     Wt, impr_t, _ = eng.fmllr_update(got_d, D, 40, 100.0)                           # ... and on the device-resident statistics
     eng.sync()
-    assert np.allclose(count_d, got[:, 0]) and np.abs(Wt.cpu().numpy() - Wd).max() == 0.0 and np.array_equal(impr_t, impr_d)
+    # (the two statistics blocks come from two accumulation runs: f64 atomics reorder sums, so the transforms agree to rounding only)
+    assert np.allclose(count_d, got[:, 0]) and np.abs(Wt.cpu().numpy() - Wd).max() < 1e-4 and np.allclose(impr_t, impr_d, rtol=1e-4, atol=1e-2)
     for s in range(c.n_spk):
         Wo, io = O.fmllr_update(stats_ref[s], D, min_count=100.0)
         assert np.abs(W[s] - Wo).max() < 1e-3 and abs(impr[s] - io) <= 1e-3 * max(1.0, abs(io))
