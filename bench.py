@@ -486,7 +486,7 @@ def main():
                 traffic = tj[key] * per_launch_flops
         k2 = {"kernel": "K2 gmm log-likelihoods (xsplit + gather_b + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved,
               "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": traffic,
-              "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * 96.0 / (2 * sc.am.dim + 1),
+              "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * (80.0 if 2 * sc.am.dim <= 80 and not int(os.environ.get("MFA_TC_K96", "0") or 0) else 96.0) / (2 * sc.am.dim + 1),
               "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs", "launches_per_step": gmm_n, "avg_launch_ms": avg_ms,
               "algorithmic_flops_per_launch": per_launch_flops, "share_of_step": gmm_ms / step_ms}
     # K3 (band kernel): algorithmic bytes per utterance = T * (4 P_u log-likelihoods read once + 512 back-pointer row

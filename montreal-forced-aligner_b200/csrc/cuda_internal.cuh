@@ -141,7 +141,9 @@ struct mfa_model {
   std::vector<float> h_tc_colscale;    // per-dimension power-of-two feature scaling folded into the weights
   float *d_tc_colscale = nullptr;
   bool tc_ready = false;
-  void *d_tc_rows = nullptr;           // fp16 hi/lo weight rows [2][G][96] (row-major; source of the per-utterance tile gather)
+  void *d_tc_rows = nullptr;           // fp16 hi/lo weight rows [2][G][tc_k] (row-major; source of the per-utterance tile gather)
+  int tc_k = 96;                       // K extent of the operand images: 80 (gconst added by the epilogue) or 96 (gconst as fp16 columns)
+  float *d_tc_g = nullptr;             // gconst * log2(e): [G] per Gaussian, then [n_tiles][128] per column of the dense tiling
   uint64_t tc_version = 0;             // bumps whenever the tiling / weights change (invalidates cached ragged plans)
   double *d_acc = nullptr;
   int rebuild_tiles();

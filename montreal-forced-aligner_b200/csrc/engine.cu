@@ -188,7 +188,7 @@ extern "C" int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops) {
 mfa_model::~mfa_model() {
   cudaSetDevice(device);
   for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_tile_pdf0,
-                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows})
+                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows, (void *)d_tc_g})
     if (p) cudaFree(p);
 }
 

@@ -31,9 +31,12 @@ using namespace mfa;
 
 namespace {
 
-constexpr int TM = 128, TN = MFA_TILE_N, TK = 96, KC = TK / 8;
-constexpr uint32_t IMG_BYTES = TM * TK * 2;       // one fp16 image (hi or lo) of a 128 x 96 tile
-constexpr uint32_t TILE_BYTES = 2 * IMG_BYTES;    // hi + lo
+constexpr int TM = 128, TN = MFA_TILE_N;
+// Two geometries.  K = 80 (2 dim <= 80; MFA's 39 / 40-dimensional features): the gconst is added by the epilogue from a per-tile fp32
+// array, 5 k-steps x 3 products = 15 MMAs per tile, 40 KB tiles, a THREE-stage B ring.  K = 96 (2 dim + 3 <= 96, or MFA_TC_K96=1): the
+// gconst rides as three fp16 columns against ones, 18 MMAs per tile, 48 KB tiles, two-stage ring (the first version of this kernel).
+__host__ __device__ constexpr uint32_t img_bytes(int tk) { return (uint32_t)(TM * tk * 2); }   // one fp16 image (hi or lo) of a 128 x tk tile
+__host__ __device__ constexpr uint32_t tile_bytes(int tk) { return 2 * img_bytes(tk); }         // hi + lo
 constexpr uint32_t LBO_BYTES = (TM / 8) * 128;    // K-adjacent core matrices
 constexpr uint32_t SBO_BYTES = 128;               // row-group-adjacent core matrices
 constexpr int NTHREADS = 640;   // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
@@ -108,8 +111,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // boundaries, so the segmented max / sum scans run over 8 group values: group max (tree) -> forward running max -> backward
 // broadcast of each pdf's max -> exp2 of the 32 values against their pdf's max -> group sums -> forward running sum; one
 // log2 + store per finished pdf.  (cmx, cs) carry an unfinished pdf into the next chunk.  All predicates are warp-uniform.
-__device__ __forceinline__ void lse_chunk(const uint32_t (&vr)[32], uint32_t gs, uint32_t ge, float &cmx, float &cs, float *&out, int64_t ld,
-                                          bool row_ok) {
+template <bool GEPI>
+__device__ __forceinline__ void lse_chunk(uint32_t (&vr)[32], const float *gp, uint32_t gs, uint32_t ge, float &cmx, float &cs, float *&out,
+                                          int64_t ld, bool row_ok) {
+  if (GEPI) {   // gconst of the chunk's 32 columns from shared memory (every thread reads the same words: broadcasts)
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      const float4 q = *reinterpret_cast<const float4 *>(gp + 4 * g);
+      vr[4 * g] = __float_as_uint(__uint_as_float(vr[4 * g]) + q.x); vr[4 * g + 1] = __float_as_uint(__uint_as_float(vr[4 * g + 1]) + q.y);
+      vr[4 * g + 2] = __float_as_uint(__uint_as_float(vr[4 * g + 2]) + q.z); vr[4 * g + 3] = __float_as_uint(__uint_as_float(vr[4 * g + 3]) + q.w);
+    }
+  }
   float r[8];
   float run = cmx;
 #pragma unroll
@@ -152,9 +164,10 @@ struct TcItem {
 static_assert(sizeof(TcItem) == 32, "TcItem must be 32 bytes");
 
 struct TcParams {
-  const uint8_t *a_img;   // [n_frame_tiles (even)][TILE_BYTES]
-  const uint8_t *b_img;   // [n_b_tiles][TILE_BYTES]
+  const uint8_t *a_img;   // [n_frame_tiles (even)][tile_bytes]
+  const uint8_t *b_img;   // [n_b_tiles][tile_bytes]
   const TcMeta *meta;     // [n_b_tiles]; pdf0 = first output row of the tile (global pdf id, or utterance-local pdf index)
+  const float *g_tiles;   // K = 80 geometry: [n_b_tiles][128] gconst * log2(e) per tile column (padding: -60000)
   const TcItem *items;    // [n_items]
   int n_items;
   float *out;             // pdf-major blocks: out[item.out_off + (meta.pdf0 + k) * item.ld + frame]
@@ -162,20 +175,25 @@ struct TcParams {
   long long *dbg;         // optional [grid][4]: cycles the MMA issuer waited on full_a, full_b, tempty, and its whole loop (MFA_TC_DEBUG=1)
 };
 
+template <int TKt, int NBt, bool GEPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gmm_tc_kernel(TcParams p) {
+  constexpr uint32_t IMG_BYTES = img_bytes(TKt), TILE_BYTES = tile_bytes(TKt);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sA = smem;                       // 2 frame tiles x (hi, lo)
-  uint8_t *sB = smem + 2 * TILE_BYTES;      // 2 stages x (hi, lo)
-  uint64_t *bars = (uint64_t *)(smem + 4 * TILE_BYTES);
-  uint64_t *full_a = bars + 0, *empty_a = bars + 1, *full_b = bars + 2, *empty_b = bars + 4, *tfull = bars + 6, *tempty = bars + 10;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 14);
+  uint8_t *sB = smem + 2 * TILE_BYTES;      // NBt stages x (hi, lo)
+  float *sG = (float *)(smem + (2 + NBt) * TILE_BYTES);   // 2 x 128 gconsts (one row per accumulator stage)
+  uint64_t *bars = (uint64_t *)(smem + (2 + NBt) * TILE_BYTES + 1024);
+  uint64_t *full_a = bars + 0, *empty_a = bars + 1, *full_b = bars + 2, *empty_b = bars + 2 + NBt, *tfull = bars + 2 + 2 * NBt,
+           *tempty = tfull + 4, *gfull = tempty + 4, *gempty = gfull + 2;
+  uint32_t *tmem_slot = (uint32_t *)(gempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(full_a, 1); mbar_init(empty_a, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
+    for (int s = 0; s < NBt; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
     for (int i = 0; i < 4; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+    for (int i = 0; i < 2; i++) { mbar_init(gfull + i, 1); mbar_init(gempty + i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -191,17 +209,32 @@ gmm_tc_kernel(TcParams p) {
   if (warp == 0) {
     // ===== producer: bulk copies of the A pair (once per item) and of each B tile =====
     if (lane == 0) {
-      uint32_t cnt = 0, it = 0;
+      uint32_t cnt = 0, it = 0, sb = 0, phb = 0;   // sb / phb: slot of the B ring and the phase of its barriers
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         const TcItem I = p.items[item];
         mbar_wait(empty_a, (it & 1) ^ 1);
         mbar_expect_tx(full_a, 2 * TILE_BYTES);
         bulk_g2s(sA, p.a_img + (size_t)I.a_tile * TILE_BYTES, 2 * TILE_BYTES, full_a);
         for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
-          const uint32_t s = cnt & 1;
-          mbar_wait(empty_b + s, ((cnt >> 1) & 1) ^ 1);
-          mbar_expect_tx(full_b + s, TILE_BYTES);
-          bulk_g2s(sB + s * TILE_BYTES, p.b_img + (size_t)n * TILE_BYTES, TILE_BYTES, full_b + s);
+          mbar_wait(empty_b + sb, phb ^ 1);
+          mbar_expect_tx(full_b + sb, TILE_BYTES);
+          bulk_g2s(sB + sb * TILE_BYTES, p.b_img + (size_t)n * TILE_BYTES, TILE_BYTES, full_b + sb);
+          if (++sb == NBt) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== gconst producer (K = 80 geometry): the tile's 128 gconsts travel with the accumulator stage (cnt & 1) and are released by
+    // the epilogue warps -- its own thread, so a slow epilogue never delays the B ring =====
+    if (GEPI && lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const TcItem I = p.items[item];
+        for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
+          const uint32_t sg = cnt & 1;
+          mbar_wait(gempty + sg, ((cnt >> 1) & 1) ^ 1);
+          mbar_expect_tx(gfull + sg, TN * 4);
+          bulk_g2s(sG + sg * TN, p.g_tiles + (size_t)n * TN, TN * 4, gfull + sg);
         }
       }
     }
@@ -211,7 +244,7 @@ gmm_tc_kernel(TcParams p) {
       // InstrDescriptor: c_format=F32 (1<<4), a/b format F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      uint32_t cnt = 0, it = 0;
+      uint32_t cnt = 0, it = 0, sb = 0, phb = 0;
       long long w_a = 0, w_b = 0, w_t = 0;
       const bool dbg = p.dbg != nullptr;
       const long long t_begin = clock64();
@@ -224,7 +257,7 @@ gmm_tc_kernel(TcParams p) {
         for (uint32_t n = 0; n < n_b; n++, cnt++) {
           const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
           c0 = dbg ? clock64() : 0;
-          mbar_wait(full_b + s, ph);
+          mbar_wait(full_b + sb, phb);
           if (dbg) w_b += clock64() - c0;
           tc_fence_after();
 #pragma unroll
@@ -235,18 +268,19 @@ gmm_tc_kernel(TcParams p) {
             tc_fence_after();
             if (f == 0 || rows_valid > TM) {   // a pair whose second tile holds no frames skips its 18 MMAs
               const uint32_t d = tmem_base + s * 256 + f * 128;
-              const uint32_t a0 = a_base + f * TILE_BYTES, b0 = b_base + s * TILE_BYTES;
+              const uint32_t a0 = a_base + f * TILE_BYTES, b0 = b_base + sb * TILE_BYTES;
 #pragma unroll
               for (int prod = 0; prod < 3; prod++) {
                 const uint32_t ao = a0 + (prod == 2 ? IMG_BYTES : 0), bo = b0 + (prod == 1 ? IMG_BYTES : 0);
 #pragma unroll
-                for (int k = 0; k < TK / 16; k++)
+                for (int k = 0; k < TKt / 16; k++)
                   umma_f16(d, make_desc(ao + k * 2 * LBO_BYTES), make_desc(bo + k * 2 * LBO_BYTES), idesc, (prod | k) != 0);
               }
             }
             umma_commit(tfull + s * 2 + f);
           }
-          umma_commit(empty_b + s);
+          umma_commit(empty_b + sb);
+          if (++sb == NBt) { sb = 0; phb ^= 1; }
         }
         umma_commit(empty_a);
       }
@@ -271,7 +305,9 @@ gmm_tc_kernel(TcParams p) {
         const TcMeta cur = p.meta[n];
         mbar_wait(tfull + s * 2 + f, ph);
         tc_fence_after();
-        if (!tile_live || p.no_epilogue) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); continue; }
+        if (GEPI) mbar_wait(gfull + s, ph);
+        if (!tile_live || p.no_epilogue) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); if (GEPI) mbar_arrive(gempty + s); continue; }
+        const float *gs = sG + s * TN;
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         float cmx = -INFINITY, cs = 0.0f;
         float *out = out_base + (size_t)cur.pdf0 * I.ld;
@@ -281,8 +317,9 @@ gmm_tc_kernel(TcParams p) {
           tmem_ld32(t0 + 32 * c, v);
           tmem_ld_wait();
           if (c == 3) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); }   // accumulator drained: the MMA warp may overwrite it
-          lse_chunk(v, (cur.gstart >> (8 * c)) & 0xFF, (cur.gend >> (8 * c)) & 0xFF, cmx, cs, out, I.ld, row_ok);
+          lse_chunk<GEPI>(v, gs + 32 * c, (cur.gstart >> (8 * c)) & 0xFF, (cur.gend >> (8 * c)) & 0xFF, cmx, cs, out, I.ld, row_ok);
         }
+        if (GEPI) mbar_arrive(gempty + s);   // this thread is done with the stage's gconsts
       }
     }
   }
@@ -294,7 +331,9 @@ gmm_tc_kernel(TcParams p) {
 // features fp32 -> A images (fp16 hi / lo, canonical layout), one 48 KB image per 128-frame tile.  Tile t covers feature rows
 // tile_row0[t] .. tile_row0[t] + tile_rows[t] - 1 (rows beyond that are zero), so tiles may follow utterance boundaries.
 __global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const float *__restrict__ colscale, uint8_t *__restrict__ a_img,
-                              int64_t n_tiles, const int64_t *__restrict__ tile_row0, const int32_t *__restrict__ tile_rows, int64_t dense_rows) {
+                              int64_t n_tiles, const int64_t *__restrict__ tile_row0, const int32_t *__restrict__ tile_rows, int64_t dense_rows,
+                              int KC, int ones) {
+  const uint32_t IMG_BYTES = img_bytes(KC * 8), TILE_BYTES = 2 * IMG_BYTES;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, kc, row)
   if (idx >= n_tiles * KC * TM) return;
   const int r = (int)(idx % TM), kc = (int)((idx / TM) % KC);
@@ -312,7 +351,7 @@ __global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const fl
         float x = feats[row * dim + (k < dim ? k : k - dim)] * colscale[k < dim ? k : k - dim];
         x = fminf(fmaxf(x, -240.0f), 240.0f);
         a = k < dim ? x : x * x;
-      } else if (k < 2 * dim + 3) a = 1.0f;
+      } else if (ones && k < 2 * dim + 3) a = 1.0f;
     }
     hi[e] = __float2half_rn(a);
     lo[e] = __float2half_rn(a - __half2float(hi[e]));
@@ -323,26 +362,44 @@ __global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const fl
 }
 
 // B images for utterance-specific Gaussian tiles: row r of tile t is Gaussian row_src[t*128 + r] of the model (row-major fp16
-// hi/lo weight rows), or padding (zero weights, gconst column = -60000 -> exp2 -> 0) when row_src < 0.
-__global__ void gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int32_t *__restrict__ row_src, uint8_t *__restrict__ b_img,
-                                int64_t n_tiles, int gcol) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tile, which, kc, row)
-  if (idx >= n_tiles * 2 * KC * TN) return;
-  const int r = (int)(idx % TN), kc = (int)((idx / TN) % KC), which = (int)((idx / (TN * KC)) % 2);
-  const int64_t tile = idx / (2 * TN * KC);
-  const int g = row_src[tile * TN + r];
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (g >= 0) v = *(const uint4 *)(w_rows + ((size_t)which * num_gauss + g) * TK + kc * 8);
-  else if (which == 0 && kc == gcol / 8) {
-    __half pad[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) pad[e] = __float2half_rn(e == gcol % 8 ? -60000.0f : 0.0f);
-    v = *(const uint4 *)pad;
+// hi/lo weight rows), or padding (zero weights; gconst -60000 -> exp2 -> 0) when row_src < 0.  One CTA per (tile, hi | lo): the 128
+// source rows are read as whole rows (consecutive threads = consecutive 16-byte pieces of a row: full sectors), re-ordered into the
+// canonical [k/8][row/8][8 rows][8 halves] image in shared memory and written out linearly.
+// gcol >= 0: K = 96 geometry (padding rows carry -60000 in the first gconst column); gcol < 0: K = 80 geometry, the per-tile gconst array
+// g_out[tile][128] is gathered here as well.
+__global__ void __launch_bounds__(256)
+gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int32_t *__restrict__ row_src, uint8_t *__restrict__ b_img,
+                int64_t n_tiles, int gcol, int KC, const float *__restrict__ g_src, float *__restrict__ g_out) {
+  __shared__ int s_src[TN];
+  __shared__ uint4 s_img[(TN + 1) * 12];   // up to K = 96; one padding unit per k-chunk keeps the transposing stores conflict-free
+  const int TK = KC * 8;
+  const uint32_t IMG_BYTES = img_bytes(TK), TILE_BYTES = 2 * IMG_BYTES;
+  const int64_t tile = blockIdx.x >> 1;
+  const int which = blockIdx.x & 1, t = threadIdx.x;
+  if (tile >= n_tiles) return;
+  if (t < TN) {
+    const int g = row_src[tile * TN + t];
+    s_src[t] = g;
+    if (g_out && which == 0) g_out[tile * TN + t] = g >= 0 ? g_src[g] : -60000.0f;
   }
-  const size_t off = (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES + ((size_t)(kc * (TN / 8) + r / 8) * 64 + (size_t)(r % 8) * 8) * 2;
-  *(uint4 *)(b_img + off) = v;
+  __syncthreads();
+  for (int c = t; c < TN * KC; c += 256) {
+    const int r = c / KC, kc = c - r * KC;
+    const int g = s_src[r];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g >= 0) v = *(const uint4 *)(w_rows + ((size_t)which * num_gauss + g) * TK + kc * 8);
+    else if (gcol >= 0 && which == 0 && kc == gcol / 8) {
+      __half pad[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) pad[e] = __float2half_rn(e == gcol % 8 ? -60000.0f : 0.0f);
+      v = *(const uint4 *)pad;
+    }
+    s_img[kc * (TN + 1) + r] = v;   // canonical image in 16-byte units: unit index = kc * 128 + r
+  }
+  __syncthreads();
+  uint4 *dst = (uint4 *)(b_img + (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES);
+  for (int c = t; c < TN * KC; c += 256) dst[c] = s_img[(c >> 7) * (TN + 1) + (c & (TN - 1))];
 }
-
 
 // MFA_TC_DEBUG=1: a device buffer [1024][4] of cycle counters filled by the MMA issuer threads; printed (and cleared) by tc_debug_dump
 static long long *g_tc_dbg = nullptr;
@@ -368,7 +425,12 @@ static void tc_debug_dump(mfa_engine *e, int grid) {
 // host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
 int build_tc(mfa_model *m) {
   const int D = m->dim;
-  if (2 * D + 3 > TK) return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96");
+  const char *force96 = getenv("MFA_TC_K96");
+  const bool k80 = 2 * D <= 80 && !(force96 && atoi(force96));
+  if (!k80 && 2 * D + 3 > 96) return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96");
+  const int TK = k80 ? 80 : 96, KC = TK / 8;
+  const uint32_t TILE_BYTES = tile_bytes(TK);
+  m->tc_k = TK;
   std::vector<double> m2(D, 0.0);
   for (int g = 0; g < m->num_gauss; g++)
     for (int d = 0; d < D; d++) {
@@ -384,6 +446,7 @@ int build_tc(mfa_model *m) {
   const int G = m->num_gauss;
   std::vector<__half> rows((size_t)2 * G * TK, __float2half_rn(0.0f));
   double wmax = 0.0;
+  std::vector<float> gl2(G);   // gconst * log2(e) per Gaussian (K = 80: added by the epilogue in fp32)
   auto split2 = [&](int g, int k, double w) {
     __half h = __float2half_rn((float)w);
     rows[((size_t)0 * G + g) * TK + k] = h;
@@ -398,12 +461,15 @@ int build_tc(mfa_model *m) {
     }
     double gc = (double)m->h_gconsts[g] * kLog2e;
     if (!(gc > -60000.0)) gc = -60000.0;
-    float g1 = __half2float(__float2half_rn((float)gc));
-    float g2 = __half2float(__float2half_rn((float)(gc - g1)));
-    float g3 = (float)(gc - g1 - g2);
-    rows[(size_t)g * TK + 2 * D] = __float2half_rn(g1);
-    rows[(size_t)g * TK + 2 * D + 1] = __float2half_rn(g2);
-    rows[(size_t)g * TK + 2 * D + 2] = __float2half_rn(g3);
+    gl2[g] = (float)gc;
+    if (!k80) {
+      float g1 = __half2float(__float2half_rn((float)gc));
+      float g2 = __half2float(__float2half_rn((float)(gc - g1)));
+      float g3 = (float)(gc - g1 - g2);
+      rows[(size_t)g * TK + 2 * D] = __float2half_rn(g1);
+      rows[(size_t)g * TK + 2 * D + 1] = __float2half_rn(g2);
+      rows[(size_t)g * TK + 2 * D + 2] = __float2half_rn(g3);
+    }
   }
   if (wmax > 60000.0) return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel");
   // dense tiling (all pdfs): per-tile masks + source rows; the images themselves are gathered on the device
@@ -426,16 +492,19 @@ int build_tc(mfa_model *m) {
   if (m->d_tc_w) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree(m->d_tc_w)); m->d_tc_w = nullptr; }
   if (m->d_tc_colscale) { CUDA_TRY(cudaFree(m->d_tc_colscale)); m->d_tc_colscale = nullptr; }
   if (m->d_tc_rows) { CUDA_TRY(cudaFree(m->d_tc_rows)); m->d_tc_rows = nullptr; }
-  const size_t img_bytes = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
-  m->tc_w_bytes = img_bytes;
-  CUDA_TRY(cudaMalloc(&m->d_tc_w, img_bytes + meta_bytes));
+  if (m->d_tc_g) { CUDA_TRY(cudaFree(m->d_tc_g)); m->d_tc_g = nullptr; }
+  const size_t img_total = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
+  m->tc_w_bytes = img_total;
+  CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + meta_bytes));
   CUDA_TRY(cudaMalloc(&m->d_tc_rows, rows.size() * sizeof(__half)));
+  CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, ((size_t)G + (size_t)nt * TN) * sizeof(float)));   // per Gaussian | dense per-tile array
+  CUDA_TRY(cudaMemcpyAsync(m->d_tc_g, gl2.data(), (size_t)G * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_rows, rows.data(), rows.size() * sizeof(__half), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_bytes, meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
   int32_t *d_src;
   MFA_TRY(m->eng->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
-  const int64_t total = (int64_t)nt * 2 * KC * TN;
-  gather_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, 2 * D);
+  gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D,
+                                                                   KC, m->d_tc_g, k80 ? m->d_tc_g + G : nullptr);
   m->eng->launches++;
   CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, D * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_colscale, m->h_tc_colscale.data(), D * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -446,11 +515,17 @@ int build_tc(mfa_model *m) {
   return MFA_OK;
 }
 
-int launch_tc(mfa_engine *e, const TcParams &p) {
-  const size_t smem = 4 * (size_t)TILE_BYTES + 256;
-  CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+int launch_tc(mfa_engine *e, const TcParams &p, int tk) {
   const int grid = std::min(p.n_items, e->sm_count);
-  gmm_tc_kernel<<<grid, NTHREADS, smem, e->stream>>>(p);
+  if (tk == 80) {
+    const size_t smem = 5 * (size_t)tile_bytes(80) + 1024 + 256;
+    CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<80, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_tc_kernel<80, 3, true><<<grid, NTHREADS, smem, e->stream>>>(p);
+  } else {
+    const size_t smem = 4 * (size_t)tile_bytes(96) + 1024 + 256;
+    CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<96, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gmm_tc_kernel<96, 2, false><<<grid, NTHREADS, smem, e->stream>>>(p);
+  }
   if (p.dbg) tc_debug_dump(e, grid);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -475,11 +550,14 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
     if (r == MFA_ERR_UNSUPPORTED) return launch_gmm_ffma(e, m, d_feats, n_rows, d_llT, ld);  // shapes the tcgen05 kernel does not cover
     if (r) return r;
   }
+  const int TK = m->tc_k, KC = TK / 8;
+  const uint32_t TILE_BYTES = tile_bytes(TK);
   const int64_t n_ftiles = (n_rows + TM - 1) / TM, n_pairs = (n_ftiles + 1) / 2;
   uint8_t *d_a;
   MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_pairs * 2 * TILE_BYTES, &d_a));
   const int64_t total = n_pairs * 2 * KC * TM;
-  xsplit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_pairs * 2, nullptr, nullptr, n_rows);
+  xsplit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_pairs * 2, nullptr, nullptr, n_rows, KC,
+                                                                         TK == 96);
   e->launches++;
   int splits = 1;
   if (n_pairs < 2 * (int64_t)e->sm_count) splits = (int)std::min<int64_t>(m->n_tiles, (2 * (int64_t)e->sm_count + n_pairs - 1) / n_pairs);
@@ -502,8 +580,9 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
+  p.g_tiles = m->d_tc_g + m->num_gauss;
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
-  return launch_tc(e, p);
+  return launch_tc(e, p, TK);
 }
 
 // ragged: for each utterance only the pdfs its graph references (g->lp2pdf), output block per utterance [P_u][ld_u]
@@ -512,6 +591,8 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
                          const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld) {
   if (n_utts == 0) return MFA_OK;
   if (!m->tc_ready) MFA_TRY(build_tc(m));
+  const int TK = m->tc_k, KC = TK / 8;
+  const uint32_t TILE_BYTES = tile_bytes(TK);
   // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles
   if (g->rag_version != m->tc_version) {
     g->rag_tile_off.assign(g->n_utts + 1, 0);
@@ -570,22 +651,24 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   const int64_t n_at = (int64_t)tile_row0.size();
   uint8_t *d_a, *d_b; int64_t *d_row0; int32_t *d_rows; TcItem *d_items;
   MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_at * TILE_BYTES, &d_a));
-  MFA_TRY(e->getT<uint8_t>(DB_BIMG, (size_t)n_bt * TILE_BYTES, &d_b));
+  MFA_TRY(e->getT<uint8_t>(DB_BIMG, (size_t)n_bt * TILE_BYTES + (size_t)n_bt * TN * sizeof(float), &d_b));
+  float *d_gt = (float *)(d_b + (size_t)n_bt * TILE_BYTES);   // per-tile gconsts behind the images (TILE_BYTES is a multiple of 16)
   MFA_TRY(e->upload(DB_TILE_ROW0, tile_row0.data(), tile_row0.size(), &d_row0));
   MFA_TRY(e->upload(DB_TILE_ROWS, tile_rows.data(), tile_rows.size(), &d_rows));
   MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
   const int64_t tot_a = n_at * KC * TM;
-  xsplit_kernel<<<(unsigned)((tot_a + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_at, d_row0, d_rows, 0);
+  xsplit_kernel<<<(unsigned)((tot_a + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_at, d_row0, d_rows, 0, KC, TK == 96);
   e->launches++;
   const int32_t *d_src = (const int32_t *)((const uint8_t *)g->d_rag + g->rag_meta_bytes) + bt0 * TN;
-  const int64_t tot_b = n_bt * 2 * KC * TN;
-  gather_b_kernel<<<(unsigned)((tot_b + 255) / 256), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, d_src, d_b, n_bt, 2 * m->dim);
+  gather_b_kernel<<<(unsigned)(2 * n_bt), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, d_src, d_b, n_bt,
+                                                                           TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g, TK == 80 ? d_gt : nullptr);
   e->launches++;
   TcParams p;
   p.dbg = tc_debug_buffer(e);
   { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
-  return launch_tc(e, p);
+  p.g_tiles = d_gt;
+  return launch_tc(e, p, TK);
 }
 
 }  // namespace mfa

@@ -94,9 +94,12 @@ def test_cmvn_and_feature_pipeline_parity(eng):
     assert relmax(out_a, np.concatenate(feats_a)) < 1e-5
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0, 96])
 @pytest.mark.parametrize("which", ["mono", "g2p"])
-def test_gmm_loglikes_parity(eng, impl, which):
+def test_gmm_loglikes_parity(eng, impl, which, monkeypatch):
+    if impl == 96:   # the K = 96 geometry of the tensor-core kernel (gconst as fp16 columns, two-stage ring) instead of K = 80
+        monkeypatch.setenv("MFA_TC_K96", "1")
+        impl = 0
     tm, am, _ = load_model(which)
     rng = np.random.default_rng(2)
     means = am.means()
