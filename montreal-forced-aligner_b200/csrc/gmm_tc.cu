@@ -422,6 +422,9 @@ static void tc_debug_dump(mfa_engine *e, int grid) {
   if (tot > 0) fprintf(stderr, "[tc-debug] MMA issuer: wait full_a %.1f%%  full_b %.1f%%  tempty %.1f%%  of %.0f cycles per CTA\n", 100 * a / tot, 100 * b / tot, 100 * t / tot, tot / grid);
 }
 
+// the dense per-tile gconst array follows the per-Gaussian one; bulk copies need a 16-byte aligned source
+static inline size_t tc_gpad(int64_t G) { return (size_t)((G + 3) & ~(int64_t)3); }
+
 // host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
 int build_tc(mfa_model *m) {
   const int D = m->dim;
@@ -497,14 +500,14 @@ int build_tc(mfa_model *m) {
   m->tc_w_bytes = img_total;
   CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + meta_bytes));
   CUDA_TRY(cudaMalloc(&m->d_tc_rows, rows.size() * sizeof(__half)));
-  CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, ((size_t)G + (size_t)nt * TN) * sizeof(float)));   // per Gaussian | dense per-tile array
+  CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, (tc_gpad(G) + (size_t)nt * TN) * sizeof(float)));   // per Gaussian | dense per-tile array
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_g, gl2.data(), (size_t)G * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_rows, rows.data(), rows.size() * sizeof(__half), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
   int32_t *d_src;
   MFA_TRY(m->eng->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
   gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D,
-                                                                   KC, m->d_tc_g, k80 ? m->d_tc_g + G : nullptr);
+                                                                   KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad(G) : nullptr);
   m->eng->launches++;
   CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, D * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_colscale, m->h_tc_colscale.data(), D * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -580,7 +583,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
-  p.g_tiles = m->d_tc_g + m->num_gauss;
+  p.g_tiles = m->d_tc_g + tc_gpad(m->num_gauss);
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
   return launch_tc(e, p, TK);
 }
