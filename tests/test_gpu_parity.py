@@ -503,3 +503,33 @@ def test_acc_stats_large_many_pdfs_against_numpy(eng, monkeypatch):
         assert np.allclose(got["mean"][:, 0], mean0_ref, rtol=1e-3, atol=5e-3), impl
         assert np.array_equal(got["trans"][1:], np.bincount(ali, minlength=nt + 1)[1:])
     dm.close()
+
+
+@pytest.mark.parametrize("k96", [False, True])
+def test_gmm_loglikes_odd_gaussian_count_and_ragged_pdfs(eng, monkeypatch, k96):
+    """Dense K2 on a model whose Gaussian count is odd and whose pdfs have 1..17 components (tiles with ragged pdf boundaries, a
+    trailing partial tile): both operand geometries against the oracle.  (A Gaussian count that is not a multiple of 4 once put the
+    per-tile gconst array of the K = 80 geometry on a misaligned address.)"""
+    from mfa_b200 import kaldi_io as K
+    if k96:
+        monkeypatch.setenv("MFA_TC_K96", "1")
+    rng = np.random.default_rng(77)
+    D, P = 39, 53
+    comps = rng.integers(1, 18, size=P)
+    if comps.sum() % 2 == 0:
+        comps[0] += 1
+    off = np.zeros(P + 1, np.int32); off[1:] = np.cumsum(comps)
+    G = int(off[-1])
+    assert G % 4 != 0 or G % 2 == 1
+    means, var = rng.normal(size=(G, D)) * 2.0, np.exp(rng.normal(scale=0.4, size=(G, D)))
+    w = np.concatenate([rng.dirichlet(np.ones(c)) for c in comps])
+    am = K.AmDiagGmm(D, off, w.astype(np.float32), (means / var).astype(np.float32), (1.0 / var).astype(np.float32))
+    tm, _, _ = load_model("mono")
+    tm.tid2pdf = (np.maximum(tm.tid2pdf, 0) % P).astype(np.int32)   # only the transition-id -> pdf range matters to the device model
+    x = (means[rng.integers(0, G, 300)] + rng.standard_normal((300, D)) * 1.5).astype(np.float32)
+    dm = E.DeviceModel(eng, tm, am)
+    for T in (300, 1, 129):
+        ll = dm.loglikes(x[:T], impl=0)
+        ref = O.gmm_loglikes(O.GmmModel.from_am(am), x[:T])
+        assert np.all(np.abs(ll - ref) <= 1e-4 * np.abs(ref) + 1e-4), (T, np.abs(ll - ref).max())
+    dm.close()
