@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""End-to-end example on a synthetic corpus: what `mfa align` does on its hot path, through the MFA-shaped job functions of this repo.
+
+  wav files -> MfccFunction -> calc_cmvn -> FinalFeatureFunction -> CompileTrainGraphsFunction
+            -> align_utterances (pass 1, speaker independent) -> calc_fmllr -> align_utterances (pass 2, fMLLR features)
+            -> export_textgrids
+
+Needs a B200 (there is no CPU fallback).  Usage:  python examples/two_pass_alignment.py [output_dir] [seconds_of_audio]
+"""
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from mfa_b200 import kaldi_io as K, kalpy_compat as KC, mfa_functions as MF, export as X  # noqa: E402
+
+
+def main():
+    out = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(tempfile.mkdtemp(prefix="mfa_b200_example_"))
+    seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
+    out.mkdir(parents=True, exist_ok=True)
+    # a small synthetic "language", corpus and triphone LDA model (the tests' scenario builder; the oracle is only used there to
+    # estimate the model's Gaussians from features -- the alignment below runs on the GPU engine)
+    from helpers import build_synth_scenario
+    sc = build_synth_scenario(seconds=seconds, seed=3, triphone=True, n_phones=10, n_words=60, gauss_per_pdf=2, n_spk=4, use_lda=True)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    split, work, wavs = out / "split", out / "work", out / "wav"
+    for d in (split, work, wavs):
+        d.mkdir(exist_ok=True)
+    utts = []
+    for u in range(c.n_utts):
+        wav = wavs / f"utt{u:04d}.wav"
+        K.write_wav_int16(wav, c.pcm[c.sample_off[u]:c.sample_off[u + 1]])
+        utts.append(MF.Utterance(u, int(c.utt2spk[u]), str(wav), " ".join(c.lexicon.id2word[w] for w in c.transcripts[u]),
+                                 duration=(c.sample_off[u + 1] - c.sample_off[u]) / 16000.0))
+    K.write_gmm_model(work / "final.mdl", tm, am)
+    K.write_tree(work / "tree", sc["tree"])
+    K.write_matrix_file(work / "lda.mat", sc["lda"])
+    jobs = MF.assign_jobs(utts, 2, split)
+    t0 = time.time()
+    mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
+    list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs]))
+    MF.calc_cmvn(jobs, split)
+    list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs]))
+    lex = {1: c.lexicon}
+    list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
+                               [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "final.mdl") for j in jobs]))
+    opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
+    score1, failed1 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
+    sil = [c.lexicon.phone_table["sil"]]
+    fm = MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil)
+    score2, failed2 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
+    written = MF.export_textgrids(jobs, work, work / "final.mdl", lex, out / "aligned")
+    dt = time.time() - t0
+    print(f"{c.n_utts} utterances / {c.seconds:.0f} s of audio, {c.n_spk} speakers; files under {out}")
+    print(f"pass 1: mean log-likelihood per utterance {score1:.1f} ({failed1} failed); fMLLR for {len(fm)} speakers "
+          f"(mean objective improvement per frame {np.mean([v[0] / max(v[1], 1) for v in fm.values()]):.3f}); "
+          f"pass 2: {score2:.1f} ({failed2} failed)")
+    first = sorted(p for p in written.values() if p is not None)[0]
+    tiers = X.read_textgrid(first)
+    print(f"{len(written)} TextGrids in {out / 'aligned'}; {first.name}: words = {[e[2] for e in tiers['words'] if e[2]][:8]} ...")
+    print(f"wall time incl. file I/O and graph compilation: {dt:.2f} s")
+
+
+if __name__ == "__main__":
+    main()
