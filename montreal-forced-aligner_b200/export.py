@@ -53,6 +53,14 @@ class HierarchicalCtm:
     def phone_intervals(self) -> List[CtmInterval]:
         return [p for w in self.word_intervals for p in w.phones]
 
+    def export_textgrid(self, output_path, file_duration: float, output_format: str = "long_textgrid", frame_shift: float = 0.01,
+                        speaker: str = "speaker", silence_word: str = "<eps>", cleanup_textgrids: bool = True):
+        """kalpy HierarchicalCtm.export_textgrid as align_one calls it (command_line/align_one.py:194-196): words / phones tiers."""
+        words = [CtmInterval(w.begin, w.end, w.label) for w in self.word_intervals if not (cleanup_textgrids and w.label == silence_word)]
+        phones = [CtmInterval(p.begin, p.end, p.label, p.confidence) for w in self.word_intervals
+                  if not (cleanup_textgrids and w.label == silence_word) for p in w.phones]
+        return export_textgrid({speaker: {"words": words, "phones": phones}}, output_path, file_duration, frame_shift, output_format)
+
     def update_utterance_boundaries(self, begin: Optional[float], end: Optional[float] = None):
         """Shift by the utterance's begin inside its file; the last phone is clipped to the utterance end."""
         b = float(begin or 0.0)

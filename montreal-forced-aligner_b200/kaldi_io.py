@@ -365,6 +365,11 @@ class TransitionModel:
         out[0] = 0.0
         return out
 
+    def acc_stats(self, alignment, stats: np.ndarray) -> np.ndarray:
+        """TransitionModel::Accumulate over an alignment (acoustic_modeling/monophone.py:120): stats[tid] += 1."""
+        np.add.at(stats, np.asarray(alignment, np.int64), 1.0)
+        return stats
+
     def InitStats(self) -> np.ndarray:
         return np.zeros(self.num_tids + 1, dtype=np.float64)
 

@@ -53,6 +53,64 @@ class Segment:
         return pcm[max(a, 0):min(b, pcm.shape[0])]
 
 
+@dataclass
+class KalpyUtterance:
+    """kalpy.utterance.Utterance as MFA drives it in align_one (command_line/align_one.py:163-183) and align_utterance_online
+    (online/alignment.py:44,82-94,122): a segment of a sound file with its transcript, raw MFCCs, and the feature chain
+    CMVN -> deltas | splice+LDA -> fMLLR (order of alignment/multiprocessing.py:1287-1304)."""
+    segment: Segment
+    transcript: str = ""
+    cmvn_string: Optional[str] = None
+    fmllr_string: Optional[str] = None
+    mfccs: Optional[np.ndarray] = None
+    _cmvn: Optional[np.ndarray] = None
+
+    def generate_mfccs(self, mfcc_computer: "MfccComputer"):
+        self.mfccs = mfcc_computer.compute_mfccs(self.segment)
+        self._cmvn = None
+        return self.mfccs
+
+    def apply_cmvn(self, cmvn: np.ndarray):
+        """Records the (file / speaker level) statistics; the subtraction is fused into the feature kernel (norm_vars = false)."""
+        self._cmvn = np.asarray(cmvn, np.float64)
+
+    def generate_features(self, mfcc_computer: "MfccComputer", pitch_computer=None, lda_mat: Optional[np.ndarray] = None,
+                          fmllr_trans: Optional[np.ndarray] = None, uses_deltas: bool = True) -> np.ndarray:
+        if pitch_computer is not None:
+            raise MfaError("pitch features are outside the hot path (SURVEY.md section 2a)")
+        if self.mfccs is None:
+            self.generate_mfccs(mfcc_computer)
+        fo = np.asarray([0, self.mfccs.shape[0]], np.int64)
+        mode = "lda" if lda_mat is not None else ("deltas" if uses_deltas else "none")
+        fm = None if fmllr_trans is None else np.asarray(fmllr_trans, np.float32)[None]
+        cm = None if self._cmvn is None else self._cmvn[None]
+        return get_engine().features(self.mfccs, fo, mode, lda=lda_mat, fmllr=fm, cmvn_stats=cm, utt2spk=np.zeros(1, np.int32), n_spk=1)
+
+
+def generate_read_specifier(path) -> str:
+    """kalpy.utils.generate_read_specifier: 'scp:...' / 'ark:...' by extension (the archives of this module take plain paths too)."""
+    path = str(path)
+    return ("scp:" if path.endswith(".scp") else "ark:") + path
+
+
+def generate_write_specifier(path, write_scp: bool = False) -> str:
+    path = str(path)
+    return f"ark,scp:{path},{path[:-4]}.scp" if write_scp else f"ark:{path}"
+
+
+def read_kaldi_object(obj_type, path):
+    """kalpy.utils.read_kaldi_object for the types the hot path reads: TransitionModel / AmDiagGmm (from a .mdl), ContextDependency
+    (tree), FloatMatrix (lda.mat)."""
+    name = getattr(obj_type, "__name__", str(obj_type))
+    if name == "TransitionModel":
+        return K.read_gmm_model(path)[0]
+    if name == "AmDiagGmm":
+        return K.read_gmm_model(path)[1]
+    if name == "ContextDependency":
+        return K.read_tree(path)
+    return K.read_matrix_file(path)
+
+
 class CompressedMatrix:
     """Kaldi CompressedMatrix value: holds the codec bytes; ``numpy()`` decodes (corpus/features.py:209,318,356)."""
 

@@ -628,3 +628,54 @@ def align_utterance_online(model_path, tree_path, lexicon: Lexicon, pcm: np.ndar
     if ali is None:
         raise AlignerError(f"Could not align the file with the current beam size ({beam}, please try increasing the beam size via `--beam X`")
     return ali, ali.generate_ctm(aligner.transition_model, phone_table or {}, mc.frame_shift / 1000.0)
+
+
+def align_utterance_online_ctm(model_path, tree_path, lexicon: Lexicon, utterance: "KC.KalpyUtterance", mfcc_computer: Optional[KC.MfccComputer] = None,
+                               cmvn: Optional[np.ndarray] = None, lda_mat: Optional[np.ndarray] = None, fmllr_trans: Optional[np.ndarray] = None,
+                               uses_cmvn: bool = True, beam: float = 10, retry_beam: float = 40, transition_scale: float = 1.0,
+                               acoustic_scale: float = 0.1, self_loop_scale: float = 0.1, boost_silence: float = 1.0,
+                               silence_phone_ids: Sequence[int] = ()):
+    """online/alignment.py:29-123 with the reference's own argument shape: a KalpyUtterance in, a HierarchicalCtm (word intervals owning
+    their phone intervals, shifted to the segment's position in the file) out.  AlignerError when the beam is too tight."""
+    from . import export as X
+    mc = mfcc_computer or KC.MfccComputer()
+    if utterance.mfccs is None:
+        utterance.generate_mfccs(mc)
+        if uses_cmvn:
+            if cmvn is None:
+                cmvn = KC.CmvnComputer().compute_cmvn_from_features([utterance.mfccs])
+            utterance.apply_cmvn(cmvn)
+    feats = utterance.generate_features(mc, None, lda_mat=lda_mat, fmllr_trans=fmllr_trans)
+    fst = KC.TrainingGraphCompiler(model_path, tree_path, lexicon).compile_fst(utterance.transcript)
+    aligner = KC.GmmAligner(model_path, transition_scale=transition_scale, acoustic_scale=acoustic_scale, self_loop_scale=self_loop_scale,
+                            beam=beam, retry_beam=retry_beam)
+    if boost_silence != 1.0 and silence_phone_ids:
+        aligner.boost_silence(boost_silence, silence_phone_ids)
+    alignment = aligner.align_utterance(fst, feats)
+    if alignment is None:
+        raise AlignerError(f"Could not align the file with the current beam size ({beam}, please try increasing the beam size via `--beam X`")
+    return X.alignment_to_ctm(alignment, aligner.transition_model, lexicon, mc.frame_shift / 1000.0, utterance.segment.begin, utterance.segment.end,
+                              utterance.transcript)
+
+
+def align_one(sound_file_path, utterances: Sequence[Tuple[Optional[float], Optional[float], int, str]], model_path, tree_path, lexicon: Lexicon,
+              output_path, file_duration: float, lda_mat: Optional[np.ndarray] = None, output_format: str = "long_textgrid", **align_options):
+    """`mfa align_one` (command_line/align_one.py:157-196) without the CLI: every (begin, end, channel, text) segment of one sound file
+    -> MFCCs, ONE CMVN over the file's segments, per-segment online alignment, one TextGrid.  Returns the merged HierarchicalCtm."""
+    from . import export as X
+    mc = KC.MfccComputer()
+    utts = []
+    for begin, end, channel, text in utterances:
+        u = KC.KalpyUtterance(KC.Segment(str(sound_file_path), begin, end, channel), text)
+        u.generate_mfccs(mc)
+        utts.append(u)
+    cmvn = KC.CmvnComputer().compute_cmvn_from_features([u.mfccs for u in utts])
+    file_ctm = X.HierarchicalCtm([])
+    for u in utts:
+        u.apply_cmvn(cmvn)
+        ctm = align_utterance_online_ctm(model_path, tree_path, lexicon, u, mc, lda_mat=lda_mat, **align_options)
+        file_ctm.word_intervals.extend(ctm.word_intervals)
+    if str(output_path) != "-":
+        Path(output_path).parent.mkdir(parents=True, exist_ok=True)
+        file_ctm.export_textgrid(output_path, file_duration=file_duration, output_format=output_format, silence_word=lexicon.silence_word)
+    return file_ctm

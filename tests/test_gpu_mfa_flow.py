@@ -323,3 +323,35 @@ def test_textgrid_export_corpus_and_reference_sanity(tmp_path):
     # informational only: the fixture monophone model is a unit-test artefact (132 single Gaussians) whose alignments -- ours and the
     # oracle's alike, see test_online_path_config1 -- are seconds away from a production model's; there is nothing to assert on here
     assert diffs.size >= 60
+
+
+def test_align_one_file_with_segments(tmp_path):
+    """`mfa align_one` flow (command_line/align_one.py:157-196): one sound file holding two segments with their own transcripts, one CMVN
+    over the file, per-segment alignment through KalpyUtterance, one TextGrid whose intervals sit inside the segments."""
+    from mfa_b200 import export as X
+    sc = build_synth_scenario(seconds=20.0, seed=37, triphone=False, n_phones=8, n_words=30, gauss_per_pdf=2, n_spk=1)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    K.write_gmm_model(tmp_path / "final.mdl", tm, am)
+    K.write_tree(tmp_path / "tree", sc["tree"])
+    gap = np.zeros(8000, np.int16)
+    a, b = c.pcm[c.sample_off[0]:c.sample_off[1]], c.pcm[c.sample_off[1]:c.sample_off[2]]
+    pcm = np.concatenate([gap, a, gap, b, gap])
+    wav = tmp_path / "file.wav"
+    K.write_wav_int16(wav, pcm)
+    t = lambda n: n / 16000.0
+    segs = [(t(8000), t(8000 + len(a)), 0, " ".join(c.lexicon.id2word[w] for w in c.transcripts[0])),
+            (t(16000 + len(a)), t(16000 + len(a) + len(b)), 0, " ".join(c.lexicon.id2word[w] for w in c.transcripts[1]))]
+    ctm = MF.align_one(wav, segs, tmp_path / "final.mdl", tmp_path / "tree", c.lexicon, tmp_path / "out" / "file.TextGrid", t(len(pcm)))
+    tiers = X.read_textgrid(tmp_path / "out" / "file.TextGrid")
+    words = [e for e in tiers["words"] if e[2]]
+    assert [e[2] for e in words] == (segs[0][3] + " " + segs[1][3]).split()
+    n0 = len(segs[0][3].split())
+    assert all(segs[0][0] - 1e-6 <= e[0] and e[1] <= segs[0][1] + 0.011 for e in words[:n0])
+    assert all(segs[1][0] - 1e-6 <= e[0] and e[1] <= segs[1][1] + 0.011 for e in words[n0:])
+    assert tiers["words"][0] == (0.0, pytest.approx(words[0][0]), "") and abs(tiers["phones"][-1][1] - t(len(pcm))) < 1e-6
+    assert len(ctm.word_intervals) >= len(words)
+    # the same segment aligned on its own (its own CMVN) gives the same word sequence through the KalpyUtterance path
+    u = KC.KalpyUtterance(KC.Segment(str(wav), segs[0][0], segs[0][1], 0), segs[0][3])
+    one = MF.align_utterance_online_ctm(tmp_path / "final.mdl", tmp_path / "tree", c.lexicon, u)
+    assert [w.label for w in one.word_intervals if w.label != "<eps>"] == segs[0][3].split()
+    assert one.word_intervals[0].begin >= segs[0][0] - 1e-6
