@@ -533,11 +533,15 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
-  // two-warp CTAs where many utterances share an SM: always when the graph is read through L1 (a CTA then needs ~15 KB), and
-  // for the classes under 44 KB when it is copied to shared memory (MFA_VIT_NW2_KB overrides the threshold).  Measured on the
-  // 10 h config-2 workload, graph through L1: 2 warps 7.6 ms, 4 warps 10.0 ms; graph in shared memory: 11.7 ms.
+  // two-warp CTAs where many utterances share an SM, four-warp CTAs for the size classes above a shared-memory threshold
+  // (MFA_VIT_NW2_KB overrides it): 44 KB when the graph is copied to shared memory; 20 KB when it is read through L1 -- a CTA then needs
+  // ~15 KB + 32 B per pdf of its graph, so the classes above 20 KB are the longest utterances, the ones on the launch's critical path,
+  // and four warps shorten their per-frame chain while the bulk keeps the residency of two-warp CTAs.  Measured on the 10 h config-2
+  // workload, graph through L1 (three boxes): all classes 2 warps 9.4-9.6 ms, all 4 warps 10.0 ms, threshold 20 KB 8.2-8.45 ms
+  // (19 KB 8.15, 21 KB 9.5-9.6, 22 KB 8.2-9.3: the launch is bounded by a handful of utterances, so neighbouring thresholds scatter);
+  // graph in shared memory: 11.7 ms.
   const char *env_nw = getenv("MFA_VIT_NW2_KB");
-  const size_t nw2_below = (size_t)(env_nw ? atoi(env_nw) : (graph_smem ? 44 : 256)) * 1024;
+  const size_t nw2_below = (size_t)(env_nw ? atoi(env_nw) : (graph_smem ? 44 : 20)) * 1024;
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
   for (int c = NC - 1; c >= 0; c--) {
     int pos = 0, cnt = 0;
