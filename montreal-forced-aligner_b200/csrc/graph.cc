@@ -16,6 +16,8 @@
 //   HMM expansion : node (instance, hmm state j', source state j) carries the self-loop of j
 //                   (reorder=true: [forward tid, self-loop tid x (n-1)]); nodes with j' = final are the
 //                   junctions from which the successors' state-0 transitions leave.
+#include <atomic>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -642,61 +644,88 @@ int mfa_fst_batch_export(const mfa_fst_batch *fb, int64_t *state_off, int64_t *a
 int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_t *tid2pdf, int32_t num_tids, mfa_graphs **out) {
   if (!fb || !tid_cost || !tid2pdf || !out) return set_error(MFA_ERR_INVALID, "null argument");
   const FstBatch &b = fb->b;
+  const int n = b.n();
+  // Phase 1, utterances in parallel on host threads (the band renumbering -- Tarjan + Kahn per graph -- is most of the time: 0.26 ms per
+  // utterance, 0.78 s for the 10 h workload when serial): everything of one utterance goes into its own PackedUtt.
+  struct PackedUtt {
+    std::vector<int32_t> inb, a_src, a_dst, a_lp, a_tid, a_olabel, pdfs;
+    std::vector<float> a_w;
+    int32_t n_eps = 0, words = 0;
+    bool ok = false;
+    BandOut bo;
+    int err = 0;
+  };
+  std::vector<PackedUtt> pu(n);
+  for (int u = 0; u < n; u++) {
+    const int64_t S = b.state_off[u + 1] - b.state_off[u], A = b.arc_off[u + 1] - b.arc_off[u];
+    if (S > 65534 || A > 65534) return set_error(MFA_ERR_UNSUPPORTED, "graph of utterance " + std::to_string(u) + " exceeds 65534 states/arcs");
+  }
+  auto work = [&](int u, std::vector<int32_t> &lpmap) {
+    PackedUtt &P = pu[u];
+    const int64_t s0 = b.state_off[u], S = b.state_off[u + 1] - s0, a0 = b.arc_off[u], A = b.arc_off[u + 1] - a0;
+    std::vector<int32_t> order(A);   // arcs by (src, original index)
+    for (int64_t a = 0; a < A; a++) order[a] = (int32_t)a;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.src[a0 + x] < b.src[a0 + y]; });
+    P.inb.assign(S + 1, 0);
+    for (int64_t a = 0; a < A; a++) P.inb[b.src[a0 + a] + 1]++;
+    for (int64_t s = 0; s < S; s++) P.inb[s + 1] += P.inb[s];
+    for (int64_t a = 0; a < A; a++) { const int il = b.il[a0 + a]; if (il > 0) { if (il > num_tids) { P.err = 1; return; } P.pdfs.push_back(tid2pdf[il]); } }
+    std::sort(P.pdfs.begin(), P.pdfs.end()); P.pdfs.erase(std::unique(P.pdfs.begin(), P.pdfs.end()), P.pdfs.end());
+    const int maxpdf = P.pdfs.empty() ? 0 : P.pdfs.back();
+    if ((int)lpmap.size() <= maxpdf) lpmap.resize(maxpdf + 1);
+    for (size_t k = 0; k < P.pdfs.size(); k++) lpmap[P.pdfs[k]] = (int32_t)k;
+    P.a_src.resize(A); P.a_dst.resize(A); P.a_lp.resize(A); P.a_tid.resize(A); P.a_olabel.resize(A); P.a_w.resize(A);
+    for (int64_t k = 0; k < A; k++) {
+      const int64_t a = a0 + order[k];
+      const int il = b.il[a];
+      P.a_src[k] = b.src[a]; P.a_dst[k] = b.dst[a]; P.a_tid[k] = il; P.a_olabel[k] = b.ol[a];
+      if (b.ol[a] != 0) P.words++;   // loose bound (a path crosses each labelled arc at most once in an acyclic word graph)
+      if (il > 0) { P.a_w[k] = b.w[a] + tid_cost[il]; P.a_lp[k] = lpmap[tid2pdf[il]]; }
+      else { P.a_w[k] = b.w[a]; P.a_lp[k] = -1; P.n_eps++; }
+    }
+    P.ok = build_band((int)S, (int)A, b.start[u], P.inb.data(), P.a_src.data(), P.a_dst.data(), P.a_lp.data(), P.a_w.data(), b.finals.data() + s0, P.bo);
+    if (!P.ok) { P.bo.stw.assign(S, 0); P.bo.fin.assign(S, 0.0f); P.bo.orig.assign(S, 0); P.bo.apk.assign(A, 0); P.bo.aw.assign(A, 0.0f); P.bo.arcid.assign(A, 0); }
+  };
+  {
+    const char *ev = getenv("MFA_PACK_THREADS");
+    int nt = ev ? atoi(ev) : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(32, n)));
+    std::atomic<int> next{0};
+    auto loop = [&]() { std::vector<int32_t> lpmap; for (int u = next.fetch_add(1); u < n; u = next.fetch_add(1)) work(u, lpmap); };
+    if (nt <= 1) loop();
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(loop); for (auto &t : th) t.join(); }
+  }
+  for (int u = 0; u < n; u++) if (pu[u].err) return set_error(MFA_ERR_INVALID, "ilabel exceeds num_tids");
+  // Phase 2: concatenate
   auto *g = new mfa_graphs();
-  int n = b.n();
   g->n_utts = n;
   g->st_off.assign(n + 1, 0); g->arc_off.assign(n + 1, 0); g->lp_off.assign(n + 1, 0); g->inb_off.assign(n + 1, 0);
   g->start.resize(n); g->n_eps.assign(n, 0); g->max_words.assign(n, 0);
-  std::vector<int32_t> lpmap;
   for (int u = 0; u < n; u++) {
-    int64_t s0 = b.state_off[u], S = b.state_off[u + 1] - s0, a0 = b.arc_off[u], A = b.arc_off[u + 1] - a0;
-    g->start[u] = b.start[u];
-    if (S > 65534 || A > 65534) { delete g; return set_error(MFA_ERR_UNSUPPORTED, "graph of utterance " + std::to_string(u) + " exceeds 65534 states/arcs"); }
-    // order arcs by (src, original index)
-    std::vector<int32_t> order(A);
-    for (int64_t a = 0; a < A; a++) order[a] = (int32_t)a;
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.src[a0 + x] < b.src[a0 + y]; });
-    std::vector<int32_t> inb(S + 1, 0);
-    for (int64_t a = 0; a < A; a++) inb[b.src[a0 + a] + 1]++;
-    for (int64_t s = 0; s < S; s++) inb[s + 1] += inb[s];
-    g->in_begin.insert(g->in_begin.end(), inb.begin(), inb.end());
-    // local pdf list
-    std::vector<int32_t> pdfs;
-    for (int64_t a = 0; a < A; a++) { int il = b.il[a0 + a]; if (il > 0) { if (il > num_tids) { delete g; return set_error(MFA_ERR_INVALID, "ilabel exceeds num_tids"); } pdfs.push_back(tid2pdf[il]); } }
-    std::sort(pdfs.begin(), pdfs.end()); pdfs.erase(std::unique(pdfs.begin(), pdfs.end()), pdfs.end());
-    int maxpdf = pdfs.empty() ? 0 : pdfs.back();
-    if ((int)lpmap.size() <= maxpdf) lpmap.resize(maxpdf + 1);
-    for (size_t k = 0; k < pdfs.size(); k++) lpmap[pdfs[k]] = (int32_t)k;
-    int words = 0;
-    for (int64_t k = 0; k < A; k++) {
-      int64_t a = a0 + order[k];
-      int il = b.il[a];
-      g->a_src.push_back(b.src[a]);
-      g->a_dst.push_back(b.dst[a]);
-      g->a_tid.push_back(il);
-      g->a_olabel.push_back(b.ol[a]);
-      if (b.ol[a] != 0) words++;
-      if (il > 0) { g->a_w.push_back(b.w[a] + tid_cost[il]); g->a_lp.push_back(lpmap[tid2pdf[il]]); }
-      else { g->a_w.push_back(b.w[a]); g->a_lp.push_back(-1); g->n_eps[u]++; }
-    }
-    g->max_words[u] = words;  // loose bound (a path crosses each labelled arc at most once in an acyclic word graph)
-    g->final_w.insert(g->final_w.end(), b.finals.begin() + s0, b.finals.begin() + s0 + S);
-    {
-      BandOut bo;
-      const size_t ga = (size_t)g->arc_off[u];
-      const bool ok = build_band((int)S, (int)A, b.start[u], inb.data(), g->a_src.data() + ga, g->a_dst.data() + ga, g->a_lp.data() + ga,
-                                 g->a_w.data() + ga, b.finals.data() + s0, bo);
-      g->band_ok.push_back(ok ? 1 : 0); g->b_start.push_back(ok ? bo.start : -1); g->b_maxback.push_back(ok ? bo.maxback : 0);
-      if (!ok) { bo.stw.assign(S, 0); bo.fin.assign(S, 0.0f); bo.orig.assign(S, 0); bo.apk.assign(A, 0); bo.aw.assign(A, 0.0f); bo.arcid.assign(A, 0); }
-      g->b_stw.insert(g->b_stw.end(), bo.stw.begin(), bo.stw.end()); g->b_fin.insert(g->b_fin.end(), bo.fin.begin(), bo.fin.end());
-      g->b_orig.insert(g->b_orig.end(), bo.orig.begin(), bo.orig.end()); g->b_apk.insert(g->b_apk.end(), bo.apk.begin(), bo.apk.end());
-      g->b_aw.insert(g->b_aw.end(), bo.aw.begin(), bo.aw.end()); g->b_arcid.insert(g->b_arcid.end(), bo.arcid.begin(), bo.arcid.end());
-    }
-    g->lp2pdf.insert(g->lp2pdf.end(), pdfs.begin(), pdfs.end());
-    g->st_off[u + 1] = g->st_off[u] + S;
-    g->arc_off[u + 1] = g->arc_off[u] + A;
-    g->lp_off[u + 1] = g->lp_off[u] + (int64_t)pdfs.size();
-    g->inb_off[u + 1] = g->inb_off[u] + S + 1;
+    const int64_t S = b.state_off[u + 1] - b.state_off[u], A = b.arc_off[u + 1] - b.arc_off[u];
+    g->st_off[u + 1] = g->st_off[u] + S; g->arc_off[u + 1] = g->arc_off[u] + A;
+    g->lp_off[u + 1] = g->lp_off[u] + (int64_t)pu[u].pdfs.size(); g->inb_off[u + 1] = g->inb_off[u] + S + 1;
+  }
+  const size_t TS = (size_t)g->st_off[n], TA = (size_t)g->arc_off[n];
+  g->in_begin.resize((size_t)g->inb_off[n]); g->lp2pdf.resize((size_t)g->lp_off[n]);
+  g->a_src.resize(TA); g->a_dst.resize(TA); g->a_lp.resize(TA); g->a_tid.resize(TA); g->a_olabel.resize(TA); g->a_w.resize(TA);
+  g->final_w.assign(b.finals.begin(), b.finals.begin() + TS);
+  g->band_ok.resize(n); g->b_start.resize(n); g->b_maxback.resize(n);
+  g->b_stw.resize(TS); g->b_fin.resize(TS); g->b_orig.resize(TS); g->b_apk.resize(TA); g->b_aw.resize(TA); g->b_arcid.resize(TA);
+  for (int u = 0; u < n; u++) {
+    PackedUtt &P = pu[u];
+    const size_t so = (size_t)g->st_off[u], ao = (size_t)g->arc_off[u];
+    g->start[u] = b.start[u]; g->n_eps[u] = P.n_eps; g->max_words[u] = P.words;
+    std::copy(P.inb.begin(), P.inb.end(), g->in_begin.begin() + g->inb_off[u]);
+    std::copy(P.pdfs.begin(), P.pdfs.end(), g->lp2pdf.begin() + g->lp_off[u]);
+    std::copy(P.a_src.begin(), P.a_src.end(), g->a_src.begin() + ao); std::copy(P.a_dst.begin(), P.a_dst.end(), g->a_dst.begin() + ao);
+    std::copy(P.a_lp.begin(), P.a_lp.end(), g->a_lp.begin() + ao); std::copy(P.a_tid.begin(), P.a_tid.end(), g->a_tid.begin() + ao);
+    std::copy(P.a_olabel.begin(), P.a_olabel.end(), g->a_olabel.begin() + ao); std::copy(P.a_w.begin(), P.a_w.end(), g->a_w.begin() + ao);
+    g->band_ok[u] = P.ok ? 1 : 0; g->b_start[u] = P.ok ? P.bo.start : -1; g->b_maxback[u] = P.ok ? P.bo.maxback : 0;
+    std::copy(P.bo.stw.begin(), P.bo.stw.end(), g->b_stw.begin() + so); std::copy(P.bo.fin.begin(), P.bo.fin.end(), g->b_fin.begin() + so);
+    std::copy(P.bo.orig.begin(), P.bo.orig.end(), g->b_orig.begin() + so); std::copy(P.bo.apk.begin(), P.bo.apk.end(), g->b_apk.begin() + ao);
+    std::copy(P.bo.aw.begin(), P.bo.aw.end(), g->b_aw.begin() + ao); std::copy(P.bo.arcid.begin(), P.bo.arcid.end(), g->b_arcid.begin() + ao);
+    P = PackedUtt();   // release as we go
   }
   *out = g;
   return MFA_OK;
