@@ -20,10 +20,12 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "cuda_internal.cuh"
 
@@ -598,27 +600,50 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   const uint32_t TILE_BYTES = tile_bytes(TK);
   // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles
   if (g->rag_version != m->tc_version) {
+    // two passes over the (utterance, local pdf) lists: count the tiles of every utterance, then fill meta / source rows on host threads
     g->rag_tile_off.assign(g->n_utts + 1, 0);
-    std::vector<TcMeta> meta;
-    std::vector<int32_t> src;
+    auto pad_of = [&](int pdf) { const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf]; return (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN; };
     for (int u = 0; u < g->n_utts; u++) {
-      int col = TN;  // force a new tile
+      int col = TN; int64_t nt_u = 0;
       for (int64_t k = g->lp_off[u]; k < g->lp_off[u + 1]; k++) {
         const int pdf = g->lp2pdf[k];
         if (pdf < 0 || pdf >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
-        const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
-        if (col + pad > TN) {
-          if (!meta.empty() && col < TN && (int64_t)meta.size() > g->rag_tile_off[u]) meta.back().gstart |= 1u << (col / 4);
-          TcMeta mt; memset(&mt, 0, sizeof(mt)); mt.pdf0 = (int32_t)(k - g->lp_off[u]);
-          meta.push_back(mt); src.resize(src.size() + TN, -1); col = 0;
-        }
-        meta.back().gstart |= 1u << (col / 4);
-        meta.back().gend |= 1u << ((col + pad - 1) / 4);
-        for (int j = 0; j < ng; j++) src[(meta.size() - 1) * TN + col + j] = m->h_pdf_off[pdf] + j;
+        const int pad = pad_of(pdf);
+        if (col + pad > TN) { nt_u++; col = 0; }
         col += pad;
       }
-      if (!meta.empty() && col < TN && (int64_t)meta.size() > g->rag_tile_off[u]) meta.back().gstart |= 1u << (col / 4);
-      g->rag_tile_off[u + 1] = (int64_t)meta.size();
+      g->rag_tile_off[u + 1] = g->rag_tile_off[u] + nt_u;
+    }
+    std::vector<TcMeta> meta((size_t)g->rag_tile_off[g->n_utts]);
+    std::vector<int32_t> src;
+    src.resize(meta.size() * TN);
+    auto fill = [&](int u) {
+      int64_t t = g->rag_tile_off[u] - 1;
+      int col = TN;  // force a new tile
+      for (int64_t k = g->lp_off[u]; k < g->lp_off[u + 1]; k++) {
+        const int pdf = g->lp2pdf[k];
+        const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = pad_of(pdf);
+        if (col + pad > TN) {
+          if (t >= g->rag_tile_off[u] && col < TN) meta[t].gstart |= 1u << (col / 4);   // trailing padding of the previous tile: a junk segment
+          t++;
+          memset(&meta[t], 0, sizeof(TcMeta)); meta[t].pdf0 = (int32_t)(k - g->lp_off[u]);
+          std::fill(src.begin() + t * TN, src.begin() + (t + 1) * TN, -1);
+          col = 0;
+        }
+        meta[t].gstart |= 1u << (col / 4);
+        meta[t].gend |= 1u << ((col + pad - 1) / 4);
+        for (int j = 0; j < ng; j++) src[t * TN + col + j] = m->h_pdf_off[pdf] + j;
+        col += pad;
+      }
+      if (t >= g->rag_tile_off[u] && col < TN) meta[t].gstart |= 1u << (col / 4);
+    };
+    {
+      int nt = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency()));
+      nt = std::min(nt, std::max(1, g->n_utts / 64));
+      std::atomic<int> next{0};
+      auto loop = [&]() { for (int u = next.fetch_add(1); u < g->n_utts; u = next.fetch_add(1)) fill(u); };
+      if (nt <= 1) loop();
+      else { std::vector<std::thread> th; for (int i = 0; i < nt; i++) th.emplace_back(loop); for (auto &x : th) x.join(); }
     }
     if (g->d_rag) { CUDA_TRY(cudaStreamSynchronize(e->stream)); CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
     const size_t mb = meta.size() * sizeof(TcMeta), sb = src.size() * sizeof(int32_t);
