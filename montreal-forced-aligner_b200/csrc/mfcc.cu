@@ -265,6 +265,10 @@ constexpr int kTB = 32 * kT2;          // float2 entries of the transpose / spec
 static_assert(kTB >= 8 * kT1 && kTB >= 256 + 16, "transpose buffer too small");
 constexpr int kWarpFloats = 2 * kTB + 260 + 32 + 32;   // transpose / spectrum buffer, power spectrum, chunk sums, log-mel
 
+// int16 -> float without the conversion unit (I2F runs on the quarter-rate XU pipe and was 24 % of this kernel's stall samples):
+// 2^23 + 32768 + v is exactly representable, so the sample is planted in the mantissa of 2^23 and the bias subtracted -- exact.
+__device__ __forceinline__ float s16_to_float(uint32_t u16) { return __uint_as_float(0x4B000000u | (u16 ^ 0x8000u)) - 8421376.0f; }
+
 __global__ void __launch_bounds__(kFW * 32, 6)
 mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restrict__ pcm, const int64_t *__restrict__ sample_off,
                const int64_t *__restrict__ frame_off, int n_utts, int64_t frame_base, int64_t n_frames, int64_t frames_per_warp, float *__restrict__ out,
@@ -310,6 +314,10 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
   while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (frame_off[mid] <= f0) lo = mid; else hi = mid - 1; }
   int u = lo;
   int64_t u_f0 = frame_off[u], u_f1 = frame_off[u + 1], u_s0 = sample_off[u], u_n = sample_off[u + 1] - u_s0;
+  // the next frame's samples (same utterance, interior, 4-byte aligned, even window) are fetched one frame ahead: the load latency
+  // at the top of a frame was a quarter of this kernel's stall samples
+  uint32_t nx[8];
+  bool have_nx = false;
   for (int64_t f = f0; f < f1; f++) {
     while (f >= u_f1) { u++; u_f0 = u_f1; u_f1 = frame_off[u + 1]; u_s0 = sample_off[u]; u_n = sample_off[u + 1] - u_s0; }
     const int64_t fi = f - u_f0;
@@ -317,21 +325,28 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
     // ---- samples: lane holds x[64 a + 2 lane + {0,1}], a = 0..7 (128 contiguous bytes per load across the warp)
     float x[16];
     const int16_t *base = pcm + u_s0 + start;
-    if (start >= 0 && start + N <= u_n) {
+    if (have_nx) {   // prefetched while the previous frame was being transformed
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int n = 64 * a + 2 * lane;
+        x[2 * a] = n + 1 < N ? s16_to_float(nx[a] & 0xFFFFu) : 0.0f;
+        x[2 * a + 1] = n + 1 < N ? s16_to_float(nx[a] >> 16) : 0.0f;
+      }
+    } else if (start >= 0 && start + N <= u_n) {
       if ((((size_t)base) & 3) == 0) {
 #pragma unroll
         for (int a = 0; a < 8; a++) {
           const int n = 64 * a + 2 * lane;
           x[2 * a] = 0.0f; x[2 * a + 1] = 0.0f;
-          if (n + 1 < N) { const uint32_t v = __ldg((const uint32_t *)(base + n)); x[2 * a] = (float)(int16_t)(v & 0xFFFF); x[2 * a + 1] = (float)(int16_t)(v >> 16); }
-          else if (n < N) x[2 * a] = (float)__ldg(base + n);
+          if (n + 1 < N) { const uint32_t v = __ldg((const uint32_t *)(base + n)); x[2 * a] = s16_to_float(v & 0xFFFFu); x[2 * a + 1] = s16_to_float(v >> 16); }
+          else if (n < N) x[2 * a] = s16_to_float((uint16_t)__ldg(base + n));
         }
       } else {
 #pragma unroll
         for (int a = 0; a < 8; a++) {
           const int n = 64 * a + 2 * lane;
-          x[2 * a] = n < N ? (float)__ldg(base + n) : 0.0f;
-          x[2 * a + 1] = n + 1 < N ? (float)__ldg(base + n + 1) : 0.0f;
+          x[2 * a] = n < N ? s16_to_float((uint16_t)__ldg(base + n)) : 0.0f;
+          x[2 * a + 1] = n + 1 < N ? s16_to_float((uint16_t)__ldg(base + n + 1)) : 0.0f;
         }
       }
     } else {   // frame overlaps an utterance edge (snip_edges = false): reflected indices
@@ -348,6 +363,16 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
           }
           x[2 * a + e] = v;
         }
+    }
+    have_nx = false;
+    if ((N & 1) == 0 && f + 1 < f1 && f + 1 < u_f1) {
+      const int64_t start1 = start + t.shift;
+      const int16_t *base1 = base + t.shift;
+      if (start1 >= 0 && start1 + N <= u_n && (((size_t)base1) & 3) == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) { const int n = 64 * a + 2 * lane; nx[a] = n + 1 < N ? __ldg((const uint32_t *)(base1 + n)) : 0u; }
+        have_nx = true;
+      }
     }
     if (remove_dc) {
       float sum = 0.0f;
