@@ -45,19 +45,26 @@ def main():
     K.write_matrix_file(work / "lda.mat", sc["lda"])
     jobs = MF.assign_jobs(utts, 2, split)
     t0 = time.time()
+    stages = {}
+
+    def timed(name, fn):
+        t = time.time()
+        r = fn()
+        stages[name] = round(time.time() - t, 3)
+        return r
     mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
-    list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs]))
-    MF.calc_cmvn(jobs, split)
-    list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs]))
+    timed("mfcc", lambda: list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs])))
+    timed("cmvn", lambda: MF.calc_cmvn(jobs, split))
+    timed("final_features", lambda: list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs])))
     lex = {1: c.lexicon}
-    list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
-                               [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "final.mdl") for j in jobs]))
+    timed("compile_graphs", lambda: list(MF.run_kaldi_function(
+        MF.CompileTrainGraphsFunction, [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "final.mdl") for j in jobs])))
     opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
-    score1, failed1 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
+    score1, failed1 = timed("align_pass1", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts))
     sil = [c.lexicon.phone_table["sil"]]
-    fm = MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil)
-    score2, failed2 = MF.align_utterances(jobs, work, work / "final.mdl", opts)
-    written = MF.export_textgrids(jobs, work, work / "final.mdl", lex, out / "aligned")
+    fm = timed("fmllr", lambda: MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil))
+    score2, failed2 = timed("align_pass2", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts))
+    written = timed("textgrids", lambda: MF.export_textgrids(jobs, work, work / "final.mdl", lex, out / "aligned"))
     dt = time.time() - t0
     print(f"{c.n_utts} utterances / {c.seconds:.0f} s of audio, {c.n_spk} speakers; files under {out}")
     print(f"pass 1: mean log-likelihood per utterance {score1:.1f} ({failed1} failed); fMLLR for {len(fm)} speakers "
@@ -66,7 +73,7 @@ def main():
     first = sorted(p for p in written.values() if p is not None)[0]
     tiers = X.read_textgrid(first)
     print(f"{len(written)} TextGrids in {out / 'aligned'}; {first.name}: words = {[e[2] for e in tiers['words'] if e[2]][:8]} ...")
-    print(f"wall time incl. file I/O and graph compilation: {dt:.2f} s")
+    print(f"wall time incl. file I/O and graph compilation: {dt:.2f} s = {c.seconds / dt:.0f} x real time; per stage (s): {stages}")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,12 @@
+"""cProfile of AlignFunction through the MFA-shaped file flow (1 h synthetic corpus prepared by examples/two_pass_alignment.py)."""
+import cProfile, pstats, sys, os
+from pathlib import Path
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "examples"))
+import two_pass_alignment as ex
+sys.argv = ["x", sys.argv[1] if len(sys.argv) > 1 else "/tmp/ex", sys.argv[2] if len(sys.argv) > 2 else "1800"]
+pr = cProfile.Profile()
+pr.enable()
+ex.main()
+pr.disable()
+st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(45)
