@@ -186,6 +186,24 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     out["k5_fmllr_stats"] = {"kernel": "K5 fmllr_frame_kernel + fmllr_accum_kernel (per-speaker beta, K, G_d in f64)", "ms": k5_ms, "bound": "f64 FMA",
                              "speakers": int(c.n_spk), "weighted_frames": weighted, "algorithmic_dfma": dfma,
                              "achieved_tflops_f64": 2.0 * dfma / (k5_ms * 1e-3) / 1e12, "xRT": c.seconds / (k5_ms * 1e-3)}
+    # config 3's flow on this shard: pass 1 -> fMLLR statistics + update -> pass 2 on the transformed features, all device-resident
+    from mfa_b200 import mfa_functions as MF
+
+    def sat():
+        holder["sat"] = MF.two_pass_align_pcm(eng, sc.model, sc.model, sc.graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda,
+                                              silence_phone_ids=[sil], workspace_bytes=int(args.workspace_gb * (1 << 30)))
+    sat(); eng.sync()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        sat()
+    eng.sync()
+    sat_ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    r1, Wh, (impr_s, cnt_s), r2 = holder["sat"]
+    ok1, ok2 = int((r1.status.cpu().numpy() < 2).sum()), int((r2.status.cpu().numpy() < 2).sum())
+    l1, l2 = float(r1.total_like.double().sum().item()), float(r2.total_like.double().sum().item())
+    out["sat_two_pass"] = {"what": "pass 1 + features + K5 statistics + transform update + pass 2 (fMLLR features), host wall clock around synchronised calls",
+                           "ms": sat_ms, "xRT": c.seconds / (sat_ms * 1e-3), "aligned_pass1": ok1, "aligned_pass2": ok2,
+                           "sum_loglike_pass1": l1, "sum_loglike_pass2": l2, "speakers": int(c.n_spk)}
     upd = {}
 
     def k5u():

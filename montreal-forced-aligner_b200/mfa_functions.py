@@ -679,3 +679,35 @@ def align_one(sound_file_path, utterances: Sequence[Tuple[Optional[float], Optio
         Path(output_path).parent.mkdir(parents=True, exist_ok=True)
         file_ctm.export_textgrid(output_path, file_duration=file_duration, output_format=output_format, silence_word=lexicon.silence_word)
     return file_ctm
+
+
+def two_pass_align_pcm(engine, ali_model, model, graphs, pcm, sample_off, utt2spk, n_spk: int, mfcc_opts, feat_mode: str = "lda", lda=None,
+                       silence_phone_ids: Sequence[int] = (), silence_weight: float = 0.0, align_opts=None, workspace_bytes: int = 0,
+                       min_count: float = 500.0, num_iters: int = 40):
+    """CorpusAligner.align's two passes (alignment/base.py:491-558) for one in-memory batch, nothing leaving the GPU but the per-speaker
+    transforms: pass 1 with the speaker-independent model -> per-speaker fMLLR statistics and transforms (K5) -> pass 2 with the
+    speaker-adapted model on the transformed features.  `ali_model` / `model` are engine.DeviceModel (the same object when there is no
+    separate .alimdl), `graphs` an engine.Graphs, `pcm` a numpy array or a torch cuda tensor (then every intermediate stays on the device).
+    Returns (pass-1 AlignResult, transforms [n_spk, D, D+1] float32 numpy, (objf improvement, count) per speaker, pass-2 AlignResult)."""
+    from . import engine as E
+    r1 = E.align_pcm(engine, ali_model, graphs, pcm, sample_off, utt2spk, n_spk, mfcc_opts, feat_mode, lda=lda, align=align_opts,
+                     workspace_bytes=workspace_bytes)
+    raw, fo = engine.mfcc(pcm, sample_off, mfcc_opts)
+    stats = engine.cmvn_stats(raw, fo, utt2spk, n_spk)
+    engine.sync()
+    cm = stats.cpu().numpy() if E._is_torch(stats) else stats
+    feats = engine.features(raw, fo, feat_mode, lda=lda, cmvn_stats=cm, utt2spk=utt2spk, n_spk=n_spk)
+    tm = model.tm
+    sil = np.isin(tm.tid2phone, np.asarray(sorted(int(p) for p in silence_phone_ids), tm.tid2phone.dtype))
+    tw = np.where(sil, np.float32(silence_weight), np.float32(1.0)).astype(np.float32)
+    tw[0] = 0.0
+    T = int(fo[-1])
+    ali = r1.ali[:T] if E._is_torch(r1.ali) else np.ascontiguousarray(r1.ali[:T])
+    fstats = model.fmllr_acc(feats, ali.contiguous() if E._is_torch(ali) else ali, fo, utt2spk, n_spk, tid_weight=tw,
+                             post_model=ali_model if ali_model is not model else None)
+    W, impr, count = engine.fmllr_update(fstats, model.dim, num_iters, min_count)
+    engine.sync()   # `raw` / `feats` / `fstats` may be recycled by torch from here on
+    Wh = W.cpu().numpy() if E._is_torch(W) else np.asarray(W)
+    r2 = E.align_pcm(engine, model, graphs, pcm, sample_off, utt2spk, n_spk, mfcc_opts, feat_mode, lda=lda, fmllr=Wh, align=align_opts,
+                     workspace_bytes=workspace_bytes)
+    return r1, Wh, (impr, count), r2

@@ -355,3 +355,49 @@ def test_align_one_file_with_segments(tmp_path):
     one = MF.align_utterance_online_ctm(tmp_path / "final.mdl", tmp_path / "tree", c.lexicon, u)
     assert [w.label for w in one.word_intervals if w.label != "<eps>"] == segs[0][3].split()
     assert one.word_intervals[0].begin >= segs[0][0] - 1e-6
+
+
+def test_two_pass_align_pcm_in_memory():
+    """The in-memory two-pass flow (pass 1 -> K5 statistics + transforms -> pass 2) on numpy and on device-resident PCM: transforms equal
+    the oracle's on the oracle's features and pass-1 alignments; pass 2 equals the oracle on the transformed features."""
+    import torch
+    from helpers import oracle_align_all
+    from mfa_b200 import engine as E
+    sc = build_synth_scenario(seconds=80.0, seed=43, triphone=True, n_phones=8, n_words=40, gauss_per_pdf=2, n_spk=3, use_lda=True)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    eng = KC.get_engine()
+    dm = E.DeviceModel(eng, tm, am)
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    sil = [c.lexicon.phone_table["sil"]]
+    r1, W, (impr, count), r2 = MF.two_pass_align_pcm(eng, dm, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda",
+                                                     lda=sc["lda"], silence_phone_ids=sil, min_count=100.0)
+    fsts = batch.export()
+    ref1 = oracle_align_all(sc, fsts)
+    g = O.GmmModel.from_am(am)
+    tw = np.where(tm.tid2phone == sil[0], np.float32(0), np.float32(1)).astype(np.float32); tw[0] = 0
+    D = am.dim
+    stats = np.zeros((c.n_spk, O.fmllr_stats_size(D)))
+    for u, r in enumerate(ref1):
+        if r["status"] < 2:
+            O.fmllr_acc(g, g, tm.tid2pdf, tw, sc["feats"][u], r["ali"], stats[c.utt2spk[u]])
+    same = total = 0
+    tc = -tm.scaled_transition_log_probs(1.0, 0.1)
+    for s in range(c.n_spk):
+        Wo, io = O.fmllr_update(stats[s], D, min_count=100.0)
+        assert np.abs(W[s] - Wo).max() < 2e-3 and abs(count[s] - stats[s, 0]) <= 1e-3 * stats[s, 0]
+    for u in range(min(c.n_utts, 8)):
+        f = O.transform(sc["feats"][u], W[c.utt2spk[u]])
+        r = O.align(fsts[u], tc, g, tm.tid2pdf, f, f.shape[0])
+        got = r2.utterance(u)
+        assert got["status"] == r["status"]
+        same += int((got["ali"] == r["ali"]).sum()); total += len(r["ali"])
+    assert same / total >= 0.999
+    # device-resident PCM: same transforms (f64 atomics reorder the statistics, so to rounding) and the same pass-2 alignments
+    d = torch.from_numpy(c.pcm).cuda()
+    _, Wd, _, r2d = MF.two_pass_align_pcm(eng, dm, dm, graphs, d, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"],
+                                          silence_phone_ids=sil, min_count=100.0)
+    eng.sync()
+    assert np.abs(Wd - W).max() < 1e-4
+    assert (r2d.ali.cpu().numpy()[: r2.ali.shape[0]] == r2.ali).mean() >= 0.999
+    graphs.close(); batch.close(); dm.close()
