@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(ANT, NIJ <= 4 ? 2 : 1)
 fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab, const float *__restrict__ cnt, int dim,
                    const int64_t *__restrict__ frame_off, const int32_t *__restrict__ spk_utt_off, const int32_t *__restrict__ spk_utts,
                    int n_dtile, int n_split, double *__restrict__ stats, int64_t stats_stride) {
-  __shared__ __align__(16) double s_xp[FB][66];
+  __shared__ __align__(16) double s_xp[FB][66];   // row stride XS below
   __shared__ __align__(16) double s_b[FB][DT], s_a[FB][DT];
   __shared__ float s_c[FB];
   const int t = threadIdx.x;
@@ -121,6 +121,12 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
   double kacc[2] = {0.0, 0.0};
   const int kd0 = t / D1, kj0 = t - kd0 * D1, kd1 = (t + ANT) / D1, kj1 = (t + ANT) - kd1 * D1;
   const bool k0ok = t < DT * D1, k1ok = t + ANT < DT * D1;
+  constexpr int XS = 66;   // row stride of s_xp (doubles)
+  const double *xi[NIJ], *xj[NIJ];
+#pragma unroll
+  for (int k = 0; k < NIJ; k++) { xi[k] = &s_xp[0][pi[k]]; xj[k] = &s_xp[0][pj[k]]; }
+  // K: the (row, column) pairs this thread owns, clamped to a valid address when it owns none (the sum is then never written)
+  const double *ka0 = &s_a[0][k0ok ? kd0 : 0], *kx0 = &s_xp[0][k0ok ? kj0 : 0], *ka1 = &s_a[0][k1ok ? kd1 : 0], *kx1 = &s_xp[0][k1ok ? kj1 : 0];
   double beta = 0.0;
   // Batches of FB frames of this speaker, every n_split-th one for this CTA.  The next batch's global loads are issued into
   // registers before the current batch is consumed (the f64 accumulation hides their latency), staged to shared memory as doubles.
@@ -168,19 +174,24 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
     more = next_batch(cur_fb, cur_n);
     if (more) prefetch(cur_fb, cur_n);
     if (dtile == 0 && t < 32) { const double c = warp_sum_d((double)s_c[t]); if (t == 0) beta += c; }
-    for (int f = 0; f < n; f++) {
-      if (s_c[f] == 0.0f) continue;   // dropped frame (weight 0): Kaldi never sees it
-      double b[DT];
+    // fully unrolled over the batch: every shared-memory operand is (a per-thread base register) + (frame * row stride) as an immediate
+    // -- no address arithmetic, no per-frame predicate recomputation in the loop (the first version spent 2/3 of its issue slots on them).
+    // Frames beyond n and dropped frames (weight 0: Kaldi never sees them) carry s_c = 0.
 #pragma unroll
-      for (int d = 0; d < DT; d += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_b[f][d]); b[d] = v.x; b[d + 1] = v.y; }
+    for (int f = 0; f < FB; f++) {
+      if (s_c[f] != 0.0f) {
+        double b[DT];
 #pragma unroll
-      for (int k = 0; k < NIJ; k++) {
-        const double z = s_xp[f][pi[k]] * s_xp[f][pj[k]];
+        for (int d = 0; d < DT; d += 2) { const double2 v = *reinterpret_cast<const double2 *>(&s_b[f][d]); b[d] = v.x; b[d + 1] = v.y; }
 #pragma unroll
-        for (int d = 0; d < DT; d++) g[k][d] += b[d] * z;
+        for (int k = 0; k < NIJ; k++) {
+          const double z = xi[k][f * XS] * xj[k][f * XS];
+#pragma unroll
+          for (int d = 0; d < DT; d++) g[k][d] += b[d] * z;
+        }
+        kacc[0] += ka0[f * DT] * kx0[f * XS];
+        kacc[1] += ka1[f * DT] * kx1[f * XS];
       }
-      if (k0ok) kacc[0] += s_a[f][kd0] * s_xp[f][kj0];
-      if (k1ok) kacc[1] += s_a[f][kd1] * s_xp[f][kj1];
     }
   }
   double *st = stats + (size_t)spk * stats_stride;
