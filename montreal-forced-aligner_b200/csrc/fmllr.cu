@@ -22,9 +22,12 @@
 using namespace mfa;
 
 namespace {
+#ifndef MFA_FMLLR_DT
+#define MFA_FMLLR_DT 8
+#endif
 constexpr int FW = 8;     // warps per CTA in the frame kernel
 constexpr int FB = 32;    // frames per staged batch in the accumulation kernel
-constexpr int DT = 8;     // rows d per CTA
+constexpr int DT = MFA_FMLLR_DT;     // rows d per CTA
 constexpr int ANT = 256;  // threads per CTA in the accumulation kernel
 
 __global__ void __launch_bounds__(FW * 32)
@@ -89,7 +92,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // stats per speaker (doubles): beta | K[D][D+1] | G[D][NP], NP = (D+1)(D+2)/2 (row-major lower triangle)
 template <int NIJ>
-__global__ void __launch_bounds__(ANT, NIJ <= 4 ? 2 : 1)
+__global__ void __launch_bounds__(ANT, NIJ <= 4 ? (DT <= 4 ? 3 : 2) : 1)
 fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab, const float *__restrict__ cnt, int dim,
                    const int64_t *__restrict__ frame_off, const int32_t *__restrict__ spk_utt_off, const int32_t *__restrict__ spk_utts,
                    int n_dtile, int n_split, double *__restrict__ stats, int64_t stats_stride) {
@@ -131,7 +134,7 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
   // Batches of FB frames of this speaker, every n_split-th one for this CTA.  The next batch's global loads are issued into
   // registers before the current batch is consumed (the f64 accumulation hides their latency), staged to shared memory as doubles.
   const int xc = t & 63, xr = t >> 6;          // x: column xc of rows xr, xr+4, ..., xr+28
-  const int af = t >> 3, ad = t & 7;           // a / b: frame af, row d0 + ad
+  const int af = t / DT, ad = t % DT;          // a / b: frame af (< FB for the first FB * DT threads), row d0 + ad
   int ui = spk_utt_off[spk];
   const int ui_end = spk_utt_off[spk + 1];
   int64_t fb = 0, f1 = 0;
@@ -155,7 +158,7 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
   auto prefetch = [&](int64_t b0, int n) {
 #pragma unroll
     for (int k = 0; k < 8; k++) { const int r = xr + 4 * k; px[k] = (r < n && xc < dim) ? __ldg(feats + (b0 + r) * dim + xc) : 0.0f; }
-    const bool ok = af < n && d0 + ad < dim;
+    const bool ok = af < n && af < FB && d0 + ad < dim;
     pa = ok ? __ldg(ab + (size_t)(b0 + af) * 2 * dim + d0 + ad) : 0.0f;
     pb = ok ? __ldg(ab + (size_t)(b0 + af) * 2 * dim + dim + d0 + ad) : 0.0f;
     pc = t < n ? __ldg(cnt + b0 + t) : 0.0f;
@@ -168,7 +171,7 @@ fmllr_accum_kernel(const float *__restrict__ feats, const float *__restrict__ ab
     __syncthreads();   // the previous batch has been consumed
 #pragma unroll
     for (int k = 0; k < 8; k++) { const int r = xr + 4 * k; if (xc < dim) s_xp[r][xc] = (double)px[k]; else if (xc == dim) s_xp[r][xc] = 1.0; }
-    s_a[af][ad] = (double)pa; s_b[af][ad] = (double)pb;
+    if (af < FB) { s_a[af][ad] = (double)pa; s_b[af][ad] = (double)pb; }
     if (t < FB) s_c[t] = t < n ? pc : 0.0f;
     __syncthreads();
     more = next_batch(cur_fb, cur_n);
