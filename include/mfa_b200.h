@@ -233,6 +233,15 @@ MFA_API int mfa_align(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_alig
                       const int64_t *frame_off, int32_t n_utts, int32_t *ali, float *per_frame, int32_t *words,
                       const int64_t *word_off, int32_t *num_words, float *total_like, int32_t *status, int where);
 
+/* ---- features -> alignments: K2 (per utterance only the pdfs of its graph) + K3 on FINAL features [frame_off[n]][dim], no log-likelihood
+ *      matrix crossing the boundary.  This is what GmmAligner.align_utterance / export_alignments run per batch
+ *      (alignment/multiprocessing.py:846-853): kalpy's decodable evaluates the GMMs lazily inside the decoder, so a drop-in must not
+ *      materialise frames x all pdfs either.  gmm_impl as in mfa_pipeline_opts; workspace_bytes 0 = 8 GiB.  Outputs as mfa_align. */
+MFA_API int mfa_align_feats(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_opts *o, const float *feats,
+                            const int64_t *frame_off, int32_t n_utts, int32_t gmm_impl, int64_t workspace_bytes, int32_t *ali,
+                            float *per_frame, int32_t *words, const int64_t *word_off, int32_t *num_words, float *total_like,
+                            int32_t *status, int where);
+
 /* ---- fused hot path: PCM -> MFCC -> CMVN -> features -> loglikes -> Viterbi, chunked so that the
  *      log-likelihood and back-pointer buffers stay inside `workspace_bytes` of HBM.
  *      This is AlignFunction._run's per-job loop (alignment/multiprocessing.py:791-863) on one GPU. */

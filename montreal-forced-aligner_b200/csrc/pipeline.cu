@@ -459,6 +459,80 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   return MFA_OK;
 }
 
+int mfa_align_feats(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_opts *o, const float *feats, const int64_t *frame_off,
+                    int32_t n_utts, int32_t gmm_impl, int64_t workspace_bytes, int32_t *ali, float *per_frame, int32_t *words,
+                    const int64_t *word_off, int32_t *num_words, float *total_like, int32_t *status, int where) {
+  if (!e || !m || !g || !o || !frame_off || !word_off) return set_error(MFA_ERR_INVALID, "bad argument");
+  if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
+  MFA_TRY(check_offsets(frame_off, n_utts, "frame_off"));
+  MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
+  e->gmm_timing_reset();
+  e->stage_reset();
+  MFA_TRY(upload_graphs(e, g));
+  const int P = m->num_pdfs, D = m->dim;
+  const int64_t nf = frame_off[n_utts], nw = word_off[n_utts];
+  int64_t *d_fo; const float *d_in;
+  MFA_TRY(e->upload(DB_FRAME_OFF, frame_off, (size_t)n_utts + 1, &d_fo));
+  MFA_TRY(to_device(e, DB_IO_FEATS, feats, (size_t)nf * D, where, &d_in));
+  AlignIO io;
+  MFA_TRY(out_buffer(e, DB_ALI, ali, (size_t)nf, where, &io.d_ali));
+  MFA_TRY(out_buffer(e, DB_PERFRAME, per_frame, (size_t)nf, where, &io.d_pf));
+  MFA_TRY(out_buffer(e, DB_WORDS, words, (size_t)nw, where, &io.d_words));
+  MFA_TRY(out_buffer(e, DB_NUM_WORDS, num_words, (size_t)n_utts, where, &io.d_num_words));
+  MFA_TRY(out_buffer(e, DB_TOTAL_LIKE, total_like, (size_t)n_utts, where, &io.d_total));
+  MFA_TRY(out_buffer(e, DB_STATUS, status, (size_t)n_utts, where, &io.d_status));
+  MFA_TRY(e->upload(DB_WORD_OFF, word_off, (size_t)n_utts + 1, &io.d_word_off));
+  CUDA_TRY(cudaMemsetAsync(io.d_ali, 0, (size_t)nf * 4, e->stream));
+  CUDA_TRY(cudaMemsetAsync(io.d_pf, 0, (size_t)nf * 4, e->stream));
+  if (nw) CUDA_TRY(cudaMemsetAsync(io.d_words, 0, (size_t)nw * 4, e->stream));
+  const int64_t budget = workspace_bytes > 0 ? workspace_bytes : ((int64_t)8 << 30);
+  const bool ragged = gmm_impl == 0 && gmm_tc_supported(m);
+  mfa_feat_opts copy{};   // mode 0: the features are final; the kernel only moves them into the 8-aligned per-utterance columns K2 reads
+  copy.mode = 0; copy.in_dim = D;
+  std::vector<ChunkPlan> plans;
+  MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, plans, ragged));
+  for (auto &c : plans) {
+    float *d_feats, *d_llT; int64_t *d_col, *d_ll_off = nullptr, *d_ld_u = nullptr;
+    MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
+    MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
+    MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
+    MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
+    CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
+    MFA_TRY(launch_features(e, &copy, d_in, d_fo + c.u0, frame_off + c.u0, d_col, nullptr, c.n, nullptr, d_feats, D));
+    MFA_TRY(e->stage_end());
+    MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
+    if (ragged) {
+      MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
+      MFA_TRY(e->upload(DB_LD_U, c.ld_u.data(), c.ld_u.size(), &d_ld_u));
+      MFA_TRY(e->gmm_timing_begin());
+      MFA_TRY(launch_gmm_tc_ragged(e, m, g, c.u0, c.n, d_feats, c.col_off.data(), frame_off + c.u0, d_llT, c.ll_off.data(), c.ld_u.data()));
+      MFA_TRY(e->gmm_timing_end(frame_off[c.u0 + c.n] - frame_off[c.u0]));
+    } else {
+      MFA_TRY(run_gmm(e, m, d_feats, c.ld, d_llT, c.ld, gmm_impl));
+    }
+    MFA_TRY(e->stage_end());
+    ViterbiArgs a{};
+    a.d_ll_off = d_ll_off; a.d_ld_u = d_ld_u;
+    a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
+    a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
+    a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
+    a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = *o;
+    MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
+    MFA_TRY(launch_viterbi(e, a));
+    MFA_TRY(e->stage_end());
+  }
+  MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
+  MFA_TRY(from_device(e, io.d_words, words, (size_t)nw, where));
+  MFA_TRY(from_device(e, io.d_num_words, num_words, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_total, total_like, (size_t)n_utts, where));
+  MFA_TRY(from_device(e, io.d_status, status, (size_t)n_utts, where));
+  if (where == MFA_HOST) CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
 int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const int32_t *ali, int64_t n_frames, int where) {
   if (!e || !m || n_frames < 0) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));

@@ -555,6 +555,24 @@ def align_loglikes(engine: Engine, model: DeviceModel, graphs: Graphs, loglikes,
     return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
 
 
+def align_feats(engine: Engine, model: DeviceModel, graphs: Graphs, feats, frame_off, opts: L.AlignOpts, gmm_impl: int = 0,
+                workspace_bytes: int = 0) -> AlignResult:
+    """K2 (per-utterance pdf subsets) + K3 on final features [sum T, dim] (mfa_align_feats): what GmmAligner runs per batch."""
+    fo, fop = _host(frame_off, np.int64)
+    n = fo.shape[0] - 1
+    wo = np.zeros(n + 1, np.int64)
+    wo[1:] = np.cumsum(graphs.max_words())
+    k, fp, where = _buf(feats, np.float32, "feats")
+    dev = feats.device if where == L.MFA_DEVICE else None
+    ali, pf, words, nw, tl, st = _alloc_outputs(int(fo[-1]), int(wo[-1]), n, dev)
+    ptrs = [_buf(x, dt)[1] for x, dt in ((ali, np.int32), (pf, np.float32), (words, np.int32))]
+    p2 = [_buf(x, dt)[1] for x, dt in ((nw, np.int32), (tl, np.float32), (st, np.int32))]
+    L.check(L.lib().mfa_align_feats(engine._h, model._h, graphs._h, C.byref(opts), fp, fop, C.c_int32(n), C.c_int32(gmm_impl),
+                                    C.c_int64(int(workspace_bytes)), ptrs[0], ptrs[1], ptrs[2], wo.ctypes.data_as(C.c_void_p), p2[0], p2[1], p2[2],
+                                    C.c_int(where)))
+    return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
+
+
 def align_pcm(engine: Engine, model: DeviceModel, graphs: Graphs, pcm, sample_off, utt2spk, n_spk: int, mfcc: L.MfccOpts,
               feat_mode: str = "deltas", lda=None, splice_ctx: int = 3, fmllr=None, cmvn_stats=None, apply_cmvn: bool = True,
               align: Optional[L.AlignOpts] = None, gmm_impl: int = 0, workspace_bytes: int = 0, outputs=None) -> AlignResult:

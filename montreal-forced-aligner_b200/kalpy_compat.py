@@ -402,8 +402,8 @@ class GmmAligner:
         """K2 + K3 for a batch of utterances whose final features are concatenated in `feats`."""
         batch = E.FstBatch.from_fsts(list(fsts))
         graphs = E.Graphs(batch, self.transition_model, self.transition_scale, self.self_loop_scale)
-        ll = self._dm.loglikes(np.ascontiguousarray(feats, np.float32), impl=self.gmm_impl)
-        res = E.align_loglikes(self.engine, self._dm, graphs, ll, frame_off, self._opts())
+        # features in, alignments out: the log-likelihoods (only the pdfs each utterance's graph references) never leave the GPU
+        res = E.align_feats(self.engine, self._dm, graphs, np.ascontiguousarray(feats, np.float32), frame_off, self._opts(), gmm_impl=self.gmm_impl)
         out: List[Optional[Alignment]] = []
         for u, k in enumerate(keys):
             r = res.utterance(u)

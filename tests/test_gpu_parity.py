@@ -533,3 +533,37 @@ def test_gmm_loglikes_odd_gaussian_count_and_ragged_pdfs(eng, monkeypatch, k96):
         ref = O.gmm_loglikes(O.GmmModel.from_am(am), x[:T])
         assert np.all(np.abs(ll - ref) <= 1e-4 * np.abs(ref) + 1e-4), (T, np.abs(ll - ref).max())
     dm.close()
+
+
+@pytest.mark.parametrize("triphone,use_lda", [(False, False), (True, True)])
+def test_align_feats_equals_dense_loglikes_path(eng, triphone, use_lda):
+    """mfa_align_feats (final features in, per-utterance pdf subsets scored on the device) against mfa_gmm_loglikes + mfa_align (the dense
+    frames x all-pdfs matrix through host memory) and the oracle; host and device inputs; a tiny workspace forces several chunks."""
+    import torch
+    sc = build_synth_scenario(seconds=40.0, seed=51, triphone=triphone, n_phones=8, n_words=30, gauss_per_pdf=3, use_lda=use_lda)
+    tm, am, c = sc["tm"], sc["am"], sc["corpus"]
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    dm = E.DeviceModel(eng, tm, am)
+    feats = np.concatenate(sc["feats"]).astype(np.float32)
+    fo = sc["frame_off"]
+    opts = E.align_opts()
+    a = E.align_feats(eng, dm, graphs, feats, fo, opts)
+    b = E.align_loglikes(eng, dm, graphs, dm.loglikes(feats, impl=0), fo, opts)
+    assert np.array_equal(a.status, b.status) and (a.ali == b.ali).mean() >= 0.999
+    assert np.allclose(a.total_like, b.total_like, rtol=1e-4)
+    ref = oracle_align_all(sc, batch.export())
+    same = total = 0
+    for u, r in enumerate(ref):
+        got = a.utterance(u)
+        assert got["status"] == r["status"]
+        if r["status"] < 2:
+            same += int((got["ali"] == r["ali"]).sum()); total += len(r["ali"])
+            assert list(got["words"]) == list(r["words"]) and abs(got["like"] - r["like"]) <= 1e-4 * abs(r["like"])
+    assert same / total >= 0.999
+    small = E.align_feats(eng, dm, graphs, feats, fo, opts, workspace_bytes=2 << 20)       # several chunks
+    assert np.array_equal(small.ali, a.ali) and np.array_equal(small.status, a.status)
+    d = E.align_feats(eng, dm, graphs, torch.from_numpy(feats).cuda(), fo, opts)            # device buffers
+    eng.sync()
+    assert np.array_equal(d.ali.cpu().numpy()[: a.ali.shape[0]], a.ali)
+    graphs.close(); batch.close(); dm.close()
