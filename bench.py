@@ -216,7 +216,7 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     return out
 
 
-def train_loop(eng, sc, step_device, dev, stream, dist, args):
+def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
     """Config 4's loop on this rank's shard: align (fused step) -> K4 statistics -> all-reduce over NCCL (N > 1) -> D2H -> host M-step
     (gmm_update.mle_update, vectorised numpy f64) -> new model on the device.  Transition costs stay folded in the packed graphs
     (MFA recompiles graphs only at realignment iterations).  Wall-clock per stage, max over ranks is NOT taken: rank 0's view."""
@@ -227,7 +227,7 @@ def train_loop(eng, sc, step_device, dev, stream, dist, args):
     fo = sc.frame_off
     T = int(fo[-1])
     model, am = sc.model, sc.am
-    raw, _ = eng.mfcc(_D_PCM[0], c.sample_off, mo)
+    raw, _ = eng.mfcc(d_pcm, c.sample_off, mo)
     stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
     eng.sync()
     feats = eng.features(raw, fo, sc.feat_mode, lda=sc.lda, cmvn_stats=stats.cpu().numpy(), utt2spk=c.utt2spk, n_spk=c.n_spk)
@@ -239,7 +239,7 @@ def train_loop(eng, sc, step_device, dev, stream, dist, args):
     for it in range(args.train_iters):
         t = {}
         t0 = time.perf_counter()
-        res = E.align_pcm(eng, model, sc.graphs, _D_PCM[0], c.sample_off, c.utt2spk, c.n_spk, mo,
+        res = E.align_pcm(eng, model, sc.graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo,
                           sc.feat_mode, lda=sc.lda, workspace_bytes=int(args.workspace_gb * (1 << 30)), outputs=outs)
         eng.sync(); t["align_ms"] = 1e3 * (time.perf_counter() - t0)
         t0 = time.perf_counter()
@@ -271,9 +271,6 @@ def train_loop(eng, sc, step_device, dev, stream, dist, args):
     if model is not sc.model:
         model.close()
     return {"iterations": iters, "note": "wall-clock per stage on rank 0 (host timers around synchronised stages); avg_loglike_per_frame must not decrease"}
-
-
-_D_PCM = [None]
 
 
 def main():
@@ -371,7 +368,6 @@ def main():
     mo = E.mfcc_opts()
     wo_total = int(np.cumsum(sc.graphs.max_words())[-1])
     d_pcm = torch.from_numpy(c.pcm).to(dev)
-    _D_PCM[0] = d_pcm
     outs = E._alloc_outputs(n_frames, wo_total, c.n_utts, dev)
     ws = int(args.workspace_gb * (1 << 30))
 
@@ -395,11 +391,9 @@ def main():
     l0 = eng.launch_count
     fb0 = eng.band_fallbacks
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gmm_ms = gmm_n = gmm_rows = 0
     ev0.record(stream)
     for _ in range(args.steps):
         res = step_device()
-        ms, n, rows = 0.0, 0, 0
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -529,7 +523,8 @@ def main():
         k1 = {"kernel": "K1 mfcc512_kernel + CMVN statistics", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
               "frac": ach / pk["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": stages["mfcc_cmvn"],
               "share_of_step": stages["mfcc_cmvn"] / step_ms,
-              "note": "fp32-ALU / issue bound (register FFT, ~600 warp instructions per frame), not HBM bound -- see profiles/r1_mfcc512_full.md"}
+              "achieved_fp32_tflops": 16.0e3 * n_frames / (stages["mfcc_cmvn"] * 1e-3) / 1e12,   # ~16 kFLOP per frame
+              "note": "fp32-ALU / issue bound (register FFT, ~1 080 warp instructions per frame, 38 % of them FADD/FFMA/FMUL), not HBM bound -- see profiles/r1_mfcc512_full.md"}
     cands = [x for x in (k2, k3, k1) if x]
     roof = max(cands, key=lambda x: x["share_of_step"]) if cands else None
 
@@ -548,7 +543,7 @@ def main():
     if not args.no_extras and (world == 1 or args.extras_dist):
         try:
             line["extras"] = train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args)
-            line["extras"]["train_loop"] = train_loop(eng, sc, step_device, dev, stream, dist, args)
+            line["extras"]["train_loop"] = train_loop(eng, sc, d_pcm, dev, stream, dist, args)
         except Exception as ex:
             line["extras"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the reference arm times the CPU path at every N)
