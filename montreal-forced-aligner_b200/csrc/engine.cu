@@ -58,8 +58,15 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  // side streams carry the Viterbi size classes (class k on side[k]); larger classes = longer utterances = the launch's critical path,
+  // so they get the higher stream priorities and their CTAs are placed first (MFA_VIT_PRIO=0: all equal)
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  const char *pv = getenv("MFA_VIT_PRIO");
+  const bool use_prio = !(pv && atoi(pv) == 0);
   for (int k = 0; k < mfa_engine::kSide; k++) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+    const int prio = use_prio ? std::max(prio_greatest, prio_least - k) : prio_least;
+    CUDA_TRY(cudaStreamCreateWithPriority(&e->side[k], cudaStreamNonBlocking, prio));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
