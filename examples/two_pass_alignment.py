@@ -17,7 +17,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from mfa_b200 import kaldi_io as K, kalpy_compat as KC, mfa_functions as MF, export as X  # noqa: E402
 
@@ -26,10 +25,10 @@ def main():
     out = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(tempfile.mkdtemp(prefix="mfa_b200_example_"))
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
     out.mkdir(parents=True, exist_ok=True)
-    # a small synthetic "language", corpus and triphone LDA model (the tests' scenario builder; the oracle is only used there to
-    # estimate the model's Gaussians from features -- the alignment below runs on the GPU engine)
-    from helpers import build_synth_scenario
-    sc = build_synth_scenario(seconds=seconds, seed=3, triphone=True, n_phones=10, n_words=60, gauss_per_pdf=2, n_spk=4, use_lda=True)
+    # a small synthetic "language", corpus and triphone LDA model; the model's Gaussians are estimated from the engine's own features
+    from mfa_b200 import scenario as SC
+    built = SC.build(KC.get_engine(), seconds, seed=3, triphone=True, target_pdfs=200, gauss_per_pdf=2, use_lda=True, n_phones=10, n_words=60)
+    sc = {"corpus": built.corpus, "tm": built.tm, "am": built.am, "tree": built.tree, "lda": built.lda}
     c, tm, am = sc["corpus"], sc["tm"], sc["am"]
     split, work, wavs = out / "split", out / "work", out / "wav"
     for d in (split, work, wavs):

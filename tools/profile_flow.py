@@ -2,7 +2,7 @@
 import cProfile, pstats, sys, os
 from pathlib import Path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "examples"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "examples"))
 import two_pass_alignment as ex
 sys.argv = ["x", sys.argv[1] if len(sys.argv) > 1 else "/tmp/ex", sys.argv[2] if len(sys.argv) > 2 else "1800"]
 pr = cProfile.Profile()
