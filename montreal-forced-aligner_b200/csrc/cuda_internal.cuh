@@ -144,7 +144,7 @@ struct mfa_model {
   void *d_tc_rows = nullptr;           // fp16 hi/lo weight rows [2][G][tc_k] (row-major; source of the per-utterance tile gather)
   int tc_k = 96;                       // K extent of the operand images: 80 (gconst added by the epilogue) or 96 (gconst as fp16 columns)
   float *d_tc_g = nullptr;             // gconst * log2(e): [G] per Gaussian, then [n_tiles][128] per column of the dense tiling
-  uint64_t tc_version = 0;             // bumps whenever the tiling / weights change (invalidates cached ragged plans)
+  uint64_t tc_version = 0;             // hash of the pdf -> Gaussian layout and the operand geometry: the key of the cached ragged plans
   double *d_acc = nullptr;
   int rebuild_tiles();
   ~mfa_model();

@@ -514,8 +514,12 @@ int build_tc(mfa_model *m) {
   CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, D * sizeof(float)));
   CUDA_TRY(cudaMemcpyAsync(m->d_tc_colscale, m->h_tc_colscale.data(), D * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  static uint64_t version_counter = 0;
-  m->tc_version = ++version_counter;
+  // The per-utterance tile plan cached in mfa_graphs depends only on how many Gaussians each pdf has (and on the geometry), not on the
+  // parameter values: key it on a hash of that layout, so that a re-estimated model with an unchanged layout (the usual case between
+  // training iterations once pruning and mix-up have settled, and for the .alimdl / .mdl pair of a two-pass alignment) reuses the plan.
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)TK;
+  for (int32_t v : m->h_pdf_off) { h ^= (uint64_t)(uint32_t)v; h *= 1099511628211ull; }
+  m->tc_version = h | 1ull;
   m->tc_ready = true;
   return MFA_OK;
 }
