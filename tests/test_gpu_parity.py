@@ -567,3 +567,47 @@ def test_align_feats_equals_dense_loglikes_path(eng, triphone, use_lda):
     eng.sync()
     assert np.array_equal(d.ali.cpu().numpy()[: a.ali.shape[0]], a.ali)
     graphs.close(); batch.close(); dm.close()
+
+
+def test_new_entry_points_edge_cases(eng):
+    """Empty / degenerate inputs through the entry points added for rows a11, N2 and the features-in aligner: nothing crashes, statuses and
+    shapes are what the callers rely on."""
+    sc = build_synth_scenario(seconds=12.0, seed=61, n_phones=6, n_words=20, gauss_per_pdf=2)
+    tm, am, c = sc["tm"], sc["am"], sc["corpus"]
+    dm = E.DeviceModel(eng, tm, am)
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    n = c.n_utts
+    D = am.dim
+    # features-in aligner with utterances that have no frames at all
+    fo0 = np.zeros(n + 1, np.int64)
+    r = E.align_feats(eng, dm, graphs, np.zeros((0, D), np.float32), fo0, E.align_opts())
+    assert (r.status == 4).all() and r.ali.shape[0] == 0                       # MFA_ALIGN_ZERO_FRAMES
+    # ... and with one real utterance among empty ones
+    fo1 = np.zeros(n + 1, np.int64); fo1[1:] = sc["feats"][0].shape[0]
+    r = E.align_feats(eng, dm, graphs, sc["feats"][0], fo1, E.align_opts())
+    ref = oracle_align_all(sc, batch.export()[:1])[0]
+    assert r.status[0] == ref["status"] and (r.status[1:] == 4).all() and (r.utterance(0)["ali"] == ref["ali"]).mean() >= 0.999
+    # fMLLR statistics: zero frames, zero speakers
+    s = dm.fmllr_acc(np.zeros((0, D), np.float32), np.zeros(0, np.int32), fo0, c.utt2spk, c.n_spk)
+    assert s.shape == (c.n_spk, dm.fmllr_stats_size()) and not s.any()
+    W, impr, cnt = eng.fmllr_update(s, D)
+    assert (W == np.eye(D, D + 1, dtype=np.float32)).all() and not impr.any() and not cnt.any()
+    W0, i0, c0 = eng.fmllr_update(np.zeros((0, dm.fmllr_stats_size())), D)
+    assert W0.shape == (0, D, D + 1) and i0.shape == (0,)
+    # statistics with a mismatching posterior model are refused
+    from mfa_b200 import kaldi_io as K, _lib as L
+    am2 = K.AmDiagGmm(D, np.arange(am.NumPdfs() + 1, dtype=np.int32), np.ones(am.NumPdfs(), np.float32),
+                      np.zeros((am.NumPdfs(), D), np.float32), np.ones((am.NumPdfs(), D), np.float32))
+    dm2 = E.DeviceModel(eng, tm, am2)
+    if am2.NumGauss() != am.NumGauss():
+        with pytest.raises(L.MfaError):
+            dm.fmllr_acc(sc["feats"][0], np.ones(sc["feats"][0].shape[0], np.int32), fo1[:2], np.zeros(1, np.int32), 1, post_model=dm2)
+    # equal alignment of an empty batch / accumulators on no frames
+    empty = E.FstBatch.from_fsts([])
+    a, w, wo, nw, st = empty.equal_align(np.zeros(1, np.int64), [])
+    assert a.shape[0] == 0 and st.shape[0] == 0
+    dm.acc_zero(); dm.acc_stats(np.zeros((0, D), np.float32), np.zeros(0, np.int32))
+    assert dm.acc_read()["frames"] == 0
+    for x in (graphs, batch, dm, dm2, empty):
+        x.close()
