@@ -42,8 +42,32 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process (and the pinned host buffers it allocates and fills from now on: first touch) to the CPUs of the NUMA node
+    the GPU hangs off, so that the end-to-end arm's H2D traffic does not cross the socket interconnect.  Returns a description."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node < 0:
+            return {"pci": pci, "numa_node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"pci": pci, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"pci": pci, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as ex:   # containers without sysfs topology, older torch: run unbound
+        return {"bound": False, "why": repr(ex)}
+
+
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML, every ~5 ms; falls back to nvidia-smi polling)."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every 50 ms -- eight ranks polling every 5 ms made the
+    driver-side NVML lock a shared stall in round 1; falls back to nvidia-smi polling)."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
@@ -70,7 +94,7 @@ class ClockSampler:
                         self.mask |= int(self._nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
                     except Exception:
                         self.mask |= int(self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                    self._stop.wait(0.005)
+                    self._stop.wait(0.05)
                 else:
                     out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active", "--format=csv,noheader,nounits",
                                           "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip().split(",")
@@ -94,7 +118,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_pass(sc, utts, cores: int):
     """The oracle port (oracle/oracle.c: scalar restatement of the Kaldi path MFA calls through kalpy) over `utts`,
-    `cores` host threads (ctypes releases the GIL).  Returns (wall seconds, audio seconds, n_ok)."""
+    `cores` host threads (ctypes releases the GIL).  Returns (wall seconds, audio seconds, n_ok, results) -- results[i] is the
+    oracle's alignment of utts[i] (status, ali, words, like, per_frame), kept for the parity block of the JSON line."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
     c = sc.corpus
@@ -112,12 +137,54 @@ def cpu_reference_pass(sc, utts, cores: int):
         def one(u):
             x = O.cmvn_apply(raw[u], stats[int(c.utt2spk[u])])
             x = O.transform(O.splice(x, 3, 3), sc.lda) if sc.feat_mode == "lda" else O.add_deltas(x)
-            r = O.align(csr[u], tid_cost, g, sc.tm.tid2pdf, x, x.shape[0], 0.1, 10.0, 40.0)
-            return r["status"]
-        st = list(ex.map(one, utts))
+            return O.align(csr[u], tid_cost, g, sc.tm.tid2pdf, x, x.shape[0], 0.1, 10.0, 40.0)
+        res = list(ex.map(one, utts))
     dt = time.perf_counter() - t0
     secs = float(sum(c.sample_off[u + 1] - c.sample_off[u] for u in utts)) / 16000.0
-    return dt, secs, sum(1 for s in st if s < 2)
+    return dt, secs, sum(1 for r in res if r["status"] < 2), res
+
+
+def parity_block(sc, utts, ref, gpu):
+    """BASELINE.json's second metric: the GPU step's outputs against the oracle's on the CPU-baseline sample of the very same
+    workload (north_star bars: >= 99.9 % identical transition-ids, boundaries within one 10 ms frame, log-likelihood 1e-4 relative).
+    `gpu` = host copies (ali, per_frame, words, num_words, total_like, status) of the last timed device-resident step."""
+    from mfa_b200 import kalpy_compat as KC
+    ali, pf, words, nw, tl, st = gpu
+    fo = sc.frame_off
+    wo = np.zeros(len(fo), np.int64)
+    wo[1:] = np.cumsum(sc.graphs.max_words())
+    same = total = status_mis = word_mis = 0
+    b_ok = b_tot = 0
+    like_err = pf_err = 0.0
+    worst = None
+    for u, r in zip(utts, ref):
+        if int(st[u]) != int(r["status"]):
+            status_mis += 1
+            continue
+        if r["status"] >= 2:
+            continue
+        a = ali[fo[u]:fo[u + 1]]
+        n_same = int((a == r["ali"]).sum())
+        same += n_same; total += len(a)
+        if worst is None or len(a) - n_same > worst[1]:
+            worst = (int(u), len(a) - n_same, len(a))
+        if list(words[wo[u]:wo[u] + nw[u]]) != list(r["words"]):
+            word_mis += 1
+        like_err = max(like_err, abs(float(tl[u]) - r["like"]) / max(1e-30, abs(r["like"])))
+        d = np.abs(pf[fo[u]:fo[u + 1]][a == r["ali"]] - r["per_frame"][a == r["ali"]])
+        if d.size:
+            pf_err = max(pf_err, float((d / np.maximum(1.0, np.abs(r["per_frame"][a == r["ali"]]))).max()))
+        cg = KC.Alignment(str(u), a, [], float(tl[u])).generate_ctm(sc.tm, None)
+        cr = KC.Alignment(str(u), r["ali"], [], r["like"]).generate_ctm(sc.tm, None)
+        b_tot += 2 * len(cr)
+        if [x.label for x in cg] == [x.label for x in cr]:
+            b_ok += sum(int(abs(x.begin - y.begin) <= 0.0101) + int(abs(x.end - y.end) <= 0.0101) for x, y in zip(cg, cr))
+    return {"against": "oracle port (oracle/oracle.c), same utterances as cpu_baseline.sample; parity unpinned vs real Kaldi (DESIGN.md 2)",
+            "utterances": len(utts), "frames": total, "frame_agreement_pct": 100.0 * same / max(1, total), "status_mismatches": status_mis,
+            "word_sequence_mismatches": word_mis, "loglike_rel_err_max": like_err, "per_frame_loglike_rel_err_max": pf_err,
+            "boundary_within_1_frame_pct": 100.0 * b_ok / max(1, b_tot), "phone_boundaries": b_tot,
+            "worst_utterance": None if worst is None else {"utt": worst[0], "differing_frames": worst[1], "frames": worst[2]},
+            "retried_utterances_in_sample": int(sum(1 for r in ref if r["status"] == 1))}
 
 
 def pick_sample(sc, audio_seconds: float):
@@ -164,11 +231,8 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     out["k4_acc_stats"] = {"kernel": "K4 acc_hist + acc_scan + acc_scatter + acc_items_kernel (one acc-stats pass over the step's alignments)",
                            "ms": k4_ms, "bound": "hbm", "algorithmic_bytes": k4_bytes, "achieved": k4_bytes / (k4_ms * 1e-3) / 1e9, "unit": "GB/s",
                            "peak": pk["hbm_gbs"], "frac": k4_bytes / (k4_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "xRT": c.seconds / (k4_ms * 1e-3)}
-    os.environ["MFA_ACC_IMPL"] = "atomic"
-    try:
+    with eng.options(acc_impl=1):
         out["k4_acc_stats"]["first_version_atomic_ms"] = timed(k4, 1)
-    finally:
-        os.environ.pop("MFA_ACC_IMPL", None)
     acc = sc.model.acc_read()
     out["k4_acc_stats"]["frames"] = acc["frames"]
     out["k4_acc_stats"]["avg_loglike_per_frame"] = acc["like"] / max(1.0, acc["frames"])
@@ -287,7 +351,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=100.0)
     ap.add_argument("--train-iters", type=int, default=2, help="iterations of the align -> acc-stats -> all-reduce -> update loop timed under extras.train_loop")
-    ap.add_argument("--extras-dist", action="store_true", help="run the extras (incl. the NCCL all-reduce of the training loop) on multi-rank runs too")
+    ap.add_argument("--extras-dist", action="store_true", help="multi-rank runs: also time K4 / K5 / the SAT two-pass flow per rank (the training loop with its NCCL all-reduce always runs)")
+    ap.add_argument("--same-shards", action="store_true", help="multi-rank runs: every rank gets the SAME corpus (seed 1234): separates data effects (a rank owning a slow utterance) from system effects in the per-rank table")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this process to the CPUs of the GPU's NUMA node")
     ap.add_argument("--no-extras", action="store_true", help="skip the K4 / K5 timings reported under 'extras'")
     ap.add_argument("--e2e-jobs", type=int, default=2, help="concurrent jobs (engines) per GPU in the end-to-end arm")
     args = ap.parse_args()
@@ -315,6 +381,7 @@ def main():
         dist.barrier()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = {"bound": False} if (args.no_numa_bind or args.impl == "reference" or world == 1) else bind_to_gpu_numa(local_rank)
     eng = E.Engine(local_rank)
     cores = os.cpu_count() or 1
     seconds = args.hours * 3600.0
@@ -322,7 +389,7 @@ def main():
         # the reference arm only needs a bounded sample of the same workload; build a smaller corpus with the same model shape
         seconds = min(seconds, 1800.0)
     t0 = time.time()
-    sc = SC.build(eng, seconds, seed=1234 + rank, target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
+    sc = SC.build(eng, seconds, seed=1234 + (0 if args.same_shards else rank), target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
                   synth_device=dev, log=log if rank == 0 else None, model_seed=1234 if world > 1 else None)
     if dist is not None:
         # one replicated acoustic model (rank 0's estimate), each rank its own shard of utterances: what MFA's jobs see
@@ -351,7 +418,7 @@ def main():
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 8)], cores)
         times = []
         for _ in range(args.steps):
-            dt, secs, ok = cpu_reference_pass(sc, utts, cores)
+            dt, secs, ok, _ = cpu_reference_pass(sc, utts, cores)
             times.append(dt)
         T = float(np.sum(times))
         val = secs * args.steps / T
@@ -402,7 +469,9 @@ def main():
     stage_ms = eng.stage_timing()
     launches = eng.launch_count - l0
     fallbacks = eng.band_fallbacks - fb0
-    st = res.status.cpu().numpy()
+    gpu_host = tuple(x.cpu().numpy() for x in (res.ali, res.per_frame, res.words, res.num_words, res.total_like, res.status))
+    st = gpu_host[5]
+    retried = np.nonzero(st == 1)[0]
     n_ok = int((st < 2).sum())
     if dist is not None:
         t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
@@ -414,6 +483,23 @@ def main():
     else:
         dev_ms_max, audio_total, launches_total, ok_total, utts_total = dev_ms, audio_s, float(launches), float(n_ok), float(c.n_utts)
     value = audio_total * args.steps / (dev_ms_max / 1000.0)
+    # per-rank view (every rank has its own corpus, so one rank may own a slow Viterbi tail or a band fallback): device time per step,
+    # per-stage CUDA-event times of the last step, fallbacks, and the part of the step no stage accounts for
+    mine = {"rank": rank, "dev_ms_per_step": dev_ms / args.steps, "stages_ms": stage_ms, "k3_band_fallbacks": int(fallbacks),
+            "unaccounted_ms": dev_ms / args.steps - float(sum(stage_ms.values())), "utterances": int(c.n_utts), "frames": n_frames,
+            "longest_utt_frames": int((sc.frame_off[1:] - sc.frame_off[:-1]).max()), "retried": int(retried.size), "numa": numa}
+    per_rank = [mine]
+    if dist is not None:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+
+    def spread(key):
+        xs = [float(key(r)) for r in per_rank]
+        return {"min": min(xs), "median": float(np.median(xs)), "max": max(xs), "argmax_rank": int(np.argmax(xs))}
+    rank_summary = {"dev_ms_per_step": spread(lambda r: r["dev_ms_per_step"]), "unaccounted_ms": spread(lambda r: r["unaccounted_ms"]),
+                    "k3_band_fallbacks": spread(lambda r: r["k3_band_fallbacks"]), "longest_utt_frames": spread(lambda r: r["longest_utt_frames"]),
+                    **{f"stage_{k}_ms": spread(lambda r, k=k: r["stages_ms"][k]) for k in stage_ms},
+                    "same_shards": bool(args.same_shards)}
 
     # ---- end-to-end arm: host (pinned) PCM in, host results out, through the same C-ABI call ---------------------
     h_pcm = torch.from_numpy(c.pcm).pin_memory()
@@ -498,7 +584,7 @@ def main():
                 traffic = tj[key] * per_launch_flops
         k2 = {"kernel": "K2 gmm log-likelihoods (xsplit + gather_b + gmm_tc_kernel)", "bound": "tensor", "achieved": achieved,
               "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": traffic,
-              "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * (80.0 if 2 * sc.am.dim <= 80 and not int(os.environ.get("MFA_TC_K96", "0") or 0) else 96.0) / (2 * sc.am.dim + 1),
+              "peak_source": pk["source"] + " bf16 sustained", "issued_over_useful_flops": 3.0 * (80.0 if 2 * sc.am.dim <= 80 and not eng.get_option("tc_k96") else 96.0) / (2 * sc.am.dim + 1),
               "scored": "per-utterance pdf subsets" if args.gmm_impl == 0 else "all pdfs", "launches_per_step": gmm_n, "avg_launch_ms": avg_ms,
               "algorithmic_flops_per_launch": per_launch_flops, "share_of_step": gmm_ms / step_ms}
     # K3 (band kernel): algorithmic bytes per utterance = T * (4 P_u log-likelihoods read once + 512 back-pointer row
@@ -535,26 +621,38 @@ def main():
                     "steps": e2e_steps if n_jobs > 1 else args.steps, "single_job_value": e2e1_val, "single_job_stage_ms": e2e_stage_ms},
             "roofline": roof, "roofline_k2": k2, "roofline_k3": k3, "roofline_k1": k1, "stages_ms": stages,
             "aligned_utterances": int(ok_total), "utterances": int(utts_total),
-            "k3_band_fallbacks_per_step": fallbacks / max(1, args.steps)}
+            "k3_band_fallbacks_per_step": fallbacks / max(1, args.steps), "per_rank": rank_summary,
+            "per_rank_rows": per_rank if world > 1 else None}
     # ---- training-loop / SAT stages next to the alignment path (config 4 and config 3's fMLLR pass), timed on their own with CUDA
     # events on the engine stream, OUTSIDE the timed alignment step: K4 accumulator statistics and K5 per-speaker fMLLR statistics
     # over the step's device-resident features and alignments.
     # (multi-rank runs skip them unless --extras-dist: a rank failing inside would leave the others waiting in the all-reduce)
-    if not args.no_extras and (world == 1 or args.extras_dist):
+    if not args.no_extras:
+        line["extras"] = {}
+        if world == 1 or args.extras_dist:
+            try:
+                line["extras"].update(train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args))
+            except Exception as ex:
+                line["extras"]["failed"] = repr(ex)
+        # config 4's loop runs at every N: its all-reduce is the one collective of the path (a rank that fails before a collective
+        # tells the others through a MIN all-reduce of an ok flag, so nobody waits forever)
         try:
-            line["extras"] = train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args)
             line["extras"]["train_loop"] = train_loop(eng, sc, d_pcm, dev, stream, dist, args)
         except Exception as ex:
-            line["extras"] = {"failed": repr(ex)}
+            line["extras"]["train_loop"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the reference arm times the CPU path at every N)
         try:
             sc._fsts = sc.batch.export()
             sample_s = args.cpu_sample_seconds or 7200.0
             utts = pick_sample(sc, sample_s)
+            if retried.size and int(retried[0]) not in utts:   # make sure a retry-beam utterance is part of the parity sample
+                utts.append(int(retried[0]))
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 10)], cores)
-            dt, secs, ok = cpu_reference_pass(sc, utts, cores)
+            dt, secs, ok, ref = cpu_reference_pass(sc, utts, cores)
             line["cpu_baseline"] = {"value": secs / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{len(utts)} utterances / {secs:.0f} audio-s of the same workload, {dt:.1f} s wall; oracle port"}
+            line["parity"] = parity_block(sc, utts, ref, gpu_host)
+            line["frame_agreement_pct"] = line["parity"]["frame_agreement_pct"]
         except Exception as ex:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {ex}"}
     if dist is not None:

@@ -60,6 +60,12 @@ MFA_API int mfa_engine_destroy(mfa_engine *e);
 MFA_API int mfa_engine_sync(mfa_engine *e);
 MFA_API void *mfa_engine_stream(mfa_engine *e); /* cudaStream_t, for torch interop */
 MFA_API int mfa_engine_sm_count(mfa_engine *e);
+/* Experiment / test switches of one engine (integers).  Initial values come from the environment variables MFA_<NAME IN UPPER CASE>,
+ * read once inside mfa_engine_create; afterwards only these calls change them.  Names: vit_band, vit_maxgroups, vit_graph_smem,
+ * vit_nw2_kb, vit_carveout, vit_carveout_band, vit_prio (creation time only), pipeline_split, acc_impl, tc_k96 (takes effect when a
+ * model's operand images are built), tc_poly, mfcc_generic, trace.  Unknown names fail with MFA_ERR_INVALID. */
+MFA_API int mfa_engine_set_option(mfa_engine *e, const char *name, int value);
+MFA_API int mfa_engine_get_option(mfa_engine *e, const char *name, int *value);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 MFA_API int64_t mfa_engine_launch_count(mfa_engine *e);
 /* Cumulative number of utterances the band Viterbi kernel handed to the sparse kernel (live window wider than the band). */
@@ -278,7 +284,7 @@ MFA_API int mfa_acc_read(mfa_engine *e, mfa_model *m, double *host_out);
  *      m: the model whose means / variances enter the statistics; both are evaluated on the same `feats`.
  *      tid_weight: host [num_tids+1] frame weight per transition-id (silence_weight for silence phones, else 1; NULL = 1).
  *      stats: [n_spk][mfa_fmllr_stats_size(dim)] f64 = beta | K[D][D+1] | G[D][(D+1)(D+2)/2] (G_d: packed lower triangle,
- *      row-major, Kaldi SpMatrix order).  The transform update from these statistics is host-side (fmllr.py). */
+ *      row-major, Kaldi SpMatrix order).  dim <= 63 (the kernel stages [x | 1] in 64-wide rows).  Transform update: mfa_fmllr_update. */
 MFA_API int64_t mfa_fmllr_stats_size(int32_t dim);
 MFA_API int mfa_fmllr_acc(mfa_engine *e, mfa_model *post_model, mfa_model *m, const float *feats, const int32_t *ali,
                           const float *tid_weight, const int64_t *frame_off, const int32_t *utt2spk, int32_t n_utts,

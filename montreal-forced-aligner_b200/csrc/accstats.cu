@@ -282,10 +282,9 @@ int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const in
   if (!m->d_acc) MFA_TRY(mfa_acc_zero(e, m));
   int max_nm = 1;
   for (int p = 0; p < m->num_pdfs; p++) max_nm = std::max(max_nm, m->h_pdf_off[p + 1] - m->h_pdf_off[p]);
-  const char *impl = getenv("MFA_ACC_IMPL");
   const int DS = m->dim | 1;
   const size_t smem = sizeof(float) * ((size_t)max_nm + 2 * (size_t)max_nm * DS + (size_t)ACC_F * DS + (size_t)ACC_F * max_nm);
-  if ((impl && !strcmp(impl, "atomic")) || smem > e->smem_optin - 1024 || n_frames > (int64_t)0x7fffffff) {
+  if (e->cfg.acc_impl == 1 || smem > e->smem_optin - 1024 || n_frames > (int64_t)0x7fffffff) {
     if (max_nm > MFA_TILE_N || m->dim > 64) return set_error(MFA_ERR_UNSUPPORTED, "acc-stats: pdf with too many components / dim > 64");
     return launch_acc_stats_atomic(e, m, d_feats, d_ali, n_frames);
   }
@@ -303,11 +302,8 @@ int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const in
   acc_hist_kernel<<<grid, 256, 0, e->stream>>>(d_ali, n_frames, NT, m->d_tid2pdf, pdf_count, tid_count);
   acc_scan_kernel<<<1, 1024, 0, e->stream>>>(P, NT, pdf_count, tid_count, pdf_start, cursor, item_off, n_items, trans);
   acc_scatter_kernel<<<grid, 256, 0, e->stream>>>(d_ali, n_frames, NT, m->d_tid2pdf, cursor, order);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(acc_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  // per device / context attribute: set on every launch (several engines on different devices may live in one process)
+  CUDA_TRY(cudaFuncSetAttribute(acc_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (e->smem_optin) / (smem + 2048)));
   // upper bound on the number of items: every pdf may leave one partial item
   const int64_t max_items = n_frames / ACC_F + P;

@@ -25,17 +25,42 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
+// Experiment / test switches.  Read from the environment ONCE, when the engine is created (MFA_<UPPER-CASE NAME>), and changed
+// afterwards only through mfa_engine_set_option; no kernel launcher consults the environment.
+struct mfa_engine_cfg {
+  int vit_band = 1;            // 0: every utterance on the sparse Viterbi kernel
+  int vit_maxgroups = 8;       // band width in groups of 32 states (1..8); tests narrow it to exercise the fallback
+  int vit_graph_smem = 0;      // 1: band kernel copies each graph to shared memory (default: read through L1)
+  int vit_nw2_kb = -1;         // size classes up to this many KB of shared memory run 2 warps per utterance (-1: 20, or 44 with graph_smem)
+  int vit_carveout = 100;      // shared-memory carve-out (percent) of the sparse kernel
+  int vit_carveout_band = -1;  // ... of the band kernel (-1: 70, or 100 with graph_smem)
+  int vit_prio = 1;            // side-stream priorities rise with the size class (creation time only)
+  int pipeline_split = -1;     // host-PCM path: -1 auto, 0 whole, 1 every stage per segment, 2 stream (K1..K2 per segment, one K3)
+  int acc_impl = 0;            // K4: 0 counting sort + register accumulation, 1 first version (f64 atomics)
+  int tc_k96 = 0;              // K2: 1 forces the K = 96 operand geometry
+  int tc_poly = -1;            // K2 epilogue: groups (of 8 per 32-column chunk) whose exp2 runs as an FMA polynomial (-1: default)
+  int mfcc_generic = 0;        // K1: 1 forces the generic (shared-memory FFT) kernel
+  int trace = 0;               // print host enqueue times per stage
+};
+
 struct mfa_engine {
+  mfa_engine_cfg cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
-  int64_t band_fallbacks = 0;          // utterances the band Viterbi kernel handed to the sparse kernel (cumulative)
+  int64_t band_fallbacks = 0;          // utterances the band Viterbi kernel handed to the sparse kernel (cumulative, harvested counts)
+  // every Viterbi launch's fallback count lands in its own slot of a pinned, device-mapped ring (written by viterbi_fallback_kernel);
+  // the slots are summed into band_fallbacks whenever the stream has been synchronised anyway -- never inside a step
+  static constexpr int kFbRing = 256;
+  int32_t *h_fb_ring = nullptr;
+  int fb_pending = 0;
+  void harvest_fallbacks() { for (int i = 0; i < fb_pending; i++) band_fallbacks += h_fb_ring[i]; fb_pending = 0; }
   // K2 timing: event pairs recorded around each K2 launch of the current API call
   std::vector<cudaEvent_t> gmm_ev;
   int gmm_ev_used = 0;
@@ -178,7 +203,6 @@ struct ViterbiArgs {
   mfa_align_opts opts;
 };
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
-bool viterbi_band_graph_in_smem();                            // MFA_VIT_GRAPH_SMEM=1: copy each graph to shared memory (default: read it through L1)
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem);   // shared memory the band kernel needs for one utterance
 int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);

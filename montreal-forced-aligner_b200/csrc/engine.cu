@@ -1,5 +1,6 @@
 // engine.cu -- engine lifetime, workspaces, acoustic-model upload/tiling, graph upload.
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -42,6 +43,29 @@ int mfa_engine::get_pinned(int id, size_t bytes, void **out) {
   return MFA_OK;
 }
 
+namespace {
+struct OptionDesc { const char *name; int mfa_engine_cfg::*field; };
+const OptionDesc kOptions[] = {
+    {"vit_band", &mfa_engine_cfg::vit_band}, {"vit_maxgroups", &mfa_engine_cfg::vit_maxgroups}, {"vit_graph_smem", &mfa_engine_cfg::vit_graph_smem},
+    {"vit_nw2_kb", &mfa_engine_cfg::vit_nw2_kb}, {"vit_carveout", &mfa_engine_cfg::vit_carveout}, {"vit_carveout_band", &mfa_engine_cfg::vit_carveout_band},
+    {"vit_prio", &mfa_engine_cfg::vit_prio}, {"pipeline_split", &mfa_engine_cfg::pipeline_split}, {"acc_impl", &mfa_engine_cfg::acc_impl},
+    {"tc_k96", &mfa_engine_cfg::tc_k96}, {"tc_poly", &mfa_engine_cfg::tc_poly}, {"mfcc_generic", &mfa_engine_cfg::mfcc_generic},
+    {"trace", &mfa_engine_cfg::trace}};
+}  // namespace
+
+extern "C" int mfa_engine_set_option(mfa_engine *e, const char *name, int value) {
+  if (!e || !name) return set_error(MFA_ERR_INVALID, "null argument");
+  for (const auto &o : kOptions)
+    if (!strcmp(o.name, name)) { e->cfg.*(o.field) = value; return MFA_OK; }
+  return set_error(MFA_ERR_INVALID, std::string("unknown engine option '") + name + "'");
+}
+extern "C" int mfa_engine_get_option(mfa_engine *e, const char *name, int *value) {
+  if (!e || !name || !value) return set_error(MFA_ERR_INVALID, "null argument");
+  for (const auto &o : kOptions)
+    if (!strcmp(o.name, name)) { *value = e->cfg.*(o.field); return MFA_OK; }
+  return set_error(MFA_ERR_INVALID, std::string("unknown engine option '") + name + "'");
+}
+
 extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   if (!out) return set_error(MFA_ERR_INVALID, "null out");
   int n = 0;
@@ -54,6 +78,11 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return set_error(MFA_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this build targets sm_100a (B200) only");
   auto *e = new mfa_engine();
+  for (const auto &o : kOptions) {   // the one place the environment is consulted
+    std::string name = "MFA_";
+    for (const char *c = o.name; *c; c++) name += (char)toupper((unsigned char)*c);
+    if (const char *v = getenv(name.c_str())) e->cfg.*(o.field) = atoi(v);
+  }
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
@@ -62,14 +91,15 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   // so they get the higher stream priorities and their CTAs are placed first (MFA_VIT_PRIO=0: all equal)
   int prio_least = 0, prio_greatest = 0;
   CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-  const char *pv = getenv("MFA_VIT_PRIO");
-  const bool use_prio = !(pv && atoi(pv) == 0);
+  const bool use_prio = e->cfg.vit_prio != 0;
   for (int k = 0; k < mfa_engine::kSide; k++) {
     const int prio = use_prio ? std::max(prio_greatest, prio_least - k) : prio_least;
     CUDA_TRY(cudaStreamCreateWithPriority(&e->side[k], cudaStreamNonBlocking, prio));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, mfa_engine::kFbRing * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(e->h_fb_ring, 0, mfa_engine::kFbRing * sizeof(int32_t));
   for (int k = 0; k < 2; k++) {
     CUDA_TRY(cudaMallocHost(&e->stage_mem[k], mfa_engine::kStageBytes));
     CUDA_TRY(cudaEventCreateWithFlags(&e->stage_ev[k], cudaEventDisableTiming));
@@ -89,6 +119,7 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto ev : e->st_ev) cudaEventDestroy(ev);
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->h_fb_ring) cudaFreeHost(e->h_fb_ring);
   for (int k = 0; k < 2; k++) { if (e->stage_mem[k]) cudaFreeHost(e->stage_mem[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }
   cudaStreamDestroy(e->stream);
   delete e;
@@ -99,12 +130,17 @@ extern "C" int mfa_engine_sync(mfa_engine *e) {
   if (!e) return set_error(MFA_ERR_INVALID, "null engine");
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   CUDA_TRY(cudaGetLastError());
+  e->harvest_fallbacks();
   return MFA_OK;
 }
 extern "C" void *mfa_engine_stream(mfa_engine *e) { return e ? (void *)e->stream : nullptr; }
 extern "C" int mfa_engine_sm_count(mfa_engine *e) { return e ? e->sm_count : 0; }
 extern "C" int64_t mfa_engine_launch_count(mfa_engine *e) { return e ? e->launches : 0; }
-extern "C" int64_t mfa_engine_band_fallbacks(mfa_engine *e) { return e ? e->band_fallbacks : 0; }
+extern "C" int64_t mfa_engine_band_fallbacks(mfa_engine *e) {
+  if (!e) return 0;
+  if (e->fb_pending) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); e->harvest_fallbacks(); }   // counts of launches still in flight
+  return e->band_fallbacks;
+}
 namespace {
 __global__ void stage_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -157,7 +193,7 @@ extern "C" int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_
 }
 
 int mfa_engine::stage_begin(int stage) {
-  if (getenv("MFA_TRACE")) {
+  if (cfg.trace) {
     static thread_local std::chrono::steady_clock::time_point t0;
     auto now = std::chrono::steady_clock::now();
     if (st_stage.empty()) t0 = now;

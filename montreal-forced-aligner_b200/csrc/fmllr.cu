@@ -424,7 +424,8 @@ int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d
   const int dim = ms->dim;
   if (mp->dim != dim || mp->num_gauss != ms->num_gauss || mp->num_pdfs != ms->num_pdfs || mp->h_pdf_off != ms->h_pdf_off)
     return set_error(MFA_ERR_INVALID, "fMLLR: the posterior model and the statistics model must share one Gaussian layout");
-  if (dim > 64) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: dim > 64");
+  // the accumulation kernel stages [x | 1] in 64-wide rows: the bias column needs a free slot, so dim 64 is out
+  if (dim > 63) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: dim > 63");
   for (int p = 0; p < ms->num_pdfs; p++)
     if (ms->h_pdf_off[p + 1] - ms->h_pdf_off[p] > MFA_TILE_N) return set_error(MFA_ERR_UNSUPPORTED, "fMLLR: pdf with more than 128 components");
   const int64_t n_frames = h_frame_off[n_utts];

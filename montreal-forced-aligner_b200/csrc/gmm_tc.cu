@@ -35,7 +35,7 @@ namespace {
 
 constexpr int TM = 128, TN = MFA_TILE_N;
 // Two geometries.  K = 80 (2 dim <= 80; MFA's 39 / 40-dimensional features): the gconst is added by the epilogue from a per-tile fp32
-// array, 5 k-steps x 3 products = 15 MMAs per tile, 40 KB tiles, a THREE-stage B ring.  K = 96 (2 dim + 3 <= 96, or MFA_TC_K96=1): the
+// array, 5 k-steps x 3 products = 15 MMAs per tile, 40 KB tiles, a THREE-stage B ring.  K = 96 (2 dim + 3 <= 96, or engine option tc_k96): the
 // gconst rides as three fp16 columns against ones, 18 MMAs per tile, 48 KB tiles, two-stage ring (the first version of this kernel).
 __host__ __device__ constexpr uint32_t img_bytes(int tk) { return (uint32_t)(TM * tk * 2); }   // one fp16 image (hi or lo) of a 128 x tk tile
 __host__ __device__ constexpr uint32_t tile_bytes(int tk) { return 2 * img_bytes(tk); }         // hi + lo
@@ -61,14 +61,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) expires, so the loop
+// below turns over a few times per wait at most.  The poll counter is the hang guard (a protocol bug must trap, not hang the GPU):
+// one integer add per failed poll, no clock reads on the hot path.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), done = 0;
-  long long t0 = clock64();
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, polls = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity), "r"(0x100000u) : "memory");
     if (done) break;
-    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s: a protocol bug must not hang the GPU
+    if (++polls > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -173,8 +176,6 @@ struct TcParams {
   const TcItem *items;    // [n_items]
   int n_items;
   float *out;             // pdf-major blocks: out[item.out_off + (meta.pdf0 + k) * item.ld + frame]
-  int no_epilogue;        // MFA_TC_NOEPI=1 (experiment): epilogue warps release the accumulators without reading them
-  long long *dbg;         // optional [grid][4]: cycles the MMA issuer waited on full_a, full_b, tempty, and its whole loop (MFA_TC_DEBUG=1)
 };
 
 template <int TKt, int NBt, bool GEPI>
@@ -247,26 +248,17 @@ gmm_tc_kernel(TcParams p) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t cnt = 0, it = 0, sb = 0, phb = 0;
-      long long w_a = 0, w_b = 0, w_t = 0;
-      const bool dbg = p.dbg != nullptr;
-      const long long t_begin = clock64();
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         const uint32_t n_b = p.items[item].n_b, rows_valid = p.items[item].rows_valid;
-        long long c0 = dbg ? clock64() : 0;
         mbar_wait(full_a, it & 1);
-        if (dbg) w_a += clock64() - c0;
         tc_fence_after();
         for (uint32_t n = 0; n < n_b; n++, cnt++) {
           const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
-          c0 = dbg ? clock64() : 0;
           mbar_wait(full_b + sb, phb);
-          if (dbg) w_b += clock64() - c0;
           tc_fence_after();
 #pragma unroll
           for (int f = 0; f < 2; f++) {
-            c0 = dbg ? clock64() : 0;
             mbar_wait(tempty + s * 2 + f, ph ^ 1);
-            if (dbg) w_t += clock64() - c0;
             tc_fence_after();
             if (f == 0 || rows_valid > TM) {   // a pair whose second tile holds no frames skips its 18 MMAs
               const uint32_t d = tmem_base + s * 256 + f * 128;
@@ -286,7 +278,6 @@ gmm_tc_kernel(TcParams p) {
         }
         umma_commit(empty_a);
       }
-      if (dbg) { long long *o = p.dbg + 4 * blockIdx.x; o[0] += w_a; o[1] += w_b; o[2] += w_t; o[3] += clock64() - t_begin; }
     }
   } else if (warp >= 4) {
     // ===== epilogue: 16 warps = 2 accumulator stages x 2 frame tiles x 4 lane quarters; thread = one frame (TMEM lane).
@@ -308,7 +299,7 @@ gmm_tc_kernel(TcParams p) {
         mbar_wait(tfull + s * 2 + f, ph);
         tc_fence_after();
         if (GEPI) mbar_wait(gfull + s, ph);
-        if (!tile_live || p.no_epilogue) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); if (GEPI) mbar_arrive(gempty + s); continue; }
+        if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); if (GEPI) mbar_arrive(gempty + s); continue; }
         const float *gs = sG + s * TN;
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         float cmx = -INFINITY, cs = 0.0f;
@@ -403,35 +394,13 @@ gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int3
   for (int c = t; c < TN * KC; c += 256) dst[c] = s_img[(c >> 7) * (TN + 1) + (c & (TN - 1))];
 }
 
-// MFA_TC_DEBUG=1: a device buffer [1024][4] of cycle counters filled by the MMA issuer threads; printed (and cleared) by tc_debug_dump
-static long long *g_tc_dbg = nullptr;
-static long long *tc_debug_buffer(mfa_engine *e) {
-  static int on = -1;
-  if (on < 0) { const char *v = getenv("MFA_TC_DEBUG"); on = v && atoi(v) ? 1 : 0; }
-  if (!on) return nullptr;
-  if (!g_tc_dbg) { if (cudaMalloc((void **)&g_tc_dbg, 1024 * 4 * sizeof(long long)) != cudaSuccess) return nullptr; cudaMemset(g_tc_dbg, 0, 1024 * 4 * sizeof(long long)); }
-  (void)e;
-  return g_tc_dbg;
-}
-static void tc_debug_dump(mfa_engine *e, int grid) {
-  if (!g_tc_dbg) return;
-  cudaStreamSynchronize(e->stream);
-  std::vector<long long> h(1024 * 4);
-  cudaMemcpy(h.data(), g_tc_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemset(g_tc_dbg, 0, h.size() * sizeof(long long));
-  double a = 0, b = 0, t = 0, tot = 0;
-  for (int i = 0; i < grid && i < 1024; i++) { a += h[4 * i]; b += h[4 * i + 1]; t += h[4 * i + 2]; tot += h[4 * i + 3]; }
-  if (tot > 0) fprintf(stderr, "[tc-debug] MMA issuer: wait full_a %.1f%%  full_b %.1f%%  tempty %.1f%%  of %.0f cycles per CTA\n", 100 * a / tot, 100 * b / tot, 100 * t / tot, tot / grid);
-}
-
 // the dense per-tile gconst array follows the per-Gaussian one; bulk copies need a 16-byte aligned source
 static inline size_t tc_gpad(int64_t G) { return (size_t)((G + 3) & ~(int64_t)3); }
 
 // host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
 int build_tc(mfa_model *m) {
   const int D = m->dim;
-  const char *force96 = getenv("MFA_TC_K96");
-  const bool k80 = 2 * D <= 80 && !(force96 && atoi(force96));
+  const bool k80 = 2 * D <= 80 && !m->eng->cfg.tc_k96;
   if (!k80 && 2 * D + 3 > 96) return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96");
   const int TK = k80 ? 80 : 96, KC = TK / 8;
   const uint32_t TILE_BYTES = tile_bytes(TK);
@@ -535,7 +504,6 @@ int launch_tc(mfa_engine *e, const TcParams &p, int tk) {
     CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<96, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_tc_kernel<96, 2, false><<<grid, NTHREADS, smem, e->stream>>>(p);
   }
-  if (p.dbg) tc_debug_dump(e, grid);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MFA_OK;
@@ -585,8 +553,6 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   TcItem *d_items;
   MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
   TcParams p;
-  p.dbg = tc_debug_buffer(e);
-  { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
   p.g_tiles = m->d_tc_g + tc_gpad(m->num_gauss);
@@ -696,8 +662,6 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
                                                                            TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g, TK == 80 ? d_gt : nullptr);
   e->launches++;
   TcParams p;
-  p.dbg = tc_debug_buffer(e);
-  { static int ne = -1; if (ne < 0) { const char *v = getenv("MFA_TC_NOEPI"); ne = v && atoi(v) ? 1 : 0; } p.no_epilogue = ne; }
   p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
   p.g_tiles = d_gt;
   return launch_tc(e, p, TK);

@@ -687,8 +687,8 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     if (!P.ok) { P.bo.stw.assign(S, 0); P.bo.fin.assign(S, 0.0f); P.bo.orig.assign(S, 0); P.bo.apk.assign(A, 0); P.bo.aw.assign(A, 0.0f); P.bo.arcid.assign(A, 0); }
   };
   {
-    const char *ev = getenv("MFA_PACK_THREADS");
-    int nt = ev ? atoi(ev) : (int)std::thread::hardware_concurrency();
+    static const int env_nt = [] { const char *ev = getenv("MFA_PACK_THREADS"); return ev ? atoi(ev) : 0; }();   // read once per process
+    int nt = env_nt > 0 ? env_nt : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min(nt, std::min(32, n)));
     std::atomic<int> next{0};
     auto loop = [&]() { std::vector<int32_t> lpmap; for (int u = next.fetch_add(1); u < n; u = next.fetch_add(1)) work(u, lpmap); };

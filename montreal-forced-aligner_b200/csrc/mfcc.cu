@@ -572,7 +572,7 @@ int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, con
     CUDA_TRY(cudaStreamSynchronize(e->stream));  // blob is a local
     memcpy(e->mfcc_tab_desc, &t, sizeof(t)); e->mfcc_tab_opts = *o; e->mfcc_tab_valid = true;
   }
-  const bool fast = t.fast && !(getenv("MFA_MFCC_GENERIC") && atoi(getenv("MFA_MFCC_GENERIC")));
+  const bool fast = t.fast && !e->cfg.mfcc_generic;
   if (fast) {
     const size_t smem = (size_t)(3 * 8 * 32 * 2 + ((t.total + 3) & ~3) + kFW * kWarpFloats) * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(mfcc512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -301,17 +301,17 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
     else { MFA_TRY(e->getT<double>(DB_CMVN_STATS, nst, &d_stats)); CUDA_TRY(cudaMemsetAsync(d_stats, 0, nst * sizeof(double), e->stream)); }
   }
   std::vector<int> seg_begin{0};
-  // Two ways to use the cuts (MFA_PIPELINE_SPLIT): 2 (default for host PCM when the batch fits one chunk) = STREAM: MFCC, CMVN,
+  // Two ways to use the cuts (engine option pipeline_split): 2 (default for host PCM when the batch fits one chunk) = STREAM: MFCC, CMVN,
   // features and log-likelihoods run per segment as its bytes arrive, the Viterbi stage runs once over the whole batch at the
   // end -- it is bounded by its longest utterance's sequential recursion, not by throughput, so it must not be cut;
   // 1 = every stage per segment (measured on the 10 h config-2 workload: end to end 45 -> 55 ms, two Viterbi tails); 0 = no cuts.
-  const char *env_split = getenv("MFA_PIPELINE_SPLIT");
-  const int split_mode = env_split ? atoi(env_split) : 2;
+  const bool split_forced = e->cfg.pipeline_split >= 0;
+  const int split_mode = split_forced ? e->cfg.pipeline_split : 2;
   const int64_t budget = o->workspace_bytes > 0 ? o->workspace_bytes : ((int64_t)8 << 30);
   const bool ragged = o->gmm_impl == 0 && gmm_tc_supported(m);
   std::vector<ChunkPlan> whole;
   bool stream = false;
-  if (where == MFA_HOST && split_mode == 2 && (getenv("MFA_PIPELINE_SPLIT") || (n_utts >= 64 && ns >= ((int64_t)64 << 20)))) {
+  if (where == MFA_HOST && split_mode == 2 && (split_forced || (n_utts >= 64 && ns >= ((int64_t)64 << 20)))) {
     MFA_TRY(plan_chunks(g, frame_off, n_utts, P, D, budget, whole, ragged));
     stream = whole.size() == 1 && ragged;   // (dense scoring keeps the chunk loop: its tiles want 128-column alignment)
   }

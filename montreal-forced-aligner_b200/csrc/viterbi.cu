@@ -72,16 +72,14 @@ __device__ __forceinline__ uint32_t f2key(float f) { uint32_t u = __float_as_uin
 __device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 constexpr unsigned long long kEmpty = ~0ull;
 
-__global__ void __launch_bounds__(VT, 16)
-viterbi_kernel(VitParams p) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+// one utterance (chunk-local id `ul`) on the calling warp; `bp` = its back-pointer rows
+__device__ __forceinline__ void viterbi_utt(const VitParams &p, const int ul, uint16_t *const bp, unsigned char *smraw) {
   __shared__ int sh_cnt, sh_nnext, sh_best_state, sh_bin, sh_rank, sh_head;
   __shared__ float sh_sel;
   __shared__ int sh_hist[128];
   __shared__ float sh_cand[64];
 
   const int tid = threadIdx.x, warp = 0, lane = tid;
-  const int ul = p.order[blockIdx.x];
   const int ug = p.utt0 + ul;
   const int S = (int)(p.st_off[ug + 1] - p.st_off[ug]);
   const int P = (int)(p.lp_off[ug + 1] - p.lp_off[ug]);
@@ -101,7 +99,6 @@ viterbi_kernel(VitParams p) {
   const float *aw = p.a_w + p.arc_off[ug];
   const float *fin = p.final_w + p.st_off[ug];
   const int32_t *lp2pdf = p.lp2pdf + p.lp_off[ug];
-  uint16_t *bp = p.bp + p.bp_off[ul];           // rows 0..T-1 (+ row T: initial epsilon closure)
   const bool rag = p.ll_off != nullptr;
   const float *ll = p.llT + (rag ? p.ll_off[ul] : p.col_off[ul]);
   const int64_t ldu = rag ? p.ld_u[ul] : p.ld;
@@ -539,9 +536,50 @@ viterbi_kernel(VitParams p) {
   p.num_words[ul] = nw;
 }
 
+__global__ void __launch_bounds__(VT, 16)
+viterbi_kernel(VitParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int ul = p.order[blockIdx.x];
+  viterbi_utt(p, ul, p.bp + p.bp_off[ul], smraw);   // rows 0..T-1 (+ row T: initial epsilon closure)
+}
+
+// Fallback pass behind the band kernel: `fb` = {count, utterance ids ...} was filled on the device by the band kernel for utterances
+// whose live window outgrew the band.  Always launched with a small fixed grid -- the count is read HERE, on the device, so the host
+// never synchronises inside a step; each CTA owns one back-pointer slab and walks the list with a grid stride.  The count is also
+// stored to a host-mapped slot so that mfa_engine_band_fallbacks can report it later.
+__global__ void __launch_bounds__(VT, 16)
+viterbi_fallback_kernel(VitParams p, const int32_t *__restrict__ fb, int64_t slab, const unsigned char *__restrict__ too_big, int32_t *h_count) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int n = fb[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *(volatile int32_t *)h_count = n; __threadfence_system(); }
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int ul = fb[1 + i];
+    if (too_big[ul]) {   // graph beyond the sparse kernel's shared memory: cannot be retried (reported as a failed alignment)
+      if (threadIdx.x == 0) { p.status[ul] = MFA_ALIGN_NO_FINAL; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; }
+    } else {
+      viterbi_utt(p, ul, p.bp + (size_t)blockIdx.x * slab, smraw);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 namespace mfa {
+
+static VitParams sparse_params(const ViterbiArgs &a) {
+  const mfa_graphs *g = a.g;
+  VitParams p{};
+  p.st_off = g->d_st_off; p.arc_off = g->d_arc_off; p.lp_off = g->d_lp_off; p.inb_off = g->d_inb_off;
+  p.start = g->d_start; p.n_eps = g->d_n_eps; p.in_begin = g->d_in_begin; p.a_tid = g->d_a_tid; p.a_olabel = g->d_a_olabel; p.lp2pdf = g->d_lp2pdf;
+  p.a_src = g->d_a_src; p.a_pack = g->d_a_pack; p.a_w = g->d_a_w; p.final_w = g->d_final_w;
+  p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
+  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.per_frame = a.d_per_frame;
+  p.total_like = a.d_total_like;
+  p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u;
+  p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta; p.min_active = a.opts.min_active;
+  return p;
+}
 
 // Sparse kernel over the utterances in `subset` (chunk-local ids).
 static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset) {
@@ -578,21 +616,13 @@ static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std:
   std::vector<int32_t> order(subset);
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cls[x] != cls[y] ? cls[x] < cls[y] : work[x] > work[y]; });
   MFA_TRY(e->upload(DB_UTT_ORDER, order.data(), order.size(), &d_order));
-  VitParams p;
-  p.st_off = g->d_st_off; p.arc_off = g->d_arc_off; p.lp_off = g->d_lp_off; p.inb_off = g->d_inb_off;
-  p.start = g->d_start; p.n_eps = g->d_n_eps; p.in_begin = g->d_in_begin; p.a_tid = g->d_a_tid; p.a_olabel = g->d_a_olabel; p.lp2pdf = g->d_lp2pdf;
-  p.a_src = g->d_a_src; p.a_pack = g->d_a_pack; p.a_w = g->d_a_w; p.final_w = g->d_final_w;
-  p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.bp_off = d_bp_off; p.word_off = a.d_word_off;
-  p.bp = d_bp; p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.per_frame = a.d_per_frame;
-  p.total_like = a.d_total_like;
-  p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u;
-  p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta; p.min_active = a.opts.min_active;
+  VitParams p = sparse_params(a);
+  p.bp_off = d_bp_off; p.bp = d_bp;
   CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   {
     // split of the unified L1/shared array (percent shared): the arcs of the live tokens are re-read every frame through L1/L2
     // measured (10 h config-2 workload): 100 -> 60.1 ms/step, 75 -> 60.8, 50 -> 69.9, 25 -> 112.4: resident warps matter more than L1
-    static int carve = getenv("MFA_VIT_CARVEOUT") ? atoi(getenv("MFA_VIT_CARVEOUT")) : 100;
-    CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    CUDA_TRY(cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, e->cfg.vit_carveout));
   }
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
   // largest-need classes first: they hold the biggest graphs; the small ones fill in around them on the side streams
@@ -617,8 +647,9 @@ static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std:
 
 // K3 dispatch: graphs with a band view run on the band kernel (viterbi_band.cu); graphs without one (input-epsilon arcs, very
 // high in-degree) run on the sparse kernel, and so does any utterance whose live window outgrew the band at run time -- the
-// band kernel lists those, the host reads the (almost always zero) count back and re-launches them.
-// MFA_VIT_BAND=0 forces the sparse kernel; MFA_VIT_MAXGROUPS=k (1..8) narrows the band (tests use it to exercise the fallback).
+// band kernel lists those on the device and a small fallback launch, always enqueued, walks that list (usually empty) without the
+// host ever reading the count inside the step.
+// Engine option vit_band = 0 forces the sparse kernel; vit_maxgroups = k (1..8) narrows the band (tests use it to exercise the fallback).
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   const mfa_graphs *g = a.g;
   const int n = a.n_utts;
@@ -631,16 +662,15 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
       if (a.h_col_off[u] + ((T + 3) / 4) * 4 > a.ld) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension too small for 4-frame blocks");
     }
   }
-  const char *env_band = getenv("MFA_VIT_BAND"), *env_mg = getenv("MFA_VIT_MAXGROUPS");
-  const bool use_band = !(env_band && atoi(env_band) == 0);
-  const int max_groups = env_mg ? atoi(env_mg) : 8;
+  const bool use_band = e->cfg.vit_band != 0;
+  const int max_groups = e->cfg.vit_maxgroups;
   std::vector<int32_t> band, sparse;
   for (int u = 0; u < n; u++) {
     const int ug = a.utt0 + u;
     bool ok = use_band && g->band_ok[ug];
     if (ok) {
       const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
-      ok = viterbi_band_smem(S, A, P, viterbi_band_graph_in_smem()) <= e->smem_optin - 4096;
+      ok = viterbi_band_smem(S, A, P, e->cfg.vit_graph_smem != 0) <= e->smem_optin - 4096;
     }
     (ok ? band : sparse).push_back(u);
   }
@@ -651,19 +681,32 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   }
   MFA_TRY(launch_viterbi_sparse(e, a, sparse));
   if (!band.empty()) {
-    int32_t *h_fb;
-    { void *pp; MFA_TRY(e->get_pinned(PB_E, ((size_t)n + 1) * sizeof(int32_t), &pp)); h_fb = (int32_t *)pp; }
-    CUDA_TRY(cudaMemcpyAsync(h_fb, d_fb, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-    const int nfb = h_fb[0];
-    e->band_fallbacks += nfb;
-    if (nfb > 0) {
-      CUDA_TRY(cudaMemcpyAsync(h_fb + 1, d_fb + 1, (size_t)nfb * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-      CUDA_TRY(cudaStreamSynchronize(e->stream));
-      std::vector<int32_t> again(h_fb + 1, h_fb + 1 + nfb);
-      std::sort(again.begin(), again.end());
-      MFA_TRY(launch_viterbi_sparse(e, a, again));
+    // fallback pass over the device-side list (no host read of the count: see viterbi_fallback_kernel)
+    constexpr int kFbCtas = 16;
+    const size_t limit = e->smem_optin - 2048;
+    std::vector<unsigned char> too_big(n, 0);
+    size_t smem = 0; int64_t slab = 0;
+    for (int u : band) {
+      const int ug = a.utt0 + u;
+      const int64_t S = g->st_off[ug + 1] - g->st_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug], T = a.h_frame_off[u + 1] - a.h_frame_off[u];
+      const size_t need = (size_t)S * 12 + (size_t)P * 16 + (size_t)((S + 1) & ~1) * 4 + 16;
+      if (need > limit) { too_big[u] = 1; continue; }
+      smem = std::max(smem, need); slab = std::max(slab, (T + 1) * S);
     }
+    slab = (slab + 7) & ~(int64_t)7;
+    const int ctas = (int)std::min<size_t>(kFbCtas, band.size());
+    uint16_t *d_bp; unsigned char *d_big;
+    MFA_TRY(e->getT<uint16_t>(DB_FB_BP, (size_t)slab * ctas + 8, &d_bp));
+    MFA_TRY(e->upload(DB_FB_BIG, too_big.data(), too_big.size(), &d_big));
+    if (e->fb_pending == mfa_engine::kFbRing) { CUDA_TRY(cudaStreamSynchronize(e->stream)); e->harvest_fallbacks(); }
+    VitParams p = sparse_params(a);
+    p.bp = d_bp;
+    smem = (smem + 15) / 16 * 16;
+    CUDA_TRY(cudaFuncSetAttribute(viterbi_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+    viterbi_fallback_kernel<<<ctas, VT, smem, e->stream>>>(p, d_fb, slab, d_big, e->h_fb_ring + e->fb_pending);
+    e->fb_pending++;
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
   }
   return MFA_OK;
 }

@@ -473,8 +473,6 @@ viterbi_band_kernel(BandParams p) {
 
 namespace mfa {
 
-bool viterbi_band_graph_in_smem() { const char *v = getenv("MFA_VIT_GRAPH_SMEM"); return v ? atoi(v) != 0 : false; }
-
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem) {
   const int64_t graph = graph_in_smem ? ((((S + 32) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 : 0;
   return (size_t)(graph + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, 2 * BT_ROWS * ROWB + 4 * BT_ROWS) + 16);
@@ -488,7 +486,7 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   CUDA_TRY(cudaMemsetAsync(d_fallback, 0, sizeof(int32_t), e->stream));
   if (ns == 0) return MFA_OK;
   const size_t limit = e->smem_optin - 4096;   // the kernel also has ~2 KB of static shared memory
-  const bool graph_smem = viterbi_band_graph_in_smem();
+  const bool graph_smem = e->cfg.vit_graph_smem != 0;
   std::vector<int64_t> bp_off(n + 1, 0);
   std::vector<size_t> need(n, 0);
   std::vector<int64_t> work(n, 0);
@@ -527,21 +525,20 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GMAX));
   // shared-memory share of the unified L1 (percent).  Graph through L1, 10 h workload: 25 -> 16.8 ms, 50 -> 9.4, 65 -> 7.6, 75 -> 7.6,
   // 88 -> 8.8, 100 -> 10.5: enough shared memory for ~9 resident utterances per SM, the rest as L1 for their graph windows
-  const int carve = getenv("MFA_VIT_CARVEOUT_BAND") ? atoi(getenv("MFA_VIT_CARVEOUT_BAND")) : (graph_smem ? 100 : 70);
+  const int carve = e->cfg.vit_carveout_band >= 0 ? e->cfg.vit_carveout_band : (graph_smem ? 100 : 70);
   for (auto fn : {(const void *)viterbi_band_kernel<4, true>, (const void *)viterbi_band_kernel<2, true>, (const void *)viterbi_band_kernel<4, false>,
                   (const void *)viterbi_band_kernel<2, false>}) {
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
   // two-warp CTAs where many utterances share an SM, four-warp CTAs for the size classes above a shared-memory threshold
-  // (MFA_VIT_NW2_KB overrides it): 44 KB when the graph is copied to shared memory; 20 KB when it is read through L1 -- a CTA then needs
+  // (engine option vit_nw2_kb overrides it): 44 KB when the graph is copied to shared memory; 20 KB when it is read through L1 -- a CTA then needs
   // ~15 KB + 32 B per pdf of its graph, so the classes above 20 KB are the longest utterances, the ones on the launch's critical path,
   // and four warps shorten their per-frame chain while the bulk keeps the residency of two-warp CTAs.  Measured on the 10 h config-2
   // workload, graph through L1 (three boxes): all classes 2 warps 9.4-9.6 ms, all 4 warps 10.0 ms, threshold 20 KB 8.2-8.45 ms
   // (19 KB 8.15, 21 KB 9.5-9.6, 22 KB 8.2-9.3: the launch is bounded by a handful of utterances, so neighbouring thresholds scatter);
   // graph in shared memory: 11.7 ms.
-  const char *env_nw = getenv("MFA_VIT_NW2_KB");
-  const size_t nw2_below = (size_t)(env_nw ? atoi(env_nw) : (graph_smem ? 44 : 20)) * 1024;
+  const size_t nw2_below = (size_t)(e->cfg.vit_nw2_kb >= 0 ? e->cfg.vit_nw2_kb : (graph_smem ? 44 : 20)) * 1024;
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));
   for (int c = NC - 1; c >= 0; c--) {
     int pos = 0, cnt = 0;

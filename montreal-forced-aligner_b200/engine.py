@@ -106,6 +106,32 @@ class Engine:
     def sm_count(self) -> int:
         return int(L.lib().mfa_engine_sm_count(self._h))
 
+    def set_option(self, name: str, value: int):
+        """mfa_engine_set_option: experiment / test switches (see include/mfa_b200.h); the environment is only read at creation."""
+        L.check(L.lib().mfa_engine_set_option(self._h, name.encode(), C.c_int(int(value))))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        L.check(L.lib().mfa_engine_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def options(self, **kw):
+        """Context manager: set the given options, restore the previous values on exit."""
+        eng = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.old = {k: eng.get_option(k) for k in kw}
+                for k, v in kw.items():
+                    eng.set_option(k, v)
+                return eng
+
+            def __exit__(self, *a):
+                for k, v in self.old.items():
+                    eng.set_option(k, v)
+                return False
+        return _Ctx()
+
     @property
     def launch_count(self) -> int:
         return int(L.lib().mfa_engine_launch_count(self._h))

@@ -127,6 +127,7 @@ class FmllrComputer:
         sil = np.isin(tm.tid2phone, np.asarray(self.silence_phones, tm.tid2phone.dtype))
         self.tid_weight = np.where(sil, np.float32(silence_weight), np.float32(1.0)).astype(np.float32)
         self.tid_weight[0] = 0.0
+        self.num_error = 0   # utterances skipped because the alignment length differs from the frame count
 
     def compute_stats(self, feats, ali, frame_off, utt2spk, n_spk: int):
         return self._dm.fmllr_acc(feats, ali, frame_off, utt2spk, n_spk, tid_weight=self.tid_weight, post_model=self._dm_post)
@@ -158,8 +159,10 @@ class FmllrComputer:
             feats, fo = feature_archive.batch([k for k, _ in keys])
             ali = np.zeros(int(fo[-1]), np.int32)
             for j, (_, a) in enumerate(keys):
-                n = min(len(a), int(fo[j + 1] - fo[j]))
-                ali[fo[j]:fo[j] + n] = a[:n]
+                if len(a) != int(fo[j + 1] - fo[j]):   # gmm-est-fmllr skips utterances whose alignment length is wrong
+                    self.num_error += 1
+                    continue                           # transition-id 0 = frame ignored by the kernel
+                ali[fo[j]:fo[j + 1]] = a
             stats = self.compute_stats(np.ascontiguousarray(feats, np.float32), ali, fo, np.asarray(u2s, np.int32), len(group))
             W, impr, count = self.compute_transforms(stats)
             for j, s in enumerate(group):

@@ -85,8 +85,8 @@ def mle_update(am: AmDiagGmm, acc: AccumAmDiagGmm, mixup: int = 0, power: float 
     if remove_low_count_gaussians:
         keep = upd.copy()
         none = np.add.reduceat(keep.astype(np.int64), off[:-1]) == 0
-        for j in np.nonzero(none)[0]:   # Kaldi refuses to remove the last Gaussian of a pdf: the heaviest one stays (un-updated)
-            keep[off[j] + int(np.argmax(occ[off[j]:off[j + 1]]))] = True
+        for j in np.nonzero(none)[0]:   # MleDiagGmmUpdate walks the components in order and refuses to remove the only one left:
+            keep[off[j + 1] - 1] = True   # the LAST index survives (un-updated)
     else:
         keep = np.ones_like(upd)
         w[~upd] = prob[~upd]

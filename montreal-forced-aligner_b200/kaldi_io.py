@@ -389,10 +389,10 @@ class TransitionModel:
             if tot < mincount:
                 continue
             old = np.exp(self.log_probs[a:b].astype(np.float64))
-            new = counts / tot
-            for _ in range(3):
-                new = np.maximum(new, floor)
+            new = counts.copy()
+            for _ in range(3):   # transition-model.cc MleUpdate: renormalise, THEN floor, three times (the floor is the last step)
                 new = new / new.sum()
+                new = np.maximum(new, floor)
             for k in range(n):
                 if counts[k] > 0 and old[k] > 0 and new[k] > 0:
                     objf_impr += counts[k] * (math.log(new[k]) - math.log(old[k]))

@@ -526,6 +526,8 @@ class GmmStatsAccumulator:
         self._dm.acc_zero()
         self.transition_accs = self.transition_model.InitStats()
         self.gmm_accs = AccumAmDiagGmm.init(self.acoustic_model)
+        self.num_done = 0    # utterances accumulated / skipped because the alignment length differs from the frame count
+        self.num_error = 0
 
     def accumulate_stats(self, feature_archive: FeatureArchive, alignment_archive: AlignmentArchive, callback: Optional[Callable] = None,
                          batch_size: int = 512):
@@ -536,8 +538,11 @@ class GmmStatsAccumulator:
             ali = np.zeros(int(fo[-1]), np.int32)
             for j, k in enumerate(ks):
                 a = np.asarray(alignment_archive[k].alignment, np.int32)
-                n = min(len(a), int(fo[j + 1] - fo[j]))
-                ali[fo[j]:fo[j] + n] = a[:n]
+                if len(a) != int(fo[j + 1] - fo[j]):   # gmm-acc-stats-ali: "Alignments has wrong size" -> utterance skipped, error counted
+                    self.num_error += 1
+                    continue                           # transition-id 0 = frame ignored by the kernel
+                ali[fo[j]:fo[j + 1]] = a
+                self.num_done += 1
             self._dm.acc_stats(np.ascontiguousarray(feats, np.float32), ali)
             if callback:
                 callback(len(ks))

@@ -17,6 +17,7 @@ File names follow Job.construct_path (db.py:2212-2236).
 from __future__ import annotations
 
 import os
+import shutil
 import traceback
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -325,17 +326,25 @@ class AlignFunction(KaldiFunction):
             fst_path = self.job.construct_path(wd, "fsts", "ark", did)
             graphs = KC.FstArchive(fst_path)
             feats = self.job.construct_feature_archive(wd, did)
-            sfx = "_first_pass" if first_pass else ""
-            ali = self.job.construct_path(wd, "ali" + sfx, "ark", did)
-            words = self.job.construct_path(wd, "words" + sfx, "ark", did)
-            likes = self.job.construct_path(wd, "likelihoods" + sfx, "ark", did)
+            ali = self.job.construct_path(wd, "ali", "ark", did)
+            words = self.job.construct_path(wd, "words", "ark", did)
+            likes = self.job.construct_path(wd, "likelihoods", "ark", did)
+            # the reference removes the three targets before every export (alignment/multiprocessing.py:836-839): after a first pass
+            # they are symlinks to the *_first_pass archives, and opening them for writing would clobber those
+            links = (ali, words, likes)
+            for path in links:
+                Path(path).unlink(missing_ok=True)
+            if first_pass:
+                ali = self.job.construct_path(wd, "ali_first_pass", "ark", did)
+                words = self.job.construct_path(wd, "words_first_pass", "ark", did)
+                likes = self.job.construct_path(wd, "likelihoods_first_pass", "ark", did)
             aligner.export_alignments(ali, graphs, feats, word_file_name=words, likelihood_file_name=likes, callback=self.callback)
             if first_pass:
-                for src, name in ((ali, "ali"), (words, "words"), (likes, "likelihoods")):
-                    link = self.job.construct_path(wd, name, "ark", did)
-                    if link.exists() or link.is_symlink():
-                        link.unlink()
-                    os.symlink(src.name, link)
+                for src, link in zip((ali, words, likes), links):
+                    try:
+                        os.symlink(Path(src).name, link)
+                    except OSError:   # file systems without symlinks
+                        shutil.copyfile(src, link)
             feats.close()
 
 

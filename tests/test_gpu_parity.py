@@ -96,9 +96,10 @@ def test_cmvn_and_feature_pipeline_parity(eng):
 
 @pytest.mark.parametrize("impl", [1, 0, 96])
 @pytest.mark.parametrize("which", ["mono", "g2p"])
-def test_gmm_loglikes_parity(eng, impl, which, monkeypatch):
+def test_gmm_loglikes_parity(eng, impl, which, request):
     if impl == 96:   # the K = 96 geometry of the tensor-core kernel (gconst as fp16 columns, two-stage ring) instead of K = 80
-        monkeypatch.setenv("MFA_TC_K96", "1")
+        eng.set_option("tc_k96", 1)   # read when the model's operand images are built
+        request.addfinalizer(lambda: eng.set_option("tc_k96", 0))
         impl = 0
     tm, am, _ = load_model(which)
     rng = np.random.default_rng(2)
@@ -161,32 +162,30 @@ def test_viterbi_parity_with_oracle(eng, triphone, beam, retry):
     assert total > 0 and same / total >= 0.999, same / total
 
 
-def _align_env(eng, sc, batch, beam, retry, monkeypatch, **env):
-    for k in ("MFA_VIT_BAND", "MFA_VIT_MAXGROUPS", "MFA_VIT_GRAPH_SMEM", "MFA_VIT_NW2_KB"):
-        monkeypatch.delenv(k, raising=False)
-    for k, v in env.items():
-        monkeypatch.setenv(k, str(v))
-    return _gpu_align_from_oracle_loglikes(eng, sc, batch, beam, retry)
+def _align_env(eng, sc, batch, beam, retry, **opts):
+    """One alignment run under the given engine options (mfa_engine_set_option), restored afterwards."""
+    with eng.options(**opts):
+        return _gpu_align_from_oracle_loglikes(eng, sc, batch, beam, retry)
 
 
 @pytest.mark.parametrize("triphone,beam,retry", [(True, 10.0, 40.0), (False, 3.0, 60.0), (True, 200.0, 0.0)])
-def test_band_kernel_equals_sparse_kernel(eng, monkeypatch, triphone, beam, retry):
+def test_band_kernel_equals_sparse_kernel(eng, triphone, beam, retry):
     """K3's two kernels implement one recursion: the band kernel (primary), the sparse kernel (epsilon graphs, fallback) and the
     band kernel with a 1- or 2-group band (most utterances overflow and are re-run by the sparse kernel) must agree exactly."""
     sc = build_synth_scenario(seconds=80.0, seed=5, triphone=triphone, n_phones=12, n_words=60, target_pdfs=100, gauss_per_pdf=2)
     batch = E.GraphCompiler(sc["tm"], sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts)
     f0 = eng.band_fallbacks
-    band = _align_env(eng, sc, batch, beam, retry, monkeypatch)
+    band = _align_env(eng, sc, batch, beam, retry)
     f1 = eng.band_fallbacks
-    sparse = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_BAND=0)
+    sparse = _align_env(eng, sc, batch, beam, retry, vit_band=0)
     assert eng.band_fallbacks == f1
-    narrow = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_MAXGROUPS=1 if beam < 100 else 2)
+    narrow = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2)
     assert eng.band_fallbacks > f1                      # the fallback path really ran
     if beam <= 10.0:
         assert f1 == f0                                   # ... and the default band is wide enough for ordinary beams
     assert np.isin(sparse.status, (0, 1)).sum() > 0
-    smem4 = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_GRAPH_SMEM=1, MFA_VIT_NW2_KB=0)   # graph in shared memory, 4 warps
-    l1w4 = _align_env(eng, sc, batch, beam, retry, monkeypatch, MFA_VIT_NW2_KB=0)                           # graph through L1, 4 warps
+    smem4 = _align_env(eng, sc, batch, beam, retry, vit_graph_smem=1, vit_nw2_kb=0)   # graph in shared memory, 4 warps
+    l1w4 = _align_env(eng, sc, batch, beam, retry, vit_nw2_kb=0)                           # graph through L1, 4 warps
     for other in (band, narrow, smem4, l1w4):
         assert np.array_equal(other.status, sparse.status) and np.array_equal(other.num_words, sparse.num_words)
         assert np.array_equal(other.ali, sparse.ali) and np.array_equal(other.words, sparse.words)
@@ -270,7 +269,7 @@ def test_fused_pipeline_config1_sample(eng, tmp_path):
     dm.close()
 
 
-def test_fused_pipeline_triphone_lda_fmllr_chunked(eng, monkeypatch):
+def test_fused_pipeline_triphone_lda_fmllr_chunked(eng):
     """Config 2/3 shape in miniature: splice+LDA(+fMLLR) features, triphone tree, several speakers, forced small workspace
     so the chunk loop runs more than once; device-resident PCM."""
     import torch
@@ -296,14 +295,13 @@ def test_fused_pipeline_triphone_lda_fmllr_chunked(eng, monkeypatch):
     assert same / total >= 0.999, same / total
     # host-buffer path cut into segments at speaker boundaries (uploads overlap work on earlier segments): same outputs as the
     # single-segment run; the corpus generator keeps each speaker's utterances contiguous, like MFA's job ordering
-    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "1")
-    res_split = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
-    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "0")
-    res_whole = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
+    with eng.options(pipeline_split=1):
+        res_split = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
+    with eng.options(pipeline_split=0):
+        res_whole = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
     # streamed: K1 / CMVN / features / K2 per segment as its PCM arrives, one Viterbi launch at the end (the default for big batches)
-    monkeypatch.setenv("MFA_PIPELINE_SPLIT", "2")
-    res_stream = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
-    monkeypatch.delenv("MFA_PIPELINE_SPLIT")
+    with eng.options(pipeline_split=2):
+        res_stream = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "lda", lda=sc["lda"])
     assert len(set(c.utt2spk.tolist())) > 1
     for r_ in (res_split, res_whole, res_stream):
         assert np.array_equal(r_.ali, ali) and np.array_equal(r_.status, st) and np.array_equal(r_.total_like, tl)
@@ -342,7 +340,7 @@ def test_acc_stats_parity(eng):
     dm.close()
 
 
-def test_acc_stats_segmented_equals_atomic_kernel_and_handles_ragged_input(eng, monkeypatch):
+def test_acc_stats_segmented_equals_atomic_kernel_and_handles_ragged_input(eng, request):
     """K4's two kernels (counting sort by pdf + register accumulation per item | one red per frame) on one concatenated batch:
     integer fields identical, f64 sums equal to rounding; frames with tid 0 / out-of-range are skipped; a pdf with many
     components and a pdf with thousands of frames (several items, one CTA reusing its staged Gaussians) are both present."""
@@ -370,7 +368,8 @@ def test_acc_stats_segmented_equals_atomic_kernel_and_handles_ragged_input(eng, 
     dm = E.DeviceModel(eng, tm, am)
     res = {}
     for impl in ("atomic", "segmented"):
-        monkeypatch.setenv("MFA_ACC_IMPL", impl)
+        eng.set_option("acc_impl", 1 if impl == "atomic" else 0)
+        request.addfinalizer(lambda: eng.set_option("acc_impl", 0))
         dm.acc_zero()
         dm.acc_stats(feats, ali)
         dm.acc_stats(feats[:0], ali[:0])               # empty call is a no-op
@@ -458,7 +457,7 @@ def test_fmllr_stats_and_transforms_parity(eng, two_models, use_lda):
         dmp.close()
 
 
-def test_acc_stats_large_many_pdfs_against_numpy(eng, monkeypatch):
+def test_acc_stats_large_many_pdfs_against_numpy(eng, request):
     """K4 at a size where every CTA walks several items and pdfs (4 000 pdfs x 10 components, 600 k frames): both kernels against a
     float64 numpy evaluation of the same posteriors (total log-likelihood, occupancies, first-order sums)."""
     from mfa_b200 import kaldi_io as K
@@ -493,7 +492,8 @@ def test_acc_stats_large_many_pdfs_against_numpy(eng, monkeypatch):
     mean0_ref = np.bincount(idx.ravel(), weights=(post * x[:, :1]).ravel(), minlength=G)
     dm = E.DeviceModel(eng, tm, am)
     for impl in ("segmented", "atomic"):
-        monkeypatch.setenv("MFA_ACC_IMPL", impl)
+        eng.set_option("acc_impl", 1 if impl == "atomic" else 0)
+        request.addfinalizer(lambda: eng.set_option("acc_impl", 0))
         dm.acc_zero()
         dm.acc_stats(feats, ali)
         got = dm.acc_read()
@@ -506,13 +506,14 @@ def test_acc_stats_large_many_pdfs_against_numpy(eng, monkeypatch):
 
 
 @pytest.mark.parametrize("k96", [False, True])
-def test_gmm_loglikes_odd_gaussian_count_and_ragged_pdfs(eng, monkeypatch, k96):
+def test_gmm_loglikes_odd_gaussian_count_and_ragged_pdfs(eng, request, k96):
     """Dense K2 on a model whose Gaussian count is odd and whose pdfs have 1..17 components (tiles with ragged pdf boundaries, a
     trailing partial tile): both operand geometries against the oracle.  (A Gaussian count that is not a multiple of 4 once put the
     per-tile gconst array of the K = 80 geometry on a misaligned address.)"""
     from mfa_b200 import kaldi_io as K
     if k96:
-        monkeypatch.setenv("MFA_TC_K96", "1")
+        eng.set_option("tc_k96", 1)
+        request.addfinalizer(lambda: eng.set_option("tc_k96", 0))
     rng = np.random.default_rng(77)
     D, P = 39, 53
     comps = rng.integers(1, 18, size=P)

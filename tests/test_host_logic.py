@@ -130,3 +130,76 @@ def test_accumulator_allreduce_two_ranks_gloo(tmp_path):
     i0, i1 = np.load(tmp_path / "in0.npy"), np.load(tmp_path / "in1.npy")
     o0, o1 = np.load(tmp_path / "out0.npy"), np.load(tmp_path / "out1.npy")
     assert np.array_equal(o0, o1) and np.allclose(o0, i0 + i1, rtol=1e-15)
+
+
+def test_align_function_first_pass_then_second_pass_keeps_first_pass_archives(tmp_path, monkeypatch):
+    """AlignFunction with final.alimdl writes *_first_pass archives and links ali/words/likelihoods to them; the pass with final.mdl
+    must REPLACE those links by regular files and leave the first-pass archives untouched (the reference unlinks the three targets
+    before every export, alignment/multiprocessing.py:836-839).  The aligner is stubbed: this is file-flow logic, no GPU."""
+    from pathlib import Path
+    from mfa_b200 import kalpy_compat as KC
+
+    class FakeAligner:
+        def __init__(self, model_path, **kw):
+            self.tag = Path(str(model_path)).name.encode()
+
+        def boost_silence(self, *a):
+            pass
+
+        def export_alignments(self, ali, graphs, feats, word_file_name=None, likelihood_file_name=None, callback=None):
+            for p in (ali, word_file_name, likelihood_file_name):
+                with open(p, "wb") as f:    # follows symlinks, like ArkWriter
+                    f.write(self.tag)
+
+    class FakeArchive:
+        def __init__(self, *a, **k):
+            pass
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(KC, "GmmAligner", FakeAligner)
+    monkeypatch.setattr(KC, "FstArchive", FakeArchive)
+    job = MF.Job(1, [], tmp_path)
+    monkeypatch.setattr(MF.Job, "construct_feature_archive", lambda self, wd, did=None, **k: FakeArchive())
+    for model in ("final.alimdl", "final.mdl"):
+        args = MF.AlignArguments(1, job, None, tmp_path, tmp_path / model, {"beam": 10}, False, False, ())
+        MF.AlignFunction(args)._run()
+        if model == "final.alimdl":
+            for name in ("ali", "words", "likelihoods"):
+                link = tmp_path / f"{name}.1.1.ark"
+                assert link.is_symlink() and link.read_bytes() == b"final.alimdl"
+    for name in ("ali", "words", "likelihoods"):
+        out, first = tmp_path / f"{name}.1.1.ark", tmp_path / f"{name}_first_pass.1.1.ark"
+        assert not out.is_symlink() and out.read_bytes() == b"final.mdl"
+        assert first.read_bytes() == b"final.alimdl"         # the first pass survives the second
+
+
+def test_transition_update_floor_is_the_last_step():
+    """TransitionModel::MleUpdate renormalises, then floors, three times: a transition seen far less often than floor ends exactly at
+    the floor (0.01), not below it."""
+    tm, _, _ = load_model("mono")
+    stats = tm.InitStats()
+    ts = next(t for t in range(1, tm.tuples.shape[0] + 1) if tm.state2id[t + 1] - tm.state2id[t] == 2)
+    a = int(tm.state2id[ts])
+    stats[a], stats[a + 1] = 100000.0, 3.0
+    tm.mle_update(stats)
+    p = np.exp(tm.log_probs[a:a + 2].astype(np.float64))
+    assert abs(p[1] - 0.01) < 1e-7 and p[0] < 1.0
+
+
+def test_mle_update_keeps_the_last_gaussian_of_a_starved_pdf():
+    tm, am, _ = load_model("g2p")
+    acc = GU.AccumAmDiagGmm.init(am)
+    pdf = int(np.argmax(np.diff(am.offsets)))
+    a, b = int(am.offsets[pdf]), int(am.offsets[pdf + 1])
+    assert b - a >= 2
+    rng = np.random.default_rng(0)
+    acc.occ[:] = 50.0
+    acc.mean[:] = 50.0 * am.means()
+    acc.var[:] = 50.0 * (am.variances() + am.means() ** 2)
+    acc.occ[a:b] = np.linspace(5.0, 1.0, b - a)     # every component under min_gaussian_occupancy; the FIRST is the heaviest
+    new, _, _ = GU.mle_update(am, acc)
+    assert new.offsets[pdf + 1] - new.offsets[pdf] == 1
+    k = int(new.offsets[pdf])
+    assert np.allclose(new.means()[k], am.means()[b - 1], rtol=1e-5)    # Kaldi keeps the LAST index, un-updated

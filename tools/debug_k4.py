@@ -16,6 +16,6 @@ ali = res.ali[:T].contiguous()
 eng.sync()
 print("sum per_frame / T", float(res.per_frame[:T].double().sum()) / T, "nm max", int(np.diff(sc.am.offsets).max()))
 for impl in ("segmented", "atomic", "segmented"):
-    os.environ["MFA_ACC_IMPL"] = impl
+    eng.set_option("acc_impl", 1 if impl == "atomic" else 0)
     sc.model.acc_zero(); sc.model.acc_stats(feats, ali); a = sc.model.acc_read()
     print(impl, a["like"] / a["frames"], a["frames"], a["occ"].sum())
