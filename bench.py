@@ -156,7 +156,8 @@ def parity_block(sc, utts, ref, gpu):
     same = total = status_mis = word_mis = 0
     b_ok = b_tot = 0
     like_err = pf_err = 0.0
-    worst = None
+    worst = pf_worst = None
+    pf_n_bad = 0
     for u, r in zip(utts, ref):
         if int(st[u]) != int(r["status"]):
             status_mis += 1
@@ -171,9 +172,14 @@ def parity_block(sc, utts, ref, gpu):
         if list(words[wo[u]:wo[u] + nw[u]]) != list(r["words"]):
             word_mis += 1
         like_err = max(like_err, abs(float(tl[u]) - r["like"]) / max(1e-30, abs(r["like"])))
-        d = np.abs(pf[fo[u]:fo[u + 1]][a == r["ali"]] - r["per_frame"][a == r["ali"]])
-        if d.size:
-            pf_err = max(pf_err, float((d / np.maximum(1.0, np.abs(r["per_frame"][a == r["ali"]]))).max()))
+        eq = a == r["ali"]
+        d = np.abs(pf[fo[u]:fo[u + 1]] - r["per_frame"]) / np.maximum(1.0, np.abs(r["per_frame"]))
+        d[~eq] = 0.0
+        if d.size and float(d.max()) > pf_err:
+            t = int(np.argmax(d))
+            pf_err = float(d.max())
+            pf_worst = {"utt": int(u), "frame": t, "oracle": float(r["per_frame"][t]), "gpu": float(pf[fo[u] + t]), "tid": int(a[t])}
+        pf_n_bad += int((d > 1e-4).sum())
         cg = KC.Alignment(str(u), a, [], float(tl[u])).generate_ctm(sc.tm, None)
         cr = KC.Alignment(str(u), r["ali"], [], r["like"]).generate_ctm(sc.tm, None)
         b_tot += 2 * len(cr)
@@ -182,20 +188,31 @@ def parity_block(sc, utts, ref, gpu):
     return {"against": "oracle port (oracle/oracle.c), same utterances as cpu_baseline.sample; parity unpinned vs real Kaldi (DESIGN.md 2)",
             "utterances": len(utts), "frames": total, "frame_agreement_pct": 100.0 * same / max(1, total), "status_mismatches": status_mis,
             "word_sequence_mismatches": word_mis, "loglike_rel_err_max": like_err, "per_frame_loglike_rel_err_max": pf_err,
+            "per_frame_loglike_worst": pf_worst, "per_frame_loglikes_beyond_1e-4": pf_n_bad,
             "boundary_within_1_frame_pct": 100.0 * b_ok / max(1, b_tot), "phone_boundaries": b_tot,
             "worst_utterance": None if worst is None else {"utt": worst[0], "differing_frames": worst[1], "frames": worst[2]},
             "retried_utterances_in_sample": int(sum(1 for r in ref if r["status"] == 1))}
 
 
-def pick_sample(sc, audio_seconds: float):
+def pick_sample(sc, audio_seconds: float, also=()):
+    """Whole speakers from the start of the corpus until `audio_seconds` are covered, plus the whole speakers of the utterances in
+    `also`: per-speaker CMVN statistics need every utterance of a speaker, so a sample that cuts a speaker would give the CPU arm
+    different features from the GPU arm's."""
     c = sc.corpus
-    utts, tot = [], 0.0
+    dur = (c.sample_off[1:] - c.sample_off[:-1]) / 16000.0
+    spk, tot = [], 0.0
     for u in range(c.n_utts):
-        utts.append(u)
-        tot += (c.sample_off[u + 1] - c.sample_off[u]) / 16000.0
-        if tot >= audio_seconds:
-            break
-    return utts
+        s = int(c.utt2spk[u])
+        if s not in spk:
+            if tot >= audio_seconds:
+                break
+            spk.append(s)
+        tot += float(dur[u])
+    for u in also:
+        if int(c.utt2spk[u]) not in spk:
+            spk.append(int(c.utt2spk[u]))
+    keep = set(spk)
+    return [u for u in range(c.n_utts) if int(c.utt2spk[u]) in keep]
 
 
 def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
@@ -281,60 +298,96 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
 
 
 def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
-    """Config 4's loop on this rank's shard: align (fused step) -> K4 statistics -> all-reduce over NCCL (N > 1) -> D2H -> host M-step
-    (gmm_update.mle_update, vectorised numpy f64) -> new model on the device.  Transition costs stay folded in the packed graphs
-    (MFA recompiles graphs only at realignment iterations).  Wall-clock per stage, max over ranks is NOT taken: rank 0's view."""
+    """Config 4's loop on this rank's shard, `--train-iters` iterations: align (the fused step, PCM in) -> K4 statistics -> NCCL
+    all-reduce of the f64 accumulator block (N > 1) -> M-step ON THE DEVICE (csrc/mstep.cu: GMM update with low-count removal and mix-up
+    back to the starting size, transition update, K2 operand images rebuilt) -> transition costs re-folded into the packed graphs.  No
+    accumulator and no model parameter crosses PCIe; per iteration the host reads one result struct and the new pdf offsets (16 KB).
+    Stage times are host wall clock around synchronised stages on THIS rank; `iteration_ms` is additionally reduced with MAX over ranks.
+    A rank that fails tells the others before the next collective (MIN all-reduce of an ok flag), so nobody waits forever."""
     import torch
-    from mfa_b200 import engine as E, gmm_update as GU
+    from mfa_b200 import engine as E
     c = sc.corpus
     mo = E.mfcc_opts()
     fo = sc.frame_off
     T = int(fo[-1])
-    model, am = sc.model, sc.am
+    model = E.DeviceModel(eng, sc.tm, sc.am)      # the loop updates its own copy in place; sc.model stays the benchmark's model
+    graphs = E.Graphs(sc.batch, sc.tm, 1.0, 0.1)
+    model.set_transitions(sc.tm)
+    g0 = sc.am.NumGauss()
     raw, _ = eng.mfcc(d_pcm, c.sample_off, mo)
     stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
     eng.sync()
     feats = eng.features(raw, fo, sc.feat_mode, lda=sc.lda, cmvn_stats=stats.cpu().numpy(), utt2spk=c.utt2spk, n_spk=c.n_spk)
     eng.sync()   # the feature kernel reads `raw` on the engine stream: it must finish before torch may recycle that memory
     del raw
-    wo_total = int(np.cumsum(sc.graphs.max_words())[-1])
+    wo_total = int(np.cumsum(graphs.max_words())[-1])
     outs = E._alloc_outputs(T, wo_total, c.n_utts, dev)
-    iters = []
+    ws = int(args.workspace_gb * (1 << 30))
+
+    def all_ok(ok: bool) -> bool:
+        if dist is None:
+            return ok
+        f = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item() > 0.5)
+
+    iters, failed = [], None
+    E.align_pcm(eng, model, graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda, workspace_bytes=ws, outputs=outs)
+    eng.sync()   # first call with this model / these graphs: plans and uploads are paid here, like the warm-up steps of the main arm
     for it in range(args.train_iters):
         t = {}
-        t0 = time.perf_counter()
-        res = E.align_pcm(eng, model, sc.graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo,
-                          sc.feat_mode, lda=sc.lda, workspace_bytes=int(args.workspace_gb * (1 << 30)), outputs=outs)
-        eng.sync(); t["align_ms"] = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        model.acc_zero()
-        model.acc_stats(feats, res.ali[:T].contiguous())
-        eng.sync(); t["acc_stats_ms"] = 1e3 * (time.perf_counter() - t0)
+        ok = True
+        t_it = time.perf_counter()
+        try:
+            t0 = time.perf_counter()
+            res = E.align_pcm(eng, model, graphs, d_pcm, c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda, workspace_bytes=ws, outputs=outs)
+            eng.sync(); t["align_ms"] = 1e3 * (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            model.acc_zero()
+            model.acc_stats(feats, res.ali[:T])
+            eng.sync(); t["acc_stats_ms"] = 1e3 * (time.perf_counter() - t0)
+        except Exception as ex:
+            ok, failed = False, repr(ex)
+        if not all_ok(ok):
+            failed = failed or "another rank failed"
+            break
         t0 = time.perf_counter()
         if dist is not None:
-            eng.sync()
-            dist.all_reduce(model.acc_tensor())
+            acc_t = model.acc_tensor()
+            dist.all_reduce(acc_t)
             torch.cuda.synchronize(dev)
+            t["allreduce_bytes"] = int(acc_t.numel() * 8)
         t["allreduce_ms"] = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        acc = model.acc_read()
-        t["d2h_ms"] = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        new_am, impr, count = GU.mle_update(am, GU.AccumAmDiagGmm.from_dict(acc), mixup=0)
-        t["mstep_host_ms"] = 1e3 * (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        new_model = E.DeviceModel(eng, sc.tm, new_am)
-        eng.sync(); t["model_upload_ms"] = 1e3 * (time.perf_counter() - t0)
-        t["avg_loglike_per_frame"] = acc["like"] / max(1.0, acc["frames"])
-        t["frames_all_ranks"] = acc["frames"]
-        t["gaussians"] = new_am.NumGauss()
-        if model is not sc.model:
-            model.close()
-        model, am = new_model, new_am
+        try:
+            t0 = time.perf_counter()
+            r = model.mle_update(mixup=g0, update_transitions=True, seed=1234 + it)
+            t["mstep_device_ms"] = 1e3 * (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            graphs.set_transitions(eng, model, 1.0, 0.1)
+            eng.sync(); t["refold_graphs_ms"] = 1e3 * (time.perf_counter() - t0)
+            t["avg_loglike_per_frame"] = r["tot_like"] / max(1.0, r["tot_frames"])
+            t["frames_all_ranks"] = r["tot_frames"]
+            t["gaussians"] = r["num_gauss_after"]; t["removed"] = r["num_removed"]; t["split"] = r["num_split"]
+            t["layout_changed"] = r["layout_changed"]
+        except Exception as ex:
+            ok, failed = False, repr(ex)
+        if not all_ok(ok):
+            failed = failed or "another rank failed"
+            break
+        t["iteration_ms"] = 1e3 * (time.perf_counter() - t_it)
+        if dist is not None:
+            m = torch.tensor([t["iteration_ms"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            t["iteration_ms_max_over_ranks"] = float(m.item())
         iters.append(t)
-    if model is not sc.model:
-        model.close()
-    return {"iterations": iters, "note": "wall-clock per stage on rank 0 (host timers around synchronised stages); avg_loglike_per_frame must not decrease"}
+    model.close()
+    graphs.close()
+    out = {"iterations": iters, "hours_all_ranks": c.seconds / 3600.0 * (dist.get_world_size() if dist is not None else 1),
+           "note": "config 4: align -> K4 -> NCCL all-reduce -> device M-step (mix-up to the starting size) -> graph re-fold; wall clock per "
+                   "synchronised stage on rank 0; avg_loglike_per_frame must not decrease"}
+    if failed:
+        out["failed"] = failed
+    return out
 
 
 def main():
@@ -350,7 +403,7 @@ def main():
     ap.add_argument("--cpu-sample-seconds", type=float, default=0.0, help="audio seconds for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=100.0)
-    ap.add_argument("--train-iters", type=int, default=2, help="iterations of the align -> acc-stats -> all-reduce -> update loop timed under extras.train_loop")
+    ap.add_argument("--train-iters", type=int, default=4, help="iterations of the align -> acc-stats -> all-reduce -> update loop timed under extras.train_loop")
     ap.add_argument("--extras-dist", action="store_true", help="multi-rank runs: also time K4 / K5 / the SAT two-pass flow per rank (the training loop with its NCCL all-reduce always runs)")
     ap.add_argument("--same-shards", action="store_true", help="multi-rank runs: every rank gets the SAME corpus (seed 1234): separates data effects (a rank owning a slow utterance) from system effects in the per-rank table")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this process to the CPUs of the GPU's NUMA node")
@@ -644,9 +697,7 @@ def main():
         try:
             sc._fsts = sc.batch.export()
             sample_s = args.cpu_sample_seconds or 7200.0
-            utts = pick_sample(sc, sample_s)
-            if retried.size and int(retried[0]) not in utts:   # make sure a retry-beam utterance is part of the parity sample
-                utts.append(int(retried[0]))
+            utts = pick_sample(sc, sample_s, also=[int(u) for u in retried[:2]])   # a retry-beam utterance is part of the parity sample
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 10)], cores)
             dt, secs, ok, ref = cpu_reference_pass(sc, utts, cores)
             line["cpu_baseline"] = {"value": secs / dt, "unit": UNIT, "cores": cores, "kind": "port",

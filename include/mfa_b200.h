@@ -129,11 +129,54 @@ typedef struct {
   const float *means_invvars;  /* [num_gauss][dim] */
   const float *inv_vars;       /* [num_gauss][dim] */
   const int32_t *tid2pdf;      /* [num_tids+1], index 0 unused */
+  const float *weights;        /* [num_gauss] mixture weights, or NULL (only needed to read an updated model back: mfa_model_read) */
 } mfa_model_desc;
 MFA_API int mfa_model_create(mfa_engine *e, const mfa_model_desc *d, mfa_model **out);
 MFA_API int mfa_model_destroy(mfa_model *m);
 /* GmmAligner.boost_silence (alignment/multiprocessing.py:803-815): gconst += log(factor) for pdfs */
 MFA_API int mfa_model_boost_pdfs(mfa_model *m, float factor, const int32_t *pdfs, int32_t n);
+
+/* ---- N3 / a10: the M-step on the device.  Replaces, after the accumulators of all jobs have been summed (here: the NCCL all-reduce of
+ *      the block behind mfa_acc_device_ptr), `tm.mle_update(transition_accs)` and `am.mle_update(gmm_accs, mixup=, power=)` of
+ *      AcousticModelTrainingMixin.acc_stats (acoustic_modeling/base.py:319-338 upstream; monophone.py:275-296): Kaldi MleDiagGmmUpdate /
+ *      MleAmDiagGmmUpdate, AmDiagGmm::SplitByCount + DiagGmm::Split, TransitionModel::MleUpdate.  The model is updated IN PLACE from its
+ *      own accumulator block (which is released: call mfa_acc_zero before the next mfa_acc_stats; mfa_acc_size changes with the number
+ *      of Gaussians), and the K2 operand images are rebuilt on the device.  No accumulator leaves the GPU. */
+typedef struct {
+  int32_t num_tstates;
+  const int32_t *tstate_first_tid;  /* [num_tstates+2], 1-based transition-states -> first transition-id */
+  const int32_t *self_loop_tid;     /* [num_tstates+1] self-loop transition-id of the state, 0 if none */
+  const float *log_probs;           /* [num_tids+1] */
+} mfa_trans_desc;
+MFA_API int mfa_model_set_transitions(mfa_model *m, const mfa_trans_desc *d);
+typedef struct {
+  double min_gaussian_occupancy;    /* Kaldi 10 (MFA: 3 at monophone iteration 0, monophone.py:282) */
+  double min_gaussian_weight;       /* 1e-5 */
+  double min_variance;              /* 1e-3 */
+  int32_t remove_low_count_gaussians; /* 1 */
+  int32_t mixup;                    /* target total number of Gaussians (SplitByCount), 0 = no mix-up */
+  float power;                      /* 0.25 */
+  float min_count;                  /* 20 */
+  float perturb_factor;             /* 0.01 */
+  int32_t update_transitions;       /* 1: TransitionModel::MleUpdate from the transition counts of the block */
+  float transition_floor;           /* 0.01 */
+  float transition_mincount;        /* 5 */
+  uint64_t seed;                    /* of the counter-based normal draws of the mix-up perturbation */
+} mfa_mle_opts;
+typedef struct {
+  double gmm_objf_impr, gmm_count;  /* summed over the pdfs that lost no component (Kaldi reports no change for the others) */
+  double trans_objf_impr, trans_count;
+  double tot_like, tot_frames;      /* of the accumulation pass that fed this update */
+  int64_t variance_floored;
+  int32_t num_gauss_before, num_gauss_after, num_removed, num_split;
+  int32_t layout_changed;           /* 1: some pdf's component count changed (per-utterance K2 tile plans are rebuilt on next use) */
+} mfa_mle_result;
+MFA_API int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa_mle_result *res);
+MFA_API int mfa_model_num_gauss(const mfa_model *m);
+/* device -> host copy of the current parameters (any pointer may be NULL): pdf_off[num_pdfs+1], weights / gconsts [num_gauss],
+ * means_invvars / inv_vars [num_gauss][dim], log_probs[num_tids+1] -- what write_gmm_model needs ({it}.mdl, acoustic_modeling/base.py). */
+MFA_API int mfa_model_read(mfa_engine *e, mfa_model *m, int32_t *pdf_off, float *weights, float *gconsts, float *means_invvars,
+                           float *inv_vars, float *log_probs);
 
 /* ---- K2: all-pdf frame log-likelihoods.  Replaces DecodableAmDiagGmmScaled / gmm_compute_likes
  *      (inside GmmAligner; alignment/multiprocessing.py:1415).  out: [n_frames][num_pdfs] f32,
@@ -214,6 +257,9 @@ MFA_API int mfa_rand_sequence(uint32_t seed, int32_t n, int32_t *out);
 MFA_API int mfa_graphs_pack(const mfa_fst_batch *b, const float *tid_cost, const int32_t *tid2pdf, int32_t num_tids,
                             mfa_graphs **out);
 MFA_API int mfa_graphs_destroy(mfa_graphs *g);
+/* AddTransitionProbs again, on the device, from the model's CURRENT transition log-probabilities (after mfa_model_mle_update): what
+ * GmmAligner does per graph at align time when it reads the re-estimated model (alignment/multiprocessing.py:814-853). */
+MFA_API int mfa_graphs_set_transitions(mfa_engine *e, mfa_graphs *g, mfa_model *m, float transition_scale, float self_loop_scale);
 MFA_API int mfa_graphs_max_words(const mfa_graphs *g, int32_t *max_words /* [n_utts] upper bound on olabels per path */);
 /* per-utterance prefix offsets ([n_utts+1] each; any pointer may be NULL): states, arcs, distinct pdfs referenced */
 MFA_API int mfa_graphs_offsets(const mfa_graphs *g, int64_t *state_off, int64_t *arc_off, int64_t *pdf_off);
@@ -277,6 +323,8 @@ MFA_API int mfa_acc_stats(mfa_engine *e, mfa_model *m, const float *feats, const
 /* device pointer to the accumulator block (for an NCCL all-reduce by the host layer) */
 MFA_API double *mfa_acc_device_ptr(mfa_engine *e, mfa_model *m);
 MFA_API int mfa_acc_read(mfa_engine *e, mfa_model *m, double *host_out);
+/* host block (same layout) -> device accumulators: for callers that summed kalpy-style accumulator objects on the host */
+MFA_API int mfa_acc_write(mfa_engine *e, mfa_model *m, const double *host_in);
 
 /* ---- K5 (N2): per-speaker fMLLR statistics.  Replaces the accumulation inside kalpy FmllrComputer.export_transforms
  *      (CalcFmllrFunction._run, corpus/features.py:460-548; Kaldi gmm-est-fmllr / gmm-est-fmllr-gpost + weight-silence-post).

@@ -37,7 +37,24 @@ class FeatOpts(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [("dim", C.c_int32), ("num_pdfs", C.c_int32), ("num_gauss", C.c_int32), ("num_tids", C.c_int32),
                 ("pdf_off", C.c_void_p), ("gconsts", C.c_void_p), ("means_invvars", C.c_void_p),
-                ("inv_vars", C.c_void_p), ("tid2pdf", C.c_void_p)]
+                ("inv_vars", C.c_void_p), ("tid2pdf", C.c_void_p), ("weights", C.c_void_p)]
+
+
+class TransDesc(C.Structure):
+    _fields_ = [("num_tstates", C.c_int32), ("tstate_first_tid", C.c_void_p), ("self_loop_tid", C.c_void_p), ("log_probs", C.c_void_p)]
+
+
+class MleOpts(C.Structure):
+    _fields_ = [("min_gaussian_occupancy", C.c_double), ("min_gaussian_weight", C.c_double), ("min_variance", C.c_double),
+                ("remove_low_count_gaussians", C.c_int32), ("mixup", C.c_int32), ("power", C.c_float), ("min_count", C.c_float),
+                ("perturb_factor", C.c_float), ("update_transitions", C.c_int32), ("transition_floor", C.c_float),
+                ("transition_mincount", C.c_float), ("seed", C.c_uint64)]
+
+
+class MleResult(C.Structure):
+    _fields_ = [("gmm_objf_impr", C.c_double), ("gmm_count", C.c_double), ("trans_objf_impr", C.c_double), ("trans_count", C.c_double),
+                ("tot_like", C.c_double), ("tot_frames", C.c_double), ("variance_floored", C.c_int64), ("num_gauss_before", C.c_int32),
+                ("num_gauss_after", C.c_int32), ("num_removed", C.c_int32), ("num_split", C.c_int32), ("layout_changed", C.c_int32)]
 
 
 class HmmDesc(C.Structure):
@@ -73,10 +90,11 @@ SYMBOLS = [
     "mfa_last_error", "mfa_abi_version", "mfa_engine_create", "mfa_engine_destroy", "mfa_engine_sync", "mfa_engine_stream",
     "mfa_engine_sm_count", "mfa_engine_set_option", "mfa_engine_get_option", "mfa_engine_launch_count", "mfa_engine_band_fallbacks", "mfa_engine_gmm_timing", "mfa_engine_gmm_flops", "mfa_engine_stage_timing", "mfa_mfcc_num_frames", "mfa_mfcc",
     "mfa_cmvn_stats", "mfa_cmvn_apply", "mfa_feat_out_dim", "mfa_features", "mfa_model_create", "mfa_model_destroy",
-    "mfa_model_boost_pdfs", "mfa_gmm_loglikes", "mfa_graph_compiler_create", "mfa_graph_compiler_destroy", "mfa_graph_compile",
+    "mfa_model_boost_pdfs", "mfa_model_set_transitions", "mfa_model_mle_update", "mfa_model_num_gauss", "mfa_model_read",
+    "mfa_graphs_set_transitions", "mfa_gmm_loglikes", "mfa_graph_compiler_create", "mfa_graph_compiler_destroy", "mfa_graph_compile",
     "mfa_fst_batch_create", "mfa_fst_batch_destroy", "mfa_fst_batch_sizes", "mfa_fst_batch_export", "mfa_graphs_pack",
     "mfa_graphs_destroy", "mfa_graphs_max_words", "mfa_graphs_offsets", "mfa_graphs_band_view", "mfa_align", "mfa_align_feats", "mfa_align_pcm", "mfa_acc_size", "mfa_acc_zero", "mfa_acc_stats",
-    "mfa_acc_device_ptr", "mfa_acc_read", "mfa_equal_align", "mfa_rand_sequence", "mfa_fmllr_stats_size", "mfa_fmllr_acc", "mfa_fmllr_update",
+    "mfa_acc_device_ptr", "mfa_acc_read", "mfa_acc_write", "mfa_equal_align", "mfa_rand_sequence", "mfa_fmllr_stats_size", "mfa_fmllr_acc", "mfa_fmllr_update",
 ]
 
 _lib = None

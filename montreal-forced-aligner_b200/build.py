@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmfa_b200.so")
-SOURCES = ["engine.cu", "mfcc.cu", "feats.cu", "gmm.cu", "gmm_tc.cu", "viterbi.cu", "viterbi_band.cu", "accstats.cu", "fmllr.cu", "pipeline.cu", "graph.cc"]
+SOURCES = ["engine.cu", "mfcc.cu", "feats.cu", "gmm.cu", "gmm_tc.cu", "viterbi.cu", "viterbi_band.cu", "accstats.cu", "fmllr.cu", "mstep.cu", "pipeline.cu", "graph.cc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 

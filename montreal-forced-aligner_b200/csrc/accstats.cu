@@ -265,6 +265,17 @@ extern "C" int mfa_acc_read(mfa_engine *e, mfa_model *m, double *host_out) {
   return MFA_OK;
 }
 
+// host accumulators -> the device block (statistics summed on the host by a caller that keeps kalpy's AccumAmDiagGmm objects, and tests)
+extern "C" int mfa_acc_write(mfa_engine *e, mfa_model *m, const double *host_in) {
+  if (!e || !m || !host_in) return set_error(MFA_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t bytes = (size_t)mfa_acc_size(m) * sizeof(double);
+  if (!m->d_acc) CUDA_TRY(cudaMalloc((void **)&m->d_acc, bytes));
+  CUDA_TRY(cudaMemcpyAsync(m->d_acc, host_in, bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return MFA_OK;
+}
+
 namespace mfa {
 static int launch_acc_stats_atomic(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames) {
   int64_t blocks = (n_frames + AW - 1) / AW;

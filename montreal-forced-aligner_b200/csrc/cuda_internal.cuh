@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -146,10 +146,17 @@ struct mfa_model {
   mfa_engine *eng = nullptr;
   int device = 0;                      // copied from the engine at creation: the destructor must not touch `eng` (it may be gone)
   int dim = 0, num_pdfs = 0, num_gauss = 0, num_tids = 0;
-  std::vector<int32_t> h_pdf_off, h_tid2pdf;
-  std::vector<float> h_gconsts, h_miv, h_iv;
+  std::vector<int32_t> h_pdf_off, h_tid2pdf;   // h_pdf_off is ALWAYS current (the host plans K2 tiles from it)
+  std::vector<float> h_gconsts, h_miv, h_iv, h_weights;   // host mirrors of the parameters; stale after a device M-step until ensure_host()
+  bool host_stale = false;
+  int ensure_host();                   // refresh the host mirrors from the device arrays
   int32_t *d_pdf_off = nullptr, *d_tid2pdf = nullptr;
-  float *d_gconsts = nullptr, *d_miv = nullptr, *d_iv = nullptr;  // natural layout (K4)
+  float *d_gconsts = nullptr, *d_miv = nullptr, *d_iv = nullptr;  // natural layout (K4, K5, the M-step, source of the K2 operand images)
+  float *d_weights = nullptr;          // [num_gauss] mixture weights (nullptr when the model was created without them)
+  // transition model tables for on-device training (mfa_model_set_transitions)
+  int num_tstates = 0;
+  int32_t *d_first_tid = nullptr, *d_self_loop_tid = nullptr;
+  float *d_log_probs = nullptr, *d_tid_cost = nullptr;
   // tiled layout (K2)
   int n_tiles = 0, kdim = 0;           // kdim = 2*dim
   std::vector<int32_t> h_tile_pdf0;    // [n_tiles+1] first pdf of each tile
@@ -159,6 +166,9 @@ struct mfa_model {
   float *d_W = nullptr;                // [n_tiles][kdim][TILE_N]  (k-major: coalesced / conflict-free tile loads)
   float *d_G = nullptr;                // [n_tiles][TILE_N] gconsts (-1e30 padding)
   int32_t *d_gauss_row = nullptr;      // [num_gauss] tile row (tile*TILE_N + col) of natural Gaussian m
+  bool ffma_ready = false;             // d_W / d_G / d_tile_* (the fp32 CUDA-core kernel's layout) are built on first use
+  int layout_tiles();                  // host: n_tiles / h_tile_pdf0 from h_pdf_off
+  int ensure_ffma();
   // tensor-core operand images (gmm_tc.cu); built lazily
   void *d_tc_w = nullptr;
   size_t tc_w_bytes = 0;
@@ -166,12 +176,14 @@ struct mfa_model {
   std::vector<float> h_tc_colscale;    // per-dimension power-of-two feature scaling folded into the weights
   float *d_tc_colscale = nullptr;
   bool tc_ready = false;
+  bool tc_unsupported = false;         // weights beyond the fp16 range / dim too large: the fp32 kernel scores this model
+  size_t tc_cap_gauss = 0;             // Gaussians d_tc_rows / d_tc_g were allocated for
+  int32_t *d_tc_flag = nullptr;        // device flag: a weight exceeded the fp16 range while the operand rows were written
   void *d_tc_rows = nullptr;           // fp16 hi/lo weight rows [2][G][tc_k] (row-major; source of the per-utterance tile gather)
   int tc_k = 96;                       // K extent of the operand images: 80 (gconst added by the epilogue) or 96 (gconst as fp16 columns)
   float *d_tc_g = nullptr;             // gconst * log2(e): [G] per Gaussian, then [n_tiles][128] per column of the dense tiling
   uint64_t tc_version = 0;             // hash of the pdf -> Gaussian layout and the operand geometry: the key of the cached ragged plans
   double *d_acc = nullptr;
-  int rebuild_tiles();
   ~mfa_model();
 };
 
@@ -188,6 +200,8 @@ int launch_features(mfa_engine *e, const mfa_feat_opts *o, const float *d_in, co
 int launch_gmm_ffma(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
 int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld);
 bool gmm_tc_supported(mfa_model *m);
+int build_tc_device(mfa_model *m, bool layout_changed);        // K2 operand images from the device-resident natural-layout parameters
+int refold_graphs(mfa_engine *e, mfa_graphs *g, const float *d_tid_cost);   // a_w = a_w0 + tid_cost[a_tid] on the device, band copy included
 int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
                          const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld);
 int launch_transpose(mfa_engine *e, const float *d_in, int64_t rows, int64_t cols, int64_t in_ld, float *d_out, int64_t out_ld);

@@ -16,7 +16,7 @@ int set_error(int code, const std::string &msg) { g_last_error = msg; return cod
 using namespace mfa;
 
 extern "C" const char *mfa_last_error(void) { return g_last_error.c_str(); }
-extern "C" int mfa_abi_version(void) { return 1; }
+extern "C" int mfa_abi_version(void) { return 2; }
 
 int mfa_engine::get(int id, size_t bytes, void **out) {
   Buf &b = dev[id];
@@ -230,14 +230,15 @@ extern "C" int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops) {
 // ------------------------------------------------------------------------------------------------ model
 mfa_model::~mfa_model() {
   cudaSetDevice(device);
-  for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_tile_pdf0,
-                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows, (void *)d_tc_g})
+  for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_weights, (void *)d_tile_pdf0,
+                  (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows, (void *)d_tc_g,
+                  (void *)d_first_tid, (void *)d_self_loop_tid, (void *)d_log_probs, (void *)d_tid_cost, (void *)d_tc_flag})
     if (p) cudaFree(p);
 }
 
-int mfa_model::rebuild_tiles() {
-  // greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows; every pdf's column range is padded to a multiple of
-  // MFA_SEG_ALIGN columns (padding = gconst -1e30 / zero weights) so the tensor-core epilogue can work on 4-column groups
+// greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows; every pdf's column range is padded to a multiple of
+// MFA_SEG_ALIGN columns (padding = gconst -1e30 / zero weights) so the tensor-core epilogue can work on 4-column groups
+int mfa_model::layout_tiles() {
   h_tile_pdf0.clear();
   auto padded = [](int ng) { return (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN; };
   int cur = 0, t = -1;
@@ -251,6 +252,30 @@ int mfa_model::rebuild_tiles() {
   n_tiles = t + 1;
   h_tile_pdf0.push_back(num_pdfs);
   kdim = 2 * dim;
+  return MFA_OK;
+}
+
+int mfa_model::ensure_host() {
+  if (!host_stale) return MFA_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = eng->stream;
+  const size_t G = (size_t)num_gauss, D = (size_t)dim;
+  h_gconsts.resize(G); h_miv.resize(G * D); h_iv.resize(G * D);
+  CUDA_TRY(cudaMemcpyAsync(h_gconsts.data(), d_gconsts, G * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_miv.data(), d_miv, G * D * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h_iv.data(), d_iv, G * D * 4, cudaMemcpyDeviceToHost, s));
+  if (d_weights) { h_weights.resize(G); CUDA_TRY(cudaMemcpyAsync(h_weights.data(), d_weights, G * 4, cudaMemcpyDeviceToHost, s)); }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  host_stale = false;
+  return MFA_OK;
+}
+
+// the fp32 CUDA-core kernel's layout ([tile][k][128] weights, per-tile gconsts and segment starts): only the cross-check kernel and
+// models the tcgen05 kernel cannot take need it, so it is built on first use from the host mirrors
+int mfa_model::ensure_ffma() {
+  if (ffma_ready) return MFA_OK;
+  MFA_TRY(ensure_host());
+  auto padded = [](int ng) { return (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN; };
   std::vector<float> W((size_t)n_tiles * kdim * MFA_TILE_N, 0.0f), G((size_t)n_tiles * MFA_TILE_N, -1.0e30f);
   h_tile_seg.assign((size_t)n_tiles * (MFA_TILE_N + 1), MFA_TILE_N);
   h_gauss_col.assign(num_gauss, 0);
@@ -283,9 +308,9 @@ int mfa_model::rebuild_tiles() {
     return MFA_OK;
   };
   MFA_TRY(up(&d_W, W)); MFA_TRY(up(&d_G, G)); MFA_TRY(up(&d_tile_pdf0, h_tile_pdf0)); MFA_TRY(up(&d_tile_seg, h_tile_seg));
-  MFA_TRY(up(&d_gauss_row, grow)); MFA_TRY(up(&d_gconsts, h_gconsts));
+  MFA_TRY(up(&d_gauss_row, grow));
   CUDA_TRY(cudaStreamSynchronize(s));
-  tc_ready = false;
+  ffma_ready = true;
   return MFA_OK;
 }
 
@@ -300,6 +325,7 @@ extern "C" int mfa_model_create(mfa_engine *e, const mfa_model_desc *d, mfa_mode
   m->h_gconsts.assign(d->gconsts, d->gconsts + d->num_gauss);
   m->h_miv.assign(d->means_invvars, d->means_invvars + (size_t)d->num_gauss * d->dim);
   m->h_iv.assign(d->inv_vars, d->inv_vars + (size_t)d->num_gauss * d->dim);
+  if (d->weights) m->h_weights.assign(d->weights, d->weights + d->num_gauss);
   m->h_tid2pdf.assign(d->tid2pdf, d->tid2pdf + d->num_tids + 1);
   for (int t = 1; t <= d->num_tids; t++)
     if (m->h_tid2pdf[t] < 0 || m->h_tid2pdf[t] >= d->num_pdfs) { delete m; return set_error(MFA_ERR_INVALID, "tid2pdf out of range"); }
@@ -313,28 +339,41 @@ extern "C" int mfa_model_create(mfa_engine *e, const mfa_model_desc *d, mfa_mode
   if (!r) r = alloc_up(&m->d_tid2pdf, m->h_tid2pdf);
   if (!r) r = alloc_up(&m->d_miv, m->h_miv);
   if (!r) r = alloc_up(&m->d_iv, m->h_iv);
-  if (!r) r = m->rebuild_tiles();
+  if (!r) r = alloc_up(&m->d_gconsts, m->h_gconsts);
+  if (!r && !m->h_weights.empty()) r = alloc_up(&m->d_weights, m->h_weights);
+  if (!r) r = m->layout_tiles();
+  if (!r) { cudaError_t ce = cudaStreamSynchronize(e->stream); if (ce != cudaSuccess) r = set_error(MFA_ERR_CUDA, cudaGetErrorString(ce)); }
   if (r) { delete m; return r; }
   *out = m;
   return MFA_OK;
 }
 
 extern "C" int mfa_model_destroy(mfa_model *m) {
-  if (m && m->eng) cudaStreamSynchronize(m->eng->stream);
+  // the engine may already be gone (Python tears objects down in any order): never touch m->eng here
+  if (m) { cudaSetDevice(m->device); cudaDeviceSynchronize(); }
   delete m;
   return MFA_OK;
 }
 
+// GmmAligner.boost_silence -> Kaldi gmm-boost-silence: the weights of the given pdfs are scaled WITHOUT renormalisation, i.e.
+// gconst += log(factor)
 extern "C" int mfa_model_boost_pdfs(mfa_model *m, float factor, const int32_t *pdfs, int32_t n) {
   if (!m || (n > 0 && !pdfs) || !(factor > 0.0f)) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(m->eng->device));
+  MFA_TRY(m->ensure_host());
   float lb = logf(factor);
   for (int i = 0; i < n; i++) {
     int p = pdfs[i];
     if (p < 0 || p >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "pdf id out of range");
-    for (int g = m->h_pdf_off[p]; g < m->h_pdf_off[p + 1]; g++) m->h_gconsts[g] += lb;
+    for (int g = m->h_pdf_off[p]; g < m->h_pdf_off[p + 1]; g++) { m->h_gconsts[g] += lb; if (!m->h_weights.empty()) m->h_weights[g] *= factor; }
   }
-  CUDA_TRY(cudaSetDevice(m->eng->device));
-  return m->rebuild_tiles();
+  cudaStream_t s = m->eng->stream;
+  CUDA_TRY(cudaMemcpyAsync(m->d_gconsts, m->h_gconsts.data(), m->h_gconsts.size() * 4, cudaMemcpyHostToDevice, s));
+  if (m->d_weights) CUDA_TRY(cudaMemcpyAsync(m->d_weights, m->h_weights.data(), m->h_weights.size() * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  m->tc_ready = false;
+  m->ffma_ready = false;
+  return MFA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ graphs
@@ -346,6 +385,7 @@ mfa_graphs::~mfa_graphs() {
 namespace mfa {
 int upload_graphs(mfa_engine *e, mfa_graphs *g) {
   if (g->d_blob && g->device == e->device) return MFA_OK;
+  if (g->host_w_stale) return set_error(MFA_ERR_UNSUPPORTED, "these graphs had their transition costs re-folded on another device; pack them again for this one");
   if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
   size_t A = g->a_src.size();
   std::vector<uint32_t> barc(2 * A);
@@ -366,7 +406,8 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
       {g->b_start.data(), g->b_start.size() * 4, (void **)&g->d_b_start}, {g->b_maxback.data(), g->b_maxback.size() * 4, (void **)&g->d_b_maxback},
       {g->b_stw.data(), g->b_stw.size() * 4, (void **)&g->d_b_stw}, {barc.data(), barc.size() * 4, (void **)&g->d_b_arc},
       {g->b_fin.data(), g->b_fin.size() * 4, (void **)&g->d_b_fin},
-      {g->b_arcid.data(), g->b_arcid.size() * 2, (void **)&g->d_b_arcid}, {g->b_orig.data(), g->b_orig.size() * 2, (void **)&g->d_b_orig}};
+      {g->b_arcid.data(), g->b_arcid.size() * 2, (void **)&g->d_b_arcid}, {g->b_orig.data(), g->b_orig.size() * 2, (void **)&g->d_b_orig},
+      {g->a_w0.data(), g->a_w0.size() * 4, (void **)&g->d_a_w0}};
   size_t total = 0;
   for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
   CUDA_TRY(cudaMalloc(&g->d_blob, std::max<size_t>(total, 256)));
@@ -378,6 +419,32 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
     off += (it.bytes + 255) / 256 * 256;
   }
   CUDA_TRY(cudaStreamSynchronize(e->stream));  // `pack` is a local
+  return MFA_OK;
+}
+}  // namespace mfa
+
+namespace {
+// one CTA per utterance: by-source arc weights from the unfolded weights + the per-tid cost, then the band copy (arcs grouped by
+// destination; b_arcid = utterance-local index of the same arc in by-source order)
+__global__ void refold_kernel(const int64_t *__restrict__ arc_off, const int32_t *__restrict__ a_tid, const float *__restrict__ a_w0,
+                              const float *__restrict__ tid_cost, const uint16_t *__restrict__ b_arcid, float *__restrict__ a_w, uint2 *__restrict__ b_arc) {
+  const int64_t a0 = arc_off[blockIdx.x], A = arc_off[blockIdx.x + 1] - a0;
+  for (int64_t k = threadIdx.x; k < A; k += blockDim.x) {
+    const int tid = a_tid[a0 + k];
+    a_w[a0 + k] = tid > 0 ? a_w0[a0 + k] + tid_cost[tid] : a_w0[a0 + k];
+  }
+  __syncthreads();
+  for (int64_t j = threadIdx.x; j < A; j += blockDim.x) b_arc[a0 + j].y = __float_as_uint(a_w[a0 + b_arcid[a0 + j]]);
+}
+}  // namespace
+
+namespace mfa {
+int refold_graphs(mfa_engine *e, mfa_graphs *g, const float *d_tid_cost) {
+  if (g->n_utts == 0) return MFA_OK;
+  refold_kernel<<<(unsigned)g->n_utts, 256, 0, e->stream>>>(g->d_arc_off, g->d_a_tid, g->d_a_w0, d_tid_cost, g->d_b_arcid, g->d_a_w, (uint2 *)g->d_b_arc);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  g->host_w_stale = true;
   return MFA_OK;
 }
 }  // namespace mfa

@@ -97,6 +97,7 @@ namespace mfa {
 int launch_gmm_ffma(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_rows, float *d_llT, int64_t ld) {
   if (n_rows == 0) return MFA_OK;
   if (ld < n_rows) return set_error(MFA_ERR_INVALID, "ld < n_rows");
+  MFA_TRY(m->ensure_ffma());
   size_t smem = ((size_t)m->kdim * TM + (size_t)m->kdim * TN + (size_t)TM * CLD) * sizeof(float);
   if (smem > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "GMM tile exceeds shared memory");
   CUDA_TRY(cudaFuncSetAttribute(gmm_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

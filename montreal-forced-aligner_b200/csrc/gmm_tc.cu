@@ -397,58 +397,95 @@ gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int3
 // the dense per-tile gconst array follows the per-Gaussian one; bulk copies need a 16-byte aligned source
 static inline size_t tc_gpad(int64_t G) { return (size_t)((G + 3) & ~(int64_t)3); }
 
-// host: fp16 hi/lo weight rows [2][G][96] (row-major, for gathering) and the dense tile images + per-tile segment masks
-int build_tc(mfa_model *m) {
-  const int D = m->dim;
-  const bool k80 = 2 * D <= 80 && !m->eng->cfg.tc_k96;
-  if (!k80 && 2 * D + 3 > 96) return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96");
+// ---- operand images from the device-resident natural-layout parameters (model creation and after every device M-step) ----
+// second moments about zero per dimension (features are not re-centred): m2[d] += mu^2 + sigma^2 over the Gaussians
+__global__ void __launch_bounds__(128)
+tc_moment_kernel(const float *__restrict__ miv, const float *__restrict__ iv, int G, int D, double *__restrict__ m2) {
+  const int d = threadIdx.x;
+  if (d >= D) return;
+  double acc = 0.0;
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const double v = (double)iv[(size_t)g * D + d], mu = (double)miv[(size_t)g * D + d] / v;
+    acc += mu * mu + 1.0 / v;
+  }
+  atomicAdd(&m2[d], acc);
+}
+// per-dimension power-of-two feature scale: x * s has unit order, so x s and (x s)^2 sit inside fp16's range
+__global__ void tc_colscale_kernel(const double *__restrict__ m2, int G, int D, float *__restrict__ colscale) {
+  const int d = threadIdx.x;
+  if (d >= D) return;
+  const double rms = sqrt(fmax(m2[d] / G, 1e-30));
+  colscale[d] = (float)exp2(-round(log2(rms)));
+}
+// fp16 hi / lo weight rows [2][G][TK] (row-major: the source of every tile gather) and gconst * log2(e) per Gaussian
+__global__ void tc_rows_kernel(const float *__restrict__ miv, const float *__restrict__ iv, const float *__restrict__ gconsts,
+                               const float *__restrict__ colscale, int G, int D, int TK, int k80, __half *__restrict__ rows,
+                               float *__restrict__ gl2, int32_t *__restrict__ flag) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * TK) return;
+  const int g = (int)(idx / TK), k = (int)(idx - (int64_t)g * TK);
+  double gc = (double)gconsts[g] * (double)kLog2e;
+  if (!(gc > -60000.0)) gc = -60000.0;
+  if (k == 0) gl2[g] = (float)gc;
+  __half hi = __float2half_rn(0.0f), lo = hi;
+  if (k < 2 * D) {
+    const int d = k < D ? k : k - D;
+    const double s = (double)colscale[d];
+    const double w = k < D ? (double)miv[(size_t)g * D + d] / s * (double)kLog2e : -0.5 * (double)iv[(size_t)g * D + d] / (s * s) * (double)kLog2e;
+    hi = __float2half_rn((float)w);
+    lo = __float2half_rn((float)(w - (double)__half2float(hi)));
+    if (fabs(w) > 60000.0) *flag = 1;
+  } else if (!k80 && k < 2 * D + 3) {   // K = 96 geometry: the gconst as three fp16 columns against ones
+    const float g1 = __half2float(__float2half_rn((float)gc));
+    const float g2 = __half2float(__float2half_rn((float)(gc - g1)));
+    const float g3 = (float)(gc - g1 - g2);
+    hi = __float2half_rn(k == 2 * D ? g1 : (k == 2 * D + 1 ? g2 : g3));
+  }
+  rows[((size_t)0 * G + g) * TK + k] = hi;
+  rows[((size_t)1 * G + g) * TK + k] = lo;
+}
+
+}  // namespace
+
+namespace mfa {
+int build_tc_device(mfa_model *m, bool layout_changed) {
+  const int D = m->dim, G = m->num_gauss;
+  mfa_engine *e = m->eng;
+  const bool k80 = 2 * D <= 80 && !e->cfg.tc_k96;
+  m->tc_ready = false;
+  if (!k80 && 2 * D + 3 > 96) { m->tc_unsupported = true; return set_error(MFA_ERR_UNSUPPORTED, "tensor-core GMM kernel needs 2*dim+3 <= 96"); }
   const int TK = k80 ? 80 : 96, KC = TK / 8;
   const uint32_t TILE_BYTES = tile_bytes(TK);
+  const bool geometry_changed = m->tc_k != TK;
   m->tc_k = TK;
-  std::vector<double> m2(D, 0.0);
-  for (int g = 0; g < m->num_gauss; g++)
-    for (int d = 0; d < D; d++) {
-      double iv = m->h_iv[(size_t)g * D + d], mu = m->h_miv[(size_t)g * D + d] / iv;
-      m2[d] += mu * mu + 1.0 / iv;
-    }
-  m->h_tc_colscale.assign(D, 1.0f);
-  for (int d = 0; d < D; d++) {
-    double rms = std::sqrt(std::max(m2[d] / m->num_gauss, 1e-30));  // second moment about 0: features are not re-centred
-    m->h_tc_colscale[d] = (float)std::exp2(-std::round(std::log2(rms)));
-  }
   const int nt = m->n_tiles;
-  const int G = m->num_gauss;
-  std::vector<__half> rows((size_t)2 * G * TK, __float2half_rn(0.0f));
-  double wmax = 0.0;
-  std::vector<float> gl2(G);   // gconst * log2(e) per Gaussian (K = 80: added by the epilogue in fp32)
-  auto split2 = [&](int g, int k, double w) {
-    __half h = __float2half_rn((float)w);
-    rows[((size_t)0 * G + g) * TK + k] = h;
-    rows[((size_t)1 * G + g) * TK + k] = __float2half_rn((float)(w - (double)__half2float(h)));
-    wmax = std::max(wmax, std::fabs(w));
-  };
-  for (int g = 0; g < G; g++) {
-    for (int d = 0; d < D; d++) {
-      double s = m->h_tc_colscale[d];
-      split2(g, d, (double)m->h_miv[(size_t)g * D + d] / s * kLog2e);
-      split2(g, D + d, -0.5 * (double)m->h_iv[(size_t)g * D + d] / (s * s) * kLog2e);
-    }
-    double gc = (double)m->h_gconsts[g] * kLog2e;
-    if (!(gc > -60000.0)) gc = -60000.0;
-    gl2[g] = (float)gc;
-    if (!k80) {
-      float g1 = __half2float(__float2half_rn((float)gc));
-      float g2 = __half2float(__float2half_rn((float)(gc - g1)));
-      float g3 = (float)(gc - g1 - g2);
-      rows[(size_t)g * TK + 2 * D] = __float2half_rn(g1);
-      rows[(size_t)g * TK + 2 * D + 1] = __float2half_rn(g2);
-      rows[(size_t)g * TK + 2 * D + 2] = __float2half_rn(g3);
-    }
+  cudaStream_t s = e->stream;
+  if (!m->d_tc_colscale) CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, 64 * sizeof(float)));
+  if (!m->d_tc_flag) CUDA_TRY(cudaMalloc((void **)&m->d_tc_flag, 64 * sizeof(double) + 16));   // flag | m2[64]
+  double *d_m2 = (double *)((uint8_t *)m->d_tc_flag + 16);
+  CUDA_TRY(cudaMemsetAsync(m->d_tc_flag, 0, 64 * sizeof(double) + 16, s));
+  if ((size_t)G > m->tc_cap_gauss || geometry_changed || !m->d_tc_rows || (layout_changed && m->d_tc_w)) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (void **p : {&m->d_tc_rows, (void **)&m->d_tc_g, &m->d_tc_w}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+    m->tc_cap_gauss = (size_t)G + (size_t)G / 8 + 64;
   }
-  if (wmax > 60000.0) return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel");
-  // dense tiling (all pdfs): per-tile masks + source rows; the images themselves are gathered on the device
-  std::vector<TcMeta> meta(nt);
+  const size_t img_total = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
+  const bool new_dense = m->d_tc_w == nullptr;
+  if (!m->d_tc_rows) CUDA_TRY(cudaMalloc(&m->d_tc_rows, (size_t)2 * m->tc_cap_gauss * TK * sizeof(__half)));
+  // per Gaussian | dense per-tile array: the tile count can only be bounded by the number of pdfs
+  if (!m->d_tc_g) CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, (tc_gpad((int64_t)m->tc_cap_gauss) + (size_t)m->num_pdfs * TN + TN) * sizeof(float)));
+  if (new_dense) CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + meta_bytes));
+  m->tc_w_bytes = img_total;
+  tc_moment_kernel<<<std::min(G, 4 * e->sm_count), 128, 0, s>>>(m->d_miv, m->d_iv, G, D, d_m2);
+  tc_colscale_kernel<<<1, 64, 0, s>>>(d_m2, G, D, m->d_tc_colscale);
+  const int64_t tot = (int64_t)G * TK;
+  tc_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m->d_miv, m->d_iv, m->d_gconsts, m->d_tc_colscale, G, D, TK, k80 ? 1 : 0,
+                                                              (__half *)m->d_tc_rows, m->d_tc_g, m->d_tc_flag);
+  e->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  // dense tiling (all pdfs): per-tile masks + source rows from the host's copy of the layout; the images are gathered on the device
   std::vector<int32_t> row_src((size_t)nt * TN, -1);
+  std::vector<TcMeta> meta(nt);
   for (int tl = 0; tl < nt; tl++) {
     int col = 0;
     memset(&meta[tl], 0, sizeof(TcMeta));
@@ -462,27 +499,18 @@ int build_tc(mfa_model *m) {
     }
     if (col < TN) meta[tl].gstart |= 1u << (col / 4);  // trailing padding: one junk segment that never ends
   }
-  cudaStream_t s = m->eng->stream;
-  if (m->d_tc_w) { CUDA_TRY(cudaStreamSynchronize(s)); CUDA_TRY(cudaFree(m->d_tc_w)); m->d_tc_w = nullptr; }
-  if (m->d_tc_colscale) { CUDA_TRY(cudaFree(m->d_tc_colscale)); m->d_tc_colscale = nullptr; }
-  if (m->d_tc_rows) { CUDA_TRY(cudaFree(m->d_tc_rows)); m->d_tc_rows = nullptr; }
-  if (m->d_tc_g) { CUDA_TRY(cudaFree(m->d_tc_g)); m->d_tc_g = nullptr; }
-  const size_t img_total = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
-  m->tc_w_bytes = img_total;
-  CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + meta_bytes));
-  CUDA_TRY(cudaMalloc(&m->d_tc_rows, rows.size() * sizeof(__half)));
-  CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, (tc_gpad(G) + (size_t)nt * TN) * sizeof(float)));   // per Gaussian | dense per-tile array
-  CUDA_TRY(cudaMemcpyAsync(m->d_tc_g, gl2.data(), (size_t)G * sizeof(float), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(m->d_tc_rows, rows.data(), rows.size() * sizeof(__half), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, meta.data(), meta_bytes, cudaMemcpyHostToDevice, s));
-  int32_t *d_src;
-  MFA_TRY(m->eng->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
+  int32_t *d_src; TcMeta *d_meta_stage;
+  MFA_TRY(e->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
+  MFA_TRY(e->upload(DB_TC_ITEMS, meta.data(), meta.size(), &d_meta_stage));
+  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, d_meta_stage, meta_bytes, cudaMemcpyDeviceToDevice, s));
   gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D,
-                                                                   KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad(G) : nullptr);
-  m->eng->launches++;
-  CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, D * sizeof(float)));
-  CUDA_TRY(cudaMemcpyAsync(m->d_tc_colscale, m->h_tc_colscale.data(), D * sizeof(float), cudaMemcpyHostToDevice, s));
+                                                    KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss) : nullptr);
+  e->launches++;
+  int32_t h_flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_flag, m->d_tc_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (h_flag) { m->tc_unsupported = true; return set_error(MFA_ERR_UNSUPPORTED, "model weights exceed the fp16 range of the tensor-core kernel"); }
+  m->tc_unsupported = false;
   // The per-utterance tile plan cached in mfa_graphs depends only on how many Gaussians each pdf has (and on the geometry), not on the
   // parameter values: key it on a hash of that layout, so that a re-estimated model with an unchanged layout (the usual case between
   // training iterations once pruning and mix-up have settled, and for the .alimdl / .mdl pair of a two-pass alignment) reuses the plan.
@@ -492,6 +520,9 @@ int build_tc(mfa_model *m) {
   m->tc_ready = true;
   return MFA_OK;
 }
+}  // namespace mfa
+
+namespace {
 
 int launch_tc(mfa_engine *e, const TcParams &p, int tk) {
   const int grid = std::min(p.n_items, e->sm_count);
@@ -514,7 +545,7 @@ int launch_tc(mfa_engine *e, const TcParams &p, int tk) {
 namespace mfa {
 
 bool gmm_tc_supported(mfa_model *m) {
-  if (!m->tc_ready) { if (build_tc(m) != MFA_OK) return false; }
+  if (!m->tc_ready) { if (m->tc_unsupported || build_tc_device(m, true) != MFA_OK) return false; }
   return true;
 }
 
@@ -523,7 +554,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   if (n_rows == 0) return MFA_OK;
   if (ld < n_rows) return set_error(MFA_ERR_INVALID, "ld < n_rows");
   if (!m->tc_ready) {
-    int r = build_tc(m);
+    int r = m->tc_unsupported ? MFA_ERR_UNSUPPORTED : build_tc_device(m, true);
     if (r == MFA_ERR_UNSUPPORTED) return launch_gmm_ffma(e, m, d_feats, n_rows, d_llT, ld);  // shapes the tcgen05 kernel does not cover
     if (r) return r;
   }
@@ -555,7 +586,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   TcParams p;
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
-  p.g_tiles = m->d_tc_g + tc_gpad(m->num_gauss);
+  p.g_tiles = m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss);
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
   return launch_tc(e, p, TK);
 }
@@ -565,7 +596,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
 int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
                          const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld) {
   if (n_utts == 0) return MFA_OK;
-  if (!m->tc_ready) MFA_TRY(build_tc(m));
+  if (!m->tc_ready) MFA_TRY(build_tc_device(m, true));
   const int TK = m->tc_k, KC = TK / 8;
   const uint32_t TILE_BYTES = tile_bytes(TK);
   // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles

@@ -649,7 +649,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
   // utterance, 0.78 s for the 10 h workload when serial): everything of one utterance goes into its own PackedUtt.
   struct PackedUtt {
     std::vector<int32_t> inb, a_src, a_dst, a_lp, a_tid, a_olabel, pdfs;
-    std::vector<float> a_w;
+    std::vector<float> a_w, a_w0;
     int32_t n_eps = 0, words = 0;
     bool ok = false;
     BandOut bo;
@@ -674,12 +674,13 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     const int maxpdf = P.pdfs.empty() ? 0 : P.pdfs.back();
     if ((int)lpmap.size() <= maxpdf) lpmap.resize(maxpdf + 1);
     for (size_t k = 0; k < P.pdfs.size(); k++) lpmap[P.pdfs[k]] = (int32_t)k;
-    P.a_src.resize(A); P.a_dst.resize(A); P.a_lp.resize(A); P.a_tid.resize(A); P.a_olabel.resize(A); P.a_w.resize(A);
+    P.a_src.resize(A); P.a_dst.resize(A); P.a_lp.resize(A); P.a_tid.resize(A); P.a_olabel.resize(A); P.a_w.resize(A); P.a_w0.resize(A);
     for (int64_t k = 0; k < A; k++) {
       const int64_t a = a0 + order[k];
       const int il = b.il[a];
       P.a_src[k] = b.src[a]; P.a_dst[k] = b.dst[a]; P.a_tid[k] = il; P.a_olabel[k] = b.ol[a];
       if (b.ol[a] != 0) P.words++;   // loose bound (a path crosses each labelled arc at most once in an acyclic word graph)
+      P.a_w0[k] = b.w[a];
       if (il > 0) { P.a_w[k] = b.w[a] + tid_cost[il]; P.a_lp[k] = lpmap[tid2pdf[il]]; }
       else { P.a_w[k] = b.w[a]; P.a_lp[k] = -1; P.n_eps++; }
     }
@@ -699,6 +700,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
   // Phase 2: concatenate
   auto *g = new mfa_graphs();
   g->n_utts = n;
+  g->num_tids = num_tids;
   g->st_off.assign(n + 1, 0); g->arc_off.assign(n + 1, 0); g->lp_off.assign(n + 1, 0); g->inb_off.assign(n + 1, 0);
   g->start.resize(n); g->n_eps.assign(n, 0); g->max_words.assign(n, 0);
   for (int u = 0; u < n; u++) {
@@ -708,7 +710,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
   }
   const size_t TS = (size_t)g->st_off[n], TA = (size_t)g->arc_off[n];
   g->in_begin.resize((size_t)g->inb_off[n]); g->lp2pdf.resize((size_t)g->lp_off[n]);
-  g->a_src.resize(TA); g->a_dst.resize(TA); g->a_lp.resize(TA); g->a_tid.resize(TA); g->a_olabel.resize(TA); g->a_w.resize(TA);
+  g->a_src.resize(TA); g->a_dst.resize(TA); g->a_lp.resize(TA); g->a_tid.resize(TA); g->a_olabel.resize(TA); g->a_w.resize(TA); g->a_w0.resize(TA);
   g->final_w.assign(b.finals.begin(), b.finals.begin() + TS);
   g->band_ok.resize(n); g->b_start.resize(n); g->b_maxback.resize(n);
   g->b_stw.resize(TS); g->b_fin.resize(TS); g->b_orig.resize(TS); g->b_apk.resize(TA); g->b_aw.resize(TA); g->b_arcid.resize(TA);
@@ -721,6 +723,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     std::copy(P.a_src.begin(), P.a_src.end(), g->a_src.begin() + ao); std::copy(P.a_dst.begin(), P.a_dst.end(), g->a_dst.begin() + ao);
     std::copy(P.a_lp.begin(), P.a_lp.end(), g->a_lp.begin() + ao); std::copy(P.a_tid.begin(), P.a_tid.end(), g->a_tid.begin() + ao);
     std::copy(P.a_olabel.begin(), P.a_olabel.end(), g->a_olabel.begin() + ao); std::copy(P.a_w.begin(), P.a_w.end(), g->a_w.begin() + ao);
+    std::copy(P.a_w0.begin(), P.a_w0.end(), g->a_w0.begin() + ao);
     g->band_ok[u] = P.ok ? 1 : 0; g->b_start[u] = P.ok ? P.bo.start : -1; g->b_maxback[u] = P.ok ? P.bo.maxback : 0;
     std::copy(P.bo.stw.begin(), P.bo.stw.end(), g->b_stw.begin() + so); std::copy(P.bo.fin.begin(), P.bo.fin.end(), g->b_fin.begin() + so);
     std::copy(P.bo.orig.begin(), P.bo.orig.end(), g->b_orig.begin() + so); std::copy(P.bo.apk.begin(), P.bo.apk.end(), g->b_apk.begin() + ao);

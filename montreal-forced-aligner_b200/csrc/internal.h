@@ -43,6 +43,12 @@ struct mfa_graphs {
   float *d_b_fin = nullptr;
   uint16_t *d_b_arcid = nullptr, *d_b_orig = nullptr;
   float *d_a_w = nullptr, *d_final_w = nullptr;
+  // graph weights WITHOUT the AddTransitionProbs cost (a_w = a_w0 + tid_cost[a_tid]): what mfa_graphs_set_transitions re-folds on the
+  // device when the transition model has been re-estimated.  After a re-fold the host copies of a_w / b_aw are stale.
+  int32_t num_tids = 0;
+  std::vector<float> a_w0;
+  float *d_a_w0 = nullptr;
+  bool host_w_stale = false;
   // per-utterance Gaussian tiling for the ragged K2 path (cached against the model's tiling version)
   uint64_t rag_version = 0;
   std::vector<int64_t> rag_tile_off;

@@ -254,16 +254,23 @@ def make_feat_opts(in_dim, mode, lda, splice_ctx, fmllr, cmvn_stats, n_spk):
 class DeviceModel:
     """Device-resident AmDiagGmm + tid->pdf map (mfa_model)."""
 
-    def __init__(self, engine: Engine, tm: TransitionModel, am: AmDiagGmm):
+    def __init__(self, engine: Engine, tm: Optional[TransitionModel], am: AmDiagGmm):
+        """tm may be None for a bare AmDiagGmm (M-step of host-side accumulators): no transition-ids, nothing to align."""
         self.engine = engine
+        if tm is None:
+            class _NoTm:
+                tid2pdf = np.zeros(1, np.int32)
+                num_tids = 0
+            tm = _NoTm()
         self.tm, self.am = tm, am
         self._arrs = [np.ascontiguousarray(am.offsets, dtype=np.int32), np.ascontiguousarray(am.gconsts, dtype=np.float32),
                       np.ascontiguousarray(am.means_invvars, dtype=np.float32), np.ascontiguousarray(am.inv_vars, dtype=np.float32),
-                      np.ascontiguousarray(np.maximum(tm.tid2pdf, 0), dtype=np.int32)]
+                      np.ascontiguousarray(np.maximum(tm.tid2pdf, 0), dtype=np.int32), np.ascontiguousarray(am.weights, dtype=np.float32)]
         d = L.ModelDesc(am.dim, am.NumPdfs(), am.NumGauss(), tm.num_tids, *[a.ctypes.data_as(C.c_void_p).value for a in self._arrs])
         self._h = C.c_void_p()
         L.check(L.lib().mfa_model_create(engine._h, C.byref(d), C.byref(self._h)))
         self.dim, self.num_pdfs, self.num_gauss, self.num_tids = am.dim, am.NumPdfs(), am.NumGauss(), tm.num_tids
+        self._trans_set = False
 
     def close(self):
         if self._h:
@@ -292,6 +299,44 @@ class DeviceModel:
         k2, op, _ = _buf(out, np.float32)
         L.check(L.lib().mfa_gmm_loglikes(self.engine._h, self._h, fp, C.c_int64(T), op, C.c_int(where), C.c_int(impl)))
         return out
+
+    # ---- N3: M-step on the device
+    def set_transitions(self, tm: Optional[TransitionModel] = None):
+        """mfa_model_set_transitions: transition-state tables + current log-probabilities (needed to re-estimate transitions on the
+        device and to re-fold them into packed graphs)."""
+        tm = tm or self.tm
+        arrs = [np.ascontiguousarray(tm.state2id, np.int32), np.ascontiguousarray(tm.self_loop_tid, np.int32),
+                np.ascontiguousarray(tm.log_probs, np.float32)]
+        d = L.TransDesc(int(tm.tuples.shape[0]), *[a.ctypes.data_as(C.c_void_p).value for a in arrs])
+        L.check(L.lib().mfa_model_set_transitions(self._h, C.byref(d)))
+        self._trans_set = True
+
+    def mle_update(self, mixup: int = 0, power: float = 0.25, min_gaussian_occupancy: float = 10.0, min_gaussian_weight: float = 1.0e-5,
+                   min_variance: float = 0.001, remove_low_count_gaussians: bool = True, perturb_factor: float = 0.01, min_count: float = 20.0,
+                   update_transitions: bool = False, transition_floor: float = 0.01, transition_mincount: float = 5.0, seed: int = 1234) -> dict:
+        """mfa_model_mle_update: the model is re-estimated in place from its (all-reduced) device accumulators; returns the result
+        struct as a dict.  ``self.am`` / ``self.tm`` are NOT touched: call ``read()`` for host copies of the new parameters."""
+        if update_transitions and not self._trans_set:
+            self.set_transitions()
+        o = L.MleOpts(float(min_gaussian_occupancy), float(min_gaussian_weight), float(min_variance), int(bool(remove_low_count_gaussians)),
+                      int(mixup or 0), float(power), float(min_count), float(perturb_factor), int(bool(update_transitions)),
+                      float(transition_floor), float(transition_mincount), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        r = L.MleResult()
+        L.check(L.lib().mfa_model_mle_update(self.engine._h, self._h, C.byref(o), C.byref(r)))
+        self.num_gauss = int(r.num_gauss_after)
+        return {k: getattr(r, k) for k, _ in L.MleResult._fields_}
+
+    def read(self, with_transitions: bool = False):
+        """mfa_model_read: host AmDiagGmm of the current device parameters (+ the transition log-probabilities)."""
+        G, D = int(L.lib().mfa_model_num_gauss(self._h)), self.dim
+        off, w, gc = np.zeros(self.num_pdfs + 1, np.int32), np.zeros(G, np.float32), np.zeros(G, np.float32)
+        miv, iv = np.zeros((G, D), np.float32), np.zeros((G, D), np.float32)
+        lp = np.zeros(self.num_tids + 1, np.float32) if with_transitions else None
+        L.check(L.lib().mfa_model_read(self.engine._h, self._h, *[a.ctypes.data_as(C.c_void_p) for a in (off, w, gc, miv, iv)],
+                                       lp.ctypes.data_as(C.c_void_p) if lp is not None else None))
+        am = AmDiagGmm(D, off, w, miv, iv)
+        am.device_gconsts = gc
+        return (am, lp) if with_transitions else am
 
     # ---- K4
     def acc_size(self) -> int:
@@ -352,6 +397,19 @@ class DeviceModel:
         out = np.zeros(self.acc_size(), dtype=np.float64)
         L.check(L.lib().mfa_acc_read(self.engine._h, self._h, out.ctypes.data_as(C.c_void_p)))
         return self.split_accs(out)
+
+    def acc_write(self, occ, mean, var, trans=None, like: float = 0.0, frames: float = 0.0):
+        """mfa_acc_write: host accumulators (kalpy-style objects summed on the host) -> the device block."""
+        G, D, nt = self.num_gauss, self.dim, self.num_tids
+        flat = np.zeros(self.acc_size(), np.float64)
+        flat[:G] = occ
+        flat[G:G + G * D] = np.asarray(mean, np.float64).reshape(-1)
+        flat[G + G * D:G + 2 * G * D] = np.asarray(var, np.float64).reshape(-1)
+        o = G + 2 * G * D
+        if trans is not None:
+            flat[o:o + nt + 1] = trans
+        flat[o + nt + 1], flat[o + nt + 2] = like, frames
+        L.check(L.lib().mfa_acc_write(self.engine._h, self._h, flat.ctypes.data_as(C.c_void_p)))
 
     def split_accs(self, flat: np.ndarray) -> dict:
         G, D, nt = self.num_gauss, self.dim, self.num_tids
@@ -501,6 +559,10 @@ class Graphs:
         L.check(L.lib().mfa_graphs_pack(batch._h, tid_cost.ctypes.data_as(C.c_void_p), tid2pdf.ctypes.data_as(C.c_void_p),
                                         C.c_int32(tm.num_tids), C.byref(self._h)))
         self.n_utts = batch.sizes()[0]
+
+    def set_transitions(self, engine: "Engine", model: "DeviceModel", transition_scale: float = 1.0, self_loop_scale: float = 0.1):
+        """mfa_graphs_set_transitions: AddTransitionProbs again, on the device, from the model's current transition log-probabilities."""
+        L.check(L.lib().mfa_graphs_set_transitions(engine._h, self._h, model._h, C.c_float(transition_scale), C.c_float(self_loop_scale)))
 
     def offsets(self):
         """(state_off, arc_off, pdf_off): per-utterance prefix offsets of states / arcs / distinct pdfs."""

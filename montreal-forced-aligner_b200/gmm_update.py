@@ -1,23 +1,19 @@
-"""Host-side M-step for the align -> acc-stats -> update loop (row a10 / N3 of SURVEY.md section 8).
+"""Accumulator container and M-step entry point of the align -> acc-stats -> update loop (rows a10 / N3 of SURVEY.md section 8).
 
-Restates Kaldi gmm/mle-diag-gmm.cc ``MleDiagGmmUpdate``, gmm/mle-am-diag-gmm.cc ``MleAmDiagGmmUpdate``,
-gmm/am-diag-gmm.cc ``SplitByCount`` / ``GetSplitTargets`` and gmm/diag-gmm.cc ``Split`` as called by the reference at
-montreal_forced_aligner/acoustic_modeling/base.py:319-338 (upstream ``acc_stats``):
-``am.mle_update(gmm_accs, mixup=current_gaussians, power=power)``.
-
-The accumulators come from the CUDA K4 kernel (f64, summed across GPUs with an NCCL all-reduce); this update is small
-(G x D float64) and runs in numpy.  ``SplitByCount`` perturbs means with Gaussian noise, so model parity across
-iterations with Kaldi is statistical (hard part 8); the RNG here is seeded.
+``am.mle_update(gmm_accs, mixup=current_gaussians, power=power)`` of the reference (montreal_forced_aligner/acoustic_modeling/base.py:
+319-338 upstream, monophone.py:275-296) runs on the DEVICE here: the accumulators are written into the model's f64 block (or are already
+there, all-reduced over NCCL, in the in-memory training loop), ``mfa_model_mle_update`` (csrc/mstep.cu: Kaldi MleDiagGmmUpdate /
+MleAmDiagGmmUpdate, SplitByCount + Split, TransitionModel::MleUpdate) re-estimates the model in place and rebuilds the K2 operand images,
+and the new parameters are read back only when a file ({it+1}.mdl) has to be written.  There is no host fallback; the numpy restatement
+used to check the kernels lives in oracle/mstep_oracle.py (test infrastructure).
 """
 from __future__ import annotations
 
-import heapq
-import math
 from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-from .kaldi_io import AmDiagGmm
+from .kaldi_io import AmDiagGmm, TransitionModel
 
 
 class AccumAmDiagGmm:
@@ -56,104 +52,31 @@ class AccumAmDiagGmm:
         return float(self.occ.sum())
 
 
-def _gmm_objf(am: AmDiagGmm, acc: AccumAmDiagGmm) -> float:
-    """MlObjective of mle-diag-gmm.cc summed over pdfs: sum_m occ*gconst + mean_acc.means_invvars - 0.5 var_acc.inv_vars."""
-    return float((acc.occ * am.gconsts.astype(np.float64)).sum() + (acc.mean * am.means_invvars).sum() - 0.5 * (acc.var * am.inv_vars).sum())
-
-
 def mle_update(am: AmDiagGmm, acc: AccumAmDiagGmm, mixup: int = 0, power: float = 0.25, min_gaussian_occupancy: float = 10.0,
                min_gaussian_weight: float = 1.0e-5, min_variance: float = 0.001, remove_low_count_gaussians: bool = True,
-               perturb_factor: float = 0.01, min_count: float = 20.0, seed: int = 1234) -> Tuple[AmDiagGmm, float, float]:
-    """Returns (new model, objective improvement, total count).  Updates means, variances and weights.
-    Vectorised over all Gaussians (segment sums per pdf with np.add.reduceat); only mix-up walks pdfs one by one."""
-    D, P = am.dim, am.NumPdfs()
-    objf_before = _gmm_objf(am, acc)
-    off = np.asarray(am.offsets, dtype=np.int64)
-    n_per = np.diff(off)
-    pdf_of = np.repeat(np.arange(P), n_per)
-    occ = acc.occ
-    state_occs = np.add.reduceat(occ, off[:-1]) if P else np.zeros(0)
-    state_occs[n_per == 0] = 0.0
-    prob = np.where(state_occs[pdf_of] > 0, occ / np.where(state_occs[pdf_of] > 0, state_occs[pdf_of], 1.0), 1.0 / n_per[pdf_of])
-    upd = (occ > min_gaussian_occupancy) & (prob > min_gaussian_weight)
-    w = am.weights.astype(np.float64).copy()
-    mu, var = am.means().copy(), am.variances().copy()
-    safe = np.where(upd, occ, 1.0)[:, None]
-    m_new = acc.mean / safe
-    v_new = np.maximum(acc.var / safe - m_new * m_new, min_variance)
-    mu[upd], var[upd], w[upd] = m_new[upd], v_new[upd], prob[upd]
-    if remove_low_count_gaussians:
-        keep = upd.copy()
-        none = np.add.reduceat(keep.astype(np.int64), off[:-1]) == 0
-        for j in np.nonzero(none)[0]:   # MleDiagGmmUpdate walks the components in order and refuses to remove the only one left:
-            keep[off[j + 1] - 1] = True   # the LAST index survives (un-updated)
-    else:
-        keep = np.ones_like(upd)
-        w[~upd] = prob[~upd]
-    w, mu, var = w[keep], mu[keep], var[keep]
-    new_n = np.add.reduceat(keep.astype(np.int64), off[:-1])
-    new_off = np.zeros(P + 1, dtype=np.int64)
-    new_off[1:] = np.cumsum(new_n)
-    w = w / np.repeat(np.add.reduceat(w, new_off[:-1]), new_n)
-    out = AmDiagGmm(D, new_off.astype(np.int32), w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))
-    objf_after = None
-    if out.NumGauss() == am.NumGauss():
-        objf_after = _gmm_objf(out, acc)
-    if mixup and mixup > out.NumGauss():
-        out = split_by_count(out, state_occs, mixup, perturb_factor, power, min_count, seed)
-    count = acc.TotCount()
-    impr = (objf_after - objf_before) if objf_after is not None else float("nan")
-    return out, impr, count
-
-
-def get_split_targets(state_occs: np.ndarray, target_components: int, power: float, min_count: float) -> np.ndarray:
-    """am-diag-gmm.cc GetSplitTargets: greedy allocation by occupancy^power / num_components."""
-    n = state_occs.shape[0]
-    comps = np.ones(n, dtype=np.int64)
-    occp = np.power(np.maximum(state_occs, 0.0), power)
-    heap = [(-occp[j] / (1 + 1.0e-10), j) for j in range(n)]
-    heapq.heapify(heap)
-    num = n
-    dead = np.zeros(n, dtype=bool)
-    while num < target_components and heap:
-        negkey, j = heapq.heappop(heap)
-        if negkey == 0.0 or dead[j]:
-            break
-        if (comps[j] + 1) * min_count >= state_occs[j]:
-            dead[j] = True
-            heapq.heappush(heap, (0.0, j))
+               perturb_factor: float = 0.01, min_count: float = 20.0, seed: int = 1234, tm: Optional[TransitionModel] = None,
+               transition_accs: Optional[np.ndarray] = None, engine=None) -> Tuple[AmDiagGmm, float, float]:
+    """kalpy ``AmDiagGmm.mle_update(accs, mixup=, power=, min_gaussian_occupancy=, ...)`` for host-resident accumulators (the file-based
+    flow, where jobs hand their statistics back through callbacks): upload -> device M-step -> read back.  With ``tm`` and
+    ``transition_accs`` the transition model is re-estimated in the same call (``tm.log_probs`` updated in place).
+    Returns (new model, objective improvement, total count)."""
+    from . import engine as E
+    from .kalpy_compat import get_engine
+    eng = engine or get_engine()
+    dm = E.DeviceModel(eng, tm, am)
+    try:
+        dm.acc_zero()
+        dm.acc_write(acc.occ, acc.mean, acc.var, trans=transition_accs if tm is not None else None, like=acc.tot_like, frames=acc.tot_frames)
+        upd_t = tm is not None and transition_accs is not None
+        r = dm.mle_update(mixup=mixup, power=power, min_gaussian_occupancy=min_gaussian_occupancy, min_gaussian_weight=min_gaussian_weight,
+                          min_variance=min_variance, remove_low_count_gaussians=remove_low_count_gaussians, perturb_factor=perturb_factor,
+                          min_count=min_count, update_transitions=upd_t, seed=seed)
+        if upd_t:
+            new_am, lp = dm.read(with_transitions=True)
+            tm.log_probs = lp.astype(np.float32)
+            tm._derive()
         else:
-            comps[j] += 1
-            num += 1
-            heapq.heappush(heap, (-occp[j] / (comps[j] + 1.0e-10), j))
-    return comps
-
-
-def split_by_count(am: AmDiagGmm, state_occs: np.ndarray, target_components: int, perturb_factor: float = 0.01, power: float = 0.25,
-                   min_count: float = 20.0, seed: int = 1234) -> AmDiagGmm:
-    """AmDiagGmm::SplitByCount -> DiagGmm::Split (heaviest component split, means perturbed by +-perturb*sqrt(var)*randn)."""
-    rng = np.random.default_rng(seed)
-    targets = get_split_targets(state_occs, target_components, power, min_count)
-    mu_all, var_all = am.means(), am.variances()
-    ws, mus, vars_, off = [], [], [], [0]
-    for j in range(am.NumPdfs()):
-        a, b = int(am.offsets[j]), int(am.offsets[j + 1])
-        if targets[j] <= b - a:   # nothing to split: copy the pdf as it is (no random draws are consumed, as in DiagGmm::Split)
-            ws.append(am.weights[a:b].astype(np.float64)); mus.append(mu_all[a:b]); vars_.append(var_all[a:b])
-            off.append(off[-1] + (b - a))
-            continue
-        w = list(am.weights[a:b].astype(np.float64))
-        mu = [m.copy() for m in mu_all[a:b]]
-        var = [v.copy() for v in var_all[a:b]]
-        while len(w) < targets[j]:
-            k = int(np.argmax(w))
-            w[k] *= 0.5
-            w.append(w[k])
-            r = rng.standard_normal(am.dim) * np.sqrt(var[k]) * perturb_factor
-            mu.append(mu[k] + r)
-            mu[k] = mu[k] - r
-            var.append(var[k].copy())
-        ws.append(np.asarray(w)); mus.append(np.asarray(mu)); vars_.append(np.asarray(var))
-        off.append(off[-1] + len(w))
-    w = np.concatenate(ws); mu = np.concatenate(mus); var = np.concatenate(vars_)
-    return AmDiagGmm(am.dim, np.asarray(off, np.int32), w.astype(np.float32), (mu / var).astype(np.float32), (1.0 / var).astype(np.float32))
+            new_am = dm.read()
+    finally:
+        dm.close()
+    return new_am, float(r["gmm_objf_impr"]), float(r["gmm_count"])

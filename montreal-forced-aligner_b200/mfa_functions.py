@@ -406,8 +406,8 @@ def acc_stats(jobs: Sequence[Job], working_directory, iteration: int, mixup: int
         gacc.occ = flat[:G]; gacc.mean = flat[G:G + G * D].reshape(G, D); gacc.var = flat[G + G * D:G + 2 * G * D].reshape(G, D)
         trans = flat[G + 2 * G * D:G + 2 * G * D + tm.num_tids + 1]
         gacc.tot_like, gacc.tot_frames = float(flat[-2]), float(flat[-1])
-    tm.mle_update(trans)
-    new_am, impr, count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=min_gaussian_occupancy)
+    # tm.mle_update(transition_accs) + am.mle_update(gmm_accs, mixup=, power=) of the reference: one device call (csrc/mstep.cu)
+    new_am, impr, count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=min_gaussian_occupancy, tm=tm, transition_accs=trans)
     K.write_gmm_model(wd / f"{iteration + 1}.mdl", tm, new_am)
     avg = gacc.tot_like / max(gacc.tot_frames, 1.0)
     return avg, impr, gacc.tot_frames
@@ -479,8 +479,7 @@ def mono_align_equal(jobs: Sequence[Job], working_directory, all_reduce: Optiona
         gacc.occ = flat[:G]; gacc.mean = flat[G:G + G * D].reshape(G, D); gacc.var = flat[G + G * D:G + 2 * G * D].reshape(G, D)
         trans = flat[G + 2 * G * D:G + 2 * G * D + tm.num_tids + 1]
         gacc.tot_like, gacc.tot_frames = float(flat[-2]), float(flat[-1])
-    tm.mle_update(trans)
-    new_am, _impr, _count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=3.0)   # monophone.py:279-284
+    new_am, _impr, _count = mle_update(am, gacc, mixup=mixup, power=power, min_gaussian_occupancy=3.0, tm=tm, transition_accs=trans)   # monophone.py:279-284
     K.write_gmm_model(wd / "1.mdl", tm, new_am)
     return gacc.tot_like / max(gacc.tot_frames, 1.0), gacc.tot_frames
 

@@ -18,14 +18,15 @@ def test_header_symbols_exported():
     lib = L.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mfa_abi_version() == 1
+    assert lib.mfa_abi_version() == 2
 
 
 def test_struct_layouts_match_header_order():
     # field counts of the ctypes mirrors == the header's structs (a cheap guard against silent ABI drift)
     hdr = open(os.path.join(ROOT, "include", "mfa_b200.h")).read()
     for cname, cls in (("mfa_mfcc_opts", L.MfccOpts), ("mfa_feat_opts", L.FeatOpts), ("mfa_model_desc", L.ModelDesc),
-                       ("mfa_hmm_desc", L.HmmDesc), ("mfa_lexicon_desc", L.LexiconDesc), ("mfa_align_opts", L.AlignOpts)):
+                       ("mfa_hmm_desc", L.HmmDesc), ("mfa_lexicon_desc", L.LexiconDesc), ("mfa_align_opts", L.AlignOpts),
+                       ("mfa_trans_desc", L.TransDesc), ("mfa_mle_opts", L.MleOpts), ("mfa_mle_result", L.MleResult)):
         body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\}\s*" + cname + ";", hdr, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         n = sum(len(decl.split(",")) for decl in body.split(";") if decl.strip())

