@@ -46,7 +46,8 @@ constexpr float kLn2 = 0.69314718055994530942f, kLog2e = 1.44269504088896340736f
 
 struct TcMeta {  // per Gaussian tile: pdf structure of its 128 columns at 4-column group granularity (32 groups)
   uint32_t gstart, gend;  // bit g: group g starts a pdf / is the last group of a pdf (pdf column ranges are multiples of 4)
-  int32_t pdf0, pad;
+  int32_t pdf0;           // first output row of the tile: global pdf id (dense tiling) or utterance-local pdf index (ragged)
+  int32_t lp0;            // ragged tiles: index into the graphs' lp2pdf list of the tile's first pdf (its pdfs are lp0 .. lp0 + popc(gend) - 1)
 };
 static_assert(sizeof(TcMeta) == 16, "TcMeta must be 16 bytes");
 
@@ -360,22 +361,46 @@ __global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const fl
 // canonical [k/8][row/8][8 rows][8 halves] image in shared memory and written out linearly.
 // gcol >= 0: K = 96 geometry (padding rows carry -60000 in the first gconst column); gcol < 0: K = 80 geometry, the per-tile gconst array
 // g_out[tile][128] is gathered here as well.
+// row_src == nullptr (the per-utterance tiles of the ragged path): the source rows follow from the tile's own pdf list -- pdfs
+// lp2pdf[meta.lp0 ...], each occupying its Gaussian count rounded up to 4 columns -- so no per-column table exists in memory at all.
 __global__ void __launch_bounds__(256)
 gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int32_t *__restrict__ row_src, uint8_t *__restrict__ b_img,
-                int64_t n_tiles, int gcol, int KC, const float *__restrict__ g_src, float *__restrict__ g_out) {
+                int64_t n_tiles, int gcol, int KC, const float *__restrict__ g_src, float *__restrict__ g_out,
+                const TcMeta *__restrict__ meta, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off) {
   __shared__ int s_src[TN];
+  __shared__ int s_c0[33], s_g0[32];
   __shared__ uint4 s_img[(TN + 1) * 12];   // up to K = 96; one padding unit per k-chunk keeps the transposing stores conflict-free
   const int TK = KC * 8;
   const uint32_t IMG_BYTES = img_bytes(TK), TILE_BYTES = 2 * IMG_BYTES;
   const int64_t tile = blockIdx.x >> 1;
   const int which = blockIdx.x & 1, t = threadIdx.x;
   if (tile >= n_tiles) return;
-  if (t < TN) {
-    const int g = row_src[tile * TN + t];
-    s_src[t] = g;
-    if (g_out && which == 0) g_out[tile * TN + t] = g >= 0 ? g_src[g] : -60000.0f;
+  if (row_src) {
+    if (t < TN) s_src[t] = row_src[tile * TN + t];
+  } else {
+    const TcMeta mt = meta[tile];
+    const int npdf = __popc(mt.gend);
+    if (t < 32) {   // warp 0: column start of each pdf of the tile = exclusive prefix of the padded component counts
+      int ng = 0, g0 = 0;
+      if (t < npdf) { const int pdf = lp2pdf[mt.lp0 + t]; g0 = pdf_off[pdf]; ng = pdf_off[pdf + 1] - g0; }
+      int pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN, inc = pad;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += v; }
+      s_c0[t] = inc - pad; s_g0[t] = g0 | (ng << 24);   // ng <= 128 fits the top byte; g0 < 2^24 Gaussians
+      if (t == 31) s_c0[32] = inc;
+    }
+    __syncthreads();
+    if (t < TN) {
+      int g = -1;
+      for (int i = 0; i < npdf; i++) {
+        const int c = t - s_c0[i], ng = s_g0[i] >> 24;
+        if (c >= 0 && c < ng) { g = (s_g0[i] & 0xFFFFFF) + c; break; }
+      }
+      s_src[t] = g;
+    }
   }
   __syncthreads();
+  if (t < TN && g_out && which == 0) { const int g = s_src[t]; g_out[tile * TN + t] = g >= 0 ? g_src[g] : -60000.0f; }
   for (int c = t; c < TN * KC; c += 256) {
     const int r = c / KC, kc = c - r * KC;
     const int g = s_src[r];
@@ -392,6 +417,34 @@ gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int3
   __syncthreads();
   uint4 *dst = (uint4 *)(b_img + (size_t)tile * TILE_BYTES + (size_t)which * IMG_BYTES);
   for (int c = t; c < TN * KC; c += 256) dst[c] = s_img[(c >> 7) * (TN + 1) + (c & (TN - 1))];
+}
+
+// Per-utterance tile plan of the ragged path, on the device (it is rebuilt whenever an M-step changed some pdf's component count):
+// one thread per utterance walks its pdf list (sorted pdf ids, graphs' lp2pdf) and packs the padded component counts into 128-column
+// tiles that never split a pdf.  fill == 0: tile count per utterance; fill == 1: the tiles' TcMeta at tile_off[u].
+__global__ void rag_plan_kernel(int n_utts, const int64_t *__restrict__ lp_off, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off,
+                                int fill, int32_t *__restrict__ n_tiles_out, const int64_t *__restrict__ tile_off, TcMeta *__restrict__ meta) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_utts) return;
+  const int64_t k0 = lp_off[u], k1 = lp_off[u + 1];
+  int col = TN;   // forces a new tile at the first pdf
+  int64_t t = (fill ? tile_off[u] : 0) - 1;
+  TcMeta cur{};
+  for (int64_t k = k0; k < k1; k++) {
+    const int pdf = lp2pdf[k];
+    const int ng = pdf_off[pdf + 1] - pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
+    if (col + pad > TN) {
+      if (fill && k > k0) { if (col < TN) cur.gstart |= 1u << (col / 4); meta[t] = cur; }   // trailing padding: a junk segment that never ends
+      t++;
+      cur.gstart = 0; cur.gend = 0; cur.pdf0 = (int32_t)(k - k0); cur.lp0 = (int32_t)k;
+      col = 0;
+    }
+    cur.gstart |= 1u << (col / 4);
+    cur.gend |= 1u << ((col + pad - 1) / 4);
+    col += pad;
+  }
+  if (fill && k1 > k0) { if (col < TN) cur.gstart |= 1u << (col / 4); meta[t] = cur; }
+  if (!fill) n_tiles_out[u] = (int)(t + 1);
 }
 
 // the dense per-tile gconst array follows the per-Gaussian one; bulk copies need a 16-byte aligned source
@@ -504,7 +557,7 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
   MFA_TRY(e->upload(DB_TC_ITEMS, meta.data(), meta.size(), &d_meta_stage));
   CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, d_meta_stage, meta_bytes, cudaMemcpyDeviceToDevice, s));
   gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D,
-                                                    KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss) : nullptr);
+                                                    KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss) : nullptr, nullptr, nullptr, nullptr);
   e->launches++;
   int32_t h_flag = 0;
   CUDA_TRY(cudaMemcpyAsync(&h_flag, m->d_tc_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -601,58 +654,29 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   const uint32_t TILE_BYTES = tile_bytes(TK);
   // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles
   if (g->rag_version != m->tc_version) {
-    // two passes over the (utterance, local pdf) lists: count the tiles of every utterance, then fill meta / source rows on host threads
-    g->rag_tile_off.assign(g->n_utts + 1, 0);
-    auto pad_of = [&](int pdf) { const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf]; return (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN; };
-    for (int u = 0; u < g->n_utts; u++) {
-      int col = TN; int64_t nt_u = 0;
-      for (int64_t k = g->lp_off[u]; k < g->lp_off[u + 1]; k++) {
-        const int pdf = g->lp2pdf[k];
-        if (pdf < 0 || pdf >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
-        const int pad = pad_of(pdf);
-        if (col + pad > TN) { nt_u++; col = 0; }
-        col += pad;
-      }
-      g->rag_tile_off[u + 1] = g->rag_tile_off[u] + nt_u;
-    }
-    std::vector<TcMeta> meta((size_t)g->rag_tile_off[g->n_utts]);
-    std::vector<int32_t> src;
-    src.resize(meta.size() * TN);
-    auto fill = [&](int u) {
-      int64_t t = g->rag_tile_off[u] - 1;
-      int col = TN;  // force a new tile
-      for (int64_t k = g->lp_off[u]; k < g->lp_off[u + 1]; k++) {
-        const int pdf = g->lp2pdf[k];
-        const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = pad_of(pdf);
-        if (col + pad > TN) {
-          if (t >= g->rag_tile_off[u] && col < TN) meta[t].gstart |= 1u << (col / 4);   // trailing padding of the previous tile: a junk segment
-          t++;
-          memset(&meta[t], 0, sizeof(TcMeta)); meta[t].pdf0 = (int32_t)(k - g->lp_off[u]);
-          std::fill(src.begin() + t * TN, src.begin() + (t + 1) * TN, -1);
-          col = 0;
-        }
-        meta[t].gstart |= 1u << (col / 4);
-        meta[t].gend |= 1u << ((col + pad - 1) / 4);
-        for (int j = 0; j < ng; j++) src[t * TN + col + j] = m->h_pdf_off[pdf] + j;
-        col += pad;
-      }
-      if (t >= g->rag_tile_off[u] && col < TN) meta[t].gstart |= 1u << (col / 4);
-    };
-    {
-      int nt = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency()));
-      nt = std::min(nt, std::max(1, g->n_utts / 64));
-      std::atomic<int> next{0};
-      auto loop = [&]() { for (int u = next.fetch_add(1); u < g->n_utts; u = next.fetch_add(1)) fill(u); };
-      if (nt <= 1) loop();
-      else { std::vector<std::thread> th; for (int i = 0; i < nt; i++) th.emplace_back(loop); for (auto &x : th) x.join(); }
-    }
-    if (g->d_rag) { CUDA_TRY(cudaStreamSynchronize(e->stream)); CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
-    const size_t mb = meta.size() * sizeof(TcMeta), sb = src.size() * sizeof(int32_t);
-    CUDA_TRY(cudaMalloc(&g->d_rag, std::max<size_t>(mb + sb, 16)));
-    CUDA_TRY(cudaMemcpyAsync(g->d_rag, meta.data(), mb, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemcpyAsync((uint8_t *)g->d_rag + mb, src.data(), sb, cudaMemcpyHostToDevice, e->stream));
+    if (g->lp_off[g->n_utts] > 0x7fffffffLL) return set_error(MFA_ERR_UNSUPPORTED, "more than 2^31 (utterance, pdf) pairs in one graph batch");
+    for (int64_t k = 0; k < g->lp_off[g->n_utts]; k++)
+      if (g->lp2pdf[k] < 0 || g->lp2pdf[k] >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
+    const int nu = g->n_utts;
+    int32_t *d_cnt; int32_t *h_cnt;
+    MFA_TRY(e->getT<int32_t>(DB_RAG_CNT, (size_t)nu + 1, &d_cnt));
+    { void *pp; MFA_TRY(e->get_pinned(PB_D, ((size_t)nu + 1) * sizeof(int32_t), &pp)); h_cnt = (int32_t *)pp; }
+    rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 0, d_cnt, nullptr, nullptr);
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)nu * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    g->rag_meta_bytes = mb;
+    g->rag_tile_off.assign((size_t)nu + 1, 0);
+    for (int u = 0; u < nu; u++) g->rag_tile_off[u + 1] = g->rag_tile_off[u] + h_cnt[u];
+    const size_t n_meta = (size_t)g->rag_tile_off[nu];
+    if (g->d_rag && n_meta * sizeof(TcMeta) > g->rag_meta_bytes) { CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
+    if (!g->d_rag) {
+      g->rag_meta_bytes = (n_meta + n_meta / 8 + 64) * sizeof(TcMeta);
+      CUDA_TRY(cudaMalloc(&g->d_rag, g->rag_meta_bytes));
+    }
+    int64_t *d_toff;
+    MFA_TRY(e->upload(DB_TILE_ROW0, g->rag_tile_off.data(), g->rag_tile_off.size(), &d_toff));
+    rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 1, nullptr, d_toff, (TcMeta *)g->d_rag);
+    e->launches += 2;
+    CUDA_TRY(cudaGetLastError());
     g->rag_version = m->tc_version;
   }
   const int64_t bt0 = g->rag_tile_off[utt0], n_bt = g->rag_tile_off[utt0 + n_utts] - bt0;
@@ -688,9 +712,9 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   const int64_t tot_a = n_at * KC * TM;
   xsplit_kernel<<<(unsigned)((tot_a + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_at, d_row0, d_rows, 0, KC, TK == 96);
   e->launches++;
-  const int32_t *d_src = (const int32_t *)((const uint8_t *)g->d_rag + g->rag_meta_bytes) + bt0 * TN;
-  gather_b_kernel<<<(unsigned)(2 * n_bt), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, d_src, d_b, n_bt,
-                                                                           TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g, TK == 80 ? d_gt : nullptr);
+  gather_b_kernel<<<(unsigned)(2 * n_bt), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, nullptr, d_b, n_bt,
+                                                                           TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g, TK == 80 ? d_gt : nullptr,
+                                                                           (const TcMeta *)g->d_rag + bt0, g->d_lp2pdf, m->d_pdf_off);
   e->launches++;
   TcParams p;
   p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;

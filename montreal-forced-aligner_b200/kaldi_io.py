@@ -474,6 +474,61 @@ def _read_topology(r: _Reader) -> Topology:
     return Topology(phones, phone2idx, entries)
 
 
+def read_topology_text(path_or_text) -> Topology:
+    """Kaldi's TEXT topology format (what MFA writes as ``topo``: reference tests/data/dictionaries/expected/topo; kalpy
+    ``read_topology``): <TopologyEntry> <ForPhones> ids </ForPhones> <State> i [<PdfClass> c | <ForwardPdfClass> f <SelfLoopPdfClass> s]
+    (<Transition> dst p)* </State> ... </TopologyEntry>."""
+    text = path_or_text if "<Topology>" in str(path_or_text) else open(path_or_text, "r").read()
+    tok = text.split()
+    i = 0
+
+    def expect(t):
+        nonlocal i
+        if tok[i] != t:
+            raise ValueError(f"topology: expected {t}, got {tok[i]}")
+        i += 1
+    expect("<Topology>")
+    entries, for_phones = [], []
+    while tok[i] == "<TopologyEntry>":
+        i += 1
+        expect("<ForPhones>")
+        ph = []
+        while tok[i] != "</ForPhones>":
+            ph.append(int(tok[i])); i += 1
+        i += 1
+        states = []
+        while tok[i] == "<State>":
+            i += 1
+            idx = int(tok[i]); i += 1
+            if idx != len(states):
+                raise ValueError("topology: states must be numbered consecutively")
+            fpc = spc = -1
+            if tok[i] == "<PdfClass>":
+                fpc = spc = int(tok[i + 1]); i += 2
+            elif tok[i] == "<ForwardPdfClass>":
+                fpc = int(tok[i + 1]); i += 2
+                expect("<SelfLoopPdfClass>")
+                spc = int(tok[i]); i += 1
+            trans = []
+            while tok[i] in ("<Transition>", "<Final>"):
+                if tok[i] == "<Final>":      # old format: probability of leaving through the final state
+                    trans.append((len(states) + 1, float(tok[i + 1]))); i += 2
+                else:
+                    trans.append((int(tok[i + 1]), float(tok[i + 2]))); i += 3
+            expect("</State>")
+            states.append(HmmState(fpc, spc, trans))
+        expect("</TopologyEntry>")
+        entries.append(states)
+        for_phones.append(ph)
+    expect("</Topology>")
+    phones = np.asarray(sorted(p for ph in for_phones for p in ph), np.int32)
+    phone2idx = np.full(int(phones.max()) + 1 if phones.size else 1, -1, np.int32)
+    for e, ph in enumerate(for_phones):
+        for p in ph:
+            phone2idx[p] = e
+    return Topology(phones, phone2idx, entries)
+
+
 def _write_topology(f, topo: Topology):
     _w_token(f, "<Topology>")
     write_int_vector(f, topo.phones)

@@ -35,6 +35,82 @@ read_gmm_model = K.read_gmm_model
 write_gmm_model = K.write_gmm_model
 
 
+import logging
+
+kalpy_logger = logging.getLogger("kalpy")   # kalpy.utils.kalpy_logger (acoustic_modeling/monophone.py:15, corpus/acoustic_corpus.py:20)
+
+
+def read_topology(path):
+    """kalpy.gmm.utils.read_topology: Kaldi text topology (`topo`)."""
+    return K.read_topology_text(path)
+
+
+def read_tree(path):
+    return K.read_tree(path)
+
+
+def read_transition_model(path):
+    """kalpy.gmm.utils.read_transition_model (alignment/base.py:27): the TransitionModel at the head of a .mdl."""
+    return K.read_gmm_model(path)[0]
+
+
+class FloatMatrix(np.ndarray):
+    """numpy array carrying the three Kaldi matrix methods MFA's job functions call on what the archives hand back
+    (``feats.NumRows()`` acoustic_modeling/monophone.py:100, ``mfccs.NumRows()`` corpus/features.py:353)."""
+
+    def NumRows(self) -> int:
+        return int(self.shape[0])
+
+    def NumCols(self) -> int:
+        return int(self.shape[1]) if self.ndim > 1 else 0
+
+    def numpy(self) -> np.ndarray:
+        return np.asarray(self)
+
+
+def as_matrix(a) -> FloatMatrix:
+    return np.asarray(a).view(FloatMatrix)
+
+
+class KaldiMapping(dict):
+    """kalpy.data.KaldiMapping (corpus/features.py:298-305,492; db.py:2114): utt2spk / spk2utt text maps (``key value...`` per line)."""
+
+    def __init__(self, list_mapping: bool = False):
+        super().__init__()
+        self.list_mapping = list_mapping
+
+    def load(self, file_name):
+        with open(file_name, "r", encoding="utf8") as f:
+            for line in f:
+                parts = line.split()
+                if not parts:
+                    continue
+                self[parts[0]] = parts[1:] if self.list_mapping else (parts[1] if len(parts) > 1 else "")
+
+    def export(self, file_name, skip_safe: bool = False):
+        with open(file_name, "w", encoding="utf8") as f:
+            for k in sorted(self):
+                v = self[k]
+                f.write(f"{k} {' '.join(str(x) for x in v) if self.list_mapping else v}\n")
+
+
+def _outside(name: str, what: str):
+    class _Outside:
+        __doc__ = f"kalpy {name}: {what} -- outside the alignment hot path this engine replaces (SURVEY.md section 8); importable, not constructible."
+
+        def __init__(self, *a, **k):
+            raise MfaError(f"{name}: {what} is outside the alignment hot path this engine replaces (SURVEY.md section 8)")
+    _Outside.__name__ = _Outside.__qualname__ = name
+    return _Outside
+
+
+PitchComputer = _outside("PitchComputer", "pitch features")
+VadComputer = _outside("VadComputer", "voice activity detection")
+IvectorExtractor = _outside("IvectorExtractor", "i-vector extraction")
+TranscriptionArchive = _outside("TranscriptionArchive", "lattice / transcription archives")
+TwoFeatsStatsAccumulator = _outside("TwoFeatsStatsAccumulator", "SAT two-feature accumulation (train_sat model surgery)")
+
+
 # ------------------------------------------------------------------------------------------------ audio / MFCC
 @dataclass
 class Segment:
@@ -202,9 +278,12 @@ class FeatureArchive:
 
     Lazily applies CMVN -> deltas | splice+LDA -> fMLLR (order of alignment/multiprocessing.py:1287-1304) on the GPU."""
 
-    def __init__(self, file_name, utt2spk_file_name=None, cmvn_file_name=None, lda_mat_file_name=None, transform_file_name=None,
+    def __init__(self, file_name, utt2spk=None, cmvn_file_name=None, lda_mat_file_name=None, transform_file_name=None,
                  vad_file_name=None, deltas: bool = False, splices: bool = False, splice_frames: int = 3, subsample_n: int = 0,
-                 use_sliding_cmvn: bool = False):
+                 use_sliding_cmvn: bool = False, utt2spk_file_name=None):
+        """``utt2spk``: a KaldiMapping / dict (what db.py:2114-2129 passes) or the path of an utt2spk file."""
+        if utt2spk is None:
+            utt2spk = utt2spk_file_name
         if vad_file_name or subsample_n or use_sliding_cmvn:
             raise MfaError("vad / subsampling / sliding CMVN are outside the alignment hot path (SURVEY.md section 2a)")
         self.file_name = str(file_name)
@@ -212,7 +291,7 @@ class FeatureArchive:
         self._ark = None if self._entries is not None else dict(K.read_ark(self.file_name, "matrix"))
         self.keys = [e[0] for e in self._entries] if self._entries is not None else list(self._ark)
         self._index = {e[0]: e for e in self._entries} if self._entries is not None else None
-        self.utt2spk = _read_map(utt2spk_file_name) if utt2spk_file_name else {}
+        self.utt2spk = {} if utt2spk is None else (dict(utt2spk) if isinstance(utt2spk, dict) else _read_map(utt2spk))
         self.cmvn_read_specifier = str(cmvn_file_name) if cmvn_file_name else None
         self._cmvn = {k: np.asarray(v, np.float64) for k, v in _read_table(cmvn_file_name, "matrix").items()} if cmvn_file_name else None
         self.lda_mat_file_name = str(lda_mat_file_name) if lda_mat_file_name else None
@@ -250,7 +329,7 @@ class FeatureArchive:
         return out, fo
 
     def __getitem__(self, key: str) -> np.ndarray:
-        return self.batch([key])[0]
+        return as_matrix(self.batch([key])[0])
 
     def __iter__(self) -> Iterator[Tuple[str, np.ndarray]]:
         B = 256
@@ -258,7 +337,7 @@ class FeatureArchive:
             ks = self.keys[i:i + B]
             out, fo = self.batch(ks)
             for j, k in enumerate(ks):
-                yield k, out[fo[j]:fo[j + 1]]
+                yield k, as_matrix(out[fo[j]:fo[j + 1]])
 
     def close(self):
         self._ark = None
@@ -276,7 +355,7 @@ class TrainingGraphCompiler:
         self.tree = K.read_tree(tree_path)
         self.lexicon_compiler = lexicon_compiler
         self.batch_size = batch_size
-        self._gc = E.GraphCompiler(self.transition_model, self.tree, lexicon_compiler)
+        self._gc = E.GraphCompiler(self.transition_model, self.tree, getattr(lexicon_compiler, "lexicon", lexicon_compiler))
 
     def compile_fst(self, text: str) -> K.Fst:
         return self._gc.compile([self.lexicon_compiler.to_int(text)]).export()[0]
