@@ -194,6 +194,34 @@ def parity_block(sc, utts, ref, gpu):
             "retried_utterances_in_sample": int(sum(1 for r in ref if r["status"] == 1))}
 
 
+def reference_scenario(seconds: float, seed: int, target_pdfs: int, gauss_per_pdf: int, cores: int):
+    """The CPU arm's own workload, built WITHOUT this repo's CUDA library (libmfa_b200.so is never loaded by `--impl reference`): the same
+    synthetic corpus generator and model recipe as mfa_b200.scenario.build (numpy), features from the oracle, training graphs from the
+    oracle's pure-Python restatement of the graph compiler (oracle/graph_oracle.py)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from types import SimpleNamespace
+    from mfa_b200 import synth as SY
+    from oracle import graph_oracle as GO, oracle as O
+    corpus = SY.make_corpus(seconds, seed=seed, n_phones=40, n_words=2000, device=None)
+    rng = np.random.default_rng(seed + 1)
+    topo = SY.make_topology(corpus.phone_table)
+    tree, n_pdfs = SY.make_tree(rng, topo, True, target_pdfs)
+    tm = SY.make_transition_model(topo, tree, n_pdfs)
+    lda = SY.random_lda(rng)
+    c = corpus
+    opts = O.mfcc_opts()
+    with ThreadPoolExecutor(cores) as ex:
+        raw = list(ex.map(lambda u: O.mfcc(c.pcm[c.sample_off[u]:c.sample_off[u + 1]], opts), range(c.n_utts)))
+        stats = [O.cmvn_stats([raw[u] for u in range(c.n_utts) if c.utt2spk[u] == s]) for s in range(c.n_spk)]
+        feats = list(ex.map(lambda u: O.transform(O.splice(O.cmvn_apply(raw[u], stats[int(c.utt2spk[u])]), 3, 3), lda), range(c.n_utts)))
+    frame_off = np.zeros(c.n_utts + 1, np.int64)
+    frame_off[1:] = np.cumsum([f.shape[0] for f in feats])
+    fp = SY.frame_pdfs_from_truth(corpus, topo, tree, frame_off)
+    am = SY.estimate_gmms(np.concatenate(feats), fp, n_pdfs, gauss_per_pdf, rng)
+    fsts = [GO.compile_fst(tm, tree, corpus.lexicon, w) for w in corpus.transcripts]
+    return SimpleNamespace(corpus=corpus, tm=tm, am=am, tree=tree, lda=lda, feat_mode="lda", frame_off=frame_off, _fsts=fsts)
+
+
 def pick_sample(sc, audio_seconds: float, also=()):
     """Whole speakers from the start of the corpus until `audio_seconds` are covered, plus the whole speakers of the utterances in
     `also`: per-speaker CMVN statistics need every utterance of a speaker, so a sample that cuts a speaker would give the CPU arm
@@ -297,6 +325,103 @@ def train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args):
     return out
 
 
+def mfcc_sweep(eng, dev, stream, pk, dist, sizes, seed=1234, chunk_utts=16384):
+    """BASELINE config 5: MFCC + per-speaker CMVN statistics (K1) over N utterances of 1-30 s (uniform), N in `sizes`, split evenly over
+    the ranks.  The PCM (up to ~0.5 TB for 1 M utterances) does not fit HBM, so it is generated ON THE DEVICE chunk by chunk (noise with a
+    slow envelope: K1's cost does not depend on the signal) and only the kernel work is timed: CUDA events on the engine stream around
+    mfa_mfcc + mfa_cmvn_stats of each chunk, summed; max over ranks.  GB/s uses SURVEY.md 8(d)'s algorithmic bytes: 2 per sample in,
+    4 x 13 per frame out, + the CMVN second pass over the MFCCs (4 x 13 per frame read)."""
+    import torch
+    from mfa_b200 import engine as E
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    mo = E.mfcc_opts()
+    rows = []
+    for n_total in sizes:
+        n_mine = n_total // world + (1 if rank < n_total % world else 0)
+        rng = np.random.default_rng(seed + 7919 * rank + n_total)
+        ms = 0.0
+        samples = frames = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for c0 in range(0, n_mine, chunk_utts):
+            n = min(chunk_utts, n_mine - c0)
+            lens = (rng.uniform(1.0, 30.0, n) * 16000).astype(np.int64)
+            so = np.zeros(n + 1, np.int64)
+            so[1:] = np.cumsum(lens)
+            N = int(so[-1])
+            g = torch.Generator(device=dev)
+            g.manual_seed(int(seed + c0 + n_total))
+            pcm = torch.empty(N, dtype=torch.int16, device=dev)
+            step = 1 << 28
+            for a in range(0, N, step):     # bounded temporaries: 1 GiB of float noise at a time
+                b = min(N, a + step)
+                x = torch.randn(b - a, device=dev, generator=g)
+                x *= 3000.0 * (1.0 + 0.5 * torch.sin(torch.arange(a, b, device=dev, dtype=torch.float32) * (2 * np.pi * 4.0 / 16000.0)))
+                pcm[a:b] = x.clamp_(-32767, 32767).to(torch.int16)
+                del x
+            u2s = (np.arange(n) // 64).astype(np.int32)      # ~64 utterances per speaker
+            n_spk = int(u2s[-1]) + 1
+            torch.cuda.synchronize(dev)
+            fo = E.frame_offsets(mo, so)
+            out = torch.empty((int(fo[-1]), mo.num_ceps), dtype=torch.float32, device=dev)
+            if c0 == 0:   # first chunk of a size warms the tables / workspaces outside the timing
+                eng.mfcc(pcm, so, mo, out=out); eng.cmvn_stats(out, fo, u2s, n_spk); eng.sync()
+            e0.record(stream)
+            eng.mfcc(pcm, so, mo, out=out)
+            eng.cmvn_stats(out, fo, u2s, n_spk)
+            e1.record(stream)
+            eng.sync(); torch.cuda.synchronize(dev)
+            ms += e0.elapsed_time(e1)
+            samples += N; frames += int(fo[-1])
+            del pcm, out
+        t = torch.tensor([ms, float(samples), float(frames)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            mx = t[:1].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t[1:].clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms_max, samples_all, frames_all = float(mx.item()), float(sm[0].item()), float(sm[1].item())
+        else:
+            ms_max, samples_all, frames_all = ms, float(samples), float(frames)
+        byt = 2.0 * samples_all + 52.0 * frames_all + 52.0 * frames_all
+        gbs = byt / (ms_max * 1e-3) / 1e9
+        rows.append({"utterances": int(n_total), "audio_hours": samples_all / 16000.0 / 3600.0, "ms": ms_max, "algorithmic_GB": byt / 1e9,
+                     "GB_per_s": gbs, "frac_of_hbm_peak_all_gpus": gbs / (pk["hbm_gbs"] * world), "fp32_tflops": 16.0e3 * frames_all / (ms_max * 1e-3) / 1e12,
+                     "xRT": samples_all / 16000.0 / (ms_max * 1e-3)})
+    return {"what": "config 5: K1 MFCC + CMVN statistics over N utterances of 1-30 s, PCM generated on the device in chunks; kernel time only "
+                    "(CUDA events), max over ranks; K1 is fp32-issue bound, not HBM bound (roofline_k1)", "n_gpus": world, "sizes": rows}
+
+
+def cold_single_shot(eng, sc, dev, args, cores):
+    """What a user sees for ONE 10 h job that starts from transcripts and host PCM: training graphs compiled (host C++ threads) and packed,
+    graphs + tile plan uploaded, the fused alignment with host buffers, results back on the host -- everything inside the timed region
+    except the CUDA context and the model upload (a loaded aligner, as in MFA where the job function constructs GmmAligner once).
+    Stages are host wall clock; the alignment call overlaps its own H2D with compute."""
+    import torch
+    from mfa_b200 import engine as E
+    c = sc.corpus
+    mo = E.mfcc_opts()
+    model = E.DeviceModel(eng, sc.tm, sc.am)
+    gc = E.GraphCompiler(sc.tm, sc.tree, c.lexicon)
+    h_pcm = torch.from_numpy(c.pcm).pin_memory().numpy()
+    eng.sync()
+    t = {}
+    t0 = time.perf_counter()
+    batch = gc.compile(c.transcripts, n_threads=cores)
+    t["graph_compile_ms"] = 1e3 * (time.perf_counter() - t0)
+    t1 = time.perf_counter()
+    graphs = E.Graphs(batch, sc.tm, 1.0, 0.1)
+    t["graph_pack_ms"] = 1e3 * (time.perf_counter() - t1)
+    t1 = time.perf_counter()
+    res = E.align_pcm(eng, model, graphs, h_pcm, c.sample_off, c.utt2spk, c.n_spk, mo, sc.feat_mode, lda=sc.lda,
+                      workspace_bytes=int(args.workspace_gb * (1 << 30)))
+    t["first_align_call_ms"] = 1e3 * (time.perf_counter() - t1)
+    total = time.perf_counter() - t0
+    ok = int((res.status < 2).sum())
+    model.close(); graphs.close(); batch.close(); gc.close()
+    return {"what": "single-shot job: compile graphs + pack + first alignment call (host PCM in, host alignments out), graphs compiled inside "
+                    "the timed region", "ms": 1e3 * total, "xRT": c.seconds / total, "stages_ms": t, "aligned_utterances": ok,
+            "host_threads": cores}
+
+
 def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
     """Config 4's loop on this rank's shard, `--train-iters` iterations: align (the fused step, PCM in) -> K4 statistics -> NCCL
     all-reduce of the f64 accumulator block (N > 1) -> M-step ON THE DEVICE (csrc/mstep.cu: GMM update with low-count removal and mix-up
@@ -390,6 +515,44 @@ def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
     return out
 
 
+def reference_arm(args, real_stdout):
+    """`--impl reference`: the reference's CPU implementation of the path -- kalpy / Kaldi cannot be installed offline, so this is the
+    oracle port (oracle/oracle.c, scalar C, one utterance per host thread) -- on all host cores, on a bounded sample of the same workload
+    shape (same corpus generator, same model recipe: 4 000 pdfs / ~40 k Gaussians / D = 40), each step one pass over the sample.
+    Nothing of this repo's CUDA library is loaded or called: scenario, features, graphs and alignment all come from oracle/."""
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    seconds = min(args.hours * 3600.0, args.cpu_sample_seconds or 1800.0)
+    t0 = time.time()
+    sc = reference_scenario(seconds, 1234, args.pdfs, args.gauss_per_pdf, cores)
+    log(f"reference scenario ({sc.corpus.n_utts} utts, {sc.corpus.seconds:.0f} s, {sc.am.NumGauss()} Gaussians) built in {time.time() - t0:.1f}s without libmfa_b200.so")
+    c = sc.corpus
+    utts = list(range(c.n_utts))
+    workload = (f"configs[1]: triphone LDA-shaped GMM-HMM ({sc.am.NumPdfs()} pdfs, {sc.am.NumGauss()} Gaussians, D={sc.am.dim}), "
+                f"{c.seconds / 3600:.2f} h sample of the synthetic 16 kHz workload ({c.n_utts} utts, {c.n_spk} speakers), beam 10 / retry 40")
+    config = {"workload": workload, "hours_per_gpu": round(c.seconds / 3600, 3), "utterances_per_gpu": c.n_utts, "pdfs": sc.am.NumPdfs(),
+              "gaussians": sc.am.NumGauss(), "dim": sc.am.dim, "beam": 10, "retry_beam": 40, "parallelism": f"{cores} host threads"}
+    for _ in range(args.warmup):
+        cpu_reference_pass(sc, utts[: max(1, len(utts) // 8)], cores)
+    times = []
+    for _ in range(args.steps):
+        dt, secs, ok, _ = cpu_reference_pass(sc, utts, cores)
+        times.append(dt)
+    T = float(np.sum(times))
+    val = secs * args.steps / T
+    sample = f"{len(utts)} utterances / {secs:.0f} audio-s of the same synthetic workload shape per step; oracle port (kalpy/Kaldi not installable offline)"
+    loaded = [ln.split()[-1] for ln in open("/proc/self/maps") if "libmfa_b200" in ln]
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * T / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "impl": "reference",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "cuda_library_loaded": bool(loaded)}
+    real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,6 +570,7 @@ def main():
     ap.add_argument("--extras-dist", action="store_true", help="multi-rank runs: also time K4 / K5 / the SAT two-pass flow per rank (the training loop with its NCCL all-reduce always runs)")
     ap.add_argument("--same-shards", action="store_true", help="multi-rank runs: every rank gets the SAME corpus (seed 1234): separates data effects (a rank owning a slow utterance) from system effects in the per-rank table")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this process to the CPUs of the GPU's NUMA node")
+    ap.add_argument("--sweep-max", type=int, default=100000, help="largest utterance count of the config-5 MFCC sweep under extras (1000000 = BASELINE's full sweep; ~10 s more)")
     ap.add_argument("--no-extras", action="store_true", help="skip the K4 / K5 timings reported under 'extras'")
     ap.add_argument("--e2e-jobs", type=int, default=2, help="concurrent jobs (engines) per GPU in the end-to-end arm")
     args = ap.parse_args()
@@ -419,6 +583,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference" and rank != 0:
         return 0
+    if args.impl == "reference":
+        return reference_arm(args, real_stdout)
     import torch
     import __graft_entry__ as G
     if rank == 0:
@@ -438,9 +604,6 @@ def main():
     eng = E.Engine(local_rank)
     cores = os.cpu_count() or 1
     seconds = args.hours * 3600.0
-    if args.impl == "reference":
-        # the reference arm only needs a bounded sample of the same workload; build a smaller corpus with the same model shape
-        seconds = min(seconds, 1800.0)
     t0 = time.time()
     sc = SC.build(eng, seconds, seed=1234 + (0 if args.same_shards else rank), target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
                   synth_device=dev, log=log if rank == 0 else None, model_seed=1234 if world > 1 else None)
@@ -462,27 +625,6 @@ def main():
               "gaussians": sc.am.NumGauss(), "dim": sc.am.dim, "beam": 10, "retry_beam": 40, "parallelism": f"utterance-sharded x{world}",
               "l2": "inputs larger than L2 (PCM >> 126 MB per step); no explicit flush"}
     log(f"setup {time.time() - t0:.1f}s")
-
-    if args.impl == "reference":
-        sc._fsts = sc.batch.export()
-        sample_s = args.cpu_sample_seconds or 1800.0
-        utts = pick_sample(sc, sample_s)
-        for _ in range(args.warmup):
-            cpu_reference_pass(sc, utts[: max(1, len(utts) // 8)], cores)
-        times = []
-        for _ in range(args.steps):
-            dt, secs, ok, _ = cpu_reference_pass(sc, utts, cores)
-            times.append(dt)
-        T = float(np.sum(times))
-        val = secs * args.steps / T
-        sample = f"{len(utts)} utterances / {secs:.0f} audio-s of the same synthetic workload per step; oracle port (kalpy/Kaldi not installable offline)"
-        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1000.0 * T / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config, "impl": "reference",
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
-        return 0
 
     # ---- device-resident arm -----------------------------------------------------------------------------------
     mo = E.mfcc_opts()
@@ -693,6 +835,18 @@ def main():
             line["extras"]["train_loop"] = train_loop(eng, sc, d_pcm, dev, stream, dist, args)
         except Exception as ex:
             line["extras"]["train_loop"] = {"failed": repr(ex)}
+        try:
+            del d_pcm
+            torch.cuda.empty_cache()
+            sizes = [n for n in (1000, 10000, 100000, 1000000) if n <= args.sweep_max]
+            line["extras"]["mfcc_sweep"] = mfcc_sweep(eng, dev, stream, pk, dist, sizes)
+        except Exception as ex:
+            line["extras"]["mfcc_sweep"] = {"failed": repr(ex)}
+        if world == 1:
+            try:
+                line["cold_e2e"] = cold_single_shot(eng, sc, dev, args, cores)
+            except Exception as ex:
+                line["cold_e2e"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the reference arm times the CPU path at every N)
         try:
             sc._fsts = sc.batch.export()

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmfa_b200.so")
+LIB_PATH = os.environ.get("MFA_B200_LIB") or os.path.join(HERE, "libmfa_b200.so")   # MFA_B200_LIB: a development build (tools/k2_experiment.py)
 
 MFA_HOST, MFA_DEVICE = 0, 1
 ALIGN_STATUS = {0: "OK", 1: "RETRIED", 2: "NO_FINAL", 3: "EMPTY_GRAPH", 4: "ZERO_FRAMES"}

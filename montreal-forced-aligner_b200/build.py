@@ -21,16 +21,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None, objdir: str = None) -> str:
+    """`extra_flags` / `out` / `objdir`: development variants (e.g. -DMFA_TC_EXP=3 into /tmp) that never replace the in-tree library."""
+    if out is None and not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:
         o = os.path.join(objdir, s.rsplit(".", 1)[0] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC, *FLAGS, *extra_flags, "-c", os.path.join(CSRC, s), "-o", o]
         if s.endswith(".cc"):
             cmd.insert(1, "-x")
             cmd.insert(2, "cu")
@@ -41,14 +42,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
     failed = False
     for s, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {s}\n{out}\n")
+            sys.stderr.write(f"--- {s}\n{log}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", out or LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -73,6 +73,11 @@ struct mfa_engine {
   static constexpr int kSide = 12;
   cudaStream_t side[kSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
+  // per-utterance B images gathered ahead of time on a side stream (gmm_tc.cu prefetch_b_images): valid for utterances [pf_u0, pf_u1)
+  // of graphs pf_g under model pf_m until the next ragged launch consumes or replaces them
+  cudaEvent_t ev_bimg = nullptr;
+  const void *pf_g = nullptr, *pf_m = nullptr;
+  int pf_u0 = 0, pf_u1 = 0;
   std::vector<cudaEvent_t> ev_piece;   // H2D pieces of the PCM upload (end-to-end path)
   // per-stage CUDA-event timing of the last fused call: intervals (begin event, end event, stage) on the main stream
   enum Stage { ST_MFCC = 0, ST_FEAT = 1, ST_GMM = 2, ST_VITERBI = 3, ST_N = 4 };
@@ -176,6 +181,7 @@ struct mfa_model {
   std::vector<float> h_tc_colscale;    // per-dimension power-of-two feature scaling folded into the weights
   float *d_tc_colscale = nullptr;
   bool tc_ready = false;
+  int tc_n_tiles = 0;                  // tiles of the dense width-class tiling (gmm_tc.cu)
   bool tc_unsupported = false;         // weights beyond the fp16 range / dim too large: the fp32 kernel scores this model
   size_t tc_cap_gauss = 0;             // Gaussians d_tc_rows / d_tc_g were allocated for
   int32_t *d_tc_flag = nullptr;        // device flag: a weight exceeded the fp16 range while the operand rows were written
@@ -202,6 +208,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
 bool gmm_tc_supported(mfa_model *m);
 int build_tc_device(mfa_model *m, bool layout_changed);        // K2 operand images from the device-resident natural-layout parameters
 int refold_graphs(mfa_engine *e, mfa_graphs *g, const float *d_tid_cost);   // a_w = a_w0 + tid_cost[a_tid] on the device, band copy included
+int prefetch_b_images(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts);   // gather_b on a side stream, ahead of the features
 int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
                          const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld);
 int launch_transpose(mfa_engine *e, const float *d_in, int64_t rows, int64_t cols, int64_t in_ld, float *d_out, int64_t out_ld);

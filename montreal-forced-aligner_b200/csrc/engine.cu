@@ -98,6 +98,7 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_bimg, cudaEventDisableTiming));
   CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, mfa_engine::kFbRing * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
   memset(e->h_fb_ring, 0, mfa_engine::kFbRing * sizeof(int32_t));
   for (int k = 0; k < 2; k++) {
@@ -119,6 +120,7 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (auto ev : e->st_ev) cudaEventDestroy(ev);
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_bimg) cudaEventDestroy(e->ev_bimg);
   if (e->h_fb_ring) cudaFreeHost(e->h_fb_ring);
   for (int k = 0; k < 2; k++) { if (e->stage_mem[k]) cudaFreeHost(e->stage_mem[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }
   cudaStreamDestroy(e->stream);

@@ -1,5 +1,5 @@
-// gmm_tc.cu -- K2 on the 5th-generation tensor cores: all-pdf diagonal-GMM log-likelihoods as the dense contraction
-//   C[t, m] = [x s, (x s)^2, 1, 1, 1] . [mu/(sigma^2 s), -1/(2 sigma^2 s^2), g1, g2, g3]^T * log2(e)       (m = Gaussian)
+// gmm_tc.cu -- K2 on the 5th-generation tensor cores: diagonal-GMM log-likelihoods as the dense contraction
+//   C[t, m] = [x s, (x s)^2] . [mu/(sigma^2 s), -1/(2 sigma^2 s^2)]^T * log2(e)  (+ g_m log2(e) in the epilogue)      (m = Gaussian)
 // issued as tcgen05.mma (kind::f16, fp32 accumulators in TMEM), followed by a per-pdf log-sum-exp computed by the
 // epilogue warps straight out of TMEM (tcgen05.ld), one frame per thread.
 //
@@ -8,15 +8,21 @@
 //
 // Split precision: both operands are split into fp16 hi + lo parts (22 significand bits) and three products are
 // accumulated (hi*hi, hi*lo, lo*hi); features are pre-scaled per dimension by a power of two s_d (folded into the
-// weights) so x s and (x s)^2 sit well inside fp16's range; the gconst enters as three fp16 columns against ones.
-// K = 2D + 3 padded to 96 -> 6 k-steps x 3 products = 18 MMAs (M=128, N=128, K=16) per 128x128 output tile.
+// weights) so x s and (x s)^2 sit well inside fp16's range.
 //
 // Data movement: operands live in global memory ALREADY in the UMMA canonical K-major no-swizzle layout
-// ([k/8][row/8][8 rows][8 halves], core matrix = 128 contiguous bytes), so a tile is one contiguous 48 KB image and
+// ([k/8][row/8][8 rows][8 halves], core matrix = 128 contiguous bytes), so a tile is one contiguous image and
 // is fetched with a single 1-D bulk copy (cp.async.bulk -> UBLKCP) completing on an mbarrier; no tensor maps.
 // Each CTA keeps the A images of two frame tiles (256 frames) resident and streams the Gaussian tiles through a
-// two-stage ring, so every B image fetched from L2 feeds 2 x 18 MMAs.  TMEM holds 2 stages x 2 accumulators of 128
+// ring, so every B image fetched from L2 feeds two accumulators.  TMEM holds 2 stages x 2 accumulators of 128
 // columns (all 512 columns): the MMA warp runs one Gaussian tile ahead of the two epilogue warpgroups.
+//
+// Width-class tiles (round 2).  A Gaussian tile holds pdfs of ONE width class W (4, 8, ..., 32, 48, 64 or 128 columns per pdf:
+// the pdf's component count rounded up to the class), floor(128 / W) pdfs per tile, so the column range of every pdf is a
+// compile-time constant of the tile's class and the epilogue is straight-line code per class -- no segment masks, no predicates
+// per 4-column group, no reconvergence barriers: 1 333 -> ~700 SASS instructions per 128-column tile (the round-1 epilogue was
+// what the tensor pipe waited for).  The per-tile side data (gconst per column, output row per pdf slot, the class) travels
+// with the accumulator stage as one 672-byte bulk copy.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -34,22 +40,40 @@ using namespace mfa;
 namespace {
 
 constexpr int TM = 128, TN = MFA_TILE_N;
-// Two geometries.  K = 80 (2 dim <= 80; MFA's 39 / 40-dimensional features): the gconst is added by the epilogue from a per-tile fp32
-// array, 5 k-steps x 3 products = 15 MMAs per tile, 40 KB tiles, a THREE-stage B ring.  K = 96 (2 dim + 3 <= 96, or engine option tc_k96): the
-// gconst rides as three fp16 columns against ones, 18 MMAs per tile, 48 KB tiles, two-stage ring (the first version of this kernel).
+// Two geometries.  K = 80 (2 dim <= 80; MFA's 39 / 40-dimensional features): the gconst is added by the epilogue from the tile's side
+// data, 5 k-steps x 3 products = 15 MMAs per tile, 40 KB tiles, a THREE-stage B ring.  K = 96 (2 dim + 3 <= 96, or engine option tc_k96):
+// the gconst rides as three fp16 columns against ones, 18 MMAs per tile, 48 KB tiles, two-stage ring (the first version of this kernel).
 __host__ __device__ constexpr uint32_t img_bytes(int tk) { return (uint32_t)(TM * tk * 2); }   // one fp16 image (hi or lo) of a 128 x tk tile
 __host__ __device__ constexpr uint32_t tile_bytes(int tk) { return 2 * img_bytes(tk); }         // hi + lo
 constexpr uint32_t LBO_BYTES = (TM / 8) * 128;    // K-adjacent core matrices
 constexpr uint32_t SBO_BYTES = 128;               // row-group-adjacent core matrices
 constexpr int NTHREADS = 640;   // 4 control warps + 16 epilogue warps (4 per SM sub-partition)
 constexpr float kLn2 = 0.69314718055994530942f, kLog2e = 1.44269504088896340736f;
+// Timing experiments (WRONG results), compiled only by tools/k2_experiment.py with -DMFA_TC_EXP=n into a scratch library, never shipped:
+// 1 no stores, 2 epilogue loads TMEM and releases (no arithmetic, no stores), 3 epilogue releases without reading, 4 one k-step per
+// product (3 MMAs per tile instead of 15), 5 B tiles fetched once per item (no B traffic), 6 = 2 + 5, 7 = correct results + cycle counters
+// of every role's barrier waits (printed per launch)
+#ifndef MFA_TC_EXP
+#define MFA_TC_EXP 0
+#endif
 
-struct TcMeta {  // per Gaussian tile: pdf structure of its 128 columns at 4-column group granularity (32 groups)
-  uint32_t gstart, gend;  // bit g: group g starts a pdf / is the last group of a pdf (pdf column ranges are multiples of 4)
-  int32_t pdf0;           // first output row of the tile: global pdf id (dense tiling) or utterance-local pdf index (ragged)
-  int32_t lp0;            // ragged tiles: index into the graphs' lp2pdf list of the tile's first pdf (its pdfs are lp0 .. lp0 + popc(gend) - 1)
+// Width classes: pdfs of up to W components share tiles of class W.
+constexpr int NCLS = 11;
+__host__ __device__ constexpr int cls_width(int c) { return c < 8 ? 4 * (c + 1) : (c == 8 ? 48 : (c == 9 ? 64 : 128)); }
+__host__ __device__ constexpr int cls_cap(int c) { return TN / cls_width(c); }               // pdfs per tile: 32 16 10 8 6 5 4 4 2 2 1
+__host__ __device__ inline int cls_of(int ng) { return ng <= 32 ? (ng + 3) / 4 - 1 : (ng <= 48 ? 8 : (ng <= 64 ? 9 : 10)); }
+
+// Side data of one Gaussian tile (bulk-copied into shared memory next to the accumulator stage it belongs to).
+struct TcAux {
+  float g[TN];        // gconst * log2(e) per column (padding columns: -60000 -> exp2 -> 0); written by gather_b_kernel
+  int32_t row[32];    // output row of pdf slot j (utterance-local pdf index, or global pdf id in the dense tiling); -1 = empty slot
+  int32_t cls;        // width class of the tile
+  int32_t npdf;       // occupied slots
+  int32_t lp_base;    // ragged tiles: index of the utterance's first entry in the graphs' lp2pdf list (pdf of slot j = lp2pdf[lp_base + row[j]]); dense: -1 (pdf = row[j])
+  int32_t pad[5];
 };
-static_assert(sizeof(TcMeta) == 16, "TcMeta must be 16 bytes");
+static_assert(sizeof(TcAux) == 672 && sizeof(TcAux) % 16 == 0, "TcAux must be 672 bytes");
+constexpr uint32_t AUX_BYTES = sizeof(TcAux);
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,56 +137,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 32-column chunk (8 groups of 4 columns) of a frame's component scores (log2 domain).  pdf boundaries fall on group
-// boundaries, so the segmented max / sum scans run over 8 group values: group max (tree) -> forward running max -> backward
-// broadcast of each pdf's max -> exp2 of the 32 values against their pdf's max -> group sums -> forward running sum; one
-// log2 + store per finished pdf.  (cmx, cs) carry an unfinished pdf into the next chunk.  All predicates are warp-uniform.
-template <bool GEPI>
-__device__ __forceinline__ void lse_chunk(uint32_t (&vr)[32], const float *gp, uint32_t gs, uint32_t ge, float &cmx, float &cs, float *&out,
-                                          int64_t ld, bool row_ok) {
-  if (GEPI) {   // gconst of the chunk's 32 columns from shared memory (every thread reads the same words: broadcasts)
+// ---- epilogue of one accumulator (128 frames x 128 columns) whose tile has width class W: thread = frame (TMEM lane).  The tile's
+// pdf slot j owns columns [j W, (j + 1) W); the accumulator is read in four 32-column chunks, a pdf that straddles a chunk edge carries
+// (max, sum) across it.  Everything about the segmentation is a compile-time constant after unrolling.
+template <int W, bool GEPI>
+__device__ __forceinline__ void epi_tile(const uint32_t t0, const TcAux *__restrict__ ax, float *__restrict__ out_base, const uint32_t ld,
+                                         const bool row_ok, uint64_t *tempty_bar) {
+  constexpr int NP = TN / W;                       // pdf slots per tile
+  constexpr int NCH = (NP * W + 31) / 32;          // chunks that hold pdf columns
+  float cm = 0.0f, cs = 0.0f;
+  uint32_t v[32];
 #pragma unroll
-    for (int g = 0; g < 8; g++) {
-      const float4 q = *reinterpret_cast<const float4 *>(gp + 4 * g);
-      vr[4 * g] = __float_as_uint(__uint_as_float(vr[4 * g]) + q.x); vr[4 * g + 1] = __float_as_uint(__uint_as_float(vr[4 * g + 1]) + q.y);
-      vr[4 * g + 2] = __float_as_uint(__uint_as_float(vr[4 * g + 2]) + q.z); vr[4 * g + 3] = __float_as_uint(__uint_as_float(vr[4 * g + 3]) + q.w);
+  for (int c = 0; c < NCH; c++) {
+    tmem_ld32(t0 + 32 * c, v);
+    tmem_ld_wait();
+    if (c == NCH - 1) { tc_fence_before(); mbar_arrive(tempty_bar); }   // accumulator drained: the MMA warp may overwrite it
+#if MFA_TC_EXP == 2 || MFA_TC_EXP == 6
+    if (__uint_as_float(v[0]) == 1.2345e-30f && row_ok) out_base[0] = 0.0f;
+    continue;
+#endif
+    if (GEPI) {   // gconst of the chunk's columns from shared memory (every thread reads the same words: broadcasts)
+#pragma unroll
+      for (int q4 = 0; q4 < 8; q4++) {
+        if (32 * c + 4 * q4 >= NP * W) break;
+        const float4 q = *reinterpret_cast<const float4 *>(ax->g + 32 * c + 4 * q4);
+        v[4 * q4] = __float_as_uint(__uint_as_float(v[4 * q4]) + q.x); v[4 * q4 + 1] = __float_as_uint(__uint_as_float(v[4 * q4 + 1]) + q.y);
+        v[4 * q4 + 2] = __float_as_uint(__uint_as_float(v[4 * q4 + 2]) + q.z); v[4 * q4 + 3] = __float_as_uint(__uint_as_float(v[4 * q4 + 3]) + q.w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      const int lo = (j * W > 32 * c ? j * W : 32 * c) - 32 * c, hi = ((j + 1) * W < 32 * c + 32 ? (j + 1) * W : 32 * c + 32) - 32 * c;
+      if (lo >= hi) continue;
+      const bool starts = j * W >= 32 * c, ends = (j + 1) * W <= 32 * c + 32;
+      // (lo, hi and W are multiples of 4: the loops run over 4-column groups with literal indices, which keeps v[] in registers)
+      float m = fmaxf(fmaxf(__uint_as_float(v[lo]), __uint_as_float(v[lo + 1])), fmaxf(__uint_as_float(v[lo + 2]), __uint_as_float(v[lo + 3])));
+#pragma unroll
+      for (int q4 = 1; q4 < 8; q4++) {
+        if (lo + 4 * q4 >= hi) break;
+        const int i = lo + 4 * q4;
+        m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]))));
+      }
+      float s0 = 0.0f, s1 = 0.0f;
+      if (!starts) { const float nm = fmaxf(cm, m); s0 = cs * ex2(cm - nm); m = nm; }
+#pragma unroll
+      for (int q4 = 0; q4 < 8; q4++) {
+        if (lo + 4 * q4 >= hi) break;
+        const int i = lo + 4 * q4;
+        s0 += ex2(__uint_as_float(v[i]) - m) + ex2(__uint_as_float(v[i + 2]) - m);
+        s1 += ex2(__uint_as_float(v[i + 1]) - m) + ex2(__uint_as_float(v[i + 3]) - m);
+      }
+      const float s = s0 + s1;
+      if (ends) {
+        const int row = ax->row[j];
+#if MFA_TC_EXP == 1
+        if (row_ok && row == -12345) out_base[(size_t)((uint32_t)row * ld)] = (m + lg2(s)) * kLn2;
+#else
+        if (row_ok && row >= 0) out_base[(size_t)((uint32_t)row * ld)] = (m + lg2(s)) * kLn2;
+#endif
+      } else { cm = m; cs = s; }
     }
   }
-  float r[8];
-  float run = cmx;
-#pragma unroll
-  for (int g = 0; g < 8; g++) {
-    const float gm = fmaxf(fmaxf(__uint_as_float(vr[4 * g]), __uint_as_float(vr[4 * g + 1])),
-                           fmaxf(__uint_as_float(vr[4 * g + 2]), __uint_as_float(vr[4 * g + 3])));
-    run = ((gs >> g) & 1u) ? gm : fmaxf(run, gm);
-    r[g] = run;
-  }
-  float m = r[7];
-#pragma unroll
-  for (int g = 7; g >= 0; g--) {
-    m = ((ge >> g) & 1u) ? r[g] : m;
-    r[g] = m;
-  }
-  float q = cs * ex2(cmx - r[0]);
-#pragma unroll
-  for (int g = 0; g < 8; g++) {
-    const float e0 = ex2(__uint_as_float(vr[4 * g]) - r[g]), e1 = ex2(__uint_as_float(vr[4 * g + 1]) - r[g]);
-    const float e2 = ex2(__uint_as_float(vr[4 * g + 2]) - r[g]), e3 = ex2(__uint_as_float(vr[4 * g + 3]) - r[g]);
-    const float s4 = (e0 + e1) + (e2 + e3);
-    q = ((gs >> g) & 1u) ? s4 : q + s4;
-    if ((ge >> g) & 1u) {
-      if (row_ok) *out = (r[g] + lg2(q)) * kLn2;
-      out += ld;
-    }
-  }
-  cmx = r[7];
-  cs = q;
 }
 
 // One work item = one pair of frame tiles (256 frames) against a run of Gaussian tiles.
 struct TcItem {
   uint32_t a_tile;       // first of the two A images of the pair
-  uint32_t b_tile0, n_b; // Gaussian tiles [b_tile0, b_tile0 + n_b): images in b_img, segment masks in meta
+  uint32_t b_tile0, n_b; // Gaussian tiles [b_tile0, b_tile0 + n_b): images in b_img, side data in aux
   uint32_t rows_valid;   // frames of the pair that exist (<= 256)
   uint64_t out_off;      // float offset of the pair's first frame in `out`
   uint32_t ld, pad;      // leading dimension (frames) of this item's output block
@@ -172,12 +213,21 @@ static_assert(sizeof(TcItem) == 32, "TcItem must be 32 bytes");
 struct TcParams {
   const uint8_t *a_img;   // [n_frame_tiles (even)][tile_bytes]
   const uint8_t *b_img;   // [n_b_tiles][tile_bytes]
-  const TcMeta *meta;     // [n_b_tiles]; pdf0 = first output row of the tile (global pdf id, or utterance-local pdf index)
-  const float *g_tiles;   // K = 80 geometry: [n_b_tiles][128] gconst * log2(e) per tile column (padding: -60000)
+  const TcAux *aux;       // [n_b_tiles] side data (gconsts, output rows, width class)
   const TcItem *items;    // [n_items]
   int n_items;
-  float *out;             // pdf-major blocks: out[item.out_off + (meta.pdf0 + k) * item.ld + frame]
+  float *out;             // pdf-major blocks: out[item.out_off + row * item.ld + frame]
+#if MFA_TC_EXP == 7
+  long long *dbg;         // [grid][16] cycle counters
+#endif
 };
+#if MFA_TC_EXP == 7
+#define DBG_T0() const long long dbg_t0 = clock64()
+#define DBG_ADD(slot) p.dbg[blockIdx.x * 16 + (slot)] += clock64() - dbg_t0
+#else
+#define DBG_T0()
+#define DBG_ADD(slot)
+#endif
 
 template <int TKt, int NBt, bool GEPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -186,16 +236,16 @@ gmm_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sA = smem;                       // 2 frame tiles x (hi, lo)
   uint8_t *sB = smem + 2 * TILE_BYTES;      // NBt stages x (hi, lo)
-  float *sG = (float *)(smem + (2 + NBt) * TILE_BYTES);   // 2 x 128 gconsts (one row per accumulator stage)
-  uint64_t *bars = (uint64_t *)(smem + (2 + NBt) * TILE_BYTES + 1024);
+  TcAux *sX = (TcAux *)(smem + (2 + NBt) * TILE_BYTES);   // 2 x side data (one per accumulator stage)
+  uint64_t *bars = (uint64_t *)(smem + (2 + NBt) * TILE_BYTES + 2 * AUX_BYTES);
   uint64_t *full_a = bars + 0, *empty_a = bars + 1, *full_b = bars + 2, *empty_b = bars + 2 + NBt, *tfull = bars + 2 + 2 * NBt,
            *tempty = tfull + 4, *gfull = tempty + 4, *gempty = gfull + 2;
   uint32_t *tmem_slot = (uint32_t *)(gempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(full_a, 1); mbar_init(empty_a, 1);
-    for (int s = 0; s < NBt; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
+    mbar_init(full_a, 1); mbar_init(empty_a, 2);    // two MMA issuers (one per frame tile of the pair) release the operand buffers
+    for (int s = 0; s < NBt; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 2); }
     for (int i = 0; i < 4; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
     for (int i = 0; i < 2; i++) { mbar_init(gfull + i, 1); mbar_init(gempty + i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,14 +263,17 @@ gmm_tc_kernel(TcParams p) {
   if (warp == 0) {
     // ===== producer: bulk copies of the A pair (once per item) and of each B tile =====
     if (lane == 0) {
-      uint32_t cnt = 0, it = 0, sb = 0, phb = 0;   // sb / phb: slot of the B ring and the phase of its barriers
+      uint32_t it = 0, sb = 0, phb = 0;   // sb / phb: slot of the B ring and the phase of its barriers
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         const TcItem I = p.items[item];
-        mbar_wait(empty_a, (it & 1) ^ 1);
+        { DBG_T0(); mbar_wait(empty_a, (it & 1) ^ 1); DBG_ADD(0); }
         mbar_expect_tx(full_a, 2 * TILE_BYTES);
         bulk_g2s(sA, p.a_img + (size_t)I.a_tile * TILE_BYTES, 2 * TILE_BYTES, full_a);
-        for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
-          mbar_wait(empty_b + sb, phb ^ 1);
+        for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++) {
+          { DBG_T0(); mbar_wait(empty_b + sb, phb ^ 1); DBG_ADD(1); }
+#if MFA_TC_EXP == 5 || MFA_TC_EXP == 6
+          if (n >= I.b_tile0 + NBt) { mbar_arrive(full_b + sb); if (++sb == NBt) { sb = 0; phb ^= 1; } continue; }
+#endif
           mbar_expect_tx(full_b + sb, TILE_BYTES);
           bulk_g2s(sB + sb * TILE_BYTES, p.b_img + (size_t)n * TILE_BYTES, TILE_BYTES, full_b + sb);
           if (++sb == NBt) { sb = 0; phb ^= 1; }
@@ -228,57 +281,74 @@ gmm_tc_kernel(TcParams p) {
       }
     }
   } else if (warp == 3) {
-    // ===== gconst producer (K = 80 geometry): the tile's 128 gconsts travel with the accumulator stage (cnt & 1) and are released by
-    // the epilogue warps -- its own thread, so a slow epilogue never delays the B ring =====
-    if (GEPI && lane == 0) {
+    // ===== side-data producer: the tile's TcAux travels with the accumulator stage (cnt & 1) and is released by the epilogue warps
+    // -- its own thread, so a slow epilogue never delays the B ring =====
+    if (lane == 0) {
       uint32_t cnt = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const TcItem I = p.items[item];
         for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
           const uint32_t sg = cnt & 1;
-          mbar_wait(gempty + sg, ((cnt >> 1) & 1) ^ 1);
-          mbar_expect_tx(gfull + sg, TN * 4);
-          bulk_g2s(sG + sg * TN, p.g_tiles + (size_t)n * TN, TN * 4, gfull + sg);
+          { DBG_T0(); mbar_wait(gempty + sg, ((cnt >> 1) & 1) ^ 1); DBG_ADD(2); }
+          mbar_expect_tx(gfull + sg, AUX_BYTES);
+          bulk_g2s(sX + sg, p.aux + n, AUX_BYTES, gfull + sg);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
+  } else if (warp == 1 || warp == 2) {
+    // ===== MMA issuers: one thread per frame tile of the pair (f = 0: warp 1, f = 1: warp 2).  The round-1 kernel issued both
+    // accumulators from one thread; its cycle counters (tools/k2_experiment.py, variant 7) showed that thread busy 90 % of the time, ~70
+    // cycles per tcgen05.mma of descriptor arithmetic and register -> uniform-register moves, i.e. the ISSUE rate bounded the kernel, not
+    // the tensor pipe.  Two threads halve that, and the shared-memory descriptors are now one 32-bit add away from a per-tile base. =====
     if (lane == 0) {
+      const int f = warp - 1;
       // InstrDescriptor: c_format=F32 (1<<4), a/b format F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      // SmemDescriptor: low word = (address >> 4) [0,14) | (LBO >> 4) << 16; high word = (SBO >> 4) | version 1 << 14 -- constant
+      const uint32_t desc_hi = (SBO_BYTES >> 4) | (1u << 14);
+      const uint32_t a_lo = (((smem_u32(sA) + f * TILE_BYTES) & 0x3FFFF) >> 4) | ((LBO_BYTES >> 4) << 16);
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFF) >> 4) | ((LBO_BYTES >> 4) << 16);
       uint32_t cnt = 0, it = 0, sb = 0, phb = 0;
+#if MFA_TC_EXP == 7
+      const long long dbg_loop0 = clock64();
+#endif
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
         const uint32_t n_b = p.items[item].n_b, rows_valid = p.items[item].rows_valid;
-        mbar_wait(full_a, it & 1);
+        const bool live = f == 0 || rows_valid > TM;   // a pair whose second tile holds no frames skips its MMAs
+        { DBG_T0(); mbar_wait(full_a, it & 1); if (f == 0) DBG_ADD(3); }
         tc_fence_after();
         for (uint32_t n = 0; n < n_b; n++, cnt++) {
           const uint32_t s = cnt & 1, ph = (cnt >> 1) & 1;
-          mbar_wait(full_b + sb, phb);
+          { DBG_T0(); mbar_wait(full_b + sb, phb); if (f == 0) DBG_ADD(4); }
+          { DBG_T0(); mbar_wait(tempty + s * 2 + f, ph ^ 1); if (f == 0) DBG_ADD(5); }
           tc_fence_after();
+          DBG_T0();
+          if (live) {
+            const uint32_t d = tmem_base + s * 256 + f * 128;
+            const uint32_t b_lo = b_lo0 + sb * (TILE_BYTES >> 4);
 #pragma unroll
-          for (int f = 0; f < 2; f++) {
-            mbar_wait(tempty + s * 2 + f, ph ^ 1);
-            tc_fence_after();
-            if (f == 0 || rows_valid > TM) {   // a pair whose second tile holds no frames skips its 18 MMAs
-              const uint32_t d = tmem_base + s * 256 + f * 128;
-              const uint32_t a0 = a_base + f * TILE_BYTES, b0 = b_base + sb * TILE_BYTES;
+            for (int prod = 0; prod < 3; prod++) {
 #pragma unroll
-              for (int prod = 0; prod < 3; prod++) {
-                const uint32_t ao = a0 + (prod == 2 ? IMG_BYTES : 0), bo = b0 + (prod == 1 ? IMG_BYTES : 0);
-#pragma unroll
-                for (int k = 0; k < TKt / 16; k++)
-                  umma_f16(d, make_desc(ao + k * 2 * LBO_BYTES), make_desc(bo + k * 2 * LBO_BYTES), idesc, (prod | k) != 0);
+              for (int k = 0; k < (MFA_TC_EXP == 4 ? 1 : TKt / 16); k++) {
+                const uint32_t ao = (uint32_t)((k * 2 * LBO_BYTES + (prod == 2 ? IMG_BYTES : 0)) >> 4);
+                const uint32_t bo = (uint32_t)((k * 2 * LBO_BYTES + (prod == 1 ? IMG_BYTES : 0)) >> 4);
+                umma_f16(d, ((uint64_t)desc_hi << 32) | (a_lo + ao), ((uint64_t)desc_hi << 32) | (b_lo + bo), idesc, (prod | k) != 0);
               }
             }
-            umma_commit(tfull + s * 2 + f);
           }
+          umma_commit(tfull + s * 2 + f);
           umma_commit(empty_b + sb);
+          if (f == 0) DBG_ADD(6);
+#if MFA_TC_EXP == 7
+          if (f == 0) p.dbg[blockIdx.x * 16 + 12] += 1;
+#endif
           if (++sb == NBt) { sb = 0; phb ^= 1; }
         }
         umma_commit(empty_a);
       }
+#if MFA_TC_EXP == 7
+      if (f == 0) p.dbg[blockIdx.x * 16 + 7] += clock64() - dbg_loop0;
+#endif
     }
   } else if (warp >= 4) {
     // ===== epilogue: 16 warps = 2 accumulator stages x 2 frame tiles x 4 lane quarters; thread = one frame (TMEM lane).
@@ -287,33 +357,50 @@ gmm_tc_kernel(TcParams p) {
     const int e = warp - 4, wq = e & 3, f = (e >> 2) & 1, s = e >> 3;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     uint32_t cnt = 0;   // tiles seen by the CTA so far (all roles count alike); this warp serves those with (cnt & 1) == s
+    const TcAux *ax = sX + s;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const TcItem I = p.items[item];
       const uint32_t row = f * TM + wq * 32 + lane;
       const bool row_ok = row < I.rows_valid;
       const bool tile_live = (uint32_t)(f * TM) < I.rows_valid;
       float *out_base = p.out + I.out_off + row;
-      for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
+      for (uint32_t n = 0; n < I.n_b; n++, cnt++) {
         if ((cnt & 1u) != (uint32_t)s) continue;
         const uint32_t ph = (cnt >> 1) & 1;
-        const TcMeta cur = p.meta[n];
+#if MFA_TC_EXP == 7
+        const bool dbg_me = warp == 4 && lane == 0;
+        { const long long t0 = clock64(); mbar_wait(tfull + s * 2 + f, ph); if (dbg_me) p.dbg[blockIdx.x * 16 + 8] += clock64() - t0; }
+        tc_fence_after();
+        { const long long t0 = clock64(); mbar_wait(gfull + s, ph); if (dbg_me) p.dbg[blockIdx.x * 16 + 9] += clock64() - t0; }
+        const long long dbg_e0 = clock64();
+#else
         mbar_wait(tfull + s * 2 + f, ph);
         tc_fence_after();
-        if (GEPI) mbar_wait(gfull + s, ph);
-        if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); if (GEPI) mbar_arrive(gempty + s); continue; }
-        const float *gs = sG + s * TN;
+        mbar_wait(gfull + s, ph);
+#endif
+#if MFA_TC_EXP == 3
+        { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); mbar_arrive(gempty + s); continue; }
+#endif
+        if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); mbar_arrive(gempty + s); continue; }
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
-        float cmx = -INFINITY, cs = 0.0f;
-        float *out = out_base + (size_t)cur.pdf0 * I.ld;
-        uint32_t v[32];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          tmem_ld32(t0 + 32 * c, v);
-          tmem_ld_wait();
-          if (c == 3) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); }   // accumulator drained: the MMA warp may overwrite it
-          lse_chunk<GEPI>(v, gs + 32 * c, (cur.gstart >> (8 * c)) & 0xFF, (cur.gend >> (8 * c)) & 0xFF, cmx, cs, out, I.ld, row_ok);
+        uint64_t *tb = tempty + s * 2 + f;
+        switch (ax->cls) {   // uniform across the CTA: one class per tile
+          case 0: epi_tile<4, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 1: epi_tile<8, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 2: epi_tile<12, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 3: epi_tile<16, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 4: epi_tile<20, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 5: epi_tile<24, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 6: epi_tile<28, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 7: epi_tile<32, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 8: epi_tile<48, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 9: epi_tile<64, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          default: epi_tile<128, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
         }
-        if (GEPI) mbar_arrive(gempty + s);   // this thread is done with the stage's gconsts
+        mbar_arrive(gempty + s);   // this thread is done with the stage's side data
+#if MFA_TC_EXP == 7
+        if (dbg_me) { p.dbg[blockIdx.x * 16 + 10] += clock64() - dbg_e0; p.dbg[blockIdx.x * 16 + 11] += 1; }
+#endif
       }
     }
   }
@@ -355,52 +442,40 @@ __global__ void xsplit_kernel(const float *__restrict__ feats, int dim, const fl
   *(uint4 *)(a_img + off + IMG_BYTES) = *(const uint4 *)lo;
 }
 
-// B images for utterance-specific Gaussian tiles: row r of tile t is Gaussian row_src[t*128 + r] of the model (row-major fp16
-// hi/lo weight rows), or padding (zero weights; gconst -60000 -> exp2 -> 0) when row_src < 0.  One CTA per (tile, hi | lo): the 128
-// source rows are read as whole rows (consecutive threads = consecutive 16-byte pieces of a row: full sectors), re-ordered into the
-// canonical [k/8][row/8][8 rows][8 halves] image in shared memory and written out linearly.
-// gcol >= 0: K = 96 geometry (padding rows carry -60000 in the first gconst column); gcol < 0: K = 80 geometry, the per-tile gconst array
-// g_out[tile][128] is gathered here as well.
-// row_src == nullptr (the per-utterance tiles of the ragged path): the source rows follow from the tile's own pdf list -- pdfs
-// lp2pdf[meta.lp0 ...], each occupying its Gaussian count rounded up to 4 columns -- so no per-column table exists in memory at all.
+// B images: column t of a tile of class W belongs to pdf slot j = t / W, component t % W.  One CTA per (tile, hi | lo): the source rows
+// (row-major fp16 hi/lo weight rows of the model) are read whole (consecutive threads = consecutive 16-byte pieces of a row: full
+// sectors), re-ordered into the canonical [k/8][row/8][8 rows][8 halves] image in shared memory and written out linearly; the tile's
+// gconst column (aux.g) is gathered here as well.  Padding columns get zero weights and gconst -60000 (K = 96 geometry: -60000 in the
+// first gconst column of the weight row).
 __global__ void __launch_bounds__(256)
-gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int32_t *__restrict__ row_src, uint8_t *__restrict__ b_img,
-                int64_t n_tiles, int gcol, int KC, const float *__restrict__ g_src, float *__restrict__ g_out,
-                const TcMeta *__restrict__ meta, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off) {
+gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, uint8_t *__restrict__ b_img, int64_t n_tiles, int gcol, int KC,
+                const float *__restrict__ g_src, TcAux *__restrict__ aux, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off) {
   __shared__ int s_src[TN];
-  __shared__ int s_c0[33], s_g0[32];
+  __shared__ int s_g0[32], s_ng[32];
   __shared__ uint4 s_img[(TN + 1) * 12];   // up to K = 96; one padding unit per k-chunk keeps the transposing stores conflict-free
   const int TK = KC * 8;
   const uint32_t IMG_BYTES = img_bytes(TK), TILE_BYTES = 2 * IMG_BYTES;
   const int64_t tile = blockIdx.x >> 1;
   const int which = blockIdx.x & 1, t = threadIdx.x;
   if (tile >= n_tiles) return;
-  if (row_src) {
-    if (t < TN) s_src[t] = row_src[tile * TN + t];
-  } else {
-    const TcMeta mt = meta[tile];
-    const int npdf = __popc(mt.gend);
-    if (t < 32) {   // warp 0: column start of each pdf of the tile = exclusive prefix of the padded component counts
-      int ng = 0, g0 = 0;
-      if (t < npdf) { const int pdf = lp2pdf[mt.lp0 + t]; g0 = pdf_off[pdf]; ng = pdf_off[pdf + 1] - g0; }
-      int pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN, inc = pad;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += v; }
-      s_c0[t] = inc - pad; s_g0[t] = g0 | (ng << 24);   // ng <= 128 fits the top byte; g0 < 2^24 Gaussians
-      if (t == 31) s_c0[32] = inc;
+  TcAux *ax = aux + tile;
+  const int W = cls_width(ax->cls), NP = TN / W;
+  if (t < 32) {
+    int g0 = 0, ng = 0;
+    if (t < NP) {
+      const int row = ax->row[t];
+      if (row >= 0) { const int pdf = ax->lp_base >= 0 ? lp2pdf[ax->lp_base + row] : row; g0 = pdf_off[pdf]; ng = pdf_off[pdf + 1] - g0; }
     }
-    __syncthreads();
-    if (t < TN) {
-      int g = -1;
-      for (int i = 0; i < npdf; i++) {
-        const int c = t - s_c0[i], ng = s_g0[i] >> 24;
-        if (c >= 0 && c < ng) { g = (s_g0[i] & 0xFFFFFF) + c; break; }
-      }
-      s_src[t] = g;
-    }
+    s_g0[t] = g0; s_ng[t] = ng;
   }
   __syncthreads();
-  if (t < TN && g_out && which == 0) { const int g = s_src[t]; g_out[tile * TN + t] = g >= 0 ? g_src[g] : -60000.0f; }
+  if (t < TN) {
+    const int j = t / W, c = t - j * W;
+    const int g = (j < NP && c < s_ng[j]) ? s_g0[j] + c : -1;
+    s_src[t] = g;
+    if (which == 0) ax->g[t] = g >= 0 ? g_src[g] : -60000.0f;
+  }
+  __syncthreads();
   for (int c = t; c < TN * KC; c += 256) {
     const int r = c / KC, kc = c - r * KC;
     const int g = s_src[r];
@@ -419,36 +494,42 @@ gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, const int3
   for (int c = t; c < TN * KC; c += 256) dst[c] = s_img[(c >> 7) * (TN + 1) + (c & (TN - 1))];
 }
 
-// Per-utterance tile plan of the ragged path, on the device (it is rebuilt whenever an M-step changed some pdf's component count):
-// one thread per utterance walks its pdf list (sorted pdf ids, graphs' lp2pdf) and packs the padded component counts into 128-column
-// tiles that never split a pdf.  fill == 0: tile count per utterance; fill == 1: the tiles' TcMeta at tile_off[u].
+// Per-utterance tile plan of the ragged path, on the device (rebuilt whenever an M-step changed some pdf's component count): one
+// thread per utterance walks its pdf list (graphs' lp2pdf), counts the pdfs per width class (fill == 0: tiles per utterance) and, given
+// the utterance's first tile (fill == 1), writes the tiles' class / rows: tiles of a class are consecutive, classes ascending.
 __global__ void rag_plan_kernel(int n_utts, const int64_t *__restrict__ lp_off, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off,
-                                int fill, int32_t *__restrict__ n_tiles_out, const int64_t *__restrict__ tile_off, TcMeta *__restrict__ meta) {
+                                int fill, int32_t *__restrict__ n_tiles_out, const int64_t *__restrict__ tile_off, TcAux *__restrict__ aux) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n_utts) return;
   const int64_t k0 = lp_off[u], k1 = lp_off[u + 1];
-  int col = TN;   // forces a new tile at the first pdf
-  int64_t t = (fill ? tile_off[u] : 0) - 1;
-  TcMeta cur{};
+  int cnt[NCLS];
+#pragma unroll
+  for (int c = 0; c < NCLS; c++) cnt[c] = 0;
+  for (int64_t k = k0; k < k1; k++) { const int pdf = lp2pdf[k]; cnt[cls_of(pdf_off[pdf + 1] - pdf_off[pdf])]++; }
+  int64_t base[NCLS];
+  int64_t t = fill ? tile_off[u] : 0;
+  for (int c = 0; c < NCLS; c++) {
+    base[c] = t;
+    const int nt = (cnt[c] + cls_cap(c) - 1) / cls_cap(c);
+    if (fill)
+      for (int i = 0; i < nt; i++) {
+        TcAux *ax = aux + t + i;
+        ax->cls = c; ax->lp_base = (int32_t)k0;
+        const int left = cnt[c] - i * cls_cap(c);
+        ax->npdf = left < cls_cap(c) ? left : cls_cap(c);
+        for (int j = 0; j < 32; j++) ax->row[j] = -1;
+      }
+    t += nt;
+    cnt[c] = 0;
+  }
+  if (!fill) { n_tiles_out[u] = (int)t; return; }
   for (int64_t k = k0; k < k1; k++) {
     const int pdf = lp2pdf[k];
-    const int ng = pdf_off[pdf + 1] - pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
-    if (col + pad > TN) {
-      if (fill && k > k0) { if (col < TN) cur.gstart |= 1u << (col / 4); meta[t] = cur; }   // trailing padding: a junk segment that never ends
-      t++;
-      cur.gstart = 0; cur.gend = 0; cur.pdf0 = (int32_t)(k - k0); cur.lp0 = (int32_t)k;
-      col = 0;
-    }
-    cur.gstart |= 1u << (col / 4);
-    cur.gend |= 1u << ((col + pad - 1) / 4);
-    col += pad;
+    const int c = cls_of(pdf_off[pdf + 1] - pdf_off[pdf]);
+    const int slot = cnt[c]++;
+    aux[base[c] + slot / cls_cap(c)].row[slot % cls_cap(c)] = (int32_t)(k - k0);
   }
-  if (fill && k1 > k0) { if (col < TN) cur.gstart |= 1u << (col / 4); meta[t] = cur; }
-  if (!fill) n_tiles_out[u] = (int)(t + 1);
 }
-
-// the dense per-tile gconst array follows the per-Gaussian one; bulk copies need a 16-byte aligned source
-static inline size_t tc_gpad(int64_t G) { return (size_t)((G + 3) & ~(int64_t)3); }
 
 // ---- operand images from the device-resident natural-layout parameters (model creation and after every device M-step) ----
 // second moments about zero per dimension (features are not re-centred): m2[d] += mu^2 + sigma^2 over the Gaussians
@@ -511,7 +592,27 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
   const uint32_t TILE_BYTES = tile_bytes(TK);
   const bool geometry_changed = m->tc_k != TK;
   m->tc_k = TK;
-  const int nt = m->n_tiles;
+  // dense tiling (all pdfs) by width class, from the host's copy of the layout
+  std::vector<std::vector<int32_t>> by_cls(NCLS);
+  for (int p = 0; p < m->num_pdfs; p++) {
+    const int ng = m->h_pdf_off[p + 1] - m->h_pdf_off[p];
+    if (ng <= 0) return set_error(MFA_ERR_INVALID, "pdf " + std::to_string(p) + " has no Gaussians");
+    if (ng > TN) { m->tc_unsupported = true; return set_error(MFA_ERR_UNSUPPORTED, "pdf " + std::to_string(p) + " has more than 128 Gaussians"); }
+    by_cls[cls_of(ng)].push_back(p);
+  }
+  std::vector<TcAux> aux;
+  for (int c = 0; c < NCLS; c++)
+    for (size_t i = 0; i < by_cls[c].size(); i += (size_t)cls_cap(c)) {
+      TcAux a;
+      memset(&a, 0, sizeof(a));
+      a.cls = c; a.lp_base = -1;
+      for (int j = 0; j < 32; j++) a.row[j] = -1;
+      a.npdf = (int32_t)std::min<size_t>((size_t)cls_cap(c), by_cls[c].size() - i);
+      for (int j = 0; j < a.npdf; j++) a.row[j] = by_cls[c][i + j];
+      aux.push_back(a);
+    }
+  const int nt = (int)aux.size();
+  m->tc_n_tiles = nt;
   cudaStream_t s = e->stream;
   if (!m->d_tc_colscale) CUDA_TRY(cudaMalloc((void **)&m->d_tc_colscale, 64 * sizeof(float)));
   if (!m->d_tc_flag) CUDA_TRY(cudaMalloc((void **)&m->d_tc_flag, 64 * sizeof(double) + 16));   // flag | m2[64]
@@ -522,12 +623,10 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
     for (void **p : {&m->d_tc_rows, (void **)&m->d_tc_g, &m->d_tc_w}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
     m->tc_cap_gauss = (size_t)G + (size_t)G / 8 + 64;
   }
-  const size_t img_total = (size_t)nt * TILE_BYTES, meta_bytes = (size_t)nt * sizeof(TcMeta);
-  const bool new_dense = m->d_tc_w == nullptr;
+  const size_t img_total = (size_t)nt * TILE_BYTES, aux_bytes = (size_t)nt * sizeof(TcAux);
   if (!m->d_tc_rows) CUDA_TRY(cudaMalloc(&m->d_tc_rows, (size_t)2 * m->tc_cap_gauss * TK * sizeof(__half)));
-  // per Gaussian | dense per-tile array: the tile count can only be bounded by the number of pdfs
-  if (!m->d_tc_g) CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, (tc_gpad((int64_t)m->tc_cap_gauss) + (size_t)m->num_pdfs * TN + TN) * sizeof(float)));
-  if (new_dense) CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + meta_bytes));
+  if (!m->d_tc_g) CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, m->tc_cap_gauss * sizeof(float)));
+  if (!m->d_tc_w) CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + aux_bytes));
   m->tc_w_bytes = img_total;
   tc_moment_kernel<<<std::min(G, 4 * e->sm_count), 128, 0, s>>>(m->d_miv, m->d_iv, G, D, d_m2);
   tc_colscale_kernel<<<1, 64, 0, s>>>(d_m2, G, D, m->d_tc_colscale);
@@ -536,28 +635,12 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
                                                               (__half *)m->d_tc_rows, m->d_tc_g, m->d_tc_flag);
   e->launches += 3;
   CUDA_TRY(cudaGetLastError());
-  // dense tiling (all pdfs): per-tile masks + source rows from the host's copy of the layout; the images are gathered on the device
-  std::vector<int32_t> row_src((size_t)nt * TN, -1);
-  std::vector<TcMeta> meta(nt);
-  for (int tl = 0; tl < nt; tl++) {
-    int col = 0;
-    memset(&meta[tl], 0, sizeof(TcMeta));
-    meta[tl].pdf0 = m->h_tile_pdf0[tl];
-    for (int pdf = m->h_tile_pdf0[tl]; pdf < m->h_tile_pdf0[tl + 1]; pdf++) {
-      const int ng = m->h_pdf_off[pdf + 1] - m->h_pdf_off[pdf], pad = (ng + MFA_SEG_ALIGN - 1) / MFA_SEG_ALIGN * MFA_SEG_ALIGN;
-      meta[tl].gstart |= 1u << (col / 4);
-      meta[tl].gend |= 1u << ((col + pad - 1) / 4);
-      for (int k = 0; k < ng; k++) row_src[(size_t)tl * TN + col + k] = m->h_pdf_off[pdf] + k;
-      col += pad;
-    }
-    if (col < TN) meta[tl].gstart |= 1u << (col / 4);  // trailing padding: one junk segment that never ends
-  }
-  int32_t *d_src; TcMeta *d_meta_stage;
-  MFA_TRY(e->upload(DB_SCRATCH, row_src.data(), row_src.size(), &d_src));
-  MFA_TRY(e->upload(DB_TC_ITEMS, meta.data(), meta.size(), &d_meta_stage));
-  CUDA_TRY(cudaMemcpyAsync((uint8_t *)m->d_tc_w + img_total, d_meta_stage, meta_bytes, cudaMemcpyDeviceToDevice, s));
-  gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, d_src, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D,
-                                                    KC, m->d_tc_g, k80 ? m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss) : nullptr, nullptr, nullptr, nullptr);
+  TcAux *d_aux_stage;
+  MFA_TRY(e->upload(DB_TC_ITEMS, aux.data(), aux.size(), &d_aux_stage));
+  TcAux *d_aux = (TcAux *)((uint8_t *)m->d_tc_w + img_total);
+  CUDA_TRY(cudaMemcpyAsync(d_aux, d_aux_stage, aux_bytes, cudaMemcpyDeviceToDevice, s));
+  gather_b_kernel<<<(unsigned)(2 * nt), 256, 0, s>>>((const __half *)m->d_tc_rows, G, (uint8_t *)m->d_tc_w, nt, k80 ? -1 : 2 * D, KC, m->d_tc_g, d_aux,
+                                                    nullptr, m->d_pdf_off);
   e->launches++;
   int32_t h_flag = 0;
   CUDA_TRY(cudaMemcpyAsync(&h_flag, m->d_tc_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -577,19 +660,38 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
 
 namespace {
 
-int launch_tc(mfa_engine *e, const TcParams &p, int tk) {
+int launch_tc(mfa_engine *e, const TcParams &p_in, int tk) {
+  TcParams p = p_in;
   const int grid = std::min(p.n_items, e->sm_count);
+#if MFA_TC_EXP == 7
+  static long long *d_dbg = nullptr;
+  if (!d_dbg) cudaMalloc((void **)&d_dbg, 1024 * 16 * sizeof(long long));
+  cudaMemsetAsync(d_dbg, 0, 1024 * 16 * sizeof(long long), e->stream);
+  p.dbg = d_dbg;
+#endif
   if (tk == 80) {
-    const size_t smem = 5 * (size_t)tile_bytes(80) + 1024 + 256;
+    const size_t smem = 5 * (size_t)tile_bytes(80) + 2 * AUX_BYTES + 256;
     CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<80, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_tc_kernel<80, 3, true><<<grid, NTHREADS, smem, e->stream>>>(p);
   } else {
-    const size_t smem = 4 * (size_t)tile_bytes(96) + 1024 + 256;
+    const size_t smem = 4 * (size_t)tile_bytes(96) + 2 * AUX_BYTES + 256;
     CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<96, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gmm_tc_kernel<96, 2, false><<<grid, NTHREADS, smem, e->stream>>>(p);
   }
   e->launches++;
   CUDA_TRY(cudaGetLastError());
+#if MFA_TC_EXP == 7
+  {
+    cudaStreamSynchronize(e->stream);
+    std::vector<long long> h(1024 * 16);
+    cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double a[16] = {0};
+    for (int b = 0; b < grid; b++) for (int k = 0; k < 16; k++) a[k] += (double)h[b * 16 + k] / grid;
+    fprintf(stderr, "[tc-exp7] per CTA (cycles): producer wait empty_a %.0f empty_b %.0f | aux producer wait gempty %.0f | issuer wait full_a %.0f full_b %.0f "
+                    "tempty %.0f, issue+commit %.0f, loop %.0f, accumulators %.0f | epilogue warp 4: wait tfull %.0f gfull %.0f body %.0f tiles %.0f\n",
+            a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[12], a[8], a[9], a[10], a[11]);
+  }
+#endif
   return MFA_OK;
 }
 
@@ -613,6 +715,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   }
   const int TK = m->tc_k, KC = TK / 8;
   const uint32_t TILE_BYTES = tile_bytes(TK);
+  const int nt = m->tc_n_tiles;
   const int64_t n_ftiles = (n_rows + TM - 1) / TM, n_pairs = (n_ftiles + 1) / 2;
   uint8_t *d_a;
   MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_pairs * 2 * TILE_BYTES, &d_a));
@@ -621,27 +724,89 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
                                                                          TK == 96);
   e->launches++;
   int splits = 1;
-  if (n_pairs < 2 * (int64_t)e->sm_count) splits = (int)std::min<int64_t>(m->n_tiles, (2 * (int64_t)e->sm_count + n_pairs - 1) / n_pairs);
-  const int tps = (m->n_tiles + splits - 1) / splits;
-  splits = (m->n_tiles + tps - 1) / tps;
+  if (n_pairs < 2 * (int64_t)e->sm_count) splits = (int)std::min<int64_t>(nt, (2 * (int64_t)e->sm_count + n_pairs - 1) / n_pairs);
+  const int tps = (nt + splits - 1) / splits;
+  splits = (nt + tps - 1) / tps;
   std::vector<TcItem> items;
   items.reserve((size_t)n_pairs * splits);
   for (int64_t pr = 0; pr < n_pairs; pr++)
     for (int sp = 0; sp < splits; sp++) {
       TcItem I{};
-      I.a_tile = (uint32_t)(2 * pr); I.b_tile0 = (uint32_t)(sp * tps); I.n_b = (uint32_t)std::min(tps, m->n_tiles - sp * tps);
+      I.a_tile = (uint32_t)(2 * pr); I.b_tile0 = (uint32_t)(sp * tps); I.n_b = (uint32_t)std::min(tps, nt - sp * tps);
       I.rows_valid = (uint32_t)std::min<int64_t>(2 * TM, ld - pr * 2 * TM); I.out_off = (uint64_t)(pr * 2 * TM); I.ld = (uint32_t)ld;
       items.push_back(I);
     }
-  if (ld > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "leading dimension exceeds 2^32 frames");
+  if ((int64_t)m->num_pdfs * ld > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "log-likelihood block exceeds 2^32 floats: chunk the frames");
   TcItem *d_items;
   MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
   TcParams p;
-  p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.meta = (const TcMeta *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
+  p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.aux = (const TcAux *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
-  p.g_tiles = m->d_tc_g + tc_gpad((int64_t)m->tc_cap_gauss);
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
   return launch_tc(e, p, TK);
+}
+
+// ---- plan (cached per (graphs, model layout)), built on the device: per utterance, its pdfs by width class into 128-column tiles
+static int ensure_rag_plan(mfa_engine *e, mfa_model *m, mfa_graphs *g) {
+  if (!m->tc_ready) MFA_TRY(build_tc_device(m, true));
+  if (g->rag_version == m->tc_version) return MFA_OK;
+  if (g->lp_off[g->n_utts] > 0x7fffffffLL) return set_error(MFA_ERR_UNSUPPORTED, "more than 2^31 (utterance, pdf) pairs in one graph batch");
+  for (int64_t k = 0; k < g->lp_off[g->n_utts]; k++)
+    if (g->lp2pdf[k] < 0 || g->lp2pdf[k] >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
+  const int nu = g->n_utts;
+  int32_t *d_cnt; int32_t *h_cnt;
+  MFA_TRY(e->getT<int32_t>(DB_RAG_CNT, (size_t)nu + 1, &d_cnt));
+  { void *pp; MFA_TRY(e->get_pinned(PB_D, ((size_t)nu + 1) * sizeof(int32_t), &pp)); h_cnt = (int32_t *)pp; }
+  rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 0, d_cnt, nullptr, nullptr);
+  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)nu * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  g->rag_tile_off.assign((size_t)nu + 1, 0);
+  for (int u = 0; u < nu; u++) g->rag_tile_off[u + 1] = g->rag_tile_off[u] + h_cnt[u];
+  const size_t n_aux = (size_t)g->rag_tile_off[nu];
+  if (g->d_rag && n_aux * sizeof(TcAux) > g->rag_meta_bytes) { CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
+  if (!g->d_rag) {
+    g->rag_meta_bytes = (n_aux + n_aux / 8 + 64) * sizeof(TcAux);
+    CUDA_TRY(cudaMalloc(&g->d_rag, g->rag_meta_bytes));
+  }
+  int64_t *d_toff;
+  MFA_TRY(e->upload(DB_TILE_ROW0, g->rag_tile_off.data(), g->rag_tile_off.size(), &d_toff));
+  rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 1, nullptr, d_toff, (TcAux *)g->d_rag);
+  e->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  g->rag_version = m->tc_version;
+  e->pf_g = nullptr;
+  return MFA_OK;
+}
+
+// B images (and the gconst column of the tiles' side data) of utterances [utt0, utt0 + n_utts) into DB_BIMG on stream `st`
+static int gather_range(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, cudaStream_t st, uint8_t **d_b_out) {
+  const int TK = m->tc_k, KC = TK / 8;
+  const uint32_t TILE_BYTES = tile_bytes(TK);
+  const int64_t bt0 = g->rag_tile_off[utt0], n_bt = g->rag_tile_off[utt0 + n_utts] - bt0;
+  uint8_t *d_b;
+  MFA_TRY(e->getT<uint8_t>(DB_BIMG, (size_t)std::max<int64_t>(n_bt, 1) * TILE_BYTES, &d_b));
+  *d_b_out = d_b;
+  if (n_bt == 0) return MFA_OK;
+  gather_b_kernel<<<(unsigned)(2 * n_bt), 256, 0, st>>>((const __half *)m->d_tc_rows, m->num_gauss, d_b, n_bt, TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g,
+                                                       (TcAux *)g->d_rag + bt0, g->d_lp2pdf, m->d_pdf_off);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return MFA_OK;
+}
+
+// The gather depends on the model and the graphs only, not on the audio: the fused pipeline starts it on a side stream before K1, so the
+// ~1.4 ms (10 h) of HBM-bound image building hide behind the issue-bound MFCC kernel instead of sitting in front of the tensor-core kernel.
+int prefetch_b_images(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts) {
+  if (n_utts <= 0) return MFA_OK;
+  MFA_TRY(ensure_rag_plan(e, m, g));
+  cudaStream_t st = e->side[mfa_engine::kSide - 1];
+  CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));      // everything queued so far (the previous call's readers of DB_BIMG) comes first
+  CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fork, 0));
+  uint8_t *d_b;
+  MFA_TRY(gather_range(e, m, g, utt0, n_utts, st, &d_b));
+  CUDA_TRY(cudaEventRecord(e->ev_bimg, st));
+  e->pf_g = g; e->pf_m = m; e->pf_u0 = utt0; e->pf_u1 = utt0 + n_utts;
+  return MFA_OK;
 }
 
 // ragged: for each utterance only the pdfs its graph references (g->lp2pdf), output block per utterance [P_u][ld_u]
@@ -649,43 +814,17 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
 int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts, const float *d_feats, const int64_t *h_row_off,
                          const int64_t *h_frame_off, float *d_out, const int64_t *h_ll_off, const int64_t *h_ld) {
   if (n_utts == 0) return MFA_OK;
-  if (!m->tc_ready) MFA_TRY(build_tc_device(m, true));
+  MFA_TRY(ensure_rag_plan(e, m, g));
   const int TK = m->tc_k, KC = TK / 8;
   const uint32_t TILE_BYTES = tile_bytes(TK);
-  // ---- plan (cached per (graphs, model tiling)): per utterance, pack its local pdfs into 128-column tiles
-  if (g->rag_version != m->tc_version) {
-    if (g->lp_off[g->n_utts] > 0x7fffffffLL) return set_error(MFA_ERR_UNSUPPORTED, "more than 2^31 (utterance, pdf) pairs in one graph batch");
-    for (int64_t k = 0; k < g->lp_off[g->n_utts]; k++)
-      if (g->lp2pdf[k] < 0 || g->lp2pdf[k] >= m->num_pdfs) return set_error(MFA_ERR_INVALID, "graph references a pdf outside the model");
-    const int nu = g->n_utts;
-    int32_t *d_cnt; int32_t *h_cnt;
-    MFA_TRY(e->getT<int32_t>(DB_RAG_CNT, (size_t)nu + 1, &d_cnt));
-    { void *pp; MFA_TRY(e->get_pinned(PB_D, ((size_t)nu + 1) * sizeof(int32_t), &pp)); h_cnt = (int32_t *)pp; }
-    rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 0, d_cnt, nullptr, nullptr);
-    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)nu * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-    g->rag_tile_off.assign((size_t)nu + 1, 0);
-    for (int u = 0; u < nu; u++) g->rag_tile_off[u + 1] = g->rag_tile_off[u] + h_cnt[u];
-    const size_t n_meta = (size_t)g->rag_tile_off[nu];
-    if (g->d_rag && n_meta * sizeof(TcMeta) > g->rag_meta_bytes) { CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
-    if (!g->d_rag) {
-      g->rag_meta_bytes = (n_meta + n_meta / 8 + 64) * sizeof(TcMeta);
-      CUDA_TRY(cudaMalloc(&g->d_rag, g->rag_meta_bytes));
-    }
-    int64_t *d_toff;
-    MFA_TRY(e->upload(DB_TILE_ROW0, g->rag_tile_off.data(), g->rag_tile_off.size(), &d_toff));
-    rag_plan_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, e->stream>>>(nu, g->d_lp_off, g->d_lp2pdf, m->d_pdf_off, 1, nullptr, d_toff, (TcMeta *)g->d_rag);
-    e->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-    g->rag_version = m->tc_version;
-  }
   const int64_t bt0 = g->rag_tile_off[utt0], n_bt = g->rag_tile_off[utt0 + n_utts] - bt0;
   // ---- frame tiles follow utterance boundaries (pairs of 128 frames)
   std::vector<int64_t> tile_row0; std::vector<int32_t> tile_rows; std::vector<TcItem> items;
   for (int u = 0; u < n_utts; u++) {
     const int64_t T = h_frame_off[u + 1] - h_frame_off[u];
     const int64_t nb = g->rag_tile_off[utt0 + u + 1] - g->rag_tile_off[utt0 + u];
-    if (h_ld[u] > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "utterance longer than 2^32 frames");
+    const int64_t P_u = g->lp_off[utt0 + u + 1] - g->lp_off[utt0 + u];
+    if (P_u * h_ld[u] > 0xFFFFFFFFLL) return set_error(MFA_ERR_UNSUPPORTED, "an utterance's log-likelihood block exceeds 2^32 floats");
     for (int64_t r0 = 0; r0 < T; r0 += 2 * TM) {
       TcItem I{};
       I.a_tile = (uint32_t)tile_row0.size();
@@ -704,21 +843,24 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
   const int64_t n_at = (int64_t)tile_row0.size();
   uint8_t *d_a, *d_b; int64_t *d_row0; int32_t *d_rows; TcItem *d_items;
   MFA_TRY(e->getT<uint8_t>(DB_XSPLIT, (size_t)n_at * TILE_BYTES, &d_a));
-  MFA_TRY(e->getT<uint8_t>(DB_BIMG, (size_t)n_bt * TILE_BYTES + (size_t)n_bt * TN * sizeof(float), &d_b));
-  float *d_gt = (float *)(d_b + (size_t)n_bt * TILE_BYTES);   // per-tile gconsts behind the images (TILE_BYTES is a multiple of 16)
   MFA_TRY(e->upload(DB_TILE_ROW0, tile_row0.data(), tile_row0.size(), &d_row0));
   MFA_TRY(e->upload(DB_TILE_ROWS, tile_rows.data(), tile_rows.size(), &d_rows));
   MFA_TRY(e->upload(DB_TC_ITEMS, items.data(), items.size(), &d_items));
   const int64_t tot_a = n_at * KC * TM;
   xsplit_kernel<<<(unsigned)((tot_a + 255) / 256), 256, 0, e->stream>>>(d_feats, m->dim, m->d_tc_colscale, d_a, n_at, d_row0, d_rows, 0, KC, TK == 96);
   e->launches++;
-  gather_b_kernel<<<(unsigned)(2 * n_bt), 256, 0, e->stream>>>((const __half *)m->d_tc_rows, m->num_gauss, nullptr, d_b, n_bt,
-                                                                           TK == 80 ? -1 : 2 * m->dim, KC, m->d_tc_g, TK == 80 ? d_gt : nullptr,
-                                                                           (const TcMeta *)g->d_rag + bt0, g->d_lp2pdf, m->d_pdf_off);
-  e->launches++;
+  if (e->pf_g == g && e->pf_m == m && utt0 >= e->pf_u0 && utt0 + n_utts <= e->pf_u1) {
+    // images gathered ahead on the side stream: this launch covers a sub-range of them
+    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_bimg, 0));
+    d_b = (uint8_t *)e->dev[DB_BIMG].p + (size_t)(bt0 - g->rag_tile_off[e->pf_u0]) * TILE_BYTES;
+    if (utt0 + n_utts == e->pf_u1) e->pf_g = nullptr;   // consumed
+  } else {
+    e->pf_g = nullptr;
+    MFA_TRY(gather_range(e, m, g, utt0, n_utts, e->stream, &d_b));
+  }
+  TcAux *d_aux = (TcAux *)g->d_rag + bt0;
   TcParams p;
-  p.a_img = d_a; p.b_img = d_b; p.meta = (const TcMeta *)g->d_rag + bt0; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
-  p.g_tiles = d_gt;
+  p.a_img = d_a; p.b_img = d_b; p.aux = d_aux; p.items = d_items; p.n_items = (int)items.size(); p.out = d_out;
   return launch_tc(e, p, TK);
 }
 

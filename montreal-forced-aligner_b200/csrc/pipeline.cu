@@ -337,6 +337,16 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   }
   if (seg_begin.size() == 1) stream = false;
   seg_begin.push_back(n_utts);
+  if (ragged) {
+    // B images of the first chunk (the whole batch when it fits the workspace) start building now, under K1
+    int n_first = n_utts;
+    if (!stream) {
+      std::vector<ChunkPlan> first;
+      MFA_TRY(plan_chunks(g, frame_off, seg_begin[1], P, D, budget, first, true, 0));
+      n_first = first.empty() ? 0 : first[0].n;
+    }
+    MFA_TRY(prefetch_b_images(e, m, g, 0, n_first));
+  }
   // ---- uploads (host PCM): pieces of >= 32 MB that never straddle a segment
   struct Piece { int u0, u1, ev; };
   std::vector<Piece> pieces;
