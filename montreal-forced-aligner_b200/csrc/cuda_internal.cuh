@@ -42,7 +42,7 @@ struct mfa_engine_cfg {
   int pipeline_split = -1;     // host-PCM path: -1 auto, 0 whole, 1 every stage per segment, 2 stream (K1..K2 per segment, one K3)
   int acc_impl = 0;            // K4: 0 counting sort + register accumulation, 1 first version (f64 atomics)
   int tc_k96 = 0;              // K2: 1 forces the K = 96 operand geometry
-  int tc_poly = -1;            // K2 epilogue: groups (of 8 per 32-column chunk) whose exp2 runs as an FMA polynomial (-1: default)
+  int tc_poly = 0;             // K2 epilogue: 1 = every fourth exp2 runs as an FMA-pipe polynomial instead of MUFU.EX2 (A/B switch)
   int mfcc_generic = 0;        // K1: 1 forces the generic (shared-memory FFT) kernel
   int trace = 0;               // print host enqueue times per stage
 };

@@ -125,6 +125,21 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// exp2 on the FMA pipe (Cody-Waite range reduction + degree-5 polynomial, ~2e-7 relative on x <= 0): an alternative to MUFU.EX2 for a
+// fraction of the epilogue's exponentials (engine option tc_poly; A/B measured in DESIGN.md section 8).  x <= 0; results below 2^-126 flush to 0.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);           // in [-0.5, 0.5]
+  float p = 1.33336498402e-3f;
+  p = fmaf(p, f, 9.61812911e-3f);
+  p = fmaf(p, f, 5.55041087e-2f);
+  p = fmaf(p, f, 2.40226507e-1f);
+  p = fmaf(p, f, 6.93147181e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
@@ -140,7 +155,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- epilogue of one accumulator (128 frames x 128 columns) whose tile has width class W: thread = frame (TMEM lane).  The tile's
 // pdf slot j owns columns [j W, (j + 1) W); the accumulator is read in four 32-column chunks, a pdf that straddles a chunk edge carries
 // (max, sum) across it.  Everything about the segmentation is a compile-time constant after unrolling.
-template <int W, bool GEPI>
+template <int W, bool GEPI, bool POLY>
 __device__ __forceinline__ void epi_tile(const uint32_t t0, const TcAux *__restrict__ ax, float *__restrict__ out_base, const uint32_t ld,
                                          const bool row_ok, uint64_t *tempty_bar) {
   constexpr int NP = TN / W;                       // pdf slots per tile
@@ -185,7 +200,7 @@ __device__ __forceinline__ void epi_tile(const uint32_t t0, const TcAux *__restr
         if (lo + 4 * q4 >= hi) break;
         const int i = lo + 4 * q4;
         s0 += ex2(__uint_as_float(v[i]) - m) + ex2(__uint_as_float(v[i + 2]) - m);
-        s1 += ex2(__uint_as_float(v[i + 1]) - m) + ex2(__uint_as_float(v[i + 3]) - m);
+        s1 += ex2(__uint_as_float(v[i + 1]) - m) + (POLY ? ex2_poly(__uint_as_float(v[i + 3]) - m) : ex2(__uint_as_float(v[i + 3]) - m));
       }
       const float s = s0 + s1;
       if (ends) {
@@ -229,7 +244,7 @@ struct TcParams {
 #define DBG_ADD(slot)
 #endif
 
-template <int TKt, int NBt, bool GEPI>
+template <int TKt, int NBt, bool GEPI, bool POLY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gmm_tc_kernel(TcParams p) {
   constexpr uint32_t IMG_BYTES = img_bytes(TKt), TILE_BYTES = tile_bytes(TKt);
@@ -385,17 +400,17 @@ gmm_tc_kernel(TcParams p) {
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         uint64_t *tb = tempty + s * 2 + f;
         switch (ax->cls) {   // uniform across the CTA: one class per tile
-          case 0: epi_tile<4, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 1: epi_tile<8, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 2: epi_tile<12, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 3: epi_tile<16, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 4: epi_tile<20, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 5: epi_tile<24, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 6: epi_tile<28, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 7: epi_tile<32, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 8: epi_tile<48, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 9: epi_tile<64, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          default: epi_tile<128, GEPI>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 0: epi_tile<4, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 1: epi_tile<8, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 2: epi_tile<12, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 3: epi_tile<16, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 4: epi_tile<20, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 5: epi_tile<24, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 6: epi_tile<28, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 7: epi_tile<32, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 8: epi_tile<48, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 9: epi_tile<64, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          default: epi_tile<128, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
         }
         mbar_arrive(gempty + s);   // this thread is done with the stage's side data
 #if MFA_TC_EXP == 7
@@ -660,6 +675,14 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
 
 namespace {
 
+template <int TKt, int NBt, bool GEPI, bool POLY>
+static int launch_tc_t(mfa_engine *e, const TcParams &p, int grid) {
+  const size_t smem = (2 + NBt) * (size_t)tile_bytes(TKt) + 2 * AUX_BYTES + 256;
+  CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<TKt, NBt, GEPI, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gmm_tc_kernel<TKt, NBt, GEPI, POLY><<<grid, NTHREADS, smem, e->stream>>>(p);
+  return MFA_OK;
+}
+
 int launch_tc(mfa_engine *e, const TcParams &p_in, int tk) {
   TcParams p = p_in;
   const int grid = std::min(p.n_items, e->sm_count);
@@ -669,15 +692,9 @@ int launch_tc(mfa_engine *e, const TcParams &p_in, int tk) {
   cudaMemsetAsync(d_dbg, 0, 1024 * 16 * sizeof(long long), e->stream);
   p.dbg = d_dbg;
 #endif
-  if (tk == 80) {
-    const size_t smem = 5 * (size_t)tile_bytes(80) + 2 * AUX_BYTES + 256;
-    CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<80, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tc_kernel<80, 3, true><<<grid, NTHREADS, smem, e->stream>>>(p);
-  } else {
-    const size_t smem = 4 * (size_t)tile_bytes(96) + 2 * AUX_BYTES + 256;
-    CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<96, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gmm_tc_kernel<96, 2, false><<<grid, NTHREADS, smem, e->stream>>>(p);
-  }
+  const bool poly = e->cfg.tc_poly > 0;   // one in four exponentials on the FMA pipe
+  if (tk == 80) MFA_TRY(poly ? (launch_tc_t<80, 3, true, true>(e, p, grid)) : (launch_tc_t<80, 3, true, false>(e, p, grid)));
+  else MFA_TRY(poly ? (launch_tc_t<96, 2, false, true>(e, p, grid)) : (launch_tc_t<96, 2, false, false>(e, p, grid)));
   e->launches++;
   CUDA_TRY(cudaGetLastError());
 #if MFA_TC_EXP == 7
