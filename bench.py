@@ -573,6 +573,7 @@ def main():
     ap.add_argument("--train-iters", type=int, default=4, help="iterations of the align -> acc-stats -> all-reduce -> update loop timed under extras.train_loop")
     ap.add_argument("--extras-dist", action="store_true", help="multi-rank runs: also time K4 / K5 / the SAT two-pass flow per rank (the training loop with its NCCL all-reduce always runs)")
     ap.add_argument("--same-shards", action="store_true", help="multi-rank runs: every rank gets the SAME corpus (seed 1234): separates data effects (a rank owning a slow utterance) from system effects in the per-rank table")
+    ap.add_argument("--seed-offset", type=int, default=None, help="corpus seed = 1234 + this instead of 1234 + rank: reproduces a given rank's shard of a multi-GPU run on one GPU")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin this process to the CPUs of the GPU's NUMA node")
     ap.add_argument("--sweep-max", type=int, default=100000, help="largest utterance count of the config-5 MFCC sweep under extras (1000000 = BASELINE's full sweep; ~10 s more)")
     ap.add_argument("--no-extras", action="store_true", help="skip the K4 / K5 timings reported under 'extras'")
@@ -609,8 +610,16 @@ def main():
     cores = os.cpu_count() or 1
     seconds = args.hours * 3600.0
     t0 = time.time()
-    sc = SC.build(eng, seconds, seed=1234 + (0 if args.same_shards else rank), target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
-                  synth_device=dev, log=log if rank == 0 else None, model_seed=1234 if world > 1 else None)
+    sc = SC.build(eng, seconds, seed=1234 + (args.seed_offset if args.seed_offset is not None else (0 if args.same_shards else rank)), target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=max(1, cores // max(1, world)),
+                  synth_device=dev, log=log if rank == 0 else None, model_seed=1234 if (world > 1 or args.seed_offset is not None) else None)
+    if args.seed_offset:
+        # reproduce rank `seed_offset` of a multi-GPU run: that rank aligns ITS shard with rank 0's acoustic model
+        sc0 = SC.build(eng, seconds, seed=1234, target_pdfs=args.pdfs, gauss_per_pdf=args.gauss_per_pdf, n_threads=cores, synth_device=dev, model_seed=1234)
+        sc.am = sc0.am
+        sc.model.close()
+        sc.model = E.DeviceModel(eng, sc.tm, sc.am)
+        sc0.model.close(); sc0.graphs.close(); sc0.batch.close()
+        del sc0
     if dist is not None:
         # one replicated acoustic model (rank 0's estimate), each rank its own shard of utterances: what MFA's jobs see
         box = [(sc.am.dim, sc.am.offsets, sc.am.weights, sc.am.means_invvars, sc.am.inv_vars) if rank == 0 else None]

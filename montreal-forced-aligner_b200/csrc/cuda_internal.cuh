@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -34,6 +34,7 @@ enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 struct mfa_engine_cfg {
   int vit_band = 1;            // 0: every utterance on the sparse Viterbi kernel
   int vit_maxgroups = 8;       // band width in groups of 32 states (1..8); tests narrow it to exercise the fallback
+  int vit_wide = 1;            // 1: utterances that outgrow the band run on the 32-group band kernel before the sparse kernel is asked
   int vit_graph_smem = 0;      // 1: band kernel copies each graph to shared memory (default: read through L1)
   int vit_nw2_kb = -1;         // size classes up to this many KB of shared memory run 2 warps per utterance (-1: 20, or 44 with graph_smem)
   int vit_carveout = 100;      // shared-memory carve-out (percent) of the sparse kernel
@@ -224,7 +225,9 @@ struct ViterbiArgs {
   mfa_align_opts opts;
 };
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
-size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem);   // shared memory the band kernel needs for one utterance
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem, bool wide = false);   // shared memory the band kernel needs for one utterance
+int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, const int32_t *d_fb, int32_t *d_fb2,
+                             int32_t *h_count);
 int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
 int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d_feats, const int32_t *d_ali, const float *d_tid_weight,

@@ -46,7 +46,7 @@ int mfa_engine::get_pinned(int id, size_t bytes, void **out) {
 namespace {
 struct OptionDesc { const char *name; int mfa_engine_cfg::*field; };
 const OptionDesc kOptions[] = {
-    {"vit_band", &mfa_engine_cfg::vit_band}, {"vit_maxgroups", &mfa_engine_cfg::vit_maxgroups}, {"vit_graph_smem", &mfa_engine_cfg::vit_graph_smem},
+    {"vit_band", &mfa_engine_cfg::vit_band}, {"vit_maxgroups", &mfa_engine_cfg::vit_maxgroups}, {"vit_wide", &mfa_engine_cfg::vit_wide}, {"vit_graph_smem", &mfa_engine_cfg::vit_graph_smem},
     {"vit_nw2_kb", &mfa_engine_cfg::vit_nw2_kb}, {"vit_carveout", &mfa_engine_cfg::vit_carveout}, {"vit_carveout_band", &mfa_engine_cfg::vit_carveout_band},
     {"vit_prio", &mfa_engine_cfg::vit_prio}, {"pipeline_split", &mfa_engine_cfg::pipeline_split}, {"acc_impl", &mfa_engine_cfg::acc_impl},
     {"tc_k96", &mfa_engine_cfg::tc_k96}, {"tc_poly", &mfa_engine_cfg::tc_poly}, {"mfcc_generic", &mfa_engine_cfg::mfcc_generic},
@@ -99,8 +99,8 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_bimg, cudaEventDisableTiming));
-  CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, mfa_engine::kFbRing * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
-  memset(e->h_fb_ring, 0, mfa_engine::kFbRing * sizeof(int32_t));
+  CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, (mfa_engine::kFbRing + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(e->h_fb_ring, 0, (mfa_engine::kFbRing + 1) * sizeof(int32_t));
   for (int k = 0; k < 2; k++) {
     CUDA_TRY(cudaMallocHost(&e->stage_mem[k], mfa_engine::kStageBytes));
     CUDA_TRY(cudaEventCreateWithFlags(&e->stage_ev[k], cudaEventDisableTiming));

@@ -553,7 +553,7 @@ viterbi_fallback_kernel(VitParams p, const int32_t *__restrict__ fb, int64_t sla
   const int n = fb[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) { *(volatile int32_t *)h_count = n; __threadfence_system(); }
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int ul = fb[1 + i];
+    const int ul = fb[1 + i] & 0x3FFFFFFF;   // (the top bits carry the attempt at which the band overflowed: the sparse kernel starts over)
     if (too_big[ul]) {   // graph beyond the sparse kernel's shared memory: cannot be retried (reported as a failed alignment)
       if (threadIdx.x == 0) { p.status[ul] = MFA_ALIGN_NO_FINAL; p.num_words[ul] = 0; p.total_like[ul] = 0.0f; }
     } else {
@@ -681,7 +681,17 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
   }
   MFA_TRY(launch_viterbi_sparse(e, a, sparse));
   if (!band.empty()) {
-    // fallback pass over the device-side list (no host read of the count: see viterbi_fallback_kernel)
+    // fallback levels over device-side lists (no host read of a count: see viterbi_band_wide_kernel / viterbi_fallback_kernel):
+    // band (8 groups) -> d_fb -> wide band (32 groups) -> d_fb2 -> sparse kernel
+    if (e->fb_pending + 2 > mfa_engine::kFbRing) { CUDA_TRY(cudaStreamSynchronize(e->stream)); e->harvest_fallbacks(); }
+    const int32_t *d_list = d_fb;
+    if (e->cfg.vit_wide) {
+      int32_t *d_fb2;
+      MFA_TRY(e->getT<int32_t>(DB_FALLBACK2, (size_t)n + 1, &d_fb2));
+      MFA_TRY(launch_viterbi_band_wide(e, a, band, d_fb, d_fb2, e->h_fb_ring + e->fb_pending));
+      e->fb_pending++;
+      d_list = d_fb2;
+    }
     constexpr int kFbCtas = 16;
     const size_t limit = e->smem_optin - 2048;
     std::vector<unsigned char> too_big(n, 0);
@@ -698,13 +708,14 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     uint16_t *d_bp; unsigned char *d_big;
     MFA_TRY(e->getT<uint16_t>(DB_FB_BP, (size_t)slab * ctas + 8, &d_bp));
     MFA_TRY(e->upload(DB_FB_BIG, too_big.data(), too_big.size(), &d_big));
-    if (e->fb_pending == mfa_engine::kFbRing) { CUDA_TRY(cudaStreamSynchronize(e->stream)); e->harvest_fallbacks(); }
     VitParams p = sparse_params(a);
     p.bp = d_bp;
     smem = (smem + 15) / 16 * 16;
     CUDA_TRY(cudaFuncSetAttribute(viterbi_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-    viterbi_fallback_kernel<<<ctas, VT, smem, e->stream>>>(p, d_fb, slab, d_big, e->h_fb_ring + e->fb_pending);
-    e->fb_pending++;
+    // with the wide level in front, band_fallbacks counts the utterances that left the 8-group band; the sparse level's own count goes to
+    // a scratch slot of the ring that is never harvested
+    viterbi_fallback_kernel<<<ctas, VT, smem, e->stream>>>(p, d_list, slab, d_big, e->cfg.vit_wide ? e->h_fb_ring + mfa_engine::kFbRing : e->h_fb_ring + e->fb_pending);
+    if (!e->cfg.vit_wide) e->fb_pending++;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }

@@ -35,12 +35,18 @@
 using namespace mfa;
 
 namespace {
-constexpr int GMAX = 8;              // groups of 32 band states a frame may span
-constexpr int RS = GMAX * 32;        // window slots per frame
-constexpr int ROWB = RS * 2;         // back-pointer row stride in bytes (2 bytes per slot)
+// Band geometry, a template parameter of everything below: GM groups of 32 band states a frame may span.  The primary kernels run
+// GM = 8 (window of 256 states: median live window 29, maximum 170 at beam 10); the first fallback level re-runs an utterance whose
+// window outgrew that -- in practice a retry-beam pass -- with GM = 32 (1 024 states) before the sparse kernel is asked.
+template <int GM> struct BandK {
+  static constexpr int GMAX = GM;            // groups of 32 band states a frame may span
+  static constexpr int RS = GM * 32;         // window slots per frame
+  static constexpr int ROWB = RS * 2;        // back-pointer row stride in bytes (2 bytes per slot)
+  static constexpr int WRING = GM * 64;      // cost ring entries; >= RS + largest maxback (96) + 32
+  static constexpr unsigned MASK = WRING - 1;
+};
+constexpr int GM_MAIN = 8, GM_WIDE = 32;
 constexpr int BIAS = 16;             // back-pointer source-delta code = (dst - src) + BIAS, in 0..255
-constexpr int WRING = 512;           // cost ring entries; >= RS + largest maxback (96) + 32
-constexpr unsigned MASK = WRING - 1;
 constexpr int NST = 2;               // acoustic-cost stages of 4 frames (a block is prefetched 4 frames ahead: several microseconds)
 constexpr int BT_ROWS = 8;           // frames per back-trace batch (two staging buffers)
 constexpr unsigned FULL = 0xffffffffu;
@@ -61,7 +67,7 @@ struct BandParams {
   int64_t ld;
   const int64_t *col_off, *frame_off, *word_off, *ll_off, *ld_u, *bp_off;
   uint8_t *bp;   // per utterance: [T][RS] uint16 {in-arc choice, source-delta code}, then [T] uint16 first group of each row
-  int32_t *ali, *num_words, *words, *status, *fallback;   // fallback[0] = count, fallback[1..] = chunk-local utterance ids
+  int32_t *ali, *num_words, *words, *status, *fallback;   // fallback[0] = count, fallback[1..] = chunk-local utterance ids | attempt at overflow << 30
   float *per_frame, *total_like;
   float acwt, beam, retry_beam, beam_delta;
   int min_active, max_groups;
@@ -80,16 +86,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // are compact per-warp segments (written while pruning the previous frame); every lane ranks its own value against all
 // others with independent broadcast reads (no dependent exchange network), and the lane whose rank is `want` holds the
 // answer.  More than 64 survivors: bitwise radix select.
-template <int NW> struct LiveList { const float *seg; int n[NW]; };     // seg[w * SEG + j], j < n[w]; SEG = RS / NW
-template <int NW> __device__ __forceinline__ float live_at(const LiveList<NW> &L, int i) {
-  constexpr int SEG = RS / NW;
+template <int NW, int GM> struct LiveList { const float *seg; int n[NW]; };     // seg[w * SEG + j], j < n[w]; SEG = RS / NW
+template <int NW, int GM> __device__ __forceinline__ float live_at(const LiveList<NW, GM> &L, int i) {
+  constexpr int SEG = BandK<GM>::RS / NW;
   int w = 0;
 #pragma unroll
   for (int k = 0; k < NW - 1; k++) { if (i >= L.n[k] && w == k) { i -= L.n[k]; w = k + 1; } }
   return L.seg[w * SEG + i];
 }
-template <int NW> __device__ __forceinline__ float select_rank(const LiveList<NW> &L, int n, int want, int lane) {
-  constexpr int SEG = RS / NW;
+template <int NW, int GM> __device__ __forceinline__ float select_rank(const LiveList<NW, GM> &L, int n, int want, int lane) {
+  constexpr int SEG = BandK<GM>::RS / NW;
   if (n <= 32 && n - want <= 12) {
     // the usual case: a few more survivors than min_active.  The (n - want)-th largest value is the answer: peel maxima off with
     // one REDUX each (costs are >= +0, so their bit patterns order like the values; a peeled or empty lane holds 0)
@@ -144,7 +150,7 @@ template <int NW> __device__ __forceinline__ float select_rank(const LiveList<NW
 // gather the first four in-arcs' (source cost, candidate cost) -- in-degrees are 2..5 in training graphs -- then reduce them
 // under the cutoff; a loop takes any further arcs.
 struct Pull { uint32_t st; uint32_t s[4]; float c[4], x[4]; };
-template <class LdArc>
+template <int GM, class LdArc>
 __device__ __forceinline__ void pull_gather(Pull &q, const uint32_t st, LdArc ld_arc, const float *__restrict__ cur,
                                             const float *__restrict__ acf, const float nacwt) {
   q.st = st;
@@ -155,12 +161,12 @@ __device__ __forceinline__ void pull_gather(Pull &q, const uint32_t st, LdArc ld
     if (j < cnt) {
       const uint2 ar = ld_arc(a + j);
       q.s[j] = ar.x;
-      q.c[j] = cur[ar.x & MASK];
+      q.c[j] = cur[ar.x & BandK<GM>::MASK];
       q.x[j] = __fadd_rn(__fadd_rn(q.c[j], __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
     }
   }
 }
-template <class LdArc>
+template <int GM, class LdArc>
 __device__ __forceinline__ void pull_reduce(const Pull &q, LdArc ld_arc, const float *__restrict__ cur, const float *__restrict__ acf,
                                             const float cutoff, const float nacwt, float &v, uint32_t &arg) {
   v = INFINITY; arg = 0xFFu;
@@ -169,25 +175,24 @@ __device__ __forceinline__ void pull_reduce(const Pull &q, LdArc ld_arc, const f
   const int a = q.st & 0xFFFF, cnt = (q.st >> 16) & 0xFF;
   for (int j = 4; j < cnt; j++) {
     const uint2 ar = ld_arc(a + j);
-    const float c = cur[ar.x & MASK];
+    const float c = cur[ar.x & BandK<GM>::MASK];
     const float x = __fadd_rn(__fadd_rn(c, __uint_as_float(ar.y)), __fmul_rn(nacwt, acf[(ar.x >> 16) * 4]));
     if (c < cutoff && x < v) { v = x; arg = (uint32_t)j | ((ar.x & 0xFFFFu) << 8); }
   }
 }
 
-template <int NW, bool GS>
-#ifndef MFA_BAND_MINB2
-#define MFA_BAND_MINB2 8
-#endif
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : MFA_BAND_MINB2)
-viterbi_band_kernel(BandParams p) {
+// One utterance (chunk-local id `ul`) on the calling CTA of NW warps; `bp` = its back-pointer rows; attempts start at `first_attempt`
+// (the fallback level skips the beam that is already known to fail).
+template <int NW, bool GS, int GM>
+__device__ __forceinline__ void band_utt(const BandParams &p, const int ul, uint8_t *const bp, unsigned char *smraw, const int first_attempt,
+                                         int32_t *overflow_list) {
+  constexpr int GMAX = BandK<GM>::GMAX, RS = BandK<GM>::RS, ROWB = BandK<GM>::ROWB, WRING = BandK<GM>::WRING;
+  constexpr unsigned MASK = BandK<GM>::MASK;
   constexpr int NT = NW * 32, GPW = GMAX / NW, SEG = GPW * 32;
-  extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ uint32_t s_min[NW];                   // per-warp best new cost (ordered key) of the current frame
   __shared__ __align__(16) int s_stat[NW][4];      // per-warp {lowest live state, highest live state, highest reachable state, n_tot | n_beam << 16}
   __shared__ float s_live[NW * SEG];               // per-warp compact lists of the survivors' costs (for GetCutoff's rank)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ul = p.order[blockIdx.x];
   const int ug = p.utt0 + ul;
   const int S = (int)(p.st_off[ug + 1] - p.st_off[ug]);
   const int A = (int)(p.arc_off[ug + 1] - p.arc_off[ug]);
@@ -222,7 +227,6 @@ viterbi_band_kernel(BandParams p) {
   const float *ll = p.llT + (rag ? p.ll_off[ul] : p.col_off[ul]);
   const int64_t ldu = rag ? p.ld_u[ul] : p.ld;
   const int32_t *lp2pdf = p.lp2pdf + p.lp_off[ug];
-  uint8_t *bp = p.bp + p.bp_off[ul];                        // [T][RS] choice bytes
   uint16_t *bpg = (uint16_t *)(bp + (size_t)T * ROWB);      // [T] first group of each row
   const float inf = INFINITY, nacwt = -p.acwt;
   const int NB = (int)((T + 3) >> 2);
@@ -237,13 +241,13 @@ viterbi_band_kernel(BandParams p) {
     cp_async_commit();
   };
 
-  int result = MFA_ALIGN_NO_FINAL;
+  int result = MFA_ALIGN_NO_FINAL, over_attempt = 0;
   bool overflow = false;
   double offset = 0.0;
   int lo = 0, hi = 0;
   float *cur = ring, *nxt = ring + WRING;
 
-  for (int attempt = 0; attempt < 2 && !overflow; attempt++) {
+  for (int attempt = first_attempt; attempt < 2 && !overflow; attempt++) {
     const float beam = attempt == 0 ? p.beam : p.retry_beam;
     if (attempt == 1 && !(p.retry_beam > 0.0f)) break;
     cp_async_wait<0>();
@@ -255,7 +259,7 @@ viterbi_band_kernel(BandParams p) {
     lo = hi = start;
     int hib = start + (int)(ld_st(start) >> 24);
     int n_tot = 1, n_beam = 1;
-    LiveList<NW> L;
+    LiveList<NW, GM> L;
     L.seg = s_live; L.n[0] = 1;
 #pragma unroll
     for (int w = 1; w < NW; w++) L.n[w] = 0;
@@ -270,10 +274,10 @@ viterbi_band_kernel(BandParams p) {
       const float *acf = ac + (size_t)stage * 4 * P + (int)(t & 3);
       const int glo = max(lo - maxback, 0) >> 5;
       const int ng = min(hib >> 5, gend) - glo + 1;
-      if (ng > max_groups) { overflow = true; break; }
+      if (ng > max_groups) { overflow = true; over_attempt = attempt; break; }
       // ---- pull, first half: warp w owns groups w and w + NW of the window; the gather does not need the cutoff
       Pull q;
-      pull_gather(q, warp < ng ? ld_st((glo + warp) * 32 + lane) : 0u, ld_arc, cur, acf, nacwt);
+      pull_gather<GM>(q, warp < ng ? ld_st((glo + warp) * 32 + lane) : 0u, ld_arc, cur, acf, nacwt);
       // ---- GetCutoff on the live tokens (normalised: best == 0); every warp computes the same values
       // (a warp without a group this frame needs neither value)
       if (n_tot <= p.min_active) { cutoff = inf; adaptive = inf; }
@@ -282,7 +286,7 @@ viterbi_band_kernel(BandParams p) {
       // ---- pull, second half
       float nv[GPW];
       uint32_t na[GPW];
-      pull_reduce(q, ld_arc, cur, acf, cutoff, nacwt, nv[0], na[0]);
+      pull_reduce<GM>(q, ld_arc, cur, acf, cutoff, nacwt, nv[0], na[0]);
       na[0] |= q.st & 0xFF000000u;                     // forward reach in the top byte
       uint32_t kmin = f2key(nv[0]);
 #pragma unroll
@@ -290,8 +294,8 @@ viterbi_band_kernel(BandParams p) {
         nv[k] = inf; na[k] = 0xFFu;
         if (warp + k * NW < ng) {
           Pull q2;
-          pull_gather(q2, ld_st((glo + warp + k * NW) * 32 + lane), ld_arc, cur, acf, nacwt);
-          pull_reduce(q2, ld_arc, cur, acf, cutoff, nacwt, nv[k], na[k]);
+          pull_gather<GM>(q2, ld_st((glo + warp + k * NW) * 32 + lane), ld_arc, cur, acf, nacwt);
+          pull_reduce<GM>(q2, ld_arc, cur, acf, cutoff, nacwt, nv[k], na[k]);
           na[k] |= q2.st & 0xFF000000u;
           kmin = min(kmin, f2key(nv[k]));
         }
@@ -385,7 +389,7 @@ viterbi_band_kernel(BandParams p) {
   __syncthreads();                 // all back-pointer rows written; nobody touches `ac` any more
   if (warp != 0) return;
   if (overflow) {
-    if (lane == 0) { const int k = atomicAdd(p.fallback, 1); p.fallback[1 + k] = ul; }
+    if (lane == 0) { const int k = atomicAdd(overflow_list, 1); overflow_list[1 + k] = ul | (over_attempt << 30); }
     return;
   }
   if (result == MFA_ALIGN_NO_FINAL) {
@@ -469,13 +473,41 @@ viterbi_band_kernel(BandParams p) {
   if (lane == 0) { p.status[ul] = result; p.num_words[ul] = nw; }
 }
 
+#ifndef MFA_BAND_MINB2
+#define MFA_BAND_MINB2 8
+#endif
+template <int NW, bool GS>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : MFA_BAND_MINB2)
+viterbi_band_kernel(BandParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int ul = p.order[blockIdx.x];
+  band_utt<NW, GS, GM_MAIN>(p, ul, p.bp + p.bp_off[ul], smraw, 0, p.fallback);
+}
+
+// First fallback level, always enqueued behind the primary launches: the utterances on the device-side list `fb` ({count, ids | attempt
+// << 30}: their live window outgrew 8 groups) run again on the same recursion with a 32-group window, four warps, starting at the beam
+// that overflowed; a grid-stride loop, every CTA with its own back-pointer slab.  What outgrows even that goes on `fb2` for the sparse
+// kernel.  The count is read on the device -- the host never synchronises inside a step -- and stored to a host-mapped slot.
+__global__ void __launch_bounds__(128, 2)
+viterbi_band_wide_kernel(BandParams p, const int32_t *__restrict__ fb, int32_t *__restrict__ fb2, int64_t slab, int32_t *h_count) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int n = fb[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *(volatile int32_t *)h_count = n; __threadfence_system(); }
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int e = fb[1 + i];
+    band_utt<4, false, GM_WIDE>(p, e & 0x3FFFFFFF, p.bp + (size_t)blockIdx.x * slab, smraw, (e >> 30) & 1, fb2);
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 namespace mfa {
 
-size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem) {
+size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem, bool wide) {
   const int64_t graph = graph_in_smem ? ((((S + 32) & ~(int64_t)1) + 2 * A + 3) & ~(int64_t)3) * 4 : 0;
-  return (size_t)(graph + 2 * WRING * 4 + std::max<int64_t>(NST * 16 * P, 2 * BT_ROWS * ROWB + 4 * BT_ROWS) + 16);
+  const int64_t wring = wide ? BandK<GM_WIDE>::WRING : BandK<GM_MAIN>::WRING, rowb = wide ? BandK<GM_WIDE>::ROWB : BandK<GM_MAIN>::ROWB;
+  return (size_t)(graph + 2 * wring * 4 + std::max<int64_t>(NST * 16 * P, 2 * BT_ROWS * rowb + 4 * BT_ROWS) + 16);
 }
 
 // Launches the band kernel for the utterances in `subset` (chunk-local ids, all band_ok).  d_fallback: [1 + n_utts] ints, count
@@ -496,13 +528,13 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
     const int64_t T = a.h_frame_off[ul + 1] - a.h_frame_off[ul];
     bp_off[ul] = bp_total;
-    bp_total += (T * ROWB + T * 2 + 15) / 16 * 16;
-    need[ul] = viterbi_band_smem(S, A, P, graph_smem);
+    bp_total += (T * BandK<GM_MAIN>::ROWB + T * 2 + 15) / 16 * 16;
+    need[ul] = viterbi_band_smem(S, A, P, graph_smem, false);
     work[ul] = T;
     if (need[ul] > limit) return set_error(MFA_ERR_UNSUPPORTED, "internal: band utterance exceeds shared memory");
   }
   uint8_t *d_bp; int64_t *d_bp_off; int32_t *d_order;
-  MFA_TRY(e->getT<uint8_t>(DB_BBP, (size_t)bp_total + BT_ROWS * ROWB + 64, &d_bp));   // the back-trace stages whole batches of rows
+  MFA_TRY(e->getT<uint8_t>(DB_BBP, (size_t)bp_total + BT_ROWS * BandK<GM_MAIN>::ROWB + 64, &d_bp));   // the back-trace stages whole batches of rows
   MFA_TRY(e->upload(DB_BBP_OFF, bp_off.data(), bp_off.size(), &d_bp_off));
   constexpr int NC = mfa_engine::kSide;
   size_t bounds[NC];
@@ -522,7 +554,7 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fallback;
   p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
-  p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GMAX));
+  p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GM_MAIN));
   // shared-memory share of the unified L1 (percent).  Graph through L1, 10 h workload: 25 -> 16.8 ms, 50 -> 9.4, 65 -> 7.6, 75 -> 7.6,
   // 88 -> 8.8, 100 -> 10.5: enough shared memory for ~9 resident utterances per SM, the rest as L1 for their graph windows
   const int carve = e->cfg.vit_carveout_band >= 0 ? e->cfg.vit_carveout_band : (graph_smem ? 100 : 70);
@@ -557,6 +589,43 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
     CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
   }
+  return MFA_OK;
+}
+
+// Wide-band fallback level over the device-side list d_fb (see viterbi_band_wide_kernel); d_fb2 receives what overflows again.
+int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, const int32_t *d_fb, int32_t *d_fb2,
+                             int32_t *h_count) {
+  const mfa_graphs *g = a.g;
+  CUDA_TRY(cudaMemsetAsync(d_fb2, 0, sizeof(int32_t), e->stream));
+  if (subset.empty()) return MFA_OK;
+  constexpr int kCtas = 16;
+  size_t smem = 0; int64_t slab = 0;
+  for (int ul : subset) {
+    const int ug = a.utt0 + ul;
+    const int64_t S = g->st_off[ug + 1] - g->st_off[ug], A = g->arc_off[ug + 1] - g->arc_off[ug], P = g->lp_off[ug + 1] - g->lp_off[ug];
+    const int64_t T = a.h_frame_off[ul + 1] - a.h_frame_off[ul];
+    smem = std::max(smem, viterbi_band_smem(S, A, P, false, true));
+    slab = std::max(slab, (T * BandK<GM_WIDE>::ROWB + T * 2 + 15) / 16 * 16 + BT_ROWS * BandK<GM_WIDE>::ROWB + 64);
+  }
+  const int ctas = (int)std::min<size_t>(kCtas, subset.size());
+  uint8_t *d_bp;
+  MFA_TRY(e->getT<uint8_t>(DB_WIDE_BP, (size_t)slab * ctas + 64, &d_bp));
+  BandParams p;
+  p.st_off = g->d_st_off; p.arc_off = g->d_arc_off; p.lp_off = g->d_lp_off;
+  p.b_start = g->d_b_start; p.b_maxback = g->d_b_maxback; p.a_tid = g->d_a_tid; p.a_olabel = g->d_a_olabel; p.lp2pdf = g->d_lp2pdf;
+  p.b_stw = g->d_b_stw; p.b_arc = (const uint2 *)g->d_b_arc; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
+  p.utt0 = a.utt0; p.order = nullptr; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
+  p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u; p.bp_off = nullptr; p.bp = d_bp;
+  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fb2;
+  p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
+  p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
+  p.min_active = a.opts.min_active; p.max_groups = GM_WIDE;
+  smem = (smem + 15) / 16 * 16;
+  if (smem + 8192 > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "internal: wide-band utterance exceeds shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(viterbi_band_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  viterbi_band_wide_kernel<<<ctas, 128, smem, e->stream>>>(p, d_fb, d_fb2, slab, h_count);
+  e->launches++;
+  CUDA_TRY(cudaGetLastError());
   return MFA_OK;
 }
 

@@ -179,14 +179,17 @@ def test_band_kernel_equals_sparse_kernel(eng, triphone, beam, retry):
     f1 = eng.band_fallbacks
     sparse = _align_env(eng, sc, batch, beam, retry, vit_band=0)
     assert eng.band_fallbacks == f1
-    narrow = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2)
-    assert eng.band_fallbacks > f1                      # the fallback path really ran
+    narrow = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2)    # overflow -> 32-group band kernel (first fallback level)
+    f2 = eng.band_fallbacks
+    assert f2 > f1                                      # the fallback path really ran
+    narrow_sparse = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2, vit_wide=0)   # overflow -> sparse kernel directly
+    assert eng.band_fallbacks - f2 == f2 - f1
     if beam <= 10.0:
         assert f1 == f0                                   # ... and the default band is wide enough for ordinary beams
     assert np.isin(sparse.status, (0, 1)).sum() > 0
     smem4 = _align_env(eng, sc, batch, beam, retry, vit_graph_smem=1, vit_nw2_kb=0)   # graph in shared memory, 4 warps
     l1w4 = _align_env(eng, sc, batch, beam, retry, vit_nw2_kb=0)                           # graph through L1, 4 warps
-    for other in (band, narrow, smem4, l1w4):
+    for other in (band, narrow, narrow_sparse, smem4, l1w4):
         assert np.array_equal(other.status, sparse.status) and np.array_equal(other.num_words, sparse.num_words)
         assert np.array_equal(other.ali, sparse.ali) and np.array_equal(other.words, sparse.words)
         assert np.array_equal(other.total_like, sparse.total_like) and np.array_equal(other.per_frame, sparse.per_frame)
