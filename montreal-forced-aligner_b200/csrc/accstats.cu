@@ -249,6 +249,7 @@ extern "C" int64_t mfa_acc_size(const mfa_model *m) {
 extern "C" int mfa_acc_zero(mfa_engine *e, mfa_model *m) {
   if (!e || !m) return set_error(MFA_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(e->join_k3());
   size_t bytes = (size_t)mfa_acc_size(m) * sizeof(double);
   if (!m->d_acc) CUDA_TRY(cudaMalloc((void **)&m->d_acc, bytes));
   CUDA_TRY(cudaMemsetAsync(m->d_acc, 0, bytes, e->stream));

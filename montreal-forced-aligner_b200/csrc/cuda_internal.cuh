@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_K3_OFFS, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -39,6 +39,7 @@ struct mfa_engine_cfg {
   int vit_nw2_kb = -1;         // size classes up to this many KB of shared memory run 2 warps per utterance (-1: 20, or 44 with graph_smem)
   int vit_carveout = 100;      // shared-memory carve-out (percent) of the sparse kernel
   int vit_carveout_band = -1;  // ... of the band kernel (-1: 70, or 100 with graph_smem)
+  int k3_overlap = 1;          // 1: device-buffer mfa_align_pcm leaves its Viterbi launch un-joined so that the next call's K1 / features overlap its tail
   int vit_prio = 1;            // side-stream priorities rise with the size class (creation time only)
   int pipeline_split = -1;     // host-PCM path: -1 auto, 0 whole, 1 every stage per segment, 2 stream (K1..K2 per segment, one K3)
   int acc_impl = 0;            // K4: 0 counting sort + register accumulation, 1 first version (f64 atomics)
@@ -76,6 +77,20 @@ struct mfa_engine {
   cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
   // per-utterance B images gathered ahead of time on a side stream (gmm_tc.cu prefetch_b_images): valid for utterances [pf_u0, pf_u1)
   // of graphs pf_g under model pf_m until the next ragged launch consumes or replaces them
+  // K3 runs on the side streams and is joined on `sj`, NOT on the main stream: the next call's K1 / feature kernels (which share no
+  // buffer with it) start while the Viterbi tail is still running; whoever touches something K3 reads or writes calls join_k3() first
+  // (every entry point does at its start, except the fused alignment, which defers it to just before its own K2).
+  cudaStream_t sj = nullptr, sg = nullptr;      // join stream of K3; gather stream of the B-image prefetch
+  cudaEvent_t ev_k3_done = nullptr, ev_fb = nullptr;
+  bool k3_pending = false;
+  const char *pend_out[6] = {}; size_t pend_bytes[6] = {};   // output buffers of the K3 in flight
+  int join_k3();
+  bool k3_writes(const void *p, size_t bytes) const {
+    if (!k3_pending) return false;
+    for (int i = 0; i < 6; i++)
+      if (pend_out[i] && (const char *)p < pend_out[i] + pend_bytes[i] && pend_out[i] < (const char *)p + bytes) return true;
+    return false;
+  }
   cudaEvent_t ev_bimg = nullptr;
   const void *pf_g = nullptr, *pf_m = nullptr;
   int pf_u0 = 0, pf_u1 = 0;
@@ -85,7 +100,7 @@ struct mfa_engine {
   std::vector<cudaEvent_t> st_ev;
   std::vector<int> st_stage;           // stage of interval k (events 2k, 2k+1)
   int stage_begin(int stage);
-  int stage_end();
+  int stage_end(cudaStream_t on = nullptr);   // `on`: record the end of the interval on another stream (K3: its join stream)
   void stage_reset() { st_stage.clear(); }
   // cached MFCC tables (device blob in DB_MFCC_TAB) for the last option set
   bool mfcc_tab_valid = false;
@@ -137,9 +152,9 @@ struct mfa_engine {
   }
 };
 
-struct CallScope {   // one per C-ABI entry point that uploads: recycles the staging arena
+struct CallScope {   // one per C-ABI entry point that uploads: recycles the staging arena; joins a K3 still in flight unless told to defer
   mfa_engine *e;
-  explicit CallScope(mfa_engine *e_) : e(e_) { e->begin_call(); }
+  explicit CallScope(mfa_engine *e_, bool defer_join = false) : e(e_) { if (!defer_join) e->join_k3(); e->begin_call(); }
   ~CallScope() { e->end_call(); }
 };
 

@@ -21,7 +21,7 @@ extern "C" int mfa_abi_version(void) { return 2; }
 int mfa_engine::get(int id, size_t bytes, void **out) {
   Buf &b = dev[id];
   if (bytes > b.cap) {
-    if (b.p) { CUDA_TRY(cudaStreamSynchronize(stream)); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    if (b.p) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }   // every stream: a K3 in flight may use it
     size_t cap = bytes + bytes / 8 + 256;
     cudaError_t err = cudaMalloc(&b.p, cap);
     if (err != cudaSuccess) { b.p = nullptr; return set_error(MFA_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(err)); }
@@ -48,7 +48,7 @@ struct OptionDesc { const char *name; int mfa_engine_cfg::*field; };
 const OptionDesc kOptions[] = {
     {"vit_band", &mfa_engine_cfg::vit_band}, {"vit_maxgroups", &mfa_engine_cfg::vit_maxgroups}, {"vit_wide", &mfa_engine_cfg::vit_wide}, {"vit_graph_smem", &mfa_engine_cfg::vit_graph_smem},
     {"vit_nw2_kb", &mfa_engine_cfg::vit_nw2_kb}, {"vit_carveout", &mfa_engine_cfg::vit_carveout}, {"vit_carveout_band", &mfa_engine_cfg::vit_carveout_band},
-    {"vit_prio", &mfa_engine_cfg::vit_prio}, {"pipeline_split", &mfa_engine_cfg::pipeline_split}, {"acc_impl", &mfa_engine_cfg::acc_impl},
+    {"vit_prio", &mfa_engine_cfg::vit_prio}, {"k3_overlap", &mfa_engine_cfg::k3_overlap}, {"pipeline_split", &mfa_engine_cfg::pipeline_split}, {"acc_impl", &mfa_engine_cfg::acc_impl},
     {"tc_k96", &mfa_engine_cfg::tc_k96}, {"tc_poly", &mfa_engine_cfg::tc_poly}, {"mfcc_generic", &mfa_engine_cfg::mfcc_generic},
     {"trace", &mfa_engine_cfg::trace}};
 }  // namespace
@@ -99,6 +99,10 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   }
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_bimg, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_k3_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fb, cudaEventDisableTiming));
+  CUDA_TRY(cudaStreamCreateWithPriority(&e->sj, cudaStreamNonBlocking, prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->sg, cudaStreamNonBlocking));
   CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, (mfa_engine::kFbRing + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
   memset(e->h_fb_ring, 0, (mfa_engine::kFbRing + 1) * sizeof(int32_t));
   for (int k = 0; k < 2; k++) {
@@ -112,7 +116,7 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
 extern "C" int mfa_engine_destroy(mfa_engine *e) {
   if (!e) return MFA_OK;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  cudaDeviceSynchronize();   // main stream, K3's side / join streams, the gather stream
   for (auto &b : e->dev) if (b.p) cudaFree(b.p);
   for (auto &b : e->pin) if (b.p) cudaFreeHost(b.p);
   for (auto ev : e->gmm_ev) cudaEventDestroy(ev);
@@ -121,6 +125,10 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   for (int k = 0; k < mfa_engine::kSide; k++) { if (e->side[k]) cudaStreamDestroy(e->side[k]); if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]); }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_bimg) cudaEventDestroy(e->ev_bimg);
+  if (e->ev_k3_done) cudaEventDestroy(e->ev_k3_done);
+  if (e->ev_fb) cudaEventDestroy(e->ev_fb);
+  if (e->sj) cudaStreamDestroy(e->sj);
+  if (e->sg) cudaStreamDestroy(e->sg);
   if (e->h_fb_ring) cudaFreeHost(e->h_fb_ring);
   for (int k = 0; k < 2; k++) { if (e->stage_mem[k]) cudaFreeHost(e->stage_mem[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }
   cudaStreamDestroy(e->stream);
@@ -128,8 +136,16 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   return MFA_OK;
 }
 
+int mfa_engine::join_k3() {
+  if (!k3_pending) return MFA_OK;
+  CUDA_TRY(cudaStreamWaitEvent(stream, ev_k3_done, 0));
+  k3_pending = false;
+  return MFA_OK;
+}
+
 extern "C" int mfa_engine_sync(mfa_engine *e) {
   if (!e) return set_error(MFA_ERR_INVALID, "null engine");
+  MFA_TRY(e->join_k3());
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   CUDA_TRY(cudaGetLastError());
   e->harvest_fallbacks();
@@ -140,7 +156,7 @@ extern "C" int mfa_engine_sm_count(mfa_engine *e) { return e ? e->sm_count : 0; 
 extern "C" int64_t mfa_engine_launch_count(mfa_engine *e) { return e ? e->launches : 0; }
 extern "C" int64_t mfa_engine_band_fallbacks(mfa_engine *e) {
   if (!e) return 0;
-  if (e->fb_pending) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); e->harvest_fallbacks(); }   // counts of launches still in flight
+  if (e->fb_pending) { cudaSetDevice(e->device); e->join_k3(); cudaStreamSynchronize(e->stream); e->harvest_fallbacks(); }   // counts of launches still in flight
   return e->band_fallbacks;
 }
 namespace {
@@ -207,8 +223,8 @@ int mfa_engine::stage_begin(int stage) {
   CUDA_TRY(cudaEventRecord(st_ev[2 * k], stream));
   return MFA_OK;
 }
-int mfa_engine::stage_end() {
-  CUDA_TRY(cudaEventRecord(st_ev[2 * (st_stage.size() - 1) + 1], stream));
+int mfa_engine::stage_end(cudaStream_t on) {
+  CUDA_TRY(cudaEventRecord(st_ev[2 * (st_stage.size() - 1) + 1], on ? on : stream));
   return MFA_OK;
 }
 extern "C" int mfa_engine_stage_timing(mfa_engine *e, float *ms4) {

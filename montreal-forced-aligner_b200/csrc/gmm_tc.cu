@@ -816,7 +816,7 @@ static int gather_range(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, in
 int prefetch_b_images(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, int n_utts) {
   if (n_utts <= 0) return MFA_OK;
   MFA_TRY(ensure_rag_plan(e, m, g));
-  cudaStream_t st = e->side[mfa_engine::kSide - 1];
+  cudaStream_t st = e->sg;
   CUDA_TRY(cudaEventRecord(e->ev_fork, e->stream));      // everything queued so far (the previous call's readers of DB_BIMG) comes first
   CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fork, 0));
   uint8_t *d_b;

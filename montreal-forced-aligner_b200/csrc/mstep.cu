@@ -501,6 +501,7 @@ int mfa_model_read(mfa_engine *e, mfa_model *m, int32_t *pdf_off, float *weights
                    float *log_probs) {
   if (!e || !m) return set_error(MFA_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(e->join_k3());
   cudaStream_t s = e->stream;
   const size_t G = (size_t)m->num_gauss, D = (size_t)m->dim;
   if (pdf_off) memcpy(pdf_off, m->h_pdf_off.data(), ((size_t)m->num_pdfs + 1) * 4);
@@ -526,6 +527,7 @@ int mfa_graphs_set_transitions(mfa_engine *e, mfa_graphs *g, mfa_model *m, float
   if (!m->d_first_tid) return set_error(MFA_ERR_INVALID, "no transition tables: call mfa_model_set_transitions first");
   if (g->num_tids != m->num_tids) return set_error(MFA_ERR_INVALID, "graphs were packed for a different transition model");
   CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(e->join_k3());   // a Viterbi launch in flight reads the arc weights this rewrites
   MFA_TRY(upload_graphs(e, g));
   tid_cost_kernel<<<(unsigned)((m->num_tstates + 127) / 128), 128, 0, e->stream>>>(m->num_tstates, m->d_first_tid, m->d_self_loop_tid, m->d_log_probs,
                                                                                   transition_scale, self_loop_scale, m->d_tid_cost);

@@ -237,6 +237,7 @@ int mfa_align(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_opts *
     a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
     a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = *o;
     MFA_TRY(launch_viterbi(e, a));
+    MFA_TRY(e->join_k3());
   }
   MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
@@ -254,7 +255,10 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   if (!e || !m || !g || !o || !sample_off || !frame_off || !word_off || !utt2spk) return set_error(MFA_ERR_INVALID, "bad argument");
   if (n_utts != g->n_utts) return set_error(MFA_ERR_INVALID, "n_utts does not match the graph batch");
   CUDA_TRY(cudaSetDevice(e->device));
-  CallScope scope(e);
+  // The Viterbi launch of the PREVIOUS call may still be running (it is joined on its own stream): K1, the CMVN statistics and the
+  // feature kernel of this call share no buffer with it and start right away; the join happens before this call's K2 (which
+  // overwrites the log-likelihoods K3 reads) -- or here, if this call writes into the output buffers that launch is still filling.
+  CallScope scope(e, /*defer_join=*/true);
   MFA_TRY(check_offsets(sample_off, n_utts, "sample_off"));
   MFA_TRY(check_offsets(word_off, n_utts, "word_off"));
   for (int u = 0; u < n_utts; u++)
@@ -286,9 +290,18 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   MFA_TRY(out_buffer(e, DB_TOTAL_LIKE, total_like, (size_t)n_utts, where, &io.d_total));
   MFA_TRY(out_buffer(e, DB_STATUS, status, (size_t)n_utts, where, &io.d_status));
   MFA_TRY(e->upload(DB_WORD_OFF, word_off, (size_t)n_utts + 1, &io.d_word_off));
+  if (where == MFA_HOST || e->cfg.k3_overlap == 0 || e->k3_writes(io.d_ali, (size_t)nf * 4) || e->k3_writes(io.d_pf, (size_t)nf * 4) ||
+      e->k3_writes(io.d_words, (size_t)nw * 4) || e->k3_writes(io.d_num_words, (size_t)n_utts * 4) || e->k3_writes(io.d_total, (size_t)n_utts * 4) ||
+      e->k3_writes(io.d_status, (size_t)n_utts * 4))
+    MFA_TRY(e->join_k3());
   CUDA_TRY(cudaMemsetAsync(io.d_ali, 0, (size_t)nf * 4, e->stream));
   CUDA_TRY(cudaMemsetAsync(io.d_pf, 0, (size_t)nf * 4, e->stream));
   if (nw) CUDA_TRY(cudaMemsetAsync(io.d_words, 0, (size_t)nw * 4, e->stream));
+  auto mark_outputs = [&]() {   // the Viterbi launch just enqueued writes these; it stays un-joined until someone needs them
+    const void *ps[6] = {io.d_ali, io.d_pf, io.d_words, io.d_num_words, io.d_total, io.d_status};
+    const size_t bs[6] = {(size_t)nf * 4, (size_t)nf * 4, (size_t)nw * 4, (size_t)n_utts * 4, (size_t)n_utts * 4, (size_t)n_utts * 4};
+    for (int i = 0; i < 6; i++) { e->pend_out[i] = (const char *)ps[i]; e->pend_bytes[i] = bs[i]; }
+  };
   // ---- segments.  Device-resident PCM: one segment.  Host PCM: the batch is cut after a speaker boundary near the middle so
   // that the second half is still crossing PCIe while the first half is scored and aligned; CMVN statistics are per speaker,
   // so a cut is only legal where every speaker's utterances are contiguous (MFA orders jobs by speaker-utterance key) and the
@@ -376,6 +389,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
   float *w_feats = nullptr, *w_llT = nullptr; int64_t *w_col = nullptr, *w_ll_off = nullptr, *w_ld_u = nullptr;
   if (stream) {
     ChunkPlan &c = whole[0];
+    MFA_TRY(e->join_k3());
     MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &w_feats));
     MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &w_llT));
     MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &w_col));
@@ -421,7 +435,8 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
         a.d_num_words = io.d_num_words; a.d_total_like = io.d_total; a.d_status = io.d_status; a.opts = o->align;
         MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
         MFA_TRY(launch_viterbi(e, a));
-        MFA_TRY(e->stage_end());
+        MFA_TRY(e->stage_end(e->sj));
+        mark_outputs();
       }
       continue;
     }
@@ -431,12 +446,13 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
     for (auto &c : plans) {
       float *d_feats, *d_llT; int64_t *d_col, *d_ll_off = nullptr, *d_ld_u = nullptr;
       MFA_TRY(e->getT<float>(DB_FEATS, (size_t)c.ld * D, &d_feats));
-      MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
       MFA_TRY(e->upload(DB_COL_OFF, c.col_off.data(), c.col_off.size(), &d_col));
       MFA_TRY(e->stage_begin(mfa_engine::ST_FEAT));
       CUDA_TRY(cudaMemsetAsync(d_feats, 0, (size_t)c.ld * D * 4, e->stream));
       MFA_TRY(launch_features(e, &fo, d_mfcc, d_fo + c.u0, frame_off + c.u0, d_col, d_u2s + c.u0, c.n, d_stats, d_feats, D));
       MFA_TRY(e->stage_end());
+      MFA_TRY(e->join_k3());   // from here on this chunk overwrites what a Viterbi launch still in flight reads (log-likelihoods, offsets)
+      MFA_TRY(e->getT<float>(DB_LL, ragged ? (size_t)c.ll_floats + 8 : (size_t)P * c.ld, &d_llT));
       MFA_TRY(e->stage_begin(mfa_engine::ST_GMM));
       if (ragged) {
         MFA_TRY(e->upload(DB_LL_OFF, c.ll_off.data(), c.ll_off.size(), &d_ll_off));
@@ -456,9 +472,11 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
       a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
       MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
       MFA_TRY(launch_viterbi(e, a));
-      MFA_TRY(e->stage_end());
+      MFA_TRY(e->stage_end(e->sj));
+      mark_outputs();
     }
   }
+  if (where == MFA_HOST) MFA_TRY(e->join_k3());   // the copies below read what K3 writes
   MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_words, words, (size_t)nw, where));
@@ -531,7 +549,8 @@ int mfa_align_feats(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_align_
     a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = *o;
     MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
     MFA_TRY(launch_viterbi(e, a));
-    MFA_TRY(e->stage_end());
+    MFA_TRY(e->stage_end(e->sj));
+    MFA_TRY(e->join_k3());
   }
   MFA_TRY(from_device(e, io.d_ali, ali, (size_t)nf, where));
   MFA_TRY(from_device(e, io.d_pf, per_frame, (size_t)nf, where));
@@ -581,6 +600,7 @@ int mfa_fmllr_update(mfa_engine *e, const double *stats, int32_t dim, int32_t n_
                      double *objf_impr, double *count, int where) {
   if (!e || !stats || !transforms || n_spk < 0 || dim < 1) return set_error(MFA_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(e->device));
+  MFA_TRY(e->join_k3());
   if (num_iters <= 0) num_iters = 40;
   const size_t ns = (size_t)n_spk * (size_t)mfa_fmllr_stats_size(dim), nw = (size_t)n_spk * dim * (dim + 1);
   const double *d_stats; float *d_W; double *d_out;

@@ -640,7 +640,7 @@ static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std:
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
-    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
+    CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_join[c], 0));
   }
   return MFA_OK;
 }
@@ -650,10 +650,30 @@ static int launch_viterbi_sparse(mfa_engine *e, const ViterbiArgs &a, const std:
 // band kernel lists those on the device and a small fallback launch, always enqueued, walks that list (usually empty) without the
 // host ever reading the count inside the step.
 // Engine option vit_band = 0 forces the sparse kernel; vit_maxgroups = k (1..8) narrows the band (tests use it to exercise the fallback).
-int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
-  const mfa_graphs *g = a.g;
-  const int n = a.n_utts;
+int launch_viterbi(mfa_engine *e, const ViterbiArgs &a_in) {
+  const mfa_graphs *g = a_in.g;
+  const int n = a_in.n_utts;
   if (n == 0) return MFA_OK;
+  MFA_TRY(e->join_k3());   // one Viterbi launch in flight per engine: its scratch buffers are reused here
+  // K3 is not joined on the main stream (cuda_internal.cuh: join_k3), so the next call may overwrite the small offset arrays of THIS call
+  // (they live in per-engine upload slots) while the kernels still read them: the launch works on private copies
+  ViterbiArgs a = a_in;
+  {
+    const bool rag = a_in.d_ll_off != nullptr;
+    int64_t *k3o;
+    MFA_TRY(e->getT<int64_t>(DB_K3_OFFS, (size_t)4 * ((size_t)n + 1), &k3o));
+    CUDA_TRY(cudaMemcpyAsync(k3o, a_in.d_frame_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(k3o + (n + 1), a_in.d_word_off, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, e->stream));
+    a.d_frame_off = k3o; a.d_word_off = k3o + (n + 1);
+    if (rag) {
+      CUDA_TRY(cudaMemcpyAsync(k3o + 2 * (n + 1), a_in.d_ll_off, (size_t)n * 8, cudaMemcpyDeviceToDevice, e->stream));
+      CUDA_TRY(cudaMemcpyAsync(k3o + 3 * (n + 1), a_in.d_ld_u, (size_t)n * 8, cudaMemcpyDeviceToDevice, e->stream));
+      a.d_ll_off = k3o + 2 * (n + 1); a.d_ld_u = k3o + 3 * (n + 1);
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(k3o + 2 * (n + 1), a_in.d_col_off, (size_t)n * 8, cudaMemcpyDeviceToDevice, e->stream));
+      a.d_col_off = k3o + 2 * (n + 1);
+    }
+  }
   if (a.ld % 8 != 0) return set_error(MFA_ERR_INVALID, "log-likelihood leading dimension must be a multiple of 8");
   if (!a.d_ll_off) {
     for (int u = 0; u < n; u++) {
@@ -714,11 +734,18 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a) {
     CUDA_TRY(cudaFuncSetAttribute(viterbi_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     // with the wide level in front, band_fallbacks counts the utterances that left the 8-group band; the sparse level's own count goes to
     // a scratch slot of the ring that is never harvested
-    viterbi_fallback_kernel<<<ctas, VT, smem, e->stream>>>(p, d_list, slab, d_big, e->cfg.vit_wide ? e->h_fb_ring + mfa_engine::kFbRing : e->h_fb_ring + e->fb_pending);
+    CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));    // the uploads above precede the kernel on the join stream
+    CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_fb, 0));
+    viterbi_fallback_kernel<<<ctas, VT, smem, e->sj>>>(p, d_list, slab, d_big, e->cfg.vit_wide ? e->h_fb_ring + mfa_engine::kFbRing : e->h_fb_ring + e->fb_pending);
     if (!e->cfg.vit_wide) e->fb_pending++;
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
+  CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));
+  CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_fb, 0));   // (a launch without any class still orders the join stream behind the main stream)
+  CUDA_TRY(cudaEventRecord(e->ev_k3_done, e->sj));
+  e->k3_pending = true;
+  for (int i = 0; i < 6; i++) e->pend_out[i] = nullptr;   // the caller that defers the join says which buffers are being written
   return MFA_OK;
 }
 

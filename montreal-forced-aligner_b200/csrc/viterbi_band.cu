@@ -587,7 +587,7 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(e->ev_join[c], st));
-    CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_join[c], 0));
+    CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_join[c], 0));
   }
   return MFA_OK;
 }
@@ -623,7 +623,9 @@ int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vec
   smem = (smem + 15) / 16 * 16;
   if (smem + 8192 > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "internal: wide-band utterance exceeds shared memory");
   CUDA_TRY(cudaFuncSetAttribute(viterbi_band_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  viterbi_band_wide_kernel<<<ctas, 128, smem, e->stream>>>(p, d_fb, d_fb2, slab, h_count);
+  CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));      // the list reset above and the slab allocation precede the kernel on the join stream
+  CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_fb, 0));
+  viterbi_band_wide_kernel<<<ctas, 128, smem, e->sj>>>(p, d_fb, d_fb2, slab, h_count);
   e->launches++;
   CUDA_TRY(cudaGetLastError());
   return MFA_OK;
