@@ -168,7 +168,9 @@ def parity_block(sc, utts, ref, gpu):
         n_same = int((a == r["ali"]).sum())
         same += n_same; total += len(a)
         if worst is None or len(a) - n_same > worst[1]:
-            worst = (int(u), len(a) - n_same, len(a))
+            dt = np.nonzero(a != r["ali"])[0][:6]
+            worst = (int(u), len(a) - n_same, len(a), int(st[u]), [(int(t), int(a[t]), int(r["ali"][t]), int(sc.tm.tid2phone[a[t]]), int(sc.tm.tid2phone[r["ali"][t]]),
+                                                                   int(sc.tm.tid2pdf[a[t]]), int(sc.tm.tid2pdf[r["ali"][t]])) for t in dt])
         if list(words[wo[u]:wo[u] + nw[u]]) != list(r["words"]):
             word_mis += 1
         like_err = max(like_err, abs(float(tl[u]) - r["like"]) / max(1e-30, abs(r["like"])))
@@ -190,7 +192,8 @@ def parity_block(sc, utts, ref, gpu):
             "word_sequence_mismatches": word_mis, "loglike_rel_err_max": like_err, "per_frame_loglike_rel_err_max": pf_err,
             "per_frame_loglike_worst": pf_worst, "per_frame_loglikes_beyond_1e-4": pf_n_bad,
             "boundary_within_1_frame_pct": 100.0 * b_ok / max(1, b_tot), "phone_boundaries": b_tot,
-            "worst_utterance": None if worst is None else {"utt": worst[0], "differing_frames": worst[1], "frames": worst[2]},
+            "worst_utterance": None if worst is None else {"utt": worst[0], "differing_frames": worst[1], "frames": worst[2], "status": worst[3],
+                                                                   "first_differences_t_gpuTid_oracleTid_gpuPhone_oraclePhone_gpuPdf_oraclePdf": worst[4]},
             "retried_utterances_in_sample": int(sum(1 for r in ref if r["status"] == 1))}
 
 
