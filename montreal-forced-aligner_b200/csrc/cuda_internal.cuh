@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_K3_OFFS, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_K3_OFFS, DB_FB_CTL, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -80,8 +80,8 @@ struct mfa_engine {
   // K3 runs on the side streams and is joined on `sj`, NOT on the main stream: the next call's K1 / feature kernels (which share no
   // buffer with it) start while the Viterbi tail is still running; whoever touches something K3 reads or writes calls join_k3() first
   // (every entry point does at its start, except the fused alignment, which defers it to just before its own K2).
-  cudaStream_t sj = nullptr, sg = nullptr;      // join stream of K3; gather stream of the B-image prefetch
-  cudaEvent_t ev_k3_done = nullptr, ev_fb = nullptr;
+  cudaStream_t sj = nullptr, sg = nullptr, sw = nullptr;      // join stream of K3; gather stream of the B-image prefetch
+  cudaEvent_t ev_k3_done = nullptr, ev_fb = nullptr, ev_wide = nullptr;
   bool k3_pending = false;
   const char *pend_out[6] = {}; size_t pend_bytes[6] = {};   // output buffers of the K3 in flight
   int join_k3();
@@ -242,8 +242,8 @@ struct ViterbiArgs {
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem, bool wide = false);   // shared memory the band kernel needs for one utterance
 int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, const int32_t *d_fb, int32_t *d_fb2,
-                             int32_t *h_count);
-int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback);
+                             int32_t *h_count, int32_t *d_ctl);
+int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback, int32_t *d_ctl);
 int launch_acc_stats(mfa_engine *e, mfa_model *m, const float *d_feats, const int32_t *d_ali, int64_t n_frames);
 int launch_fmllr_acc(mfa_engine *e, mfa_model *mp, mfa_model *ms, const float *d_feats, const int32_t *d_ali, const float *d_tid_weight,
                      const int64_t *d_frame_off, const int64_t *h_frame_off, const int32_t *h_utt2spk, int32_t n_utts, int32_t n_spk,

@@ -102,6 +102,8 @@ extern "C" int mfa_engine_create(int device, mfa_engine **out) {
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_k3_done, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fb, cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithPriority(&e->sj, cudaStreamNonBlocking, prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&e->sw, cudaStreamNonBlocking, prio_greatest));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_wide, cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->sg, cudaStreamNonBlocking));
   CUDA_TRY(cudaHostAlloc((void **)&e->h_fb_ring, (mfa_engine::kFbRing + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
   memset(e->h_fb_ring, 0, (mfa_engine::kFbRing + 1) * sizeof(int32_t));
@@ -127,7 +129,9 @@ extern "C" int mfa_engine_destroy(mfa_engine *e) {
   if (e->ev_bimg) cudaEventDestroy(e->ev_bimg);
   if (e->ev_k3_done) cudaEventDestroy(e->ev_k3_done);
   if (e->ev_fb) cudaEventDestroy(e->ev_fb);
+  if (e->ev_wide) cudaEventDestroy(e->ev_wide);
   if (e->sj) cudaStreamDestroy(e->sj);
+  if (e->sw) cudaStreamDestroy(e->sw);
   if (e->sg) cudaStreamDestroy(e->sg);
   if (e->h_fb_ring) cudaFreeHost(e->h_fb_ring);
   for (int k = 0; k < 2; k++) { if (e->stage_mem[k]) cudaFreeHost(e->stage_mem[k]); if (e->stage_ev[k]) cudaEventDestroy(e->stage_ev[k]); }

@@ -694,10 +694,11 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a_in) {
     }
     (ok ? band : sparse).push_back(u);
   }
-  int32_t *d_fb = nullptr;
+  int32_t *d_fb = nullptr, *d_ctl = nullptr;
   if (!band.empty()) {
     MFA_TRY(e->getT<int32_t>(DB_FALLBACK, (size_t)n + 1, &d_fb));
-    MFA_TRY(launch_viterbi_band(e, a, band, max_groups, d_fb));
+    MFA_TRY(e->getT<int32_t>(DB_FB_CTL, 2, &d_ctl));
+    MFA_TRY(launch_viterbi_band(e, a, band, max_groups, d_fb, d_ctl));
   }
   MFA_TRY(launch_viterbi_sparse(e, a, sparse));
   if (!band.empty()) {
@@ -708,7 +709,7 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a_in) {
     if (e->cfg.vit_wide) {
       int32_t *d_fb2;
       MFA_TRY(e->getT<int32_t>(DB_FALLBACK2, (size_t)n + 1, &d_fb2));
-      MFA_TRY(launch_viterbi_band_wide(e, a, band, d_fb, d_fb2, e->h_fb_ring + e->fb_pending));
+      MFA_TRY(launch_viterbi_band_wide(e, a, band, d_fb, d_fb2, e->h_fb_ring + e->fb_pending, d_ctl));
       e->fb_pending++;
       d_list = d_fb2;
     }

@@ -68,6 +68,7 @@ struct BandParams {
   const int64_t *col_off, *frame_off, *word_off, *ll_off, *ld_u, *bp_off;
   uint8_t *bp;   // per utterance: [T][RS] uint16 {in-arc choice, source-delta code}, then [T] uint16 first group of each row
   int32_t *ali, *num_words, *words, *status, *fallback;   // fallback[0] = count, fallback[1..] = chunk-local utterance ids | attempt at overflow << 30
+  int32_t *done;   // primary launches: counter of finished CTAs (the wide level polls it); nullptr elsewhere
   float *per_frame, *total_like;
   float acwt, beam, retry_beam, beam_delta;
   int min_active, max_groups;
@@ -482,19 +483,51 @@ viterbi_band_kernel(BandParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int ul = p.order[blockIdx.x];
   band_utt<NW, GS, GM_MAIN>(p, ul, p.bp + p.bp_off[ul], smraw, 0, p.fallback);
+  // (thread 0 sits in warp 0, the last to leave band_utt: its list entry, if any, is written)
+  if (threadIdx.x == 0 && p.done) { __threadfence(); atomicAdd(p.done, 1); }
 }
 
-// First fallback level, always enqueued behind the primary launches: the utterances on the device-side list `fb` ({count, ids | attempt
-// << 30}: their live window outgrew 8 groups) run again on the same recursion with a 32-group window, four warps, starting at the beam
-// that overflowed; a grid-stride loop, every CTA with its own back-pointer slab.  What outgrows even that goes on `fb2` for the sparse
-// kernel.  The count is read on the device -- the host never synchronises inside a step -- and stored to a host-mapped slot.
+// First fallback level, always enqueued with the primary launches and running NEXT to them: the utterances on the device-side list
+// `fb` ({count, ids | attempt << 30}: their live window outgrew 8 groups) run again on the same recursion with a 32-group window, four
+// warps, starting at the beam that overflowed.  The CTAs poll the list while the primary CTAs are still running (ctl[0] counts the
+// finished ones, ctl[1] is the consumption cursor), so an overflowing utterance starts its second pass the moment it overflows, not
+// after the join of all classes: it is by construction a long utterance with a wide beam, i.e. the launch's critical path.  What
+// outgrows even 32 groups goes on `fb2` for the sparse kernel.  The count is stored to a host-mapped slot -- the host never
+// synchronises inside a step.  (The kernel is enqueued AFTER the primary launches: tools that serialise kernels then still terminate.)
+__device__ __forceinline__ int ld_vol(const int32_t *p) { return *(const volatile int32_t *)p; }
 __global__ void __launch_bounds__(128, 2)
-viterbi_band_wide_kernel(BandParams p, const int32_t *__restrict__ fb, int32_t *__restrict__ fb2, int64_t slab, int32_t *h_count) {
+viterbi_band_wide_kernel(BandParams p, const int32_t *fb, int32_t *__restrict__ fb2, int64_t slab, int32_t *h_count, int32_t *ctl, int total) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int n = fb[0];
-  if (blockIdx.x == 0 && threadIdx.x == 0) { *(volatile int32_t *)h_count = n; __threadfence_system(); }
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int e = fb[1 + i];
+  __shared__ int s_entry;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int entry = -1;
+      unsigned long long t0 = 0;
+      for (;;) {
+        const int n = ld_vol(fb), c = ld_vol(ctl + 1);
+        if (c < n) {
+          if (atomicCAS(ctl + 1, c, c + 1) != c) continue;
+          while ((entry = ld_vol(fb + 1 + c)) < 0) __nanosleep(100);   // the count is bumped before the entry is stored
+          break;
+        }
+        if (ld_vol(ctl) >= total) {            // every primary CTA has finished (fence + atomic on their side): the count is final
+          __threadfence();
+          if (ld_vol(ctl + 1) >= ld_vol(fb)) break;
+          continue;
+        }
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 20000000000ull) __trap();   // 20 s without a primary CTA finishing: fail loudly rather than spin
+        __nanosleep(2000);
+      }
+      if (entry < 0) { *(volatile int32_t *)h_count = ld_vol(fb); __threadfence_system(); }
+      s_entry = entry;
+    }
+    __syncthreads();
+    const int e = s_entry;
+    __syncthreads();
+    if (e < 0) return;
     band_utt<4, false, GM_WIDE>(p, e & 0x3FFFFFFF, p.bp + (size_t)blockIdx.x * slab, smraw, (e >> 30) & 1, fb2);
     __syncthreads();
   }
@@ -512,10 +545,12 @@ size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem, bo
 
 // Launches the band kernel for the utterances in `subset` (chunk-local ids, all band_ok).  d_fallback: [1 + n_utts] ints, count
 // first; cleared here.
-int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback) {
+int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, int max_groups, int32_t *d_fallback, int32_t *d_ctl) {
   const mfa_graphs *g = a.g;
   const int n = a.n_utts, ns = (int)subset.size();
+  CUDA_TRY(cudaMemsetAsync(d_fallback, 0xFF, ((size_t)n + 1) * sizeof(int32_t), e->stream));   // entries: -1 = not written yet
   CUDA_TRY(cudaMemsetAsync(d_fallback, 0, sizeof(int32_t), e->stream));
+  CUDA_TRY(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(int32_t), e->stream));
   if (ns == 0) return MFA_OK;
   const size_t limit = e->smem_optin - 4096;   // the kernel also has ~2 KB of static shared memory
   const bool graph_smem = e->cfg.vit_graph_smem != 0;
@@ -551,7 +586,7 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
   p.b_stw = g->d_b_stw; p.b_arc = (const uint2 *)g->d_b_arc; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
   p.utt0 = a.utt0; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
   p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u; p.bp_off = d_bp_off; p.bp = d_bp;
-  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fallback;
+  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fallback; p.done = d_ctl;
   p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
   p.min_active = a.opts.min_active; p.max_groups = std::max(1, std::min(max_groups, GM_MAIN));
@@ -594,11 +629,11 @@ int launch_viterbi_band(mfa_engine *e, const ViterbiArgs &a, const std::vector<i
 
 // Wide-band fallback level over the device-side list d_fb (see viterbi_band_wide_kernel); d_fb2 receives what overflows again.
 int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vector<int32_t> &subset, const int32_t *d_fb, int32_t *d_fb2,
-                             int32_t *h_count) {
+                             int32_t *h_count, int32_t *d_ctl) {
   const mfa_graphs *g = a.g;
   CUDA_TRY(cudaMemsetAsync(d_fb2, 0, sizeof(int32_t), e->stream));
   if (subset.empty()) return MFA_OK;
-  constexpr int kCtas = 16;
+  constexpr int kCtas = 8;   // resident next to the primary CTAs for the whole launch
   size_t smem = 0; int64_t slab = 0;
   for (int ul : subset) {
     const int ug = a.utt0 + ul;
@@ -616,18 +651,22 @@ int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vec
   p.b_stw = g->d_b_stw; p.b_arc = (const uint2 *)g->d_b_arc; p.b_fin = g->d_b_fin; p.b_arcid = g->d_b_arcid; p.b_orig = g->d_b_orig;
   p.utt0 = a.utt0; p.order = nullptr; p.llT = a.d_llT; p.ld = a.ld; p.col_off = a.d_col_off; p.frame_off = a.d_frame_off; p.word_off = a.d_word_off;
   p.ll_off = a.d_ll_off; p.ld_u = a.d_ld_u; p.bp_off = nullptr; p.bp = d_bp;
-  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fb2;
+  p.ali = a.d_ali; p.num_words = a.d_num_words; p.words = a.d_words; p.status = a.d_status; p.fallback = d_fb2; p.done = nullptr;
   p.per_frame = a.d_per_frame; p.total_like = a.d_total_like;
   p.acwt = a.opts.acoustic_scale; p.beam = a.opts.beam; p.retry_beam = a.opts.retry_beam; p.beam_delta = a.opts.beam_delta;
   p.min_active = a.opts.min_active; p.max_groups = GM_WIDE;
   smem = (smem + 15) / 16 * 16;
   if (smem + 8192 > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "internal: wide-band utterance exceeds shared memory");
   CUDA_TRY(cudaFuncSetAttribute(viterbi_band_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));      // the list reset above and the slab allocation precede the kernel on the join stream
-  CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_fb, 0));
-  viterbi_band_wide_kernel<<<ctas, 128, smem, e->sj>>>(p, d_fb, d_fb2, slab, h_count);
+  // its own highest-priority stream, ordered behind the main stream only (list resets, slab allocation): the CTAs become resident as
+  // soon as primary CTAs retire and poll from then on; the join stream waits for it before the sparse level
+  CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));
+  CUDA_TRY(cudaStreamWaitEvent(e->sw, e->ev_fb, 0));
+  viterbi_band_wide_kernel<<<ctas, 128, smem, e->sw>>>(p, d_fb, d_fb2, slab, h_count, d_ctl, (int)subset.size());
   e->launches++;
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(e->ev_wide, e->sw));
+  CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_wide, 0));
   return MFA_OK;
 }
 

@@ -1,6 +1,6 @@
-"""cProfile of AlignFunction through the MFA-shaped file flow (1 h synthetic corpus prepared by examples/two_pass_alignment.py)."""
+"""cProfile of the MFA-shaped file flow (examples/two_pass_alignment.py) on a synthetic corpus: cumulative and self-time views.
+Usage: python tools/profile_flow.py [out_dir] [seconds_of_audio]"""
 import cProfile, pstats, sys, os
-from pathlib import Path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "examples"))
 import two_pass_alignment as ex
@@ -9,4 +9,7 @@ pr = cProfile.Profile()
 pr.enable()
 ex.main()
 pr.disable()
-st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats(45)
+st = pstats.Stats(pr)
+st.sort_stats("cumulative").print_stats(40)
+st.sort_stats("tottime").print_stats(40)
+st.sort_stats("tottime").print_callers("astype|cumsum|repeat", 12)
