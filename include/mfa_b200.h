@@ -76,6 +76,9 @@ MFA_API int mfa_engine_gmm_timing(mfa_engine *e, float *total_ms, int64_t *n_lau
 /* useful FLOPs of those launches: 2*(2*dim+1) per (frame, Gaussian) actually scored.  The fused pipeline scores, per utterance,
  * only the pdfs its graph references (what Kaldi's decodable evaluates lazily), so this is less than frames x all Gaussians. */
 MFA_API int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops);
+/* FLOPs the tensor-core launches of the last call ISSUED: 3 fp16 products x 2 x K x 128 columns x 128 frames per (frame tile, Gaussian
+ * tile), padding columns / rows / K included; 0 when the last call scored with a CUDA-core kernel. */
+MFA_API int mfa_engine_gmm_issued_flops(mfa_engine *e, double *issued_flops);
 /* CUDA-event time (ms, engine stream) the last mfa_align_pcm call spent per stage:
  * ms4[0] = K1 MFCC + CMVN statistics (host-buffer calls: including the piecewise PCM upload it overlaps with),
  * ms4[1] = feature finalisation, ms4[2] = K2 log-likelihoods, ms4[3] = K3 Viterbi (all size classes, fork to join). */

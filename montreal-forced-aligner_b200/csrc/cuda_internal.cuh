@@ -68,7 +68,8 @@ struct mfa_engine {
   int gmm_ev_used = 0;
   int64_t gmm_rows = 0;
   double gmm_flops = 0.0;              // useful FLOPs (2*(2D+1) per frame x Gaussian actually scored) of the K2 launches timed
-  void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; gmm_flops = 0.0; }
+  double gmm_issued = 0.0;             // FLOPs those launches issued on the tensor pipe (padding included)
+  void gmm_timing_reset() { gmm_ev_used = 0; gmm_rows = 0; gmm_flops = 0.0; gmm_issued = 0.0; }
   int gmm_timing_begin();
   int gmm_timing_end(int64_t rows);
   // side streams + events: the Viterbi size classes run concurrently (fork/join around the main stream)

@@ -248,6 +248,11 @@ extern "C" int mfa_engine_gmm_flops(mfa_engine *e, double *useful_flops) {
   *useful_flops = e->gmm_flops;
   return MFA_OK;
 }
+extern "C" int mfa_engine_gmm_issued_flops(mfa_engine *e, double *issued_flops) {
+  if (!e || !issued_flops) return set_error(MFA_ERR_INVALID, "null argument");
+  *issued_flops = e->gmm_issued;
+  return MFA_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ model
 mfa_model::~mfa_model() {

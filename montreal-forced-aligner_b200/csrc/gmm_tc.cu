@@ -510,8 +510,12 @@ gather_b_kernel(const __half *__restrict__ w_rows, int64_t num_gauss, uint8_t *_
 }
 
 // Per-utterance tile plan of the ragged path, on the device (rebuilt whenever an M-step changed some pdf's component count): one
-// thread per utterance walks its pdf list (graphs' lp2pdf), counts the pdfs per width class (fill == 0: tiles per utterance) and, given
-// the utterance's first tile (fill == 1), writes the tiles' class / rows: tiles of a class are consecutive, classes ascending.
+// thread per utterance walks its pdf list (graphs' lp2pdf) and counts the pdfs per width class.  Tiles are then formed from the WIDEST
+// class down: a tile has the class of its widest pdf and cap(class) slots, and the slots its own class leaves free are handed to the
+// next narrower pdfs (a pdf fits any slot at least as wide as its component count; the gather pads).  Walking the pdfs in descending
+// width and closing a tile only when it is full minimises the number of tiles per utterance -- with one class per tile and no
+// hand-down a model whose pdfs spread over all eleven classes (any model after mix-up) paid up to ten partly filled tiles per
+// utterance.  fill == 0: tiles per utterance; fill == 1 (given the utterance's first tile): the tiles' class and rows.
 __global__ void rag_plan_kernel(int n_utts, const int64_t *__restrict__ lp_off, const int32_t *__restrict__ lp2pdf, const int32_t *__restrict__ pdf_off,
                                 int fill, int32_t *__restrict__ n_tiles_out, const int64_t *__restrict__ tile_off, TcAux *__restrict__ aux) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,28 +525,37 @@ __global__ void rag_plan_kernel(int n_utts, const int64_t *__restrict__ lp_off, 
 #pragma unroll
   for (int c = 0; c < NCLS; c++) cnt[c] = 0;
   for (int64_t k = k0; k < k1; k++) { const int pdf = lp2pdf[k]; cnt[cls_of(pdf_off[pdf + 1] - pdf_off[pdf])]++; }
-  int64_t base[NCLS];
-  int64_t t = fill ? tile_off[u] : 0;
-  for (int c = 0; c < NCLS; c++) {
+  // class c: its first take[c] pdfs (list order) go to slots inh_slot[c].. of the open tile inh_tile[c] of a wider class, the rest to its
+  // own tiles base[c], base[c] + 1, ...
+  int64_t base[NCLS], inh_tile[NCLS];
+  int take[NCLS], inh_slot[NCLS];
+  int64_t t = fill ? tile_off[u] : 0, open_tile = -1;
+  int room = 0, open_slot = 0;
+  for (int c = NCLS - 1; c >= 0; c--) {
+    int m = cnt[c];
+    take[c] = room < m ? room : m; inh_tile[c] = open_tile; inh_slot[c] = open_slot;
+    m -= take[c]; room -= take[c]; open_slot += take[c];
     base[c] = t;
-    const int nt = (cnt[c] + cls_cap(c) - 1) / cls_cap(c);
-    if (fill)
-      for (int i = 0; i < nt; i++) {
-        TcAux *ax = aux + t + i;
-        ax->cls = c; ax->lp_base = (int32_t)k0;
-        const int left = cnt[c] - i * cls_cap(c);
-        ax->npdf = left < cls_cap(c) ? left : cls_cap(c);
-        for (int j = 0; j < 32; j++) ax->row[j] = -1;
-      }
-    t += nt;
+    if (m > 0) {
+      const int cap = cls_cap(c), nt = (m + cap - 1) / cap;
+      if (fill)
+        for (int i = 0; i < nt; i++) {
+          TcAux *ax = aux + t + i;
+          ax->cls = c; ax->lp_base = (int32_t)k0; ax->npdf = cap;
+          for (int j = 0; j < 32; j++) ax->row[j] = -1;
+        }
+      open_tile = t + nt - 1; open_slot = m - (nt - 1) * cap; room = cap - open_slot;
+      t += nt;
+    }
     cnt[c] = 0;
   }
   if (!fill) { n_tiles_out[u] = (int)t; return; }
   for (int64_t k = k0; k < k1; k++) {
     const int pdf = lp2pdf[k];
     const int c = cls_of(pdf_off[pdf + 1] - pdf_off[pdf]);
-    const int slot = cnt[c]++;
-    aux[base[c] + slot / cls_cap(c)].row[slot % cls_cap(c)] = (int32_t)(k - k0);
+    const int i = cnt[c]++;
+    if (i < take[c]) aux[inh_tile[c]].row[inh_slot[c] + i] = (int32_t)(k - k0);
+    else { const int j = i - take[c]; aux[base[c] + j / cls_cap(c)].row[j % cls_cap(c)] = (int32_t)(k - k0); }
   }
 }
 
@@ -760,6 +773,7 @@ int launch_gmm_tc(mfa_engine *e, mfa_model *m, const float *d_feats, int64_t n_r
   p.a_img = d_a; p.b_img = (const uint8_t *)m->d_tc_w; p.aux = (const TcAux *)((const uint8_t *)m->d_tc_w + m->tc_w_bytes);
   p.items = d_items; p.n_items = (int)items.size(); p.out = d_llT;
   e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)m->num_gauss * (double)n_rows;
+  e->gmm_issued += 3.0 * 2.0 * TK * (double)TN * (double)nt * (double)(2 * TM) * (double)n_pairs;
   return launch_tc(e, p, TK);
 }
 
@@ -853,6 +867,7 @@ int launch_gmm_tc_ragged(mfa_engine *e, mfa_model *m, mfa_graphs *g, int utt0, i
     int64_t ng = 0;
     for (int64_t k = g->lp_off[utt0 + u]; k < g->lp_off[utt0 + u + 1]; k++) ng += m->h_pdf_off[g->lp2pdf[k] + 1] - m->h_pdf_off[g->lp2pdf[k]];
     e->gmm_flops += 2.0 * (2 * m->dim + 1) * (double)ng * (double)T;
+    e->gmm_issued += 3.0 * 2.0 * TK * (double)TN * (double)nb * (double)(2 * TM) * (double)((T + 2 * TM - 1) / (2 * TM));
   }
   if (items.empty()) return MFA_OK;
   // longest items first (static round-robin over CTAs then balances well)

@@ -156,6 +156,12 @@ class Engine:
         L.check(L.lib().mfa_engine_gmm_flops(self._h, C.byref(f)))
         return f.value
 
+    def gmm_issued_flops(self) -> float:
+        """FLOPs the tensor-core launches of the last call issued (padding included); 0 for the CUDA-core kernels."""
+        f = C.c_double()
+        L.check(L.lib().mfa_engine_gmm_issued_flops(self._h, C.byref(f)))
+        return f.value
+
     def fmllr_update(self, stats, dim: int, num_iters: int = 40, min_count: float = 500.0):
         """mfa_fmllr_update: per-speaker statistics [S, size] (numpy or torch cuda f64) -> (W [S, D, D+1] f32 of the same kind,
         objective improvement [S] numpy, count [S] numpy)."""
