@@ -24,6 +24,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before torch creates the CUDA context (see mfa_b200/_lib.py); reported in the line
 
 METRIC = "audio-sec aligned/sec (xRT)"
 UNIT = "audio-s/s"
@@ -815,7 +816,7 @@ def main():
     h2d_probe = {"gbs_per_rank": [round(x, 2) for x in probe_all], "concurrent_ranks": world,
                  "floor_ms_per_step": c.pcm.nbytes / (min(probe_all) * 1e9) * 1e3,
                  "what": "pinned-host -> device bandwidth of every rank while all ranks copy at once; floor = this step's PCM bytes at the slowest rank's rate",
-                 "host_cpus": len(os.sched_getaffinity(0))}
+                 "host_cpus": len(os.sched_getaffinity(0)), "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")}
     clocks["window"] = "device-resident timed steps + end-to-end timed steps"
     h2d = int(c.pcm.nbytes)
     d2h = int(sum(x.numel() * x.element_size() for x in h_outs))

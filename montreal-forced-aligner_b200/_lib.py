@@ -8,6 +8,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# read by the CUDA runtime when the context is created: an engine drives ~17 streams and MFA runs several jobs per GPU, the default of 8
+# hardware queues makes unrelated streams wait for one another (csrc/engine.cu sets the same default when the library is loaded)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 LIB_PATH = os.environ.get("MFA_B200_LIB") or os.path.join(HERE, "libmfa_b200.so")   # MFA_B200_LIB: a development build (tools/k2_experiment.py)
 
 MFA_HOST, MFA_DEVICE = 0, 1

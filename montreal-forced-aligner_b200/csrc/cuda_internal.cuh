@@ -25,7 +25,7 @@ enum DevBuf {
   DB_PCM = 0, DB_SAMPLE_OFF, DB_FRAME_OFF, DB_ROW_OFF, DB_UTT2SPK, DB_MFCC, DB_FEATS, DB_CMVN_PART, DB_CMVN_STATS,
   DB_SPK_UTT_OFF, DB_SPK_UTTS, DB_LDA, DB_FMLLR, DB_LL, DB_BP, DB_ALI, DB_PERFRAME, DB_WORDS, DB_WORD_OFF, DB_NUM_WORDS,
   DB_TOTAL_LIKE, DB_STATUS, DB_COL_OFF, DB_TILE_OFF, DB_BP_OFF, DB_UTT_ORDER, DB_IO_FEATS, DB_IO_LL, DB_IO_ALI, DB_XSPLIT,
-  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_K3_OFFS, DB_FB_CTL, DB_N
+  DB_CHUNK_FRAME_OFF, DB_SCRATCH, DB_TC_ITEMS, DB_BIMG, DB_TILE_ROW0, DB_TILE_ROWS, DB_LL_OFF, DB_LD_U, DB_MFCC_TAB, DB_BBP, DB_BBP_OFF, DB_BORDER, DB_FALLBACK, DB_ACC_INT, DB_ACC_ORDER, DB_FM_STATS, DB_FM_AUX, DB_FM_INVG, DB_FM_W, DB_FM_OUT, DB_FB_BP, DB_FB_BIG, DB_MLE, DB_RAG_CNT, DB_WIDE_BP, DB_FALLBACK2, DB_K3_OFFS, DB_FB_CTL, DB_TC_CTR, DB_N
 };
 enum PinBuf { PB_A = 0, PB_B, PB_C, PB_D, PB_E, PB_N };
 
@@ -35,6 +35,8 @@ struct mfa_engine_cfg {
   int vit_band = 1;            // 0: every utterance on the sparse Viterbi kernel
   int vit_maxgroups = 8;       // band width in groups of 32 states (1..8); tests narrow it to exercise the fallback
   int vit_wide = 1;            // 1: utterances that outgrow the band run on the 32-group band kernel before the sparse kernel is asked
+  int vit_wide_poll = -1;      // wide level: 1 = its CTAs poll the overflow list next to the primary launches, 0 = it runs after their join; -1 = poll in device-buffer calls only
+  int vit_wide_ctas = 8;       // CTAs of the wide level
   int vit_graph_smem = 0;      // 1: band kernel copies each graph to shared memory (default: read through L1)
   int vit_nw2_kb = -1;         // size classes up to this many KB of shared memory run 2 warps per utterance (-1: 20, or 44 with graph_smem)
   int vit_carveout = 100;      // shared-memory carve-out (percent) of the sparse kernel
@@ -239,6 +241,7 @@ struct ViterbiArgs {
   int32_t *d_ali; float *d_per_frame; int32_t *d_words; const int64_t *d_word_off; int32_t *d_num_words;
   float *d_total_like; int32_t *d_status;
   mfa_align_opts opts;
+  bool host_call = false;                      // the caller's buffers are host memory (the call ends with a join and device -> host copies)
 };
 int launch_viterbi(mfa_engine *e, const ViterbiArgs &a);
 size_t viterbi_band_smem(int64_t S, int64_t A, int64_t P, bool graph_in_smem, bool wide = false);   // shared memory the band kernel needs for one utterance

@@ -74,6 +74,7 @@ struct TcAux {
 };
 static_assert(sizeof(TcAux) == 672 && sizeof(TcAux) % 16 == 0, "TcAux must be 672 bytes");
 constexpr uint32_t AUX_BYTES = sizeof(TcAux);
+constexpr int IRING = 8;        // slots of the CTA's work-item ring (gmm_tc_kernel)
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -232,6 +233,7 @@ struct TcParams {
   const TcItem *items;    // [n_items]
   int n_items;
   float *out;             // pdf-major blocks: out[item.out_off + row * item.ld + frame]
+  int *counter;           // work counter of this launch (zeroed on the stream before it): items beyond the first gridDim.x are handed out dynamically
 #if MFA_TC_EXP == 7
   long long *dbg;         // [grid][16] cycle counters
 #endif
@@ -254,8 +256,14 @@ gmm_tc_kernel(TcParams p) {
   TcAux *sX = (TcAux *)(smem + (2 + NBt) * TILE_BYTES);   // 2 x side data (one per accumulator stage)
   uint64_t *bars = (uint64_t *)(smem + (2 + NBt) * TILE_BYTES + 2 * AUX_BYTES);
   uint64_t *full_a = bars + 0, *empty_a = bars + 1, *full_b = bars + 2, *empty_b = bars + 2 + NBt, *tfull = bars + 2 + 2 * NBt,
-           *tempty = tfull + 4, *gfull = tempty + 4, *gempty = gfull + 2;
-  uint32_t *tmem_slot = (uint32_t *)(gempty + 2);
+           *tempty = tfull + 4, *gfull = tempty + 4, *gempty = gfull + 2, *ifull = gempty + 2;
+  // item ring: the producer thread draws the CTA's next work item from a global counter (the items are sorted longest first, so this is
+  // longest-processing-time scheduling) and publishes it to the other roles.  A CTA that starts late -- its SM was still held by another
+  // kernel: a Viterbi tail, another job's launch -- then simply finds less work left, where a static round-robin made the whole launch
+  // wait for it.  No "empty" barrier: the producer is never more than four items ahead of the slowest reader (A buffer: 1, TMEM stages:
+  // 2, fetch-ahead: 1), the ring has eight slots.
+  volatile int32_t *s_item = (volatile int32_t *)(ifull + IRING);
+  uint32_t *tmem_slot = (uint32_t *)(s_item + IRING);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -263,6 +271,7 @@ gmm_tc_kernel(TcParams p) {
     for (int s = 0; s < NBt; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 2); }
     for (int i = 0; i < 4; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
     for (int i = 0; i < 2; i++) { mbar_init(gfull + i, 1); mbar_init(gempty + i, 256); }
+    for (int i = 0; i < IRING; i++) mbar_init(ifull + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -278,8 +287,13 @@ gmm_tc_kernel(TcParams p) {
   if (warp == 0) {
     // ===== producer: bulk copies of the A pair (once per item) and of each B tile =====
     if (lane == 0) {
-      uint32_t it = 0, sb = 0, phb = 0;   // sb / phb: slot of the B ring and the phase of its barriers
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      uint32_t sb = 0, phb = 0;   // sb / phb: slot of the B ring and the phase of its barriers
+      int item = blockIdx.x;
+      for (uint32_t it = 0;; it++) {
+        if (item >= n_items) item = -1;
+        s_item[it % IRING] = item;
+        mbar_arrive(ifull + it % IRING);
+        if (item < 0) break;
         const TcItem I = p.items[item];
         { DBG_T0(); mbar_wait(empty_a, (it & 1) ^ 1); DBG_ADD(0); }
         mbar_expect_tx(full_a, 2 * TILE_BYTES);
@@ -293,6 +307,7 @@ gmm_tc_kernel(TcParams p) {
           bulk_g2s(sB + sb * TILE_BYTES, p.b_img + (size_t)n * TILE_BYTES, TILE_BYTES, full_b + sb);
           if (++sb == NBt) { sb = 0; phb ^= 1; }
         }
+        item = (int)gridDim.x + atomicAdd(p.counter, 1);
       }
     }
   } else if (warp == 3) {
@@ -300,7 +315,10 @@ gmm_tc_kernel(TcParams p) {
     // -- its own thread, so a slow epilogue never delays the B ring =====
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (uint32_t it = 0;; it++) {
+        mbar_wait(ifull + it % IRING, (it / IRING) & 1);
+        const int item = s_item[it % IRING];
+        if (item < 0) break;
         const TcItem I = p.items[item];
         for (uint32_t n = I.b_tile0; n < I.b_tile0 + I.n_b; n++, cnt++) {
           const uint32_t sg = cnt & 1;
@@ -323,11 +341,14 @@ gmm_tc_kernel(TcParams p) {
       const uint32_t desc_hi = (SBO_BYTES >> 4) | (1u << 14);
       const uint32_t a_lo = (((smem_u32(sA) + f * TILE_BYTES) & 0x3FFFF) >> 4) | ((LBO_BYTES >> 4) << 16);
       const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFF) >> 4) | ((LBO_BYTES >> 4) << 16);
-      uint32_t cnt = 0, it = 0, sb = 0, phb = 0;
+      uint32_t cnt = 0, sb = 0, phb = 0;
 #if MFA_TC_EXP == 7
       const long long dbg_loop0 = clock64();
 #endif
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, it++) {
+      for (uint32_t it = 0;; it++) {
+        mbar_wait(ifull + it % IRING, (it / IRING) & 1);
+        const int item = s_item[it % IRING];
+        if (item < 0) break;
         const uint32_t n_b = p.items[item].n_b, rows_valid = p.items[item].rows_valid;
         const bool live = f == 0 || rows_valid > TM;   // a pair whose second tile holds no frames skips its MMAs
         { DBG_T0(); mbar_wait(full_a, it & 1); if (f == 0) DBG_ADD(3); }
@@ -373,7 +394,10 @@ gmm_tc_kernel(TcParams p) {
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     uint32_t cnt = 0;   // tiles seen by the CTA so far (all roles count alike); this warp serves those with (cnt & 1) == s
     const TcAux *ax = sX + s;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (uint32_t it = 0;; it++) {
+      mbar_wait(ifull + it % IRING, (it / IRING) & 1);
+      const int item = s_item[it % IRING];
+      if (item < 0) break;
       const TcItem I = p.items[item];
       const uint32_t row = f * TM + wq * 32 + lane;
       const bool row_ok = row < I.rows_valid;
@@ -690,7 +714,7 @@ namespace {
 
 template <int TKt, int NBt, bool GEPI, bool POLY>
 static int launch_tc_t(mfa_engine *e, const TcParams &p, int grid) {
-  const size_t smem = (2 + NBt) * (size_t)tile_bytes(TKt) + 2 * AUX_BYTES + 256;
+  const size_t smem = (2 + NBt) * (size_t)tile_bytes(TKt) + 2 * AUX_BYTES + 512;   // barriers + item ring
   CUDA_TRY(cudaFuncSetAttribute(gmm_tc_kernel<TKt, NBt, GEPI, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gmm_tc_kernel<TKt, NBt, GEPI, POLY><<<grid, NTHREADS, smem, e->stream>>>(p);
   return MFA_OK;
@@ -699,6 +723,8 @@ static int launch_tc_t(mfa_engine *e, const TcParams &p, int grid) {
 int launch_tc(mfa_engine *e, const TcParams &p_in, int tk) {
   TcParams p = p_in;
   const int grid = std::min(p.n_items, e->sm_count);
+  MFA_TRY(e->getT<int>(DB_TC_CTR, 1, &p.counter));
+  CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(int), e->stream));
 #if MFA_TC_EXP == 7
   static long long *d_dbg = nullptr;
   if (!d_dbg) cudaMalloc((void **)&d_dbg, 1024 * 16 * sizeof(long long));

@@ -432,7 +432,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
         a.g = g; a.utt0 = 0; a.n_utts = n_utts; a.d_llT = w_llT; a.ld = c.ld; a.d_col_off = w_col; a.d_frame_off = d_fo;
         a.h_frame_off = frame_off; a.h_col_off = c.col_off.data();
         a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off;
-        a.d_num_words = io.d_num_words; a.d_total_like = io.d_total; a.d_status = io.d_status; a.opts = o->align;
+        a.d_num_words = io.d_num_words; a.d_total_like = io.d_total; a.d_status = io.d_status; a.opts = o->align; a.host_call = where == MFA_HOST;
         MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
         MFA_TRY(launch_viterbi(e, a));
         MFA_TRY(e->stage_end(e->sj));
@@ -469,7 +469,7 @@ int mfa_align_pcm(mfa_engine *e, mfa_model *m, mfa_graphs *g, const mfa_pipeline
       a.g = g; a.utt0 = c.u0; a.n_utts = c.n; a.d_llT = d_llT; a.ld = c.ld; a.d_col_off = d_col; a.d_frame_off = d_fo + c.u0;
       a.h_frame_off = frame_off + c.u0; a.h_col_off = c.col_off.data();
       a.d_ali = io.d_ali; a.d_per_frame = io.d_pf; a.d_words = io.d_words; a.d_word_off = io.d_word_off + c.u0;
-      a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align;
+      a.d_num_words = io.d_num_words + c.u0; a.d_total_like = io.d_total + c.u0; a.d_status = io.d_status + c.u0; a.opts = o->align; a.host_call = where == MFA_HOST;
       MFA_TRY(e->stage_begin(mfa_engine::ST_VITERBI));
       MFA_TRY(launch_viterbi(e, a));
       MFA_TRY(e->stage_end(e->sj));

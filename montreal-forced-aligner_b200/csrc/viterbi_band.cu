@@ -633,7 +633,7 @@ int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vec
   const mfa_graphs *g = a.g;
   CUDA_TRY(cudaMemsetAsync(d_fb2, 0, sizeof(int32_t), e->stream));
   if (subset.empty()) return MFA_OK;
-  constexpr int kCtas = 8;   // resident next to the primary CTAs for the whole launch
+  const int kCtas = std::max(1, std::min(e->cfg.vit_wide_ctas, 64));
   size_t smem = 0; int64_t slab = 0;
   for (int ul : subset) {
     const int ug = a.utt0 + ul;
@@ -658,15 +658,22 @@ int launch_viterbi_band_wide(mfa_engine *e, const ViterbiArgs &a, const std::vec
   smem = (smem + 15) / 16 * 16;
   if (smem + 8192 > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "internal: wide-band utterance exceeds shared memory");
   CUDA_TRY(cudaFuncSetAttribute(viterbi_band_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // its own highest-priority stream, ordered behind the main stream only (list resets, slab allocation): the CTAs become resident as
-  // soon as primary CTAs retire and poll from then on; the join stream waits for it before the sparse level
+  // Polling mode: its own highest-priority stream, ordered behind the main stream only (list resets, slab allocation): the CTAs become
+  // resident as soon as primary CTAs retire and poll from then on; the join stream waits for it before the sparse level.  Otherwise the
+  // kernel goes on the join stream behind all classes (it then finds the list complete).  Default: poll in device-buffer calls, where
+  // nothing else of this engine competes for the SMs the pollers hold; host-buffer calls are issued by several jobs (engines) per GPU at
+  // once, and resident pollers of one job measurably slow the other jobs' launches (end to end, 2 jobs: 1.31 -> 1.15 M x RT).
+  const bool poll = e->cfg.vit_wide_poll >= 0 ? e->cfg.vit_wide_poll != 0 : !a.host_call;
+  cudaStream_t st = poll ? e->sw : e->sj;
   CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));
-  CUDA_TRY(cudaStreamWaitEvent(e->sw, e->ev_fb, 0));
-  viterbi_band_wide_kernel<<<ctas, 128, smem, e->sw>>>(p, d_fb, d_fb2, slab, h_count, d_ctl, (int)subset.size());
+  CUDA_TRY(cudaStreamWaitEvent(st, e->ev_fb, 0));
+  viterbi_band_wide_kernel<<<ctas, 128, smem, st>>>(p, d_fb, d_fb2, slab, h_count, d_ctl, (int)subset.size());
   e->launches++;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(e->ev_wide, e->sw));
-  CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_wide, 0));
+  if (poll) {
+    CUDA_TRY(cudaEventRecord(e->ev_wide, e->sw));
+    CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_wide, 0));
+  }
   return MFA_OK;
 }
 
