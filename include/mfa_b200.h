@@ -239,6 +239,13 @@ MFA_API int mfa_fst_batch_create(int32_t n_utts, const int64_t *state_off, const
                                  const float *finals, const int32_t *src, const int32_t *dst, const int32_t *ilabel,
                                  const int32_t *olabel, const float *weight, mfa_fst_batch **out);
 MFA_API int mfa_fst_batch_destroy(mfa_fst_batch *b);
+/* The state / arc body of a binary OpenFst VectorFst<StdArc> (what kalpy's FstArchive holds, alignment/multiprocessing.py:831): per state a
+ * float final weight and an int64 arc count, then 16-byte arcs {ilabel, olabel, weight, nextstate}.  `body` points behind the FST header
+ * (the host parses that: magic, type strings, flags, start, number of states).  scan: number of arcs and bytes of the body (error when
+ * it does not fit into `len`); fill: the arrays of mfa_fst_batch_create's arc-list form (finals[n_states], the rest [n_arcs]). */
+MFA_API int mfa_fst_body_scan(const uint8_t *body, int64_t len, int64_t n_states, int64_t *n_arcs, int64_t *n_bytes);
+MFA_API int mfa_fst_body_fill(const uint8_t *body, int64_t n_states, float *finals, int32_t *src, int32_t *dst, int32_t *ilabel,
+                              int32_t *olabel, float *weight);
 MFA_API int mfa_fst_batch_sizes(const mfa_fst_batch *b, int32_t *n_utts, int64_t *n_states, int64_t *n_arcs);
 MFA_API int mfa_fst_batch_export(const mfa_fst_batch *b, int64_t *state_off, int64_t *arc_off, int32_t *start,
                                  float *finals, int32_t *src, int32_t *dst, int32_t *ilabel, int32_t *olabel,

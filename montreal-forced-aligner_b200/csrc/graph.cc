@@ -433,6 +433,39 @@ struct GlibcRand {
 };
 }  // namespace
 
+// ---- binary OpenFst bodies (FstArchive import): see include/mfa_b200.h
+extern "C" int mfa_fst_body_scan(const uint8_t *body, int64_t len, int64_t n_states, int64_t *n_arcs, int64_t *n_bytes) {
+  if (!body || !n_arcs || !n_bytes || n_states < 0) return set_error(MFA_ERR_INVALID, "null argument");
+  int64_t pos = 0, arcs = 0;
+  for (int64_t s = 0; s < n_states; s++) {
+    if (pos + 12 > len) return set_error(MFA_ERR_INVALID, "truncated FST: state header beyond the buffer");
+    int64_t na;
+    memcpy(&na, body + pos + 4, 8);
+    if (na < 0 || na > (len - pos - 12) / 16) return set_error(MFA_ERR_INVALID, "truncated FST: arcs beyond the buffer");
+    pos += 12 + 16 * na;
+    arcs += na;
+  }
+  *n_arcs = arcs; *n_bytes = pos;
+  return MFA_OK;
+}
+extern "C" int mfa_fst_body_fill(const uint8_t *body, int64_t n_states, float *finals, int32_t *src, int32_t *dst, int32_t *ilabel,
+                                 int32_t *olabel, float *weight) {
+  if (!body || (n_states > 0 && !finals)) return set_error(MFA_ERR_INVALID, "null argument");
+  int64_t pos = 0, a = 0;
+  for (int64_t s = 0; s < n_states; s++) {
+    int64_t na;
+    memcpy(finals + s, body + pos, 4);
+    memcpy(&na, body + pos + 4, 8);
+    pos += 12;
+    for (int64_t k = 0; k < na; k++, a++, pos += 16) {
+      src[a] = (int32_t)s;
+      memcpy(ilabel + a, body + pos, 4); memcpy(olabel + a, body + pos + 4, 4);
+      memcpy(weight + a, body + pos + 8, 4); memcpy(dst + a, body + pos + 12, 4);
+    }
+  }
+  return MFA_OK;
+}
+
 extern "C" int mfa_rand_sequence(uint32_t seed, int32_t n, int32_t *out) {
   if (n < 0 || (n && !out)) return set_error(MFA_ERR_INVALID, "bad argument");
   GlibcRand g(seed);

@@ -382,7 +382,7 @@ class FstArchive:
 
     def __init__(self, file_name):
         self.file_name = str(file_name)
-        self._fsts = dict(K.read_ark(self.file_name, "fst"))
+        self._fsts = dict(K.read_fst_ark(self.file_name))
 
     def __getitem__(self, key) -> K.Fst:
         return self._fsts[key]
@@ -414,33 +414,38 @@ class Alignment:
 
     def __init__(self, utterance_id, alignment, words, likelihood=None, per_frame_likelihoods=None):
         self.utterance_id = utterance_id
-        self.alignment = [int(x) for x in alignment]
-        self.words = [int(x) for x in words]
+        self.alignment = np.asarray(alignment, np.int64).reshape(-1).tolist()   # plain ints, as kalpy returns them
+        self.words = np.asarray(words, np.int64).reshape(-1).tolist()
         self.likelihood = likelihood
         self.per_frame_likelihoods = None if per_frame_likelihoods is None else np.asarray(per_frame_likelihoods, np.float32)
 
     def generate_ctm(self, transition_model: K.TransitionModel, phone_table: Dict[int, str], frame_shift: float = 0.01) -> List[CtmInterval]:
         """Phone intervals from transition-ids: a phone ends at a transition into its HMM's final state followed (reorder=true)
         by that state's trailing self-loops (Kaldi SplitToPhones)."""
+        tids = np.asarray(self.alignment, np.int64)
+        n = tids.shape[0]
+        tm = transition_model
+        idx = np.nonzero(np.asarray(tm.is_final_tid)[tids])[0] if n else np.zeros(0, np.int64)
+        if idx.size == 0:
+            return []
+        # phone k ends behind its final transition idx[k] and the self-loops of that state which follow it: the first position after
+        # idx[k] whose transition-id differs (the next final transition at the latest) -- one segmented minimum instead of a Python loop
+        sl = np.asarray(tm.self_loop_tid)[np.asarray(tm.id2state)[tids[idx]]]
+        starts = idx + 1
+        seg = np.diff(np.append(starts, n + 1))
+        tp = np.append(tids, -1)                                   # position n: always a mismatch
+        cand = np.where(tp[starts[0]:] != np.repeat(sl, seg), np.arange(starts[0], n + 1), n)
+        ends = np.minimum.reduceat(cand, starts - starts[0])
+        begins = np.append(0, ends[:-1])
+        phones = np.asarray(tm.tid2phone)[tids[idx]]
+        if self.per_frame_likelihoods is not None:
+            cs = np.append(0.0, np.cumsum(self.per_frame_likelihoods, dtype=np.float64))
+            conf = (cs[ends] - cs[begins]) / (ends - begins)
+        else:
+            conf = np.zeros(idx.size)
         out: List[CtmInterval] = []
-        tids = self.alignment
-        n = len(tids)
-        start = 0
-        t = 0
-        while t < n:
-            tid = tids[t]
-            if transition_model.is_final_tid[tid]:
-                e = t + 1
-                sl = transition_model.self_loop_tid[transition_model.id2state[tid]]
-                while e < n and sl != 0 and tids[e] == sl:
-                    e += 1
-                ph = int(transition_model.tid2phone[tid])
-                conf = float(np.mean(self.per_frame_likelihoods[start:e])) if self.per_frame_likelihoods is not None else 0.0
-                out.append(CtmInterval(round(start * frame_shift, 4), round(e * frame_shift, 4), phone_table.get(ph, ph) if phone_table else ph, conf))
-                start = e
-                t = e
-            else:
-                t += 1
+        for b, e, ph, cf in zip(begins.tolist(), ends.tolist(), phones.tolist(), conf.tolist()):
+            out.append(CtmInterval(round(b * frame_shift, 4), round(e * frame_shift, 4), phone_table.get(ph, ph) if phone_table else ph, cf))
         return out
 
 

@@ -184,12 +184,16 @@ def test_band_kernel_equals_sparse_kernel(eng, triphone, beam, retry):
     assert f2 > f1                                      # the fallback path really ran
     narrow_sparse = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2, vit_wide=0)   # overflow -> sparse kernel directly
     assert eng.band_fallbacks - f2 == f2 - f1
+    f3 = eng.band_fallbacks
+    narrow_seq = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2, vit_wide_poll=0)   # wide level after the join instead of polling
+    assert eng.band_fallbacks - f3 == f2 - f1
+    narrow_few = _align_env(eng, sc, batch, beam, retry, vit_maxgroups=1 if beam < 100 else 2, vit_wide_poll=1, vit_wide_ctas=1)   # one poller takes the whole list
     if beam <= 10.0:
         assert f1 == f0                                   # ... and the default band is wide enough for ordinary beams
     assert np.isin(sparse.status, (0, 1)).sum() > 0
     smem4 = _align_env(eng, sc, batch, beam, retry, vit_graph_smem=1, vit_nw2_kb=0)   # graph in shared memory, 4 warps
     l1w4 = _align_env(eng, sc, batch, beam, retry, vit_nw2_kb=0)                           # graph through L1, 4 warps
-    for other in (band, narrow, narrow_sparse, smem4, l1w4):
+    for other in (band, narrow, narrow_sparse, narrow_seq, narrow_few, smem4, l1w4):
         assert np.array_equal(other.status, sparse.status) and np.array_equal(other.num_words, sparse.num_words)
         assert np.array_equal(other.ali, sparse.ali) and np.array_equal(other.words, sparse.words)
         assert np.array_equal(other.total_like, sparse.total_like) and np.array_equal(other.per_frame, sparse.per_frame)
@@ -615,3 +619,35 @@ def test_new_entry_points_edge_cases(eng):
     assert dm.acc_read()["frames"] == 0
     for x in (graphs, batch, dm, dm2, empty):
         x.close()
+
+
+def test_two_engines_on_one_gpu_from_two_threads(eng):
+    """MFA runs several jobs per device.  Two engines driven from two host threads (ctypes releases the GIL), each aligning the same batch
+    repeatedly with a 1-group band -- so that the polling wide-band level and the sparse level both run while the other engine's launches
+    are in flight -- must each reproduce the single-engine result bit for bit."""
+    import threading
+    sc = build_synth_scenario(seconds=80.0, seed=5, triphone=True, n_phones=12, n_words=60, target_pdfs=100, gauss_per_pdf=2)
+    batch = E.GraphCompiler(sc["tm"], sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts)
+    want = _align_env(eng, sc, batch, 10.0, 40.0)
+    eng2 = E.Engine(0)
+    results, errors = {}, []
+
+    def work(j, en):
+        try:
+            with en.options(vit_maxgroups=1, vit_wide_poll=1):
+                results[j] = [_gpu_align_from_oracle_loglikes(en, sc, batch, 10.0, 40.0) for _ in range(4)]
+        except Exception as ex:   # surfaced in the main thread
+            errors.append(repr(ex))
+
+    th = [threading.Thread(target=work, args=(j, en)) for j, en in enumerate((eng, eng2))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for j in (0, 1):
+        for got in results[j]:
+            assert np.array_equal(got.status, want.status) and np.array_equal(got.ali, want.ali) and np.array_equal(got.words, want.words)
+            assert np.array_equal(got.total_like, want.total_like) and np.array_equal(got.per_frame, want.per_frame)
+    assert eng2.band_fallbacks > 0
+    eng2.close()

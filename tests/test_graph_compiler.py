@@ -211,3 +211,34 @@ def test_band_view_refuses_epsilon_graphs():
               np.append(f.arc_weight, 0.25).astype(np.float32), np.append(f.finals, np.inf).astype(np.float32))
     bv = E.Graphs(E.FstBatch.from_fsts([g, f]), tm).band_view()
     assert bv["band_ok"].tolist() == [0, 1]
+
+
+def test_fst_archive_c_parser_equals_python_reader(tmp_path):
+    """kaldi_io.read_fst_ark (header in Python, state / arc body by mfa_fst_body_scan / _fill) against the pure-Python read_ark on a
+    written archive, including an empty FST and a state without arcs; truncated input is refused."""
+    import io
+    from mfa_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    fsts = []
+    for n_states in (1, 7, 40, 0):
+        na = 0 if n_states == 0 else int(rng.integers(0, 4 * n_states + 1))
+        src = np.sort(rng.integers(0, max(n_states, 1), na)).astype(np.int32)
+        f = K.Fst(0 if n_states else -1, n_states, src, rng.integers(0, 50, na).astype(np.int32), rng.integers(0, 9, na).astype(np.int32),
+                  rng.integers(0, max(n_states, 1), na).astype(np.int32), rng.random(na).astype(np.float32),
+                  np.where(rng.random(n_states) < 0.3, rng.random(n_states), np.inf).astype(np.float32))
+        fsts.append(f)
+    w = K.ArkWriter(str(tmp_path / "fsts.ark"))
+    for i, f in enumerate(fsts):
+        w.write_fst(f"utt-{i}", f)
+    w.close()
+    a = list(K.read_ark(str(tmp_path / "fsts.ark"), "fst"))
+    b = K.read_fst_ark(str(tmp_path / "fsts.ark"))
+    assert [k for k, _ in a] == [k for k, _ in b] == [f"utt-{i}" for i in range(len(fsts))]
+    for (_, x), (_, y), z in zip(a, b, fsts):
+        assert (x.start, x.num_states) == (y.start, y.num_states) == (z.start, z.num_states)
+        for name in ("arc_src", "arc_ilabel", "arc_olabel", "arc_dst", "arc_weight", "finals"):
+            assert np.array_equal(getattr(x, name), getattr(y, name)) and np.array_equal(getattr(y, name), getattr(z, name)), name
+    raw = (tmp_path / "fsts.ark").read_bytes()
+    (tmp_path / "cut.ark").write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(L.MfaError, match="truncated FST"):
+        K.read_fst_ark(str(tmp_path / "cut.ark"))
