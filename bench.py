@@ -920,6 +920,24 @@ def main():
                 line["cold_e2e"] = cold_single_shot(eng, sc, dev, args, cores)
             except Exception as ex:
                 line["cold_e2e"] = {"failed": repr(ex)}
+            # the MFA-shaped FILE flow (wav files -> MfccFunction -> CMVN -> features -> graph archives -> pass 1 -> fMLLR -> pass 2 ->
+            # TextGrids, all through the kalpy-compatible classes and Kaldi archives on disk) on 1 h of audio with a small model: what a
+            # maintainer who only swaps the imports gets; bound by per-utterance Python / file work, not by the GPU
+            try:
+                import shutil
+                import tempfile
+                sys.path.insert(0, os.path.join(ROOT, "examples"))
+                import two_pass_alignment as flow
+                tmp = tempfile.mkdtemp(prefix="mfa_b200_flow_")
+                try:
+                    from pathlib import Path
+                    line["file_flow"] = flow.run(Path(tmp), 3600.0, quiet=True)
+                    line["file_flow"]["what"] = ("examples/two_pass_alignment.py on 1 h of synthetic audio (200-pdf triphone LDA model, 2 jobs): wall clock from "
+                                                 "wav files to TextGrids incl. every archive written and read; first-call costs of the process included")
+                finally:
+                    shutil.rmtree(tmp, ignore_errors=True)
+            except Exception as ex:
+                line["file_flow"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the reference arm times the CPU path at every N)
         try:
             sc._fsts = sc.batch.export()

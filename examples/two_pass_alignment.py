@@ -24,6 +24,12 @@ from mfa_b200 import kaldi_io as K, kalpy_compat as KC, mfa_functions as MF, exp
 def main():
     out = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(tempfile.mkdtemp(prefix="mfa_b200_example_"))
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
+    run(out, seconds)
+
+
+def run(out: Path, seconds: float, quiet: bool = False) -> dict:
+    """The flow on `seconds` of synthetic audio under `out`; returns wall time, x real time and per-stage seconds (bench.py's file_flow)."""
+    say = (lambda *a: None) if quiet else print
     out.mkdir(parents=True, exist_ok=True)
     # a small synthetic "language", corpus and triphone LDA model; the model's Gaussians are estimated from the engine's own features
     from mfa_b200 import scenario as SC
@@ -65,14 +71,16 @@ def main():
     score2, failed2 = timed("align_pass2", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts))
     written = timed("textgrids", lambda: MF.export_textgrids(jobs, work, work / "final.mdl", lex, out / "aligned"))
     dt = time.time() - t0
-    print(f"{c.n_utts} utterances / {c.seconds:.0f} s of audio, {c.n_spk} speakers; files under {out}")
-    print(f"pass 1: mean log-likelihood per utterance {score1:.1f} ({failed1} failed); fMLLR for {len(fm)} speakers "
+    say(f"{c.n_utts} utterances / {c.seconds:.0f} s of audio, {c.n_spk} speakers; files under {out}")
+    say(f"pass 1: mean log-likelihood per utterance {score1:.1f} ({failed1} failed); fMLLR for {len(fm)} speakers "
           f"(mean objective improvement per frame {np.mean([v[0] / max(v[1], 1) for v in fm.values()]):.3f}); "
           f"pass 2: {score2:.1f} ({failed2} failed)")
     first = sorted(p for p in written.values() if p is not None)[0]
     tiers = X.read_textgrid(first)
-    print(f"{len(written)} TextGrids in {out / 'aligned'}; {first.name}: words = {[e[2] for e in tiers['words'] if e[2]][:8]} ...")
-    print(f"wall time incl. file I/O and graph compilation: {dt:.2f} s = {c.seconds / dt:.0f} x real time; per stage (s): {stages}")
+    say(f"{len(written)} TextGrids in {out / 'aligned'}; {first.name}: words = {[e[2] for e in tiers['words'] if e[2]][:8]} ...")
+    say(f"wall time incl. file I/O and graph compilation: {dt:.2f} s = {c.seconds / dt:.0f} x real time; per stage (s): {stages}")
+    return {"audio_s": float(c.seconds), "utterances": int(c.n_utts), "wall_s": dt, "xRT": c.seconds / dt, "stages_s": stages,
+            "failed_pass2": int(failed2), "textgrids": len(written)}
 
 
 if __name__ == "__main__":

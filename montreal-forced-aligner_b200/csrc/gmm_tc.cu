@@ -58,10 +58,12 @@ constexpr float kLn2 = 0.69314718055994530942f, kLog2e = 1.44269504088896340736f
 #endif
 
 // Width classes: pdfs of up to W components share tiles of class W.
-constexpr int NCLS = 11;
-__host__ __device__ constexpr int cls_width(int c) { return c < 8 ? 4 * (c + 1) : (c == 8 ? 48 : (c == 9 ? 64 : 128)); }
-__host__ __device__ constexpr int cls_cap(int c) { return TN / cls_width(c); }               // pdfs per tile: 32 16 10 8 6 5 4 4 2 2 1
-__host__ __device__ inline int cls_of(int ng) { return ng <= 32 ? (ng + 3) / 4 - 1 : (ng <= 48 ? 8 : (ng <= 64 ? 9 : 10)); }
+constexpr int NCLS = 14;
+// slot widths 4 6 8 10 12 14 16 | 20 24 28 32 | 48 64 128: even widths up to 16 (a 10-component pdf in a 12-wide slot wasted a sixth of
+// the tile: 10 pdfs per tile instead of 12), multiples of 4 up to 32, then the widths whose capacity still differs
+__host__ __device__ constexpr int cls_width(int c) { return c < 7 ? 4 + 2 * c : (c < 11 ? 20 + 4 * (c - 7) : (c == 11 ? 48 : (c == 12 ? 64 : 128))); }
+__host__ __device__ constexpr int cls_cap(int c) { return TN / cls_width(c); }               // pdfs per tile: 32 21 16 12 10 9 8 6 5 4 4 2 2 1
+__host__ __device__ inline int cls_of(int ng) { return ng <= 4 ? 0 : (ng <= 16 ? (ng + 1) / 2 - 2 : (ng <= 32 ? 7 + (ng - 17) / 4 : (ng <= 48 ? 11 : (ng <= 64 ? 12 : 13)))); }
 
 // Side data of one Gaussian tile (bulk-copied into shared memory next to the accumulator stage it belongs to).
 struct TcAux {
@@ -186,22 +188,22 @@ __device__ __forceinline__ void epi_tile(const uint32_t t0, const TcAux *__restr
       const int lo = (j * W > 32 * c ? j * W : 32 * c) - 32 * c, hi = ((j + 1) * W < 32 * c + 32 ? (j + 1) * W : 32 * c + 32) - 32 * c;
       if (lo >= hi) continue;
       const bool starts = j * W >= 32 * c, ends = (j + 1) * W <= 32 * c + 32;
-      // (lo, hi and W are multiples of 4: the loops run over 4-column groups with literal indices, which keeps v[] in registers)
-      float m = fmaxf(fmaxf(__uint_as_float(v[lo]), __uint_as_float(v[lo + 1])), fmaxf(__uint_as_float(v[lo + 2]), __uint_as_float(v[lo + 3])));
+      // (lo, hi and W are even: the loops run over column pairs with literal indices, which keeps v[] in registers)
+      float m = fmaxf(__uint_as_float(v[lo]), __uint_as_float(v[lo + 1]));
 #pragma unroll
-      for (int q4 = 1; q4 < 8; q4++) {
-        if (lo + 4 * q4 >= hi) break;
-        const int i = lo + 4 * q4;
-        m = fmaxf(m, fmaxf(fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]))));
+      for (int q2 = 1; q2 < 16; q2++) {
+        if (lo + 2 * q2 >= hi) break;
+        const int i = lo + 2 * q2;
+        m = fmaxf(m, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
       }
       float s0 = 0.0f, s1 = 0.0f;
       if (!starts) { const float nm = fmaxf(cm, m); s0 = cs * ex2(cm - nm); m = nm; }
 #pragma unroll
-      for (int q4 = 0; q4 < 8; q4++) {
-        if (lo + 4 * q4 >= hi) break;
-        const int i = lo + 4 * q4;
-        s0 += ex2(__uint_as_float(v[i]) - m) + ex2(__uint_as_float(v[i + 2]) - m);
-        s1 += ex2(__uint_as_float(v[i + 1]) - m) + (POLY ? ex2_poly(__uint_as_float(v[i + 3]) - m) : ex2(__uint_as_float(v[i + 3]) - m));
+      for (int q2 = 0; q2 < 16; q2++) {
+        if (lo + 2 * q2 >= hi) break;
+        const int i = lo + 2 * q2;
+        s0 += ex2(__uint_as_float(v[i]) - m);
+        s1 += (POLY && (q2 & 1)) ? ex2_poly(__uint_as_float(v[i + 1]) - m) : ex2(__uint_as_float(v[i + 1]) - m);
       }
       const float s = s0 + s1;
       if (ends) {
@@ -423,17 +425,20 @@ gmm_tc_kernel(TcParams p) {
         if (!tile_live) { tc_fence_before(); mbar_arrive(tempty + s * 2 + f); mbar_arrive(gempty + s); continue; }
         const uint32_t t0 = tmem_base + lane_base + s * 256 + f * 128;
         uint64_t *tb = tempty + s * 2 + f;
-        switch (ax->cls) {   // uniform across the CTA: one class per tile
+        switch (ax->cls) {   // uniform across the CTA: one class per tile (widths: cls_width)
           case 0: epi_tile<4, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 1: epi_tile<8, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 2: epi_tile<12, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 3: epi_tile<16, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 4: epi_tile<20, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 5: epi_tile<24, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 6: epi_tile<28, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 7: epi_tile<32, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 8: epi_tile<48, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
-          case 9: epi_tile<64, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 1: epi_tile<6, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 2: epi_tile<8, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 3: epi_tile<10, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 4: epi_tile<12, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 5: epi_tile<14, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 6: epi_tile<16, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 7: epi_tile<20, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 8: epi_tile<24, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 9: epi_tile<28, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 10: epi_tile<32, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 11: epi_tile<48, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
+          case 12: epi_tile<64, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
           default: epi_tile<128, GEPI, POLY>(t0, ax, out_base, I.ld, row_ok, tb); break;
         }
         mbar_arrive(gempty + s);   // this thread is done with the stage's side data

@@ -475,7 +475,7 @@ __device__ __forceinline__ void band_utt(const BandParams &p, const int ul, uint
 }
 
 #ifndef MFA_BAND_MINB2
-#define MFA_BAND_MINB2 8
+#define MFA_BAND_MINB2 10
 #endif
 template <int NW, bool GS>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : MFA_BAND_MINB2)
