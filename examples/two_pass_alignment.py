@@ -27,7 +27,7 @@ def main():
     run(out, seconds)
 
 
-def run(out: Path, seconds: float, quiet: bool = False) -> dict:
+def run(out: Path, seconds: float, quiet: bool = False, n_jobs: int = 2, threads: bool = True) -> dict:
     """The flow on `seconds` of synthetic audio under `out`; returns wall time, x real time and per-stage seconds (bench.py's file_flow)."""
     say = (lambda *a: None) if quiet else print
     out.mkdir(parents=True, exist_ok=True)
@@ -48,7 +48,8 @@ def run(out: Path, seconds: float, quiet: bool = False) -> dict:
     K.write_gmm_model(work / "final.mdl", tm, am)
     K.write_tree(work / "tree", sc["tree"])
     K.write_matrix_file(work / "lda.mat", sc["lda"])
-    jobs = MF.assign_jobs(utts, 2, split)
+    jobs = MF.assign_jobs(utts, n_jobs, split)
+    nthr = n_jobs if threads else 1   # MFA's USE_THREADING: the jobs of a stage as threads, each on its own engine
     t0 = time.time()
     stages = {}
 
@@ -58,17 +59,17 @@ def run(out: Path, seconds: float, quiet: bool = False) -> dict:
         stages[name] = round(time.time() - t, 3)
         return r
     mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
-    timed("mfcc", lambda: list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs])))
+    timed("mfcc", lambda: list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs], num_threads=nthr)))
     timed("cmvn", lambda: MF.calc_cmvn(jobs, split))
-    timed("final_features", lambda: list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs])))
+    timed("final_features", lambda: list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs], num_threads=nthr)))
     lex = {1: c.lexicon}
     timed("compile_graphs", lambda: list(MF.run_kaldi_function(
-        MF.CompileTrainGraphsFunction, [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "final.mdl") for j in jobs])))
+        MF.CompileTrainGraphsFunction, [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "final.mdl") for j in jobs], num_threads=nthr)))
     opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
-    score1, failed1 = timed("align_pass1", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts))
+    score1, failed1 = timed("align_pass1", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts, num_threads=nthr))
     sil = [c.lexicon.phone_table["sil"]]
     fm = timed("fmllr", lambda: MF.calc_fmllr(jobs, work, work / "final.mdl", work / "final.mdl", dict(silence_weight=0.0), sil))
-    score2, failed2 = timed("align_pass2", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts))
+    score2, failed2 = timed("align_pass2", lambda: MF.align_utterances(jobs, work, work / "final.mdl", opts, num_threads=nthr))
     written = timed("textgrids", lambda: MF.export_textgrids(jobs, work, work / "final.mdl", lex, out / "aligned"))
     dt = time.time() - t0
     say(f"{c.n_utts} utterances / {c.seconds:.0f} s of audio, {c.n_spk} speakers; files under {out}")
@@ -80,7 +81,7 @@ def run(out: Path, seconds: float, quiet: bool = False) -> dict:
     say(f"{len(written)} TextGrids in {out / 'aligned'}; {first.name}: words = {[e[2] for e in tiers['words'] if e[2]][:8]} ...")
     say(f"wall time incl. file I/O and graph compilation: {dt:.2f} s = {c.seconds / dt:.0f} x real time; per stage (s): {stages}")
     return {"audio_s": float(c.seconds), "utterances": int(c.n_utts), "wall_s": dt, "xRT": c.seconds / dt, "stages_s": stages,
-            "failed_pass2": int(failed2), "textgrids": len(written)}
+            "failed_pass2": int(failed2), "textgrids": len(written), "jobs": n_jobs, "jobs_as_threads": bool(threads)}
 
 
 if __name__ == "__main__":

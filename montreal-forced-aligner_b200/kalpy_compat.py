@@ -12,6 +12,8 @@ from dataclasses import dataclass
 from pathlib import Path
 from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
+import threading
+
 import numpy as np
 
 from . import engine as E, kaldi_io as K
@@ -19,16 +21,23 @@ from ._lib import MfaError
 from .gmm_update import AccumAmDiagGmm, mle_update
 from .lexicon import Lexicon
 
-_engines: Dict[int, E.Engine] = {}
+_engines: Dict[tuple, E.Engine] = {}
+_engines_lock = threading.Lock()
 
 
 def get_engine(device: Optional[int] = None) -> E.Engine:
-    """One engine per device per process (MFA runs one aligner per job; jobs map to GPUs via LOCAL_RANK / MFA_B200_DEVICE)."""
+    """One engine per device and per host THREAD.  MFA runs one aligner / accumulator per job and, with USE_THREADING, several jobs as
+    threads of one process (native code must be re-entrant): an engine owns one main stream and its scratch buffers and is not
+    re-entrant, so every job thread gets its own; the objects of this module remember the engine they were built with.  Jobs map to GPUs via
+    LOCAL_RANK / MFA_B200_DEVICE.  Engines of finished threads stay cached (thread ids are recycled) until the process ends."""
     if device is None:
         device = int(os.environ.get("MFA_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-    if device not in _engines:
-        _engines[device] = E.Engine(device)
-    return _engines[device]
+    key = (device, threading.get_ident())
+    with _engines_lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = _engines[key] = E.Engine(device)
+    return eng
 
 
 read_gmm_model = K.read_gmm_model
@@ -205,12 +214,9 @@ class MfccComputer:
         self.parameters = dict(mfcc_options)
         self.opts = E.mfcc_opts(**{k: v for k, v in mfcc_options.items() if k not in ("uses_cmvn", "use_pitch")})
         self.frame_shift = self.opts.frame_shift_ms
-        self.engine = None
 
     def _eng(self):
-        if self.engine is None:
-            self.engine = get_engine()
-        return self.engine
+        return get_engine()   # the calling thread's engine: MFA hands ONE MfccComputer to all jobs (MfccArguments), which may be threads
 
     def compute_mfccs_batch(self, pcm_list: Sequence[np.ndarray]) -> List[np.ndarray]:
         off = np.zeros(len(pcm_list) + 1, np.int64)

@@ -162,11 +162,22 @@ class KaldiFunction:
         raise NotImplementedError
 
 
-def run_kaldi_function(function, arguments: Sequence[MfaArguments], progress: Optional[Callable] = None):
-    """utils.py:1505-1642 minus the process/thread pool: on a GPU rank the jobs of that rank run back to back."""
-    for a in arguments:
+def run_kaldi_function(function, arguments: Sequence[MfaArguments], progress: Optional[Callable] = None, num_threads: int = 1):
+    """utils.py:1505-1642.  num_threads = 1: the jobs of this GPU rank run back to back; > 1: MFA's USE_THREADING mode -- jobs run as
+    threads of this process (utils.py:1560-1580), each on its own engine (kalpy_compat.get_engine is per thread), so that one job's
+    file / Python work overlaps another's GPU work.  Results are yielded per job in job order; the first job error is re-raised."""
+    def one(a):
         results = []
         function(a).run(results.append)
+        return results
+
+    if num_threads <= 1 or len(arguments) <= 1:
+        per_job = (one(a) for a in arguments)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(num_threads, len(arguments))) as ex:
+            per_job = list(ex.map(one, arguments))
+    for results in per_job:
         for r in results:
             if isinstance(r, int):
                 if progress:
@@ -348,13 +359,14 @@ class AlignFunction(KaldiFunction):
             feats.close()
 
 
-def align_utterances(jobs: Sequence[Job], working_directory, model_path, align_options: MetaDict, silence_phone_ids=(), training: bool = False):
+def align_utterances(jobs: Sequence[Job], working_directory, model_path, align_options: MetaDict, silence_phone_ids=(), training: bool = False,
+                     num_threads: int = 1):
     """AlignMixin.align_utterances (alignment/mixins.py:282-380): drains (utt, loglike), stores per-utterance likelihood / frames,
     returns the workflow score (mean log-likelihood per utterance); raises NoAlignmentsError when nothing aligned."""
     args = [AlignArguments(j.id, j, None, Path(working_directory), Path(model_path), align_options, False, False, silence_phone_ids) for j in jobs]
     by_id = {u.kaldi_id: u for j in jobs for u in j.utterances}
     likes = []
-    for utt_id, like in run_kaldi_function(AlignFunction, args):
+    for utt_id, like in run_kaldi_function(AlignFunction, args, num_threads=num_threads):
         u = by_id[utt_id]
         u.alignment_log_likelihood = like
         likes.append(like)

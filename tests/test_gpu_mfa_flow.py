@@ -1,5 +1,7 @@
 """-m gpu: MFA's corpus path and online path end to end through the kalpy-shaped API and the job functions, on files, against the
 oracle chain (including the 8-bit CompressedMatrix round trips of the corpus path)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -402,3 +404,47 @@ def test_two_pass_align_pcm_in_memory():
     assert np.abs(Wd - W).max() < 1e-4
     assert (r2d.ali.cpu().numpy()[: r2.ali.shape[0]] == r2.ali).mean() >= 0.999
     graphs.close(); batch.close(); dm.close()
+
+
+def test_jobs_as_threads_equal_jobs_in_sequence(tmp_path):
+    """MFA's USE_THREADING mode: the jobs of a stage run as threads of one process (utils.py:1560-1580), every thread on its own engine
+    (kalpy_compat.get_engine is per thread; the ONE MfccComputer of MfccArguments is shared by all jobs).  Every archive a stage writes
+    must be byte-identical to the sequential run."""
+    import threading
+    sc = build_synth_scenario(seconds=60.0, seed=23, triphone=False, n_phones=8, n_words=40, gauss_per_pdf=2, n_spk=4)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    id2w = c.lexicon.id2word
+    outs = {}
+    for mode, nthr in (("seq", 1), ("thr", 4)):
+        split = tmp_path / mode / "split"; work = tmp_path / mode / "work"
+        split.mkdir(parents=True); work.mkdir(parents=True)
+        K.write_gmm_model(work / "1.mdl", tm, am)
+        K.write_tree(work / "tree", sc["tree"])
+        utts = []
+        for u in range(c.n_utts):
+            wav = tmp_path / mode / f"u{u}.wav"
+            K.write_wav_int16(wav, c.pcm[c.sample_off[u]:c.sample_off[u + 1]])
+            utts.append(MF.Utterance(u, int(c.utt2spk[u]), str(wav), " ".join(id2w[w] for w in c.transcripts[u]),
+                                     duration=(c.sample_off[u + 1] - c.sample_off[u]) / 16000.0))
+        jobs = MF.assign_jobs(utts, 4, split)
+        mc = KC.MfccComputer(use_energy=False, dither=0.0, snip_edges=True)
+        list(MF.run_kaldi_function(MF.MfccFunction, [MF.MfccArguments(j.id, j, None, split, mc) for j in jobs], num_threads=nthr))
+        MF.calc_cmvn(jobs, split)
+        list(MF.run_kaldi_function(MF.FinalFeatureFunction, [MF.FinalFeatureArguments(j.id, j, None, split) for j in jobs], num_threads=nthr))
+        lex = {1: c.lexicon}
+        list(MF.run_kaldi_function(MF.CompileTrainGraphsFunction,
+                                   [MF.CompileTrainGraphsArguments(j.id, j, None, work, lex, work / "tree", work / "1.mdl") for j in jobs], num_threads=nthr))
+        opts = dict(transition_scale=1.0, acoustic_scale=0.1, self_loop_scale=0.1, beam=10, retry_beam=40, boost_silence=1.0)
+        score, n_fail = MF.align_utterances(jobs, work, work / "1.mdl", opts, num_threads=nthr)
+        assert n_fail == 0
+        files = {}
+        for j in jobs:
+            for name, d in (("feats", split), ("fsts", work), ("ali", work), ("words", work), ("likelihoods", work)):
+                pth = j.construct_path(d, name, "ark", 1) if d is work else j.construct_path(d, name, "ark")
+                files[(j.id, name)] = Path(pth).read_bytes()
+        outs[mode] = (score, files)
+    assert outs["seq"][0] == outs["thr"][0]
+    assert outs["seq"][1].keys() == outs["thr"][1].keys() and len(outs["seq"][1]) == 20
+    for k in outs["seq"][1]:
+        assert outs["seq"][1][k] == outs["thr"][1][k], k
+    assert len({id(e) for e in KC._engines.values()}) >= 2     # the worker threads really had their own engines
