@@ -570,7 +570,7 @@ def reference_arm(args, real_stdout):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * T / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config, "impl": "reference",
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "oracle_build": O.VARIANT},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "cuda_library_loaded": bool(loaded)}
     real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
@@ -941,13 +941,15 @@ def main():
                 line["file_flow"] = {"failed": repr(ex)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the reference arm times the CPU path at every N)
         try:
+            from oracle import oracle as O
             sc._fsts = sc.batch.export()
             sample_s = args.cpu_sample_seconds or 7200.0
             utts = pick_sample(sc, sample_s, also=[int(u) for u in retried[:2]])   # a retry-beam utterance is part of the parity sample
             cpu_reference_pass(sc, utts[: max(1, len(utts) // 10)], cores)
             dt, secs, ok, ref = cpu_reference_pass(sc, utts, cores)
             line["cpu_baseline"] = {"value": secs / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{len(utts)} utterances / {secs:.0f} audio-s of the same workload, {dt:.1f} s wall; oracle port"}
+                                    "sample": f"{len(utts)} utterances / {secs:.0f} audio-s of the same workload, {dt:.1f} s wall; oracle port",
+                                    "oracle_build": O.VARIANT}
             line["parity"] = parity_block(sc, utts, ref, gpu_host)
             line["frame_agreement_pct"] = line["parity"]["frame_agreement_pct"]
         except Exception as ex:  # the baseline is reported, never required

@@ -189,3 +189,38 @@ def test_gmm_loglikes_and_posteriors_against_sklearn():
         assert np.allclose(acc["occ"][a:b], gm.predict_proba(X[:8].astype(np.float64)).sum(0), rtol=1e-3, atol=1e-4)
         checked += 1
     assert checked >= 10
+
+
+def test_avx2_and_generic_oracle_builds_agree_bit_for_bit():
+    """oracle/Makefile builds oracle.c twice (-O2 generic; -O3 -mavx2, the one bench.py's CPU arm uses on AVX2 hosts).  No fused or
+    re-associated arithmetic in either (-ffp-contract=off, no -ffast-math): MFCC, log-likelihoods and a beam alignment must be identical
+    down to the last bit, otherwise the faster build could not stand in as the checker."""
+    import os
+    import subprocess
+    import sys
+    if O.VARIANT != "avx2":
+        pytest.skip("host without AVX2: only the generic build is in use")
+    code = (
+        "import sys, zlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from helpers import build_synth_scenario, oracle_align_all\n"
+        "from oracle import oracle as O\n"
+        "from mfa_b200 import engine as E\n"
+        "sc = build_synth_scenario(seconds=20.0, seed=11, triphone=True, n_phones=8, n_words=30, target_pdfs=60, gauss_per_pdf=3)\n"
+        "fsts = E.GraphCompiler(sc['tm'], sc['tree'], sc['corpus'].lexicon).compile(sc['corpus'].transcripts).export()\n"
+        "ref = oracle_align_all(sc, fsts, 10.0, 40.0)\n"
+        "g = O.GmmModel.from_am(sc['am'])\n"
+        "h = 0\n"
+        "for f in sc['feats']: h = zlib.crc32(np.ascontiguousarray(f).tobytes(), h); h = zlib.crc32(np.ascontiguousarray(O.gmm_loglikes(g, f)).tobytes(), h)\n"
+        "for r in ref: h = zlib.crc32(np.asarray(r['ali'], np.int32).tobytes(), h); h = zlib.crc32(np.asarray(r['per_frame'], np.float32).tobytes(), h); h = zlib.crc32(np.float64(r['like']).tobytes(), h)\n"
+        "print(O.VARIANT, h)\n"
+    ) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = {}
+    for generic in ("", "1"):
+        env = dict(os.environ)
+        env.pop("MFA_ORACLE_GENERIC", None)
+        if generic:
+            env["MFA_ORACLE_GENERIC"] = "1"
+        variant, crc = subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.split()[-2:]
+        outs[variant] = crc
+    assert set(outs) == {"avx2", "generic"} and outs["avx2"] == outs["generic"], outs
