@@ -101,7 +101,11 @@ struct FstBatch {
 };
 
 // One utterance.  Returns "" or an error string.
-static std::string compile_one(const GraphCompiler &C, const int32_t *words, int64_t nw, FstBuilder &out, int &start_state) {
+// transition-states of a phone in context, (left, phone, right) -> one per HMM state: six decision-tree walks and three map look-ups per
+// phone instance were most of the compile time; a worker thread keeps what it has resolved (contexts repeat across utterances)
+using CtxCache = std::unordered_map<uint64_t, std::vector<int>>;
+
+static std::string compile_one(const GraphCompiler &C, const int32_t *words, int64_t nw, FstBuilder &out, int &start_state, CtxCache &ctx_cache) {
   // ---- phone graph --------------------------------------------------------------------------
   // node ids: 0 = Start; per boundary i in 0..nw: NS_i = 1+3i, P_i = 2+3i, S_i = 3+3i; then chain nodes.
   std::vector<PhoneArc> arcs;
@@ -151,7 +155,8 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
   const bool tri = C.ctx_width == 3;
   struct Inst { int arc, l, r; std::vector<int> junctions; };  // junction graph nodes (hmm final reached)
   std::vector<Inst> insts;
-  std::map<std::tuple<int, int, int>, int> inst_id;
+  std::unordered_map<uint64_t, int> inst_id;   // (phone arc, left phone, right phone) -> instance
+  inst_id.reserve(arcs.size() * 4);
   out = FstBuilder();
   start_state = out.add_state();
   if (node_final[0] != kInf) out.finals[start_state] = node_final[0];
@@ -161,7 +166,7 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
   std::string err;
   auto get_inst = [&](int arc, int l, int r) -> int {
     if (!tri) { l = 0; r = 0; }
-    auto key = std::make_tuple(arc, l, r);
+    const uint64_t key = ((uint64_t)(uint32_t)arc << 40) | ((uint64_t)(uint32_t)l << 20) | (uint64_t)(uint32_t)r;   // phone ids < 2^20
     auto it = inst_id.find(key);
     if (it != inst_id.end()) return it->second;
     int id = (int)insts.size();
@@ -173,6 +178,8 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
   // per instance: entry arcs description = list of (tid, target graph node) for state-0 forward transitions
   struct Entry { int tid, node; };
   std::vector<std::vector<Entry>> entries;
+  std::vector<int> node_tab, tstate;          // scratch of expand(), reused across instances
+  std::vector<std::pair<int, int>> order;
   auto expand = [&](int id) {
     // NOTE: insts may reallocate inside; copy fields first
     int arc = insts[id].arc, l = insts[id].l, r = insts[id].r;
@@ -183,25 +190,30 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
     int nfinal = ns - 1;
     int ctx[3] = {l, ph, r};
     int ctx1[1] = {ph};
-    std::vector<int> tstate(ns, -1);
-    for (int j = 0; j < ns; j++) {
-      if (C.fwd_class[s0 + j] < 0) continue;
-      int fpdf = C.tree_lookup(tri ? ctx : ctx1, C.fwd_class[s0 + j]);
-      int spdf = C.tree_lookup(tri ? ctx : ctx1, C.self_class[s0 + j]);
-      if (fpdf < 0 || spdf < 0) { err = "tree has no pdf for context (" + std::to_string(l) + "," + std::to_string(ph) + "," + std::to_string(r) + ")"; return; }
-      tstate[j] = C.find_tstate(ph, j, fpdf, spdf);
-      if (tstate[j] < 0) { err = "no transition-state for phone " + std::to_string(ph) + " state " + std::to_string(j); return; }
+    const uint64_t ckey = tri ? (((uint64_t)(uint32_t)l << 40) | ((uint64_t)(uint32_t)ph << 20) | (uint64_t)(uint32_t)r) : (uint64_t)(uint32_t)ph;
+    auto hit = ctx_cache.find(ckey);
+    if (hit != ctx_cache.end()) tstate = hit->second;
+    else {
+      tstate.assign(ns, -1);
+      for (int j = 0; j < ns; j++) {
+        if (C.fwd_class[s0 + j] < 0) continue;
+        int fpdf = C.tree_lookup(tri ? ctx : ctx1, C.fwd_class[s0 + j]);
+        int spdf = C.tree_lookup(tri ? ctx : ctx1, C.self_class[s0 + j]);
+        if (fpdf < 0 || spdf < 0) { err = "tree has no pdf for context (" + std::to_string(l) + "," + std::to_string(ph) + "," + std::to_string(r) + ")"; return; }
+        tstate[j] = C.find_tstate(ph, j, fpdf, spdf);
+        if (tstate[j] < 0) { err = "no transition-state for phone " + std::to_string(ph) + " state " + std::to_string(j); return; }
+      }
+      ctx_cache.emplace(ckey, tstate);
     }
-    // nodes keyed by (j' dst, j src)
-    std::map<std::pair<int, int>, int> node;
-    std::vector<std::pair<int, int>> order;  // creation order (j', j)
+    // nodes keyed by (j' dst, j src): a flat ns x ns table (HMMs have a handful of states)
+    node_tab.assign((size_t)ns * ns, -1);
+    order.clear();                           // creation order (j', j)
     auto get_node = [&](int jd, int js) {
-      auto k = std::make_pair(jd, js);
-      auto it = node.find(k);
-      if (it != node.end()) return it->second;
-      int n = out.add_state();
-      node[k] = n; order.push_back(k);
-      return n;
+      int &slot = node_tab[(size_t)jd * ns + js];
+      if (slot >= 0) return slot;
+      slot = out.add_state();
+      order.push_back({jd, js});
+      return slot;
     };
     if ((int)entries.size() <= id) entries.resize(id + 1);
     // state-0 forward transitions become entry arcs (attached to predecessors' junctions later)
@@ -216,7 +228,7 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
     // closure over internal nodes
     for (size_t oi = 0; oi < order.size(); oi++) {
       int jd = order[oi].first, js = order[oi].second;
-      int n = node[order[oi]];
+      int n = node_tab[(size_t)jd * ns + js];
       if (jd != nfinal) {
         for (int t = C.trans_off[s0 + jd], k = 0; t < C.trans_off[s0 + jd + 1]; t++, k++) {
           int j2 = C.trans_dst[t];
@@ -235,13 +247,14 @@ static std::string compile_one(const GraphCompiler &C, const int32_t *words, int
   // seeds: arcs out of Start
   struct Pending { int from_node; int inst; int olabel; float cost; };  // attach inst's entry arcs at graph node
   std::vector<Pending> pend;
+  std::vector<int> rs;
   auto successors = [&](int pnode, int lphone, int from_graph_node, int rfilter) {
     // all instances following phone-graph node `pnode` with left phone `lphone`; rfilter = required phone (tri) or -1
     for (int ea : out_arcs[pnode]) {
       if (tri && rfilter >= 0 && arcs[ea].phone != rfilter) continue;
       int d = arcs[ea].dst;
       if (tri) {
-        std::vector<int> rs;
+        rs.clear();
         for (int e2 : out_arcs[d]) if (std::find(rs.begin(), rs.end(), arcs[e2].phone) == rs.end()) rs.push_back(arcs[e2].phone);
         if (node_final[d] != kInf) rs.push_back(0);
         for (int rr : rs) pend.push_back({from_graph_node, get_inst(ea, lphone, rr), arcs[ea].olabel, arcs[ea].cost});
@@ -280,16 +293,29 @@ static void trim(FstBuilder &g, int &start) {
   int S = (int)g.finals.size();
   size_t A = g.src.size();
   std::vector<char> fwd(S, 0), bwd(S, 0);
-  std::vector<std::vector<int>> outa(S), ina(S);
-  for (size_t a = 0; a < A; a++) { outa[g.src[a]].push_back((int)a); ina[g.dst[a]].push_back((int)a); }
+  // CSR adjacency in both directions (one allocation each: a vector per state made this the most expensive part of graph compilation)
+  std::vector<int> out_off(S + 1, 0), in_off(S + 1, 0), out_arc(A), in_arc(A);
+  for (size_t a = 0; a < A; a++) { out_off[g.src[a] + 1]++; in_off[g.dst[a] + 1]++; }
+  for (int s = 0; s < S; s++) { out_off[s + 1] += out_off[s]; in_off[s + 1] += in_off[s]; }
+  {
+    std::vector<int> oc(out_off.begin(), out_off.end() - 1), ic(in_off.begin(), in_off.end() - 1);
+    for (size_t a = 0; a < A; a++) { out_arc[oc[g.src[a]]++] = (int)a; in_arc[ic[g.dst[a]]++] = (int)a; }
+  }
   std::vector<int> st{start}; fwd[start] = 1;
-  while (!st.empty()) { int s = st.back(); st.pop_back(); for (int a : outa[s]) if (!fwd[g.dst[a]]) { fwd[g.dst[a]] = 1; st.push_back(g.dst[a]); } }
+  while (!st.empty()) {
+    int s = st.back(); st.pop_back();
+    for (int k = out_off[s]; k < out_off[s + 1]; k++) { const int d = g.dst[out_arc[k]]; if (!fwd[d]) { fwd[d] = 1; st.push_back(d); } }
+  }
   for (int s = 0; s < S; s++) if (g.finals[s] != kInf) { bwd[s] = 1; st.push_back(s); }
-  while (!st.empty()) { int s = st.back(); st.pop_back(); for (int a : ina[s]) if (!bwd[g.src[a]]) { bwd[g.src[a]] = 1; st.push_back(g.src[a]); } }
+  while (!st.empty()) {
+    int s = st.back(); st.pop_back();
+    for (int k = in_off[s]; k < in_off[s + 1]; k++) { const int d = g.src[in_arc[k]]; if (!bwd[d]) { bwd[d] = 1; st.push_back(d); } }
+  }
   std::vector<int> remap(S, -1); int n = 0;
   for (int s = 0; s < S; s++) if (fwd[s] && bwd[s]) remap[s] = n++;
   if (remap[start] < 0) { g = FstBuilder(); start = -1; return; }
   FstBuilder o; o.finals.resize(n);
+  o.src.reserve(A); o.dst.reserve(A); o.il.reserve(A); o.ol.reserve(A); o.w.reserve(A);
   for (int s = 0; s < S; s++) if (remap[s] >= 0) o.finals[remap[s]] = g.finals[s];
   for (size_t a = 0; a < A; a++) if (remap[g.src[a]] >= 0 && remap[g.dst[a]] >= 0) o.add_arc(remap[g.src[a]], remap[g.dst[a]], g.il[a], g.ol[a], g.w[a]);
   start = remap[start];
@@ -605,8 +631,9 @@ int mfa_graph_compile(mfa_graph_compiler *c, const int32_t *words, const int64_t
   if (n_threads < 1) n_threads = 1;
   n_threads = std::min<int>(n_threads, std::max(1, n_utts));
   auto worker = [&](int tid) {
+    CtxCache ctx_cache;
     for (int u = tid; u < n_utts; u += n_threads) {
-      errs[u] = compile_one(c->c, words + word_off[u], word_off[u + 1] - word_off[u], gs[u], starts[u]);
+      errs[u] = compile_one(c->c, words + word_off[u], word_off[u + 1] - word_off[u], gs[u], starts[u], ctx_cache);
       if (errs[u].empty()) trim(gs[u], starts[u]);
     }
   };
