@@ -541,13 +541,13 @@ def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
 
 def reference_arm(args, real_stdout):
     """`--impl reference`: the reference's CPU implementation of the path -- kalpy / Kaldi cannot be installed offline, so this is the
-    oracle port (oracle/oracle.c, scalar C, one utterance per host thread) -- on all host cores, on a bounded sample of the same workload
+    oracle port (oracle/oracle.c, the -O3 -mavx2 build on AVX2 hosts, one utterance per host thread) -- on all host cores, on a bounded sample of the same workload
     shape (same corpus generator, same model recipe: 4 000 pdfs / ~40 k Gaussians / D = 40), each step one pass over the sample.
     Nothing of this repo's CUDA library is loaded or called: scenario, features, graphs and alignment all come from oracle/."""
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    seconds = min(args.hours * 3600.0, args.cpu_sample_seconds or 1800.0)
+    seconds = min(args.hours * 3600.0, args.cpu_sample_seconds or 7200.0)   # 2 h: ~590 utterances of several speakers, ~0.5 s of 16-core work per step
     t0 = time.time()
     sc = reference_scenario(seconds, 1234, args.pdfs, args.gauss_per_pdf, cores)
     log(f"reference scenario ({sc.corpus.n_utts} utts, {sc.corpus.seconds:.0f} s, {sc.am.NumGauss()} Gaussians) built in {time.time() - t0:.1f}s without libmfa_b200.so")
