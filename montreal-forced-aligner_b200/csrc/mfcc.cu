@@ -31,7 +31,12 @@ struct MfccTables {  // offsets (in floats) into one device blob
   // fast path (mfcc512_kernel): per-lane mel chunks {first power bin, weight offset (floats, from the blob start), taps, mel bin},
   // per-bin {first chunk, number of chunks}; fast = 0 when the geometry does not fit
   int fast, off_chunk, off_binchunk, chunk_max;
+  // fixed-trip-count views for the fast path: per lane kMelTaps chunk weights (zero padded), per (coefficient, half) kDctTaps DCT weights
+  int off_cw, off_dct2, off_lift2;   // (the fast kernel stages only [off_melw, total) in shared memory)
 };
+constexpr int kMelTaps = 24;   // >= the largest chunk of MFA's 23-bin geometry (23 taps); geometries beyond it keep the runtime-length loop
+constexpr int kDctTaps = 16;   // >= half the mel bins (fast path: <= 32 bins)
+constexpr int kDctStride = 20; // row stride of the padded DCT table: 80 bytes keep the lanes' 16-byte reads on different banks
 
 static int round_up_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 static float mel_scale(float f) { return 1127.0f * logf(1.0f + f / 700.0f); }
@@ -77,7 +82,8 @@ static int build_tables(const mfa_mfcc_opts *o, MfccTables &t, std::vector<float
   t.total = t.off_melw + (int)melw.size();
   // fast-path tables: split every bin's taps into chunks of at most C taps, C minimal such that <= 32 chunks result
   t.fast = 0; t.chunk_max = 0;
-  t.off_chunk = (t.total + 3) / 4 * 4; t.off_binchunk = t.off_chunk + 4 * 32; t.total = t.off_binchunk + 2 * 32;
+  t.off_chunk = (t.total + 3) / 4 * 4; t.off_binchunk = t.off_chunk + 4 * 32; t.off_cw = t.off_binchunk + 2 * 32;
+  t.off_dct2 = t.off_cw + 32 * kMelTaps; t.off_lift2 = t.off_dct2 + 16 * 2 * kDctStride; t.total = t.off_lift2 + 16;
   std::vector<int> chunk(4 * 32, 0), binchunk(2 * 32, 0);
   if (t.NP == 512 && t.nbins <= 32 && t.nceps <= 16 && t.N >= 64 && t.N <= 512) {
     int C = 1;
@@ -113,6 +119,16 @@ static int build_tables(const mfa_mfcc_opts *o, MfccTables &t, std::vector<float
   for (int k = 0; k < t.nceps; k++)
     blob[t.off_lift + k] = (o->cepstral_lifter != 0.0f) ? (float)(1.0 + 0.5 * o->cepstral_lifter * sin(M_PI * k / o->cepstral_lifter)) : 1.0f;
   memcpy(&blob[t.off_melw], melw.data(), melw.size() * sizeof(float));
+  if (t.fast) {
+    // the same weights again, laid out for loops with a compile-time trip count (padding taps are exact zeros: they add +0 to a finite sum)
+    for (int lane = 0; lane < 32; lane++)
+      for (int i = 0; i < chunk[4 * lane + 2] && i < kMelTaps; i++) blob[t.off_cw + lane * kMelTaps + i] = blob[chunk[4 * lane + 1] + i];
+    const int half = (t.nbins + 1) / 2;
+    for (int c = 0; c < t.nceps; c++)
+      for (int h = 0; h < 2; h++)
+        for (int j = 0; j < half && h * half + j < t.nbins; j++) blob[t.off_dct2 + (c * 2 + h) * kDctStride + j] = blob[t.off_dct + c * t.nbins + h * half + j];
+    for (int c = 0; c < t.nceps; c++) blob[t.off_lift2 + c] = blob[t.off_lift + c];
+  }
   return MFA_OK;
 }
 
@@ -123,10 +139,10 @@ mfcc_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__restri
             const int64_t *__restrict__ frame_off, int n_utts, int64_t frame_base, int64_t n_frames, int64_t frames_per_warp, float *__restrict__ out,
             float preemph, int snip_edges, int remove_dc, int use_energy, int raw_energy, float log_energy_floor) {
   extern __shared__ float smem[];
-  float *stab = smem;                                   // t.total floats
+  float *stab = smem;                                   // blob[0, off_chunk): everything but the fast path's tables
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *wbuf = smem + ((t.total + 3) / 4 * 4) + warp * (4 * t.NB + 4);  // two float2[NB] buffers per warp
-  for (int i = threadIdx.x; i < t.total; i += blockDim.x) stab[i] = tab[i];
+  float *wbuf = smem + ((t.off_chunk + 3) / 4 * 4) + warp * (4 * t.NB + 4);  // two float2[NB] buffers per warp
+  for (int i = threadIdx.x; i < t.off_chunk; i += blockDim.x) stab[i] = tab[i];
   __syncthreads();
   const float *window = stab + t.off_window;
   const float2 *tw = (const float2 *)(stab + t.off_tw), *ptw = (const float2 *)(stab + t.off_ptw);
@@ -263,7 +279,8 @@ constexpr int kT1 = 34;                // row stride (float2) of the first trans
 constexpr int kT2 = 9;                 // row stride (float2) of the second transpose [lane][s]
 constexpr int kTB = 32 * kT2;          // float2 entries of the transpose / spectrum buffer: max(8 * kT1, 32 * kT2, 256 + 16)
 static_assert(kTB >= 8 * kT1 && kTB >= 256 + 16, "transpose buffer too small");
-constexpr int kWarpFloats = 2 * kTB + 260 + 32 + 32;   // transpose / spectrum buffer, power spectrum, chunk sums, log-mel
+constexpr int kPW = 260 + kMelTaps;    // power spectrum [257] + zero padding read by the fixed-length mel loop
+constexpr int kWarpFloats = 2 * kTB + kPW + 32 + 32;   // transpose / spectrum buffer, power spectrum, chunk sums, log-mel
 
 // int16 -> float without the conversion unit (I2F runs on the quarter-rate XU pipe and was 24 % of this kernel's stall samples):
 // 2^23 + 32768 + v is exactly representable, so the sample is planted in the mantissa of 2^23 and the bias subtracted -- exact.
@@ -279,14 +296,16 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
   float2 *s_win = (float2 *)smem;                        // [8][32]  window[64 m1 + 2 lane + {0,1}]
   float2 *s_tw1 = s_win + 8 * 32;                        // [8][32]  W_256^(lane k1)
   float2 *s_tw2 = s_tw1 + 8 * 32;                        // [8][32]  W_32^((lane & 3) s)
-  float *s_tab = (float *)(s_tw2 + 8 * 32);              // the table blob (mel weights, dct, lifter, chunk tables)
-  float *wbase = s_tab + ((t.total + 3) & ~3) + warp * kWarpFloats;
+  float *s_stage = (float *)(s_tw2 + 8 * 32);            // blob[off_melw, total): mel weights, chunk tables, padded mel / DCT weights, lifter
+  const int n_stage = t.total - t.off_melw;
+  const float *s_tab = s_stage - t.off_melw;             // so that blob offsets index it directly (only offsets >= off_melw are staged)
+  float *wbase = s_stage + ((n_stage + 3) & ~3) + warp * kWarpFloats;
   float2 *tb = (float2 *)wbase;                          // kTB float2: both transposes and the spectrum Z (idx(k) = k + 4 (k >> 6))
   float *pw = wbase + 2 * kTB;                       // [257] power spectrum
-  float *part = pw + 260;                                // [32] per-chunk mel sums
+  float *part = pw + kPW;                                // [32] per-chunk mel sums
   float *melv = part + 32;                               // [32] log mel energies
   const float2 *g_tw = (const float2 *)(tab + t.off_tw), *g_ptw = (const float2 *)(tab + t.off_ptw);
-  for (int i = threadIdx.x; i < t.total; i += blockDim.x) s_tab[i] = tab[i];
+  for (int i = threadIdx.x; i < n_stage; i += blockDim.x) s_stage[i] = tab[t.off_melw + i];
   for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
     const int a = i >> 5, l = i & 31, n = 64 * a + 2 * l;
     s_win[i] = make_float2(n < t.N ? tab[t.off_window + n] : 0.0f, n + 1 < t.N ? tab[t.off_window + n + 1] : 0.0f);
@@ -294,9 +313,12 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
     s_tw2[i] = g_tw[8 * (l & 3) * a];
   }
   __syncthreads();
+  for (int i = 257 + lane; i < kPW; i += 32) pw[i] = 0.0f;   // never written again: the padding taps of the mel loop read them
+  melv[lane] = 0.0f;                                        // slots >= nbins stay zero (padding taps of the DCT loop)
+  __syncwarp();
   const int4 *chunks = (const int4 *)(s_tab + t.off_chunk);
   const int2 *binchunk = (const int2 *)(s_tab + t.off_binchunk);
-  const float *dct = s_tab + t.off_dct, *lift = s_tab + t.off_lift;
+  const float *lift = s_tab + t.off_lift2;
   // W_512^k for this lane's pairs k = lane + 32 i
   float2 ptw[4];
 #pragma unroll
@@ -478,9 +500,20 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
     __syncwarp();
     // ---- mel: one balanced chunk of taps per lane, chunks of a bin summed in order, log
     {
+      // fixed trip count, weights zero-padded (the runtime-length loop cost 8 instructions per tap: 121 of the frame's 1 170)
       float e = 0.0f;
-      const float *w = s_tab + my_chunk.y, *pp = pw + my_chunk.x;
-      for (int i = 0; i < my_chunk.z; i++) e += w[i] * pp[i];
+      const float *pp = pw + my_chunk.x;
+      if (t.chunk_max <= kMelTaps) {
+        const float4 *w4 = (const float4 *)(s_tab + t.off_cw + lane * kMelTaps);
+#pragma unroll
+        for (int q = 0; q < kMelTaps / 4; q++) {
+          const float4 w = w4[q];
+          e += w.x * pp[4 * q]; e += w.y * pp[4 * q + 1]; e += w.z * pp[4 * q + 2]; e += w.w * pp[4 * q + 3];
+        }
+      } else {
+        const float *w = s_tab + my_chunk.y;
+        for (int i = 0; i < my_chunk.z; i++) e += w[i] * pp[i];
+      }
       part[lane] = e;
     }
     if (use_energy) {
@@ -498,9 +531,13 @@ mfcc512_kernel(MfccTables t, const float *__restrict__ tab, const int16_t *__res
     {
       float acc = 0.0f;
       if (dc_c < nceps) {
-        const float *d = dct + dc_c * nbins;
-        const int b0 = dc_h * dc_half, b1 = min(nbins, b0 + dc_half);
-        for (int b = b0; b < b1; b++) acc += d[b] * melv[b];
+        const float4 *d4 = (const float4 *)(s_tab + t.off_dct2 + (dc_c * 2 + dc_h) * kDctStride);
+        const float *mv = melv + dc_h * dc_half;
+#pragma unroll
+        for (int q = 0; q < kDctTaps / 4; q++) {
+          const float4 d = d4[q];
+          acc += d.x * mv[4 * q]; acc += d.y * mv[4 * q + 1]; acc += d.z * mv[4 * q + 2]; acc += d.w * mv[4 * q + 3];
+        }
       }
       acc += __shfl_down_sync(0xffffffffu, acc, 16);
       if (lane < nceps) {
@@ -574,7 +611,7 @@ int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, con
   }
   const bool fast = t.fast && !e->cfg.mfcc_generic;
   if (fast) {
-    const size_t smem = (size_t)(3 * 8 * 32 * 2 + ((t.total + 3) & ~3) + kFW * kWarpFloats) * sizeof(float);
+    const size_t smem = (size_t)(3 * 8 * 32 * 2 + ((t.total - t.off_melw + 3) & ~3) + kFW * kWarpFloats) * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(mfcc512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t max_warps = (int64_t)e->sm_count * 6 * kFW * 4;   // ~4 waves of 6 resident CTAs per SM: the tables are rebuilt per CTA
     int64_t fpw = (n_frames + max_warps - 1) / max_warps;
@@ -588,7 +625,7 @@ int launch_mfcc(mfa_engine *e, const mfa_mfcc_opts *o, const int16_t *d_pcm, con
     CUDA_TRY(cudaGetLastError());
     return MFA_OK;
   }
-  size_t smem = ((t.total + 3) / 4 * 4 + kWarps * (4 * t.NB + 4)) * sizeof(float);
+  size_t smem = ((t.off_chunk + 3) / 4 * 4 + kWarps * (4 * t.NB + 4)) * sizeof(float);
   if (smem > e->smem_optin) return set_error(MFA_ERR_UNSUPPORTED, "MFCC tables exceed shared memory");
   CUDA_TRY(cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t max_warps = (int64_t)e->sm_count * 16 * kWarps;  // ~16 resident CTAs of 4 warps per SM
