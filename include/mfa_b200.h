@@ -44,6 +44,10 @@ extern "C" {
 #define MFA_ALIGN_NO_FINAL 2
 #define MFA_ALIGN_EMPTY_GRAPH 3
 #define MFA_ALIGN_ZERO_FRAMES 4
+/* the utterance's training graph has more than 65 534 states or arcs (3-4 minutes of continuous speech): the packed graph views index
+ * states and arcs with 16 bits.  The utterance is skipped like any other failure (kalpy returns None), the rest of the batch is aligned;
+ * MFA's own segmentation (TextGrid intervals, VAD) keeps utterances far below this. */
+#define MFA_ALIGN_GRAPH_TOO_LARGE 5
 
 typedef struct mfa_engine mfa_engine;
 typedef struct mfa_model mfa_model;

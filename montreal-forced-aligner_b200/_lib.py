@@ -14,7 +14,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 LIB_PATH = os.environ.get("MFA_B200_LIB") or os.path.join(HERE, "libmfa_b200.so")   # MFA_B200_LIB: a development build (tools/k2_experiment.py)
 
 MFA_HOST, MFA_DEVICE = 0, 1
-ALIGN_STATUS = {0: "OK", 1: "RETRIED", 2: "NO_FINAL", 3: "EMPTY_GRAPH", 4: "ZERO_FRAMES"}
+ALIGN_STATUS = {0: "OK", 1: "RETRIED", 2: "NO_FINAL", 3: "EMPTY_GRAPH", 4: "ZERO_FRAMES", 5: "GRAPH_TOO_LARGE"}
 
 
 class MfaError(RuntimeError):

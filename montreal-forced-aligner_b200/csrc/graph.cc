@@ -716,13 +716,17 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     int err = 0;
   };
   std::vector<PackedUtt> pu(n);
+  // graphs beyond the 16-bit indices of the packed views are packed as EMPTY graphs and flagged: that utterance fails with its own
+  // status (MFA_ALIGN_GRAPH_TOO_LARGE), the rest of the batch is aligned
+  std::vector<uint8_t> big(n, 0);
   for (int u = 0; u < n; u++) {
     const int64_t S = b.state_off[u + 1] - b.state_off[u], A = b.arc_off[u + 1] - b.arc_off[u];
-    if (S > 65534 || A > 65534) return set_error(MFA_ERR_UNSUPPORTED, "graph of utterance " + std::to_string(u) + " exceeds 65534 states/arcs");
+    big[u] = S > 65534 || A > 65534;
   }
   auto work = [&](int u, std::vector<int32_t> &lpmap) {
     PackedUtt &P = pu[u];
-    const int64_t s0 = b.state_off[u], S = b.state_off[u + 1] - s0, a0 = b.arc_off[u], A = b.arc_off[u + 1] - a0;
+    const int64_t s0 = b.state_off[u], a0 = b.arc_off[u];
+    const int64_t S = big[u] ? 0 : b.state_off[u + 1] - s0, A = big[u] ? 0 : b.arc_off[u + 1] - a0;
     std::vector<int32_t> order(A);   // arcs by (src, original index)
     for (int64_t a = 0; a < A; a++) order[a] = (int32_t)a;
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return b.src[a0 + x] < b.src[a0 + y]; });
@@ -744,7 +748,7 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
       if (il > 0) { P.a_w[k] = b.w[a] + tid_cost[il]; P.a_lp[k] = lpmap[tid2pdf[il]]; }
       else { P.a_w[k] = b.w[a]; P.a_lp[k] = -1; P.n_eps++; }
     }
-    P.ok = build_band((int)S, (int)A, b.start[u], P.inb.data(), P.a_src.data(), P.a_dst.data(), P.a_lp.data(), P.a_w.data(), b.finals.data() + s0, P.bo);
+    P.ok = build_band((int)S, (int)A, big[u] ? -1 : b.start[u], P.inb.data(), P.a_src.data(), P.a_dst.data(), P.a_lp.data(), P.a_w.data(), b.finals.data() + s0, P.bo);
     if (!P.ok) { P.bo.stw.assign(S, 0); P.bo.fin.assign(S, 0.0f); P.bo.orig.assign(S, 0); P.bo.apk.assign(A, 0); P.bo.aw.assign(A, 0.0f); P.bo.arcid.assign(A, 0); }
   };
   {
@@ -763,21 +767,25 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
   g->num_tids = num_tids;
   g->st_off.assign(n + 1, 0); g->arc_off.assign(n + 1, 0); g->lp_off.assign(n + 1, 0); g->inb_off.assign(n + 1, 0);
   g->start.resize(n); g->n_eps.assign(n, 0); g->max_words.assign(n, 0);
+  g->too_large = big;
+  for (int u = 0; u < n; u++) g->n_too_large += big[u];
   for (int u = 0; u < n; u++) {
-    const int64_t S = b.state_off[u + 1] - b.state_off[u], A = b.arc_off[u + 1] - b.arc_off[u];
+    const int64_t S = big[u] ? 0 : b.state_off[u + 1] - b.state_off[u], A = big[u] ? 0 : b.arc_off[u + 1] - b.arc_off[u];
     g->st_off[u + 1] = g->st_off[u] + S; g->arc_off[u + 1] = g->arc_off[u] + A;
     g->lp_off[u + 1] = g->lp_off[u] + (int64_t)pu[u].pdfs.size(); g->inb_off[u + 1] = g->inb_off[u] + S + 1;
   }
   const size_t TS = (size_t)g->st_off[n], TA = (size_t)g->arc_off[n];
   g->in_begin.resize((size_t)g->inb_off[n]); g->lp2pdf.resize((size_t)g->lp_off[n]);
   g->a_src.resize(TA); g->a_dst.resize(TA); g->a_lp.resize(TA); g->a_tid.resize(TA); g->a_olabel.resize(TA); g->a_w.resize(TA); g->a_w0.resize(TA);
-  g->final_w.assign(b.finals.begin(), b.finals.begin() + TS);
+  g->final_w.resize(TS);
+  for (int u = 0; u < n; u++)
+    if (!big[u]) std::copy(b.finals.begin() + b.state_off[u], b.finals.begin() + b.state_off[u + 1], g->final_w.begin() + g->st_off[u]);
   g->band_ok.resize(n); g->b_start.resize(n); g->b_maxback.resize(n);
   g->b_stw.resize(TS); g->b_fin.resize(TS); g->b_orig.resize(TS); g->b_apk.resize(TA); g->b_aw.resize(TA); g->b_arcid.resize(TA);
   for (int u = 0; u < n; u++) {
     PackedUtt &P = pu[u];
     const size_t so = (size_t)g->st_off[u], ao = (size_t)g->arc_off[u];
-    g->start[u] = b.start[u]; g->n_eps[u] = P.n_eps; g->max_words[u] = P.words;
+    g->start[u] = big[u] ? -1 : b.start[u]; g->n_eps[u] = P.n_eps; g->max_words[u] = P.words;
     std::copy(P.inb.begin(), P.inb.end(), g->in_begin.begin() + g->inb_off[u]);
     std::copy(P.pdfs.begin(), P.pdfs.end(), g->lp2pdf.begin() + g->lp_off[u]);
     std::copy(P.a_src.begin(), P.a_src.end(), g->a_src.begin() + ao); std::copy(P.a_dst.begin(), P.a_dst.end(), g->a_dst.begin() + ao);

@@ -17,6 +17,8 @@ struct mfa_graphs {
   int32_t n_utts = 0;
   std::vector<int64_t> st_off, arc_off, lp_off, inb_off;
   std::vector<int32_t> start, n_eps, max_words;
+  std::vector<uint8_t> too_large;   // graph beyond the 16-bit packed views: packed as an empty graph, status MFA_ALIGN_GRAPH_TOO_LARGE
+  int32_t n_too_large = 0;
   std::vector<int32_t> in_begin;             // [sum(S_u+1)]
   std::vector<int32_t> a_src, a_dst, a_lp, a_tid, a_olabel;  // per arc; a_lp = local pdf index or -1 (epsilon input)
   std::vector<float> a_w;                    // graph weight + AddTransitionProbs cost

@@ -744,6 +744,12 @@ int launch_viterbi(mfa_engine *e, const ViterbiArgs &a_in) {
   }
   CUDA_TRY(cudaEventRecord(e->ev_fb, e->stream));
   CUDA_TRY(cudaStreamWaitEvent(e->sj, e->ev_fb, 0));   // (a launch without any class still orders the join stream behind the main stream)
+  if (g->n_too_large) {
+    // graphs that were packed as empty because they exceed the 16-bit views: their own status instead of EMPTY_GRAPH, after the kernels
+    static const int32_t kTooLarge = MFA_ALIGN_GRAPH_TOO_LARGE;
+    for (int u = 0; u < n; u++)
+      if (g->too_large[a.utt0 + u]) CUDA_TRY(cudaMemcpyAsync(a.d_status + u, &kTooLarge, sizeof(int32_t), cudaMemcpyHostToDevice, e->sj));
+  }
   CUDA_TRY(cudaEventRecord(e->ev_k3_done, e->sj));
   e->k3_pending = true;
   for (int i = 0; i < 6; i++) e->pend_out[i] = nullptr;   // the caller that defers the join says which buffers are being written

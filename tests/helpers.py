@@ -87,10 +87,10 @@ def oracle_features(pcm_list, utt2spk, n_spk, mode="deltas", lda=None, fmllr=Non
 
 
 def build_synth_scenario(seconds=40.0, seed=7, triphone=False, n_phones=12, n_words=60, target_pdfs=120, gauss_per_pdf=3,
-                         use_lda=False, n_spk=3, position_dependent=False):
+                         use_lda=False, n_spk=3, position_dependent=False, mean_utt_s=4.0, min_utt_s=1.0, max_utt_s=8.0):
     """Small synthetic corpus + a model estimated from its oracle features (CPU)."""
     corpus = SY.make_corpus(seconds, seed=seed, n_phones=n_phones, n_words=n_words, n_spk=n_spk, position_dependent=position_dependent,
-                            mean_utt_s=4.0, min_utt_s=1.0, max_utt_s=8.0)
+                            mean_utt_s=mean_utt_s, min_utt_s=min_utt_s, max_utt_s=max_utt_s)
     rng = np.random.default_rng(seed + 1)
     topo = SY.make_topology(corpus.phone_table)
     tree, n_pdfs = SY.make_tree(rng, topo, triphone, target_pdfs)

@@ -651,3 +651,61 @@ def test_two_engines_on_one_gpu_from_two_threads(eng):
             assert np.array_equal(got.total_like, want.total_like) and np.array_equal(got.per_frame, want.per_frame)
     assert eng2.band_fallbacks > 0
     eng2.close()
+
+
+def test_very_long_utterances_fused_path(eng):
+    """Maximum sizes: utterances of 2-4 minutes (12 000-24 000 frames, graphs of ~10^4 states -- near the 16-bit state / arc indices of the
+    packed graphs) next to short ones, through the fused PCM -> alignment call; every utterance against the oracle chain."""
+    sc = build_synth_scenario(seconds=600.0, seed=31, triphone=True, n_phones=10, n_words=50, target_pdfs=80, gauss_per_pdf=2, n_spk=2,
+                              mean_utt_s=150.0, min_utt_s=2.0, max_utt_s=240.0)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    T = np.diff(sc["frame_off"])
+    assert T.max() >= 11000
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    fsts = batch.export()
+    assert max(f.num_states for f in fsts) > 8000
+    ref = oracle_align_all(sc, fsts, 10.0, 40.0)
+    dm = E.DeviceModel(eng, tm, am)
+    graphs = E.Graphs(batch, tm, 1.0, 0.1)
+    res = E.align_pcm(eng, dm, graphs, c.pcm, c.sample_off, c.utt2spk, c.n_spk, E.mfcc_opts(), "deltas")
+    eng.sync()
+    same = total = 0
+    for u, r in enumerate(ref):
+        got = res.utterance(u)
+        assert got["status"] == r["status"], (u, got["status"], r["status"])
+        if r["status"] >= 2:
+            continue
+        same += int((got["ali"] == r["ali"]).sum()); total += len(r["ali"])
+        assert list(got["words"]) == list(r["words"])
+        assert abs(got["like"] - r["like"]) <= 1e-4 * abs(r["like"])
+    assert total >= 50000 and same / total >= 0.999, (same, total)
+    dm.close()
+
+
+def test_graph_beyond_16_bit_views_fails_alone(eng):
+    """A training graph with more than 65 534 states (minutes of continuous speech) cannot use the packed 16-bit graph views: that
+    utterance gets MFA_ALIGN_GRAPH_TOO_LARGE (5), its neighbours in the batch are aligned exactly as without it."""
+    sc = build_synth_scenario(seconds=12.0, seed=4, n_phones=6, n_words=20, gauss_per_pdf=2)
+    tm, am = sc["tm"], sc["am"]
+    from mfa_b200.kaldi_io import Fst
+    fsts = E.GraphCompiler(tm, sc["tree"], sc["corpus"].lexicon).compile(sc["corpus"].transcripts).export()
+    S = 70000
+    tid = int(fsts[0].arc_ilabel[fsts[0].arc_ilabel > 0][0])
+    fin = np.full(S, np.inf, np.float32); fin[-1] = 0.0
+    chain = Fst(0, S, np.arange(S - 1, dtype=np.int32), np.full(S - 1, tid, np.int32), np.zeros(S - 1, np.int32), np.arange(1, S, dtype=np.int32),
+                np.zeros(S - 1, np.float32), fin)
+    g = O.GmmModel.from_am(am)
+    lls = [O.gmm_loglikes(g, sc["feats"][0]), O.gmm_loglikes(g, sc["feats"][1]), O.gmm_loglikes(g, sc["feats"][2])]
+    fo = np.zeros(4, np.int64)
+    fo[1:] = np.cumsum([x.shape[0] for x in lls])
+    dm = E.DeviceModel(eng, tm, am)
+    with_big = E.align_loglikes(eng, dm, E.Graphs(E.FstBatch.from_fsts([fsts[0], chain, fsts[2]]), tm), np.concatenate(lls), fo, E.align_opts())
+    fo2 = np.asarray([0, lls[0].shape[0], lls[0].shape[0] + lls[2].shape[0]], np.int64)
+    without = E.align_loglikes(eng, dm, E.Graphs(E.FstBatch.from_fsts([fsts[0], fsts[2]]), tm), np.concatenate([lls[0], lls[2]]), fo2, E.align_opts())
+    assert [int(x) for x in with_big.status] == [int(without.status[0]), 5, int(without.status[1])]
+    assert int(with_big.status[0]) in (0, 1) and int(with_big.status[2]) in (0, 1)
+    for a, b in ((0, 0), (2, 1)):
+        x, y = with_big.utterance(a), without.utterance(b)
+        assert np.array_equal(x["ali"], y["ali"]) and list(x["words"]) == list(y["words"]) and x["like"] == y["like"]
+    assert with_big.utterance(1)["status"] == 5 and int(with_big.num_words[1]) == 0
+    dm.close()
