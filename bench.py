@@ -894,14 +894,26 @@ def main():
     # ---- training-loop / SAT stages next to the alignment path (config 4 and config 3's fMLLR pass), timed on their own with CUDA
     # events on the engine stream, OUTSIDE the timed alignment step: K4 accumulator statistics and K5 per-speaker fMLLR statistics
     # over the step's device-resident features and alignments.
-    # (multi-rank runs skip them unless --extras-dist: a rank failing inside would leave the others waiting in the all-reduce)
+    # (they run on every rank at every N: no collective inside, a failure is caught per rank; config 3 -- SAT two-pass on speaker shards --
+    # is then reported per rank: every rank's shard holds its own speakers, the way MFA's assign_jobs splits a corpus)
     if not args.no_extras:
         line["extras"] = {}
-        if world == 1 or args.extras_dist:
-            try:
-                line["extras"].update(train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args))
-            except Exception as ex:
-                line["extras"]["failed"] = repr(ex)
+        try:
+            line["extras"].update(train_extras(eng, sc, d_pcm, res, mo, dev, stream, pk, args))
+        except Exception as ex:
+            line["extras"]["failed"] = repr(ex)
+        if dist is not None:
+            mine_sat = line["extras"].get("sat_two_pass", {}).get("ms")
+            sat_all = [None] * world
+            dist.all_gather_object(sat_all, (mine_sat, float(c.seconds), int(c.n_spk)))
+            good = [x for x in sat_all if x[0] is not None]
+            if good:
+                ms = [x[0] for x in good]
+                line["extras"]["sat_two_pass_all_ranks"] = {
+                    "what": "config 3: two-pass SAT alignment, one speaker shard per GPU (speakers never span ranks, so fMLLR needs no collective); "
+                            "job time = the slowest rank", "ranks": len(good), "hours_all_ranks": sum(x[1] for x in good) / 3600.0,
+                    "speakers_all_ranks": sum(x[2] for x in good), "ms_min": min(ms), "ms_median": float(np.median(ms)), "ms_max": max(ms),
+                    "xRT_job": sum(x[1] for x in good) / (max(ms) * 1e-3)}
         # config 4's loop runs at every N: its all-reduce is the one collective of the path (a rank that fails before a collective
         # tells the others through a MIN all-reduce of an ok flag, so nobody waits forever)
         try:
