@@ -421,10 +421,8 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
   if (g->host_w_stale) return set_error(MFA_ERR_UNSUPPORTED, "these graphs had their transition costs re-folded on another device; pack them again for this one");
   if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
   size_t A = g->a_src.size();
-  std::vector<uint32_t> barc(2 * A);
-  for (size_t a = 0; a < A; a++) { barc[2 * a] = g->b_apk[a]; std::memcpy(&barc[2 * a + 1], &g->b_aw[a], 4); }
-  std::vector<uint32_t> pack(A);
-  for (size_t a = 0; a < A; a++) pack[a] = (uint32_t)(g->a_dst[a] & 0xFFFF) | ((uint32_t)(g->a_lp[a] < 0 ? 0xFFFF : g->a_lp[a]) << 16);
+  const auto &barc = g->h_barc; const auto &pack = g->h_apack;   // built by mfa_graphs_pack on its worker threads
+  if (barc.size() != 2 * A || pack.size() != A) return set_error(MFA_ERR_INVALID, "graphs object without device images");
   for (int u = 0; u < g->n_utts; u++)
     if (g->lp_off[u + 1] - g->lp_off[u] >= 0xFFFF) return set_error(MFA_ERR_UNSUPPORTED, "utterance graph references >= 65535 pdfs");
   struct Item { const void *h; size_t bytes; void **d; };
@@ -451,7 +449,7 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
     if (it.bytes) CUDA_TRY(cudaMemcpyAsync(*it.d, it.h, it.bytes, cudaMemcpyHostToDevice, e->stream));
     off += (it.bytes + 255) / 256 * 256;
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));  // `pack` is a local
+  CUDA_TRY(cudaStreamSynchronize(e->stream));  // the host arrays are pageable: the copies are staged, not asynchronous
   return MFA_OK;
 }
 }  // namespace mfa

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -95,8 +96,9 @@ struct FstBuilder {
 
 struct FstBatch {
   std::vector<int64_t> state_off{0}, arc_off{0};
-  std::vector<int32_t> start, src, dst, il, ol;
-  std::vector<float> finals, w;
+  std::vector<int32_t> start;
+  BigVec<int32_t> src, dst, il, ol;   // (filled completely by worker threads: see NoInitAlloc)
+  BigVec<float> finals, w;
   int32_t n() const { return (int32_t)start.size(); }
 };
 
@@ -642,17 +644,27 @@ int mfa_graph_compile(mfa_graph_compiler *c, const int32_t *words, const int64_t
   for (int u = 0; u < n_utts; u++) if (!errs[u].empty()) return set_error(MFA_ERR_GRAPH, "utterance " + std::to_string(u) + ": " + errs[u]);
   auto *fb = new mfa_fst_batch();
   FstBatch &b = fb->b;
+  // offsets first, then every thread copies its utterances into place (the serial append of ~180 MB was a third of the call)
+  b.state_off.assign((size_t)n_utts + 1, 0); b.arc_off.assign((size_t)n_utts + 1, 0);
+  b.start.assign(starts.begin(), starts.end());
   for (int u = 0; u < n_utts; u++) {
-    b.start.push_back(starts[u]);
-    b.finals.insert(b.finals.end(), gs[u].finals.begin(), gs[u].finals.end());
-    b.src.insert(b.src.end(), gs[u].src.begin(), gs[u].src.end());
-    b.dst.insert(b.dst.end(), gs[u].dst.begin(), gs[u].dst.end());
-    b.il.insert(b.il.end(), gs[u].il.begin(), gs[u].il.end());
-    b.ol.insert(b.ol.end(), gs[u].ol.begin(), gs[u].ol.end());
-    b.w.insert(b.w.end(), gs[u].w.begin(), gs[u].w.end());
-    b.state_off.push_back((int64_t)b.finals.size());
-    b.arc_off.push_back((int64_t)b.src.size());
+    b.state_off[u + 1] = b.state_off[u] + (int64_t)gs[u].finals.size();
+    b.arc_off[u + 1] = b.arc_off[u] + (int64_t)gs[u].src.size();
   }
+  const size_t TS = (size_t)b.state_off[n_utts], TA = (size_t)b.arc_off[n_utts];
+  b.finals.resize(TS); b.src.resize(TA); b.dst.resize(TA); b.il.resize(TA); b.ol.resize(TA); b.w.resize(TA);
+  auto gather = [&](int tid) {
+    for (int u = tid; u < n_utts; u += n_threads) {
+      const size_t so = (size_t)b.state_off[u], ao = (size_t)b.arc_off[u];
+      std::copy(gs[u].finals.begin(), gs[u].finals.end(), b.finals.begin() + so);
+      std::copy(gs[u].src.begin(), gs[u].src.end(), b.src.begin() + ao); std::copy(gs[u].dst.begin(), gs[u].dst.end(), b.dst.begin() + ao);
+      std::copy(gs[u].il.begin(), gs[u].il.end(), b.il.begin() + ao); std::copy(gs[u].ol.begin(), gs[u].ol.end(), b.ol.begin() + ao);
+      std::copy(gs[u].w.begin(), gs[u].w.end(), b.w.begin() + ao);
+      gs[u] = FstBuilder();
+    }
+  };
+  if (n_threads == 1) gather(0);
+  else { std::vector<std::thread> th; for (int t = 0; t < n_threads; t++) th.emplace_back(gather, t); for (auto &t : th) t.join(); }
   *out = fb;
   return MFA_OK;
 }
@@ -715,6 +727,9 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     BandOut bo;
     int err = 0;
   };
+  static const bool trace = getenv("MFA_PACK_TRACE") != nullptr;   // read once: phase times on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
   std::vector<PackedUtt> pu(n);
   // graphs beyond the 16-bit indices of the packed views are packed as EMPTY graphs and flagged: that utterance fails with its own
   // status (MFA_ALIGN_GRAPH_TOO_LARGE), the rest of the batch is aligned
@@ -761,6 +776,8 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(loop); for (auto &t : th) t.join(); }
   }
   for (int u = 0; u < n; u++) if (pu[u].err) return set_error(MFA_ERR_INVALID, "ilabel exceeds num_tids");
+  const double ms_phase1 = since(t_begin);
+  const auto t_alloc = std::chrono::steady_clock::now();
   // Phase 2: concatenate
   auto *g = new mfa_graphs();
   g->n_utts = n;
@@ -782,7 +799,10 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     if (!big[u]) std::copy(b.finals.begin() + b.state_off[u], b.finals.begin() + b.state_off[u + 1], g->final_w.begin() + g->st_off[u]);
   g->band_ok.resize(n); g->b_start.resize(n); g->b_maxback.resize(n);
   g->b_stw.resize(TS); g->b_fin.resize(TS); g->b_orig.resize(TS); g->b_apk.resize(TA); g->b_aw.resize(TA); g->b_arcid.resize(TA);
-  for (int u = 0; u < n; u++) {
+  g->h_barc.resize(2 * TA); g->h_apack.resize(TA);
+  const double ms_alloc = since(t_alloc);
+  const auto t_place = std::chrono::steady_clock::now();
+  auto place = [&](int u) {
     PackedUtt &P = pu[u];
     const size_t so = (size_t)g->st_off[u], ao = (size_t)g->arc_off[u];
     g->start[u] = big[u] ? -1 : b.start[u]; g->n_eps[u] = P.n_eps; g->max_words[u] = P.words;
@@ -796,8 +816,23 @@ int mfa_graphs_pack(const mfa_fst_batch *fb, const float *tid_cost, const int32_
     std::copy(P.bo.stw.begin(), P.bo.stw.end(), g->b_stw.begin() + so); std::copy(P.bo.fin.begin(), P.bo.fin.end(), g->b_fin.begin() + so);
     std::copy(P.bo.orig.begin(), P.bo.orig.end(), g->b_orig.begin() + so); std::copy(P.bo.apk.begin(), P.bo.apk.end(), g->b_apk.begin() + ao);
     std::copy(P.bo.aw.begin(), P.bo.aw.end(), g->b_aw.begin() + ao); std::copy(P.bo.arcid.begin(), P.bo.arcid.end(), g->b_arcid.begin() + ao);
+    for (size_t k = 0; k < P.a_dst.size(); k++) {
+      g->h_barc[2 * (ao + k)] = P.bo.apk[k]; std::memcpy(&g->h_barc[2 * (ao + k) + 1], &P.bo.aw[k], 4);
+      g->h_apack[ao + k] = (uint32_t)(P.a_dst[k] & 0xFFFF) | ((uint32_t)(P.a_lp[k] < 0 ? 0xFFFF : P.a_lp[k]) << 16);
+    }
     P = PackedUtt();   // release as we go
+  };
+  {
+    // (disjoint destination ranges per utterance: the placement runs on the same threads as phase 1)
+    static const int env_nt2 = [] { const char *ev = getenv("MFA_PACK_THREADS"); return ev ? atoi(ev) : 0; }();
+    int nt = env_nt2 > 0 ? env_nt2 : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(32, n)));
+    std::atomic<int> next{0};
+    auto loop = [&]() { for (int u = next.fetch_add(1); u < n; u = next.fetch_add(1)) place(u); };
+    if (nt <= 1) loop();
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; t++) th.emplace_back(loop); for (auto &t : th) t.join(); }
   }
+  if (trace) fprintf(stderr, "[mfa_graphs_pack] %d utterances: per-utterance packing %.1f ms, allocation %.1f ms, placement %.1f ms\n", n, ms_phase1, ms_alloc, since(t_place));
   *out = g;
   return MFA_OK;
 }

@@ -2,12 +2,28 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "../../include/mfa_b200.h"
 
 namespace mfa {
 int set_error(int code, const std::string &msg);
+
+// std::vector whose resize() leaves trivially constructible elements uninitialised.  The per-batch graph arrays are hundreds of MB that
+// worker threads fill completely: a zero-filling resize touched every page on ONE thread first (180 ms of page faults per 10 h batch);
+// now the first touch happens in the parallel fill.
+template <class T> struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  template <class U, class... A> void construct(U *p, A &&...a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+    else ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T> using BigVec = std::vector<T, NoInitAlloc<T>>;
 }
 
 // Decoder-ready batch of graphs (host copy; device mirror uploaded on first use by an engine).
@@ -17,21 +33,22 @@ struct mfa_graphs {
   int32_t n_utts = 0;
   std::vector<int64_t> st_off, arc_off, lp_off, inb_off;
   std::vector<int32_t> start, n_eps, max_words;
+  mfa::BigVec<uint32_t> h_barc, h_apack;   // device images built at pack time (per utterance, in parallel): {band arc word, weight} pairs; dst | local pdf << 16
   std::vector<uint8_t> too_large;   // graph beyond the 16-bit packed views: packed as an empty graph, status MFA_ALIGN_GRAPH_TOO_LARGE
   int32_t n_too_large = 0;
-  std::vector<int32_t> in_begin;             // [sum(S_u+1)]
-  std::vector<int32_t> a_src, a_dst, a_lp, a_tid, a_olabel;  // per arc; a_lp = local pdf index or -1 (epsilon input)
-  std::vector<float> a_w;                    // graph weight + AddTransitionProbs cost
-  std::vector<float> final_w;                // per state, +inf = non-final
-  std::vector<int32_t> lp2pdf;               // per utterance local pdf list (sorted pdf ids)
+  mfa::BigVec<int32_t> in_begin;             // [sum(S_u+1)]
+  mfa::BigVec<int32_t> a_src, a_dst, a_lp, a_tid, a_olabel;  // per arc; a_lp = local pdf index or -1 (epsilon input)
+  mfa::BigVec<float> a_w;                    // graph weight + AddTransitionProbs cost
+  mfa::BigVec<float> final_w;                // per state, +inf = non-final
+  mfa::BigVec<int32_t> lp2pdf;               // per utterance local pdf list (sorted pdf ids)
   // Band view (viterbi_band.cu): states renumbered in a topological order of the strongly-connected-component DAG (self-loops and
   // the small cycles of Kaldi's silence topology stay inside a component), arcs grouped by DESTINATION state in that order.
   // b_stw[st_off[u]+s]  = first in-arc (low 16) | in-degree << 16 | largest forward jump of s's out-arcs << 24
   // b_apk[arc_off[u]+j] = source band state (low 16) | local pdf << 16;  b_arcid = index of the same arc in the by-source arrays
   std::vector<int32_t> band_ok, b_start, b_maxback;   // per utterance; band_ok = 0: graph only runs on the sparse kernel
-  std::vector<uint32_t> b_stw, b_apk;
-  std::vector<float> b_aw, b_fin;
-  std::vector<uint16_t> b_arcid, b_orig;              // b_orig: band state -> original state id
+  mfa::BigVec<uint32_t> b_stw, b_apk;
+  mfa::BigVec<float> b_aw, b_fin;
+  mfa::BigVec<uint16_t> b_arcid, b_orig;              // b_orig: band state -> original state id
   // device mirror
   int device = -1;
   void *d_blob = nullptr;
@@ -48,7 +65,7 @@ struct mfa_graphs {
   // graph weights WITHOUT the AddTransitionProbs cost (a_w = a_w0 + tid_cost[a_tid]): what mfa_graphs_set_transitions re-folds on the
   // device when the transition model has been re-estimated.  After a re-fold the host copies of a_w / b_aw are stale.
   int32_t num_tids = 0;
-  std::vector<float> a_w0;
+  mfa::BigVec<float> a_w0;
   float *d_a_w0 = nullptr;
   bool host_w_stale = false;
   // per-utterance Gaussian tiling for the ragged K2 path (cached against the model's tiling version)
