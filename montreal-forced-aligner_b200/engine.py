@@ -83,6 +83,7 @@ class Engine:
         self._h = C.c_void_p()
         L.check(L.lib().mfa_engine_create(C.c_int(device), C.byref(self._h)))
         self.device = device
+        self._keepalive = []
 
     def close(self):
         if self._h:
@@ -97,6 +98,13 @@ class Engine:
 
     def sync(self):
         L.check(L.lib().mfa_engine_sync(self._h))
+        self._keepalive.clear()
+
+    def _hold(self, *tensors):
+        """Device-buffer calls return before their kernels have run (the Viterbi launch is not even joined on the main stream): the torch
+        tensors they read and write stay referenced here until sync(), so that torch's caching allocator -- which knows nothing about the
+        engine's streams -- cannot hand their memory to someone else meanwhile."""
+        self._keepalive.append(tensors)
 
     @property
     def stream(self) -> int:
@@ -646,6 +654,8 @@ def align_loglikes(engine: Engine, model: DeviceModel, graphs: Graphs, loglikes,
     p2 = [_buf(x, dt)[1] for x, dt in ((nw, np.int32), (tl, np.float32), (st, np.int32))]
     L.check(L.lib().mfa_align(engine._h, model._h, graphs._h, C.byref(opts), lp, fop, C.c_int32(n), ptrs[0], ptrs[1], ptrs[2],
                               wo.ctypes.data_as(C.c_void_p), p2[0], p2[1], p2[2], C.c_int(where)))
+    if where == L.MFA_DEVICE:
+        engine._hold(k, ali, pf, words, nw, tl, st)
     return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
 
 
@@ -664,6 +674,8 @@ def align_feats(engine: Engine, model: DeviceModel, graphs: Graphs, feats, frame
     L.check(L.lib().mfa_align_feats(engine._h, model._h, graphs._h, C.byref(opts), fp, fop, C.c_int32(n), C.c_int32(gmm_impl),
                                     C.c_int64(int(workspace_bytes)), ptrs[0], ptrs[1], ptrs[2], wo.ctypes.data_as(C.c_void_p), p2[0], p2[1], p2[2],
                                     C.c_int(where)))
+    if where == L.MFA_DEVICE:
+        engine._hold(k, ali, pf, words, nw, tl, st)
     return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
 
 
@@ -689,4 +701,6 @@ def align_pcm(engine: Engine, model: DeviceModel, graphs: Graphs, pcm, sample_of
     L.check(L.lib().mfa_align_pcm(engine._h, model._h, graphs._h, C.byref(po), pp, sop, usp, C.c_int32(n), C.c_int32(n_spk),
                                   fo.ctypes.data_as(C.c_void_p), ptrs[0], ptrs[1], ptrs[2], wo.ctypes.data_as(C.c_void_p),
                                   p2[0], p2[1], p2[2], C.c_int(where)))
+    if where == L.MFA_DEVICE:
+        engine._hold(k, keep, ali, pf, words, nw, tl, st)
     return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
