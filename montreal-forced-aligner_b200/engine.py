@@ -704,3 +704,77 @@ def align_pcm(engine: Engine, model: DeviceModel, graphs: Graphs, pcm, sample_of
     if where == L.MFA_DEVICE:
         engine._hold(k, keep, ali, pf, words, nw, tl, st)
     return AlignResult(ali, pf, words, wo, nw, tl, st, fo)
+
+
+def align_pcm_from_transcripts(engine: Engine, compiler: GraphCompiler, model: DeviceModel, transcripts, pcm, sample_off, utt2spk, n_spk: int,
+                               mfcc: L.MfccOpts, feat_mode: str = "deltas", lda=None, splice_ctx: int = 3, align: Optional[L.AlignOpts] = None,
+                               transition_scale: float = 1.0, self_loop_scale: float = 0.1, n_segments: int = 4, n_threads: int = 8,
+                               workspace_bytes: int = 0):
+    """Single-shot job from transcripts and HOST PCM (what CompileTrainGraphsFunction + AlignFunction do for one job,
+    alignment/multiprocessing.py:489-574,791-863): the batch is cut at speaker boundaries into `n_segments` pieces (CMVN is per speaker, so
+    a speaker never spans two pieces); the training graphs of piece k + 1 are compiled and packed on host threads WHILE piece k is
+    uploaded and aligned -- graph compilation is the host-bound part of a fresh batch, the GPU work hides behind it.
+    Utterances of a speaker must be contiguous (MFA orders a job by speaker); otherwise the batch runs as one piece.
+    -> (AlignResult with host arrays for the whole batch, dict of wall-clock stage times in ms)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    so = np.ascontiguousarray(sample_off, np.int64)
+    us = np.ascontiguousarray(utt2spk, np.int32)
+    n = so.shape[0] - 1
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    # ---- cuts: after a speaker change, near equal shares of the samples
+    contiguous = True
+    seen = set()
+    for u in range(n):
+        if u and us[u] != us[u - 1] and int(us[u]) in seen:
+            contiguous = False
+            break
+        seen.add(int(us[u]))
+    cuts = [0]
+    if contiguous and n_segments > 1:
+        for k in range(1, n_segments):
+            u = int(np.searchsorted(so, so[-1] * k // n_segments))
+            while 0 < u < n and us[u] == us[u - 1]:
+                u += 1
+            if cuts[-1] < u < n:
+                cuts.append(u)
+    cuts.append(n)
+    tm = compiler.tm
+    t = {"compile_pack_ms": [], "align_ms": [], "segments": len(cuts) - 1}
+
+    def prepare(k):
+        t0 = time.perf_counter()
+        batch = compiler.compile(transcripts[cuts[k]:cuts[k + 1]], n_threads=n_threads)
+        graphs = Graphs(batch, tm, transition_scale, self_loop_scale)
+        return batch, graphs, 1e3 * (time.perf_counter() - t0)
+
+    parts = []
+    t_all = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        nxt = ex.submit(prepare, 0)
+        for k in range(len(cuts) - 1):
+            batch, graphs, ms = nxt.result()
+            t["compile_pack_ms"].append(ms)
+            if k + 2 < len(cuts):
+                nxt = ex.submit(prepare, k + 1)
+            u0, u1 = cuts[k], cuts[k + 1]
+            uniq, local = np.unique(us[u0:u1], return_inverse=True)   # the piece's own speaker numbering
+            t0 = time.perf_counter()
+            r = align_pcm(engine, model, graphs, pcm[so[u0]:so[u1]], so[u0:u1 + 1] - so[u0], local.astype(np.int32), int(uniq.size), mfcc, feat_mode, lda=lda,
+                          splice_ctx=splice_ctx, align=align, workspace_bytes=workspace_bytes)
+            t["align_ms"].append(1e3 * (time.perf_counter() - t0))
+            parts.append(r)
+            t0 = time.perf_counter()
+            graphs.close(); batch.close()
+            t.setdefault("close_ms", []).append(1e3 * (time.perf_counter() - t0))
+    t["loop_ms"] = 1e3 * (time.perf_counter() - t_all)
+    t["total_ms"] = 1e3 * (time.perf_counter() - t_all)
+    fo = np.zeros(n + 1, np.int64)
+    wo = np.zeros(n + 1, np.int64)
+    fo[1:] = np.cumsum(np.concatenate([np.diff(r.frame_off) for r in parts])) if parts else 0
+    wo[1:] = np.cumsum(np.concatenate([np.diff(r.word_off) for r in parts])) if parts else 0
+    cat = lambda name: np.concatenate([getattr(r, name) for r in parts])
+    words = np.concatenate([r.words[:int(r.word_off[-1])] for r in parts]) if parts else np.zeros(0, np.int32)
+    ali = np.concatenate([r.ali[:int(r.frame_off[-1])] for r in parts])
+    pf = np.concatenate([r.per_frame[:int(r.frame_off[-1])] for r in parts])
+    return AlignResult(ali, pf, words, wo, cat("num_words"), cat("total_like"), cat("status"), fo), t

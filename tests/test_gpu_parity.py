@@ -709,3 +709,28 @@ def test_graph_beyond_16_bit_views_fails_alone(eng):
         assert np.array_equal(x["ali"], y["ali"]) and list(x["words"]) == list(y["words"]) and x["like"] == y["like"]
     assert with_big.utterance(1)["status"] == 5 and int(with_big.num_words[1]) == 0
     dm.close()
+
+
+def test_single_shot_from_transcripts_pipelined_equals_one_call(eng):
+    """align_pcm_from_transcripts compiles / packs piece k + 1 while piece k is aligned; cut at speaker boundaries, every utterance must
+    come out exactly as from ONE compile + ONE fused call over the whole batch (per-speaker CMVN, per-utterance scoring and Viterbi)."""
+    sc = build_synth_scenario(seconds=90.0, seed=13, triphone=True, n_phones=10, n_words=50, target_pdfs=80, gauss_per_pdf=2, n_spk=5)
+    c, tm, am = sc["corpus"], sc["tm"], sc["am"]
+    order = np.argsort(c.utt2spk, kind="stable")             # a job ordered by speaker, as MFA's are
+    pcm = np.concatenate([c.pcm[c.sample_off[u]:c.sample_off[u + 1]] for u in order])
+    so = np.zeros(c.n_utts + 1, np.int64); so[1:] = np.cumsum([c.sample_off[u + 1] - c.sample_off[u] for u in order])
+    u2s = c.utt2spk[order].astype(np.int32)
+    tr = [c.transcripts[u] for u in order]
+    dm = E.DeviceModel(eng, tm, am)
+    gc = E.GraphCompiler(tm, sc["tree"], c.lexicon)
+    batch = gc.compile(tr)
+    one = E.align_pcm(eng, dm, E.Graphs(batch, tm, 1.0, 0.1), pcm, so, u2s, c.n_spk, E.mfcc_opts(), "deltas")
+    piped, times = E.align_pcm_from_transcripts(eng, gc, dm, tr, pcm, so, u2s, c.n_spk, E.mfcc_opts(), "deltas", n_segments=3, n_threads=4)
+    assert times["segments"] == 3 and len(times["align_ms"]) == 3
+    assert np.array_equal(piped.status, one.status) and np.array_equal(piped.frame_off, one.frame_off) and np.array_equal(piped.num_words, one.num_words)
+    assert np.array_equal(piped.total_like, one.total_like)
+    for u in range(c.n_utts):
+        a, b = piped.utterance(u), one.utterance(u)
+        assert np.array_equal(a["ali"], b["ali"]) and np.array_equal(a["per_frame"], b["per_frame"]) and list(a["words"]) == list(b["words"])
+    assert int((one.status < 2).sum()) >= c.n_utts - 1
+    dm.close(); gc.close()
