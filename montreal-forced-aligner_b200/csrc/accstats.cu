@@ -251,7 +251,7 @@ extern "C" int mfa_acc_zero(mfa_engine *e, mfa_model *m) {
   CUDA_TRY(cudaSetDevice(e->device));
   MFA_TRY(e->join_k3());
   size_t bytes = (size_t)mfa_acc_size(m) * sizeof(double);
-  if (!m->d_acc) CUDA_TRY(cudaMalloc((void **)&m->d_acc, bytes));
+  MFA_TRY(m->acc_take(bytes));
   CUDA_TRY(cudaMemsetAsync(m->d_acc, 0, bytes, e->stream));
   return MFA_OK;
 }
@@ -271,7 +271,7 @@ extern "C" int mfa_acc_write(mfa_engine *e, mfa_model *m, const double *host_in)
   if (!e || !m || !host_in) return set_error(MFA_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(e->device));
   const size_t bytes = (size_t)mfa_acc_size(m) * sizeof(double);
-  if (!m->d_acc) CUDA_TRY(cudaMalloc((void **)&m->d_acc, bytes));
+  MFA_TRY(m->acc_take(bytes));
   CUDA_TRY(cudaMemcpyAsync(m->d_acc, host_in, bytes, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return MFA_OK;

@@ -209,6 +209,16 @@ struct mfa_model {
   float *d_tc_g = nullptr;             // gconst * log2(e): [G] per Gaussian, then [n_tiles][128] per column of the dense tiling
   uint64_t tc_version = 0;             // hash of the pdf -> Gaussian layout and the operand geometry: the key of the cached ragged plans
   double *d_acc = nullptr;
+  // Steady-state training must not call cudaMalloc / cudaFree: on this platform a tenth of those calls take 30-400 ms (tools/
+  // mstep_latency.py).  The M-step writes into a SPARE set of parameter arrays and swaps; the accumulator block and the K2 images keep
+  // their allocations; everything grows by capacity only.
+  size_t par_cap = 0;                  // Gaussians the CURRENT d_gconsts / d_miv / d_iv / d_weights were allocated for
+  float *sp_gconsts = nullptr, *sp_miv = nullptr, *sp_iv = nullptr, *sp_weights = nullptr; int32_t *sp_pdf_off = nullptr;
+  size_t sp_cap = 0;                   // Gaussians the spare set holds
+  double *acc_spare = nullptr;         // a consumed accumulator block waiting for the next mfa_acc_zero / mfa_acc_write
+  size_t acc_cap_bytes = 0;            // bytes of the block d_acc or acc_spare points to
+  size_t tc_w_cap = 0;                 // bytes d_tc_w was allocated with
+  int acc_take(size_t bytes);          // make d_acc a block of at least `bytes` (reusing the spare)
   ~mfa_model();
 };
 

@@ -265,8 +265,18 @@ mfa_model::~mfa_model() {
   cudaSetDevice(device);
   for (void *p : {(void *)d_pdf_off, (void *)d_tid2pdf, (void *)d_gconsts, (void *)d_miv, (void *)d_iv, (void *)d_weights, (void *)d_tile_pdf0,
                   (void *)d_tile_seg, (void *)d_W, (void *)d_G, (void *)d_gauss_row, d_tc_w, (void *)d_tc_colscale, (void *)d_acc, d_tc_rows, (void *)d_tc_g,
-                  (void *)d_first_tid, (void *)d_self_loop_tid, (void *)d_log_probs, (void *)d_tid_cost, (void *)d_tc_flag})
+                  (void *)d_first_tid, (void *)d_self_loop_tid, (void *)d_log_probs, (void *)d_tid_cost, (void *)d_tc_flag,
+                  (void *)sp_gconsts, (void *)sp_miv, (void *)sp_iv, (void *)sp_weights, (void *)sp_pdf_off, (void *)acc_spare})
     if (p) cudaFree(p);
+}
+
+int mfa_model::acc_take(size_t bytes) {
+  if (d_acc && acc_cap_bytes >= bytes) return MFA_OK;
+  if (!d_acc && acc_spare && acc_cap_bytes >= bytes) { d_acc = acc_spare; acc_spare = nullptr; return MFA_OK; }
+  for (double **p : {&d_acc, &acc_spare}) if (*p) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+  acc_cap_bytes = bytes + bytes / 4 + 4096;   // head room: the number of Gaussians moves by a few per cent per iteration
+  CUDA_TRY(cudaMalloc((void **)&d_acc, acc_cap_bytes));
+  return MFA_OK;
 }
 
 // greedy packing of whole pdfs into tiles of MFA_TILE_N Gaussian rows; every pdf's column range is padded to a multiple of

@@ -675,15 +675,21 @@ int build_tc_device(mfa_model *m, bool layout_changed) {
   if (!m->d_tc_flag) CUDA_TRY(cudaMalloc((void **)&m->d_tc_flag, 64 * sizeof(double) + 16));   // flag | m2[64]
   double *d_m2 = (double *)((uint8_t *)m->d_tc_flag + 16);
   CUDA_TRY(cudaMemsetAsync(m->d_tc_flag, 0, 64 * sizeof(double) + 16, s));
-  if ((size_t)G > m->tc_cap_gauss || geometry_changed || !m->d_tc_rows || (layout_changed && m->d_tc_w)) {
-    CUDA_TRY(cudaStreamSynchronize(s));
-    for (void **p : {&m->d_tc_rows, (void **)&m->d_tc_g, &m->d_tc_w}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
-    m->tc_cap_gauss = (size_t)G + (size_t)G / 8 + 64;
-  }
+  // capacity-based: a changed layout alone never re-allocates (cudaMalloc / cudaFree have a long latency tail on this platform)
   const size_t img_total = (size_t)nt * TILE_BYTES, aux_bytes = (size_t)nt * sizeof(TcAux);
+  if ((size_t)G > m->tc_cap_gauss || geometry_changed || !m->d_tc_rows) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (void **p : {&m->d_tc_rows, (void **)&m->d_tc_g}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+    m->tc_cap_gauss = (size_t)G + (size_t)G / 4 + 64;
+  }
+  if (img_total + aux_bytes > m->tc_w_cap || !m->d_tc_w) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (m->d_tc_w) { CUDA_TRY(cudaFree(m->d_tc_w)); m->d_tc_w = nullptr; }
+    m->tc_w_cap = (img_total + aux_bytes) + (img_total + aux_bytes) / 4 + 4096;
+  }
   if (!m->d_tc_rows) CUDA_TRY(cudaMalloc(&m->d_tc_rows, (size_t)2 * m->tc_cap_gauss * TK * sizeof(__half)));
   if (!m->d_tc_g) CUDA_TRY(cudaMalloc((void **)&m->d_tc_g, m->tc_cap_gauss * sizeof(float)));
-  if (!m->d_tc_w) CUDA_TRY(cudaMalloc(&m->d_tc_w, img_total + aux_bytes));
+  if (!m->d_tc_w) CUDA_TRY(cudaMalloc(&m->d_tc_w, m->tc_w_cap));
   m->tc_w_bytes = img_total;
   tc_moment_kernel<<<std::min(G, 4 * e->sm_count), 128, 0, s>>>(m->d_miv, m->d_iv, G, D, d_m2);
   tc_colscale_kernel<<<1, 64, 0, s>>>(d_m2, G, D, m->d_tc_colscale);

@@ -442,9 +442,17 @@ int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa
   uint8_t *flags = scr; double *state_occ = (double *)(scr + off_occ); int32_t *n_keep = (int32_t *)(scr + off_keep), *n_new = (int32_t *)(scr + off_new),
           *new_off = (int32_t *)(scr + off_off); MleScal *scal = (MleScal *)(scr + off_scal);
   CUDA_TRY(cudaMemsetAsync(scal, 0, sizeof(MleScal), s));
-  float *w_new = nullptr, *gc_new = nullptr, *miv_new = nullptr, *iv_new = nullptr;
-  CUDA_TRY(cudaMalloc((void **)&w_new, Gcap * 4)); CUDA_TRY(cudaMalloc((void **)&gc_new, Gcap * 4));
-  CUDA_TRY(cudaMalloc((void **)&miv_new, Gcap * D * 4)); CUDA_TRY(cudaMalloc((void **)&iv_new, Gcap * D * 4));
+  // the new parameters go into the spare set (allocated by capacity, kept across iterations), then the sets swap
+  if (m->sp_cap < Gcap || !m->sp_pdf_off) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (void **p : {(void **)&m->sp_weights, (void **)&m->sp_gconsts, (void **)&m->sp_miv, (void **)&m->sp_iv, (void **)&m->sp_pdf_off})
+      if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+    m->sp_cap = Gcap + Gcap / 8;
+    CUDA_TRY(cudaMalloc((void **)&m->sp_weights, m->sp_cap * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_gconsts, m->sp_cap * 4));
+    CUDA_TRY(cudaMalloc((void **)&m->sp_miv, m->sp_cap * D * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_iv, m->sp_cap * D * 4));
+    CUDA_TRY(cudaMalloc((void **)&m->sp_pdf_off, ((size_t)P + 1) * 4));
+  }
+  float *w_new = m->sp_weights, *gc_new = m->sp_gconsts, *miv_new = m->sp_miv, *iv_new = m->sp_iv;
   const double *occ = m->d_acc, *mean_acc = occ + G, *var_acc = mean_acc + (size_t)G * D, *trans = var_acc + (size_t)G * D, *tot = trans + (NT + 1);
   mle_pdf_kernel<<<(unsigned)((P + 7) / 8), 256, 0, s>>>(P, m->d_pdf_off, occ, o->min_gaussian_occupancy, o->min_gaussian_weight,
                                                           o->remove_low_count_gaussians, flags, state_occ, n_keep);
@@ -471,17 +479,21 @@ int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa
   CUDA_TRY(cudaMemcpyAsync(h_tot, tot, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   if (h.gauss_after <= 0 || (size_t)h.gauss_after > Gcap - 1 || h_off[P] != h.gauss_after) {
-    for (void *p : {(void *)w_new, (void *)gc_new, (void *)miv_new, (void *)iv_new}) cudaFree(p);
     return set_error(MFA_ERR_INVALID, "internal: M-step produced an inconsistent layout (" + std::to_string(h.gauss_after) + " Gaussians)");
   }
-  // swap the model over to the new arrays
-  int32_t *d_off_new;
-  CUDA_TRY(cudaMalloc((void **)&d_off_new, ((size_t)P + 1) * 4));
-  CUDA_TRY(cudaMemcpyAsync(d_off_new, new_off, ((size_t)P + 1) * 4, cudaMemcpyDeviceToDevice, s));
+  // swap the model over to the new arrays; the old ones become the spare set, the consumed accumulator block is kept for the next pass
+  CUDA_TRY(cudaMemcpyAsync(m->sp_pdf_off, new_off, ((size_t)P + 1) * 4, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  for (void *p : {(void *)m->d_pdf_off, (void *)m->d_gconsts, (void *)m->d_miv, (void *)m->d_iv, (void *)m->d_weights, (void *)m->d_acc})
-    if (p) CUDA_TRY(cudaFree(p));
-  m->d_pdf_off = d_off_new; m->d_gconsts = gc_new; m->d_miv = miv_new; m->d_iv = iv_new; m->d_weights = w_new; m->d_acc = nullptr;
+  {
+    const size_t old_cap = m->par_cap ? m->par_cap : (size_t)G;
+    std::swap(m->d_pdf_off, m->sp_pdf_off); std::swap(m->d_gconsts, m->sp_gconsts); std::swap(m->d_miv, m->sp_miv); std::swap(m->d_iv, m->sp_iv);
+    std::swap(m->d_weights, m->sp_weights);
+    m->par_cap = m->sp_cap; m->sp_cap = m->sp_weights ? old_cap : 0;
+    if (!m->sp_weights) {   // the model was created without weights: that spare array must exist next time
+      for (void **p : {(void **)&m->sp_gconsts, (void **)&m->sp_miv, (void **)&m->sp_iv, (void **)&m->sp_pdf_off}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+    }
+    m->acc_spare = m->d_acc; m->d_acc = nullptr;
+  }
   const bool layout_changed = h_off != m->h_pdf_off;
   m->h_pdf_off = std::move(h_off);
   m->num_gauss = h.gauss_after;
