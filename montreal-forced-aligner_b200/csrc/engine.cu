@@ -1,4 +1,5 @@
 // engine.cu -- engine lifetime, workspaces, acoustic-model upload/tiling, graph upload.
+#include <mutex>
 #include <algorithm>
 #include <cctype>
 #include <chrono>
@@ -420,16 +421,50 @@ extern "C" int mfa_model_boost_pdfs(mfa_model *m, float factor, const int32_t *p
 }
 
 // ------------------------------------------------------------------------------------------------ graphs
+namespace mfa {
+struct CachedBlock { int device; void *p; size_t cap; };
+static std::mutex g_cache_mu;
+static std::vector<CachedBlock> g_cache;
+static constexpr size_t kCacheBlocks = 6;
+void *dev_cache_take(int device, size_t bytes, size_t *cap) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  int best = -1;
+  for (int i = 0; i < (int)g_cache.size(); i++)
+    if (g_cache[i].device == device && g_cache[i].cap >= bytes && g_cache[i].cap <= 2 * bytes + (1 << 20) && (best < 0 || g_cache[i].cap < g_cache[best].cap)) best = i;
+  if (best < 0) return nullptr;
+  void *p = g_cache[best].p;
+  *cap = g_cache[best].cap;
+  g_cache.erase(g_cache.begin() + best);
+  return p;
+}
+void dev_cache_give(int device, void *p, size_t cap) {
+  if (!p) return;
+  void *victim = nullptr; int vdev = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.push_back({device, p, cap});
+    if (g_cache.size() > kCacheBlocks) {   // drop the smallest
+      int k = 0;
+      for (int i = 1; i < (int)g_cache.size(); i++) if (g_cache[i].cap < g_cache[k].cap) k = i;
+      victim = g_cache[k].p; vdev = g_cache[k].device;
+      g_cache.erase(g_cache.begin() + k);
+    }
+  }
+  if (victim) { cudaSetDevice(vdev); cudaFree(victim); }
+}
+}  // namespace mfa
+
 mfa_graphs::~mfa_graphs() {
-  if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
-  if (d_rag) { cudaSetDevice(device); cudaFree(d_rag); }
+  // no cudaFree (it synchronises the device and has a long latency tail): the blocks are parked for the next batch's graphs
+  if (d_blob) mfa::dev_cache_give(device, d_blob, d_blob_cap);
+  if (d_rag) mfa::dev_cache_give(device, d_rag, rag_meta_bytes);
 }
 
 namespace mfa {
 int upload_graphs(mfa_engine *e, mfa_graphs *g) {
   if (g->d_blob && g->device == e->device) return MFA_OK;
   if (g->host_w_stale) return set_error(MFA_ERR_UNSUPPORTED, "these graphs had their transition costs re-folded on another device; pack them again for this one");
-  if (g->d_blob) { cudaSetDevice(g->device); cudaFree(g->d_blob); g->d_blob = nullptr; CUDA_TRY(cudaSetDevice(e->device)); }
+  if (g->d_blob) { dev_cache_give(g->device, g->d_blob, g->d_blob_cap); g->d_blob = nullptr; }
   size_t A = g->a_src.size();
   const auto &barc = g->h_barc; const auto &pack = g->h_apack;   // built by mfa_graphs_pack on its worker threads
   if (barc.size() != 2 * A || pack.size() != A) return set_error(MFA_ERR_INVALID, "graphs object without device images");
@@ -451,7 +486,10 @@ int upload_graphs(mfa_engine *e, mfa_graphs *g) {
       {g->a_w0.data(), g->a_w0.size() * 4, (void **)&g->d_a_w0}};
   size_t total = 0;
   for (auto &it : items) total += (it.bytes + 255) / 256 * 256;
-  CUDA_TRY(cudaMalloc(&g->d_blob, std::max<size_t>(total, 256)));
+  const size_t want = std::max<size_t>(total, 256);
+  g->d_blob = dev_cache_take(e->device, want, &g->d_blob_cap);
+  if (g->d_blob) CUDA_TRY(cudaDeviceSynchronize());   // the block's previous user may still have kernels in flight
+  else { g->d_blob_cap = want + want / 8; CUDA_TRY(cudaMalloc(&g->d_blob, g->d_blob_cap)); }
   g->d_bytes = total; g->device = e->device;
   size_t off = 0;
   for (auto &it : items) {

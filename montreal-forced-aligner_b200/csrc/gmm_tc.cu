@@ -831,10 +831,12 @@ static int ensure_rag_plan(mfa_engine *e, mfa_model *m, mfa_graphs *g) {
   g->rag_tile_off.assign((size_t)nu + 1, 0);
   for (int u = 0; u < nu; u++) g->rag_tile_off[u + 1] = g->rag_tile_off[u] + h_cnt[u];
   const size_t n_aux = (size_t)g->rag_tile_off[nu];
-  if (g->d_rag && n_aux * sizeof(TcAux) > g->rag_meta_bytes) { CUDA_TRY(cudaFree(g->d_rag)); g->d_rag = nullptr; }
+  if (g->d_rag && n_aux * sizeof(TcAux) > g->rag_meta_bytes) { dev_cache_give(g->device >= 0 ? g->device : e->device, g->d_rag, g->rag_meta_bytes); g->d_rag = nullptr; }
   if (!g->d_rag) {
-    g->rag_meta_bytes = (n_aux + n_aux / 8 + 64) * sizeof(TcAux);
-    CUDA_TRY(cudaMalloc(&g->d_rag, g->rag_meta_bytes));
+    const size_t want = (n_aux + n_aux / 8 + 64) * sizeof(TcAux);
+    g->d_rag = dev_cache_take(e->device, want, &g->rag_meta_bytes);
+    if (g->d_rag) CUDA_TRY(cudaDeviceSynchronize());   // (a recycled block: its previous user may still have kernels in flight)
+    else { g->rag_meta_bytes = want; CUDA_TRY(cudaMalloc(&g->d_rag, g->rag_meta_bytes)); }
   }
   int64_t *d_toff;
   MFA_TRY(e->upload(DB_TILE_ROW0, g->rag_tile_off.data(), g->rag_tile_off.size(), &d_toff));

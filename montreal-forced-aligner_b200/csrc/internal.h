@@ -10,6 +10,11 @@
 
 namespace mfa {
 int set_error(int code, const std::string &msg);
+// Recycled device blocks for the per-batch graph mirrors (hundreds of MB each, one per new batch): cudaMalloc / cudaFree have a long
+// latency tail on this platform and cudaFree synchronises the device, so a destroyed graphs object parks its blocks here and the next
+// upload takes one that is large enough (after a device synchronisation: the previous user's kernels may still be running).
+void *dev_cache_take(int device, size_t bytes, size_t *cap);   // nullptr when nothing fits
+void dev_cache_give(int device, void *p, size_t cap);          // may cudaFree (the cache holds a few blocks per process)
 
 // std::vector whose resize() leaves trivially constructible elements uninitialised.  The per-batch graph arrays are hundreds of MB that
 // worker threads fill completely: a zero-filling resize touched every page on ONE thread first (180 ms of page faults per 10 h batch);
@@ -53,6 +58,7 @@ struct mfa_graphs {
   int device = -1;
   void *d_blob = nullptr;
   size_t d_bytes = 0;
+  size_t d_blob_cap = 0;          // bytes d_blob was allocated with (blocks are recycled through mfa::dev_cache_*)
   int64_t *d_st_off = nullptr, *d_arc_off = nullptr, *d_lp_off = nullptr, *d_inb_off = nullptr;
   int32_t *d_start = nullptr, *d_n_eps = nullptr, *d_in_begin = nullptr, *d_a_tid = nullptr, *d_a_olabel = nullptr, *d_lp2pdf = nullptr, *d_a_src = nullptr;
   uint32_t *d_a_pack = nullptr;  // dst (low 16) | lp (high 16, 0xFFFF = epsilon)

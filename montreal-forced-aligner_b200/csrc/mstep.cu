@@ -493,6 +493,15 @@ int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa
       for (void **p : {(void **)&m->sp_gconsts, (void **)&m->sp_miv, (void **)&m->sp_iv, (void **)&m->sp_pdf_off}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
     }
     m->acc_spare = m->d_acc; m->d_acc = nullptr;
+    if (m->sp_cap < m->par_cap) {
+      // the set that just became the spare is the model's original (exact-size) allocation: bring it to the same capacity NOW, so that
+      // all allocation of a training run happens inside its first M-step
+      for (void **p : {(void **)&m->sp_weights, (void **)&m->sp_gconsts, (void **)&m->sp_miv, (void **)&m->sp_iv}) if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+      m->sp_cap = m->par_cap;
+      CUDA_TRY(cudaMalloc((void **)&m->sp_weights, m->sp_cap * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_gconsts, m->sp_cap * 4));
+      CUDA_TRY(cudaMalloc((void **)&m->sp_miv, m->sp_cap * D * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_iv, m->sp_cap * D * 4));
+      if (!m->sp_pdf_off) CUDA_TRY(cudaMalloc((void **)&m->sp_pdf_off, ((size_t)P + 1) * 4));
+    }
   }
   const bool layout_changed = h_off != m->h_pdf_off;
   m->h_pdf_off = std::move(h_off);
