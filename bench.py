@@ -474,6 +474,7 @@ def train_loop(eng, sc, d_pcm, dev, stream, dist, args):
     graphs = E.Graphs(sc.batch, sc.tm, 1.0, 0.1)
     model.set_transitions(sc.tm)
     g0 = sc.am.NumGauss()
+    model.reserve(2 * g0 + 1)   # both parameter sets + the accumulator block for any M-step with mix-up target g0: no iteration allocates
     raw, _ = eng.mfcc(d_pcm, c.sample_off, mo)
     stats = eng.cmvn_stats(raw, fo, c.utt2spk, c.n_spk)
     eng.sync()

@@ -179,6 +179,10 @@ typedef struct {
   int32_t layout_changed;           /* 1: some pdf's component count changed (per-utterance K2 tile plans are rebuilt on next use) */
 } mfa_mle_result;
 MFA_API int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa_mle_result *res);
+/* Training loops: allocate everything the M-step and the accumulators will need for models of up to `max_gauss` Gaussians NOW (both
+ * parameter sets the M-step swaps between, the accumulator block), so that no iteration calls cudaMalloc / cudaFree -- on some
+ * platforms those calls take tens to hundreds of milliseconds.  max_gauss >= current Gaussians + mix-up target + 1 covers any update. */
+MFA_API int mfa_model_reserve(mfa_engine *e, mfa_model *m, int64_t max_gauss);
 MFA_API int mfa_model_num_gauss(const mfa_model *m);
 /* device -> host copy of the current parameters (any pointer may be NULL): pdf_off[num_pdfs+1], weights / gconsts [num_gauss],
  * means_invvars / inv_vars [num_gauss][dim], log_probs[num_tids+1] -- what write_gmm_model needs ({it}.mdl, acoustic_modeling/base.py). */

@@ -93,7 +93,7 @@ SYMBOLS = [
     "mfa_last_error", "mfa_abi_version", "mfa_engine_create", "mfa_engine_destroy", "mfa_engine_sync", "mfa_engine_stream",
     "mfa_engine_sm_count", "mfa_engine_set_option", "mfa_engine_get_option", "mfa_engine_launch_count", "mfa_engine_band_fallbacks", "mfa_engine_gmm_timing", "mfa_engine_gmm_flops", "mfa_engine_gmm_issued_flops", "mfa_engine_stage_timing", "mfa_mfcc_num_frames", "mfa_mfcc",
     "mfa_cmvn_stats", "mfa_cmvn_apply", "mfa_feat_out_dim", "mfa_features", "mfa_model_create", "mfa_model_destroy",
-    "mfa_model_boost_pdfs", "mfa_model_set_transitions", "mfa_model_mle_update", "mfa_model_num_gauss", "mfa_model_read",
+    "mfa_model_boost_pdfs", "mfa_model_set_transitions", "mfa_model_mle_update", "mfa_model_reserve", "mfa_model_num_gauss", "mfa_model_read",
     "mfa_graphs_set_transitions", "mfa_gmm_loglikes", "mfa_graph_compiler_create", "mfa_graph_compiler_destroy", "mfa_graph_compile",
     "mfa_fst_batch_create", "mfa_fst_batch_destroy", "mfa_fst_body_scan", "mfa_fst_body_fill", "mfa_fst_batch_sizes", "mfa_fst_batch_export", "mfa_graphs_pack",
     "mfa_graphs_destroy", "mfa_graphs_max_words", "mfa_graphs_offsets", "mfa_graphs_band_view", "mfa_align", "mfa_align_feats", "mfa_align_pcm", "mfa_acc_size", "mfa_acc_zero", "mfa_acc_stats",

@@ -423,6 +423,43 @@ int mfa_model_set_transitions(mfa_model *m, const mfa_trans_desc *d) {
   return MFA_OK;
 }
 
+int mfa_model_reserve(mfa_engine *e, mfa_model *m, int64_t max_gauss) {
+  if (!e || !m || max_gauss < m->num_gauss) return set_error(MFA_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CallScope scope(e);
+  cudaStream_t s = e->stream;
+  const size_t cap = (size_t)max_gauss + (size_t)max_gauss / 8, D = (size_t)m->dim, P = (size_t)m->num_pdfs, G = (size_t)m->num_gauss;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (m->sp_cap < cap || !m->sp_pdf_off) {
+    for (void **p : {(void **)&m->sp_weights, (void **)&m->sp_gconsts, (void **)&m->sp_miv, (void **)&m->sp_iv, (void **)&m->sp_pdf_off})
+      if (*p) { CUDA_TRY(cudaFree(*p)); *p = nullptr; }
+    m->sp_cap = cap;
+    CUDA_TRY(cudaMalloc((void **)&m->sp_weights, cap * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_gconsts, cap * 4));
+    CUDA_TRY(cudaMalloc((void **)&m->sp_miv, cap * D * 4)); CUDA_TRY(cudaMalloc((void **)&m->sp_iv, cap * D * 4));
+    CUDA_TRY(cudaMalloc((void **)&m->sp_pdf_off, (P + 1) * 4));
+  }
+  if ((m->par_cap ? m->par_cap : G) < cap && m->d_weights) {
+    // the current arrays move into new ones of the same capacity (after the first swap they become the spare set)
+    float *w, *gc, *miv, *iv;
+    CUDA_TRY(cudaMalloc((void **)&w, cap * 4)); CUDA_TRY(cudaMalloc((void **)&gc, cap * 4));
+    CUDA_TRY(cudaMalloc((void **)&miv, cap * D * 4)); CUDA_TRY(cudaMalloc((void **)&iv, cap * D * 4));
+    CUDA_TRY(cudaMemcpyAsync(w, m->d_weights, G * 4, cudaMemcpyDeviceToDevice, s)); CUDA_TRY(cudaMemcpyAsync(gc, m->d_gconsts, G * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(miv, m->d_miv, G * D * 4, cudaMemcpyDeviceToDevice, s)); CUDA_TRY(cudaMemcpyAsync(iv, m->d_iv, G * D * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (void *p : {(void *)m->d_weights, (void *)m->d_gconsts, (void *)m->d_miv, (void *)m->d_iv}) CUDA_TRY(cudaFree(p));
+    m->d_weights = w; m->d_gconsts = gc; m->d_miv = miv; m->d_iv = iv; m->par_cap = cap;
+  }
+  // accumulator block for `cap` Gaussians
+  const size_t acc_bytes = (cap * (1 + 2 * D) + (size_t)m->num_tids + 1 + 2) * sizeof(double);
+  const bool had = m->d_acc != nullptr;
+  if (!had || m->acc_cap_bytes < acc_bytes) {
+    if (had) return MFA_OK;   // live accumulators: leave them alone, the next mfa_acc_zero after the M-step sizes the block
+    MFA_TRY(m->acc_take(acc_bytes));
+    m->acc_spare = m->d_acc; m->d_acc = nullptr;
+  }
+  return MFA_OK;
+}
+
 int mfa_model_mle_update(mfa_engine *e, mfa_model *m, const mfa_mle_opts *o, mfa_mle_result *res) {
   if (!e || !m || !o) return set_error(MFA_ERR_INVALID, "null argument");
   if (!m->d_acc) return set_error(MFA_ERR_INVALID, "no accumulators: run mfa_acc_zero / mfa_acc_stats first");

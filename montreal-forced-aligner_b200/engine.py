@@ -340,6 +340,11 @@ class DeviceModel:
         self.num_gauss = int(r.num_gauss_after)
         return {k: getattr(r, k) for k, _ in L.MleResult._fields_}
 
+    def reserve(self, max_gauss: int):
+        """mfa_model_reserve: allocate now what M-steps and accumulators need for up to `max_gauss` Gaussians (training loops: pass current
+        Gaussians + mix-up target + 1), so that no iteration allocates device memory."""
+        L.check(L.lib().mfa_model_reserve(self.engine._h, self._h, C.c_int64(int(max_gauss))))
+
     def read(self, with_transitions: bool = False):
         """mfa_model_read: host AmDiagGmm of the current device parameters (+ the transition log-probabilities)."""
         G, D = int(L.lib().mfa_model_num_gauss(self._h)), self.dim

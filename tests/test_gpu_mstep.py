@@ -202,3 +202,31 @@ def test_host_accumulator_entry_point_runs_on_the_device(eng):
     tm3 = copy.deepcopy(tm)
     tm3.mle_update(trans.copy())
     assert np.allclose(tm2.log_probs[1:], tm3.log_probs[1:], rtol=1e-6, atol=1e-7)
+
+
+def test_reserved_capacity_changes_nothing_but_the_allocations(eng):
+    """mfa_model_reserve (training loops call it once so that no iteration allocates device memory): two EM iterations with and without
+    the reservation end in bit-identical models."""
+    sc = build_synth_scenario(seconds=60.0, seed=17, triphone=True, n_phones=10, n_words=50, target_pdfs=100, gauss_per_pdf=3)
+    tm, am, c = sc["tm"], sc["am"], sc["corpus"]
+    batch = E.GraphCompiler(tm, sc["tree"], c.lexicon).compile(c.transcripts)
+    feats = np.concatenate(sc["feats"]).astype(np.float32)
+    finals = []
+    for reserve in (False, True):
+        graphs = E.Graphs(batch, tm, 1.0, 0.1)
+        dm = E.DeviceModel(eng, tm, am)
+        if reserve:
+            dm.reserve(2 * am.NumGauss() + 1)
+            with pytest.raises(Exception):
+                dm.reserve(am.NumGauss() - 1)          # below the current size: refused
+        for it in range(2):
+            res = E.align_feats(eng, dm, graphs, feats, sc["frame_off"], E.align_opts())
+            dm.acc_zero()
+            dm.acc_stats(feats, res.ali)
+            dm.mle_update(mixup=am.NumGauss(), update_transitions=True, seed=7 + it)
+            graphs.set_transitions(eng, dm, 1.0, 0.1)
+        finals.append(dm.read(with_transitions=True))
+        dm.close(); graphs.close()
+    (a, lpa), (b, lpb) = finals
+    assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.weights, b.weights) and np.array_equal(a.means_invvars, b.means_invvars)
+    assert np.array_equal(a.inv_vars, b.inv_vars) and np.array_equal(lpa, lpb)
