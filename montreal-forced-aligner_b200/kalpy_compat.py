@@ -21,22 +21,52 @@ from ._lib import MfaError
 from .gmm_update import AccumAmDiagGmm, mle_update
 from .lexicon import Lexicon
 
-_engines: Dict[tuple, E.Engine] = {}
+_engines: Dict[int, E.Engine] = {}            # every engine this module created, by id (introspection / tests)
+_idle: Dict[int, List[E.Engine]] = {}         # per device: engines whose thread has ended, waiting for the next thread
 _engines_lock = threading.Lock()
+_tls = threading.local()
+
+
+class _Lease:
+    """Ties an engine to the thread that holds this object in its thread-local storage; when the thread ends the storage is dropped, the
+    lease is collected and the engine goes back to the idle list instead of being destroyed (an engine owns pinned staging buffers and
+    device work space: creating one per short-lived job thread would cost more than the jobs)."""
+
+    def __init__(self, device: int, eng: E.Engine):
+        self.device, self.eng = device, eng
+
+    def __del__(self):
+        try:
+            with _engines_lock:
+                _idle.setdefault(self.device, []).append(self.eng)
+        except Exception:   # interpreter shutdown
+            pass
 
 
 def get_engine(device: Optional[int] = None) -> E.Engine:
     """One engine per device and per host THREAD.  MFA runs one aligner / accumulator per job and, with USE_THREADING, several jobs as
     threads of one process (native code must be re-entrant): an engine owns one main stream and its scratch buffers and is not
-    re-entrant, so every job thread gets its own; the objects of this module remember the engine they were built with.  Jobs map to GPUs via
-    LOCAL_RANK / MFA_B200_DEVICE.  Engines of finished threads stay cached (thread ids are recycled) until the process ends."""
+    re-entrant, so every job thread gets its own; the objects of this module remember the engine they were built with.  Engines of ended
+    threads are handed to the next new thread (a stage's thread pool comes and goes with the stage).  Jobs map to GPUs via LOCAL_RANK /
+    MFA_B200_DEVICE."""
     if device is None:
         device = int(os.environ.get("MFA_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-    key = (device, threading.get_ident())
+    leases = getattr(_tls, "leases", None)
+    if leases is None:
+        leases = _tls.leases = {}
+    lease = leases.get(device)
+    if lease is not None:
+        return lease.eng
     with _engines_lock:
-        eng = _engines.get(key)
-        if eng is None:
-            eng = _engines[key] = E.Engine(device)
+        pool = _idle.get(device)
+        eng = pool.pop() if pool else None
+    if eng is None:
+        eng = E.Engine(device)
+        with _engines_lock:
+            _engines[id(eng)] = eng
+    else:
+        eng.sync()   # whatever its previous thread left in flight
+    leases[device] = _Lease(device, eng)
     return eng
 
 

@@ -447,4 +447,4 @@ def test_jobs_as_threads_equal_jobs_in_sequence(tmp_path):
     assert outs["seq"][1].keys() == outs["thr"][1].keys() and len(outs["seq"][1]) == 20
     for k in outs["seq"][1]:
         assert outs["seq"][1][k] == outs["thr"][1][k], k
-    assert len({id(e) for e in KC._engines.values()}) >= 2     # the worker threads really had their own engines
+    assert 2 <= len(KC._engines) <= 8     # the worker threads had their own engines, and the four stages' thread pools shared them
