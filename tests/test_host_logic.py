@@ -204,3 +204,25 @@ def test_mle_update_keeps_the_last_gaussian_of_a_starved_pdf():
     assert new.offsets[pdf + 1] - new.offsets[pdf] == 1
     k = int(new.offsets[pdf])
     assert np.allclose(new.means()[k], am.means()[b - 1], rtol=1e-5)    # Kaldi keeps the LAST index, un-updated
+
+
+def test_bench_reference_arm_contract_without_cuda_library():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON line with the contract's keys, the oracle
+    as the thing measured, and libmfa_b200.so never mapped into the process."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--hours", "0.01"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0 and d["cuda_library_loaded"] is False
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["oracle_build"] in ("avx2", "generic")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and d["vs_baseline"] is None
